@@ -1,0 +1,175 @@
+/*
+ * moonb200.h - C ABI of libmoonb200.so, the B200-native replacement for the
+ * data-parallel hot path of MoonRTX (albireo77/moonrtx).
+ *
+ * The reference has no FFI of its own: its boundary is the Python object
+ * `self.rt` (plotoptix.TkOptiX, created at moonrtx/moon_renderer.py:571-575) and
+ * three free functions of moonrtx/data_loader.py.  Each entry point below names
+ * the reference call(s) it serves.  The Python side (moonrtx_b200/) binds these
+ * with ctypes only; there are no torch types, no callbacks and no C++ types in
+ * any signature.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; mrtx_last_error() returns
+ *     the message of the last failing call on the calling thread;
+ *   - pointers are HOST pointers unless the parameter name ends in `_dev`;
+ *   - one context per GPU; a context is not thread-safe (the Python drop-in
+ *     serialises calls with its `_padlock`, like PlotOptiX);
+ *   - all work of a context is issued on the context's stream
+ *     (mrtx_set_stream / mrtx_get_stream); functions that return data to host
+ *     memory synchronise that stream before returning, all others are asynchronous;
+ *   - images are row-major, row 0 = top of the frame.
+ */
+#ifndef MOONB200_H
+#define MOONB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRTX_ABI_VERSION 1
+
+typedef struct mrtx_ctx mrtx_ctx;
+
+enum {
+    MRTX_OK = 0,
+    MRTX_ERR_INVALID = -1,      /* bad argument (ValueError on the Python side)            */
+    MRTX_ERR_CUDA = -2,         /* CUDA runtime failure                                    */
+    MRTX_ERR_STATE = -3,        /* call out of order (e.g. render before set_displacement) */
+    MRTX_ERR_NCCL = -4
+};
+
+/* ---- library / context ------------------------------------------------------ */
+int         mrtx_abi_version(void);
+const char* mrtx_last_error(void);
+int  mrtx_device_count(int* count);
+/* TkOptiX(...) constructor, moon_renderer.py:571: one context per GPU.              */
+int  mrtx_create(int device, mrtx_ctx** out_ctx);
+/* rt.close(), moon_renderer.py:883                                                   */
+int  mrtx_destroy(mrtx_ctx* ctx);
+int  mrtx_synchronize(mrtx_ctx* ctx);
+/* Issue the context's work on a caller-owned cudaStream_t (e.g. torch's current
+ * stream, so torch.cuda.Event brackets it).  NULL restores the context's own.       */
+int  mrtx_set_stream(mrtx_ctx* ctx, void* cuda_stream);
+int  mrtx_get_stream(mrtx_ctx* ctx, void** cuda_stream);
+int  mrtx_device_props(mrtx_ctx* ctx, int* sm_count, int* l2_bytes, size_t* hbm_bytes);
+
+/* CUDA-event stopwatch on the context's stream (bench.py times kernels with it).    */
+int  mrtx_timer_start(mrtx_ctx* ctx);
+int  mrtx_timer_stop(mrtx_ctx* ctx, float* elapsed_ms);   /* synchronises the stop event */
+
+/* ---- raw device / pinned memory (so the host side needs no torch) ------------- */
+int  mrtx_dev_alloc(mrtx_ctx* ctx, size_t bytes, void** out_dev);
+int  mrtx_dev_free(mrtx_ctx* ctx, void* ptr_dev);
+int  mrtx_host_alloc(size_t bytes, void** out_pinned);
+int  mrtx_host_free(void* pinned);
+int  mrtx_h2d(mrtx_ctx* ctx, void* dst_dev, const void* src, size_t bytes);   /* async  */
+int  mrtx_d2h(mrtx_ctx* ctx, void* dst, const void* src_dev, size_t bytes);   /* syncs  */
+int  mrtx_l2_flush(mrtx_ctx* ctx);   /* overwrite a scratch buffer larger than L2 (bench hygiene) */
+
+/* ---- data_loader hot path ------------------------------------------------------
+ * load_elevation_data, moonrtx/data_loader.py:215-242 (array part: int16 block mean
+ * in numpy's two-stage float32 order, *scale, +1, /max).  W, H = source size; both
+ * must be divisible by ds (else MRTX_ERR_INVALID, the reference's reshape ValueError).
+ * out = float32 [H/ds][W/ds]; *radius_scale = the float32 maximum before division.
+ * Bit-exact against the reference for every ds >= 1.                                 */
+int  mrtx_downscale_i16(mrtx_ctx* ctx, const int16_t* src, int W, int H, int ds,
+                        float* out, float* radius_scale);
+int  mrtx_downscale_i16_dev(mrtx_ctx* ctx, const int16_t* src_dev, int W, int H, int ds,
+                            float* out_dev, float* radius_scale /* host, may be NULL */);
+
+/* load_color_data, moonrtx/data_loader.py:331 (cv2 IMREAD_REDUCED_COLOR_k of a TIFF =
+ * round-half-up mean of the central 2x2 of each k x k block) followed by
+ * _moon_texture, :345-368 (256-entry LUT, BGR -> RGBA, alpha 255).
+ * bgr = uint8 [H][W][3]; k in {1,2,4,8}; W, H divisible by k; out = uint8 [H/k][W/k][4]. */
+int  mrtx_color_reduce_lut(mrtx_ctx* ctx, const uint8_t* bgr, int W, int H, int k,
+                           const uint8_t lut[256], uint8_t* out_rgba);
+int  mrtx_color_reduce_lut_dev(mrtx_ctx* ctx, const uint8_t* bgr_dev, int W, int H, int k,
+                               const uint8_t lut[256], uint8_t* out_rgba_dev);
+
+/* Synthetic LOLA-shaped inputs generated in HBM (bench/test data; the real 9 GB
+ * LDEM cannot be downloaded offline).                                                 */
+int  mrtx_synth_ldem_i16_dev(mrtx_ctx* ctx, int16_t* out_dev, int W, int H, uint32_t seed);
+int  mrtx_synth_color_bgr_dev(mrtx_ctx* ctx, uint8_t* out_dev, int W, int H, uint32_t seed);
+
+/* ---- scene (the rt.* calls of moon_renderer.py:570-650, 852-860) ----------------- */
+/* rt.set_displacement("moon", float32[h][w]), moon_renderer.py:624.  Copies the map to
+ * the device and builds the max-height pyramid.                                       */
+int  mrtx_set_displacement_f32(mrtx_ctx* ctx, const float* map, int W, int H);
+int  mrtx_set_displacement_f32_dev(mrtx_ctx* ctx, const float* map_dev, int W, int H, int copy);
+/* Same surface from the raw LDEM counts: D = fl32(fl32(fl32(c*scale)+1)/radius_scale),
+ * i.e. exactly the float32 map the reference would hold at downscale 1, at half the
+ * memory (8.5 GB instead of 17 GB for 92160x46080).                                   */
+int  mrtx_set_displacement_i16(mrtx_ctx* ctx, const int16_t* map, int W, int H,
+                               float scale, float radius_scale);
+int  mrtx_set_displacement_i16_dev(mrtx_ctx* ctx, const int16_t* map_dev, int W, int H,
+                                   float scale, float radius_scale, int copy);
+/* rt.set_texture_2d("moon_color" | "frame_overlay", uint8[h][w][4]),
+ * moon_renderer.py:614, renderer_video.py:137.  slot 0 = moon_color (bilinear),
+ * slot 1 = frame_overlay (nearest, must match the frame size); NULL clears.           */
+int  mrtx_set_texture_rgba8(mrtx_ctx* ctx, int slot, const uint8_t* rgba, int W, int H);
+/* rt.set_data/update_data("moon", pos, u, v, r), moon_renderer.py:620-621, 854:
+ * u = scene direction of the body +Z (north pole), v = scene direction of lon 0.      */
+int  mrtx_set_frame(mrtx_ctx* ctx, const double pos[3], const double u[3], const double v[3],
+                    double radius);
+/* rt.setup_camera / update_camera (Pinhole), moon_renderer.py:627-635, 568; fov is the
+ * vertical field of view in degrees.                                                  */
+int  mrtx_set_camera(mrtx_ctx* ctx, const double eye[3], const double target[3],
+                     const double up[3], double fov_deg);
+/* rt.setup_light / update_light("sun", color=, pos=, radius=), moon_renderer.py:640, 860.
+ * radiance = the light "color" (brightness * SUN_BRIGHTNESS_SCALE).                    */
+int  mrtx_set_light(mrtx_ctx* ctx, const double pos[3], double radius, double radiance);
+/* rt.set_float: scene_epsilon, tonemap_exposure, tonemap_gamma (marching_step,
+ * marching_step_eps are accepted and ignored: intersection here is exact).
+ * rt.set_uint: path_seg_range (accepted; direct light only), jitter, shadows.         */
+int  mrtx_set_float(mrtx_ctx* ctx, const char* name, double value);
+int  mrtx_set_uint(mrtx_ctx* ctx, const char* name, unsigned a, unsigned b);
+/* frame size (TkOptiX(width=, height=)); reallocates accumulation / hit / output.     */
+int  mrtx_resize(mrtx_ctx* ctx, int width, int height);
+
+/* ---- render ------------------------------------------------------------------------
+ * One launch of the path tracer over the pixel rectangle [x0,x1) x [y0,y1): samples
+ * sample0 .. sample0+nsamples-1 of every pixel (primary ray, sun shadow ray, Lambert
+ * shading) are ADDED to the float4 accumulation buffer; reset != 0 clears it first.
+ * Sample s of pixel p uses a counter-based RNG keyed on (p, s); with jitter off every
+ * sample is the pixel centre and the light centre.                                    */
+int  mrtx_render(mrtx_ctx* ctx, int x0, int y0, int x1, int y1,
+                 unsigned sample0, unsigned nsamples, int reset);
+/* Gamma + Overlay post-processing (moon_renderer.py:597-600, renderer_video.py:137-144):
+ * rgba8 = overlay over (exposure * accum / weight)^(1/gamma).                          */
+int  mrtx_resolve(mrtx_ctx* ctx);
+int  mrtx_read_rgba8(mrtx_ctx* ctx, uint8_t* out);          /* [H][W][4]                */
+int  mrtx_read_accum_f32(mrtx_ctx* ctx, float* out);        /* [H][W][4] sum r,g,b,count */
+int  mrtx_read_hit_f32(mrtx_ctx* ctx, float* out);          /* [H][W][4] x,y,z,dist      */
+/* rt._get_hit_at(x, y) -> (hx, hy, hz, hd), moon_renderer.py:1138; hd <= 0 = miss.     */
+int  mrtx_hit_at(mrtx_ctx* ctx, int x, int y, float out4[4]);
+/* device views of the frame buffers (for collectives and zero-copy consumers)        */
+int  mrtx_frame_buffers_dev(mrtx_ctx* ctx, void** accum_dev, void** rgba8_dev, void** hit_dev);
+/* Per-sample first-hit record of the last mrtx_render with nsamples == 1 and
+ * debug_hits on: float64 [H][W][4] = (s_hit, radius, lon, lat) for parity tests.      */
+int  mrtx_read_hit_f64(mrtx_ctx* ctx, double* out);
+
+/* counters since the last reset: [0] primary rays, [1] primary rays entering the
+ * bounding sphere, [2] primary hits, [3] shadow rays, [4] shadow rays occluded,
+ * [5] pyramid node visits, [6] exact patch tests, [7] reserved                         */
+int  mrtx_counters(mrtx_ctx* ctx, uint64_t out[8], int reset);
+
+/* ---- multi-GPU (one process per GPU) ----------------------------------------------
+ * NCCL is loaded at run time from `libnccl_path` (the torch-bundled libnccl.so.2).     */
+int  mrtx_comm_unique_id(const char* libnccl_path, uint8_t id128[128]);
+int  mrtx_comm_init(mrtx_ctx* ctx, const char* libnccl_path, int nranks, int rank,
+                    const uint8_t id128[128]);
+int  mrtx_comm_destroy(mrtx_ctx* ctx);
+/* progressive-sample split: sum the float4 accumulation buffers of all ranks          */
+int  mrtx_allreduce_accum(mrtx_ctx* ctx);
+/* screen-tile split: rank r rendered the rows y with (y / tile_rows) % nranks == r;
+ * gather every rank's rows of the resolved RGBA8 frame into every rank's frame.       */
+int  mrtx_allgather_rows(mrtx_ctx* ctx, int tile_rows);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOONB200_H */

@@ -1,0 +1,529 @@
+// C ABI of libmoonb200.so: context lifetime, memory, timers, data_loader entry points,
+// scene setters and frame read-back.  Kernels live in their own translation units.
+
+#include "common.cuh"
+
+#include <stdarg.h>
+#include <stdlib.h>
+
+// ---- errors ------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void mrtx_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" {
+
+int mrtx_abi_version(void) { return MRTX_ABI_VERSION; }
+const char* mrtx_last_error(void) { return g_err; }
+
+int mrtx_device_count(int* count) {
+    MRTX_REQUIRE(count, "null argument");
+    MRTX_CUDA(cudaGetDeviceCount(count));
+    return MRTX_OK;
+}
+
+// ---- context -------------------------------------------------------------------------
+int mrtx_create(int device, mrtx_ctx** out_ctx) {
+    MRTX_REQUIRE(out_ctx, "null argument");
+    *out_ctx = nullptr;
+    int n = 0;
+    MRTX_CUDA(cudaGetDeviceCount(&n));
+    MRTX_REQUIRE(device >= 0 && device < n, "device %d out of range (%d visible)", device, n);
+    MRTX_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    MRTX_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        // no fallback path exists: the kernels use sm_100-only instructions
+        mrtx_set_error("device %d is sm_%d%d; libmoonb200 is built for sm_100a (B200) only",
+                       device, prop.major, prop.minor);
+        return MRTX_ERR_STATE;
+    }
+    mrtx_ctx* c = (mrtx_ctx*)calloc(1, sizeof(mrtx_ctx));
+    MRTX_REQUIRE(c, "out of host memory");
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->l2_bytes = prop.l2CacheSize;
+    c->hbm_bytes = prop.totalGlobalMem;
+    MRTX_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    MRTX_CUDA(cudaEventCreate(&c->ev0));
+    MRTX_CUDA(cudaEventCreate(&c->ev1));
+    MRTX_CUDA(cudaMalloc(&c->d_max_bits, sizeof(unsigned)));
+    MRTX_CUDA(cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long)));
+    MRTX_CUDA(cudaMemset(c->d_counters, 0, 8 * sizeof(unsigned long long)));
+    // scene defaults = the reference's (moon_renderer.py:37, 85-101, 597-599, 620-621)
+    SceneParams& sp = c->sp;
+    sp.radius = 10.0;
+    const double u[3] = {0, 0, 1}, v[3] = {0, -1, 0}, pos[3] = {0, 0, 0};
+    mrtx_set_frame(c, pos, u, v, 10.0);
+    sp.light_pos[0] = 21460.0; sp.light_radius = 100.0; sp.light_radiance = 80.0 * 460.5316;
+    sp.scene_epsilon = 1.0e-4;
+    sp.exposure = 0.9f; sp.inv_gamma = 1.0f / 2.2f;
+    sp.jitter = 0; sp.shadows = 1; sp.debug_hits = 0;
+    const double eye[3] = {0, -300, 0}, tgt[3] = {0, 0, 0}, up[3] = {0, 0, 1};
+    mrtx_set_camera(c, eye, tgt, up, 4.242192793);
+    *out_ctx = c;
+    return MRTX_OK;
+}
+
+static void free_frame(mrtx_ctx* c) {
+    cudaFree(c->accum); cudaFree(c->rgba8); cudaFree(c->hit); cudaFree(c->hit64);
+    c->accum = nullptr; c->rgba8 = nullptr; c->hit = nullptr; c->hit64 = nullptr;
+}
+
+int mrtx_destroy(mrtx_ctx* ctx) {
+    if (!ctx) return MRTX_OK;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    mrtx_comm_destroy(ctx);
+    free_heightfield(ctx);
+    for (int s = 0; s < 2; ++s) cudaFree(ctx->tex_owned[s]);
+    free_frame(ctx);
+    cudaFree(ctx->d_max_bits);
+    cudaFree(ctx->d_counters);
+    cudaFree(ctx->flush_buf);
+    cudaFree(ctx->gather_buf);
+    cudaEventDestroy(ctx->ev0);
+    cudaEventDestroy(ctx->ev1);
+    cudaStreamDestroy(ctx->own_stream);
+    free(ctx);
+    return MRTX_OK;
+}
+
+int mrtx_synchronize(mrtx_ctx* ctx) {
+    MRTX_CTX(ctx);
+    MRTX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return MRTX_OK;
+}
+
+int mrtx_set_stream(mrtx_ctx* ctx, void* cuda_stream) {
+    MRTX_CTX(ctx);
+    MRTX_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return MRTX_OK;
+}
+
+int mrtx_get_stream(mrtx_ctx* ctx, void** cuda_stream) {
+    MRTX_CTX(ctx);
+    MRTX_REQUIRE(cuda_stream, "null argument");
+    *cuda_stream = (void*)ctx->stream;
+    return MRTX_OK;
+}
+
+int mrtx_device_props(mrtx_ctx* ctx, int* sm_count, int* l2_bytes, size_t* hbm_bytes) {
+    MRTX_CTX(ctx);
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (l2_bytes) *l2_bytes = ctx->l2_bytes;
+    if (hbm_bytes) *hbm_bytes = ctx->hbm_bytes;
+    return MRTX_OK;
+}
+
+int mrtx_timer_start(mrtx_ctx* ctx) {
+    MRTX_CTX(ctx);
+    MRTX_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    return MRTX_OK;
+}
+
+int mrtx_timer_stop(mrtx_ctx* ctx, float* elapsed_ms) {
+    MRTX_CTX(ctx);
+    MRTX_REQUIRE(elapsed_ms, "null argument");
+    MRTX_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    MRTX_CUDA(cudaEventSynchronize(ctx->ev1));
+    MRTX_CUDA(cudaEventElapsedTime(elapsed_ms, ctx->ev0, ctx->ev1));
+    return MRTX_OK;
+}
+
+// ---- memory ------------------------------------------------------------------------
+int mrtx_dev_alloc(mrtx_ctx* ctx, size_t bytes, void** out_dev) {
+    MRTX_CTX(ctx);
+    MRTX_REQUIRE(out_dev, "null argument");
+    MRTX_CUDA(cudaMalloc(out_dev, bytes ? bytes : 1));
+    return MRTX_OK;
+}
+int mrtx_dev_free(mrtx_ctx* ctx, void* ptr_dev) {
+    MRTX_CTX(ctx);
+    MRTX_CUDA(cudaStreamSynchronize(ctx->stream));
+    MRTX_CUDA(cudaFree(ptr_dev));
+    return MRTX_OK;
+}
+int mrtx_host_alloc(size_t bytes, void** out_pinned) {
+    MRTX_REQUIRE(out_pinned, "null argument");
+    MRTX_CUDA(cudaMallocHost(out_pinned, bytes ? bytes : 1));
+    return MRTX_OK;
+}
+int mrtx_host_free(void* pinned) {
+    MRTX_CUDA(cudaFreeHost(pinned));
+    return MRTX_OK;
+}
+int mrtx_h2d(mrtx_ctx* ctx, void* dst_dev, const void* src, size_t bytes) {
+    MRTX_CTX(ctx);
+    MRTX_CUDA(cudaMemcpyAsync(dst_dev, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return MRTX_OK;
+}
+int mrtx_d2h(mrtx_ctx* ctx, void* dst, const void* src_dev, size_t bytes) {
+    MRTX_CTX(ctx);
+    MRTX_CUDA(cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    MRTX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return MRTX_OK;
+}
+int mrtx_l2_flush(mrtx_ctx* ctx) {
+    MRTX_CTX(ctx);
+    const size_t want = (size_t)ctx->l2_bytes * 2 + (64u << 20);
+    if (ctx->flush_bytes < want) {
+        cudaFree(ctx->flush_buf);
+        ctx->flush_buf = nullptr; ctx->flush_bytes = 0;
+        MRTX_CUDA(cudaMalloc(&ctx->flush_buf, want));
+        ctx->flush_bytes = want;
+    }
+    MRTX_CUDA(cudaMemsetAsync(ctx->flush_buf, 0x5a, ctx->flush_bytes, ctx->stream));
+    return MRTX_OK;
+}
+
+// ---- data_loader ---------------------------------------------------------------------
+static int check_downscale_args(const void* src, int W, int H, int ds, const void* out) {
+    MRTX_REQUIRE(src && out, "null buffer");
+    MRTX_REQUIRE(W > 0 && H > 0, "bad map size %d x %d", W, H);
+    MRTX_REQUIRE(ds >= 1 && ds <= 512, "downscale %d outside 1..512 (row sums must stay exact in float32)", ds);
+    // numpy's reshape(1, h, ds, w, ds) raises ValueError here (data_loader.py:225)
+    MRTX_REQUIRE(W % ds == 0 && H % ds == 0,
+                 "cannot reshape array of size %lld into shape (1,%d,%d,%d,%d)",
+                 (long long)W * H, H / ds, ds, W / ds, ds);
+    return MRTX_OK;
+}
+
+int mrtx_downscale_i16_dev(mrtx_ctx* ctx, const int16_t* src_dev, int W, int H, int ds,
+                           float* out_dev, float* radius_scale) {
+    MRTX_CTX(ctx);
+    int rc = check_downscale_args(src_dev, W, H, ds, out_dev);
+    if (rc) return rc;
+    rc = launch_downscale_i16(ctx, src_dev, W, H, ds, out_dev);
+    if (rc) return rc;
+    if (radius_scale) {
+        MRTX_CUDA(cudaMemcpyAsync(radius_scale, ctx->d_max_bits, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        MRTX_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return MRTX_OK;
+}
+
+int mrtx_downscale_i16(mrtx_ctx* ctx, const int16_t* src, int W, int H, int ds,
+                       float* out, float* radius_scale) {
+    MRTX_CTX(ctx);
+    int rc = check_downscale_args(src, W, H, ds, out);
+    if (rc) return rc;
+    MRTX_REQUIRE(radius_scale, "null radius_scale");
+    const size_t in_bytes = (size_t)W * H * sizeof(int16_t);
+    const size_t out_bytes = (size_t)(W / ds) * (H / ds) * sizeof(float);
+    int16_t* d_src = nullptr; float* d_out = nullptr;
+    MRTX_CUDA(cudaMalloc(&d_src, in_bytes));
+    cudaError_t e = cudaMalloc(&d_out, out_bytes);
+    if (e != cudaSuccess) { cudaFree(d_src); mrtx_set_error("cudaMalloc: %s", cudaGetErrorString(e)); return MRTX_ERR_CUDA; }
+    rc = MRTX_OK;
+    do {
+        if (cudaMemcpyAsync(d_src, src, in_bytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { rc = MRTX_ERR_CUDA; break; }
+        rc = launch_downscale_i16(ctx, d_src, W, H, ds, d_out);
+        if (rc) break;
+        if (cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) { rc = MRTX_ERR_CUDA; break; }
+        if (cudaMemcpyAsync(radius_scale, ctx->d_max_bits, 4, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) { rc = MRTX_ERR_CUDA; break; }
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = MRTX_ERR_CUDA; break; }
+    } while (0);
+    if (rc == MRTX_ERR_CUDA) mrtx_set_error("downscale: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(d_src); cudaFree(d_out);
+    return rc;
+}
+
+static int check_color_args(const void* bgr, int W, int H, int k, const void* lut, const void* out) {
+    MRTX_REQUIRE(bgr && lut && out, "null buffer");
+    MRTX_REQUIRE(W > 0 && H > 0, "bad image size %d x %d", W, H);
+    MRTX_REQUIRE(k == 1 || k == 2 || k == 4 || k == 8, "color downscale must be one of 1, 2, 4, 8");
+    MRTX_REQUIRE(W % k == 0 && H % k == 0, "image size %d x %d is not divisible by %d", W, H, k);
+    return MRTX_OK;
+}
+
+int mrtx_color_reduce_lut_dev(mrtx_ctx* ctx, const uint8_t* bgr_dev, int W, int H, int k,
+                              const uint8_t lut[256], uint8_t* out_rgba_dev) {
+    MRTX_CTX(ctx);
+    int rc = check_color_args(bgr_dev, W, H, k, lut, out_rgba_dev);
+    if (rc) return rc;
+    uint8_t* d_lut = nullptr;
+    MRTX_CUDA(cudaMalloc(&d_lut, 256));
+    MRTX_CUDA(cudaMemcpyAsync(d_lut, lut, 256, cudaMemcpyHostToDevice, ctx->stream));
+    rc = launch_color_reduce(ctx, bgr_dev, W, H, k, d_lut, out_rgba_dev);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_lut);
+    return rc;
+}
+
+int mrtx_color_reduce_lut(mrtx_ctx* ctx, const uint8_t* bgr, int W, int H, int k,
+                          const uint8_t lut[256], uint8_t* out_rgba) {
+    MRTX_CTX(ctx);
+    int rc = check_color_args(bgr, W, H, k, lut, out_rgba);
+    if (rc) return rc;
+    const size_t in_bytes = (size_t)W * H * 3, out_bytes = (size_t)(W / k) * (H / k) * 4;
+    uint8_t *d_in = nullptr, *d_out = nullptr;
+    MRTX_CUDA(cudaMalloc(&d_in, in_bytes));
+    cudaError_t e = cudaMalloc(&d_out, out_bytes);
+    if (e != cudaSuccess) { cudaFree(d_in); mrtx_set_error("cudaMalloc: %s", cudaGetErrorString(e)); return MRTX_ERR_CUDA; }
+    rc = MRTX_OK;
+    if (cudaMemcpyAsync(d_in, bgr, in_bytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) rc = MRTX_ERR_CUDA;
+    if (!rc) rc = mrtx_color_reduce_lut_dev(ctx, d_in, W, H, k, lut, d_out);
+    if (!rc && cudaMemcpyAsync(out_rgba, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) rc = MRTX_ERR_CUDA;
+    if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = MRTX_ERR_CUDA;
+    if (rc == MRTX_ERR_CUDA) mrtx_set_error("color_reduce: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(d_in); cudaFree(d_out);
+    return rc;
+}
+
+int mrtx_synth_ldem_i16_dev(mrtx_ctx* ctx, int16_t* out_dev, int W, int H, uint32_t seed) {
+    MRTX_CTX(ctx);
+    MRTX_REQUIRE(out_dev && W > 0 && H > 0, "bad arguments");
+    return launch_synth_ldem(ctx, out_dev, W, H, seed);
+}
+int mrtx_synth_color_bgr_dev(mrtx_ctx* ctx, uint8_t* out_dev, int W, int H, uint32_t seed) {
+    MRTX_CTX(ctx);
+    MRTX_REQUIRE(out_dev && W > 0 && H > 0, "bad arguments");
+    return launch_synth_color(ctx, out_dev, W, H, seed);
+}
+
+// ---- scene ---------------------------------------------------------------------------
+static void norm3(double* a) {
+    const double n = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+    if (n > 0) { a[0] /= n; a[1] /= n; a[2] /= n; }
+}
+static void cross3(const double* a, const double* b, double* c) {
+    c[0] = a[1] * b[2] - a[2] * b[1];
+    c[1] = a[2] * b[0] - a[0] * b[2];
+    c[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+}  // extern "C"
+
+void free_heightfield(mrtx_ctx* ctx) {
+    if (ctx->hf_owned_base) cudaFree(ctx->hf_owned_base);
+    if (ctx->hf_levels_owned) cudaFree(ctx->hf_levels_owned);
+    ctx->hf_owned_base = nullptr;
+    ctx->hf_levels_owned = nullptr;
+    memset(&ctx->hf, 0, sizeof(ctx->hf));
+}
+
+extern "C" {
+
+static int set_displacement_common(mrtx_ctx* ctx, const void* map, int W, int H, int is_i16,
+                                   float scale, float radius_scale, int from_host, int copy) {
+    MRTX_CTX(ctx);
+    MRTX_REQUIRE(map, "null map");
+    MRTX_REQUIRE(W >= 8 && H >= 4, "displacement map %d x %d too small (need >= 8 x 4)", W, H);
+    MRTX_REQUIRE(!is_i16 || (radius_scale > 0.0f), "radius_scale must be positive");
+    MRTX_CUDA(cudaStreamSynchronize(ctx->stream));
+    free_heightfield(ctx);
+    const size_t bytes = (size_t)W * H * (is_i16 ? 2 : 4);
+    const void* base = map;
+    if (from_host || copy) {
+        MRTX_CUDA(cudaMalloc(&ctx->hf_owned_base, bytes));
+        MRTX_CUDA(cudaMemcpyAsync(ctx->hf_owned_base, map, bytes,
+                                  from_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, ctx->stream));
+        base = ctx->hf_owned_base;
+    }
+    ctx->hf.base = base;
+    ctx->hf.is_i16 = is_i16;
+    ctx->hf.W = W; ctx->hf.H = H;
+    ctx->hf.scale = scale; ctx->hf.radius_scale = radius_scale;
+    int rc = build_pyramid(ctx);
+    if (rc) free_heightfield(ctx);
+    return rc;
+}
+
+int mrtx_set_displacement_f32(mrtx_ctx* ctx, const float* map, int W, int H) {
+    return set_displacement_common(ctx, map, W, H, 0, 0.f, 1.f, 1, 1);
+}
+int mrtx_set_displacement_f32_dev(mrtx_ctx* ctx, const float* map_dev, int W, int H, int copy) {
+    return set_displacement_common(ctx, map_dev, W, H, 0, 0.f, 1.f, 0, copy);
+}
+int mrtx_set_displacement_i16(mrtx_ctx* ctx, const int16_t* map, int W, int H, float scale, float radius_scale) {
+    return set_displacement_common(ctx, map, W, H, 1, scale, radius_scale, 1, 1);
+}
+int mrtx_set_displacement_i16_dev(mrtx_ctx* ctx, const int16_t* map_dev, int W, int H, float scale,
+                                  float radius_scale, int copy) {
+    return set_displacement_common(ctx, map_dev, W, H, 1, scale, radius_scale, 0, copy);
+}
+
+int mrtx_set_texture_rgba8(mrtx_ctx* ctx, int slot, const uint8_t* rgba, int W, int H) {
+    MRTX_CTX(ctx);
+    MRTX_REQUIRE(slot == 0 || slot == 1, "texture slot %d (0 = moon_color, 1 = frame_overlay)", slot);
+    MRTX_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (!rgba) {
+        cudaFree(ctx->tex_owned[slot]);
+        ctx->tex_owned[slot] = nullptr;
+        ctx->tex[slot].data = nullptr; ctx->tex[slot].W = ctx->tex[slot].H = 0;
+        return MRTX_OK;
+    }
+    MRTX_REQUIRE(W > 0 && H > 0, "bad texture size");
+    const size_t bytes = (size_t)W * H * 4;
+    if (ctx->tex[slot].W != W || ctx->tex[slot].H != H || !ctx->tex_owned[slot]) {
+        cudaFree(ctx->tex_owned[slot]);
+        ctx->tex_owned[slot] = nullptr;
+        MRTX_CUDA(cudaMalloc(&ctx->tex_owned[slot], bytes));
+    }
+    MRTX_CUDA(cudaMemcpyAsync(ctx->tex_owned[slot], rgba, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    MRTX_CUDA(cudaStreamSynchronize(ctx->stream));   // the caller may drop its array right away
+    ctx->tex[slot].data = (const uchar4*)ctx->tex_owned[slot];
+    ctx->tex[slot].W = W; ctx->tex[slot].H = H;
+    return MRTX_OK;
+}
+
+int mrtx_set_frame(mrtx_ctx* ctx, const double pos[3], const double u[3], const double v[3], double radius) {
+    MRTX_REQUIRE(ctx && pos && u && v, "null argument");
+    MRTX_REQUIRE(radius > 0, "radius must be positive");
+    SceneParams& sp = ctx->sp;
+    double ez[3] = {u[0], u[1], u[2]};
+    norm3(ez);
+    // v is the scene direction of longitude 0 (body -Y); make it orthogonal to u
+    double vv[3] = {v[0], v[1], v[2]};
+    const double d = vv[0] * ez[0] + vv[1] * ez[1] + vv[2] * ez[2];
+    for (int i = 0; i < 3; ++i) vv[i] -= d * ez[i];
+    MRTX_REQUIRE(vv[0] * vv[0] + vv[1] * vv[1] + vv[2] * vv[2] > 1e-24, "u and v are parallel");
+    norm3(vv);
+    double ex[3];
+    cross3(ez, vv, ex);          // body +X (lon +90 E) = u x v
+    for (int i = 0; i < 3; ++i) {
+        sp.ex[i] = ex[i]; sp.ey[i] = -vv[i]; sp.ez[i] = ez[i]; sp.pos[i] = pos[i];
+    }
+    sp.radius = radius;
+    return MRTX_OK;
+}
+
+int mrtx_set_camera(mrtx_ctx* ctx, const double eye[3], const double target[3], const double up[3], double fov_deg) {
+    MRTX_REQUIRE(ctx && eye && target && up, "null argument");
+    MRTX_REQUIRE(fov_deg > 0.0 && fov_deg < 180.0, "fov %g outside (0, 180)", fov_deg);
+    Camera& c = ctx->cam;
+    double w[3] = {target[0] - eye[0], target[1] - eye[1], target[2] - eye[2]};
+    MRTX_REQUIRE(w[0] * w[0] + w[1] * w[1] + w[2] * w[2] > 0, "eye == target");
+    norm3(w);
+    double r[3];
+    cross3(w, up, r);
+    MRTX_REQUIRE(r[0] * r[0] + r[1] * r[1] + r[2] * r[2] > 1e-24, "up is parallel to the view direction");
+    norm3(r);
+    double u2[3];
+    cross3(r, w, u2);
+    for (int i = 0; i < 3; ++i) { c.eye[i] = eye[i]; c.w[i] = w[i]; c.right[i] = r[i]; c.up[i] = u2[i]; }
+    c.tan_half_fov = tan(fov_deg * 0.5 * 3.14159265358979323846 / 180.0);
+    return MRTX_OK;
+}
+
+int mrtx_set_light(mrtx_ctx* ctx, const double pos[3], double radius, double radiance) {
+    MRTX_REQUIRE(ctx && pos, "null argument");
+    MRTX_REQUIRE(radius >= 0 && radiance >= 0, "negative light radius / radiance");
+    for (int i = 0; i < 3; ++i) ctx->sp.light_pos[i] = pos[i];
+    ctx->sp.light_radius = radius;
+    ctx->sp.light_radiance = radiance;
+    return MRTX_OK;
+}
+
+int mrtx_set_float(mrtx_ctx* ctx, const char* name, double value) {
+    MRTX_REQUIRE(ctx && name, "null argument");
+    SceneParams& sp = ctx->sp;
+    if (!strcmp(name, "scene_epsilon")) { MRTX_REQUIRE(value >= 0, "scene_epsilon < 0"); sp.scene_epsilon = value; }
+    else if (!strcmp(name, "tonemap_exposure")) sp.exposure = (float)value;
+    else if (!strcmp(name, "tonemap_gamma")) { MRTX_REQUIRE(value > 0, "gamma <= 0"); sp.inv_gamma = (float)(1.0 / value); }
+    else if (!strcmp(name, "marching_step") || !strcmp(name, "marching_step_eps")) { /* exact intersection: unused */ }
+    else { mrtx_set_error("unknown float parameter '%s'", name); return MRTX_ERR_INVALID; }
+    return MRTX_OK;
+}
+
+int mrtx_set_uint(mrtx_ctx* ctx, const char* name, unsigned a, unsigned b) {
+    MRTX_REQUIRE(ctx && name, "null argument");
+    (void)b;
+    if (!strcmp(name, "path_seg_range")) { /* direct light only: camera segment + light segment */ }
+    else if (!strcmp(name, "jitter")) ctx->sp.jitter = a ? 1u : 0u;
+    else if (!strcmp(name, "shadows")) ctx->sp.shadows = a ? 1u : 0u;
+    else if (!strcmp(name, "debug_hits")) ctx->sp.debug_hits = a ? 1u : 0u;
+    else { mrtx_set_error("unknown uint parameter '%s'", name); return MRTX_ERR_INVALID; }
+    return MRTX_OK;
+}
+
+int mrtx_resize(mrtx_ctx* ctx, int width, int height) {
+    MRTX_CTX(ctx);
+    MRTX_REQUIRE(width > 0 && height > 0 && width <= 65536 && height <= 65536, "bad frame size %d x %d", width, height);
+    if (width == ctx->width && height == ctx->height && ctx->accum) return MRTX_OK;
+    MRTX_CUDA(cudaStreamSynchronize(ctx->stream));
+    free_frame(ctx);
+    const size_t n = (size_t)width * height;
+    MRTX_CUDA(cudaMalloc(&ctx->accum, n * sizeof(float4)));
+    MRTX_CUDA(cudaMalloc(&ctx->rgba8, n * sizeof(uchar4)));
+    MRTX_CUDA(cudaMalloc(&ctx->hit, n * sizeof(float4)));
+    MRTX_CUDA(cudaMemsetAsync(ctx->accum, 0, n * sizeof(float4), ctx->stream));
+    MRTX_CUDA(cudaMemsetAsync(ctx->rgba8, 0, n * sizeof(uchar4), ctx->stream));
+    MRTX_CUDA(cudaMemsetAsync(ctx->hit, 0, n * sizeof(float4), ctx->stream));
+    ctx->width = width; ctx->height = height;
+    return MRTX_OK;
+}
+
+// ---- render / read-back ----------------------------------------------------------------
+int mrtx_render(mrtx_ctx* ctx, int x0, int y0, int x1, int y1, unsigned sample0, unsigned nsamples, int reset) {
+    MRTX_CTX(ctx);
+    if (!ctx->accum) { mrtx_set_error("mrtx_resize has not been called"); return MRTX_ERR_STATE; }
+    if (!ctx->hf.base) { mrtx_set_error("no displacement map set"); return MRTX_ERR_STATE; }
+    MRTX_REQUIRE(0 <= x0 && x0 <= x1 && x1 <= ctx->width && 0 <= y0 && y0 <= y1 && y1 <= ctx->height,
+                 "render rectangle [%d,%d)x[%d,%d) outside the %d x %d frame", x0, x1, y0, y1, ctx->width, ctx->height);
+    const size_t n = (size_t)ctx->width * ctx->height;
+    if (reset) MRTX_CUDA(cudaMemsetAsync(ctx->accum, 0, n * sizeof(float4), ctx->stream));
+    if (ctx->sp.debug_hits && !ctx->hit64) MRTX_CUDA(cudaMalloc(&ctx->hit64, n * sizeof(double4)));
+    if (nsamples == 0 || x0 == x1 || y0 == y1) return MRTX_OK;
+    return launch_trace(ctx, x0, y0, x1, y1, sample0, nsamples);
+}
+
+int mrtx_resolve(mrtx_ctx* ctx) {
+    MRTX_CTX(ctx);
+    if (!ctx->accum) { mrtx_set_error("mrtx_resize has not been called"); return MRTX_ERR_STATE; }
+    if (ctx->tex[1].data)
+        MRTX_REQUIRE(ctx->tex[1].W == ctx->width && ctx->tex[1].H == ctx->height,
+                     "frame_overlay is %d x %d, frame is %d x %d", ctx->tex[1].W, ctx->tex[1].H, ctx->width, ctx->height);
+    return launch_resolve(ctx);
+}
+
+static int read_back(mrtx_ctx* ctx, void* out, const void* src, size_t elem) {
+    MRTX_CTX(ctx);
+    MRTX_REQUIRE(out, "null buffer");
+    if (!src) { mrtx_set_error("frame buffer not allocated"); return MRTX_ERR_STATE; }
+    MRTX_CUDA(cudaMemcpyAsync(out, src, (size_t)ctx->width * ctx->height * elem, cudaMemcpyDeviceToHost, ctx->stream));
+    MRTX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return MRTX_OK;
+}
+int mrtx_read_rgba8(mrtx_ctx* ctx, uint8_t* out) { return read_back(ctx, out, ctx ? ctx->rgba8 : nullptr, 4); }
+int mrtx_read_accum_f32(mrtx_ctx* ctx, float* out) { return read_back(ctx, out, ctx ? ctx->accum : nullptr, 16); }
+int mrtx_read_hit_f32(mrtx_ctx* ctx, float* out) { return read_back(ctx, out, ctx ? ctx->hit : nullptr, 16); }
+int mrtx_read_hit_f64(mrtx_ctx* ctx, double* out) { return read_back(ctx, out, ctx ? ctx->hit64 : nullptr, 32); }
+
+int mrtx_hit_at(mrtx_ctx* ctx, int x, int y, float out4[4]) {
+    MRTX_CTX(ctx);
+    MRTX_REQUIRE(out4, "null buffer");
+    if (!ctx->hit) { mrtx_set_error("frame buffer not allocated"); return MRTX_ERR_STATE; }
+    MRTX_REQUIRE(x >= 0 && x < ctx->width && y >= 0 && y < ctx->height, "pixel (%d, %d) outside the frame", x, y);
+    MRTX_CUDA(cudaMemcpyAsync(out4, ctx->hit + (size_t)y * ctx->width + x, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    MRTX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return MRTX_OK;
+}
+
+int mrtx_frame_buffers_dev(mrtx_ctx* ctx, void** accum_dev, void** rgba8_dev, void** hit_dev) {
+    MRTX_CTX(ctx);
+    if (accum_dev) *accum_dev = ctx->accum;
+    if (rgba8_dev) *rgba8_dev = ctx->rgba8;
+    if (hit_dev) *hit_dev = ctx->hit;
+    return MRTX_OK;
+}
+
+int mrtx_counters(mrtx_ctx* ctx, uint64_t out[8], int reset) {
+    MRTX_CTX(ctx);
+    if (out) {
+        MRTX_CUDA(cudaMemcpyAsync(out, ctx->d_counters, 64, cudaMemcpyDeviceToHost, ctx->stream));
+        MRTX_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    if (reset) MRTX_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 64, ctx->stream));
+    return MRTX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,119 @@
+// Shared declarations of libmoonb200.so (internal; the public ABI is include/moonb200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+
+#include "../../include/moonb200.h"
+
+// ---- error plumbing -------------------------------------------------------------
+void mrtx_set_error(const char* fmt, ...);
+
+#define MRTX_CUDA(call)                                                              \
+    do {                                                                             \
+        cudaError_t e_ = (call);                                                     \
+        if (e_ != cudaSuccess) {                                                     \
+            mrtx_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),   \
+                           __FILE__, __LINE__);                                      \
+            return MRTX_ERR_CUDA;                                                    \
+        }                                                                            \
+    } while (0)
+
+#define MRTX_REQUIRE(cond, ...)                                                      \
+    do {                                                                             \
+        if (!(cond)) {                                                               \
+            mrtx_set_error(__VA_ARGS__);                                             \
+            return MRTX_ERR_INVALID;                                                 \
+        }                                                                            \
+    } while (0)
+
+#define MRTX_CTX(ctx)                                                                \
+    do {                                                                             \
+        if (!(ctx)) {                                                                \
+            mrtx_set_error("null context");                                          \
+            return MRTX_ERR_INVALID;                                                 \
+        }                                                                            \
+        MRTX_CUDA(cudaSetDevice((ctx)->device));                                     \
+    } while (0)
+
+// ---- scene state ------------------------------------------------------------------
+#define MRTX_MAX_LEVELS 20
+
+// Height field + max pyramid as the kernels see it.  Level 0 (the 2x2-corner max of
+// every bilinear patch) is never stored: the patch's own four texels give it.
+// Level k >= 1 holds, per cell, the max texel over the (2^k+1)^2 corner footprint of
+// the 2^k x 2^k level-0 cells it covers (wrap in longitude, clamp in latitude).
+struct HeightField {
+    const void* base;           // int16 or float32 [H][W]
+    int   is_i16;
+    int   W, H;                 // texels
+    int   top;                  // highest level used by traversal (0 = plain DDA)
+    float scale, radius_scale;  // int16 decode: D = ((c*scale)+1)/radius_scale, each op f32
+    const void* level[MRTX_MAX_LEVELS];   // level[k], k = 1..top; same dtype as base
+    int   nx[MRTX_MAX_LEVELS], ny[MRTX_MAX_LEVELS];   // cells per level (level 0: W, H-1)
+    float dmax, dmin;           // global max / min displacement factor
+};
+
+struct Texture8 {
+    const uchar4* data;
+    int W, H;
+};
+
+struct Camera {
+    double eye[3], w[3], right[3], up[3];   // orthonormal view basis (scene space)
+    double tan_half_fov;                    // vertical
+};
+
+struct SceneParams {
+    // scene -> body rotation rows (body x = u x v, y = -v, z = u) and sphere centre
+    double ex[3], ey[3], ez[3], pos[3];
+    double radius;                          // sphere radius (scene units), 10 in MoonRTX
+    double light_pos[3], light_radius, light_radiance;
+    double scene_epsilon;
+    float  exposure, inv_gamma;
+    unsigned jitter, shadows, debug_hits;
+};
+
+struct mrtx_ctx {
+    int device;
+    int sm_count, l2_bytes;
+    size_t hbm_bytes;
+    cudaStream_t own_stream, stream;
+    cudaEvent_t ev0, ev1;
+
+    // data_loader scratch
+    unsigned* d_max_bits;       // running max of the un-normalised elevation (as uint bits)
+    void* flush_buf; size_t flush_bytes;
+
+    // scene
+    HeightField hf;
+    void* hf_owned_base;        // non-null when the context owns the base map
+    void* hf_levels_owned;      // one allocation holding all pyramid levels
+    Texture8 tex[2];
+    void* tex_owned[2];
+    Camera cam;
+    SceneParams sp;
+
+    // frame
+    int width, height;
+    float4* accum; uchar4* rgba8; float4* hit; double4* hit64;
+    unsigned long long* d_counters;
+
+    // comm
+    void* nccl_lib; void* nccl_comm; int nranks, rank;
+    void* gather_buf; size_t gather_bytes;
+};
+
+// ---- kernels' host launchers (one per .cu) ---------------------------------------------
+int launch_downscale_i16(mrtx_ctx* ctx, const int16_t* src_dev, int W, int H, int ds, float* out_dev);
+int launch_color_reduce(mrtx_ctx* ctx, const uint8_t* bgr_dev, int W, int H, int k,
+                        const uint8_t* lut_dev, uint8_t* out_dev);
+int launch_synth_ldem(mrtx_ctx* ctx, int16_t* out_dev, int W, int H, uint32_t seed);
+int launch_synth_color(mrtx_ctx* ctx, uint8_t* out_dev, int W, int H, uint32_t seed);
+int build_pyramid(mrtx_ctx* ctx);
+int launch_trace(mrtx_ctx* ctx, int x0, int y0, int x1, int y1, unsigned s0, unsigned ns);
+int launch_resolve(mrtx_ctx* ctx);
+void free_heightfield(mrtx_ctx* ctx);
