@@ -154,7 +154,7 @@ int  mrtx_read_hit_f64(mrtx_ctx* ctx, double* out);
 
 /* counters since the last reset: [0] primary rays, [1] primary rays entering the
  * bounding sphere, [2] primary hits, [3] shadow rays, [4] shadow rays occluded,
- * [5] pyramid node visits, [6] exact patch tests, [7] reserved                         */
+ * [5] pyramid node visits, [6] exact patch tests, [7] rays that ran out of steps                         */
 int  mrtx_counters(mrtx_ctx* ctx, uint64_t out[8], int reset);
 
 /* ---- multi-GPU (one process per GPU) ----------------------------------------------

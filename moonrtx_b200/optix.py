@@ -1,0 +1,416 @@
+"""
+`B200OptiX`: drop-in for the subset of `plotoptix.TkOptiX` / `NpOptiX` that MoonRTX's hot
+path calls (`self.rt` in moonrtx/moon_renderer.py:571-650, 852-871, renderer_video.py,
+renderer_navigation.py) - same method names, argument meaning and threading contract
+(SURVEY.md §8b).  The scene it accepts is the one MoonRTX builds: one textured, displaced
+sphere ("moon"), one spherical light ("sun"), one pinhole camera, Gamma and Overlay
+post-processing.  Geometry the hot path does not need (sun disk, grid/label tubes, star
+background) is accepted and ignored so that the reference's call sequence runs unchanged.
+
+Rendering runs on the B200 through libmoonb200.so; there is no CPU fallback.
+
+Threading contract (as PlotOptiX): `start()` spawns the render thread; every accumulation
+cycle renders `max_accumulation_frames` passes of 1 spp, then resolves (Gamma, Overlay),
+reads the image back and fires `on_launch_finished(rt)` and the accum-done callback with
+`_padlock` (an RLock) held, so a callback may call the setters and `refresh_scene()`.
+Headless users can skip the thread and call `render_cycle()` synchronously.
+"""
+
+import ctypes as C
+import threading
+from typing import Callable, Optional
+
+import numpy as np
+
+from . import _lib
+from .device import Device, get_device
+
+
+class _OptixShim:
+    """`rt._optix.get_camera_fov(0)` / `set_camera_fov(fov)` (renderer_navigation.py:262, 521)."""
+
+    def __init__(self, rt: "B200OptiX"):
+        self._rt = rt
+
+    def get_camera_fov(self, handle: int = 0) -> float:
+        return float(self._rt._cam["fov"])
+
+    def set_camera_fov(self, fov: float) -> None:
+        self._rt.update_camera(fov=fov)
+
+
+class B200OptiX:
+    def __init__(self, width: int = 1920, height: int = 1080,
+                 on_launch_finished: Optional[Callable] = None,
+                 on_rt_accum_done: Optional[Callable] = None,
+                 device: Optional[Device] = None, **_ignored):
+        self._dev = device or get_device()
+        self._lib = self._dev.lib
+        self._ctx = self._dev.ctx
+        self._padlock = threading.RLock()
+        self._width, self._height = int(width), int(height)
+        self._is_started = False
+        self._is_closed = False
+        self._on_launch_finished = on_launch_finished
+        self._accum_done_cb = on_rt_accum_done
+        self._optix = _OptixShim(self)
+        self._params = {"min_accumulation_step": 1, "max_accumulation_frames": 1}
+        self._floats = {}
+        self._uints = {}
+        self._postproc = []
+        self._moon = {"pos": (0.0, 0.0, 0.0), "u": (0.0, 0.0, 1.0), "v": (0.0, -1.0, 0.0), "r": 10.0}
+        self._moon_name = None
+        self._cam_name = None
+        self._cam = {"eye": (0.0, -300.0, 0.0), "target": (0.0, 0.0, 0.0), "up": (0.0, 0.0, 1.0), "fov": 4.242192793}
+        self._light = {"pos": (21460.0, 0.0, 0.0), "radius": 100.0, "color": 80.0 * (2146.0 / 100.0) ** 2}
+        self._ignored_geometry = {}
+        self._img_rgba = np.zeros((self._height, self._width, 4), dtype=np.uint8)
+        self._dirty = threading.Event()
+        self._stop = threading.Event()
+        self._thread = None
+        self._encoder = None
+        self._frames_rendered = 0
+        self.deterministic = None      # None: jitter iff max_accumulation_frames > 1
+        _lib.check(self._lib.mrtx_resize(self._ctx, self._width, self._height))
+        self._push_camera()
+        self._push_light()
+        self._push_frame()
+
+    # ---- pushes to the C ABI ---------------------------------------------------------
+    def _push_camera(self):
+        c = self._cam
+        _lib.check(self._lib.mrtx_set_camera(self._ctx, _lib.vec3(c["eye"]), _lib.vec3(c["target"]),
+                                             _lib.vec3(c["up"]), float(c["fov"])))
+
+    def _push_light(self):
+        l = self._light
+        _lib.check(self._lib.mrtx_set_light(self._ctx, _lib.vec3(l["pos"]), float(l["radius"]), float(l["color"])))
+
+    def _push_frame(self):
+        m = self._moon
+        _lib.check(self._lib.mrtx_set_frame(self._ctx, _lib.vec3(m["pos"]), _lib.vec3(m["u"]), _lib.vec3(m["v"]),
+                                            float(m["r"])))
+
+    # ---- parameters (moon_renderer.py:578-600) -----------------------------------------
+    def set_param(self, **kwargs):
+        with self._padlock:
+            for k, v in kwargs.items():
+                if k not in ("min_accumulation_step", "max_accumulation_frames", "rt_timeout",
+                             "light_shading", "compute_timeout"):
+                    raise ValueError(f"unknown parameter {k}")
+                self._params[k] = v
+
+    def get_param(self, name):
+        return self._params.get(name)
+
+    def set_uint(self, name: str, x: int, y: Optional[int] = None, refresh: bool = False):
+        with self._padlock:
+            self._uints[name] = (x, y)
+            _lib.check(self._lib.mrtx_set_uint(self._ctx, name.encode(), int(x), int(y or 0)))
+        if refresh:
+            self.refresh_scene()
+
+    def set_float(self, name: str, x: float, y=None, z=None, refresh: bool = False):
+        with self._padlock:
+            self._floats[name] = x
+            _lib.check(self._lib.mrtx_set_float(self._ctx, name.encode(), float(x)))
+        if refresh:
+            self.refresh_scene()
+
+    def get_float(self, name: str):
+        return self._floats.get(name)
+
+    def set_ambient(self, color, refresh: bool = False):
+        # MoonRTX renders with zero ambient (moon_renderer.py:595); nothing else is supported
+        if np.any(np.asarray(color, dtype=np.float64) != 0):
+            raise ValueError("B200OptiX supports ambient 0 only (moon_renderer.py:595)")
+
+    def add_postproc(self, stage: str, refresh: bool = False):
+        if stage not in ("Gamma", "Overlay"):
+            raise ValueError(f"unsupported post-processing stage {stage}")
+        if stage not in self._postproc:
+            self._postproc.append(stage)
+
+    # ---- textures / background (moon_renderer.py:602-617, renderer_video.py:137) ----------
+    def set_texture_2d(self, name: str, data, addr_mode=None, filter_mode=None, keep_on_host=False,
+                       refresh: bool = False, **_):
+        a = np.ascontiguousarray(data)
+        if a.dtype != np.uint8 or a.ndim != 3 or a.shape[2] != 4:
+            raise ValueError("texture must be a (h, w, 4) uint8 array")
+        slot = {"moon_color": 0, "frame_overlay": 1}.get(name)
+        if slot is None:
+            raise ValueError(f"unknown texture {name} (moon_color, frame_overlay)")
+        if slot == 1 and a.shape[:2] != (self._height, self._width):
+            raise ValueError("frame_overlay must match the frame size")
+        with self._padlock:
+            _lib.check(self._lib.mrtx_set_texture_rgba8(self._ctx, slot, a.ctypes.data, a.shape[1], a.shape[0]))
+        if refresh:
+            self.refresh_scene()
+
+    def set_background_mode(self, mode, refresh: bool = False):
+        self._background_mode = mode       # star background: SURVEY.md §8f N1 (next)
+
+    def set_background(self, bg, gamma=None, rt_format=None, refresh: bool = False, **_):
+        self._background = None            # rendered black; see set_background_mode
+
+    def update_material(self, name, data, refresh: bool = False):
+        self._material = (name, dict(data))
+
+    def setup_material(self, name, data):
+        self._ignored_geometry["material:" + name] = dict(data)
+
+    # ---- geometry (moon_renderer.py:620-624, 648-650, 854-855) ------------------------------
+    def set_data(self, name: str, pos=None, r=None, u=None, v=None, geom="ParticleSet", geom_attr=None,
+                 mat=None, c=None, refresh: bool = False, **_):
+        if geom == "ParticleSetTextured" and geom_attr == "DisplacedSurface":
+            with self._padlock:
+                self._moon_name = name
+                if pos is not None:
+                    self._moon["pos"] = tuple(np.asarray(pos, dtype=np.float64).reshape(-1)[:3])
+                if u is not None:
+                    self._moon["u"] = tuple(np.asarray(u, dtype=np.float64).reshape(-1)[:3])
+                if v is not None:
+                    self._moon["v"] = tuple(np.asarray(v, dtype=np.float64).reshape(-1)[:3])
+                if r is not None:
+                    self._moon["r"] = float(np.asarray(r, dtype=np.float64).reshape(-1)[0])
+                self._push_frame()
+        else:
+            # sun disk / overlay geometry: not on the hot path
+            self._ignored_geometry[name] = {"geom": geom, "pos": pos, "r": r, "c": c, "mat": mat}
+        if refresh:
+            self.refresh_scene()
+
+    def update_data(self, name: str, pos=None, r=None, u=None, v=None, c=None, refresh: bool = False, **_):
+        if name == self._moon_name:
+            with self._padlock:
+                if pos is not None:
+                    self._moon["pos"] = tuple(np.asarray(pos, dtype=np.float64).reshape(-1)[:3])
+                if u is not None:
+                    self._moon["u"] = tuple(np.asarray(u, dtype=np.float64).reshape(-1)[:3])
+                if v is not None:
+                    self._moon["v"] = tuple(np.asarray(v, dtype=np.float64).reshape(-1)[:3])
+                if r is not None:
+                    self._moon["r"] = float(np.asarray(r, dtype=np.float64).reshape(-1)[0])
+                self._push_frame()
+        elif name in self._ignored_geometry:
+            self._ignored_geometry[name].update({k: w for k, w in (("pos", pos), ("r", r), ("c", c)) if w is not None})
+        else:
+            raise ValueError(f"no geometry named {name}")
+        if refresh:
+            self.refresh_scene()
+
+    def set_displacement(self, name: str, data, refresh: bool = False, **_):
+        if name != self._moon_name:
+            raise ValueError(f"{name} is not a displaced surface")
+        a = np.ascontiguousarray(data)
+        if a.ndim != 2 or a.dtype != np.float32:
+            raise ValueError("displacement map must be a 2-D float32 array")
+        with self._padlock:
+            _lib.check(self._lib.mrtx_set_displacement_f32(self._ctx, a.ctypes.data, a.shape[1], a.shape[0]))
+        if refresh:
+            self.refresh_scene()
+
+    def set_displacement_i16(self, name: str, counts, radius_scale: float,
+                             scale: float = 0.5 / 1_737_400.0, refresh: bool = False):
+        """
+        B200 extension: the same surface straight from the int16 LDEM counts (what
+        load_elevation_data(ds=1) would produce as float32, data_loader.py:215-242) at half
+        the memory.  `counts` is a host int16 array or a DeviceBuffer (zero-copy).
+        """
+        if name != self._moon_name:
+            raise ValueError(f"{name} is not a displaced surface")
+        from .device import DeviceBuffer
+        with self._padlock:
+            if isinstance(counts, tuple) and isinstance(counts[0], DeviceBuffer):
+                buf, W, H = counts
+                self._displacement_keepalive = buf
+                _lib.check(self._lib.mrtx_set_displacement_i16_dev(self._ctx, buf.ptr, W, H, float(np.float32(scale)),
+                                                                   float(radius_scale), 0))
+            else:
+                a = np.ascontiguousarray(counts)
+                if a.ndim != 2 or a.dtype != np.int16:
+                    raise ValueError("counts must be a 2-D int16 array")
+                _lib.check(self._lib.mrtx_set_displacement_i16(self._ctx, a.ctypes.data, a.shape[1], a.shape[0],
+                                                               float(np.float32(scale)), float(radius_scale)))
+        if refresh:
+            self.refresh_scene()
+
+    # ---- camera (moon_renderer.py:627-635, 565-568; renderer_navigation.py) -------------------
+    def setup_camera(self, name: str, eye=None, target=None, up=None, cam_type: str = "Pinhole", fov: float = -1,
+                     aperture_radius=None, aperture_fract=None, focal_scale=None, make_current: bool = True, **_):
+        if cam_type != "Pinhole":
+            raise ValueError("B200OptiX implements the Pinhole camera only (shared_types.py:56-69)")
+        self._cam_name = name
+        self.update_camera(name, eye=eye, target=target, up=up, fov=fov if fov and fov > 0 else None)
+
+    def update_camera(self, name: Optional[str] = None, eye=None, target=None, up=None, fov=None, **_):
+        with self._padlock:
+            if eye is not None:
+                self._cam["eye"] = tuple(float(x) for x in eye)
+            if target is not None:
+                self._cam["target"] = tuple(float(x) for x in target)
+            if up is not None:
+                self._cam["up"] = tuple(float(x) for x in up)
+            if fov is not None:
+                self._cam["fov"] = float(fov)
+            self._push_camera()
+        if self._is_started:
+            self.refresh_scene()
+
+    def get_camera(self, name: Optional[str] = None) -> dict:
+        c = self._cam
+        return {"Eye": list(c["eye"]), "Target": list(c["target"]), "Up": list(c["up"]), "FoV": c["fov"],
+                "Type": "Pinhole"}
+
+    def get_camera_name_handle(self, name=None):
+        return self._cam_name, 0
+
+    # ---- light (moon_renderer.py:640, 347, 860) ------------------------------------------------
+    def setup_light(self, name: str, pos=None, color=None, radius: float = -1, in_geometry: bool = True, **_):
+        self._light_name = name
+        self.update_light(name, pos=pos, color=color, radius=radius if radius is not None and radius >= 0 else None)
+
+    def update_light(self, name: str, pos=None, color=None, radius=None, **_):
+        with self._padlock:
+            if pos is not None:
+                self._light["pos"] = tuple(float(x) for x in pos)
+            if color is not None:
+                col = np.asarray(color, dtype=np.float64).reshape(-1)
+                self._light["color"] = float(col[0])       # MoonRTX passes a scalar radiance
+            if radius is not None:
+                self._light["radius"] = float(radius)
+            self._push_light()
+
+    # ---- run ----------------------------------------------------------------------------------
+    def refresh_scene(self):
+        self._dirty.set()
+
+    def set_accum_done_cb(self, cb: Optional[Callable]):
+        self._accum_done_cb = cb
+
+    def set_launch_finished_cb(self, cb: Optional[Callable]):
+        self._on_launch_finished = cb
+
+    def render_cycle(self, read_back: bool = True) -> Optional[np.ndarray]:
+        """One accumulation cycle, synchronously, on the calling thread (padlock held)."""
+        with self._padlock:
+            n = max(1, int(self._params["max_accumulation_frames"]))
+            step = max(1, int(self._params["min_accumulation_step"]))
+            jitter = (n > 1) if self.deterministic is None else (not self.deterministic)
+            _lib.check(self._lib.mrtx_set_uint(self._ctx, b"jitter", 1 if jitter else 0, 0))
+            done = 0
+            while done < n:
+                k = min(step, n - done)
+                _lib.check(self._lib.mrtx_render(self._ctx, 0, 0, self._width, self._height, done, k,
+                                                 1 if done == 0 else 0))
+                done += k
+            _lib.check(self._lib.mrtx_resolve(self._ctx))
+            self._frames_rendered += 1
+            if read_back:
+                _lib.check(self._lib.mrtx_read_rgba8(self._ctx, self._img_rgba.ctypes.data))
+                if self._encoder is not None:
+                    self._encoder.grab(self._img_rgba)
+            else:
+                _lib.check(self._lib.mrtx_synchronize(self._ctx))
+            if self._on_launch_finished is not None:
+                self._on_launch_finished(self)
+            if self._accum_done_cb is not None:
+                self._accum_done_cb(self)
+            return self._img_rgba if read_back else None
+
+    def _run(self):
+        while not self._stop.is_set():
+            if not self._dirty.wait(timeout=0.05):
+                continue
+            self._dirty.clear()
+            try:
+                self.render_cycle()
+            except Exception as e:                       # PlotOptiX logs and continues
+                print(f"B200OptiX render thread: {e}")
+
+    def start(self):
+        if self._is_started:
+            return
+        self._is_started = True
+        self._stop.clear()
+        self._dirty.set()
+        self._thread = threading.Thread(target=self._run, name="B200OptiX-render", daemon=True)
+        self._thread.start()
+
+    def close(self):
+        self._stop.set()
+        if self._thread is not None and self._thread is not threading.current_thread():
+            self._thread.join(timeout=10)
+        self._thread = None
+        self._is_started = False
+        self._is_closed = True
+        if self._encoder is not None:
+            self._encoder.stop()
+            self._encoder = None
+
+    # ---- read-back (moon_renderer.py:1137-1142, renderer_dialogs.py:1222-1224) -----------------
+    def get_rt_output(self) -> np.ndarray:
+        return self._img_rgba.copy()
+
+    def _get_image_xy(self, x, y):
+        return int(x), int(y)
+
+    def _get_hit_at(self, x: int, y: int):
+        if not (0 <= x < self._width and 0 <= y < self._height):
+            return 0.0, 0.0, 0.0, 0.0
+        out = (C.c_float * 4)()
+        with self._padlock:
+            _lib.check(self._lib.mrtx_hit_at(self._ctx, int(x), int(y), out))
+        return float(out[0]), float(out[1]), float(out[2]), float(out[3])
+
+    def get_hit_buffer(self) -> np.ndarray:
+        out = np.empty((self._height, self._width, 4), dtype=np.float32)
+        with self._padlock:
+            _lib.check(self._lib.mrtx_read_hit_f32(self._ctx, out.ctypes.data))
+        return out
+
+    def get_accum_buffer(self) -> np.ndarray:
+        out = np.empty((self._height, self._width, 4), dtype=np.float32)
+        with self._padlock:
+            _lib.check(self._lib.mrtx_read_accum_f32(self._ctx, out.ctypes.data))
+        return out
+
+    def get_hit_records_f64(self) -> np.ndarray:
+        """(s_hit, radius, lon, lat) per pixel of the last 1-spp launch (needs set_uint('debug_hits', 1))."""
+        out = np.empty((self._height, self._width, 4), dtype=np.float64)
+        with self._padlock:
+            _lib.check(self._lib.mrtx_read_hit_f64(self._ctx, out.ctypes.data))
+        return out
+
+    def counters(self, reset: bool = False) -> dict:
+        out = (C.c_uint64 * 8)()
+        _lib.check(self._lib.mrtx_counters(self._ctx, out, 1 if reset else 0))
+        names = ("primary_rays", "primary_in_sphere", "primary_hits", "shadow_rays", "shadow_occluded",
+                 "node_visits", "patch_tests", "overflow")
+        return {k: int(out[i]) for i, k in enumerate(names)}
+
+    def save_image(self, path: str, bps: str = "Bps8"):
+        import cv2
+        img = self._img_rgba
+        if bps == "Bps16":
+            cv2.imwrite(path, (img[..., [2, 1, 0, 3]].astype(np.uint16) * 257))
+        else:
+            cv2.imwrite(path, img[..., [2, 1, 0, 3]])
+
+    # ---- encoder (renderer_video.py:222-256, 290, 339-340) ----------------------------------------
+    def encoder_create(self, fps: int = 25, bitrate: float = 16, idrrate=None, profile=None, preset=None):
+        from .video import FrameSink
+        self._encoder_cfg = (int(fps), float(bitrate))
+        FrameSink.check_available()
+
+    def encoder_start(self, out_name: str, n_frames: int = 0):
+        from .video import FrameSink
+        fps, _ = getattr(self, "_encoder_cfg", (25, 16.0))
+        self._encoder = FrameSink(out_name, self._width, self._height, fps, n_frames)
+
+    def encoder_is_open(self) -> bool:
+        return self._encoder is not None and self._encoder.is_open()
+
+    def encoder_stop(self):
+        if self._encoder is not None:
+            self._encoder.stop()

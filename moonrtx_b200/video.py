@@ -1,0 +1,105 @@
+"""
+Frame-parallel time-lapse: the reference's F11 export
+(moonrtx/renderer_video.py:148-364) renders frame i at t0 + i*step strictly one after
+another on one GPU, although only a few scalars change between frames
+(moon_renderer.py:840-860).  Here frame i goes to rank i mod G (one process per GPU, the
+height field replicated); no collective is needed while rendering, frames come back in
+order through per-rank host buffers.
+
+`FrameSink` stands in for PlotOptiX's NVENC encoder (encoder_create / encoder_start /
+encoder_is_open / encoder_stop): B200 has no NVENC and this OpenCV build has no H.264,
+so frames go to an `mp4v` cv2.VideoWriter.
+"""
+
+from typing import Callable, Iterable, Optional, Sequence
+
+import numpy as np
+
+from .scene import FrameState
+
+
+class FrameSink:
+    def __init__(self, path: str, width: int, height: int, fps: int, n_frames: int = 0):
+        import cv2
+        self.path, self.n_frames, self.count = path, int(n_frames), 0
+        self._w = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"mp4v"), float(fps), (int(width), int(height)))
+        if not self._w.isOpened():
+            self._w = None
+            raise RuntimeError(f"could not open a video writer for {path}")
+
+    @staticmethod
+    def check_available():
+        import cv2  # noqa: F401
+
+    def is_open(self) -> bool:
+        return self._w is not None
+
+    def grab(self, rgba: np.ndarray):
+        """One frame per completed accumulation cycle; closes itself after n_frames
+        (renderer_video.py:154-159)."""
+        if self._w is None:
+            return
+        self._w.write(np.ascontiguousarray(rgba[..., 2::-1]))
+        self.count += 1
+        if self.n_frames and self.count >= self.n_frames:
+            self.stop()
+
+    def stop(self):
+        if self._w is not None:
+            self._w.release()
+            self._w = None
+
+
+def frames_of_rank(n_frames: int, rank: int, world: int) -> list[int]:
+    """Frame i is rendered by rank i mod world (round-robin keeps every rank's frames
+    spread over the whole terminator sweep, so per-rank cost is balanced)."""
+    if not (0 <= rank < world):
+        raise ValueError("rank outside the world")
+    return list(range(rank, n_frames, world))
+
+
+def apply_frame_state(rt, st: FrameState, moon_name: str = "moon", light_name: str = "sun",
+                      camera_name: str = "cam1"):
+    """The rt.* calls of update_view (moon_renderer.py:852-860) for one time step."""
+    with rt._padlock:
+        rt.update_camera(camera_name, eye=st.eye, target=st.target, up=st.up, fov=st.fov)
+        rt.update_data(moon_name, u=st.u, v=st.v)
+        rt.update_light(light_name, pos=st.light_pos, radius=st.light_radius)
+
+
+def render_timelapse(rt, states: Sequence[FrameState], rank: int = 0, world: int = 1,
+                     on_frame: Optional[Callable[[int, np.ndarray], None]] = None,
+                     overlay_for: Optional[Callable[[int], Optional[np.ndarray]]] = None,
+                     keep: bool = True) -> dict[int, np.ndarray]:
+    """
+    Render this rank's share of a time-lapse.  Each frame is one full accumulation cycle
+    (rt.set_param(max_accumulation_frames=...) applies), exactly as the reference lets every
+    frame converge before the encoder grabs it.  Returns {frame index: RGBA8 image}.
+    """
+    out: dict[int, np.ndarray] = {}
+    for i in frames_of_rank(len(states), rank, world):
+        if overlay_for is not None:
+            ov = overlay_for(i)
+            if ov is not None:
+                rt.set_texture_2d("frame_overlay", ov, filter_mode="Nearest", refresh=False)
+        apply_frame_state(rt, states[i])
+        img = rt.render_cycle()
+        if on_frame is not None:
+            on_frame(i, img)
+        if keep:
+            out[i] = img.copy()
+    return out
+
+
+def merge_in_order(per_rank: Iterable[dict[int, np.ndarray]], n_frames: int) -> list[np.ndarray]:
+    """Frames of all ranks back in time order (what feeds the encoder on rank 0)."""
+    merged: dict[int, np.ndarray] = {}
+    for d in per_rank:
+        for i, img in d.items():
+            if i in merged:
+                raise ValueError(f"frame {i} rendered twice")
+            merged[i] = img
+    missing = [i for i in range(n_frames) if i not in merged]
+    if missing:
+        raise ValueError(f"frames missing: {missing[:8]}")
+    return [merged[i] for i in range(n_frames)]

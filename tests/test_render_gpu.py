@@ -1,0 +1,233 @@
+"""
+Parity of the CUDA render path (through the C ABI, driven with the reference's own rt.* call
+sequence) against the float64 oracle.  Tolerances are BASELINE.json's: hit-radius error
+<= 1e-3 texel, 8-bit image MAE <= 1 and PSNR >= 40 dB at deterministic 1 spp.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from helpers import image_metrics, make_gpu, make_oracle, sun_at_phase
+
+pytestmark = pytest.mark.gpu
+
+R = 10.0
+
+
+def synth_elevation(W, H, seed=3, ds=1):
+    from moonrtx_b200.synth import synth_ldem
+    from moonrtx_b200.data_loader import downscale_elevation
+    return downscale_elevation(synth_ldem(W, H, seed=seed, craters=60), ds)
+
+
+def compare(rt, orc, stride=1, texel_tol=1e-3, allow_mismatch=0):
+    """Render both; returns metrics after asserting the hit-radius and image tolerances."""
+    img = rt.render_cycle().copy()
+    g = rt.get_hit_records_f64()[::stride, ::stride]
+    o = orc.render(stride=stride)
+    oh = o["hit64"]
+    assert g.shape == oh.shape
+    ghit, ohit = g[..., 0] > 0, oh[..., 0] > 0
+    mismatch = int((ghit != ohit).sum())
+    assert mismatch <= allow_mismatch, f"{mismatch} pixels disagree on hit/miss"
+    both = ghit & ohit
+    texel = 2.0 * math.pi * R / orc.s.W                       # scene units per texel at the equator
+    dr = np.abs(g[..., 1] - oh[..., 1])[both] / texel
+    ds_ = np.abs(g[..., 0] - oh[..., 0])[both] / texel
+    # silhouette pixels can legitimately land on a different ridge when the ray grazes a crest;
+    # they must be very few, everything else must be within tolerance
+    bad = int((dr > texel_tol).sum())
+    assert bad <= allow_mismatch, f"{bad} of {both.sum()} hits differ by more than {texel_tol} texel (max {dr.max():.3g})"
+    ref_img = orc.tonemap(o["accum"])
+    mae, psnr = image_metrics(img[::stride, ::stride], ref_img)
+    assert mae <= 1.0 and psnr >= 40.0, (mae, psnr)
+    return {"max_dr_texel": float(np.sort(dr)[-1 - bad] if len(dr) > bad else 0.0), "max_ds_texel": float(ds_.max()),
+            "mae": mae, "psnr": psnr, "hits": int(both.sum()), "img": img, "oracle": o}
+
+
+def test_flat_sphere_is_analytic():
+    elev = np.ones((45, 90), dtype=np.float32)
+    rt = make_gpu(elev, 96, 96, shadows=False)
+    rt.render_cycle()
+    g = rt.get_hit_records_f64()
+    hits = g[g[..., 0] > 0]
+    assert len(hits) > 4000
+    assert np.allclose(hits[:, 1], R, atol=1e-9)
+    # s = distance from the eye (0,-300,0) to the sphere along the pixel ray
+    yy, xx = np.nonzero(g[..., 0] > 0)
+    t = math.tan(math.radians(4.242192793) / 2)
+    sx = ((xx + 0.5) / 96 * 2 - 1) * t
+    sy = (1 - (yy + 0.5) / 96 * 2) * t
+    d = np.stack([sx, np.ones_like(sx), sy], axis=1)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    b = -300.0 * d[:, 1]
+    s = -b - np.sqrt(b * b - (300.0 ** 2 - R * R))
+    assert np.allclose(hits[:, 0], s, atol=1e-8)
+    rt.close()
+
+
+@pytest.mark.parametrize("phase", [90.0, 30.0, 150.0])
+def test_whole_disk_matches_oracle(phase):
+    elev, _ = synth_elevation(720, 360)
+    from moonrtx_b200.synth import synth_color
+    from moonrtx_b200.data_loader import color_texture
+    tex = color_texture(synth_color(256, 128), 2.2, 1)
+    kw = dict(light_pos=sun_at_phase(phase))
+    rt = make_gpu(elev, 160, 120, texture=tex, **kw)
+    orc = make_oracle(elev, 160, 120, texture=tex, **kw)
+    m = compare(rt, orc, allow_mismatch=3)
+    assert m["hits"] > 4000
+    c = rt.counters()
+    assert c["primary_rays"] == 160 * 120 and c["primary_hits"] == m["hits"] or abs(c["primary_hits"] - m["hits"]) <= 3
+    assert c["overflow"] == 0
+    rt.close()
+
+
+def test_int16_surface_equals_float32_surface():
+    from moonrtx_b200.synth import synth_ldem
+    from moonrtx_b200.data_loader import downscale_elevation
+    counts = synth_ldem(720, 360, seed=9, craters=60)
+    elev, rs = downscale_elevation(counts, 1)
+    scale = float(np.float32(0.5 / 1737400.0))
+    kw = dict(light_pos=sun_at_phase(80.0))
+    rt_f = make_gpu(elev, 128, 128, **kw)
+    rt_i = make_gpu(counts, 128, 128, scale=scale, radius_scale=rs, **kw)
+    a = rt_f.render_cycle().copy()
+    b = rt_i.render_cycle().copy()
+    assert np.array_equal(rt_f.get_hit_records_f64(), rt_i.get_hit_records_f64())
+    assert np.array_equal(a, b)
+    orc = make_oracle(counts, 128, 128, scale=scale, radius_scale=rs, **kw)
+    compare(rt_i, orc, allow_mismatch=3)
+    rt_f.close(); rt_i.close()
+
+
+def test_rotated_body_offcentre_camera_narrow_fov():
+    elev, _ = synth_elevation(1440, 720, seed=5)
+    # libration-like rotation of the body, camera panned to the limb, narrow field
+    a, b = math.radians(7.0), math.radians(-5.0)
+    Rz = np.array([[math.cos(a), -math.sin(a), 0], [math.sin(a), math.cos(a), 0], [0, 0, 1]])
+    Rx = np.array([[1, 0, 0], [0, math.cos(b), -math.sin(b)], [0, math.sin(b), math.cos(b)]])
+    Rm = Rz @ Rx
+    kw = dict(u=tuple(Rm[:, 2]), v=tuple(-Rm[:, 1]), eye=(20.0, -298.0, 30.0), target=(6.5, 0.0, 6.9), fov=0.6,
+              light_pos=sun_at_phase(60.0, bright_limb_deg=-70.0))
+    rt = make_gpu(elev, 128, 96, **kw)
+    orc = make_oracle(elev, 128, 96, **kw)
+    m = compare(rt, orc, allow_mismatch=3)
+    assert m["hits"] > 2000
+    rt.close()
+
+
+def test_polar_view():
+    """Camera over the north pole: every ray crosses the converging longitude walls."""
+    elev, _ = synth_elevation(720, 360, seed=6)
+    kw = dict(eye=(0.0, 0.0, 300.0), target=(0.0, 0.0, 0.0), up=(0.0, 1.0, 0.0), fov=1.0,
+              light_pos=(21460.0 * math.cos(0.2), 0.0, 21460.0 * math.sin(0.2)))
+    rt = make_gpu(elev, 96, 96, **kw)
+    orc = make_oracle(elev, 96, 96, **kw)
+    compare(rt, orc, allow_mismatch=3)
+    assert rt.counters()["overflow"] == 0
+    rt.close()
+
+
+def test_config2_1080p_ds16_terminator():
+    """BASELINE config 2: 1920x1080, 5760x2880 float32 map (a LOLA-shaped synthetic map block-meaned on the
+    GPU), sun on the terminator, 1 spp primary + shadow; oracle on every 12th pixel."""
+    import ctypes as C
+    from moonrtx_b200 import _lib
+    from moonrtx_b200.device import get_device
+    from moonrtx_b200.data_loader import downscale_elevation_dev
+    dev = get_device()
+    W, H, ds = 23040, 11520, 4
+    src = dev.alloc(W * H * 2)
+    _lib.check(dev.lib.mrtx_synth_ldem_i16_dev(dev.ctx, src.ptr, W, H, 20240314))
+    out, rs = downscale_elevation_dev(src, W, H, ds)
+    elev = out.download((H // ds, W // ds), np.float32)
+    src.free(); out.free()
+    kw = dict(light_pos=sun_at_phase(90.0))
+    rt = make_gpu(elev, 1920, 1080, **kw)
+    orc = make_oracle(elev, 1920, 1080, **kw)
+    m = compare(rt, orc, stride=12, allow_mismatch=4)
+    assert m["hits"] > 3000
+    c = rt.counters()
+    assert c["overflow"] == 0
+    print({k: v for k, v in m.items() if k not in ("img", "oracle")}, c)
+    rt.close()
+
+
+def test_jittered_multisample_matches_oracle():
+    elev, _ = synth_elevation(720, 360, seed=8)
+    kw = dict(light_pos=sun_at_phase(85.0))
+    rt = make_gpu(elev, 64, 64, debug_hits=False, **kw)
+    rt.set_param(max_accumulation_frames=8)
+    img = rt.render_cycle().copy()
+    acc = rt.get_accum_buffer()
+    orc = make_oracle(elev, 64, 64, jitter=True, **kw)
+    o = orc.render(nsamples=8)
+    assert np.all(acc[..., 3] == 8.0)
+    mae, psnr = image_metrics(img, orc.tonemap(o["accum"]))
+    assert mae <= 1.0 and psnr >= 35.0, (mae, psnr)     # a handful of grazing samples may flip
+    rt.close()
+
+
+def test_hit_buffer_and_get_hit_at():
+    elev, _ = synth_elevation(720, 360, seed=3)
+    rt = make_gpu(elev, 96, 96)
+    rt.render_cycle()
+    hb = rt.get_hit_buffer()
+    orc = make_oracle(elev, 96, 96)
+    o = orc.render()
+    hit = o["hit32"][..., 3] > 0
+    assert np.array_equal(hb[..., 3] > 0, hit)
+    assert np.allclose(hb[hit], o["hit32"][hit], atol=2e-5)
+    hx, hy, hz, hd = rt._get_hit_at(48, 48)
+    assert hd > 0 and 0.9 * R <= math.sqrt(hx * hx + hy * hy + hz * hz) <= 1.15 * R    # renderer_navigation.py:474-476
+    assert rt._get_hit_at(0, 0)[3] <= 0
+    rt.close()
+
+
+def test_overlay_blend_and_callbacks():
+    elev = np.ones((45, 90), dtype=np.float32)
+    rt = make_gpu(elev, 64, 48, light_pos=sun_at_phase(0.0), shadows=False)
+    base = rt.render_cycle().copy()
+    ov = np.zeros((48, 64, 4), dtype=np.uint8)
+    ov[10:20, 10:20] = (0, 0, 0, 255)            # opaque black patch renders 0
+    ov[24:40, 24:40] = (0, 0, 0, 128)            # ~50 % black
+    ov[0:4, 0:4] = (255, 255, 255, 255)
+    rt.set_texture_2d("frame_overlay", ov, filter_mode="Nearest", refresh=False)
+    rt.add_postproc("Overlay")
+    seen = []
+    rt.set_accum_done_cb(lambda r: seen.append(r._frames_rendered))
+    img = rt.render_cycle().copy()
+    assert seen == [2]
+    assert np.all(img[10:20, 10:20, :3] == 0)
+    assert np.all(img[0:4, 0:4, :3] == 255)
+    expect = (base[24:40, 24:40, :3].astype(np.int64) * 127 + 127) // 255
+    assert np.array_equal(img[24:40, 24:40, :3], expect.astype(np.uint8))
+    assert np.array_equal(img[44:, 50:], base[44:, 50:])
+    # render thread contract: start() renders, callback runs with the padlock held (re-entrant)
+    done = []
+    def cb(r):
+        with r._padlock:
+            done.append(1)
+    rt.set_accum_done_cb(cb)
+    rt.start()
+    import time
+    t0 = time.time()
+    while not done and time.time() - t0 < 10:
+        time.sleep(0.01)
+    rt.close()
+    assert done
+
+
+def test_state_errors():
+    from moonrtx_b200.optix import B200OptiX
+    from moonrtx_b200._lib import MoonB200Error
+    rt = B200OptiX(width=32, height=32)
+    with pytest.raises(MoonB200Error):
+        rt.render_cycle()                          # no displacement map yet
+    with pytest.raises(ValueError):
+        rt.set_texture_2d("moon_color", np.zeros((4, 4, 3), dtype=np.uint8))
+    with pytest.raises(ValueError):
+        rt.setup_camera("cam1", cam_type="ThinLens", eye=[0, -300, 0], target=[0, 0, 0], up=[0, 0, 1], fov=4)
+    rt.close()
