@@ -18,351 +18,11 @@
 // Traversal state is float32 re-based at the bounding-sphere entry (H4); every float32
 // decision carries a margin so that it can only add candidate cells, never drop one.
 
-#include "common.cuh"
+#include "trace_core.cuh"
 
 namespace {
 
-constexpr double PI_D = 3.14159265358979323846;
-constexpr float  PI_F = 3.14159265358979323846f;
-constexpr int    MAX_STEPS = 60000;
-
-struct Counters { unsigned nodes, tests, overflow; };
-
-// ---- height field access ---------------------------------------------------------------
-template <bool I16>
-__device__ __forceinline__ float texel_D(const HeightField& hf, int r, int c) {
-    if (I16) {
-        const float v = (float)__ldg((const int16_t*)hf.base + (size_t)r * hf.W + c);
-        // exactly data_loader.py:219-242: *scale, +1, /radius_scale, one rounding each
-        return __fdiv_rn(__fadd_rn(__fmul_rn(v, hf.scale), 1.0f), hf.radius_scale);
-    }
-    return __ldg((const float*)hf.base + (size_t)r * hf.W + c);
-}
-
-template <bool I16>
-__device__ __forceinline__ float level_D(const HeightField& hf, int L, int J, int I) {
-    if (I16) {
-        const float v = (float)__ldg((const int16_t*)hf.level[L] + (size_t)J * hf.nx[L] + I);
-        return __fdiv_rn(__fadd_rn(__fmul_rn(v, hf.scale), 1.0f), hf.radius_scale);
-    }
-    return __ldg((const float*)hf.level[L] + (size_t)J * hf.nx[L] + I);
-}
-
-struct Patch { int r0, c0; float d00, d01, d10, d11; };
-
-template <bool I16>
-__device__ __forceinline__ void load_patch(const HeightField& hf, int r0, int c0, Patch& P) {
-    const int c1 = c0 + 1 == hf.W ? 0 : c0 + 1;
-    P.r0 = r0; P.c0 = c0;
-    P.d00 = texel_D<I16>(hf, r0, c0);     P.d01 = texel_D<I16>(hf, r0, c1);
-    P.d10 = texel_D<I16>(hf, r0 + 1, c0); P.d11 = texel_D<I16>(hf, r0 + 1, c1);
-}
-
-// ---- float64 exact patch test -------------------------------------------------------------
-struct Ray64 { double ox, oy, oz, dx, dy, dz, oo, od; };
-
-struct HitInfo { double s, r, lon, lat, fc, fr; };
-
-__device__ __forceinline__ double patch_f(const Ray64& R, const Patch& P, int W, int H, double radius, double s,
-                                          HitInfo* info) {
-    const double x = R.ox + s * R.dx, y = R.oy + s * R.dy, z = R.oz + s * R.dz;
-    const double rho2 = x * x + y * y;
-    const double r = sqrt(rho2 + z * z);
-    const double lon = atan2(x, -y), lat = atan2(z, sqrt(rho2));
-    const double u = (lon * (0.5 / PI_D) + 0.5) * W - 0.5, v = (0.5 - lat * (1.0 / PI_D)) * H - 0.5;
-    double fc = u - P.c0;
-    if (fc < -0.5 * W) fc += W;
-    if (fc > 0.5 * W) fc -= W;
-    double fr = v - P.r0;
-    fr = fr < 0.0 ? 0.0 : (fr > 1.0 ? 1.0 : fr);
-    const double d = (double)P.d00 * (1.0 - fr) * (1.0 - fc) + (double)P.d10 * fr * (1.0 - fc) +
-                     (double)P.d01 * (1.0 - fr) * fc + (double)P.d11 * fr * fc;
-    if (info) { info->s = s; info->r = r; info->lon = lon; info->lat = lat; info->fc = fc; info->fr = v - P.r0; }
-    return r - radius * d;
-}
-
-// first root of f on [a, b] inside one patch; lo/hi bracket polished to ~1e-13
-__device__ bool patch_root(const Ray64& R, const Patch& P, int W, int H, double radius, double a, double b, double* s_hit) {
-    double fa = patch_f(R, P, W, H, radius, a, nullptr);
-    if (fa <= 0.0) { *s_hit = a; return true; }
-    double fb = patch_f(R, P, W, H, radius, b, nullptr);
-    double lo = a, flo = fa, hi = b, fhi = fb;
-    if (fb > 0.0) {
-        // no sign change at the ends: a grazing double root shows up as a dip in between
-        const double m = 0.5 * (a + b);
-        const double fm = patch_f(R, P, W, H, radius, m, nullptr);
-        if (fm <= 0.0) { hi = m; fhi = fm; }
-        else {
-            // vertex of the parabola through (a, fa), (m, fm), (b, fb)
-            const double h = 0.5 * (b - a);
-            const double c2 = (fa - 2.0 * fm + fb) / (2.0 * h * h), c1 = (fb - fa) / (2.0 * h);
-            if (!(c2 > 0.0)) return false;
-            const double tv = m - c1 / (2.0 * c2);
-            if (!(tv > a && tv < b)) return false;
-            if (fm - c1 * c1 / (4.0 * c2) > 0.25 * fm + 1e-9) return false;      // the dip stays clear of zero
-            const double fv = patch_f(R, P, W, H, radius, tv, nullptr);
-            if (fv > 0.0) return false;
-            hi = tv; fhi = fv;
-        }
-    }
-    for (int it = 0; it < 100 && hi - lo > 1e-14 * (1.0 + fabs(hi)); ++it) {
-        double m = (it & 1) ? 0.5 * (lo + hi) : lo + (hi - lo) * flo / (flo - fhi);
-        if (!(m > lo && m < hi)) m = 0.5 * (lo + hi);
-        const double fm = patch_f(R, P, W, H, radius, m, nullptr);
-        if (fm > 0.0) { lo = m; flo = fm; } else { hi = m; fhi = fm; }
-    }
-    *s_hit = hi;
-    return true;
-}
-
-// The exact interval(s) of the ray inside cell (r0, c0) within the window [wa, wb], each
-// searched for a root in order.  Cell walls: lon half-planes g = p.t (t = (cos lam, sin lam, 0)),
-// lat cones h = z - k r (k = sin phi).
-__device__ bool cell_test64(const Ray64& R, const Patch& P, int W, int H, double radius, double wa, double wb,
-                            double* s_hit) {
-    double crit[10];
-    int n = 0;
-    crit[n++] = wa;
-    double tx[2], ty[2], kk[2];
-    bool has_lat[2];
-#pragma unroll
-    for (int side = 0; side < 2; ++side) {
-        double sn, cs;
-        sincospi((2.0 * (P.c0 + side) + 1.0) / W - 1.0, &sn, &cs);
-        tx[side] = cs; ty[side] = sn;
-        const double g0 = R.ox * cs + R.oy * sn, g1 = R.dx * cs + R.dy * sn;
-        if (g1 != 0.0) {
-            const double sc = -g0 / g1;
-            if (sc > wa && sc < wb) crit[n++] = sc;
-        }
-    }
-#pragma unroll
-    for (int side = 0; side < 2; ++side) {
-        has_lat[side] = side == 0 ? (P.r0 > 0) : (P.r0 < H - 2);
-        kk[side] = 0.0;
-        if (!has_lat[side]) continue;
-        const double k = cospi((P.r0 + side + 0.5) / H);        // sin(phi) of the wall
-        kk[side] = k;
-        const double k2 = k * k;
-        const double A = R.dz * R.dz - k2, B = R.oz * R.dz - k2 * R.od, Cq = R.oz * R.oz - k2 * R.oo;
-        double r1 = wa, r2 = wa;                               // "not inside the window"
-        if (fabs(A) < 1e-300) { if (B != 0.0) r1 = -Cq / (2.0 * B); }
-        else {
-            const double disc = B * B - A * Cq;
-            if (disc >= 0.0) {
-                const double q = -(B + (B >= 0.0 ? 1.0 : -1.0) * sqrt(disc));
-                r1 = q / A;
-                if (q != 0.0) r2 = Cq / q;
-            }
-        }
-        if (r1 > wa && r1 < wb) crit[n++] = r1;
-        if (r2 > wa && r2 < wb) crit[n++] = r2;
-    }
-    crit[n++] = wb;
-    for (int i = 1; i < n; ++i) {                                // insertion sort, n <= 8
-        const double key = crit[i];
-        int j = i - 1;
-        while (j >= 0 && crit[j] > key) { crit[j + 1] = crit[j]; --j; }
-        crit[j + 1] = key;
-    }
-    for (int i = 0; i + 1 < n; ++i) {
-        const double a = crit[i], b = crit[i + 1];
-        if (!(b > a)) continue;
-        const double m = 0.5 * (a + b);
-        const double x = R.ox + m * R.dx, y = R.oy + m * R.dy, z = R.oz + m * R.dz;
-        if (x * tx[0] + y * ty[0] < 0.0) continue;               // west of the cell
-        if (x * tx[1] + y * ty[1] > 0.0) continue;               // east of it
-        const double r = sqrt(x * x + y * y + z * z);
-        if (has_lat[0] && z - kk[0] * r > 0.0) continue;         // north of it
-        if (has_lat[1] && z - kk[1] * r < 0.0) continue;         // south of it
-        if (patch_root(R, P, W, H, radius, a, b, s_hit)) return true;
-    }
-    return false;
-}
-
-// ---- float32 pyramid traversal ---------------------------------------------------------------
-struct Trav {
-    float ox, oy, oz, dx, dy, dz, oo, od;    // re-based ray
-    float smax;
-};
-
-__device__ __forceinline__ float ray_r2(const Trav& T, float s) { return fmaf(s, fmaf(2.0f, T.od, s), T.oo); }
-
-// exit parameter + face (0 lon-lo, 1 lon-hi, 2 north, 3 south, 4 end of ray) of the level-L cell (J, I)
-__device__ float cell_exit32(const HeightField& hf, const Trav& T, int L, int J, int I, float s, int& face) {
-    const int W = hf.W, H = hf.H;
-    const int a = I << L, b = min((I + 1) << L, W);
-    const int n = J << L, m = min((J + 1) << L, H - 1);
-    float best = T.smax;
-    face = 4;
-    const float invW = 1.0f / (float)W, invH = 1.0f / (float)H;
-    {   // east wall: leaving when g = p.t goes positive
-        float sn, cs;
-        sincospif((float)(2 * b + 1) * invW - 1.0f, &sn, &cs);
-        const float g1 = T.dx * cs + T.dy * sn;
-        if (g1 > 0.0f) {
-            const float sc = -(T.ox * cs + T.oy * sn) / g1;
-            const float px = fmaf(sc, T.dx, T.ox), py = fmaf(sc, T.dy, T.oy);
-            if (sc < best && px * sn - py * cs > 0.0f) { best = sc; face = 1; }
-        }
-    }
-    {   // west wall: leaving when g goes negative
-        float sn, cs;
-        sincospif((float)(2 * a + 1) * invW - 1.0f, &sn, &cs);
-        const float g1 = T.dx * cs + T.dy * sn;
-        if (g1 < 0.0f) {
-            const float sc = -(T.ox * cs + T.oy * sn) / g1;
-            const float px = fmaf(sc, T.dx, T.ox), py = fmaf(sc, T.dy, T.oy);
-            if (sc < best && px * sn - py * cs > 0.0f) { best = sc; face = 0; }
-        }
-    }
-#pragma unroll
-    for (int side = 0; side < 2; ++side) {
-        if (side == 0 ? (n == 0) : (m == H - 1)) continue;      // polar caps have no wall
-        const float k = cospif(((float)(side == 0 ? n : m) + 0.5f) * invH);
-        // already beyond the wall?  (h = z - k r; north wall: outside when h > 0)
-        const float zs = fmaf(s, T.dz, T.oz), rs = sqrtf(fmaxf(ray_r2(T, s), 0.0f));
-        const float hs = zs - k * rs;
-        if (side == 0 ? hs > 0.0f : hs < 0.0f) { if (s < best) { best = s; face = 2 + side; } continue; }
-        const float k2 = k * k;
-        const float A = T.dz * T.dz - k2, B = T.oz * T.dz - k2 * T.od, Cq = T.oz * T.oz - k2 * T.oo;
-        float r1 = -1.0f, r2 = -1.0f;
-        if (fabsf(A) < 1e-12f) { if (B != 0.0f) r1 = -Cq / (2.0f * B); }
-        else {
-            const float disc = B * B - A * Cq;
-            if (disc >= 0.0f) {
-                const float q = -(B + copysignf(sqrtf(disc), B));
-                r1 = q / A;
-                if (q != 0.0f) r2 = Cq / q;
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const float sc = i ? r2 : r1;
-            if (!(sc > s) || !(sc < best)) continue;
-            const float z = fmaf(sc, T.dz, T.oz);
-            if (k != 0.0f && z * k < 0.0f) continue;             // the cone's other nappe
-            const float r = sqrtf(fmaxf(ray_r2(T, sc), 1e-30f));
-            const float dh = T.dz - k * (T.od + sc) / r;
-            if (side == 0 ? dh > 0.0f : dh < 0.0f) { best = sc; face = 2 + side; }
-        }
-    }
-    return best;
-}
-
-struct TraceOut { bool hit; double s; HitInfo info; Patch patch; };
-
-// First intersection of the body-frame ray for s >= s_min.  any_hit: stop at any intersection.
-template <bool I16>
-__device__ void trace_ray(const HeightField& hf, double radius, const Ray64& R, double s_min, bool any_hit,
-                          TraceOut& out, Counters& cnt) {
-    out.hit = false;
-    const double Rb = radius * (double)hf.dmax;
-    const double disc = R.od * R.od - (R.oo - Rb * Rb);
-    if (disc < 0.0) return;
-    const double sq = sqrt(disc);
-    const double s_end = -R.od + sq;
-    if (s_end <= s_min) return;
-    const double s_in = fmax(s_min, -R.od - sq);
-
-    Trav T;
-    {
-        const double bx = R.ox + s_in * R.dx, by = R.oy + s_in * R.dy, bz = R.oz + s_in * R.dz;
-        T.ox = (float)bx; T.oy = (float)by; T.oz = (float)bz;
-        T.dx = (float)R.dx; T.dy = (float)R.dy; T.dz = (float)R.dz;
-        T.oo = T.ox * T.ox + T.oy * T.oy + T.oz * T.oz;
-        T.od = T.ox * T.dx + T.oy * T.dy + T.oz * T.dz;
-        T.smax = (float)(s_end - s_in);
-    }
-    const float Rf = (float)radius;
-    const float marg = 2.0e-6f * Rf;                             // > float32 error of a radius near R
-    const int W = hf.W, H = hf.H;
-
-    // start cell at the top level, from the position just inside
-    int L = hf.top, J, I;
-    {
-        const float t0 = fminf(1e-5f * Rf, 0.5f * T.smax);
-        const float x = fmaf(t0, T.dx, T.ox), y = fmaf(t0, T.dy, T.oy), z = fmaf(t0, T.dz, T.oz);
-        const float lon = atan2f(x, -y), lat = atan2f(z, sqrtf(x * x + y * y));
-        const float u = (lon * (0.5f / PI_F) + 0.5f) * (float)W - 0.5f, v = (0.5f - lat * (1.0f / PI_F)) * (float)H - 0.5f;
-        int c0 = (int)floorf(u);
-        c0 = c0 < 0 ? c0 + W : (c0 >= W ? c0 - W : c0);
-        const int r0 = min(max((int)floorf(v), 0), H - 2);
-        J = r0 >> L; I = c0 >> L;
-    }
-
-    float s = 0.0f;
-    for (int step = 0; step < MAX_STEPS; ++step) {
-        int face;
-        const float sx_raw = cell_exit32(hf, T, L, J, I, s, face);
-        const float sx = fmaxf(sx_raw, s);
-        ++cnt.nodes;
-
-        // max radius of the surface over this cell
-        float dmax;
-        Patch P;
-        if (L == 0) {
-            load_patch<I16>(hf, J, I, P);
-            dmax = fmaxf(fmaxf(P.d00, P.d01), fmaxf(P.d10, P.d11));
-        } else {
-            dmax = level_D<I16>(hf, L, J, I);
-        }
-        const float rc = fmaf(Rf, dmax, marg);
-        // min radius of the ray over [s, sx] (with a little slack either side)
-        const float pad = 4.0e-6f * Rf;
-        const float ta = fmaxf(s - pad, 0.0f), tb = fminf(sx + pad, T.smax);
-        const float tm = fminf(fmaxf(-T.od, ta), tb);
-        const float rmin2 = ray_r2(T, tm);
-
-        bool advance = true;
-        if (rmin2 <= rc * rc) {
-            if (L > 0) {
-                // move up to where the ray enters the cell's shell, then pick the child there
-                float sd = s;
-                if (ray_r2(T, s) > rc * rc) {
-                    const float dq = T.od * T.od - (T.oo - rc * rc);
-                    if (dq > 0.0f) sd = fminf(fmaxf(-T.od - sqrtf(dq), s), sx);
-                }
-                const float x = fmaf(sd, T.dx, T.ox), y = fmaf(sd, T.dy, T.oy), z = fmaf(sd, T.dz, T.oz);
-                const int mi = (2 * I + 1) << (L - 1), mj = (2 * J + 1) << (L - 1);
-                int ci = 2 * I, cj = 2 * J;
-                if (mi < min((I + 1) << L, W)) {
-                    float sn, cs;
-                    sincospif((float)(2 * mi + 1) / (float)W - 1.0f, &sn, &cs);
-                    if (x * cs + y * sn >= 0.0f) ci += 1;
-                }
-                if (mj < min((J + 1) << L, H - 1)) {
-                    const float k = cospif(((float)mj + 0.5f) / (float)H);
-                    if (z - k * sqrtf(x * x + y * y + z * z) < 0.0f) cj += 1;     // south of the mid wall
-                }
-                s = sd; L -= 1; I = ci; J = cj;
-                advance = false;
-            } else {
-                ++cnt.tests;
-                const double wpad = 2.0e-5 * radius;
-                const double wa = fmax(s_in + (double)s - wpad, s_min), wb = fmin(s_in + (double)sx + wpad, s_end);
-                double sh;
-                if (cell_test64(R, P, W, H, radius, wa, wb, &sh)) {
-                    out.hit = true; out.s = sh; out.patch = P;
-                    if (!any_hit) patch_f(R, P, W, H, radius, sh, &out.info);
-                    return;
-                }
-            }
-        }
-        if (advance) {
-            if (face == 4) return;                               // left the bounding sphere
-            s = sx;
-            bool up;
-            if (face == 1)      { I += 1; if (I >= hf.nx[L]) I = 0; up = (I & 1) == 0; }
-            else if (face == 0) { up = (I & 1) == 0; I -= 1; if (I < 0) I = hf.nx[L] - 1; }
-            else if (face == 3) { J += 1; up = (J & 1) == 0; }
-            else                { up = (J & 1) == 0; J -= 1; }
-            if (J < 0 || J >= hf.ny[L]) return;                  // cannot happen (caps have no wall); be safe
-            if (up && L < hf.top) { L += 1; I >>= 1; J >>= 1; }
-        }
-    }
-    ++cnt.overflow;                                              // step budget exhausted: reported as a miss
-}
+using namespace mrtx_core;
 
 // ---- sampling ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t hash_u32(uint32_t x) {

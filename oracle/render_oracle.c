@@ -32,6 +32,7 @@
  */
 
 #include <math.h>
+#include <stdio.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -189,8 +190,10 @@ static int patch_first_root(const fctx_t* F, double a, double b, double* s_hit) 
 }
 
 /* parameter at which the ray leaves the (lon, lat) cell (r0, c0), given it is inside at s */
-static double cell_exit(const orc_scene* S, const double* o, const double* d, int r0, int c0, double s, double s_end) {
+/* *face: 0 west, 1 east, 2 north, 3 south, 4 = end of the ray */
+static double cell_exit(const orc_scene* S, const double* o, const double* d, int r0, int c0, double s, double s_end, int* face) {
     double best = s_end;
+    *face = 4;
     const double oo = dot3(o, o), od = dot3(o, d);
     /* longitude half-planes through the polar axis */
     for (int side = 0; side < 2; ++side) {
@@ -200,7 +203,7 @@ static double cell_exit(const orc_scene* S, const double* o, const double* d, in
         if ((side == 1 && g1 > 0.0) || (side == 0 && g1 < 0.0)) {
             const double sc = -g0 / g1;
             const double p[3] = {o[0] + sc * d[0], o[1] + sc * d[1], o[2] + sc * d[2]};
-            if (sc > s && sc < best && dot3(p, e) > 0.0) best = sc;
+            if (sc > s && sc < best && dot3(p, e) > 0.0) { best = sc; *face = side; }
         }
     }
     /* latitude cones about the polar axis (none at the polar caps) */
@@ -229,7 +232,7 @@ static double cell_exit(const orc_scene* S, const double* o, const double* d, in
             const double r = sqrt(oo + 2.0 * od * sc + sc * sc);
             if (k != 0.0 && z * k < 0.0) continue;                    /* other nappe */
             const double dh = d[2] - k * (od + sc) / r;               /* d/ds (z - k r) */
-            if ((side == 0 && dh > 0.0) || (side == 1 && dh < 0.0)) best = sc;
+            if ((side == 0 && dh > 0.0) || (side == 1 && dh < 0.0)) { best = sc; *face = 2 + side; }
         }
     }
     return best;
@@ -248,19 +251,44 @@ static void trace(const orc_scene* S, const double* o, const double* d, double s
     double s_in = -b - sq, s_end = -b + sq;
     if (s_end <= s0) return;
     double s = s_in > s0 ? s_in : s0;
-    const double nudge = 1e-11;
-    for (long guard = 0; guard < 4000000 && s < s_end; ++guard) {
-        const double sp = s + nudge;
+    /* The first cell is found from the position just inside; after that the walk is handed from
+     * cell to cell across the wall it leaves through (a ray nearly tangent to a wall changes its
+     * texel coordinate by less than atan2's rounding per step, so re-locating by position can
+     * stall in the cell just left). */
+    int r0, c0;
+    {
+        const double sp = s + 1e-9;
         const double p[3] = {o[0] + sp * d[0], o[1] + sp * d[1], o[2] + sp * d[2]};
         double u, v, lon, lat;
         point_uv(S, p, &u, &v, &lon, &lat);
-        int r0, c0;
         cell_of(S, u, v, &r0, &c0);
-        double sx = cell_exit(S, o, d, r0, c0, sp, s_end);
-        if (!(sx > s)) sx = s + 1e-9;
+    }
+    int face = 4;
+    for (long guard = 0; guard < 4000000 && s < s_end; ++guard) {
+        double u, v, lon, lat;
+        if (guard > 0) {
+            if (face == 0) c0 = c0 == 0 ? S->W - 1 : c0 - 1;
+            else if (face == 1) c0 = c0 + 1 == S->W ? 0 : c0 + 1;
+            else if (face == 2) r0 -= 1;
+            else if (face == 3) r0 += 1;
+            else break;
+            if (r0 < 0 || r0 > S->H - 2) break;            /* cannot happen: polar caps have no wall */
+        }
+        double sx = cell_exit(S, o, d, r0, c0, s, s_end, &face);
+        if (!(sx > s)) sx = s;
+        if (sx - s > 1e-7) {
+            /* self-check: the middle of the piece must lie in this cell */
+            const double sm = 0.5 * (s + sx);
+            const double pm[3] = {o[0] + sm * d[0], o[1] + sm * d[1], o[2] + sm * d[2]};
+            int rr, cc;
+            point_uv(S, pm, &u, &v, &lon, &lat);
+            cell_of(S, u, v, &rr, &cc);
+            if (rr != r0 || cc != c0) { out->cells = -1000000000L; }
+        }
         patch_t P;
         load_patch(S, r0, c0, &P);
         out->cells++;
+        if (getenv("ORC_DEBUG")) fprintf(stderr, "orc cell r%d c%d s=%.9f sx=%.9f\n", r0, c0, s, sx);
         /* cheap cull: the ray stays above the patch's highest corner over [s, sx] */
         double dm = P.d00 > P.d01 ? P.d00 : P.d01;
         if (P.d10 > dm) dm = P.d10;
