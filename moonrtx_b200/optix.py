@@ -23,7 +23,7 @@ from typing import Callable, Optional
 import numpy as np
 
 from . import _lib
-from .device import Device, get_device
+from .device import Device, default_index
 
 
 class _OptixShim:
@@ -44,7 +44,9 @@ class B200OptiX:
                  on_launch_finished: Optional[Callable] = None,
                  on_rt_accum_done: Optional[Callable] = None,
                  device: Optional[Device] = None, **_ignored):
-        self._dev = device or get_device()
+        # one C-ABI context (scene + frame buffers + stream) per renderer object
+        self._own_device = device is None
+        self._dev = device or Device(default_index())
         self._lib = self._dev.lib
         self._ctx = self._dev.ctx
         self._padlock = threading.RLock()
@@ -347,6 +349,9 @@ class B200OptiX:
         if self._encoder is not None:
             self._encoder.stop()
             self._encoder = None
+        if self._own_device and self._dev is not None:
+            self._dev.close()
+            self._dev = None
 
     # ---- read-back (moon_renderer.py:1137-1142, renderer_dialogs.py:1222-1224) -----------------
     def get_rt_output(self) -> np.ndarray:

@@ -79,7 +79,8 @@ def test_whole_disk_matches_oracle(phase):
     m = compare(rt, orc, allow_mismatch=3)
     assert m["hits"] > 4000
     c = rt.counters()
-    assert c["primary_rays"] == 160 * 120 and c["primary_hits"] == m["hits"] or abs(c["primary_hits"] - m["hits"]) <= 3
+    assert c["primary_rays"] == 160 * 120 and abs(c["primary_hits"] - m["hits"]) <= 3
+    assert 0 < c["shadow_rays"] <= c["primary_hits"] and c["shadow_occluded"] <= c["shadow_rays"]
     assert c["overflow"] == 0
     rt.close()
 
