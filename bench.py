@@ -1,0 +1,445 @@
+#!/usr/bin/env python
+"""
+bench.py - the headline benchmark of BASELINE.json on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [--gpus N] ...               # CPU arm (oracle port)
+
+Workload (config 3 of BASELINE.json, `config.workload`): one step = one 3840x2160 frame of
+the default whole-disk camera with the sun on the terminator, rendered from the full-size
+92160x46080 int16 LOLA-shaped synthetic height map (8.5 GB, generated in HBM) and a colour
+texture, 16 spp progressive accumulation (primary ray + sun shadow ray + Lambert shading
+per sample) followed by the Gamma/Overlay resolve.  With N > 1 GPUs every rank renders its
+own frame of the terminator sweep per step (frame-parallel time-lapse, config 4): weak scaling,
+no data-path collective; `value` = rays traced by all ranks / max-over-ranks device time.
+
+Metric: Mrays/s (primary + shadow rays actually traced, primary rays that miss the Moon
+included), device-timed with CUDA events on the launching stream; `e2e` = the same through
+the public drop-in API (B200OptiX: overlay texture upload from pinned memory, scene update,
+render_cycle, RGBA8 frame read-back to pinned memory), wall clock around synchronised calls.
+"""
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MAP_W, MAP_H = 92160, 46080
+IMG_W, IMG_H = 3840, 2160
+COLOR_W, COLOR_H = 27360, 13680
+COLOR_K = 4
+SEED = 20240314
+FRAME_STEP_MIN = 10.0            # config 4: 10-minute steps through the terminator sweep
+FALLBACK_HBM_GBS = 6650.0        # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def quadtree_depth(W):
+    k = 0
+    while (W >> (k + 1)) >= 64:
+        k += 1
+    return k
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            if len(r) < 6:
+                continue
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def frame_states(n, rank, world, steps_total):
+    """Frame (step j, rank r) of the terminator sweep: index j*world + r, 10 minutes apart."""
+    from moonrtx_b200 import scene
+    from moonrtx_b200.synth import synth_ephemeris
+    return [scene.frame_state(synth_ephemeris((j * world + rank) * FRAME_STEP_MIN)) for j in range(steps_total)]
+
+
+# ------------------------------------------------------------------------------------------------
+def build_scene(args, local_rank):
+    """Synthetic maps in HBM + the drop-in renderer, set up with the reference's call sequence."""
+    from moonrtx_b200 import _lib, scene
+    from moonrtx_b200.optix import B200OptiX
+    from moonrtx_b200.data_loader import albedo_lut
+
+    rt = B200OptiX(width=args.img_w, height=args.img_h)
+    dev = rt._dev
+    W, H = args.map_w, args.map_h
+    ldem = dev.alloc(W * H * 2)
+    _lib.check(dev.lib.mrtx_synth_ldem_i16_dev(dev.ctx, ldem.ptr, W, H, SEED))
+    # radius_scale exactly as load_elevation_data(ds=1) would return it (data_loader.py:232-242)
+    radius_scale = _radius_scale_ds1(dev, ldem, W, H)
+    # colour map: synth BGR in HBM -> reduce + LUT kernel -> RGBA texture (data_loader.py:290-368)
+    cw, ch, k = args.color_w, args.color_h, COLOR_K
+    bgr = dev.alloc(cw * ch * 3)
+    _lib.check(dev.lib.mrtx_synth_color_bgr_dev(dev.ctx, bgr.ptr, cw, ch, 4720))
+    tex_dev = dev.alloc((cw // k) * (ch // k) * 4)
+    lut = albedo_lut(2.2)
+    _lib.check(dev.lib.mrtx_color_reduce_lut_dev(dev.ctx, bgr.ptr, cw, ch, k, lut.ctypes.data, tex_dev.ptr))
+    tex = tex_dev.download((ch // k, cw // k, 4), np.uint8)
+    bgr.free(); tex_dev.free()
+
+    rt.set_param(min_accumulation_step=args.spp, max_accumulation_frames=args.spp)
+    rt.set_uint("path_seg_range", 2, 4)
+    rt.set_float("scene_epsilon", scene.SCENE_EPSILON)
+    rt.set_float("marching_step", scene.MARCHING_STEP)
+    rt.set_float("marching_step_eps", scene.MARCHING_STEP_EPS)
+    rt.set_ambient(0)
+    rt.set_float("tonemap_exposure", scene.TONEMAP_EXPOSURE)
+    rt.set_float("tonemap_gamma", 2.2)
+    rt.add_postproc("Gamma")
+    rt.set_background(0)
+    rt.set_texture_2d("moon_color", tex)
+    rt.update_material("diffuse", {"ColorTextures": ["moon_color"]})
+    rt.set_data("moon", geom="ParticleSetTextured", geom_attr="DisplacedSurface",
+                pos=[0, 0, 0], u=[0, 0, 1], v=[0, -1, 0], r=scene.MOON_RADIUS)
+    rt.set_displacement_i16("moon", (ldem, W, H), radius_scale=radius_scale)
+    rt.setup_camera("cam1", cam_type="Pinhole", eye=[0, -scene.CAMERA_DISTANCE, 0], target=[0, 0, 0], up=[0, 0, 1],
+                    fov=scene.default_fov())
+    rt.setup_light("sun", color=scene.light_radiance(80.0), radius=scene.SUN_RADIUS, in_geometry=False)
+    rt.add_postproc("Overlay")
+    return rt, ldem, radius_scale
+
+
+def _radius_scale_ds1(dev, ldem, W, H, band=512):
+    """max of fl32(fl32(c*scale)+1) over the whole map, i.e. the radius_scale the reference computes at
+    downscale 1 (data_loader.py:218-220, 232, 241): the ds=1 kernel run band by band into a scratch
+    buffer (the full float32 map would be 17 GB), keeping only each band's maximum."""
+    import ctypes as C
+    from moonrtx_b200 import _lib
+    out = dev.alloc(W * band * 4)
+    best = 0.0
+    for r0 in range(0, H, band):
+        rows = min(band, H - r0)
+        rs = C.c_float()
+        _lib.check(dev.lib.mrtx_downscale_i16_dev(dev.ctx, C.c_void_p(ldem.ptr + r0 * W * 2), W, rows, 1, out.ptr,
+                                                  C.byref(rs)))
+        best = max(best, float(rs.value))
+    out.free()
+    return best
+
+
+def overlay_image(h, w, text_seed):
+    """A frame_overlay like renderer_video.py:106-144 draws (time label box, bottom-left)."""
+    buf = np.zeros((h, w, 4), dtype=np.uint8)
+    bh, bw = max(8, h // 40), max(64, w // 6)
+    m = max(6, int(round(h * 0.015)))
+    buf[h - m - bh:h - m, m:m + bw] = (0, 0, 0, 150)
+    buf[h - m - bh + 4:h - m - 4, m + 8:m + 8 + (text_seed % (bw - 16))] = (255, 255, 255, 255)
+    return buf
+
+
+def run_ours(args):
+    rank, world, local = dist_env()
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from moonrtx_b200 import _lib
+    from moonrtx_b200.video import apply_frame_state
+
+    t_setup = time.time()
+    rt, ldem, radius_scale = build_scene(args, local)
+    dev = rt._dev
+    lib, ctx = dev.lib, dev.ctx
+    total = args.warmup + args.steps
+    states = frame_states(total, rank, world, total)
+    t_setup = time.time() - t_setup
+
+    def barrier():
+        dev.synchronize()
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    _lib.check(lib.mrtx_set_uint(ctx, b"jitter", 1 if args.spp > 1 else 0, 0))
+
+    def device_step(st):
+        apply_frame_state(rt, st)
+        _lib.check(lib.mrtx_render(ctx, 0, 0, args.img_w, args.img_h, 0, args.spp, 1))
+        _lib.check(lib.mrtx_resolve(ctx))
+
+    # ---- device-resident throughput (value) -------------------------------------------------
+    for j in range(args.warmup):
+        device_step(states[j])
+    rt.counters(reset=True)
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    dev.timer_start()
+    for j in range(args.warmup, total):
+        device_step(states[j])
+    ms_total = dev.timer_stop()
+    barrier()
+    clock_info = clocks.stop()
+    c = rt.counters()
+    launches = 2 * args.steps
+    ms_total = max_over_ranks(ms_total)
+    rays_local = c["primary_rays"] + c["shadow_rays"]
+    rays_all = sum_over_ranks(float(rays_local))
+    value = rays_all / (ms_total * 1e-3) / 1e6
+
+    # ---- dominant kernel alone (roofline) -------------------------------------------------------
+    rt.counters(reset=True)
+    kms = []
+    for j in range(args.warmup, total):
+        apply_frame_state(rt, states[j])
+        dev.synchronize()
+        dev.timer_start()
+        _lib.check(lib.mrtx_render(ctx, 0, 0, args.img_w, args.img_h, 0, args.spp, 1))
+        kms.append(dev.timer_stop())
+    ck = rt.counters()
+    k_ms = sum(kms) / len(kms)
+    depth = quadtree_depth(args.map_w)
+    b_floor = 32 * (depth + 3)
+    rays_in = (ck["primary_in_sphere"] + ck["shadow_rays"]) / args.steps
+    algo_bytes = b_floor * rays_in
+    peak, peak_src = measured_peak()
+    achieved = algo_bytes / (k_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "trace_kernel<int16>", "achieved": round(achieved, 2), "peak": peak,
+                "unit": "GB/s", "frac": round(achieved / peak, 5), "traffic": args.traffic,
+                "algorithmic_bytes_per_launch": int(algo_bytes), "bytes_per_ray": b_floor,
+                "rays_in_sphere_per_launch": int(rays_in), "kernel_ms": round(k_ms, 3), "peak_source": peak_src,
+                "kernel_share_of_step": round(k_ms * args.steps / ms_total, 4) if world == 1 else None}
+
+    # ---- end to end through the public API (e2e) ----------------------------------------------------
+    e2e = None
+    if not args.skip_e2e:
+        overlays = [overlay_image(args.img_h, args.img_w, 37 * j + rank) for j in range(total)]
+        pinned = rt.pinned_like(overlays[0])
+        rt.counters(reset=True)
+        e2e_rays = 0
+        for j in range(total):
+            if j == args.warmup:
+                barrier()
+                rt.counters(reset=True)
+                t0 = time.perf_counter()
+            np.copyto(pinned, overlays[j])                       # the label the host drew for this frame
+            rt.set_texture_2d("frame_overlay", pinned, filter_mode="Nearest", refresh=False)
+            apply_frame_state(rt, states[j])
+            img = rt.render_cycle()                               # renders, resolves, reads the frame back
+            checksum = int(img[::97, ::89, :3].sum())
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        ce = rt.counters()
+        e2e_rays = sum_over_ranks(float(ce["primary_rays"] + ce["shadow_rays"]))
+        e2e = {"value": round(e2e_rays / dt / 1e6, 2), "unit": "Mrays/s",
+               "h2d_bytes_per_step": int(overlays[0].nbytes + 1024), "d2h_bytes_per_step": int(args.img_w * args.img_h * 4),
+               "ms_per_step": round(dt * 1e3 / args.steps, 2), "frame_checksum": checksum}
+
+    # ---- CPU baseline (rank 0, N = 1 only): the float64 oracle on a bounded sample -----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        cpu = cpu_baseline(args, ldem_host=ldem.download((args.map_h, args.map_w), np.int16),
+                           radius_scale=radius_scale, state=states[args.warmup])
+
+    if rank == 0:
+        line = {
+            "metric": "Mrays/s (primary+shadow) @4K", "value": round(value, 2), "unit": "Mrays/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 traversal + f64 root refinement over int16 texels", "data": "synthetic",
+            "config": {"workload": f"{args.img_w}x{args.img_h} frame, {args.map_w}x{args.map_h} int16 synthetic LOLA map + "
+                                   f"{args.color_w // COLOR_K}x{args.color_h // COLOR_K} colour texture, {args.spp} spp "
+                                   f"(BASELINE config 3; N>1: one frame per rank per step, config 4)",
+                       "spp": args.spp, "camera": "default whole-disk, fov 4.2422 deg", "sun": "terminator sweep from phase 90 deg",
+                       "l2_hygiene": "inputs_larger_than_L2 (8.5 GB map + 2.8 GB pyramid)",
+                       "frames_per_step_per_gpu": 1, "setup_s": round(t_setup, 1)},
+            "rays": {"primary_per_step": c["primary_rays"] // args.steps, "shadow_per_step": c["shadow_rays"] // args.steps,
+                     "primary_in_sphere_per_step": c["primary_in_sphere"] // args.steps,
+                     "node_visits_per_step": c["node_visits"] // args.steps, "patch_tests_per_step": c["patch_tests"] // args.steps,
+                     "overflow": c["overflow"]},
+            "frames_per_s": round(world * args.steps / (ms_total * 1e-3), 3),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clock_info,
+        }
+        print(json.dumps(line))
+    rt.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_baseline(args, ldem_host, radius_scale, state, budget_s=20.0):
+    """The oracle (oracle/render_oracle.c, float64, OpenMP on every host core) on a strided sub-grid
+    of the same frame; the stride is chosen so the sample costs about `budget_s` seconds."""
+    from oracle.render_oracle import OracleScene
+    from moonrtx_b200 import scene
+    cores = os.cpu_count() or 1
+    sc = OracleScene(ldem_host, scale=float(np.float32(0.5 / 1737400.0)), radius_scale=radius_scale,
+                     img_w=args.img_w, img_h=args.img_h, u=state.u, v=state.v, eye=state.eye, target=state.target,
+                     up=state.up, fov=state.fov, light_pos=state.light_pos, light_radius=state.light_radius,
+                     light_radiance=scene.light_radiance(80.0), jitter=args.spp > 1)
+    # calibrate on a coarse grid, then size the real sample
+    t0 = time.perf_counter()
+    o = sc.render(stride=96, nsamples=1)
+    t_cal = time.perf_counter() - t0
+    n_cal = o["accum"].shape[0] * o["accum"].shape[1]
+    per_px = t_cal / n_cal * args.spp
+    want = max(1, int(budget_s / max(per_px, 1e-9)))
+    stride = max(1, int(np.ceil(np.sqrt(args.img_w * args.img_h / want))))
+    t0 = time.perf_counter()
+    o = sc.render(stride=stride, nsamples=args.spp)
+    dt = time.perf_counter() - t0
+    npx = o["accum"].shape[0] * o["accum"].shape[1]
+    primary = npx * args.spp
+    # shadow rays = samples that hit a sun-facing slope; the oracle reports the cells walked by each
+    shadow = int((o["stats"][..., 1] > 0).sum()) * args.spp          # last-sample estimate
+    return {"value": round((primary + shadow) / dt / 1e6, 4), "unit": "Mrays/s", "cores": cores, "kind": "port",
+            "sample": f"every {stride}th pixel in x and y of the same {args.img_w}x{args.img_h} frame "
+                      f"({npx} pixels x {args.spp} spp), {dt:.1f} s, float64 oracle (exhaustive cell walk, no pyramid), "
+                      f"OpenMP {cores} threads"}
+
+
+def run_reference(args):
+    """--impl reference: the CPU arm.  The reference's own engine (PlotOptiX) is a closed binary that
+    cannot be installed offline, so the oracle port is what runs (kind 'port')."""
+    rank, world, local = dist_env()
+    if rank != 0:
+        return
+    from moonrtx_b200.synth import synth_ephemeris
+    from moonrtx_b200 import scene
+    # the CPU arm needs the same map: generate it on the GPU when there is one, else a host FFT map
+    ldem_host, radius_scale = None, None
+    try:
+        from moonrtx_b200 import _lib
+        from moonrtx_b200.device import Device
+        dev = Device(local)
+        buf = dev.alloc(args.map_w * args.map_h * 2)
+        _lib.check(dev.lib.mrtx_synth_ldem_i16_dev(dev.ctx, buf.ptr, args.map_w, args.map_h, SEED))
+        radius_scale = _radius_scale_ds1(dev, buf, args.map_w, args.map_h)
+        ldem_host = buf.download((args.map_h, args.map_w), np.int16)
+        buf.free(); dev.close()
+    except Exception as e:
+        print(json.dumps({"impl": "reference", "unavailable": f"could not generate the synthetic map: {e}"}))
+        return
+    st = scene.frame_state(synth_ephemeris(args.warmup * FRAME_STEP_MIN))
+    vals = []
+    cpu = None
+    per_step_budget = max(2.0, min(20.0, 120.0 / (args.steps + args.warmup)))
+    for j in range(args.warmup + args.steps):
+        cpu = cpu_baseline(args, ldem_host, radius_scale, st, budget_s=per_step_budget)
+        if j >= args.warmup:
+            vals.append(cpu["value"])
+    v = statistics.mean(vals)
+    cpu["value"] = round(v, 4)
+    print(json.dumps({
+        "impl": "reference", "metric": "Mrays/s (primary+shadow) @4K", "value": round(v, 4), "unit": "Mrays/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.img_w}x{args.img_h} frame, {args.map_w}x{args.map_h} int16 synthetic LOLA map, "
+                               f"{args.spp} spp (BASELINE config 3), bounded sample per step"},
+        "cpu_baseline": cpu,
+        "e2e": {"value": round(v, 4), "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--spp", type=int, default=16)
+    ap.add_argument("--map-w", type=int, default=MAP_W)
+    ap.add_argument("--map-h", type=int, default=MAP_H)
+    ap.add_argument("--img-w", type=int, default=IMG_W)
+    ap.add_argument("--img-h", type=int, default=IMG_H)
+    ap.add_argument("--color-w", type=int, default=COLOR_W)
+    ap.add_argument("--color-h", type=int, default=COLOR_H)
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch from the ncu capture (profiles/)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

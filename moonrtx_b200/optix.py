@@ -66,7 +66,9 @@ class B200OptiX:
         self._cam = {"eye": (0.0, -300.0, 0.0), "target": (0.0, 0.0, 0.0), "up": (0.0, 0.0, 1.0), "fov": 4.242192793}
         self._light = {"pos": (21460.0, 0.0, 0.0), "radius": 100.0, "color": 80.0 * (2146.0 / 100.0) ** 2}
         self._ignored_geometry = {}
-        self._img_rgba = np.zeros((self._height, self._width, 4), dtype=np.uint8)
+        self._pinned = []
+        self._img_rgba = self.pinned_empty((self._height, self._width, 4), np.uint8)
+        self._img_rgba[...] = 0
         self._dirty = threading.Event()
         self._stop = threading.Event()
         self._thread = None
@@ -77,6 +79,18 @@ class B200OptiX:
         self._push_camera()
         self._push_light()
         self._push_frame()
+
+    # ---- pinned host memory (frame read-back / texture upload at PCIe speed) ------------------
+    def pinned_empty(self, shape, dtype) -> np.ndarray:
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        _lib.check(self._lib.mrtx_host_alloc(n, C.byref(p)))
+        self._pinned.append(p.value)
+        buf = (C.c_uint8 * n).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def pinned_like(self, a: np.ndarray) -> np.ndarray:
+        return self.pinned_empty(a.shape, a.dtype)
 
     # ---- pushes to the C ABI ---------------------------------------------------------
     def _push_camera(self):
@@ -349,6 +363,11 @@ class B200OptiX:
         if self._encoder is not None:
             self._encoder.stop()
             self._encoder = None
+        if self._dev is not None:
+            self._img_rgba = np.array(self._img_rgba)      # detach from the pinned allocation
+            for p in self._pinned:
+                self._lib.mrtx_host_free(p)
+            self._pinned = []
         if self._own_device and self._dev is not None:
             self._dev.close()
             self._dev = None
