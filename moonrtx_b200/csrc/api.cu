@@ -305,6 +305,8 @@ static void cross3(const double* a, const double* b, double* c) {
 void free_heightfield(mrtx_ctx* ctx) {
     if (ctx->hf_owned_base) cudaFree(ctx->hf_owned_base);
     if (ctx->hf_levels_owned) cudaFree(ctx->hf_levels_owned);
+    if (ctx->hf_tables_owned) cudaFree(ctx->hf_tables_owned);
+    ctx->hf_tables_owned = nullptr;
     ctx->hf_owned_base = nullptr;
     ctx->hf_levels_owned = nullptr;
     memset(&ctx->hf, 0, sizeof(ctx->hf));

@@ -55,6 +55,13 @@ struct HeightField {
     const void* level[MRTX_MAX_LEVELS];   // level[k], k = 1..top; same dtype as base
     int   nx[MRTX_MAX_LEVELS], ny[MRTX_MAX_LEVELS];   // cells per level (level 0: W, H-1)
     float dmax, dmin;           // global max / min displacement factor
+    // wall tables (one allocation, hf_tables_owned): cell walls are the half-planes of constant
+    // longitude through texel-centre column i and the cones of constant latitude through
+    // texel-centre row j
+    const float2*  lon32;       // [W+1] (cos, sin) of lambda_i = ((i+0.5)/W - 0.5) * 2 pi
+    const double2* lon64;
+    const float*   lat32;       // [H]   sin(phi_j), phi_j = (0.5 - (j+0.5)/H) * pi
+    const double2* lat64;       // [H]   (sin, cos)(phi_j)
 };
 
 struct Texture8 {
@@ -92,6 +99,7 @@ struct mrtx_ctx {
     HeightField hf;
     void* hf_owned_base;        // non-null when the context owns the base map
     void* hf_levels_owned;      // one allocation holding all pyramid levels
+    void* hf_tables_owned;      // wall tables
     Texture8 tex[2];
     void* tex_owned[2];
     Camera cam;

@@ -109,7 +109,7 @@ trace_kernel(const __grid_constant__ RenderArgs A) {
             ++n_primary;
             TraceOut h;
             const unsigned nodes_before = cnt.nodes;
-            trace_ray<I16>(A.hf, sp.radius, R, 0.0, false, h, cnt);
+            trace_ray<I16>(A.hf, sp.radius, R, 0.0, false, A.hf.top - 3, h, cnt);
             if (cnt.nodes != nodes_before) ++n_inside;
             float3 rgb = make_float3(0.f, 0.f, 0.f);
             if (h.hit) {
@@ -162,7 +162,7 @@ trace_kernel(const __grid_constant__ RenderArgs A) {
                         S.od = S.ox * S.dx + S.oy * S.dy + S.oz * S.dz;
                         TraceOut sh;
                         ++n_shadow;
-                        trace_ray<I16>(A.hf, sp.radius, S, 0.0, true, sh, cnt);
+                        trace_ray<I16>(A.hf, sp.radius, S, 0.0, true, 2, sh, cnt);
                         if (sh.hit) { vis = 0.0; ++n_occl; }
                     }
                     const float3 alb = sample_albedo(A.tex, hi.lon, hi.lat);

@@ -70,53 +70,105 @@ struct Ray64 { double ox, oy, oz, dx, dy, dz, oo, od; };
 
 struct HitInfo { double s, r, lon, lat, fc, fr; };
 
-MRTX_HD inline double patch_f(const Ray64& R, const Patch& P, int W, int H, double radius, double s,
-                                          HitInfo* info) {
-    const double x = R.ox + s * R.dx, y = R.oy + s * R.dy, z = R.oz + s * R.dz;
-    const double rho2 = x * x + y * y;
-    const double r = sqrt(rho2 + z * z);
-    const double lon = atan2(x, -y), lat = atan2(z, sqrt(rho2));
-    const double u = (lon * (0.5 / PI_D) + 0.5) * W - 0.5, v = (0.5 - lat * (1.0 / PI_D)) * H - 0.5;
-    double fc = u - P.c0;
-    if (fc < -0.5 * W) fc += W;
-    if (fc > 0.5 * W) fc -= W;
-    double fr = v - P.r0;
-    fr = fr < 0.0 ? 0.0 : (fr > 1.0 ? 1.0 : fr);
-    const double d = (double)P.d00 * (1.0 - fr) * (1.0 - fc) + (double)P.d10 * fr * (1.0 - fc) +
-                     (double)P.d01 * (1.0 - fr) * fc + (double)P.d11 * fr * fc;
-    if (info) { info->s = s; info->r = r; info->lon = lon; info->lat = lat; info->fc = fc; info->fr = v - P.r0; }
-    return r - radius * d;
+// The four walls of a level-0 cell, from the tables: west/east (cos, sin) of the wall longitude,
+// north/south (sin, cos) of the wall latitude.  Row index r0 / r0+1 always exists in the table
+// (it is the latitude of a texel-centre row) even where a polar cap has no wall.
+struct Cell64 { double wcs, wsn, ecs, esn, nk, nc, sk; bool has_n, has_s; };
+
+MRTX_HD inline void load_cell64(const HeightField& hf, const Patch& P, Cell64& C) {
+    const double2 w = MRTX_LDG(hf.lon64 + P.c0), e = MRTX_LDG(hf.lon64 + P.c0 + 1);
+    const double2 n = MRTX_LDG(hf.lat64 + P.r0), s = MRTX_LDG(hf.lat64 + P.r0 + 1);
+    C.wcs = w.x; C.wsn = w.y; C.ecs = e.x; C.esn = e.y;
+    C.nk = n.x; C.nc = n.y; C.sk = s.x;
+    C.has_n = P.r0 > 0; C.has_s = P.r0 < hf.H - 2;
 }
 
-// first root of f on [a, b] inside one patch; lo/hi bracket polished to ~1e-13
-MRTX_HD bool patch_root(const Ray64& R, const Patch& P, int W, int H, double radius, double a, double b, double* s_hit) {
-    double fa = patch_f(R, P, W, H, radius, a, nullptr);
+// atan2(y, x) for x > 0; the angles met here are at most one texel wide, so the odd series is
+// exact to double rounding (|y/x| < 1/8: next term < 3e-18 relative)
+MRTX_HD inline double atan_small(double y, double x) {
+    const double q = y / x, q2 = q * q;
+    if (q2 < 0.015625) {
+        double p = 1.0 / 17.0;
+        p = fma(p, q2, -1.0 / 15.0); p = fma(p, q2, 1.0 / 13.0); p = fma(p, q2, -1.0 / 11.0);
+        p = fma(p, q2, 1.0 / 9.0);   p = fma(p, q2, -1.0 / 7.0);  p = fma(p, q2, 1.0 / 5.0);
+        p = fma(p, q2, -1.0 / 3.0);  p = fma(p, q2, 1.0);
+        return q * p;
+    }
+    return atan2(y, x);
+}
+
+// f(s) = |p(s)| - R * bilinear(fc, fr): fc, fr = texel fractions measured from the cell's west
+// wall and from latitude row r0 as SMALL angles (no full-circle atan2, no cancellation)
+MRTX_HD inline double patch_f(const Ray64& R, const Patch& P, const Cell64& C, int W, int H, double radius, double s,
+                              HitInfo* info) {
+    const double x = fma(s, R.dx, R.ox), y = fma(s, R.dy, R.oy), z = fma(s, R.dz, R.oz);
+    const double rho = sqrt(x * x + y * y);
+    const double r = sqrt(rho * rho + z * z);
+    const double fc = atan_small(x * C.wcs + y * C.wsn, x * C.wsn - y * C.wcs) * (0.5 / PI_D) * W;
+    const double fr_raw = -atan_small(z * C.nc - rho * C.nk, rho * C.nc + z * C.nk) * (1.0 / PI_D) * H;
+    const double fr = fr_raw < 0.0 ? 0.0 : (fr_raw > 1.0 ? 1.0 : fr_raw);        // rows clamp (renderer_navigation.py:584)
+    const double top = fma(fc, (double)P.d01 - (double)P.d00, (double)P.d00);
+    const double bot = fma(fc, (double)P.d11 - (double)P.d10, (double)P.d10);
+    const double d = fma(fr, bot - top, top);
+    if (info) {
+        info->s = s; info->r = r; info->fc = fc; info->fr = fr_raw;
+        info->lon = ((P.c0 + 0.5 + fc) / W - 0.5) * (2.0 * PI_D);
+        info->lat = (0.5 - (P.r0 + 0.5 + fr_raw) / H) * PI_D;
+    }
+    return fma(-radius, d, r);
+}
+
+// First root of f on [a, b] inside one patch (f is close to a parabola there: a bilinear patch
+// along a nearly straight (u, v) path).  Bracketed: parabola through the ends and the middle,
+// then Illinois regula falsi, until the step is below 1e-10 R.
+MRTX_HD bool patch_root(const Ray64& R, const Patch& P, const Cell64& C, int W, int H, double radius, double a, double b,
+                        double* s_hit) {
+    const double fa = patch_f(R, P, C, W, H, radius, a, nullptr);
     if (fa <= 0.0) { *s_hit = a; return true; }
-    double fb = patch_f(R, P, W, H, radius, b, nullptr);
-    double lo = a, flo = fa, hi = b, fhi = fb;
-    if (fb > 0.0) {
-        // no sign change at the ends: a grazing double root shows up as a dip in between
-        const double m = 0.5 * (a + b);
-        const double fm = patch_f(R, P, W, H, radius, m, nullptr);
-        if (fm <= 0.0) { hi = m; fhi = fm; }
-        else {
-            // vertex of the parabola through (a, fa), (m, fm), (b, fb)
-            const double h = 0.5 * (b - a);
-            const double c2 = (fa - 2.0 * fm + fb) / (2.0 * h * h), c1 = (fb - fa) / (2.0 * h);
-            if (!(c2 > 0.0)) return false;
-            const double tv = m - c1 / (2.0 * c2);
-            if (!(tv > a && tv < b)) return false;
-            if (fm - c1 * c1 / (4.0 * c2) > 0.25 * fm + 1e-9) return false;      // the dip stays clear of zero
-            const double fv = patch_f(R, P, W, H, radius, tv, nullptr);
-            if (fv > 0.0) return false;
-            hi = tv; fhi = fv;
+    const double fb = patch_f(R, P, C, W, H, radius, b, nullptr);
+    const double m = 0.5 * (a + b), h = 0.5 * (b - a);
+    const double fm = patch_f(R, P, C, W, H, radius, m, nullptr);
+    // f ~ fm + c1 t + c2 t^2, t = s - m
+    const double c2 = (fa - 2.0 * fm + fb) / (2.0 * h * h), c1 = (fb - fa) / (2.0 * h);
+    double lo = a, flo = fa, hi, fhi;
+    if (fm <= 0.0) { hi = m; fhi = fm; }
+    else if (fb <= 0.0) { lo = m; flo = fm; hi = b; fhi = fb; }
+    else {
+        // no sign change at the three samples: a grazing double root shows up as a dip
+        if (!(c2 > 0.0)) return false;
+        const double tv = -c1 / (2.0 * c2);
+        if (!(tv > -h && tv < h)) return false;
+        if (fm - c1 * c1 / (4.0 * c2) > 0.25 * fmin(fm, fmin(fa, fb))) return false;   // the dip stays well clear of zero
+        const double fv = patch_f(R, P, C, W, H, radius, m + tv, nullptr);
+        if (fv > 0.0) return false;
+        if (tv > 0.0) { lo = m; flo = fm; }
+        hi = m + tv; fhi = fv;
+    }
+    // first guess: the parabola's root inside the bracket
+    const double tol = 1.0e-10 * radius;
+    double x = 0.5 * (lo + hi);
+    {
+        const double disc = c1 * c1 - 4.0 * c2 * fm;
+        if (disc >= 0.0) {
+            const double sq = sqrt(disc);
+            // descending crossing: f goes + -> -, i.e. derivative c1 + 2 c2 t < 0 -> t = (-c1 - sq) / (2 c2) ... use the stable form
+            const double q = -0.5 * (c1 + (c1 >= 0.0 ? sq : -sq));
+            const double t1 = c2 != 0.0 ? q / c2 : 2.0 * h, t2 = q != 0.0 ? fm / q : 2.0 * h;
+            const double s1 = m + t1, s2 = m + t2;
+            if (s1 > lo && s1 < hi) x = s1;
+            if (s2 > lo && s2 < hi && (!(s1 > lo && s1 < hi) || s2 < s1)) x = s2;
         }
     }
-    for (int it = 0; it < 100 && hi - lo > 1e-14 * (1.0 + fabs(hi)); ++it) {
-        double m = (it & 1) ? 0.5 * (lo + hi) : lo + (hi - lo) * flo / (flo - fhi);
-        if (!(m > lo && m < hi)) m = 0.5 * (lo + hi);
-        const double fm = patch_f(R, P, W, H, radius, m, nullptr);
-        if (fm > 0.0) { lo = m; flo = fm; } else { hi = m; fhi = fm; }
+    int side = 0;
+    for (int it = 0; it < 60; ++it) {
+        const double fx = patch_f(R, P, C, W, H, radius, x, nullptr);
+        if (fx > 0.0) { lo = x; flo = fx; if (side == 1) fhi *= 0.5; side = 1; }
+        else { hi = x; fhi = fx; if (side == -1) flo *= 0.5; side = -1; }
+        if (hi - lo < tol) break;
+        double nx = lo + (hi - lo) * flo / (flo - fhi);
+        if (!(nx > lo && nx < hi)) nx = 0.5 * (lo + hi);
+        if (fabs(nx - x) < 0.25 * tol && fx <= 0.0) break;                             // converged onto the root from below
+        x = nx;
     }
     *s_hit = hi;
     return true;
@@ -130,20 +182,19 @@ MRTX_HD bool patch_root(const Ray64& R, const Patch& P, int W, int H, double rad
 // Cell walls: lon half-planes g = p.t (t = (cos lam, sin lam, 0)), lat cones h = z - k r (k = sin phi).
 // Returns 0 = no root, 1 = root at *s_hit, 2 = the ray is already below the surface where it
 // ENTERS the cell through wall *entry_face at *s_hit: the crossing happened in the cell on the
-// other side of that wall, which the float32 traversal did not propose (see resolve_missed()).
-MRTX_HD int cell_test64(const Ray64& R, const Patch& P, int W, int H, double radius, double wa, double wb,
+// other side of that wall, which the float32 traversal did not propose (see the walk-back).
+MRTX_HD int cell_test64(const HeightField& hf, const Ray64& R, const Patch& P, double radius, double wa, double wb,
                         double oa, double ob, double* s_hit, int* entry_face) {
+    const int W = hf.W, H = hf.H;
+    Cell64 C;
+    load_cell64(hf, P, C);
     double crit[10];
     int cid[10];
     int n = 0;
     crit[n] = wa; cid[n++] = -1;
-    double tx[2], ty[2], kk[2];
-    bool has_lat[2];
 #pragma unroll
     for (int side = 0; side < 2; ++side) {
-        double sn, cs;
-        sincospi((2.0 * (P.c0 + side) + 1.0) / W - 1.0, &sn, &cs);
-        tx[side] = cs; ty[side] = sn;
+        const double cs = side ? C.ecs : C.wcs, sn = side ? C.esn : C.wsn;
         const double g0 = R.ox * cs + R.oy * sn, g1 = R.dx * cs + R.dy * sn;
         if (g1 != 0.0) {
             const double sc = -g0 / g1;
@@ -152,11 +203,8 @@ MRTX_HD int cell_test64(const Ray64& R, const Patch& P, int W, int H, double rad
     }
 #pragma unroll
     for (int side = 0; side < 2; ++side) {
-        has_lat[side] = side == 0 ? (P.r0 > 0) : (P.r0 < H - 2);
-        kk[side] = 0.0;
-        if (!has_lat[side]) continue;
-        const double k = cospi((P.r0 + side + 0.5) / H);        // sin(phi) of the wall
-        kk[side] = k;
+        if (!(side ? C.has_s : C.has_n)) continue;
+        const double k = side ? C.sk : C.nk;
         const double k2 = k * k;
         const double A = R.dz * R.dz - k2, B = R.oz * R.dz - k2 * R.od, Cq = R.oz * R.oz - k2 * R.oo;
         double r1 = wa, r2 = wa;                               // "not inside the window"
@@ -186,12 +234,12 @@ MRTX_HD int cell_test64(const Ray64& R, const Patch& P, int W, int H, double rad
         if (!(b > a) || b < oa || a > ob) continue;
         const double m = 0.5 * (a + b);
         const double x = R.ox + m * R.dx, y = R.oy + m * R.dy, z = R.oz + m * R.dz;
-        if (x * tx[0] + y * ty[0] < 0.0) continue;               // west of the cell
-        if (x * tx[1] + y * ty[1] > 0.0) continue;               // east of it
+        if (x * C.wcs + y * C.wsn < 0.0) continue;               // west of the cell
+        if (x * C.ecs + y * C.esn > 0.0) continue;               // east of it
         const double r = sqrt(x * x + y * y + z * z);
-        if (has_lat[0] && z - kk[0] * r > 0.0) continue;         // north of it
-        if (has_lat[1] && z - kk[1] * r < 0.0) continue;         // south of it
-        if (patch_root(R, P, W, H, radius, a, b, s_hit)) {
+        if (C.has_n && z - C.nk * r > 0.0) continue;             // north of it
+        if (C.has_s && z - C.sk * r < 0.0) continue;             // south of it
+        if (patch_root(R, P, C, W, H, radius, a, b, s_hit)) {
             if (*s_hit == a && cid[i] >= 0) { *entry_face = cid[i]; return 2; }
             return 1;
         }
@@ -218,14 +266,13 @@ MRTX_HD float cell_exit32(const HeightField& hf, const Trav& T, int L, int J, in
     const int n = J << L, m = min((J + 1) << L, H - 1);
     float best = T.smax;
     face = 4;
-    const float invW = 1.0f / (float)W, invH = 1.0f / (float)H;
     const float x = fmaf(s, T.dx, T.ox), y = fmaf(s, T.dy, T.oy), z = fmaf(s, T.dz, T.oz);
     const float r = sqrtf(fmaxf(ray_r2(T, s), 1e-30f));
     const float tol = 2.0e-6f * r;
 #pragma unroll
     for (int side = 0; side < 2; ++side) {      // 0 = west wall (index a), 1 = east wall (index b)
-        float sn, cs;
-        sincospif((float)(2 * (side ? b : a) + 1) * invW - 1.0f, &sn, &cs);
+        const float2 wl = MRTX_LDG(hf.lon32 + (side ? b : a));
+        const float cs = wl.x, sn = wl.y;
         const float sg = side ? 1.0f : -1.0f;                   // outward = +g east, -g west
         const float q = sg * (x * cs + y * sn), dq = sg * (T.dx * cs + T.dy * sn);
         if (!(dq > 0.0f)) continue;                             // not heading out through this wall
@@ -241,7 +288,7 @@ MRTX_HD float cell_exit32(const HeightField& hf, const Trav& T, int L, int J, in
 #pragma unroll
     for (int side = 0; side < 2; ++side) {      // 0 = north wall (index n), 1 = south wall (index m)
         if (side == 0 ? (n == 0) : (m == H - 1)) continue;      // polar caps have no wall
-        const float k = cospif(((float)(side == 0 ? n : m) + 0.5f) * invH);   // sin(lat) of the wall
+        const float k = MRTX_LDG(hf.lat32 + (side == 0 ? n : m));               // sin(lat) of the wall
         const float sg = side ? -1.0f : 1.0f;                   // outward = +h north, -h south; h = z - k r
         const float q = sg * (z - k * r), dq = sg * (T.dz - k * (T.od + s) / r);
         if (q >= -tol && dq > 0.0f) {                           // on or beyond the wall, moving outward
@@ -279,7 +326,7 @@ struct TraceOut { bool hit; double s; HitInfo info; Patch patch; };
 // First intersection of the body-frame ray for s >= s_min.  any_hit: stop at any intersection.
 template <bool I16>
 MRTX_HD void trace_ray(const HeightField& hf, double radius, const Ray64& R, double s_min, bool any_hit,
-                          TraceOut& out, Counters& cnt) {
+                       int start_level, TraceOut& out, Counters& cnt) {
     out.hit = false;
     const double Rb = radius * (double)hf.dmax;
     const double disc = R.od * R.od - (R.oo - Rb * Rb);
@@ -303,7 +350,7 @@ MRTX_HD void trace_ray(const HeightField& hf, double radius, const Ray64& R, dou
     const int W = hf.W, H = hf.H;
 
     // start cell at the top level, from the position just inside
-    int L = hf.top, J, I;
+    int L = min(max(start_level, 0), hf.top), J, I;
     {
         const float t0 = fminf(1e-5f * Rf, 0.5f * T.smax);
         const float x = fmaf(t0, T.dx, T.ox), y = fmaf(t0, T.dy, T.oy), z = fmaf(t0, T.dz, T.oz);
@@ -352,12 +399,11 @@ MRTX_HD void trace_ray(const HeightField& hf, double radius, const Ray64& R, dou
                 const int mi = (2 * I + 1) << (L - 1), mj = (2 * J + 1) << (L - 1);
                 int ci = 2 * I, cj = 2 * J;
                 if (mi < min((I + 1) << L, W)) {
-                    float sn, cs;
-                    sincospif((float)(2 * mi + 1) / (float)W - 1.0f, &sn, &cs);
-                    if (x * cs + y * sn >= 0.0f) ci += 1;
+                    const float2 wl = MRTX_LDG(hf.lon32 + mi);
+                    if (x * wl.x + y * wl.y >= 0.0f) ci += 1;
                 }
                 if (mj < min((J + 1) << L, H - 1)) {
-                    const float k = cospif(((float)mj + 0.5f) / (float)H);
+                    const float k = MRTX_LDG(hf.lat32 + mj);
                     if (z - k * sqrtf(x * x + y * y + z * z) < 0.0f) cj += 1;     // south of the mid wall
                 }
                 s = sd; L -= 1; I = ci; J = cj;
@@ -369,7 +415,7 @@ MRTX_HD void trace_ray(const HeightField& hf, double radius, const Ray64& R, dou
                 const double wa = fmax(sa - big, s_min), wb = fmin(sb + big, s_end);
                 double sh;
                 int ef = -1;
-                int code = cell_test64(R, P, W, H, radius, wa, wb, sa - small, sb + small, &sh, &ef);
+                int code = cell_test64(hf, R, P, radius, wa, wb, sa - small, sb + small, &sh, &ef);
                 // Entered the cell already below the surface: the first crossing lies in a cell the
                 // float32 walk skipped (ray within rounding of a wall or a corner).  Walk back
                 // through the neighbours across the entry walls, in float64, until it is found.
@@ -386,14 +432,14 @@ MRTX_HD void trace_ray(const HeightField& hf, double radius, const Ray64& R, dou
                     double sq2;
                     int ef2 = -1;
                     const double tiny = 1.0e-9 * radius;
-                    const int c2 = cell_test64(R, Q, W, H, radius, fmax(sh - big, s_min), fmin(sh + small, s_end),
+                    const int c2 = cell_test64(hf, R, Q, radius, fmax(sh - big, s_min), fmin(sh + small, s_end),
                                                sh - small, sh - tiny, &sq2, &ef2);
                     if (c2 == 0) break;                          // surface continuous: should not happen
                     P = Q; sh = sq2; ef = ef2; code = c2;
                 }
                 if (code != 0) {
                     out.hit = true; out.s = sh; out.patch = P;
-                    if (!any_hit) patch_f(R, P, W, H, radius, sh, &out.info);
+                    if (!any_hit) { Cell64 C; load_cell64(hf, P, C); patch_f(R, P, C, W, H, radius, sh, &out.info); }
                     return;
                 }
             }

@@ -10,10 +10,10 @@ from helpers import make_oracle, sun_at_phase, DEFAULTS
 SO = "/tmp/libtrace_host.so"
 def build():
     subprocess.run(["nvcc", "-O2", "-Xcompiler", "-fPIC,-fopenmp,-ffp-contract=off", "-shared", "-o", SO,
-                    os.path.join(ROOT, "tools", "trace_host.cu")], check=True, stderr=subprocess.DEVNULL)
+                    os.path.join(ROOT, "tools", "trace_host.cu")], check=True, stderr=subprocess.PIPE)
     l = C.CDLL(SO)
     l.dbg_trace.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_int,
-                            C.c_double, C.c_double, C.c_int, C.c_void_p]
+                            C.c_double, C.c_double, C.c_int, C.c_int, C.c_void_p]
     return l
 
 def camera_rays(img_w, img_h, eye, target, up, fov, u=(0,0,1), v=(0,-1,0), stride=1):
@@ -30,14 +30,14 @@ def camera_rays(img_w, img_h, eye, target, up, fov, u=(0,0,1), v=(0,-1,0), strid
     rays = np.concatenate([np.broadcast_to(ob, db.shape), db], axis=-1)
     return np.ascontiguousarray(rays.reshape(-1, 6)), ys.shape
 
-def run_host(l, elev, rays, s_min=0.0, any_hit=0, scale=0.0, rs=1.0):
+def run_host(l, elev, rays, s_min=0.0, any_hit=0, scale=0.0, rs=1.0, start_level=-3):
     out = np.zeros((len(rays), 8))
     if elev.dtype == np.int16:
         m = np.float32(elev.max()); dmax = float(np.float32(np.float32(np.float32(m*np.float32(scale))+np.float32(1))/np.float32(rs)))
     else:
         dmax = float(elev.max())
     l.dbg_trace(elev.ctypes.data, int(elev.dtype == np.int16), elev.shape[1], elev.shape[0], scale, rs, dmax,
-                rays.ctypes.data, len(rays), s_min, 10.0, any_hit, out.ctypes.data)
+                rays.ctypes.data, len(rays), s_min, 10.0, any_hit, start_level, out.ctypes.data)
     return out
 
 if __name__ == "__main__":
