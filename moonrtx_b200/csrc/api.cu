@@ -53,7 +53,7 @@ int mrtx_create(int device, mrtx_ctx** out_ctx) {
     c->stream = c->own_stream;
     MRTX_CUDA(cudaEventCreate(&c->ev0));
     MRTX_CUDA(cudaEventCreate(&c->ev1));
-    MRTX_CUDA(cudaMalloc(&c->d_max_bits, sizeof(unsigned)));
+    MRTX_CUDA(cudaMalloc(&c->d_max_bits, 2 * sizeof(unsigned)));     // [0] running max, [1] trace work counter
     MRTX_CUDA(cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long)));
     MRTX_CUDA(cudaMemset(c->d_counters, 0, 8 * sizeof(unsigned long long)));
     // scene defaults = the reference's (moon_renderer.py:37, 85-101, 597-599, 620-621)
@@ -64,7 +64,7 @@ int mrtx_create(int device, mrtx_ctx** out_ctx) {
     sp.light_pos[0] = 21460.0; sp.light_radius = 100.0; sp.light_radiance = 80.0 * 460.5316;
     sp.scene_epsilon = 1.0e-4;
     sp.exposure = 0.9f; sp.inv_gamma = 1.0f / 2.2f;
-    sp.jitter = 0; sp.shadows = 1; sp.debug_hits = 0;
+    sp.jitter = 0; sp.shadows = 1; sp.debug_hits = 0; sp.kernel = 1;
     const double eye[3] = {0, -300, 0}, tgt[3] = {0, 0, 0}, up[3] = {0, 0, 1};
     mrtx_set_camera(c, eye, tgt, up, 4.242192793);
     *out_ctx = c;
@@ -443,6 +443,7 @@ int mrtx_set_uint(mrtx_ctx* ctx, const char* name, unsigned a, unsigned b) {
     else if (!strcmp(name, "jitter")) ctx->sp.jitter = a ? 1u : 0u;
     else if (!strcmp(name, "shadows")) ctx->sp.shadows = a ? 1u : 0u;
     else if (!strcmp(name, "debug_hits")) ctx->sp.debug_hits = a ? 1u : 0u;
+    else if (!strcmp(name, "kernel")) ctx->sp.kernel = a ? 1u : 0u;
     else { mrtx_set_error("unknown uint parameter '%s'", name); return MRTX_ERR_INVALID; }
     return MRTX_OK;
 }

@@ -82,6 +82,7 @@ struct SceneParams {
     double scene_epsilon;
     float  exposure, inv_gamma;
     unsigned jitter, shadows, debug_hits;
+    unsigned kernel;                        // 1 = persistent warp-compacting kernel (default), 0 = one thread per pixel
 };
 
 struct mrtx_ctx {

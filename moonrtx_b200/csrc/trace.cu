@@ -63,139 +63,331 @@ struct RenderArgs {
     unsigned sample0, nsamples;
     float4* accum; float4* hit; double4* hit64;
     unsigned long long* counters;
+    unsigned* work_counter;          // persistent kernel: next unclaimed pixel
+    // eye and light centre in the body frame (host-computed once per launch)
+    double eye_b[3], light_b[3];
 };
 
+struct RayStats { unsigned primary, inside, hits, shadow, occluded; };
+
+// Primary ray of (pixel x, y; sample sm) in the body frame.
+__device__ __forceinline__ void primary_ray(const RenderArgs& A, int x, int y, uint32_t pixel, unsigned sm, Ray64& R) {
+    const SceneParams& sp = A.sp;
+    const Camera& cam = A.cam;
+    const double aspect = (double)A.width / (double)A.height;
+    const double jx = sp.jitter ? rnd(pixel, sm, 0) : 0.5, jy = sp.jitter ? rnd(pixel, sm, 1) : 0.5;
+    const double sx = ((x + jx) / A.width * 2.0 - 1.0) * cam.tan_half_fov * aspect;
+    const double sy = (1.0 - (y + jy) / A.height * 2.0) * cam.tan_half_fov;
+    double d[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) d[a] = cam.w[a] + sx * cam.right[a] + sy * cam.up[a];
+    const double dn = 1.0 / sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) d[a] *= dn;
+    R.ox = A.eye_b[0]; R.oy = A.eye_b[1]; R.oz = A.eye_b[2];
+    R.dx = sp.ex[0] * d[0] + sp.ex[1] * d[1] + sp.ex[2] * d[2];
+    R.dy = sp.ey[0] * d[0] + sp.ey[1] * d[1] + sp.ey[2] * d[2];
+    R.dz = sp.ez[0] * d[0] + sp.ez[1] * d[1] + sp.ez[2] * d[2];
+    R.oo = R.ox * R.ox + R.oy * R.oy + R.oz * R.oz;
+    R.od = R.ox * R.dx + R.oy * R.dy + R.oz * R.dz;
+}
+
+// Shade a primary hit: Lambert term towards the (sampled) sun point, albedo lookup, hit buffers.
+// Returns the radiance the sample receives if the sun is visible and, when it faces the sun, the
+// shadow ray S to decide that.
+__device__ __forceinline__ bool shade_hit(const RenderArgs& A, const Ray64& R, const TraceOut& h, int x, int y,
+                                          uint32_t pixel, unsigned sm, float3& lit, Ray64& S) {
+    const SceneParams& sp = A.sp;
+    const HitInfo& hi = h.info;
+    const Patch& P = h.patch;
+    const double px = R.ox + h.s * R.dx, py = R.oy + h.s * R.dy, pz = R.oz + h.s * R.dz;
+    // normal of r(lon, lat) = R * D: n ~ e_r - (r_lon / (r cos lat)) e_lon - (r_lat / r) e_lat
+    const double frc = hi.fr < 0.0 ? 0.0 : (hi.fr > 1.0 ? 1.0 : hi.fr);
+    const double dD_dfc = ((double)P.d01 - (double)P.d00) * (1.0 - frc) + ((double)P.d11 - (double)P.d10) * frc;
+    double dD_dfr = ((double)P.d10 - (double)P.d00) * (1.0 - hi.fc) + ((double)P.d11 - (double)P.d01) * hi.fc;
+    if (hi.fr <= 0.0 || hi.fr >= 1.0) dD_dfr = 0.0;
+    const double r_lon = sp.radius * dD_dfc * A.hf.W / (2.0 * PI_D);
+    const double r_lat = -sp.radius * dD_dfr * A.hf.H / PI_D;
+    const double rho = sqrt(px * px + py * py);
+    const double cl = rho / hi.r, sl = pz / hi.r;
+    const double so = rho > 0.0 ? px / rho : 0.0, co = rho > 0.0 ? -py / rho : 1.0;
+    const double clc = cl > 1e-12 ? cl : 1e-12;
+    const double a1 = r_lon / (hi.r * clc), a2 = r_lat / hi.r;
+    double nx = cl * so - a1 * co - a2 * (-sl * so);
+    double ny = -cl * co - a1 * so - a2 * (sl * co);
+    double nz = sl - a2 * cl;
+    const double nn = 1.0 / sqrt(nx * nx + ny * ny + nz * nz);
+    nx *= nn; ny *= nn; nz *= nn;
+    // light sample
+    const double Lx = A.light_b[0], Ly = A.light_b[1], Lz = A.light_b[2];
+    const double tx = Lx - px, ty = Ly - py, tz = Lz - pz;
+    const double dist = sqrt(tx * tx + ty * ty + tz * tz);
+    double gx = Lx, gy = Ly, gz = Lz;
+    if (sp.jitter && sp.light_radius > 0.0) {
+        // uniform point on the disk facing the hit (branchless ONB, Duff et al. 2017)
+        const double cx = tx / dist, cy = ty / dist, cz = tz / dist;
+        const double sg = cz >= 0.0 ? 1.0 : -1.0, a = -1.0 / (sg + cz), b = cx * cy * a;
+        const double b1x = 1.0 + sg * cx * cx * a, b1y = sg * b, b1z = -sg * cx;
+        const double b2x = b, b2y = sg + cy * cy * a, b2z = -cy;
+        const double rr = sp.light_radius * sqrt(rnd(pixel, sm, 2)), th = 2.0 * PI_D * rnd(pixel, sm, 3);
+        double st, ct;
+        sincos(th, &st, &ct);
+        gx += rr * (ct * b1x + st * b2x); gy += rr * (ct * b1y + st * b2y); gz += rr * (ct * b1z + st * b2z);
+    }
+    double lx = gx - px, ly = gy - py, lz = gz - pz;
+    const double ln = 1.0 / sqrt(lx * lx + ly * ly + lz * lz);
+    lx *= ln; ly *= ln; lz *= ln;
+    const double cosl = nx * lx + ny * ly + nz * lz;
+    if (sm == A.sample0 && A.hit) {
+        // scene = pos + R^T p_body
+        const float hx = (float)(sp.pos[0] + sp.ex[0] * px + sp.ey[0] * py + sp.ez[0] * pz);
+        const float hy = (float)(sp.pos[1] + sp.ex[1] * px + sp.ey[1] * py + sp.ez[1] * pz);
+        const float hz = (float)(sp.pos[2] + sp.ex[2] * px + sp.ey[2] * py + sp.ez[2] * pz);
+        A.hit[(size_t)y * A.width + x] = make_float4(hx, hy, hz, (float)h.s);
+    }
+    if (A.hit64) A.hit64[(size_t)y * A.width + x] = make_double4(h.s, hi.r, hi.lon, hi.lat);
+    lit = make_float3(0.f, 0.f, 0.f);
+    if (!(cosl > 0.0)) return false;
+    const float3 alb = sample_albedo(A.tex, hi.lon, hi.lat);
+    const double q = sp.light_radius / dist;
+    const float E = (float)(sp.light_radiance * q * q * cosl);
+    lit = make_float3(alb.x * E, alb.y * E, alb.z * E);
+    S.ox = px + sp.scene_epsilon * nx; S.oy = py + sp.scene_epsilon * ny; S.oz = pz + sp.scene_epsilon * nz;
+    S.dx = lx; S.dy = ly; S.dz = lz;
+    S.oo = S.ox * S.ox + S.oy * S.oy + S.oz * S.oz;
+    S.od = S.ox * S.dx + S.oy * S.dy + S.oz * S.dz;
+    return sp.shadows != 0;
+}
+
+__device__ __forceinline__ void write_miss(const RenderArgs& A, int x, int y, bool first_sample) {
+    if (first_sample && A.hit) A.hit[(size_t)y * A.width + x] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (A.hit64) A.hit64[(size_t)y * A.width + x] = make_double4(-1.0, 0.0, 0.0, 0.0);
+}
+
+__device__ __forceinline__ void flush_counters(const RenderArgs& A, const RayStats& rs, const Counters& cnt, int lane) {
+    const unsigned vals[8] = {rs.primary, rs.inside, rs.hits, rs.shadow, rs.occluded, cnt.nodes, cnt.tests, cnt.overflow};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const unsigned v = __reduce_add_sync(0xffffffffu, vals[i]);
+        if (lane == 0 && v) atomicAdd(&A.counters[i], (unsigned long long)v);
+    }
+}
+
+// ---- reference kernel: one thread per pixel, rays traced to completion one after another -------------
 template <bool I16>
 __global__ void __launch_bounds__(128)
-trace_kernel(const __grid_constant__ RenderArgs A) {
+trace_kernel_simple(const __grid_constant__ RenderArgs A) {
     const int x = A.x0 + blockIdx.x * blockDim.x + threadIdx.x;
     const int y = A.y0 + blockIdx.y * blockDim.y + threadIdx.y;
-    const bool active = x < A.x1 && y < A.y1;
     Counters cnt = {0u, 0u, 0u};
-    unsigned n_primary = 0, n_inside = 0, n_hit = 0, n_shadow = 0, n_occl = 0;
-    if (active) {
-        const SceneParams& sp = A.sp;
-        const Camera& cam = A.cam;
+    RayStats rs = {0u, 0u, 0u, 0u, 0u};
+    if (x < A.x1 && y < A.y1) {
         const uint32_t pixel = (uint32_t)y * (uint32_t)A.width + (uint32_t)x;
-        const double aspect = (double)A.width / (double)A.height;
-        // eye and light in the body frame
-        const double er[3] = {cam.eye[0] - sp.pos[0], cam.eye[1] - sp.pos[1], cam.eye[2] - sp.pos[2]};
-        const double lr[3] = {sp.light_pos[0] - sp.pos[0], sp.light_pos[1] - sp.pos[1], sp.light_pos[2] - sp.pos[2]};
-        Ray64 R;
-        R.ox = sp.ex[0] * er[0] + sp.ex[1] * er[1] + sp.ex[2] * er[2];
-        R.oy = sp.ey[0] * er[0] + sp.ey[1] * er[1] + sp.ey[2] * er[2];
-        R.oz = sp.ez[0] * er[0] + sp.ez[1] * er[1] + sp.ez[2] * er[2];
-        R.oo = R.ox * R.ox + R.oy * R.oy + R.oz * R.oz;
-        const double Lx = sp.ex[0] * lr[0] + sp.ex[1] * lr[1] + sp.ex[2] * lr[2];
-        const double Ly = sp.ey[0] * lr[0] + sp.ey[1] * lr[1] + sp.ey[2] * lr[2];
-        const double Lz = sp.ez[0] * lr[0] + sp.ez[1] * lr[1] + sp.ez[2] * lr[2];
-
         float3 acc = make_float3(0.f, 0.f, 0.f);
         for (unsigned sm = A.sample0; sm < A.sample0 + A.nsamples; ++sm) {
-            const double jx = sp.jitter ? rnd(pixel, sm, 0) : 0.5, jy = sp.jitter ? rnd(pixel, sm, 1) : 0.5;
-            const double sx = ((x + jx) / A.width * 2.0 - 1.0) * cam.tan_half_fov * aspect;
-            const double sy = (1.0 - (y + jy) / A.height * 2.0) * cam.tan_half_fov;
-            double d[3];
-#pragma unroll
-            for (int a = 0; a < 3; ++a) d[a] = cam.w[a] + sx * cam.right[a] + sy * cam.up[a];
-            const double dn = 1.0 / sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-#pragma unroll
-            for (int a = 0; a < 3; ++a) d[a] *= dn;
-            R.dx = sp.ex[0] * d[0] + sp.ex[1] * d[1] + sp.ex[2] * d[2];
-            R.dy = sp.ey[0] * d[0] + sp.ey[1] * d[1] + sp.ey[2] * d[2];
-            R.dz = sp.ez[0] * d[0] + sp.ez[1] * d[1] + sp.ez[2] * d[2];
-            R.od = R.ox * R.dx + R.oy * R.dy + R.oz * R.dz;
-
-            ++n_primary;
+            Ray64 R;
+            primary_ray(A, x, y, pixel, sm, R);
+            ++rs.primary;
             TraceOut h;
             const unsigned nodes_before = cnt.nodes;
-            trace_ray<I16>(A.hf, sp.radius, R, 0.0, false, A.hf.top - 3, h, cnt);
-            if (cnt.nodes != nodes_before) ++n_inside;
-            float3 rgb = make_float3(0.f, 0.f, 0.f);
+            trace_ray<I16>(A.hf, A.sp.radius, R, 0.0, false, A.hf.top - 3, h, cnt);
+            if (cnt.nodes != nodes_before) ++rs.inside;
             if (h.hit) {
-                ++n_hit;
-                const HitInfo& hi = h.info;
-                const double px = R.ox + h.s * R.dx, py = R.oy + h.s * R.dy, pz = R.oz + h.s * R.dz;
-                // normal of r(lon, lat) = R * D: n ~ e_r - (r_lon / (r cos lat)) e_lon - (r_lat / r) e_lat
-                const Patch& P = h.patch;
-                const double frc = hi.fr < 0.0 ? 0.0 : (hi.fr > 1.0 ? 1.0 : hi.fr);
-                const double dD_dfc = ((double)P.d01 - (double)P.d00) * (1.0 - frc) + ((double)P.d11 - (double)P.d10) * frc;
-                double dD_dfr = ((double)P.d10 - (double)P.d00) * (1.0 - hi.fc) + ((double)P.d11 - (double)P.d01) * hi.fc;
-                if (hi.fr <= 0.0 || hi.fr >= 1.0) dD_dfr = 0.0;
-                const double r_lon = sp.radius * dD_dfc * A.hf.W / (2.0 * PI_D);
-                const double r_lat = -sp.radius * dD_dfr * A.hf.H / PI_D;
-                const double rho = sqrt(px * px + py * py);
-                const double cl = rho / hi.r, sl = pz / hi.r;
-                const double so = rho > 0.0 ? px / rho : 0.0, co = rho > 0.0 ? -py / rho : 1.0;
-                const double clc = cl > 1e-12 ? cl : 1e-12;
-                const double a1 = r_lon / (hi.r * clc), a2 = r_lat / hi.r;
-                double nx = cl * so - a1 * co - a2 * (-sl * so);
-                double ny = -cl * co - a1 * so - a2 * (sl * co);
-                double nz = sl - a2 * cl;
-                const double nn = 1.0 / sqrt(nx * nx + ny * ny + nz * nz);
-                nx *= nn; ny *= nn; nz *= nn;
-                // light sample
-                double tx = Lx - px, ty = Ly - py, tz = Lz - pz;
-                const double dist = sqrt(tx * tx + ty * ty + tz * tz);
-                double gx = Lx, gy = Ly, gz = Lz;
-                if (sp.jitter && sp.light_radius > 0.0) {
-                    const double cx = tx / dist, cy = ty / dist, cz = tz / dist;
-                    const double sg = cz >= 0.0 ? 1.0 : -1.0, a = -1.0 / (sg + cz), b = cx * cy * a;
-                    const double b1x = 1.0 + sg * cx * cx * a, b1y = sg * b, b1z = -sg * cx;
-                    const double b2x = b, b2y = sg + cy * cy * a, b2z = -cy;
-                    const double rr = sp.light_radius * sqrt(rnd(pixel, sm, 2)), th = 2.0 * PI_D * rnd(pixel, sm, 3);
-                    double st, ct;
-                    sincos(th, &st, &ct);
-                    gx += rr * (ct * b1x + st * b2x); gy += rr * (ct * b1y + st * b2y); gz += rr * (ct * b1z + st * b2z);
+                ++rs.hits;
+                float3 lit;
+                Ray64 S;
+                if (shade_hit(A, R, h, x, y, pixel, sm, lit, S)) {
+                    TraceOut sh;
+                    ++rs.shadow;
+                    trace_ray<I16>(A.hf, A.sp.radius, S, 0.0, true, 2, sh, cnt);
+                    if (sh.hit) { lit = make_float3(0.f, 0.f, 0.f); ++rs.occluded; }
                 }
-                double lx = gx - px, ly = gy - py, lz = gz - pz;
-                const double ln = 1.0 / sqrt(lx * lx + ly * ly + lz * lz);
-                lx *= ln; ly *= ln; lz *= ln;
-                const double cosl = nx * lx + ny * ly + nz * lz;
-                if (cosl > 0.0) {
-                    double vis = 1.0;
-                    if (sp.shadows) {
-                        Ray64 S;
-                        S.ox = px + sp.scene_epsilon * nx; S.oy = py + sp.scene_epsilon * ny; S.oz = pz + sp.scene_epsilon * nz;
-                        S.dx = lx; S.dy = ly; S.dz = lz;
-                        S.oo = S.ox * S.ox + S.oy * S.oy + S.oz * S.oz;
-                        S.od = S.ox * S.dx + S.oy * S.dy + S.oz * S.dz;
-                        TraceOut sh;
-                        ++n_shadow;
-                        trace_ray<I16>(A.hf, sp.radius, S, 0.0, true, 2, sh, cnt);
-                        if (sh.hit) { vis = 0.0; ++n_occl; }
-                    }
-                    const float3 alb = sample_albedo(A.tex, hi.lon, hi.lat);
-                    const double q = sp.light_radius / dist;
-                    const float E = (float)(sp.light_radiance * q * q * cosl * vis);
-                    rgb = make_float3(alb.x * E, alb.y * E, alb.z * E);
-                }
-                if (sm == A.sample0 && A.hit) {
-                    // scene = pos + R^T p_body
-                    const float hx = (float)(sp.pos[0] + sp.ex[0] * px + sp.ey[0] * py + sp.ez[0] * pz);
-                    const float hy = (float)(sp.pos[1] + sp.ex[1] * px + sp.ey[1] * py + sp.ez[1] * pz);
-                    const float hz = (float)(sp.pos[2] + sp.ex[2] * px + sp.ey[2] * py + sp.ez[2] * pz);
-                    A.hit[(size_t)y * A.width + x] = make_float4(hx, hy, hz, (float)h.s);
-                }
-                if (A.hit64) A.hit64[(size_t)y * A.width + x] = make_double4(h.s, hi.r, hi.lon, hi.lat);
+                acc.x += lit.x; acc.y += lit.y; acc.z += lit.z;
             } else {
-                if (sm == A.sample0 && A.hit) A.hit[(size_t)y * A.width + x] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (A.hit64) A.hit64[(size_t)y * A.width + x] = make_double4(-1.0, 0.0, 0.0, 0.0);
+                write_miss(A, x, y, sm == A.sample0);
             }
-            acc.x += rgb.x; acc.y += rgb.y; acc.z += rgb.z;
         }
         float4* ap = A.accum + (size_t)y * A.width + x;
         float4 old = *ap;
         old.x += acc.x; old.y += acc.y; old.z += acc.z; old.w += (float)A.nsamples;
         *ap = old;
     }
-    // counters: one atomic per warp and counter
-    unsigned vals[8] = {n_primary, n_inside, n_hit, n_shadow, n_occl, cnt.nodes, cnt.tests, cnt.overflow};
+    flush_counters(A, rs, cnt, (threadIdx.y * blockDim.x + threadIdx.x) & 31);
+}
+
+// ---- production kernel: persistent warps, per-lane ray state machine, dynamic refill ---------------------
+// Rays differ wildly in cost (64 % of a whole-disk frame misses the Moon, limb and terminator rays walk
+// hundreds of cells), so a pixel->thread mapping leaves most lanes idle.  Here every lane owns one pixel
+// at a time and steps a small state machine; idle lanes are refilled from a global pixel counter (one
+// atomic per warp and refill), and the warp alternates between phases that all active lanes can share:
+//   START (ray generation + sphere clip)  ->  TRAV (float32 pyramid steps, primary and shadow rays alike)
+//   ->  CAND (float64 exact patch test [+ shading, shadow-ray set-up])  ->  next sample / next pixel.
+enum { M_IDLE = 0, M_START = 1, M_TRAV = 2, M_CAND = 3 };
+constexpr int TRAV_BURST = 8;
+
+template <bool I16>
+__global__ void __launch_bounds__(128, 3)
+trace_kernel_persistent(const __grid_constant__ RenderArgs A) {
+    const int lane = threadIdx.x & 31;
+    const int rw = A.x1 - A.x0, rh = A.y1 - A.y0;
+    const unsigned tiles_x = (unsigned)(rw + 7) / 8u, tiles_y = (unsigned)(rh + 3) / 4u;
+    const unsigned total = tiles_x * tiles_y * 32u;
+    const float Rf = (float)A.sp.radius;
+    // a pixel whose centre ray passes the bounding sphere by more than this cannot touch it with any jitter
+    const double Rb = A.sp.radius * (double)A.hf.dmax;
+    const double eye_dist = sqrt(A.eye_b[0] * A.eye_b[0] + A.eye_b[1] * A.eye_b[1] + A.eye_b[2] * A.eye_b[2]);
+    const double cull_r = Rb + eye_dist * 3.0 * A.cam.tan_half_fov / A.height;
+
+    Counters cnt = {0u, 0u, 0u};
+    RayStats rs = {0u, 0u, 0u, 0u, 0u};
+    int mode = M_IDLE;
+    bool shadow = false, exhausted = false;
+    int x = 0, y = 0;
+    uint32_t pixel = 0;
+    unsigned sm = 0;
+    float3 acc = make_float3(0.f, 0.f, 0.f), lit = make_float3(0.f, 0.f, 0.f);
+    Ray64 R;
+    TravState st;
+    Patch P;
+    float sx = 0.f;
+    int face = 4;
+
+    for (;;) {
+        // ---- refill idle lanes ------------------------------------------------------------------
+        const unsigned idle = __ballot_sync(0xffffffffu, mode == M_IDLE);
+        if (idle == 0xffffffffu && exhausted) break;
+        if (idle && !exhausted) {
+            const int n = __popc(idle);
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(A.work_counter, (unsigned)n);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base + (unsigned)n >= total) exhausted = true;
+            if (mode == M_IDLE) {
+                const unsigned p = base + (unsigned)__popc(idle & ((1u << lane) - 1u));
+                if (p < total) {
+                    const unsigned tile = p >> 5, within = p & 31u;
+                    x = A.x0 + (int)(tile % tiles_x) * 8 + (int)(within & 7u);
+                    y = A.y0 + (int)(tile / tiles_x) * 4 + (int)(within >> 3);
+                    if (x < A.x1 && y < A.y1) {
+                        pixel = (uint32_t)y * (uint32_t)A.width + (uint32_t)x;
+                        sm = A.sample0;
+                        acc = make_float3(0.f, 0.f, 0.f);
+                        mode = M_START;
+                        // whole-pixel cull against the bounding sphere
+                        Ray64 C;
+                        const unsigned jit = 0;
+                        (void)jit;
+                        {
+                            const Camera& cam = A.cam;
+                            const double aspect = (double)A.width / (double)A.height;
+                            const double cx = ((x + 0.5) / A.width * 2.0 - 1.0) * cam.tan_half_fov * aspect;
+                            const double cy = (1.0 - (y + 0.5) / A.height * 2.0) * cam.tan_half_fov;
+                            double d[3];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const unsigned v = __reduce_add_sync(0xffffffffu, vals[i]);
-        if (((threadIdx.y * blockDim.x + threadIdx.x) & 31) == 0 && v) atomicAdd(&A.counters[i], (unsigned long long)v);
+                            for (int a = 0; a < 3; ++a) d[a] = cam.w[a] + cx * cam.right[a] + cy * cam.up[a];
+                            const double dn = 1.0 / sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+                            C.dx = (A.sp.ex[0] * d[0] + A.sp.ex[1] * d[1] + A.sp.ex[2] * d[2]) * dn;
+                            C.dy = (A.sp.ey[0] * d[0] + A.sp.ey[1] * d[1] + A.sp.ey[2] * d[2]) * dn;
+                            C.dz = (A.sp.ez[0] * d[0] + A.sp.ez[1] * d[1] + A.sp.ez[2] * d[2]) * dn;
+                            const double od = A.eye_b[0] * C.dx + A.eye_b[1] * C.dy + A.eye_b[2] * C.dz;
+                            const double d2 = eye_dist * eye_dist - od * od;
+                            if (d2 > cull_r * cull_r || od > 0.0 && eye_dist > Rb) {
+                                // every sample of this pixel misses
+                                rs.primary += A.nsamples;
+                                write_miss(A, x, y, true);
+                                float4* ap = A.accum + (size_t)y * A.width + x;
+                                float4 old = *ap;
+                                old.w += (float)A.nsamples;
+                                *ap = old;
+                                mode = M_IDLE;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+
+        // ---- START: generate the next primary ray, clip it to the bounding sphere ----------------------
+        if (mode == M_START) {
+            primary_ray(A, x, y, pixel, sm, R);
+            ++rs.primary;
+            shadow = false;
+            if (trav_begin(A.hf, A.sp.radius, R, 0.0, A.hf.top - 3, st)) { mode = M_TRAV; ++rs.inside; }
+            else {
+                write_miss(A, x, y, sm == A.sample0);
+                if (++sm < A.sample0 + A.nsamples) mode = M_START;
+                else {
+                    float4* ap = A.accum + (size_t)y * A.width + x;
+                    float4 old = *ap;
+                    old.x += acc.x; old.y += acc.y; old.z += acc.z; old.w += (float)A.nsamples;
+                    *ap = old;
+                    mode = M_IDLE;
+                }
+            }
+        }
+
+        // ---- TRAV: a burst of pyramid steps shared by primary and shadow rays ---------------------------
+        bool done_sample = false;
+#pragma unroll 1
+        for (int it = 0; it < TRAV_BURST; ++it) {
+            if (mode == M_TRAV) {
+                const int r = trav_step<I16>(A.hf, Rf, st, P, sx, face, cnt);
+                if (r == TR_CANDIDATE) mode = M_CAND;
+                else if (r == TR_END) {
+                    // primary: missed the terrain; shadow: the sun is visible
+                    if (shadow) { acc.x += lit.x; acc.y += lit.y; acc.z += lit.z; }
+                    else write_miss(A, x, y, sm == A.sample0);
+                    done_sample = true;
+                    mode = M_IDLE;
+                }
+            }
+            if (__ballot_sync(0xffffffffu, mode == M_TRAV) == 0u) break;
+        }
+
+        // ---- CAND: exact patch test; a primary hit is shaded and may spawn its shadow ray -------------
+        if (mode == M_CAND) {
+            TraceOut h;
+            h.hit = false;
+            if (exact_test<I16>(A.hf, A.sp.radius, R, st, P, sx, !shadow, h, cnt)) {
+                if (shadow) { ++rs.occluded; done_sample = true; mode = M_IDLE; }
+                else {
+                    ++rs.hits;
+                    Ray64 S;
+                    const bool need_shadow = shade_hit(A, R, h, x, y, pixel, sm, lit, S);
+                    if (need_shadow) {
+                        ++rs.shadow;
+                        R = S;
+                        shadow = true;
+                        if (trav_begin(A.hf, A.sp.radius, R, 0.0, 2, st)) mode = M_TRAV;
+                        else { acc.x += lit.x; acc.y += lit.y; acc.z += lit.z; done_sample = true; mode = M_IDLE; }
+                    } else {
+                        acc.x += lit.x; acc.y += lit.y; acc.z += lit.z;
+                        done_sample = true; mode = M_IDLE;
+                    }
+                }
+            } else {
+                if (trav_advance(A.hf, st, sx, face)) mode = M_TRAV;
+                else {
+                    if (shadow) { acc.x += lit.x; acc.y += lit.y; acc.z += lit.z; }
+                    else write_miss(A, x, y, sm == A.sample0);
+                    done_sample = true; mode = M_IDLE;
+                }
+            }
+        }
+
+        // ---- sample finished: next sample of the same pixel, or retire the pixel ----------------------------
+        if (done_sample) {
+            if (++sm < A.sample0 + A.nsamples) mode = M_START;
+            else {
+                float4* ap = A.accum + (size_t)y * A.width + x;
+                float4 old = *ap;
+                old.x += acc.x; old.y += acc.y; old.z += acc.z; old.w += (float)A.nsamples;
+                *ap = old;
+                mode = M_IDLE;
+            }
+        }
     }
+    flush_counters(A, rs, cnt, lane);
 }
 
 // K8: Gamma post-process + Overlay alpha blend -> RGBA8
@@ -227,6 +419,12 @@ __global__ void resolve_kernel(const float4* __restrict__ accum, const uchar4* _
 
 }  // namespace
 
+static void to_body(const SceneParams& sp, const double* v, double* out) {
+    out[0] = sp.ex[0] * v[0] + sp.ex[1] * v[1] + sp.ex[2] * v[2];
+    out[1] = sp.ey[0] * v[0] + sp.ey[1] * v[1] + sp.ey[2] * v[2];
+    out[2] = sp.ez[0] * v[0] + sp.ez[1] * v[1] + sp.ez[2] * v[2];
+}
+
 int launch_trace(mrtx_ctx* ctx, int x0, int y0, int x1, int y1, unsigned s0, unsigned ns) {
     RenderArgs A;
     A.hf = ctx->hf; A.tex = ctx->tex[0]; A.cam = ctx->cam; A.sp = ctx->sp;
@@ -236,10 +434,29 @@ int launch_trace(mrtx_ctx* ctx, int x0, int y0, int x1, int y1, unsigned s0, uns
     A.accum = ctx->accum; A.hit = ctx->hit;
     A.hit64 = ctx->sp.debug_hits ? ctx->hit64 : nullptr;
     A.counters = ctx->d_counters;
-    const dim3 block(8, 16);
-    const dim3 grid((x1 - x0 + block.x - 1) / block.x, (y1 - y0 + block.y - 1) / block.y);
-    if (ctx->hf.is_i16) trace_kernel<true><<<grid, block, 0, ctx->stream>>>(A);
-    else                trace_kernel<false><<<grid, block, 0, ctx->stream>>>(A);
+    A.work_counter = ctx->d_max_bits + 1;        // second word of the context's scratch pair
+    const double er[3] = {A.cam.eye[0] - A.sp.pos[0], A.cam.eye[1] - A.sp.pos[1], A.cam.eye[2] - A.sp.pos[2]};
+    const double lr[3] = {A.sp.light_pos[0] - A.sp.pos[0], A.sp.light_pos[1] - A.sp.pos[1], A.sp.light_pos[2] - A.sp.pos[2]};
+    to_body(A.sp, er, A.eye_b);
+    to_body(A.sp, lr, A.light_b);
+    if (ctx->sp.kernel == 0) {
+        const dim3 block(8, 16);
+        const dim3 grid((x1 - x0 + block.x - 1) / block.x, (y1 - y0 + block.y - 1) / block.y);
+        if (ctx->hf.is_i16) trace_kernel_simple<true><<<grid, block, 0, ctx->stream>>>(A);
+        else                trace_kernel_simple<false><<<grid, block, 0, ctx->stream>>>(A);
+    } else {
+        MRTX_CUDA(cudaMemsetAsync(A.work_counter, 0, sizeof(unsigned), ctx->stream));
+        int per_sm = 0;
+        if (ctx->hf.is_i16) MRTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel_persistent<true>, 128, 0));
+        else                MRTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel_persistent<false>, 128, 0));
+        if (per_sm < 1) per_sm = 1;
+        const long long warps_needed = ((long long)(x1 - x0) * (y1 - y0) + 31) / 32;
+        long long blocks = (long long)ctx->sm_count * per_sm;
+        if (blocks * 4 > warps_needed) blocks = (warps_needed + 3) / 4;
+        if (blocks < 1) blocks = 1;
+        if (ctx->hf.is_i16) trace_kernel_persistent<true><<<(unsigned)blocks, 128, 0, ctx->stream>>>(A);
+        else                trace_kernel_persistent<false><<<(unsigned)blocks, 128, 0, ctx->stream>>>(A);
+    }
     MRTX_CUDA(cudaGetLastError());
     return MRTX_OK;
 }

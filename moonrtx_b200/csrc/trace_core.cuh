@@ -323,141 +323,179 @@ MRTX_HD float cell_exit32(const HeightField& hf, const Trav& T, int L, int J, in
 
 struct TraceOut { bool hit; double s; HitInfo info; Patch patch; };
 
-// First intersection of the body-frame ray for s >= s_min.  any_hit: stop at any intersection.
+// Traversal state of one ray (float32, re-based at the bounding-sphere entry s_in).
+struct TravState {
+    Trav T;
+    float s;                 // current parameter (relative to s_in)
+    int L, J, I;             // current cell
+    int steps;
+    double s_in, s_end, s_min;
+};
+
+enum { TR_CONTINUE = 0, TR_CANDIDATE = 1, TR_END = 2 };
+
+// Clip the ray to the bounding sphere R * dmax and find its first cell.  false = misses the Moon.
+MRTX_HD inline bool trav_begin(const HeightField& hf, double radius, const Ray64& R, double s_min, int start_level,
+                               TravState& st) {
+    const double Rb = radius * (double)hf.dmax;
+    const double disc = R.od * R.od - (R.oo - Rb * Rb);
+    if (disc < 0.0) return false;
+    const double sq = sqrt(disc);
+    const double s_end = -R.od + sq;
+    if (s_end <= s_min) return false;
+    const double s_in = fmax(s_min, -R.od - sq);
+    st.s_in = s_in; st.s_end = s_end; st.s_min = s_min;
+    Trav& T = st.T;
+    const double bx = R.ox + s_in * R.dx, by = R.oy + s_in * R.dy, bz = R.oz + s_in * R.dz;
+    T.ox = (float)bx; T.oy = (float)by; T.oz = (float)bz;
+    T.dx = (float)R.dx; T.dy = (float)R.dy; T.dz = (float)R.dz;
+    T.oo = T.ox * T.ox + T.oy * T.oy + T.oz * T.oz;
+    T.od = T.ox * T.dx + T.oy * T.dy + T.oz * T.dz;
+    T.smax = (float)(s_end - s_in);
+    const int W = hf.W, H = hf.H;
+    const int L = min(max(start_level, 0), hf.top);
+    // first cell from the position just inside (a wrong neighbour is corrected by the exit rules)
+    const float t0 = fminf(1e-5f * (float)radius, 0.5f * T.smax);
+    const float x = fmaf(t0, T.dx, T.ox), y = fmaf(t0, T.dy, T.oy), z = fmaf(t0, T.dz, T.oz);
+    const float lon = atan2f(x, -y), lat = atan2f(z, sqrtf(x * x + y * y));
+    const float u = (lon * (0.5f / PI_F) + 0.5f) * (float)W - 0.5f, v = (0.5f - lat * (1.0f / PI_F)) * (float)H - 0.5f;
+    int c0 = (int)floorf(u);
+    c0 = c0 < 0 ? c0 + W : (c0 >= W ? c0 - W : c0);
+    const int r0 = min(max((int)floorf(v), 0), H - 2);
+    st.L = L; st.J = r0 >> L; st.I = c0 >> L;
+    st.s = 0.0f; st.steps = 0;
+    return true;
+}
+
+// Hand the ray to the neighbour across `face` (ascending one level when a parent wall is crossed).
+// false = the ray has left the bounding sphere.
+MRTX_HD inline bool trav_advance(const HeightField& hf, TravState& st, float sx, int face) {
+    if (face == 4) return false;
+    st.s = sx;
+    int L = st.L, J = st.J, I = st.I;
+    bool up;
+    if (face == 1)      { I += 1; if (I >= hf.nx[L]) I = 0; up = (I & 1) == 0; }
+    else if (face == 0) { up = (I & 1) == 0; I -= 1; if (I < 0) I = hf.nx[L] - 1; }
+    else if (face == 3) { J += 1; up = (J & 1) == 0; }
+    else                { up = (J & 1) == 0; J -= 1; }
+    if (J < 0 || J >= hf.ny[L]) return false;                // cannot happen (caps have no wall); be safe
+    if (up && L < hf.top) { L += 1; I >>= 1; J >>= 1; }
+    st.L = L; st.J = J; st.I = I;
+    return true;
+}
+
+// One node visit.  TR_CANDIDATE: the current cell is a level-0 patch the ray may hit - P, sx, face
+// describe it and the caller runs exact_test() then trav_advance().  TR_CONTINUE: skipped, advanced
+// or descended.  TR_END: left the sphere (or ran out of steps: counted in cnt.overflow).
+template <bool I16>
+MRTX_HD inline int trav_step(const HeightField& hf, float Rf, TravState& st, Patch& P, float& sx_out, int& face_out,
+                             Counters& cnt) {
+    if (++st.steps > MAX_STEPS) { ++cnt.overflow; return TR_END; }
+    const Trav& T = st.T;
+    const int L = st.L, J = st.J, I = st.I;
+    const float s = st.s;
+    int face;
+    const float sx = fmaxf(cell_exit32(hf, T, L, J, I, s, face), s);
+    ++cnt.nodes;
+    float dmax;                                              // max of the surface over this cell
+    if (L == 0) {
+        load_patch<I16>(hf, J, I, P);
+        dmax = fmaxf(fmaxf(P.d00, P.d01), fmaxf(P.d10, P.d11));
+    } else {
+        dmax = level_D<I16>(hf, L, J, I);
+    }
+    const float marg = 2.0e-6f * Rf;                         // > float32 error of a radius near R
+    const float rc = fmaf(Rf, dmax, marg);
+    MRTX_DBG("step %d L%d J%d I%d s=%.7f sx=%.7f face=%d dmax=%.7f r(s)=%.7f\n", st.steps, L, J, I, s, sx, face, dmax, sqrtf(ray_r2(T, s)));
+    // min radius of the ray over [s, sx] (with a little slack either side)
+    const float pad = 4.0e-6f * Rf;
+    const float ta = fmaxf(s - pad, 0.0f), tb = fminf(sx + pad, T.smax);
+    const float tm = fminf(fmaxf(-T.od, ta), tb);
+    if (ray_r2(T, tm) <= rc * rc) {
+        if (L == 0) { sx_out = sx; face_out = face; return TR_CANDIDATE; }
+        // move up to where the ray enters the cell's shell, then pick the child there
+        float sd = s;
+        if (ray_r2(T, s) > rc * rc) {
+            const float dq = T.od * T.od - (T.oo - rc * rc);
+            if (dq > 0.0f) sd = fminf(fmaxf(-T.od - sqrtf(dq), s), sx);
+        }
+        const float x = fmaf(sd, T.dx, T.ox), y = fmaf(sd, T.dy, T.oy), z = fmaf(sd, T.dz, T.oz);
+        const int mi = (2 * I + 1) << (L - 1), mj = (2 * J + 1) << (L - 1);
+        int ci = 2 * I, cj = 2 * J;
+        if (mi < min((I + 1) << L, hf.W)) {
+            const float2 wl = MRTX_LDG(hf.lon32 + mi);
+            if (x * wl.x + y * wl.y >= 0.0f) ci += 1;
+        }
+        if (mj < min((J + 1) << L, hf.H - 1)) {
+            const float k = MRTX_LDG(hf.lat32 + mj);
+            if (z - k * sqrtf(x * x + y * y + z * z) < 0.0f) cj += 1;     // south of the mid wall
+        }
+        st.s = sd; st.L = L - 1; st.I = ci; st.J = cj;
+        return TR_CONTINUE;
+    }
+    return trav_advance(hf, st, sx, face) ? TR_CONTINUE : TR_END;
+}
+
+// Exact float64 test of a candidate patch (window [st.s, sx] of the float32 walk).  On a hit fills
+// `out` (out.info only when want_info).
+template <bool I16>
+MRTX_HD inline bool exact_test(const HeightField& hf, double radius, const Ray64& R, const TravState& st, Patch P,
+                               float sx, bool want_info, TraceOut& out, Counters& cnt) {
+    const int W = hf.W, H = hf.H;
+    ++cnt.tests;
+    const double big = 3.0e-3 * radius, small = 2.0e-5 * radius;
+    const double sa = st.s_in + (double)st.s, sb = st.s_in + (double)sx;
+    const double wa = fmax(sa - big, st.s_min), wb = fmin(sb + big, st.s_end);
+    double sh;
+    int ef = -1;
+    int code = cell_test64(hf, R, P, radius, wa, wb, sa - small, sb + small, &sh, &ef);
+    // Entered the cell already below the surface: the first crossing lies in a cell the float32
+    // walk skipped (ray within rounding of a wall or a corner).  Walk back through the neighbours
+    // across the entry walls, in float64, until it is found.
+    for (int back = 0; code == 2 && back < 16; ++back) {
+        int r0 = P.r0, c0 = P.c0;
+        if (ef == 0) c0 = c0 == 0 ? W - 1 : c0 - 1;
+        else if (ef == 1) c0 = c0 + 1 == W ? 0 : c0 + 1;
+        else if (ef == 2) r0 -= 1;
+        else r0 += 1;
+        if (r0 < 0 || r0 > H - 2) break;
+        Patch Q;
+        load_patch<I16>(hf, r0, c0, Q);
+        ++cnt.tests;
+        double sq2;
+        int ef2 = -1;
+        const double tiny = 1.0e-9 * radius;
+        const int c2 = cell_test64(hf, R, Q, radius, fmax(sh - big, st.s_min), fmin(sh + small, st.s_end),
+                                   sh - small, sh - tiny, &sq2, &ef2);
+        if (c2 == 0) break;                                  // surface continuous: should not happen
+        P = Q; sh = sq2; ef = ef2; code = c2;
+    }
+    if (code == 0) return false;
+    out.hit = true; out.s = sh; out.patch = P;
+    if (want_info) { Cell64 C; load_cell64(hf, P, C); patch_f(R, P, C, W, H, radius, sh, &out.info); }
+    return true;
+}
+
+// First intersection of the body-frame ray for s >= s_min (sequential form of the three pieces
+// above; the render kernel interleaves them across a warp).  any_hit: stop at any intersection.
 template <bool I16>
 MRTX_HD void trace_ray(const HeightField& hf, double radius, const Ray64& R, double s_min, bool any_hit,
                        int start_level, TraceOut& out, Counters& cnt) {
     out.hit = false;
-    const double Rb = radius * (double)hf.dmax;
-    const double disc = R.od * R.od - (R.oo - Rb * Rb);
-    if (disc < 0.0) return;
-    const double sq = sqrt(disc);
-    const double s_end = -R.od + sq;
-    if (s_end <= s_min) return;
-    const double s_in = fmax(s_min, -R.od - sq);
-
-    Trav T;
-    {
-        const double bx = R.ox + s_in * R.dx, by = R.oy + s_in * R.dy, bz = R.oz + s_in * R.dz;
-        T.ox = (float)bx; T.oy = (float)by; T.oz = (float)bz;
-        T.dx = (float)R.dx; T.dy = (float)R.dy; T.dz = (float)R.dz;
-        T.oo = T.ox * T.ox + T.oy * T.oy + T.oz * T.oz;
-        T.od = T.ox * T.dx + T.oy * T.dy + T.oz * T.dz;
-        T.smax = (float)(s_end - s_in);
-    }
+    TravState st;
+    if (!trav_begin(hf, radius, R, s_min, start_level, st)) return;
     const float Rf = (float)radius;
-    const float marg = 2.0e-6f * Rf;                             // > float32 error of a radius near R
-    const int W = hf.W, H = hf.H;
-
-    // start cell at the top level, from the position just inside
-    int L = min(max(start_level, 0), hf.top), J, I;
-    {
-        const float t0 = fminf(1e-5f * Rf, 0.5f * T.smax);
-        const float x = fmaf(t0, T.dx, T.ox), y = fmaf(t0, T.dy, T.oy), z = fmaf(t0, T.dz, T.oz);
-        const float lon = atan2f(x, -y), lat = atan2f(z, sqrtf(x * x + y * y));
-        const float u = (lon * (0.5f / PI_F) + 0.5f) * (float)W - 0.5f, v = (0.5f - lat * (1.0f / PI_F)) * (float)H - 0.5f;
-        int c0 = (int)floorf(u);
-        c0 = c0 < 0 ? c0 + W : (c0 >= W ? c0 - W : c0);
-        const int r0 = min(max((int)floorf(v), 0), H - 2);
-        J = r0 >> L; I = c0 >> L;
-    }
-
-    float s = 0.0f;
-    for (int step = 0; step < MAX_STEPS; ++step) {
-        int face;
-        const float sx_raw = cell_exit32(hf, T, L, J, I, s, face);
-        const float sx = fmaxf(sx_raw, s);
-        ++cnt.nodes;
-
-        // max radius of the surface over this cell
-        float dmax;
+    for (;;) {
         Patch P;
-        if (L == 0) {
-            load_patch<I16>(hf, J, I, P);
-            dmax = fmaxf(fmaxf(P.d00, P.d01), fmaxf(P.d10, P.d11));
-        } else {
-            dmax = level_D<I16>(hf, L, J, I);
-        }
-        const float rc = fmaf(Rf, dmax, marg);
-        MRTX_DBG("step %d L%d J%d I%d s=%.7f sx_raw=%.7f face=%d dmax=%.7f r(s)=%.7f\n", step, L, J, I, s, sx_raw, face, dmax, sqrtf(ray_r2(T, s)));
-        // min radius of the ray over [s, sx] (with a little slack either side)
-        const float pad = 4.0e-6f * Rf;
-        const float ta = fmaxf(s - pad, 0.0f), tb = fminf(sx + pad, T.smax);
-        const float tm = fminf(fmaxf(-T.od, ta), tb);
-        const float rmin2 = ray_r2(T, tm);
-
-        bool advance = true;
-        if (rmin2 <= rc * rc) {
-            if (L > 0) {
-                // move up to where the ray enters the cell's shell, then pick the child there
-                float sd = s;
-                if (ray_r2(T, s) > rc * rc) {
-                    const float dq = T.od * T.od - (T.oo - rc * rc);
-                    if (dq > 0.0f) sd = fminf(fmaxf(-T.od - sqrtf(dq), s), sx);
-                }
-                const float x = fmaf(sd, T.dx, T.ox), y = fmaf(sd, T.dy, T.oy), z = fmaf(sd, T.dz, T.oz);
-                const int mi = (2 * I + 1) << (L - 1), mj = (2 * J + 1) << (L - 1);
-                int ci = 2 * I, cj = 2 * J;
-                if (mi < min((I + 1) << L, W)) {
-                    const float2 wl = MRTX_LDG(hf.lon32 + mi);
-                    if (x * wl.x + y * wl.y >= 0.0f) ci += 1;
-                }
-                if (mj < min((J + 1) << L, H - 1)) {
-                    const float k = MRTX_LDG(hf.lat32 + mj);
-                    if (z - k * sqrtf(x * x + y * y + z * z) < 0.0f) cj += 1;     // south of the mid wall
-                }
-                s = sd; L -= 1; I = ci; J = cj;
-                advance = false;
-            } else {
-                ++cnt.tests;
-                const double big = 3.0e-3 * radius, small = 2.0e-5 * radius;
-                const double sa = s_in + (double)s, sb = s_in + (double)sx;
-                const double wa = fmax(sa - big, s_min), wb = fmin(sb + big, s_end);
-                double sh;
-                int ef = -1;
-                int code = cell_test64(hf, R, P, radius, wa, wb, sa - small, sb + small, &sh, &ef);
-                // Entered the cell already below the surface: the first crossing lies in a cell the
-                // float32 walk skipped (ray within rounding of a wall or a corner).  Walk back
-                // through the neighbours across the entry walls, in float64, until it is found.
-                for (int back = 0; code == 2 && back < 16; ++back) {
-                    int r0 = P.r0, c0 = P.c0;
-                    if (ef == 0) c0 = c0 == 0 ? W - 1 : c0 - 1;
-                    else if (ef == 1) c0 = c0 + 1 == W ? 0 : c0 + 1;
-                    else if (ef == 2) r0 -= 1;
-                    else r0 += 1;
-                    if (r0 < 0 || r0 > H - 2) break;
-                    Patch Q;
-                    load_patch<I16>(hf, r0, c0, Q);
-                    ++cnt.tests;
-                    double sq2;
-                    int ef2 = -1;
-                    const double tiny = 1.0e-9 * radius;
-                    const int c2 = cell_test64(hf, R, Q, radius, fmax(sh - big, s_min), fmin(sh + small, s_end),
-                                               sh - small, sh - tiny, &sq2, &ef2);
-                    if (c2 == 0) break;                          // surface continuous: should not happen
-                    P = Q; sh = sq2; ef = ef2; code = c2;
-                }
-                if (code != 0) {
-                    out.hit = true; out.s = sh; out.patch = P;
-                    if (!any_hit) { Cell64 C; load_cell64(hf, P, C); patch_f(R, P, C, W, H, radius, sh, &out.info); }
-                    return;
-                }
-            }
-        }
-        if (advance) {
-            if (face == 4) return;                               // left the bounding sphere
-            s = sx;
-            bool up;
-            if (face == 1)      { I += 1; if (I >= hf.nx[L]) I = 0; up = (I & 1) == 0; }
-            else if (face == 0) { up = (I & 1) == 0; I -= 1; if (I < 0) I = hf.nx[L] - 1; }
-            else if (face == 3) { J += 1; up = (J & 1) == 0; }
-            else                { up = (J & 1) == 0; J -= 1; }
-            if (J < 0 || J >= hf.ny[L]) return;                  // cannot happen (caps have no wall); be safe
-            if (up && L < hf.top) { L += 1; I >>= 1; J >>= 1; }
+        float sx;
+        int face;
+        const int r = trav_step<I16>(hf, Rf, st, P, sx, face, cnt);
+        if (r == TR_END) return;
+        if (r == TR_CANDIDATE) {
+            if (exact_test<I16>(hf, radius, R, st, P, sx, !any_hit, out, cnt)) return;
+            if (!trav_advance(hf, st, sx, face)) return;
         }
     }
-    ++cnt.overflow;                                              // step budget exhausted: reported as a miss
 }
-
 
 }  // namespace mrtx_core
