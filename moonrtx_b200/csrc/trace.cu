@@ -131,7 +131,7 @@ __device__ __forceinline__ bool shade_hit(const RenderArgs& A, const Ray64& R, c
         const double b2x = b, b2y = sg + cy * cy * a, b2z = -cy;
         const double rr = sp.light_radius * sqrt(rnd(pixel, sm, 2)), th = 2.0 * PI_D * rnd(pixel, sm, 3);
         double st, ct;
-        sincos(th, &st, &ct);
+        sincospi(2.0 * rnd(pixel, sm, 3), &st, &ct);      // = sincos(th), without the library's huge-argument path
         gx += rr * (ct * b1x + st * b2x); gy += rr * (ct * b1y + st * b2y); gz += rr * (ct * b1z + st * b2z);
     }
     double lx = gx - px, ly = gy - py, lz = gz - pz;
@@ -222,8 +222,8 @@ trace_kernel_simple(const __grid_constant__ RenderArgs A) {
 // atomic per warp and refill), and the warp alternates between phases that all active lanes can share:
 //   START (ray generation + sphere clip)  ->  TRAV (float32 pyramid steps, primary and shadow rays alike)
 //   ->  CAND (float64 exact patch test [+ shading, shadow-ray set-up])  ->  next sample / next pixel.
-enum { M_IDLE = 0, M_START = 1, M_TRAV = 2, M_CAND = 3 };
-constexpr int TRAV_BURST = 8;
+enum { M_IDLE = 0, M_START = 1, M_TRAV = 2, M_CAND = 3, M_BEGIN = 4 };
+constexpr int TRAV_BURST = 16;
 
 template <bool I16>
 __global__ void __launch_bounds__(128, 3)
@@ -252,16 +252,34 @@ trace_kernel_persistent(const __grid_constant__ RenderArgs A) {
     float sx = 0.f;
     int face = 4;
 
+    auto retire_sample = [&]() {
+        // next sample of the same pixel, or write the pixel back and free the lane
+        if (++sm < A.sample0 + A.nsamples) mode = M_START;
+        else {
+            float4* ap = A.accum + (size_t)y * A.width + x;
+            float4 old = *ap;
+            old.x += acc.x; old.y += acc.y; old.z += acc.z; old.w += (float)A.nsamples;
+            *ap = old;
+            mode = M_IDLE;
+        }
+    };
+
     for (;;) {
-        // ---- refill idle lanes ------------------------------------------------------------------
-        const unsigned idle = __ballot_sync(0xffffffffu, mode == M_IDLE);
-        if (idle == 0xffffffffu && exhausted) break;
-        if (idle && !exhausted) {
-            const int n = __popc(idle);
+        // Phase census.  Whatever phase most lanes are waiting for runs next, so the expensive phases
+        // (float64 patch tests) execute with many lanes at once instead of whenever one lane needs them.
+        int n_idle = __popc(__ballot_sync(0xffffffffu, mode == M_IDLE));
+        int n_start = __popc(__ballot_sync(0xffffffffu, mode == M_START || mode == M_BEGIN));
+        int n_trav = __popc(__ballot_sync(0xffffffffu, mode == M_TRAV));
+        int n_cand = __popc(__ballot_sync(0xffffffffu, mode == M_CAND));
+        if (n_idle == 32 && exhausted) break;
+
+        // ---- refill idle lanes (batched: at least a quarter warp, or nothing else left to run) ---------
+        if (!exhausted && n_idle > 0 && (n_idle >= 8 || n_idle + n_start == 32 || n_trav + n_cand == 0)) {
+            const unsigned idle = __ballot_sync(0xffffffffu, mode == M_IDLE);
             unsigned base = 0;
-            if (lane == 0) base = atomicAdd(A.work_counter, (unsigned)n);
+            if (lane == 0) base = atomicAdd(A.work_counter, (unsigned)n_idle);
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (base + (unsigned)n >= total) exhausted = true;
+            if (base + (unsigned)n_idle >= total) exhausted = true;
             if (mode == M_IDLE) {
                 const unsigned p = base + (unsigned)__popc(idle & ((1u << lane) - 1u));
                 if (p < total) {
@@ -273,117 +291,99 @@ trace_kernel_persistent(const __grid_constant__ RenderArgs A) {
                         sm = A.sample0;
                         acc = make_float3(0.f, 0.f, 0.f);
                         mode = M_START;
-                        // whole-pixel cull against the bounding sphere
-                        Ray64 C;
-                        const unsigned jit = 0;
-                        (void)jit;
-                        {
-                            const Camera& cam = A.cam;
-                            const double aspect = (double)A.width / (double)A.height;
-                            const double cx = ((x + 0.5) / A.width * 2.0 - 1.0) * cam.tan_half_fov * aspect;
-                            const double cy = (1.0 - (y + 0.5) / A.height * 2.0) * cam.tan_half_fov;
-                            double d[3];
+                        // whole-pixel cull against the bounding sphere (centre ray + 1.5 pixels of slack)
+                        const Camera& cam = A.cam;
+                        const double aspect = (double)A.width / (double)A.height;
+                        const double cx = ((x + 0.5) / A.width * 2.0 - 1.0) * cam.tan_half_fov * aspect;
+                        const double cy = (1.0 - (y + 0.5) / A.height * 2.0) * cam.tan_half_fov;
+                        double d[3];
 #pragma unroll
-                            for (int a = 0; a < 3; ++a) d[a] = cam.w[a] + cx * cam.right[a] + cy * cam.up[a];
-                            const double dn = 1.0 / sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-                            C.dx = (A.sp.ex[0] * d[0] + A.sp.ex[1] * d[1] + A.sp.ex[2] * d[2]) * dn;
-                            C.dy = (A.sp.ey[0] * d[0] + A.sp.ey[1] * d[1] + A.sp.ey[2] * d[2]) * dn;
-                            C.dz = (A.sp.ez[0] * d[0] + A.sp.ez[1] * d[1] + A.sp.ez[2] * d[2]) * dn;
-                            const double od = A.eye_b[0] * C.dx + A.eye_b[1] * C.dy + A.eye_b[2] * C.dz;
-                            const double d2 = eye_dist * eye_dist - od * od;
-                            if (d2 > cull_r * cull_r || od > 0.0 && eye_dist > Rb) {
-                                // every sample of this pixel misses
-                                rs.primary += A.nsamples;
-                                write_miss(A, x, y, true);
-                                float4* ap = A.accum + (size_t)y * A.width + x;
-                                float4 old = *ap;
-                                old.w += (float)A.nsamples;
-                                *ap = old;
-                                mode = M_IDLE;
-                            }
+                        for (int a = 0; a < 3; ++a) d[a] = cam.w[a] + cx * cam.right[a] + cy * cam.up[a];
+                        const double dn = 1.0 / sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+                        const double bx = (A.sp.ex[0] * d[0] + A.sp.ex[1] * d[1] + A.sp.ex[2] * d[2]) * dn;
+                        const double by = (A.sp.ey[0] * d[0] + A.sp.ey[1] * d[1] + A.sp.ey[2] * d[2]) * dn;
+                        const double bz = (A.sp.ez[0] * d[0] + A.sp.ez[1] * d[1] + A.sp.ez[2] * d[2]) * dn;
+                        const double od = A.eye_b[0] * bx + A.eye_b[1] * by + A.eye_b[2] * bz;
+                        const double d2 = eye_dist * eye_dist - od * od;
+                        if (eye_dist > cull_r && (d2 > cull_r * cull_r || od > 0.0)) {
+                            rs.primary += A.nsamples;                      // every sample of this pixel misses
+                            write_miss(A, x, y, true);
+                            float4* ap = A.accum + (size_t)y * A.width + x;
+                            float4 old = *ap;
+                            old.w += (float)A.nsamples;
+                            *ap = old;
+                            mode = M_IDLE;
                         }
                     }
                 }
             }
+            n_start = __popc(__ballot_sync(0xffffffffu, mode == M_START || mode == M_BEGIN));
         }
 
-        // ---- START: generate the next primary ray, clip it to the bounding sphere ----------------------
-        if (mode == M_START) {
-            primary_ray(A, x, y, pixel, sm, R);
-            ++rs.primary;
-            shadow = false;
-            if (trav_begin(A.hf, A.sp.radius, R, 0.0, A.hf.top - 3, st)) { mode = M_TRAV; ++rs.inside; }
-            else {
-                write_miss(A, x, y, sm == A.sample0);
-                if (++sm < A.sample0 + A.nsamples) mode = M_START;
-                else {
-                    float4* ap = A.accum + (size_t)y * A.width + x;
-                    float4 old = *ap;
-                    old.x += acc.x; old.y += acc.y; old.z += acc.z; old.w += (float)A.nsamples;
-                    *ap = old;
-                    mode = M_IDLE;
-                }
+        if (n_start > 0 && n_start >= n_trav && n_start >= n_cand) {
+            // ---- START: generate the next primary ray, clip it to the bounding sphere ----------------------
+            // (also where a freshly shaded hit starts its shadow ray: one trav_begin site)
+            if (mode == M_START) {
+                primary_ray(A, x, y, pixel, sm, R);
+                ++rs.primary;
+                shadow = false;
             }
-        }
-
-        // ---- TRAV: a burst of pyramid steps shared by primary and shadow rays ---------------------------
-        bool done_sample = false;
-#pragma unroll 1
-        for (int it = 0; it < TRAV_BURST; ++it) {
-            if (mode == M_TRAV) {
-                const int r = trav_step<I16>(A.hf, Rf, st, P, sx, face, cnt);
-                if (r == TR_CANDIDATE) mode = M_CAND;
-                else if (r == TR_END) {
-                    // primary: missed the terrain; shadow: the sun is visible
+            if (mode == M_START || mode == M_BEGIN) {
+                if (trav_begin(A.hf, A.sp.radius, R, 0.0, shadow ? 2 : A.hf.top - 3, st)) {
+                    mode = M_TRAV;
+                    if (!shadow) ++rs.inside;
+                } else {
                     if (shadow) { acc.x += lit.x; acc.y += lit.y; acc.z += lit.z; }
                     else write_miss(A, x, y, sm == A.sample0);
-                    done_sample = true;
-                    mode = M_IDLE;
+                    retire_sample();
                 }
             }
-            if (__ballot_sync(0xffffffffu, mode == M_TRAV) == 0u) break;
-        }
-
-        // ---- CAND: exact patch test; a primary hit is shaded and may spawn its shadow ray -------------
-        if (mode == M_CAND) {
-            TraceOut h;
-            h.hit = false;
-            if (exact_test<I16>(A.hf, A.sp.radius, R, st, P, sx, !shadow, h, cnt)) {
-                if (shadow) { ++rs.occluded; done_sample = true; mode = M_IDLE; }
-                else {
-                    ++rs.hits;
-                    Ray64 S;
-                    const bool need_shadow = shade_hit(A, R, h, x, y, pixel, sm, lit, S);
-                    if (need_shadow) {
-                        ++rs.shadow;
-                        R = S;
-                        shadow = true;
-                        if (trav_begin(A.hf, A.sp.radius, R, 0.0, 2, st)) mode = M_TRAV;
-                        else { acc.x += lit.x; acc.y += lit.y; acc.z += lit.z; done_sample = true; mode = M_IDLE; }
-                    } else {
-                        acc.x += lit.x; acc.y += lit.y; acc.z += lit.z;
-                        done_sample = true; mode = M_IDLE;
+        } else if (n_cand > 0 && n_cand >= n_trav) {
+            // ---- CAND: exact patch test; a primary hit is shaded and may spawn its shadow ray -------------
+            if (mode == M_CAND) {
+                TraceOut h;
+                h.hit = false;
+                if (exact_test<I16>(A.hf, A.sp.radius, R, st, P, sx, h, cnt)) {
+                    if (shadow) { ++rs.occluded; retire_sample(); }
+                    else {
+                        ++rs.hits;
+                        Ray64 S;
+                        const bool need_shadow = shade_hit(A, R, h, x, y, pixel, sm, lit, S);
+                        if (need_shadow) {
+                            ++rs.shadow;
+                            R = S;
+                            shadow = true;
+                            mode = M_BEGIN;
+                        } else {
+                            acc.x += lit.x; acc.y += lit.y; acc.z += lit.z;
+                            retire_sample();
+                        }
+                    }
+                } else {
+                    if (trav_advance(A.hf, st, sx, face)) mode = M_TRAV;
+                    else {
+                        if (shadow) { acc.x += lit.x; acc.y += lit.y; acc.z += lit.z; }
+                        else write_miss(A, x, y, sm == A.sample0);
+                        retire_sample();
                     }
                 }
-            } else {
-                if (trav_advance(A.hf, st, sx, face)) mode = M_TRAV;
-                else {
-                    if (shadow) { acc.x += lit.x; acc.y += lit.y; acc.z += lit.z; }
-                    else write_miss(A, x, y, sm == A.sample0);
-                    done_sample = true; mode = M_IDLE;
-                }
             }
-        }
-
-        // ---- sample finished: next sample of the same pixel, or retire the pixel ----------------------------
-        if (done_sample) {
-            if (++sm < A.sample0 + A.nsamples) mode = M_START;
-            else {
-                float4* ap = A.accum + (size_t)y * A.width + x;
-                float4 old = *ap;
-                old.x += acc.x; old.y += acc.y; old.z += acc.z; old.w += (float)A.nsamples;
-                *ap = old;
-                mode = M_IDLE;
+        } else if (n_trav > 0) {
+            // ---- TRAV: pyramid steps shared by primary and shadow rays, while they are the majority -------
+#pragma unroll 1
+            for (int it = 0; it < TRAV_BURST; ++it) {
+                if (mode == M_TRAV) {
+                    const int r = trav_step<I16>(A.hf, Rf, st, P, sx, face, cnt);
+                    if (r == TR_CANDIDATE) mode = M_CAND;
+                    else if (r == TR_END) {
+                        // primary: missed the terrain; shadow: the sun is visible
+                        if (shadow) { acc.x += lit.x; acc.y += lit.y; acc.z += lit.z; }
+                        else write_miss(A, x, y, sm == A.sample0);
+                        retire_sample();
+                    }
+                }
+                const int nt = __popc(__ballot_sync(0xffffffffu, mode == M_TRAV));
+                if (nt == 0 || nt < __popc(__ballot_sync(0xffffffffu, mode == M_CAND))) break;
             }
         }
     }

@@ -84,7 +84,14 @@ MRTX_HD inline void load_cell64(const HeightField& hf, const Patch& P, Cell64& C
 }
 
 // atan2(y, x) for x > 0; the angles met here are at most one texel wide, so the odd series is
-// exact to double rounding (|y/x| < 1/8: next term < 3e-18 relative)
+// exact to double rounding (|y/x| < 1/8: next term < 3e-18 relative).  Maps coarser than 64 x 32
+// texels take the library call, kept out of line so it does not bloat the hot loop.
+#ifdef __CUDA_ARCH__
+__device__ __noinline__ double atan_wide(double y, double x) { return atan2(y, x); }
+#else
+static double atan_wide(double y, double x) { return atan2(y, x); }
+#endif
+
 MRTX_HD inline double atan_small(double y, double x) {
     const double q = y / x, q2 = q * q;
     if (q2 < 0.015625) {
@@ -94,13 +101,13 @@ MRTX_HD inline double atan_small(double y, double x) {
         p = fma(p, q2, -1.0 / 3.0);  p = fma(p, q2, 1.0);
         return q * p;
     }
-    return atan2(y, x);
+    return atan_wide(y, x);
 }
 
 // f(s) = |p(s)| - R * bilinear(fc, fr): fc, fr = texel fractions measured from the cell's west
 // wall and from latitude row r0 as SMALL angles (no full-circle atan2, no cancellation)
 MRTX_HD inline double patch_f(const Ray64& R, const Patch& P, const Cell64& C, int W, int H, double radius, double s,
-                              HitInfo* info) {
+                              HitInfo& info) {
     const double x = fma(s, R.dx, R.ox), y = fma(s, R.dy, R.oy), z = fma(s, R.dz, R.oz);
     const double rho = sqrt(x * x + y * y);
     const double r = sqrt(rho * rho + z * z);
@@ -110,67 +117,82 @@ MRTX_HD inline double patch_f(const Ray64& R, const Patch& P, const Cell64& C, i
     const double top = fma(fc, (double)P.d01 - (double)P.d00, (double)P.d00);
     const double bot = fma(fc, (double)P.d11 - (double)P.d10, (double)P.d10);
     const double d = fma(fr, bot - top, top);
-    if (info) {
-        info->s = s; info->r = r; info->fc = fc; info->fr = fr_raw;
-        info->lon = ((P.c0 + 0.5 + fc) / W - 0.5) * (2.0 * PI_D);
-        info->lat = (0.5 - (P.r0 + 0.5 + fr_raw) / H) * PI_D;
-    }
+    info.s = s; info.r = r; info.fc = fc; info.fr = fr_raw;
     return fma(-radius, d, r);
+}
+
+MRTX_HD inline void finish_info(const Patch& P, int W, int H, HitInfo& info) {
+    info.lon = ((P.c0 + 0.5 + info.fc) / W - 0.5) * (2.0 * PI_D);
+    info.lat = (0.5 - (P.r0 + 0.5 + info.fr) / H) * PI_D;
 }
 
 // First root of f on [a, b] inside one patch (f is close to a parabola there: a bilinear patch
 // along a nearly straight (u, v) path).  Bracketed: parabola through the ends and the middle,
-// then Illinois regula falsi, until the step is below 1e-10 R.
-MRTX_HD bool patch_root(const Ray64& R, const Patch& P, const Cell64& C, int W, int H, double radius, double a, double b,
-                        double* s_hit) {
-    const double fa = patch_f(R, P, C, W, H, radius, a, nullptr);
-    if (fa <= 0.0) { *s_hit = a; return true; }
-    const double fb = patch_f(R, P, C, W, H, radius, b, nullptr);
-    const double m = 0.5 * (a + b), h = 0.5 * (b - a);
-    const double fm = patch_f(R, P, C, W, H, radius, m, nullptr);
-    // f ~ fm + c1 t + c2 t^2, t = s - m
-    const double c2 = (fa - 2.0 * fm + fb) / (2.0 * h * h), c1 = (fb - fa) / (2.0 * h);
-    double lo = a, flo = fa, hi, fhi;
-    if (fm <= 0.0) { hi = m; fhi = fm; }
-    else if (fb <= 0.0) { lo = m; flo = fm; hi = b; fhi = fb; }
-    else {
-        // no sign change at the three samples: a grazing double root shows up as a dip
-        if (!(c2 > 0.0)) return false;
-        const double tv = -c1 / (2.0 * c2);
-        if (!(tv > -h && tv < h)) return false;
-        if (fm - c1 * c1 / (4.0 * c2) > 0.25 * fmin(fm, fmin(fa, fb))) return false;   // the dip stays well clear of zero
-        const double fv = patch_f(R, P, C, W, H, radius, m + tv, nullptr);
-        if (fv > 0.0) return false;
-        if (tv > 0.0) { lo = m; flo = fm; }
-        hi = m + tv; fhi = fv;
-    }
-    // first guess: the parabola's root inside the bracket
-    const double tol = 1.0e-10 * radius;
-    double x = 0.5 * (lo + hi);
-    {
-        const double disc = c1 * c1 - 4.0 * c2 * fm;
-        if (disc >= 0.0) {
-            const double sq = sqrt(disc);
-            // descending crossing: f goes + -> -, i.e. derivative c1 + 2 c2 t < 0 -> t = (-c1 - sq) / (2 c2) ... use the stable form
-            const double q = -0.5 * (c1 + (c1 >= 0.0 ? sq : -sq));
-            const double t1 = c2 != 0.0 ? q / c2 : 2.0 * h, t2 = q != 0.0 ? fm / q : 2.0 * h;
-            const double s1 = m + t1, s2 = m + t2;
-            if (s1 > lo && s1 < hi) x = s1;
-            if (s2 > lo && s2 < hi && (!(s1 > lo && s1 < hi) || s2 < s1)) x = s2;
+// then Illinois regula falsi until the step is below 1e-10 R; `info` is left at the root.
+// Written as ONE evaluation site driven by a small state machine: patch_f is ~150 float64
+// instructions and the kernel is instruction-cache bound, so it must exist exactly once.
+MRTX_HD inline bool patch_root(const Ray64& R, const Patch& P, const Cell64& C, int W, int H, double radius, double a, double b,
+                        HitInfo& info) {
+    const double m = 0.5 * (a + b), h = 0.5 * (b - a), tol = 1.0e-10 * radius;
+    double fa = 0.0, fb = 0.0, fm = 0.0, c1 = 0.0, c2 = 0.0, tv = 0.0;
+    double lo = a, flo = 0.0, hi = b, fhi = 0.0, xs = a;
+    int stage = 0, side = 0;
+    for (int it = 0; it < 80; ++it) {
+        const double fx = patch_f(R, P, C, W, H, radius, xs, info);
+        bool guess = false;
+        if (stage == 0) {                       // f(a)
+            fa = fx;
+            if (fa <= 0.0) return true;         // entered below the surface: root at a
+            xs = b; stage = 1;
+        } else if (stage == 1) {                // f(b)
+            fb = fx; xs = m; stage = 2;
+        } else if (stage == 2) {                // f(m): f ~ fm + c1 t + c2 t^2, t = s - m
+            fm = fx;
+            c2 = (fa - 2.0 * fm + fb) / (2.0 * h * h); c1 = (fb - fa) / (2.0 * h);
+            flo = fa;
+            if (fm <= 0.0) { hi = m; fhi = fm; guess = true; }
+            else if (fb <= 0.0) { lo = m; flo = fm; hi = b; fhi = fb; guess = true; }
+            else {
+                // no sign change at the three samples: a grazing double root shows up as a dip
+                if (!(c2 > 0.0)) return false;
+                tv = -c1 / (2.0 * c2);
+                if (!(tv > -h && tv < h)) return false;
+                if (fm - c1 * c1 / (4.0 * c2) > 0.25 * fmin(fm, fmin(fa, fb))) return false;   // the dip stays clear of zero
+                xs = m + tv; stage = 3;
+            }
+        } else if (stage == 3) {                // f at the parabola's vertex
+            if (fx > 0.0) return false;
+            if (tv > 0.0) { lo = m; flo = fm; }
+            hi = m + tv; fhi = fx; guess = true;
+        } else if (stage == 4) {                // Illinois iterations
+            if (fx > 0.0) { lo = xs; flo = fx; if (side == 1) fhi *= 0.5; side = 1; }
+            else { hi = xs; fhi = fx; if (side == -1) flo *= 0.5; side = -1; }
+            double nx = lo + (hi - lo) * flo / (flo - fhi);
+            if (!(nx > lo && nx < hi)) nx = 0.5 * (lo + hi);
+            if (hi - lo < tol || (fabs(nx - xs) < 0.25 * tol && fx <= 0.0)) {
+                if (xs == hi) return true;      // info already describes the root
+                xs = hi; stage = 5;
+            } else xs = nx;
+        } else {                                // stage 5: final evaluation at the root
+            return true;
+        }
+        if (guess) {
+            // first guess: the parabola's root inside the bracket
+            xs = 0.5 * (lo + hi);
+            const double disc = c1 * c1 - 4.0 * c2 * fm;
+            if (disc >= 0.0) {
+                const double sq = sqrt(disc);
+                const double q = -0.5 * (c1 + (c1 >= 0.0 ? sq : -sq));
+                const double t1 = c2 != 0.0 ? q / c2 : 2.0 * h, t2 = q != 0.0 ? fm / q : 2.0 * h;
+                const double s1 = m + t1, s2 = m + t2;
+                const bool in1 = s1 > lo && s1 < hi, in2 = s2 > lo && s2 < hi;
+                if (in1) xs = s1;
+                if (in2 && (!in1 || s2 < s1)) xs = s2;
+            }
+            stage = 4;
         }
     }
-    int side = 0;
-    for (int it = 0; it < 60; ++it) {
-        const double fx = patch_f(R, P, C, W, H, radius, x, nullptr);
-        if (fx > 0.0) { lo = x; flo = fx; if (side == 1) fhi *= 0.5; side = 1; }
-        else { hi = x; fhi = fx; if (side == -1) flo *= 0.5; side = -1; }
-        if (hi - lo < tol) break;
-        double nx = lo + (hi - lo) * flo / (flo - fhi);
-        if (!(nx > lo && nx < hi)) nx = 0.5 * (lo + hi);
-        if (fabs(nx - x) < 0.25 * tol && fx <= 0.0) break;                             // converged onto the root from below
-        x = nx;
-    }
-    *s_hit = hi;
+    info.s = hi;
     return true;
 }
 
@@ -183,8 +205,8 @@ MRTX_HD bool patch_root(const Ray64& R, const Patch& P, const Cell64& C, int W, 
 // Returns 0 = no root, 1 = root at *s_hit, 2 = the ray is already below the surface where it
 // ENTERS the cell through wall *entry_face at *s_hit: the crossing happened in the cell on the
 // other side of that wall, which the float32 traversal did not propose (see the walk-back).
-MRTX_HD int cell_test64(const HeightField& hf, const Ray64& R, const Patch& P, double radius, double wa, double wb,
-                        double oa, double ob, double* s_hit, int* entry_face) {
+MRTX_HD inline int cell_test64(const HeightField& hf, const Ray64& R, const Patch& P, double radius, double wa, double wb,
+                        double oa, double ob, HitInfo& info, int* entry_face) {
     const int W = hf.W, H = hf.H;
     Cell64 C;
     load_cell64(hf, P, C);
@@ -239,8 +261,8 @@ MRTX_HD int cell_test64(const HeightField& hf, const Ray64& R, const Patch& P, d
         const double r = sqrt(x * x + y * y + z * z);
         if (C.has_n && z - C.nk * r > 0.0) continue;             // north of it
         if (C.has_s && z - C.sk * r < 0.0) continue;             // south of it
-        if (patch_root(R, P, C, W, H, radius, a, b, s_hit)) {
-            if (*s_hit == a && cid[i] >= 0) { *entry_face = cid[i]; return 2; }
+        if (patch_root(R, P, C, W, H, radius, a, b, info)) {
+            if (info.s == a && cid[i] >= 0) { *entry_face = cid[i]; return 2; }
             return 1;
         }
     }
@@ -437,42 +459,38 @@ MRTX_HD inline int trav_step(const HeightField& hf, float Rf, TravState& st, Pat
 }
 
 // Exact float64 test of a candidate patch (window [st.s, sx] of the float32 walk).  On a hit fills
-// `out` (out.info only when want_info).
+// `out`.  If the ray turns out to ENTER the cell already below the surface, the first crossing
+// lies in a cell the float32 walk skipped (ray within rounding of a wall or a corner): the loop
+// walks back through the neighbours across the entry walls, in float64, until it is found.
 template <bool I16>
 MRTX_HD inline bool exact_test(const HeightField& hf, double radius, const Ray64& R, const TravState& st, Patch P,
-                               float sx, bool want_info, TraceOut& out, Counters& cnt) {
+                               float sx, TraceOut& out, Counters& cnt) {
     const int W = hf.W, H = hf.H;
-    ++cnt.tests;
-    const double big = 3.0e-3 * radius, small = 2.0e-5 * radius;
+    const double big = 3.0e-3 * radius, small = 2.0e-5 * radius, tiny = 1.0e-9 * radius;
     const double sa = st.s_in + (double)st.s, sb = st.s_in + (double)sx;
-    const double wa = fmax(sa - big, st.s_min), wb = fmin(sb + big, st.s_end);
-    double sh;
-    int ef = -1;
-    int code = cell_test64(hf, R, P, radius, wa, wb, sa - small, sb + small, &sh, &ef);
-    // Entered the cell already below the surface: the first crossing lies in a cell the float32
-    // walk skipped (ray within rounding of a wall or a corner).  Walk back through the neighbours
-    // across the entry walls, in float64, until it is found.
-    for (int back = 0; code == 2 && back < 16; ++back) {
+    double wa = fmax(sa - big, st.s_min), wb = fmin(sb + big, st.s_end), oa = sa - small, ob = sb + small;
+    int found = 0;
+    for (int back = 0; back < 17; ++back) {
+        ++cnt.tests;
+        int ef = -1;
+        HitInfo info;
+        const int code = cell_test64(hf, R, P, radius, wa, wb, oa, ob, info, &ef);
+        if (code == 0) break;                                // (after a walk-back: cannot happen, the surface is continuous)
+        found = 1; out.info = info; out.patch = P;
+        if (code == 1) break;
         int r0 = P.r0, c0 = P.c0;
         if (ef == 0) c0 = c0 == 0 ? W - 1 : c0 - 1;
         else if (ef == 1) c0 = c0 + 1 == W ? 0 : c0 + 1;
         else if (ef == 2) r0 -= 1;
         else r0 += 1;
         if (r0 < 0 || r0 > H - 2) break;
-        Patch Q;
-        load_patch<I16>(hf, r0, c0, Q);
-        ++cnt.tests;
-        double sq2;
-        int ef2 = -1;
-        const double tiny = 1.0e-9 * radius;
-        const int c2 = cell_test64(hf, R, Q, radius, fmax(sh - big, st.s_min), fmin(sh + small, st.s_end),
-                                   sh - small, sh - tiny, &sq2, &ef2);
-        if (c2 == 0) break;                                  // surface continuous: should not happen
-        P = Q; sh = sq2; ef = ef2; code = c2;
+        load_patch<I16>(hf, r0, c0, P);
+        wa = fmax(info.s - big, st.s_min); wb = fmin(info.s + small, st.s_end);
+        oa = info.s - small; ob = info.s - tiny;
     }
-    if (code == 0) return false;
-    out.hit = true; out.s = sh; out.patch = P;
-    if (want_info) { Cell64 C; load_cell64(hf, P, C); patch_f(R, P, C, W, H, radius, sh, &out.info); }
+    if (!found) return false;
+    out.hit = true; out.s = out.info.s;
+    finish_info(out.patch, W, H, out.info);
     return true;
 }
 
@@ -492,7 +510,7 @@ MRTX_HD void trace_ray(const HeightField& hf, double radius, const Ray64& R, dou
         const int r = trav_step<I16>(hf, Rf, st, P, sx, face, cnt);
         if (r == TR_END) return;
         if (r == TR_CANDIDATE) {
-            if (exact_test<I16>(hf, radius, R, st, P, sx, !any_hit, out, cnt)) return;
+            if (exact_test<I16>(hf, radius, R, st, P, sx, out, cnt)) return;
             if (!trav_advance(hf, st, sx, face)) return;
         }
     }

@@ -252,6 +252,8 @@ def test_persistent_kernel_equals_per_pixel_kernel():
     assert np.array_equal(a[1], b[1])
     assert np.array_equal(a[0], b[0])
     assert np.array_equal(a[2], b[2])
-    assert np.array_equal(a[3], b[3])
+    # the two kernels are separate instantiations: the compiler may contract a*b+c differently,
+    # so float64 records agree to rounding, not bit for bit
+    assert np.allclose(a[3], b[3], rtol=0, atol=1e-9)
     for k in ("primary_rays", "primary_hits", "shadow_rays", "shadow_occluded"):
         assert a[4][k] == b[4][k], k

@@ -70,5 +70,6 @@ if __name__ == "__main__":
     elif which == "cfg1k":
         rt, info = setup(23040, 11520, 3840, 2160, ds=1)
     print(json.dumps(info))
-    for spp in (1, 4) if which != "cfg3" else (1, 16):
+    spps = [int(v) for v in sys.argv[2].split(',')] if len(sys.argv) > 2 else ((1, 4) if which != "cfg3" else (1, 16))
+    for spp in spps:
         print(json.dumps(time_frame(rt, spp)))
