@@ -154,8 +154,11 @@ int  mrtx_read_hit_f64(mrtx_ctx* ctx, double* out);
 
 /* counters since the last reset: [0] primary rays, [1] primary rays entering the
  * bounding sphere, [2] primary hits, [3] shadow rays, [4] shadow rays occluded,
- * [5] pyramid node visits, [6] exact patch tests, [7] rays that ran out of steps                         */
-int  mrtx_counters(mrtx_ctx* ctx, uint64_t out[8], int reset);
+ * [5] pyramid node visits, [6] exact patch tests, [7] rays that ran out of steps,
+ * warp-phase statistics of the persistent kernel (lanes / executions = SIMD occupancy of a phase):
+ * [8] float64 test phases executed, [9] lanes in them, [10] traversal steps executed (per warp),
+ * [11] lanes in them, [12] ray-start phases, [13] lanes in them, [14] refills, [15] pixels culled */
+int  mrtx_counters(mrtx_ctx* ctx, uint64_t out[16], int reset);
 
 /* ---- multi-GPU (one process per GPU) ----------------------------------------------
  * NCCL is loaded at run time from `libnccl_path` (the torch-bundled libnccl.so.2).     */

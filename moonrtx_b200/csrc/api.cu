@@ -54,8 +54,8 @@ int mrtx_create(int device, mrtx_ctx** out_ctx) {
     MRTX_CUDA(cudaEventCreate(&c->ev0));
     MRTX_CUDA(cudaEventCreate(&c->ev1));
     MRTX_CUDA(cudaMalloc(&c->d_max_bits, 2 * sizeof(unsigned)));     // [0] running max, [1] trace work counter
-    MRTX_CUDA(cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long)));
-    MRTX_CUDA(cudaMemset(c->d_counters, 0, 8 * sizeof(unsigned long long)));
+    MRTX_CUDA(cudaMalloc(&c->d_counters, 16 * sizeof(unsigned long long)));
+    MRTX_CUDA(cudaMemset(c->d_counters, 0, 16 * sizeof(unsigned long long)));
     // scene defaults = the reference's (moon_renderer.py:37, 85-101, 597-599, 620-621)
     SceneParams& sp = c->sp;
     sp.radius = 10.0;
@@ -519,13 +519,13 @@ int mrtx_frame_buffers_dev(mrtx_ctx* ctx, void** accum_dev, void** rgba8_dev, vo
     return MRTX_OK;
 }
 
-int mrtx_counters(mrtx_ctx* ctx, uint64_t out[8], int reset) {
+int mrtx_counters(mrtx_ctx* ctx, uint64_t out[16], int reset) {
     MRTX_CTX(ctx);
     if (out) {
-        MRTX_CUDA(cudaMemcpyAsync(out, ctx->d_counters, 64, cudaMemcpyDeviceToHost, ctx->stream));
+        MRTX_CUDA(cudaMemcpyAsync(out, ctx->d_counters, 128, cudaMemcpyDeviceToHost, ctx->stream));
         MRTX_CUDA(cudaStreamSynchronize(ctx->stream));
     }
-    if (reset) MRTX_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 64, ctx->stream));
+    if (reset) MRTX_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 128, ctx->stream));
     return MRTX_OK;
 }
 

@@ -224,6 +224,7 @@ trace_kernel_simple(const __grid_constant__ RenderArgs A) {
 //   ->  CAND (float64 exact patch test [+ shading, shadow-ray set-up])  ->  next sample / next pixel.
 enum { M_IDLE = 0, M_START = 1, M_TRAV = 2, M_CAND = 3, M_BEGIN = 4 };
 constexpr int TRAV_BURST = 16;
+constexpr int CAND_GROUP = 20;     // run the float64 phase once this many lanes wait for it
 
 template <bool I16>
 __global__ void __launch_bounds__(128, 3)
@@ -240,6 +241,7 @@ trace_kernel_persistent(const __grid_constant__ RenderArgs A) {
 
     Counters cnt = {0u, 0u, 0u};
     RayStats rs = {0u, 0u, 0u, 0u, 0u};
+    unsigned ph[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};   // lane 0: phase executions / lanes in them
     int mode = M_IDLE;
     bool shadow = false, exhausted = false;
     int x = 0, y = 0;
@@ -277,6 +279,7 @@ trace_kernel_persistent(const __grid_constant__ RenderArgs A) {
         if (!exhausted && n_idle > 0 && (n_idle >= 8 || n_idle + n_start == 32 || n_trav + n_cand == 0)) {
             const unsigned idle = __ballot_sync(0xffffffffu, mode == M_IDLE);
             unsigned base = 0;
+            ++ph[6];
             if (lane == 0) base = atomicAdd(A.work_counter, (unsigned)n_idle);
             base = __shfl_sync(0xffffffffu, base, 0);
             if (base + (unsigned)n_idle >= total) exhausted = true;
@@ -307,6 +310,7 @@ trace_kernel_persistent(const __grid_constant__ RenderArgs A) {
                         const double d2 = eye_dist * eye_dist - od * od;
                         if (eye_dist > cull_r && (d2 > cull_r * cull_r || od > 0.0)) {
                             rs.primary += A.nsamples;                      // every sample of this pixel misses
+                            ++ph[7];
                             write_miss(A, x, y, true);
                             float4* ap = A.accum + (size_t)y * A.width + x;
                             float4 old = *ap;
@@ -320,9 +324,11 @@ trace_kernel_persistent(const __grid_constant__ RenderArgs A) {
             n_start = __popc(__ballot_sync(0xffffffffu, mode == M_START || mode == M_BEGIN));
         }
 
-        if (n_start > 0 && n_start >= n_trav && n_start >= n_cand) {
+        const bool others_blocked = exhausted || n_idle < 8;      // no refill possible right now
+        if (n_start > 0 && (n_start >= 8 || (n_trav == 0 && (n_cand < CAND_GROUP || others_blocked)))) {
             // ---- START: generate the next primary ray, clip it to the bounding sphere ----------------------
             // (also where a freshly shaded hit starts its shadow ray: one trav_begin site)
+            ++ph[4]; ph[5] += (unsigned)n_start;
             if (mode == M_START) {
                 primary_ray(A, x, y, pixel, sm, R);
                 ++rs.primary;
@@ -338,15 +344,25 @@ trace_kernel_persistent(const __grid_constant__ RenderArgs A) {
                     retire_sample();
                 }
             }
-        } else if (n_cand > 0 && n_cand >= n_trav) {
+        } else if (n_cand > 0 && (n_cand >= CAND_GROUP || n_trav == 0)) {
             // ---- CAND: exact patch test; a primary hit is shaded and may spawn its shadow ray -------------
+            ++ph[0]; ph[1] += (unsigned)n_cand;
+            // One warp-uniform loop: each trip every lane that still needs an evaluation of f takes it
+            // at the same instruction, whatever piece / walk-back state it is in.
+            ExactState X;
+            bool run = false;
+            if (mode == M_CAND) run = exact_begin<I16>(A.hf, A.sp.radius, R, st, P, sx, X, cnt);
+            else X.found = 0;
+            while (__any_sync(0xffffffffu, run)) {
+                if (run) run = exact_step<I16>(A.hf, A.sp.radius, R, st, X, cnt);
+            }
             if (mode == M_CAND) {
-                TraceOut h;
-                h.hit = false;
-                if (exact_test<I16>(A.hf, A.sp.radius, R, st, P, sx, h, cnt)) {
+                if (X.found) {
                     if (shadow) { ++rs.occluded; retire_sample(); }
                     else {
                         ++rs.hits;
+                        TraceOut h;
+                        exact_result(A.hf, X, h);
                         Ray64 S;
                         const bool need_shadow = shade_hit(A, R, h, x, y, pixel, sm, lit, S);
                         if (need_shadow) {
@@ -372,6 +388,7 @@ trace_kernel_persistent(const __grid_constant__ RenderArgs A) {
             // ---- TRAV: pyramid steps shared by primary and shadow rays, while they are the majority -------
 #pragma unroll 1
             for (int it = 0; it < TRAV_BURST; ++it) {
+                ++ph[2]; ph[3] += (unsigned)__popc(__ballot_sync(0xffffffffu, mode == M_TRAV));
                 if (mode == M_TRAV) {
                     const int r = trav_step<I16>(A.hf, Rf, st, P, sx, face, cnt);
                     if (r == TR_CANDIDATE) mode = M_CAND;
@@ -383,11 +400,19 @@ trace_kernel_persistent(const __grid_constant__ RenderArgs A) {
                     }
                 }
                 const int nt = __popc(__ballot_sync(0xffffffffu, mode == M_TRAV));
-                if (nt == 0 || nt < __popc(__ballot_sync(0xffffffffu, mode == M_CAND))) break;
+                if (nt == 0 || __popc(__ballot_sync(0xffffffffu, mode == M_CAND)) >= CAND_GROUP) break;
             }
         }
     }
     flush_counters(A, rs, cnt, lane);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) if (ph[i]) atomicAdd(&A.counters[8 + i], (unsigned long long)ph[i]);
+    }
+    {
+        const unsigned r6 = __reduce_add_sync(0xffffffffu, lane == 0 ? ph[6] : 0u), r7 = __reduce_add_sync(0xffffffffu, ph[7]);
+        if (lane == 0) { atomicAdd(&A.counters[14], (unsigned long long)r6); atomicAdd(&A.counters[15], (unsigned long long)r7); }
+    }
 }
 
 // K8: Gamma post-process + Overlay alpha blend -> RGBA8

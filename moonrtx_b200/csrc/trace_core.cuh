@@ -127,89 +127,94 @@ MRTX_HD inline void finish_info(const Patch& P, int W, int H, HitInfo& info) {
 }
 
 // First root of f on [a, b] inside one patch (f is close to a parabola there: a bilinear patch
-// along a nearly straight (u, v) path).  Bracketed: parabola through the ends and the middle,
-// then Illinois regula falsi until the step is below 1e-10 R; `info` is left at the root.
-// Written as ONE evaluation site driven by a small state machine: patch_f is ~150 float64
-// instructions and the kernel is instruction-cache bound, so it must exist exactly once.
-MRTX_HD inline bool patch_root(const Ray64& R, const Patch& P, const Cell64& C, int W, int H, double radius, double a, double b,
-                        HitInfo& info) {
-    const double m = 0.5 * (a + b), h = 0.5 * (b - a), tol = 1.0e-10 * radius;
-    double fa = 0.0, fb = 0.0, fm = 0.0, c1 = 0.0, c2 = 0.0, tv = 0.0;
-    double lo = a, flo = 0.0, hi = b, fhi = 0.0, xs = a;
-    int stage = 0, side = 0;
-    for (int it = 0; it < 80; ++it) {
-        const double fx = patch_f(R, P, C, W, H, radius, xs, info);
-        bool guess = false;
-        if (stage == 0) {                       // f(a)
-            fa = fx;
-            if (fa <= 0.0) return true;         // entered below the surface: root at a
-            xs = b; stage = 1;
-        } else if (stage == 1) {                // f(b)
-            fb = fx; xs = m; stage = 2;
-        } else if (stage == 2) {                // f(m): f ~ fm + c1 t + c2 t^2, t = s - m
-            fm = fx;
-            c2 = (fa - 2.0 * fm + fb) / (2.0 * h * h); c1 = (fb - fa) / (2.0 * h);
-            flo = fa;
-            if (fm <= 0.0) { hi = m; fhi = fm; guess = true; }
-            else if (fb <= 0.0) { lo = m; flo = fm; hi = b; fhi = fb; guess = true; }
-            else {
-                // no sign change at the three samples: a grazing double root shows up as a dip
-                if (!(c2 > 0.0)) return false;
-                tv = -c1 / (2.0 * c2);
-                if (!(tv > -h && tv < h)) return false;
-                if (fm - c1 * c1 / (4.0 * c2) > 0.25 * fmin(fm, fmin(fa, fb))) return false;   // the dip stays clear of zero
-                xs = m + tv; stage = 3;
-            }
-        } else if (stage == 3) {                // f at the parabola's vertex
-            if (fx > 0.0) return false;
-            if (tv > 0.0) { lo = m; flo = fm; }
-            hi = m + tv; fhi = fx; guess = true;
-        } else if (stage == 4) {                // Illinois iterations
-            if (fx > 0.0) { lo = xs; flo = fx; if (side == 1) fhi *= 0.5; side = 1; }
-            else { hi = xs; fhi = fx; if (side == -1) flo *= 0.5; side = -1; }
-            double nx = lo + (hi - lo) * flo / (flo - fhi);
-            if (!(nx > lo && nx < hi)) nx = 0.5 * (lo + hi);
-            if (hi - lo < tol || (fabs(nx - xs) < 0.25 * tol && fx <= 0.0)) {
-                if (xs == hi) return true;      // info already describes the root
-                xs = hi; stage = 5;
-            } else xs = nx;
-        } else {                                // stage 5: final evaluation at the root
-            return true;
+// along a nearly straight (u, v) path): parabola through the ends and the middle, then Illinois
+// regula falsi on the bracket until the step is below 1e-10 R.
+// Written as an ITERATOR - root_step() performs exactly one evaluation of f - so that the render
+// kernel can run one warp-uniform loop in which every lane that still needs an evaluation takes
+// it at the same instruction (patch_f is ~150 float64 instructions; lanes need 4-9 of them).
+struct RootIter {
+    double a, m, h, fa, fb, fm, c1, c2, tv, lo, flo, hi, fhi, xs;
+    int stage, side;
+};
+
+MRTX_HD inline void root_begin(RootIter& q, double a, double b) {
+    q.a = a; q.m = 0.5 * (a + b); q.h = 0.5 * (b - a);
+    q.fa = q.fb = q.fm = q.c1 = q.c2 = q.tv = q.flo = q.fhi = 0.0;
+    q.lo = a; q.hi = b; q.xs = a; q.stage = 0; q.side = 0;
+}
+
+// 0 = needs another evaluation, 1 = root found (info describes it), 2 = no root on this piece
+MRTX_HD inline int root_step(RootIter& q, const Ray64& R, const Patch& P, const Cell64& C, int W, int H, double radius,
+                             HitInfo& info) {
+    const double tol = 1.0e-10 * radius;
+    const double fx = patch_f(R, P, C, W, H, radius, q.xs, info);
+    bool guess = false;
+    if (q.stage == 0) {                         // f(a)
+        q.fa = fx;
+        if (fx <= 0.0) return 1;                // entered below the surface: root at a
+        q.xs = q.m + q.h; q.stage = 1;
+    } else if (q.stage == 1) {                  // f(b)
+        q.fb = fx; q.xs = q.m; q.stage = 2;
+    } else if (q.stage == 2) {                  // f(m): f ~ fm + c1 t + c2 t^2, t = s - m
+        q.fm = fx;
+        q.c2 = (q.fa - 2.0 * fx + q.fb) / (2.0 * q.h * q.h); q.c1 = (q.fb - q.fa) / (2.0 * q.h);
+        q.flo = q.fa;
+        if (fx <= 0.0) { q.hi = q.m; q.fhi = fx; guess = true; }
+        else if (q.fb <= 0.0) { q.lo = q.m; q.flo = fx; q.fhi = q.fb; guess = true; }
+        else {
+            // no sign change at the three samples: a grazing double root shows up as a dip
+            if (!(q.c2 > 0.0)) return 2;
+            q.tv = -q.c1 / (2.0 * q.c2);
+            if (!(q.tv > -q.h && q.tv < q.h)) return 2;
+            if (fx - q.c1 * q.c1 / (4.0 * q.c2) > 0.25 * fmin(fx, fmin(q.fa, q.fb))) return 2;   // dip clear of zero
+            q.xs = q.m + q.tv; q.stage = 3;
         }
-        if (guess) {
-            // first guess: the parabola's root inside the bracket
-            xs = 0.5 * (lo + hi);
-            const double disc = c1 * c1 - 4.0 * c2 * fm;
-            if (disc >= 0.0) {
-                const double sq = sqrt(disc);
-                const double q = -0.5 * (c1 + (c1 >= 0.0 ? sq : -sq));
-                const double t1 = c2 != 0.0 ? q / c2 : 2.0 * h, t2 = q != 0.0 ? fm / q : 2.0 * h;
-                const double s1 = m + t1, s2 = m + t2;
-                const bool in1 = s1 > lo && s1 < hi, in2 = s2 > lo && s2 < hi;
-                if (in1) xs = s1;
-                if (in2 && (!in1 || s2 < s1)) xs = s2;
-            }
-            stage = 4;
-        }
+    } else if (q.stage == 3) {                  // f at the parabola's vertex
+        if (fx > 0.0) return 2;
+        if (q.tv > 0.0) { q.lo = q.m; q.flo = q.fm; }
+        q.hi = q.m + q.tv; q.fhi = fx; guess = true;
+    } else if (q.stage == 4) {                  // Illinois iterations
+        if (fx > 0.0) { q.lo = q.xs; q.flo = fx; if (q.side == 1) q.fhi *= 0.5; q.side = 1; }
+        else { q.hi = q.xs; q.fhi = fx; if (q.side == -1) q.flo *= 0.5; q.side = -1; }
+        double nx = q.lo + (q.hi - q.lo) * q.flo / (q.flo - q.fhi);
+        if (!(nx > q.lo && nx < q.hi)) nx = 0.5 * (q.lo + q.hi);
+        if (q.hi - q.lo < tol || (fabs(nx - q.xs) < 0.25 * tol && fx <= 0.0) || ++q.stage > 64 + 4) {
+            if (q.xs == q.hi) return 1;         // info already describes the root
+            q.xs = q.hi; q.stage = 100;
+        } else { q.xs = nx; q.stage = 4; }
+    } else if (q.stage >= 100) {                // final evaluation at the root
+        return 1;
+    } else {                                    // stages 5..68 count Illinois iterations
+        q.stage = 4;
     }
-    info.s = hi;
-    return true;
+    if (guess) {
+        // first guess: the parabola's root inside the bracket
+        q.xs = 0.5 * (q.lo + q.hi);
+        const double disc = q.c1 * q.c1 - 4.0 * q.c2 * q.fm;
+        if (disc >= 0.0) {
+            const double sq = sqrt(disc);
+            const double t = -0.5 * (q.c1 + (q.c1 >= 0.0 ? sq : -sq));
+            const double t1 = q.c2 != 0.0 ? t / q.c2 : 2.0 * q.h, t2 = t != 0.0 ? q.fm / t : 2.0 * q.h;
+            const double s1 = q.m + t1, s2 = q.m + t2;
+            const bool in1 = s1 > q.lo && s1 < q.hi, in2 = s2 > q.lo && s2 < q.hi;
+            if (in1) q.xs = s1;
+            if (in2 && (!in1 || s2 < s1)) q.xs = s2;
+        }
+        q.stage = 4;
+    }
+    return 0;
 }
 
 // The exact interval(s) of the ray inside cell (r0, c0): all wall crossings inside the generous
-// window [wa, wb] split it into pieces, the pieces inside the cell that touch [oa, ob] (where the
-// float32 traversal believes the ray crosses the cell) are searched for a root, in order and in
-// full - so the searched intervals of consecutive cells tile the ray exactly even where the
-// float32 crossing parameters are ill-conditioned (ray nearly tangent to a wall).
+// window [wa, wb] split it into pieces; the pieces inside the cell that touch [oa, ob] (where the
+// float32 traversal believes the ray crosses the cell) are the ones searched for a root, in order
+// and in full - so the searched intervals of consecutive cells tile the ray exactly even where
+// the float32 crossing parameters are ill-conditioned (ray nearly tangent to a wall).
 // Cell walls: lon half-planes g = p.t (t = (cos lam, sin lam, 0)), lat cones h = z - k r (k = sin phi).
-// Returns 0 = no root, 1 = root at *s_hit, 2 = the ray is already below the surface where it
-// ENTERS the cell through wall *entry_face at *s_hit: the crossing happened in the cell on the
-// other side of that wall, which the float32 traversal did not propose (see the walk-back).
-MRTX_HD inline int cell_test64(const HeightField& hf, const Ray64& R, const Patch& P, double radius, double wa, double wb,
-                        double oa, double ob, HitInfo& info, int* entry_face) {
-    const int W = hf.W, H = hf.H;
-    Cell64 C;
-    load_cell64(hf, P, C);
+// next_piece() returns the k-th such piece (k counted from `from`), its start wall id in *cid
+// (-1 = window edge) and the index to continue from.
+MRTX_HD inline bool next_piece(const Ray64& R, const Cell64& C, double wa, double wb, double oa, double ob,
+                               int& from, double& pa, double& pb, int& pcid) {
     double crit[10];
     int cid[10];
     int n = 0;
@@ -250,9 +255,9 @@ MRTX_HD inline int cell_test64(const HeightField& hf, const Ray64& R, const Patc
         while (j >= 0 && crit[j] > key) { crit[j + 1] = crit[j]; cid[j + 1] = cid[j]; --j; }
         crit[j + 1] = key; cid[j + 1] = kid;
     }
-    for (int i = 0; i + 1 < n; ++i) {
+    for (int i = from; i + 1 < n; ++i) {
         const double a = crit[i], b = crit[i + 1];
-        MRTX_DBG("   piece [%.9f, %.9f] overlap [%.9f, %.9f] cell r%d c%d\n", a, b, oa, ob, P.r0, P.c0);
+        MRTX_DBG("   piece [%.9f, %.9f] overlap [%.9f, %.9f]\n", a, b, oa, ob);
         if (!(b > a) || b < oa || a > ob) continue;
         const double m = 0.5 * (a + b);
         const double x = R.ox + m * R.dx, y = R.oy + m * R.dy, z = R.oz + m * R.dz;
@@ -261,12 +266,10 @@ MRTX_HD inline int cell_test64(const HeightField& hf, const Ray64& R, const Patc
         const double r = sqrt(x * x + y * y + z * z);
         if (C.has_n && z - C.nk * r > 0.0) continue;             // north of it
         if (C.has_s && z - C.sk * r < 0.0) continue;             // south of it
-        if (patch_root(R, P, C, W, H, radius, a, b, info)) {
-            if (info.s == a && cid[i] >= 0) { *entry_face = cid[i]; return 2; }
-            return 1;
-        }
+        pa = a; pb = b; pcid = cid[i]; from = i + 1;
+        return true;
     }
-    return 0;
+    return false;
 }
 
 // ---- float32 pyramid traversal ---------------------------------------------------------------
@@ -458,39 +461,83 @@ MRTX_HD inline int trav_step(const HeightField& hf, float Rf, TravState& st, Pat
     return trav_advance(hf, st, sx, face) ? TR_CONTINUE : TR_END;
 }
 
-// Exact float64 test of a candidate patch (window [st.s, sx] of the float32 walk).  On a hit fills
-// `out`.  If the ray turns out to ENTER the cell already below the surface, the first crossing
-// lies in a cell the float32 walk skipped (ray within rounding of a wall or a corner): the loop
-// walks back through the neighbours across the entry walls, in float64, until it is found.
+// Exact float64 test of a candidate patch (window [st.s, sx] of the float32 walk), as a state
+// machine: exact_begin() sets it up, exact_step() spends ONE evaluation of f and returns true while
+// more are needed; afterwards X.found tells whether the ray hits (X.info, X.P describe the hit).
+// If the ray turns out to ENTER a cell already below the surface, the first crossing lies in a cell
+// the float32 walk skipped (ray within rounding of a wall or a corner): the machine then walks back
+// through the neighbours across the entry walls until it is found.
+struct ExactState {
+    Patch P;
+    Cell64 C;
+    RootIter q;
+    HitInfo info;            // scratch of the evaluation in flight
+    HitInfo hit;             // the accepted root
+    Patch hitP;
+    double wa, wb, oa, ob;
+    int from, pcid, back, found;
+};
+
 template <bool I16>
-MRTX_HD inline bool exact_test(const HeightField& hf, double radius, const Ray64& R, const TravState& st, Patch P,
-                               float sx, TraceOut& out, Counters& cnt) {
-    const int W = hf.W, H = hf.H;
-    const double big = 3.0e-3 * radius, small = 2.0e-5 * radius, tiny = 1.0e-9 * radius;
+MRTX_HD inline bool exact_begin(const HeightField& hf, double radius, const Ray64& R, const TravState& st, const Patch& P,
+                                float sx, ExactState& X, Counters& cnt) {
+    const double big = 3.0e-3 * radius, small = 2.0e-5 * radius;
     const double sa = st.s_in + (double)st.s, sb = st.s_in + (double)sx;
-    double wa = fmax(sa - big, st.s_min), wb = fmin(sb + big, st.s_end), oa = sa - small, ob = sb + small;
-    int found = 0;
-    for (int back = 0; back < 17; ++back) {
-        ++cnt.tests;
-        int ef = -1;
-        HitInfo info;
-        const int code = cell_test64(hf, R, P, radius, wa, wb, oa, ob, info, &ef);
-        if (code == 0) break;                                // (after a walk-back: cannot happen, the surface is continuous)
-        found = 1; out.info = info; out.patch = P;
-        if (code == 1) break;
-        int r0 = P.r0, c0 = P.c0;
-        if (ef == 0) c0 = c0 == 0 ? W - 1 : c0 - 1;
-        else if (ef == 1) c0 = c0 + 1 == W ? 0 : c0 + 1;
-        else if (ef == 2) r0 -= 1;
+    X.P = P;
+    X.wa = fmax(sa - big, st.s_min); X.wb = fmin(sb + big, st.s_end); X.oa = sa - small; X.ob = sb + small;
+    X.from = 0; X.back = 0; X.found = 0; X.pcid = -1;
+    load_cell64(hf, X.P, X.C);
+    ++cnt.tests;
+    double pa, pb;
+    if (!next_piece(R, X.C, X.wa, X.wb, X.oa, X.ob, X.from, pa, pb, X.pcid)) return false;
+    root_begin(X.q, pa, pb);
+    return true;
+}
+
+template <bool I16>
+MRTX_HD inline bool exact_step(const HeightField& hf, double radius, const Ray64& R, const TravState& st, ExactState& X,
+                               Counters& cnt) {
+    const int r = root_step(X.q, R, X.P, X.C, hf.W, hf.H, radius, X.info);
+    if (r == 0) return true;
+    double pa, pb;
+    if (r == 1) {
+        X.found = 1; X.hit = X.info; X.hitP = X.P;
+        if (!(X.info.s == X.q.a && X.pcid >= 0 && X.back < 16)) return false;     // a proper root: done
+        // below the surface at the wall the ray came in through: look in the cell behind that wall
+        const double big = 3.0e-3 * radius, small = 2.0e-5 * radius, tiny = 1.0e-9 * radius;
+        int r0 = X.P.r0, c0 = X.P.c0;
+        if (X.pcid == 0) c0 = c0 == 0 ? hf.W - 1 : c0 - 1;
+        else if (X.pcid == 1) c0 = c0 + 1 == hf.W ? 0 : c0 + 1;
+        else if (X.pcid == 2) r0 -= 1;
         else r0 += 1;
-        if (r0 < 0 || r0 > H - 2) break;
-        load_patch<I16>(hf, r0, c0, P);
-        wa = fmax(info.s - big, st.s_min); wb = fmin(info.s + small, st.s_end);
-        oa = info.s - small; ob = info.s - tiny;
+        if (r0 < 0 || r0 > hf.H - 2) return false;
+        load_patch<I16>(hf, r0, c0, X.P);
+        load_cell64(hf, X.P, X.C);
+        ++cnt.tests; ++X.back;
+        const double sh = X.info.s;
+        X.wa = fmax(sh - big, st.s_min); X.wb = fmin(sh + small, st.s_end); X.oa = sh - small; X.ob = sh - tiny;
+        X.from = 0;
     }
-    if (!found) return false;
-    out.hit = true; out.s = out.info.s;
-    finish_info(out.patch, W, H, out.info);
+    // r == 2 (no root on this piece) or a walk-back: continue with the next piece, if any
+    if (!next_piece(R, X.C, X.wa, X.wb, X.oa, X.ob, X.from, pa, pb, X.pcid)) return false;
+    root_begin(X.q, pa, pb);
+    return true;
+}
+
+MRTX_HD inline void exact_result(const HeightField& hf, const ExactState& X, TraceOut& out) {
+    out.hit = true; out.info = X.hit; out.patch = X.hitP; out.s = X.hit.s;
+    finish_info(out.patch, hf.W, hf.H, out.info);
+}
+
+// sequential form (host tool, per-pixel kernel)
+template <bool I16>
+MRTX_HD inline bool exact_test(const HeightField& hf, double radius, const Ray64& R, const TravState& st, const Patch& P,
+                               float sx, TraceOut& out, Counters& cnt) {
+    ExactState X;
+    bool run = exact_begin<I16>(hf, radius, R, st, P, sx, X, cnt);
+    while (run) run = exact_step<I16>(hf, radius, R, st, X, cnt);
+    if (!X.found) return false;
+    exact_result(hf, X, out);
     return true;
 }
 

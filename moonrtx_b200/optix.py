@@ -407,10 +407,11 @@ class B200OptiX:
         return out
 
     def counters(self, reset: bool = False) -> dict:
-        out = (C.c_uint64 * 8)()
+        out = (C.c_uint64 * 16)()
         _lib.check(self._lib.mrtx_counters(self._ctx, out, 1 if reset else 0))
         names = ("primary_rays", "primary_in_sphere", "primary_hits", "shadow_rays", "shadow_occluded",
-                 "node_visits", "patch_tests", "overflow")
+                 "node_visits", "patch_tests", "overflow", "test_phases", "test_phase_lanes", "trav_steps",
+                 "trav_step_lanes", "start_phases", "start_phase_lanes", "refills", "pixels_culled")
         return {k: int(out[i]) for i, k in enumerate(names)}
 
     def save_image(self, path: str, bps: str = "Bps8"):
