@@ -257,7 +257,7 @@ def run_ours(args):
     barrier()
     clock_info = clocks.stop()
     c = rt.counters()
-    launches = 2 * args.steps
+    launches = 3 * args.steps          # cull_kernel + trace_kernel_persistent + resolve_kernel per frame
     ms_total = max_over_ranks(ms_total)
     rays_local = c["primary_rays"] + c["shadow_rays"]
     rays_all = sum_over_ranks(float(rays_local))
@@ -280,7 +280,7 @@ def run_ours(args):
     algo_bytes = b_floor * rays_in
     peak, peak_src = measured_peak()
     achieved = algo_bytes / (k_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "trace_kernel<int16>", "achieved": round(achieved, 2), "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "cull_kernel + trace_kernel_persistent<int16> (one mrtx_render)", "achieved": round(achieved, 2), "peak": peak,
                 "unit": "GB/s", "frac": round(achieved / peak, 5), "traffic": args.traffic,
                 "algorithmic_bytes_per_launch": int(algo_bytes), "bytes_per_ray": b_floor,
                 "rays_in_sphere_per_launch": int(rays_in), "kernel_ms": round(k_ms, 3), "peak_source": peak_src,
@@ -332,7 +332,9 @@ def run_ours(args):
             "rays": {"primary_per_step": c["primary_rays"] // args.steps, "shadow_per_step": c["shadow_rays"] // args.steps,
                      "primary_in_sphere_per_step": c["primary_in_sphere"] // args.steps,
                      "node_visits_per_step": c["node_visits"] // args.steps, "patch_tests_per_step": c["patch_tests"] // args.steps,
-                     "overflow": c["overflow"]},
+                     "overflow": c["overflow"],
+                     "simd_lanes_per_traversal_step": round(c["trav_step_lanes"] / max(1, c["trav_steps"]), 2),
+                     "simd_lanes_per_float64_test_phase": round(c["test_phase_lanes"] / max(1, c["test_phases"]), 2)},
             "frames_per_s": round(world * args.steps / (ms_total * 1e-3), 3),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clock_info,
         }

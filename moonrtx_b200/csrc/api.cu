@@ -53,7 +53,8 @@ int mrtx_create(int device, mrtx_ctx** out_ctx) {
     c->stream = c->own_stream;
     MRTX_CUDA(cudaEventCreate(&c->ev0));
     MRTX_CUDA(cudaEventCreate(&c->ev1));
-    MRTX_CUDA(cudaMalloc(&c->d_max_bits, 2 * sizeof(unsigned)));     // [0] running max, [1] trace work counter
+    MRTX_CUDA(cudaMalloc(&c->d_max_bits, sizeof(unsigned)));
+    MRTX_CUDA(cudaMalloc(&c->d_work, 2 * sizeof(unsigned)));
     MRTX_CUDA(cudaMalloc(&c->d_counters, 16 * sizeof(unsigned long long)));
     MRTX_CUDA(cudaMemset(c->d_counters, 0, 16 * sizeof(unsigned long long)));
     // scene defaults = the reference's (moon_renderer.py:37, 85-101, 597-599, 620-621)
@@ -72,7 +73,8 @@ int mrtx_create(int device, mrtx_ctx** out_ctx) {
 }
 
 static void free_frame(mrtx_ctx* c) {
-    cudaFree(c->accum); cudaFree(c->rgba8); cudaFree(c->hit); cudaFree(c->hit64);
+    cudaFree(c->accum); cudaFree(c->rgba8); cudaFree(c->hit); cudaFree(c->hit64); cudaFree(c->pixel_list);
+    c->pixel_list = nullptr;
     c->accum = nullptr; c->rgba8 = nullptr; c->hit = nullptr; c->hit64 = nullptr;
 }
 
@@ -85,6 +87,7 @@ int mrtx_destroy(mrtx_ctx* ctx) {
     for (int s = 0; s < 2; ++s) cudaFree(ctx->tex_owned[s]);
     free_frame(ctx);
     cudaFree(ctx->d_max_bits);
+    cudaFree(ctx->d_work);
     cudaFree(ctx->d_counters);
     cudaFree(ctx->flush_buf);
     cudaFree(ctx->gather_buf);
@@ -458,6 +461,7 @@ int mrtx_resize(mrtx_ctx* ctx, int width, int height) {
     MRTX_CUDA(cudaMalloc(&ctx->accum, n * sizeof(float4)));
     MRTX_CUDA(cudaMalloc(&ctx->rgba8, n * sizeof(uchar4)));
     MRTX_CUDA(cudaMalloc(&ctx->hit, n * sizeof(float4)));
+    MRTX_CUDA(cudaMalloc(&ctx->pixel_list, n * sizeof(unsigned)));
     MRTX_CUDA(cudaMemsetAsync(ctx->accum, 0, n * sizeof(float4), ctx->stream));
     MRTX_CUDA(cudaMemsetAsync(ctx->rgba8, 0, n * sizeof(uchar4), ctx->stream));
     MRTX_CUDA(cudaMemsetAsync(ctx->hit, 0, n * sizeof(float4), ctx->stream));

@@ -110,6 +110,8 @@ struct mrtx_ctx {
     int width, height;
     float4* accum; uchar4* rgba8; float4* hit; double4* hit64;
     unsigned long long* d_counters;
+    unsigned* d_work;           // trace work counter + list length
+    unsigned* pixel_list;       // width * height entries
 
     // comm
     void* nccl_lib; void* nccl_comm; int nranks, rank;

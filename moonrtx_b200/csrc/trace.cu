@@ -63,7 +63,8 @@ struct RenderArgs {
     unsigned sample0, nsamples;
     float4* accum; float4* hit; double4* hit64;
     unsigned long long* counters;
-    unsigned* work_counter;          // persistent kernel: next unclaimed pixel
+    unsigned* work_counter;          // persistent kernel: [0] next unclaimed list entry, [1] list length
+    unsigned* pixel_list;            // pixels whose rays can touch the bounding sphere (x | y << 16)
     // eye and light centre in the body frame (host-computed once per launch)
     double eye_b[3], light_b[3];
 };
@@ -215,6 +216,64 @@ trace_kernel_simple(const __grid_constant__ RenderArgs A) {
     flush_counters(A, rs, cnt, (threadIdx.y * blockDim.x + threadIdx.x) & 31);
 }
 
+// ---- pass 1 of the production path: whole-pixel cull + compaction -------------------------------------
+// 64 % of a whole-disk frame never touches the Moon.  One thread per pixel (8x4 tiles, so the list
+// keeps screen-space coherence) tests the pixel's centre ray against the bounding sphere grown by 1.5
+// pixels; pixels that cannot hit are finished here, the rest are appended to the work list that the
+// persistent kernel consumes - its lanes then only ever receive pixels with real work.
+__global__ void __launch_bounds__(256)
+cull_kernel(const __grid_constant__ RenderArgs A) {
+    const int rw = A.x1 - A.x0, rh = A.y1 - A.y0;
+    const unsigned tiles_x = (unsigned)(rw + 7) / 8u, tiles_y = (unsigned)(rh + 3) / 4u;
+    const unsigned total = tiles_x * tiles_y * 32u;
+    const unsigned p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    bool keep = false;
+    unsigned culled = 0;
+    int x = 0, y = 0;
+    if (p < total) {
+        const unsigned tile = p >> 5, within = p & 31u;
+        x = A.x0 + (int)(tile % tiles_x) * 8 + (int)(within & 7u);
+        y = A.y0 + (int)(tile / tiles_x) * 4 + (int)(within >> 3);
+        if (x < A.x1 && y < A.y1) {
+            const Camera& cam = A.cam;
+            const double Rb = A.sp.radius * (double)A.hf.dmax;
+            const double eye_dist = sqrt(A.eye_b[0] * A.eye_b[0] + A.eye_b[1] * A.eye_b[1] + A.eye_b[2] * A.eye_b[2]);
+            const double cull_r = Rb + eye_dist * 3.0 * cam.tan_half_fov / A.height;
+            const double aspect = (double)A.width / (double)A.height;
+            const double cx = ((x + 0.5) / A.width * 2.0 - 1.0) * cam.tan_half_fov * aspect;
+            const double cy = (1.0 - (y + 0.5) / A.height * 2.0) * cam.tan_half_fov;
+            double d[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) d[a] = cam.w[a] + cx * cam.right[a] + cy * cam.up[a];
+            const double dn = 1.0 / sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+            const double bx = (A.sp.ex[0] * d[0] + A.sp.ex[1] * d[1] + A.sp.ex[2] * d[2]) * dn;
+            const double by = (A.sp.ey[0] * d[0] + A.sp.ey[1] * d[1] + A.sp.ey[2] * d[2]) * dn;
+            const double bz = (A.sp.ez[0] * d[0] + A.sp.ez[1] * d[1] + A.sp.ez[2] * d[2]) * dn;
+            const double od = A.eye_b[0] * bx + A.eye_b[1] * by + A.eye_b[2] * bz;
+            const double d2 = eye_dist * eye_dist - od * od;
+            if (eye_dist > cull_r && (d2 > cull_r * cull_r || od > 0.0)) {
+                culled = 1;                                     // every sample of this pixel misses
+                write_miss(A, x, y, true);
+                float4* ap = A.accum + (size_t)y * A.width + x;
+                float4 old = *ap;
+                old.w += (float)A.nsamples;
+                *ap = old;
+            } else keep = true;
+        }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    unsigned base = 0;
+    if (lane == 0 && m) base = atomicAdd(&A.work_counter[1], (unsigned)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (keep) A.pixel_list[base + (unsigned)__popc(m & ((1u << lane) - 1u))] = (unsigned)x | ((unsigned)y << 16);
+    const unsigned nc = __reduce_add_sync(0xffffffffu, culled);
+    if (lane == 0 && nc) {
+        atomicAdd(&A.counters[0], (unsigned long long)nc * A.nsamples);
+        atomicAdd(&A.counters[15], (unsigned long long)nc);
+    }
+}
+
 // ---- production kernel: persistent warps, per-lane ray state machine, dynamic refill ---------------------
 // Rays differ wildly in cost (64 % of a whole-disk frame misses the Moon, limb and terminator rays walk
 // hundreds of cells), so a pixel->thread mapping leaves most lanes idle.  Here every lane owns one pixel
@@ -230,14 +289,8 @@ template <bool I16>
 __global__ void __launch_bounds__(128, 3)
 trace_kernel_persistent(const __grid_constant__ RenderArgs A) {
     const int lane = threadIdx.x & 31;
-    const int rw = A.x1 - A.x0, rh = A.y1 - A.y0;
-    const unsigned tiles_x = (unsigned)(rw + 7) / 8u, tiles_y = (unsigned)(rh + 3) / 4u;
-    const unsigned total = tiles_x * tiles_y * 32u;
+    const unsigned total = A.work_counter[1];             // list length, written by cull_kernel
     const float Rf = (float)A.sp.radius;
-    // a pixel whose centre ray passes the bounding sphere by more than this cannot touch it with any jitter
-    const double Rb = A.sp.radius * (double)A.hf.dmax;
-    const double eye_dist = sqrt(A.eye_b[0] * A.eye_b[0] + A.eye_b[1] * A.eye_b[1] + A.eye_b[2] * A.eye_b[2]);
-    const double cull_r = Rb + eye_dist * 3.0 * A.cam.tan_half_fov / A.height;
 
     Counters cnt = {0u, 0u, 0u};
     RayStats rs = {0u, 0u, 0u, 0u, 0u};
@@ -286,39 +339,12 @@ trace_kernel_persistent(const __grid_constant__ RenderArgs A) {
             if (mode == M_IDLE) {
                 const unsigned p = base + (unsigned)__popc(idle & ((1u << lane) - 1u));
                 if (p < total) {
-                    const unsigned tile = p >> 5, within = p & 31u;
-                    x = A.x0 + (int)(tile % tiles_x) * 8 + (int)(within & 7u);
-                    y = A.y0 + (int)(tile / tiles_x) * 4 + (int)(within >> 3);
-                    if (x < A.x1 && y < A.y1) {
-                        pixel = (uint32_t)y * (uint32_t)A.width + (uint32_t)x;
-                        sm = A.sample0;
-                        acc = make_float3(0.f, 0.f, 0.f);
-                        mode = M_START;
-                        // whole-pixel cull against the bounding sphere (centre ray + 1.5 pixels of slack)
-                        const Camera& cam = A.cam;
-                        const double aspect = (double)A.width / (double)A.height;
-                        const double cx = ((x + 0.5) / A.width * 2.0 - 1.0) * cam.tan_half_fov * aspect;
-                        const double cy = (1.0 - (y + 0.5) / A.height * 2.0) * cam.tan_half_fov;
-                        double d[3];
-#pragma unroll
-                        for (int a = 0; a < 3; ++a) d[a] = cam.w[a] + cx * cam.right[a] + cy * cam.up[a];
-                        const double dn = 1.0 / sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-                        const double bx = (A.sp.ex[0] * d[0] + A.sp.ex[1] * d[1] + A.sp.ex[2] * d[2]) * dn;
-                        const double by = (A.sp.ey[0] * d[0] + A.sp.ey[1] * d[1] + A.sp.ey[2] * d[2]) * dn;
-                        const double bz = (A.sp.ez[0] * d[0] + A.sp.ez[1] * d[1] + A.sp.ez[2] * d[2]) * dn;
-                        const double od = A.eye_b[0] * bx + A.eye_b[1] * by + A.eye_b[2] * bz;
-                        const double d2 = eye_dist * eye_dist - od * od;
-                        if (eye_dist > cull_r && (d2 > cull_r * cull_r || od > 0.0)) {
-                            rs.primary += A.nsamples;                      // every sample of this pixel misses
-                            ++ph[7];
-                            write_miss(A, x, y, true);
-                            float4* ap = A.accum + (size_t)y * A.width + x;
-                            float4 old = *ap;
-                            old.w += (float)A.nsamples;
-                            *ap = old;
-                            mode = M_IDLE;
-                        }
-                    }
+                    const unsigned packed = A.pixel_list[p];
+                    x = (int)(packed & 0xffffu); y = (int)(packed >> 16);
+                    pixel = (uint32_t)y * (uint32_t)A.width + (uint32_t)x;
+                    sm = A.sample0;
+                    acc = make_float3(0.f, 0.f, 0.f);
+                    mode = M_START;
                 }
             }
             n_start = __popc(__ballot_sync(0xffffffffu, mode == M_START || mode == M_BEGIN));
@@ -459,7 +485,8 @@ int launch_trace(mrtx_ctx* ctx, int x0, int y0, int x1, int y1, unsigned s0, uns
     A.accum = ctx->accum; A.hit = ctx->hit;
     A.hit64 = ctx->sp.debug_hits ? ctx->hit64 : nullptr;
     A.counters = ctx->d_counters;
-    A.work_counter = ctx->d_max_bits + 1;        // second word of the context's scratch pair
+    A.work_counter = ctx->d_work;
+    A.pixel_list = ctx->pixel_list;
     const double er[3] = {A.cam.eye[0] - A.sp.pos[0], A.cam.eye[1] - A.sp.pos[1], A.cam.eye[2] - A.sp.pos[2]};
     const double lr[3] = {A.sp.light_pos[0] - A.sp.pos[0], A.sp.light_pos[1] - A.sp.pos[1], A.sp.light_pos[2] - A.sp.pos[2]};
     to_body(A.sp, er, A.eye_b);
@@ -470,14 +497,19 @@ int launch_trace(mrtx_ctx* ctx, int x0, int y0, int x1, int y1, unsigned s0, uns
         if (ctx->hf.is_i16) trace_kernel_simple<true><<<grid, block, 0, ctx->stream>>>(A);
         else                trace_kernel_simple<false><<<grid, block, 0, ctx->stream>>>(A);
     } else {
-        MRTX_CUDA(cudaMemsetAsync(A.work_counter, 0, sizeof(unsigned), ctx->stream));
+        MRTX_CUDA(cudaMemsetAsync(A.work_counter, 0, 2 * sizeof(unsigned), ctx->stream));
+        {
+            const unsigned tiles_x = (unsigned)(x1 - x0 + 7) / 8u, tiles_y = (unsigned)(y1 - y0 + 3) / 4u;
+            const unsigned total = tiles_x * tiles_y * 32u;
+            cull_kernel<<<(total + 255u) / 256u, 256, 0, ctx->stream>>>(A);
+        }
         int per_sm = 0;
         if (ctx->hf.is_i16) MRTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel_persistent<true>, 128, 0));
         else                MRTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel_persistent<false>, 128, 0));
         if (per_sm < 1) per_sm = 1;
         const long long warps_needed = ((long long)(x1 - x0) * (y1 - y0) + 31) / 32;
         long long blocks = (long long)ctx->sm_count * per_sm;
-        if (blocks * 4 > warps_needed) blocks = (warps_needed + 3) / 4;
+        if (blocks * 4 > warps_needed) blocks = (warps_needed + 3) / 4;     // small rectangles: fewer blocks
         if (blocks < 1) blocks = 1;
         if (ctx->hf.is_i16) trace_kernel_persistent<true><<<(unsigned)blocks, 128, 0, ctx->stream>>>(A);
         else                trace_kernel_persistent<false><<<(unsigned)blocks, 128, 0, ctx->stream>>>(A);

@@ -22,6 +22,13 @@ static inline float mrtx_fdiv(float a, float b) { volatile float r = a / b; retu
 
 namespace mrtx_core {
 
+// float32 traversal arithmetic is protected by margins, so approximate division is enough there
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ float fdiv_fast(float a, float b) { return __fdividef(a, b); }
+#else
+static inline float fdiv_fast(float a, float b) { return a / b; }
+#endif
+
 static int g_debug = 0;   // host-side debugging only (tools/trace_host.cu)
 #ifndef __CUDA_ARCH__
 #define MRTX_DBG(...) do { if (g_debug) printf(__VA_ARGS__); } while (0)
@@ -304,7 +311,7 @@ MRTX_HD float cell_exit32(const HeightField& hf, const Trav& T, int L, int J, in
         float sc;
         if (q >= -tol) sc = s;                                  // on or beyond the wall, moving outward
         else {
-            sc = s - q / dq;
+            sc = s - fdiv_fast(q, dq);
             const float px = fmaf(sc, T.dx, T.ox), py = fmaf(sc, T.dy, T.oy);
             if (!(px * sn - py * cs > 0.0f)) continue;          // crosses the opposite half-plane
         }
@@ -315,32 +322,35 @@ MRTX_HD float cell_exit32(const HeightField& hf, const Trav& T, int L, int J, in
         if (side == 0 ? (n == 0) : (m == H - 1)) continue;      // polar caps have no wall
         const float k = MRTX_LDG(hf.lat32 + (side == 0 ? n : m));               // sin(lat) of the wall
         const float sg = side ? -1.0f : 1.0f;                   // outward = +h north, -h south; h = z - k r
-        const float q = sg * (z - k * r), dq = sg * (T.dz - k * (T.od + s) / r);
+        const float q = sg * (z - k * r), dq = sg * (T.dz * r - k * (T.od + s));  // dq: sign of d(q)/ds (times r > 0)
         if (q >= -tol && dq > 0.0f) {                           // on or beyond the wall, moving outward
             if (s < best) { best = s; face = 2 + side; }
             continue;
         }
-        // outward crossings ahead: roots of z^2 = k^2 r^2 on the wall's nappe with d(q)/ds > 0
+        // outward crossings ahead: roots of F(s) = z^2 - k^2 r^2 = A s^2 + 2 B s + C on the wall's nappe.
+        // On that nappe h = F / (z + k r) and z + k r has the sign of k, so the crossing direction
+        // d(h)/ds has the sign of k * F'(s) = k * 2 (A s + B): no square root or division needed.
         const float k2 = k * k;
         const float A = T.dz * T.dz - k2, B = T.oz * T.dz - k2 * T.od, Cq = T.oz * T.oz - k2 * T.oo;
         float r1 = -1.0f, r2 = -1.0f;
-        if (fabsf(A) < 1e-12f) { if (B != 0.0f) r1 = -Cq / (2.0f * B); }
+        if (fabsf(A) < 1e-12f) { if (B != 0.0f) r1 = fdiv_fast(-Cq, 2.0f * B); }
         else {
             const float disc = B * B - A * Cq;
             if (disc >= 0.0f) {
                 const float qq = -(B + copysignf(sqrtf(disc), B));
-                r1 = qq / A;
-                if (qq != 0.0f) r2 = Cq / qq;
+                r1 = fdiv_fast(qq, A);
+                if (qq != 0.0f) r2 = fdiv_fast(Cq, qq);
             }
         }
+        const float ksg = k >= 0.0f ? sg : -sg;
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
             const float sc = i ? r2 : r1;
             if (!(sc > s) || !(sc < best)) continue;
             const float zc = fmaf(sc, T.dz, T.oz);
             if (k != 0.0f && zc * k < 0.0f) continue;            // the cone's other nappe
-            const float rc = sqrtf(fmaxf(ray_r2(T, sc), 1e-30f));
-            if (sg * (T.dz - k * (T.od + sc) / rc) > 0.0f) { best = sc; face = 2 + side; }
+            const float dF = fmaf(A, sc, B);
+            if ((k != 0.0f ? ksg * dF : sg * T.dz) > 0.0f) { best = sc; face = 2 + side; }
         }
     }
     return best;
