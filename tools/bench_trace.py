@@ -20,8 +20,14 @@ def setup(W, H, iw, ih, ds=1, tex=True):
     t = time.time()
     if ds == 1:
         # radius_scale from the max count, as data_loader.py:232-242 would compute it
-        out, rs = downscale_elevation_dev(src, W, H, 1, want_scale=True)
-        out.free()
+        if os.environ.get("BANDS"):
+            sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+            import bench
+            rs = bench._radius_scale_ds1(dev, src, W, H)
+        else:
+            out, rs = downscale_elevation_dev(src, W, H, 1, want_scale=True)
+            out.free()
+        print("radius_scale", rs)
         rt.set_displacement_i16("moon", (src, W, H), radius_scale=rs)
     else:
         out, rs = downscale_elevation_dev(src, W, H, ds)
