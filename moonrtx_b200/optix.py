@@ -307,20 +307,61 @@ class B200OptiX:
     def set_launch_finished_cb(self, cb: Optional[Callable]):
         self._on_launch_finished = cb
 
-    def render_cycle(self, read_back: bool = True) -> Optional[np.ndarray]:
-        """One accumulation cycle, synchronously, on the calling thread (padlock held)."""
+    # ---- multi-GPU sharding of ONE frame; time-lapse needs none of this ------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """128 opaque bytes rank 0 creates and hands to every rank (any side channel)."""
+        buf = (C.c_uint8 * 128)()
+        _lib.check(_lib.load().mrtx_comm_unique_id(_lib.nccl_library_path().encode(), buf))
+        return bytes(buf)
+
+    def comm_init(self, rank: int, world: int, unique_id: bytes):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        with self._padlock:
+            _lib.check(self._lib.mrtx_comm_init(self._ctx, _lib.nccl_library_path().encode(), int(world), int(rank), buf))
+        self._rank, self._world = int(rank), int(world)
+
+    def render_cycle(self, read_back: bool = True, shard: Optional[str] = None,
+                     tile_rows: int = 64) -> Optional[np.ndarray]:
+        """
+        One accumulation cycle, synchronously, on the calling thread (padlock held).
+
+        shard=None      this GPU renders the whole frame;
+        shard="samples" the cycle's samples are split across the communicator's ranks and the float4
+                        accumulators are summed with one ncclAllReduce before the resolve;
+        shard="rows"    interleaved bands of `tile_rows` rows are split across the ranks and the
+                        resolved RGBA8 bands are exchanged with one ncclAllGather.
+        """
         with self._padlock:
             n = max(1, int(self._params["max_accumulation_frames"]))
             step = max(1, int(self._params["min_accumulation_step"]))
             jitter = (n > 1) if self.deterministic is None else (not self.deterministic)
             _lib.check(self._lib.mrtx_set_uint(self._ctx, b"jitter", 1 if jitter else 0, 0))
-            done = 0
-            while done < n:
-                k = min(step, n - done)
-                _lib.check(self._lib.mrtx_render(self._ctx, 0, 0, self._width, self._height, done, k,
-                                                 1 if done == 0 else 0))
-                done += k
+            W, H = self._width, self._height
+            if shard is None:
+                done = 0
+                while done < n:
+                    k = min(step, n - done)
+                    _lib.check(self._lib.mrtx_render(self._ctx, 0, 0, W, H, done, k, 1 if done == 0 else 0))
+                    done += k
+            elif shard == "samples":
+                lo = (n * self._rank) // self._world
+                hi = (n * (self._rank + 1)) // self._world
+                _lib.check(self._lib.mrtx_render(self._ctx, 0, 0, W, H, lo, hi - lo, 1))
+                _lib.check(self._lib.mrtx_allreduce_accum(self._ctx))
+            elif shard == "rows":
+                first = True
+                for t in range(self._rank, (H + tile_rows - 1) // tile_rows, self._world):
+                    y0, y1 = t * tile_rows, min(H, (t + 1) * tile_rows)
+                    _lib.check(self._lib.mrtx_render(self._ctx, 0, y0, W, y1, 0, n, 1 if first else 0))
+                    first = False
+                if first:                               # more ranks than bands: still clear the accumulators
+                    _lib.check(self._lib.mrtx_render(self._ctx, 0, 0, W, 0, 0, 0, 1))
+            else:
+                raise ValueError(f"unknown shard mode {shard}")
             _lib.check(self._lib.mrtx_resolve(self._ctx))
+            if shard == "rows":
+                _lib.check(self._lib.mrtx_allgather_rows(self._ctx, int(tile_rows)))
             self._frames_rendered += 1
             if read_back:
                 _lib.check(self._lib.mrtx_read_rgba8(self._ctx, self._img_rgba.ctypes.data))

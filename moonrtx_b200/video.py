@@ -103,3 +103,20 @@ def merge_in_order(per_rank: Iterable[dict[int, np.ndarray]], n_frames: int) -> 
     if missing:
         raise ValueError(f"frames missing: {missing[:8]}")
     return [merged[i] for i in range(n_frames)]
+
+
+def gather_frames(local: dict[int, np.ndarray], n_frames: int, rank: int, world: int, group=None):
+    """
+    Collect every rank's frames on rank 0, in time order (the encoder feed of the reference's
+    export loop).  Uses torch.distributed's object gather on whatever backend the group has
+    (gloo on CPU-only boxes); frames are host arrays at this point, 33 MB each at 4K.
+    Returns the ordered list on rank 0, None elsewhere.
+    """
+    if world == 1:
+        return merge_in_order([local], n_frames)
+    import torch.distributed as dist
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object(local, gathered, dst=0, group=group)
+    if rank != 0:
+        return None
+    return merge_in_order(gathered, n_frames)
