@@ -54,7 +54,7 @@ int mrtx_create(int device, mrtx_ctx** out_ctx) {
     MRTX_CUDA(cudaEventCreate(&c->ev0));
     MRTX_CUDA(cudaEventCreate(&c->ev1));
     MRTX_CUDA(cudaMalloc(&c->d_max_bits, sizeof(unsigned)));
-    MRTX_CUDA(cudaMalloc(&c->d_work, 2 * sizeof(unsigned)));
+    MRTX_CUDA(cudaMalloc(&c->d_work, 8 * sizeof(unsigned)));
     MRTX_CUDA(cudaMalloc(&c->d_counters, 16 * sizeof(unsigned long long)));
     MRTX_CUDA(cudaMemset(c->d_counters, 0, 16 * sizeof(unsigned long long)));
     // scene defaults = the reference's (moon_renderer.py:37, 85-101, 597-599, 620-621)
@@ -65,7 +65,7 @@ int mrtx_create(int device, mrtx_ctx** out_ctx) {
     sp.light_pos[0] = 21460.0; sp.light_radius = 100.0; sp.light_radiance = 80.0 * 460.5316;
     sp.scene_epsilon = 1.0e-4;
     sp.exposure = 0.9f; sp.inv_gamma = 1.0f / 2.2f;
-    sp.jitter = 0; sp.shadows = 1; sp.debug_hits = 0; sp.kernel = 1;
+    sp.jitter = 0; sp.shadows = 1; sp.debug_hits = 0; sp.kernel = 2;
     const double eye[3] = {0, -300, 0}, tgt[3] = {0, 0, 0}, up[3] = {0, 0, 1};
     mrtx_set_camera(c, eye, tgt, up, 4.242192793);
     *out_ctx = c;
@@ -73,8 +73,8 @@ int mrtx_create(int device, mrtx_ctx** out_ctx) {
 }
 
 static void free_frame(mrtx_ctx* c) {
-    cudaFree(c->accum); cudaFree(c->rgba8); cudaFree(c->hit); cudaFree(c->hit64); cudaFree(c->pixel_list);
-    c->pixel_list = nullptr;
+    cudaFree(c->accum); cudaFree(c->rgba8); cudaFree(c->hit); cudaFree(c->hit64); cudaFree(c->pixel_list); cudaFree(c->defer_list);
+    c->pixel_list = nullptr; c->defer_list = nullptr;
     c->accum = nullptr; c->rgba8 = nullptr; c->hit = nullptr; c->hit64 = nullptr;
 }
 
@@ -446,7 +446,7 @@ int mrtx_set_uint(mrtx_ctx* ctx, const char* name, unsigned a, unsigned b) {
     else if (!strcmp(name, "jitter")) ctx->sp.jitter = a ? 1u : 0u;
     else if (!strcmp(name, "shadows")) ctx->sp.shadows = a ? 1u : 0u;
     else if (!strcmp(name, "debug_hits")) ctx->sp.debug_hits = a ? 1u : 0u;
-    else if (!strcmp(name, "kernel")) ctx->sp.kernel = a ? 1u : 0u;
+    else if (!strcmp(name, "kernel")) { MRTX_REQUIRE(a <= 2u, "kernel must be 0, 1 or 2"); ctx->sp.kernel = a; }
     else { mrtx_set_error("unknown uint parameter '%s'", name); return MRTX_ERR_INVALID; }
     return MRTX_OK;
 }
@@ -462,6 +462,7 @@ int mrtx_resize(mrtx_ctx* ctx, int width, int height) {
     MRTX_CUDA(cudaMalloc(&ctx->rgba8, n * sizeof(uchar4)));
     MRTX_CUDA(cudaMalloc(&ctx->hit, n * sizeof(float4)));
     MRTX_CUDA(cudaMalloc(&ctx->pixel_list, n * sizeof(unsigned)));
+    MRTX_CUDA(cudaMalloc(&ctx->defer_list, n * sizeof(uint2)));
     MRTX_CUDA(cudaMemsetAsync(ctx->accum, 0, n * sizeof(float4), ctx->stream));
     MRTX_CUDA(cudaMemsetAsync(ctx->rgba8, 0, n * sizeof(uchar4), ctx->stream));
     MRTX_CUDA(cudaMemsetAsync(ctx->hit, 0, n * sizeof(float4), ctx->stream));

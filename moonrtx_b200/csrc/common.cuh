@@ -82,7 +82,8 @@ struct SceneParams {
     double scene_epsilon;
     float  exposure, inv_gamma;
     unsigned jitter, shadows, debug_hits;
-    unsigned kernel;                        // 1 = persistent warp-compacting kernel (default), 0 = one thread per pixel
+    unsigned kernel;                        // 2 = filtered float32 kernel + exact kernel on what it defers (default),
+                                            // 1 = exact persistent kernel only, 0 = exact, one thread per pixel
 };
 
 struct mrtx_ctx {
@@ -112,6 +113,7 @@ struct mrtx_ctx {
     unsigned long long* d_counters;
     unsigned* d_work;           // trace work counter + list length
     unsigned* pixel_list;       // width * height entries
+    uint2* defer_list;          // width * height entries: samples the filtered kernel hands to the exact one
 
     // comm
     void* nccl_lib; void* nccl_comm; int nranks, rank;

@@ -18,7 +18,7 @@
 // Traversal state is float32 re-based at the bounding-sphere entry (H4); every float32
 // decision carries a margin so that it can only add candidate cells, never drop one.
 
-#include "trace_core.cuh"
+#include "trace_fast.cuh"
 
 namespace {
 
@@ -63,8 +63,13 @@ struct RenderArgs {
     unsigned sample0, nsamples;
     float4* accum; float4* hit; double4* hit64;
     unsigned long long* counters;
-    unsigned* work_counter;          // persistent kernel: [0] next unclaimed list entry, [1] list length
+    unsigned* work_counter;          // [0] persistent kernel: next unclaimed entry, [1] pixel list length,
+                                     // [2] fast kernel: next unclaimed warp task, [3] deferred list length
     unsigned* pixel_list;            // pixels whose rays can touch the bounding sphere (x | y << 16)
+    uint2* defer_list;               // (pixel, mask of samples sample0 + bit) the fast kernel could not certify
+    FastConsts K;
+    float inv_rs;
+    int g_log2;                      // fast kernel: 2^g_log2 lanes share one pixel (one sample each per round)
     // eye and light centre in the body frame (host-computed once per launch)
     double eye_b[3], light_b[3];
 };
@@ -285,11 +290,14 @@ enum { M_IDLE = 0, M_START = 1, M_TRAV = 2, M_CAND = 3, M_BEGIN = 4 };
 constexpr int TRAV_BURST = 16;
 constexpr int CAND_GROUP = 20;     // run the float64 phase once this many lanes wait for it
 
-template <bool I16>
+// DEFER = true: the work list is the fast kernel's deferred list; a lane then owns one (pixel, sample mask)
+// entry, traces exactly the samples in the mask and adds their radiance to what the fast kernel wrote.
+template <bool I16, bool DEFER>
 __global__ void __launch_bounds__(128, 3)
 trace_kernel_persistent(const __grid_constant__ RenderArgs A) {
     const int lane = threadIdx.x & 31;
-    const unsigned total = A.work_counter[1];             // list length, written by cull_kernel
+    const unsigned total = A.work_counter[DEFER ? 3 : 1]; // list length, written by cull_kernel / trace_kernel_fast
+    unsigned mask = 0;
     const float Rf = (float)A.sp.radius;
 
     Counters cnt = {0u, 0u, 0u};
@@ -309,11 +317,15 @@ trace_kernel_persistent(const __grid_constant__ RenderArgs A) {
 
     auto retire_sample = [&]() {
         // next sample of the same pixel, or write the pixel back and free the lane
-        if (++sm < A.sample0 + A.nsamples) mode = M_START;
+        bool more;
+        if (DEFER) { mask &= mask - 1u; more = mask != 0u; if (more) sm = A.sample0 + (unsigned)(__ffs(mask) - 1); }
+        else more = ++sm < A.sample0 + A.nsamples;
+        if (more) mode = M_START;
         else {
             float4* ap = A.accum + (size_t)y * A.width + x;
             float4 old = *ap;
-            old.x += acc.x; old.y += acc.y; old.z += acc.z; old.w += (float)A.nsamples;
+            old.x += acc.x; old.y += acc.y; old.z += acc.z;
+            if (!DEFER) old.w += (float)A.nsamples;             // the fast kernel has counted its deferred samples
             *ap = old;
             mode = M_IDLE;
         }
@@ -339,10 +351,12 @@ trace_kernel_persistent(const __grid_constant__ RenderArgs A) {
             if (mode == M_IDLE) {
                 const unsigned p = base + (unsigned)__popc(idle & ((1u << lane) - 1u));
                 if (p < total) {
-                    const unsigned packed = A.pixel_list[p];
+                    unsigned packed;
+                    if (DEFER) { const uint2 e = A.defer_list[p]; packed = e.x; mask = e.y; }
+                    else packed = A.pixel_list[p];
                     x = (int)(packed & 0xffffu); y = (int)(packed >> 16);
                     pixel = (uint32_t)y * (uint32_t)A.width + (uint32_t)x;
-                    sm = A.sample0;
+                    sm = DEFER ? A.sample0 + (unsigned)(__ffs(mask) - 1) : A.sample0;
                     acc = make_float3(0.f, 0.f, 0.f);
                     mode = M_START;
                 }
@@ -441,6 +455,250 @@ trace_kernel_persistent(const __grid_constant__ RenderArgs A) {
     }
 }
 
+// ---- production path: filtered float32 kernel, one lane per (pixel, sample) -----------------------------
+// The exact machinery above costs ~2 500 float64 instructions per patch test and ~300 per node, executed by
+// ~10 of 32 lanes.  This kernel decides the same rays with trace_fast.cuh (float32 in a cell-local frame that
+// is re-based in float64 per candidate) in one tenth of the instructions, and is laid out for the SIMD
+// width instead of around it:
+//   * a warp owns 32 >> g_log2 neighbouring pixels, 2^g_log2 lanes share one pixel and trace one sample each,
+//     so the lanes of a warp walk the same pyramid nodes (coherent loads, similar trip counts);
+//   * while-while: lanes traverse until each holds a candidate patch (or has left the sphere), then all
+//     candidates are tested at one instruction; primary and shadow rays run through the same loop body;
+//   * per-pixel sums are reduced with shuffles: one accumulator read-modify-write per pixel;
+//   * warps claim tasks from a counter, so limb / terminator warps that walk hundreds of cells do not leave
+//     SMs idle at the end of the frame.
+// A sample the filter cannot certify (FT_DEFER) contributes nothing here; its bit is set in the pixel's entry of
+// the deferred list and trace_kernel_persistent<.., true> traces it exactly afterwards.
+__device__ __forceinline__ void primary_ray_fast(const RenderArgs& A, int x, int y, uint32_t pixel, unsigned sm, Ray64& R) {
+    const SceneParams& sp = A.sp;
+    const Camera& cam = A.cam;
+    const double aspect = (double)A.width / (double)A.height;
+    const double jx = sp.jitter ? rnd(pixel, sm, 0) : 0.5, jy = sp.jitter ? rnd(pixel, sm, 1) : 0.5;
+    const double sx = ((x + jx) / A.width * 2.0 - 1.0) * cam.tan_half_fov * aspect;
+    const double sy = (1.0 - (y + jy) / A.height * 2.0) * cam.tan_half_fov;
+    double d[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) d[a] = cam.w[a] + sx * cam.right[a] + sy * cam.up[a];
+    const double dn = d_rsqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) d[a] *= dn;
+    R.ox = A.eye_b[0]; R.oy = A.eye_b[1]; R.oz = A.eye_b[2];
+    R.dx = sp.ex[0] * d[0] + sp.ex[1] * d[1] + sp.ex[2] * d[2];
+    R.dy = sp.ey[0] * d[0] + sp.ey[1] * d[1] + sp.ey[2] * d[2];
+    R.dz = sp.ez[0] * d[0] + sp.ez[1] * d[1] + sp.ez[2] * d[2];
+    R.oo = R.ox * R.ox + R.oy * R.oy + R.oz * R.oz;
+    R.od = R.ox * R.dx + R.oy * R.dy + R.oz * R.dz;
+}
+
+// hit64 debug record (tests): everything from the float64 hit point
+__device__ __noinline__ void write_hit64(const RenderArgs& A, const Ray64& R, const FastHit& h, int x, int y) {
+    const double px = R.ox + h.s * R.dx, py = R.oy + h.s * R.dy, pz = R.oz + h.s * R.dz;
+    const double lon = ((h.c0 + 0.5 + (double)h.fc) / A.hf.W - 0.5) * (2.0 * PI_D);
+    const double lat = (0.5 - (h.r0 + 0.5 + (double)h.fr) / A.hf.H) * PI_D;
+    A.hit64[(size_t)y * A.width + x] = make_double4(h.s, sqrt(px * px + py * py + pz * pz), lon, lat);
+}
+
+// Lambert term, albedo and shadow ray of a primary hit; float32 except where positions near R are
+// added or subtracted.  Same model as shade_hit().
+__device__ __forceinline__ bool shade_fast(const RenderArgs& A, const Ray64& R, const FastHit& h, int x, int y,
+                                           uint32_t pixel, unsigned sm, float3& lit, Ray64& S) {
+    const SceneParams& sp = A.sp;
+    const double px = fma(h.s, R.dx, R.ox), py = fma(h.s, R.dy, R.oy), pz = fma(h.s, R.dz, R.oz);
+    const float fx = (float)px, fy = (float)py, fz = (float)pz;
+    // normal of r(lon, lat) = R * D: n ~ e_r - (r_lon / (r cos lat)) e_lon - (r_lat / r) e_lat
+    const float dD_dfc = fmaf(h.fr, (h.d11 - h.d10) - (h.d01 - h.d00), h.d01 - h.d00);
+    const float dD_dfr = fmaf(h.fc, (h.d11 - h.d01) - (h.d10 - h.d00), h.d10 - h.d00);
+    const float Rf = A.K.R;
+    const float r_lon = Rf * dD_dfc * A.K.Kw, r_lat = -Rf * dD_dfr * A.K.Kh;
+    const float rho2 = fmaf(fx, fx, fy * fy);
+    const float irho = f_rsqrt(rho2), ir = f_rsqrt(fmaf(fz, fz, rho2));
+    const float rho = rho2 * irho;
+    const float cl = rho * ir, sl = fz * ir, so = fx * irho, co = -fy * irho;
+    const float a1 = r_lon * irho, a2 = r_lat * ir;              // r_lon / (r cos lat), r_lat / r
+    float nx = cl * so - a1 * co + a2 * sl * so;
+    float ny = -cl * co - a1 * so - a2 * sl * co;
+    float nz = sl - a2 * cl;
+    const float nn = f_rsqrt(nx * nx + ny * ny + nz * nz);
+    nx *= nn; ny *= nn; nz *= nn;
+    // light sample
+    double tx = A.light_b[0] - px, ty = A.light_b[1] - py, tz = A.light_b[2] - pz;
+    const double idist = d_rsqrt(tx * tx + ty * ty + tz * tz);
+    if (sp.jitter && sp.light_radius > 0.0) {
+        // uniform point on the disk facing the hit (branchless ONB, Duff et al. 2017)
+        const float cx = (float)(tx * idist), cy = (float)(ty * idist), cz = (float)(tz * idist);
+        const float sg = cz >= 0.0f ? 1.0f : -1.0f, a = -1.0f / (sg + cz), b = cx * cy * a;
+        const float b1x = 1.0f + sg * cx * cx * a, b1y = sg * b, b1z = -sg * cx;
+        const float b2x = b, b2y = sg + cy * cy * a, b2z = -cy;
+        const float rr = (float)sp.light_radius * sqrtf((float)rnd(pixel, sm, 2));
+        float st, ct;
+        sincospif(2.0f * (float)rnd(pixel, sm, 3), &st, &ct);
+        tx += (double)(rr * (ct * b1x + st * b2x)); ty += (double)(rr * (ct * b1y + st * b2y)); tz += (double)(rr * (ct * b1z + st * b2z));
+    }
+    const double ln = d_rsqrt(tx * tx + ty * ty + tz * tz);
+    const double lx = tx * ln, ly = ty * ln, lz = tz * ln;
+    const float cosl = nx * (float)lx + ny * (float)ly + nz * (float)lz;
+    if (sm == A.sample0 && A.hit) {
+        // scene = pos + R^T p_body
+        const float hx = (float)(sp.pos[0] + sp.ex[0] * px + sp.ey[0] * py + sp.ez[0] * pz);
+        const float hy = (float)(sp.pos[1] + sp.ex[1] * px + sp.ey[1] * py + sp.ez[1] * pz);
+        const float hz = (float)(sp.pos[2] + sp.ex[2] * px + sp.ey[2] * py + sp.ez[2] * pz);
+        A.hit[(size_t)y * A.width + x] = make_float4(hx, hy, hz, (float)h.s);
+    }
+    if (A.hit64) write_hit64(A, R, h, x, y);
+    lit = make_float3(0.f, 0.f, 0.f);
+    if (!(cosl > 0.0f)) return false;
+    float3 alb = make_float3(1.0f, 1.0f, 1.0f);
+    if (A.tex.data) {
+        const int w = A.tex.W, hgt = A.tex.H;
+        const float u = ((float)h.c0 + 0.5f + h.fc) * ((float)w / (float)A.hf.W) - 0.5f;
+        const float v = ((float)h.r0 + 0.5f + h.fr) * ((float)hgt / (float)A.hf.H) - 0.5f;
+        const float fu = floorf(u);
+        int c0 = (int)fu;
+        const float fc = u - fu;
+        c0 = c0 < 0 ? c0 + w : (c0 >= w ? c0 - w : c0);
+        const int c1 = c0 + 1 == w ? 0 : c0 + 1;
+        const int r0 = min(max((int)floorf(v), 0), hgt - 2);
+        const float fr = fminf(fmaxf(v - (float)r0, 0.0f), 1.0f);
+        const uchar4 ta = __ldg(A.tex.data + (size_t)r0 * w + c0), tb = __ldg(A.tex.data + (size_t)r0 * w + c1);
+        const uchar4 tc = __ldg(A.tex.data + (size_t)(r0 + 1) * w + c0), td = __ldg(A.tex.data + (size_t)(r0 + 1) * w + c1);
+        const float w00 = (1.0f - fc) * (1.0f - fr), w01 = fc * (1.0f - fr), w10 = (1.0f - fc) * fr, w11 = fc * fr;
+        const float sc = 1.0f / 255.0f;
+        alb = make_float3((ta.x * w00 + tb.x * w01 + tc.x * w10 + td.x * w11) * sc,
+                          (ta.y * w00 + tb.y * w01 + tc.y * w10 + td.y * w11) * sc,
+                          (ta.z * w00 + tb.z * w01 + tc.z * w10 + td.z * w11) * sc);
+    }
+    const float q = (float)(sp.light_radius * idist);
+    const float E = (float)sp.light_radiance * q * q * cosl;
+    lit = make_float3(alb.x * E, alb.y * E, alb.z * E);
+    const double eps = sp.scene_epsilon;
+    S.ox = fma(eps, (double)nx, px); S.oy = fma(eps, (double)ny, py); S.oz = fma(eps, (double)nz, pz);
+    S.dx = lx; S.dy = ly; S.dz = lz;
+    S.oo = S.ox * S.ox + S.oy * S.oy + S.oz * S.oz;
+    S.od = S.ox * S.dx + S.oy * S.dy + S.oz * S.dz;
+    return sp.shadows != 0;
+}
+
+template <bool I16>
+__global__ void __launch_bounds__(128, 4)
+trace_kernel_fast(const __grid_constant__ RenderArgs A) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int gl = A.g_log2, g = 1 << gl;
+    const int sub = lane & (g - 1), pw = lane >> gl;         // lane within the pixel's group, pixel within the warp
+    const unsigned ppw = 32u >> gl;
+    const unsigned nkept = A.work_counter[1];
+    const unsigned ntasks = (nkept + ppw - 1u) / ppw;
+    const float Rf = A.K.R;
+    const unsigned rounds = (A.nsamples + (unsigned)g - 1u) >> gl;
+
+    Counters cnt = {0u, 0u, 0u};
+    RayStats rs = {0u, 0u, 0u, 0u, 0u};
+    unsigned n_defer = 0;
+
+    for (;;) {
+        unsigned task = 0;
+        if (lane == 0) task = atomicAdd(&A.work_counter[2], 1u);
+        task = __shfl_sync(FULL, task, 0);
+        if (task >= ntasks) break;
+        const unsigned p = task * ppw + (unsigned)pw;
+        const bool valid = p < nkept;
+        const unsigned packed = valid ? A.pixel_list[p] : 0u;
+        const int x = (int)(packed & 0xffffu), y = (int)(packed >> 16);
+        const uint32_t pixel = (uint32_t)y * (uint32_t)A.width + (uint32_t)x;
+        float3 acc = make_float3(0.f, 0.f, 0.f);
+        unsigned dmask = 0;                                  // group leader: deferred samples of this pixel
+
+#pragma unroll 1
+        for (unsigned rd = 0; rd < rounds; ++rd) {
+            const unsigned k = rd * (unsigned)g + (unsigned)sub;
+            const unsigned sm = A.sample0 + k;
+            const bool active = valid && k < A.nsamples;
+            Ray64 R;
+            Walk st;
+            FastHit fh;
+            float3 lit = make_float3(0.f, 0.f, 0.f);
+            bool defer = false, want = active, hit = false, entered = false, occluded = false, shadowed = false;
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {           // 0: primary ray, 1: shadow ray
+                bool alive = false;
+                if (want) {
+                    if (pass == 0) primary_ray_fast(A, x, y, pixel, sm, R);
+                    alive = walk_begin(A.hf, A.sp.radius, R, 0.0, pass ? 2 : A.hf.top - 3, st);
+                    if (pass == 0) entered = alive;
+                }
+                int res = FT_MISS;
+                while (__any_sync(FULL, alive)) {
+                    RawPatch P;
+                    float sx = 0.f;
+                    int face = 4;
+                    bool cand = false;
+                    if (alive) {
+                        for (;;) {
+                            const int r = walk_step<I16>(A.hf, Rf, A.inv_rs, st, P, sx, face, cnt);
+                            if (r == TR_CONTINUE) continue;
+                            if (r == TR_END) alive = false; else cand = true;
+                            break;
+                        }
+                    }
+                    __syncwarp();
+                    if (cand) {
+                        ++cnt.tests;
+                        const int t = fast_test<I16>(A.hf, A.K, R, st.s_in, 0.0, st.s, sx, st.smax, P, fh);
+                        if (t == FT_MISS) { if (!walk_advance(A.hf, st, sx, face)) alive = false; }
+                        else { res = t; alive = false; }
+                    }
+                }
+                if (res == FT_DEFER) defer = true;
+                if (pass == 0) {
+                    hit = res == FT_HIT;
+                    want = false;
+                    if (hit) {
+                        Ray64 S;
+                        want = shade_fast(A, R, fh, x, y, pixel, sm, lit, S);
+                        shadowed = want;
+                        if (want) R = S;
+                    }
+                    if (!__any_sync(FULL, want)) break;
+                } else if (want) {
+                    occluded = res == FT_HIT;
+                }
+            }
+            if (active && !defer) {
+                ++rs.primary;
+                if (entered) ++rs.inside;
+                if (hit) {
+                    ++rs.hits;
+                    if (shadowed) { ++rs.shadow; if (occluded) ++rs.occluded; }
+                    if (!occluded) { acc.x += lit.x; acc.y += lit.y; acc.z += lit.z; }
+                } else write_miss(A, x, y, sm == A.sample0);
+            }
+            // deferred samples of each pixel -> its leader's mask (bit = sample index in this launch)
+            const unsigned dm = __ballot_sync(FULL, defer);
+            if (dm) {
+                const unsigned gm = g == 32 ? dm : (dm >> (pw << gl)) & ((1u << g) - 1u);
+                dmask |= gm << (rd << gl);
+                if (defer) ++n_defer;
+            }
+        }
+        // per-pixel sum over the group's lanes, one read-modify-write per pixel
+        for (int o = g >> 1; o > 0; o >>= 1) {
+            acc.x += __shfl_xor_sync(FULL, acc.x, o);
+            acc.y += __shfl_xor_sync(FULL, acc.y, o);
+            acc.z += __shfl_xor_sync(FULL, acc.z, o);
+        }
+        if (valid && sub == 0) {
+            float4* ap = A.accum + (size_t)y * A.width + x;
+            float4 old = *ap;
+            old.x += acc.x; old.y += acc.y; old.z += acc.z; old.w += (float)A.nsamples;
+            *ap = old;
+            if (dmask) A.defer_list[atomicAdd(&A.work_counter[3], 1u)] = make_uint2(packed, dmask);
+        }
+    }
+    flush_counters(A, rs, cnt, lane);
+    const unsigned nd = __reduce_add_sync(FULL, n_defer);
+    if (lane == 0 && nd) atomicAdd(&A.counters[13], (unsigned long long)nd);
+}
+
 // K8: Gamma post-process + Overlay alpha blend -> RGBA8
 __global__ void resolve_kernel(const float4* __restrict__ accum, const uchar4* __restrict__ overlay,
                                uchar4* __restrict__ out, size_t n, float exposure, float inv_gamma) {
@@ -491,28 +749,71 @@ int launch_trace(mrtx_ctx* ctx, int x0, int y0, int x1, int y1, unsigned s0, uns
     const double lr[3] = {A.sp.light_pos[0] - A.sp.pos[0], A.sp.light_pos[1] - A.sp.pos[1], A.sp.light_pos[2] - A.sp.pos[2]};
     to_body(A.sp, er, A.eye_b);
     to_body(A.sp, lr, A.light_b);
-    if (ctx->sp.kernel == 0) {
+    A.defer_list = ctx->defer_list;
+    A.K = make_fast_consts(ctx->hf, ctx->sp.radius);
+    A.inv_rs = 1.0f / ctx->hf.radius_scale;
+    A.g_log2 = 0;
+    const bool i16 = ctx->hf.is_i16 != 0;
+    unsigned kernel = ctx->sp.kernel;
+    if (kernel == 2 && !A.K.enabled) kernel = 1;             // map too coarse for the filter: everything would defer
+    if (kernel == 0) {
         const dim3 block(8, 16);
         const dim3 grid((x1 - x0 + block.x - 1) / block.x, (y1 - y0 + block.y - 1) / block.y);
-        if (ctx->hf.is_i16) trace_kernel_simple<true><<<grid, block, 0, ctx->stream>>>(A);
-        else                trace_kernel_simple<false><<<grid, block, 0, ctx->stream>>>(A);
-    } else {
-        MRTX_CUDA(cudaMemsetAsync(A.work_counter, 0, 2 * sizeof(unsigned), ctx->stream));
-        {
-            const unsigned tiles_x = (unsigned)(x1 - x0 + 7) / 8u, tiles_y = (unsigned)(y1 - y0 + 3) / 4u;
-            const unsigned total = tiles_x * tiles_y * 32u;
-            cull_kernel<<<(total + 255u) / 256u, 256, 0, ctx->stream>>>(A);
-        }
+        if (i16) trace_kernel_simple<true><<<grid, block, 0, ctx->stream>>>(A);
+        else     trace_kernel_simple<false><<<grid, block, 0, ctx->stream>>>(A);
+        MRTX_CUDA(cudaGetLastError());
+        return MRTX_OK;
+    }
+    MRTX_CUDA(cudaMemsetAsync(A.work_counter, 0, 4 * sizeof(unsigned), ctx->stream));
+    {
+        const unsigned tiles_x = (unsigned)(x1 - x0 + 7) / 8u, tiles_y = (unsigned)(y1 - y0 + 3) / 4u;
+        const unsigned total = tiles_x * tiles_y * 32u;
+        cull_kernel<<<(total + 255u) / 256u, 256, 0, ctx->stream>>>(A);
+    }
+    const long long npix = (long long)(x1 - x0) * (y1 - y0);
+    if (kernel == 1) {
         int per_sm = 0;
-        if (ctx->hf.is_i16) MRTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel_persistent<true>, 128, 0));
-        else                MRTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel_persistent<false>, 128, 0));
+        if (i16) MRTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel_persistent<true, false>, 128, 0));
+        else     MRTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel_persistent<false, false>, 128, 0));
         if (per_sm < 1) per_sm = 1;
-        const long long warps_needed = ((long long)(x1 - x0) * (y1 - y0) + 31) / 32;
+        const long long warps_needed = (npix + 31) / 32;
         long long blocks = (long long)ctx->sm_count * per_sm;
         if (blocks * 4 > warps_needed) blocks = (warps_needed + 3) / 4;     // small rectangles: fewer blocks
         if (blocks < 1) blocks = 1;
-        if (ctx->hf.is_i16) trace_kernel_persistent<true><<<(unsigned)blocks, 128, 0, ctx->stream>>>(A);
-        else                trace_kernel_persistent<false><<<(unsigned)blocks, 128, 0, ctx->stream>>>(A);
+        if (i16) trace_kernel_persistent<true, false><<<(unsigned)blocks, 128, 0, ctx->stream>>>(A);
+        else     trace_kernel_persistent<false, false><<<(unsigned)blocks, 128, 0, ctx->stream>>>(A);
+    } else {
+        // filtered kernel in chunks of <= 32 samples (one mask bit per sample in the deferred list), each
+        // followed by the exact kernel over whatever it deferred
+        int per_sm = 0, per_sm_x = 0;
+        if (i16) {
+            MRTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel_fast<true>, 128, 0));
+            MRTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_x, trace_kernel_persistent<true, true>, 128, 0));
+        } else {
+            MRTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel_fast<false>, 128, 0));
+            MRTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_x, trace_kernel_persistent<false, true>, 128, 0));
+        }
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm_x < 1) per_sm_x = 1;
+        for (unsigned done = 0; done < ns; done += 32u) {
+            const unsigned n = ns - done < 32u ? ns - done : 32u;
+            A.sample0 = s0 + done; A.nsamples = n;
+            int gl = 0;
+            while ((2u << gl) <= n && gl < 5) ++gl;
+            A.g_log2 = gl;
+            if (done) MRTX_CUDA(cudaMemsetAsync(A.work_counter + 2, 0, 2 * sizeof(unsigned), ctx->stream));
+            const long long warps_needed = ((npix << gl) + 31) / 32;
+            long long blocks = (long long)ctx->sm_count * per_sm;
+            if (blocks * 4 > warps_needed) blocks = (warps_needed + 3) / 4;
+            if (blocks < 1) blocks = 1;
+            if (i16) trace_kernel_fast<true><<<(unsigned)blocks, 128, 0, ctx->stream>>>(A);
+            else     trace_kernel_fast<false><<<(unsigned)blocks, 128, 0, ctx->stream>>>(A);
+            if (done) MRTX_CUDA(cudaMemsetAsync(A.work_counter, 0, sizeof(unsigned), ctx->stream));
+            long long xblocks = (long long)ctx->sm_count * per_sm_x;
+            if (xblocks * 128 > npix) xblocks = (npix + 127) / 128;
+            if (i16) trace_kernel_persistent<true, true><<<(unsigned)xblocks, 128, 0, ctx->stream>>>(A);
+            else     trace_kernel_persistent<false, true><<<(unsigned)xblocks, 128, 0, ctx->stream>>>(A);
+        }
     }
     MRTX_CUDA(cudaGetLastError());
     return MRTX_OK;

@@ -1,0 +1,426 @@
+// Filtered fast path of the ray / height-field intersection (K5, K6).
+//
+// trace_core.cuh decides every candidate patch with ~2 500 float64 instructions.  Almost all
+// of that precision is spent on cancellation: f(s) = |p(s)| - R*D(u, v) subtracts two numbers
+// near R = 10 to find a root to 1e-10 R.  Here the same function is evaluated in a frame in which
+// nothing is large:
+//
+//   * origin on the sphere of radius R*D00 at the patch's north-west corner (lambda_w, phi_n),
+//     axes east / north / up there.  The ray is moved into that frame ONCE per candidate in
+//     float64 (about 25 DFMA, walls from the same float64 tables the exact test uses) and is
+//     then a float32 line  (a, b, c)(t) = (a0, b0, c0) + t (da, db, dc)  whose coordinates are of
+//     the size of one cell;
+//   * longitude / latitude offsets from the corner are small-angle arctangents of ratios of
+//     those coordinates, the height above the corner sphere is c + (a^2 + b^2) / (r + R + c):
+//     no cancellation anywhere, so float32 keeps ~1e-10 R in f where the global form keeps 1e-7 R.
+//
+// The result is a FILTER, not a replacement: every decision carries a margin (FastConsts::mg), and
+// whatever falls inside a margin - grazing double roots, a ray that enters a cell already below
+// the surface, polar-cap rows, ill-conditioned roots - returns FT_DEFER.  Deferred samples are
+// re-traced from scratch by the exact kernel, so the rendered frame never depends on a float32
+// decision that float64 could have made differently.
+#pragma once
+
+#include "trace_core.cuh"
+
+namespace mrtx_core {
+
+enum { FT_MISS = 0, FT_HIT = 1, FT_DEFER = 2 };
+
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ float f_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float f_rsqrt(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+#else
+static inline float f_rcp(float x) { return 1.0f / x; }
+static inline float f_rsqrt(float x) { return 1.0f / sqrtf(x); }
+#endif
+
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ float f_sqrt_fast(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float f_rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+#else
+static inline float f_sqrt_fast(float x) { return sqrtf(x); }
+static inline float f_rcp_fast(float x) { return 1.0f / x; }
+#endif
+
+// 1/sqrt(x) in float64 from the float32 seed (two Newton steps: 1e-7 -> 1e-14 -> rounding)
+MRTX_HD inline double d_rsqrt(double x) {
+    double y = (double)f_rsqrt((float)x);
+    y = y * fma(-0.5 * x, y * y, 1.5);
+    y = y * fma(-0.5 * x, y * y, 1.5);
+    return y;
+}
+
+struct FastConsts {
+    float R;            // sphere radius
+    float Kw, Kh;       // texels per radian: W / 2 pi, H / pi
+    float mg;           // |f| below this is "on the surface": undecidable in float32
+    float pad;          // float32 traversal parameter slack
+    float epsc;         // a root this far outside the cell (in cells) still belongs to it
+    float ds_tol;       // a root must be located to this (ray parameter) or the sample is deferred
+    int   enabled;      // 0: map too coarse for the small-angle series (W < 360) -> always defer
+};
+
+MRTX_HD inline FastConsts make_fast_consts(const HeightField& hf, double radius) {
+    FastConsts K;
+    K.R = (float)radius;
+    K.Kw = (float)(hf.W / (2.0 * PI_D));
+    K.Kh = (float)(hf.H / PI_D);
+    K.mg = (float)(2.0e-9 * radius);
+    K.pad = (float)(4.0e-6 * radius);
+    K.epsc = 2.0e-5f;
+    K.ds_tol = (float)(1.0e-4 * 2.0 * PI_D * radius / hf.W);     // 1e-4 texel
+    K.enabled = hf.W >= 360 && hf.H >= 180;
+    return K;
+}
+
+// Raw patch as the traversal loaded it: texel values before decoding (int16 counts as floats, or D).
+struct RawPatch { int r0, c0; float v00, v01, v10, v11; };
+
+template <bool I16>
+MRTX_HD inline float decode_exact(const HeightField& hf, float v) {
+    // exactly data_loader.py:219-242: *scale, +1, /radius_scale, one rounding each
+    return I16 ? mrtx_fdiv(mrtx_fadd(mrtx_fmul(v, hf.scale), 1.0f), hf.radius_scale) : v;
+}
+// for the traversal's conservative bounds two roundings fewer are fine (covered by its margin)
+template <bool I16>
+MRTX_HD inline float decode_bound(const HeightField& hf, float v, float inv_rs) {
+    return I16 ? fmaf(v, hf.scale, 1.0f) * inv_rs : v;
+}
+
+struct FastHit {
+    double s;               // ray parameter of the hit
+    float fc, fr;           // position in the patch, cells from the west wall / north row
+    float d00, d01, d10, d11;
+    int r0, c0;
+};
+
+// One evaluation of f in the local frame; also yields the in-cell coordinates.
+struct LocalRay {
+    float a0, b0, c0, da, db, dc;       // east, north, up (above the corner sphere R*D00)
+    float nk, nc;                       // sin, cos of the north row's latitude
+    float Rc0;                          // R * D00: radius of the corner sphere
+    float e01, e10, exx;                // R * (D01-D00), R * (D10-D00), R * (D11-D10-D01+D00)
+};
+
+MRTX_HD inline float local_f(const LocalRay& Q, const FastConsts& K, float t, float& fc, float& fr) {
+    const float a = fmaf(t, Q.da, Q.a0), b = fmaf(t, Q.db, Q.b0), c = fmaf(t, Q.dc, Q.c0);
+    const float Rc = Q.Rc0 + c;
+    const float hh = fmaf(Q.nc, Rc, -Q.nk * b);                 // horizontal distance from the polar axis (towards lambda_w)
+    const float q = a * f_rcp(hh), q2 = q * q;
+    fc = K.Kw * q * fmaf(q2, fmaf(q2, 0.2f, -0.33333334f), 1.0f);           // atan(q) * W / 2 pi
+    const float u = 0.5f * a * q * fmaf(-0.25f, q2, 1.0f);      // rho - hh = a^2 / (rho + hh)
+    const float v = fmaf(-Q.nk, u, b) * f_rcp(fmaf(Q.nc, u, Rc)), v2 = v * v;
+    fr = -K.Kh * v * fmaf(v2, fmaf(v2, 0.2f, -0.33333334f), 1.0f);          // -atan(v) * H / pi
+    const float rr2 = fmaf(a, a, b * b);
+    const float r = f_sqrt_fast(fmaf(Rc, Rc, rr2));
+    const float hr = fmaf(rr2, f_rcp(r + Rc), c);               // |p| - R*D00
+    const float dd = fmaf(fc, Q.e01, fr * fmaf(fc, Q.exx, Q.e10));          // R*(D(fc, fr) - D00)
+    return hr - dd;
+}
+
+// Decide one candidate patch.  [ws, we]: the float32 traversal's window (relative to s_in);
+// s_lo, s_in + smax: the extent of the ray.
+template <bool I16>
+MRTX_HD inline int fast_test(const HeightField& hf, const FastConsts& K, const Ray64& R, double s_in, double s_lo,
+                             float ws, float we, float smax, const RawPatch& P, FastHit& out) {
+    if (!K.enabled || P.r0 <= 0 || P.r0 >= hf.H - 2) return FT_DEFER;       // polar caps: rows clamp, no wall
+    const float d00 = decode_exact<I16>(hf, P.v00), d01 = decode_exact<I16>(hf, P.v01);
+    const float d10 = decode_exact<I16>(hf, P.v10), d11 = decode_exact<I16>(hf, P.v11);
+    const double2 w = MRTX_LDG(hf.lon64 + P.c0), n = MRTX_LDG(hf.lat64 + P.r0);   // (cos, sin) lon_w; (sin, cos) lat_n
+    const double s_c = s_in + (double)ws;
+    LocalRay Q;
+    {
+        const double px = fma(s_c, R.dx, R.ox), py = fma(s_c, R.dy, R.oy), pz = fma(s_c, R.dz, R.oz);
+        const double a0 = px * w.x + py * w.y, m0 = px * w.y - py * w.x;
+        const double da = R.dx * w.x + R.dy * w.y, dm = R.dx * w.y - R.dy * w.x;
+        const double Rc0 = (double)K.R * (double)d00;
+        Q.a0 = (float)a0; Q.da = (float)da;
+        Q.b0 = (float)(n.y * pz - n.x * m0); Q.db = (float)(n.y * R.dz - n.x * dm);
+        Q.c0 = (float)(fma(n.y, m0, n.x * pz) - Rc0); Q.dc = (float)fma(n.y, dm, n.x * R.dz);
+        Q.nk = (float)n.x; Q.nc = (float)n.y; Q.Rc0 = (float)Rc0;
+    }
+    Q.e01 = K.R * (d01 - d00); Q.e10 = K.R * (d10 - d00); Q.exx = K.R * ((d11 - d10) - (d01 - d00));
+
+    float ta = fmaxf(-K.pad, (float)(s_lo - s_c)), tb = fminf((we - ws) + K.pad, smax - ws);
+    if (!(tb > ta)) return FT_MISS;
+    float fc, fr;
+    // start of the window: the ray must be clear of the surface there
+    float fa = local_f(Q, K, ta, fc, fr);
+    if (!(fa > K.mg)) {
+        // inside the cell that is "entered below the surface" (the exact test walks back); in the
+        // slack before the cell the patch is only an extrapolation: retry at the nominal entry
+        const bool inside = fc >= -K.epsc && fc <= 1.0f + K.epsc && fr >= -K.epsc && fr <= 1.0f + K.epsc;
+        if (inside || !(ta + K.pad < tb)) return FT_DEFER;
+        ta += K.pad;
+        fa = local_f(Q, K, ta, fc, fr);
+        if (!(fa > K.mg)) return FT_DEFER;
+    }
+    const float fca = fc, fra = fr;
+    const float fb = local_f(Q, K, tb, fc, fr);
+    const float dfc = fc - fca, dfr = fr - fra;                 // direction of travel through the cell
+    const float tm = 0.5f * (ta + tb), h = 0.5f * (tb - ta);
+    const float fm = local_f(Q, K, tm, fc, fr);
+    // f ~ fm + c1 tau + c2 tau^2 (a bilinear patch along a nearly straight track)
+    const float ih = f_rcp(h);
+    const float c2 = 0.5f * (fa - 2.0f * fm + fb) * ih * ih, c1 = 0.5f * (fb - fa) * ih;
+    float lo, hi;
+    if (fm < -K.mg) { lo = -h; hi = 0.0f; }
+    else if (!(fm > K.mg)) return FT_DEFER;
+    else if (fb < -K.mg) { lo = 0.0f; hi = h; }
+    else if (!(fb > K.mg)) return FT_DEFER;
+    else {
+        // no sign change at the three samples: a grazing double root shows up as a dip
+        if (!(c2 > 0.0f)) return FT_MISS;
+        const float tv = -0.5f * c1 / c2;
+        if (!(tv > -h && tv < h)) return FT_MISS;
+        const float qv = fm - 0.25f * c1 * c1 / c2;
+        if (qv > 0.25f * fminf(fm, fminf(fa, fb))) return FT_MISS;          // dip clear of zero
+        const float fv = local_f(Q, K, tm + tv, fc, fr);
+        if (fv > K.mg + 0.05f * c2 * h * h) return FT_MISS;
+        if (!(fv < -K.mg)) return FT_DEFER;
+        lo = tv > 0.0f ? 0.0f : -h; hi = tv;
+    }
+    // the parabola's root inside the bracket, polished on f itself
+    float tau = 0.5f * (lo + hi);
+    {
+        const float disc = c1 * c1 - 4.0f * c2 * fm;
+        if (disc >= 0.0f) {
+            const float sq = f_sqrt_fast(disc);
+            const float tq = -0.5f * (c1 + (c1 >= 0.0f ? sq : -sq));
+            const float t1 = c2 != 0.0f ? tq / c2 : 2.0f * h, t2 = tq != 0.0f ? fm / tq : 2.0f * h;
+            const bool in1 = t1 > lo && t1 < hi, in2 = t2 > lo && t2 < hi;
+            if (in1) tau = t1;
+            if (in2 && (!in1 || t2 < t1)) tau = t2;
+        }
+    }
+    float fx = 0.0f, slope = 0.0f;
+#pragma unroll
+    for (int it = 0; it < 3; ++it) {
+        fx = local_f(Q, K, tm + tau, fc, fr);
+        slope = fmaf(2.0f * c2, tau, c1);
+        if (it == 2) break;
+        if (!(slope < 0.0f)) return FT_DEFER;                   // the first crossing goes downwards
+        tau -= fx / slope;
+        if (!(tau >= lo - K.pad && tau <= hi + K.pad)) return FT_DEFER;
+    }
+    if (!(slope < 0.0f) || !(fabsf(fx) <= -slope * K.ds_tol) || !(fabsf(fx) <= 64.0f * K.mg)) return FT_DEFER;
+    // whose root is it?  Outside the cell and moving further out: the ray left the cell before it
+    // reached the surface (the next cell decides).  Outside and moving in: the ray was already
+    // below the surface when it entered -> exact path.
+    const float e = K.epsc;
+    if (fc < -e) { if (dfc < 0.0f) return FT_MISS; return FT_DEFER; }
+    if (fc > 1.0f + e) { if (dfc > 0.0f) return FT_MISS; return FT_DEFER; }
+    if (fr < -e) { if (dfr < 0.0f) return FT_MISS; return FT_DEFER; }
+    if (fr > 1.0f + e) { if (dfr > 0.0f) return FT_MISS; return FT_DEFER; }
+    out.s = s_c + (double)(tm + tau);
+    out.fc = fminf(fmaxf(fc, 0.0f), 1.0f); out.fr = fminf(fmaxf(fr, 0.0f), 1.0f);
+    out.d00 = d00; out.d01 = d01; out.d10 = d10; out.d11 = d11;
+    out.r0 = P.r0; out.c0 = P.c0;
+    return FT_HIT;
+}
+
+// ---- directional walk ----------------------------------------------------------------------------
+// trav_step() solves all four walls of a cell at every node (two planes, two cones, each with its on-wall
+// rules): ~600 instructions, most of them predicated off for most lanes.  A straight ray, however,
+//   * turns about the polar axis in ONE sense for its whole length (x dy - y dx is constant), so of the
+//     two longitude walls only the one ahead can ever be crossed, and
+//   * has a single turning point in latitude (d(z/r)/ds has the sign of n0 + s n1, linear in s), so only
+//     the latitude wall ahead matters, except in the one cell that contains the turning point.
+// One plane and one cone per node, no wall can be crossed backwards, and the rule "within tol of the wall
+// ahead = on it, leave now" is all the rounding protection that is needed.  Margins, pads and the
+// conservative overlap test are those of trav_step().
+struct Walk {
+    float ox, oy, oz, dx, dy, dz, oo, od, smax;   // ray re-based at the bounding-sphere entry s_in
+    float n0, n1;           // heading in latitude: northwards where n0 + s n1 > 0
+    float s;                // current parameter (relative to s_in)
+    int L, J, I;            // current cell
+    int steps;
+    bool east;              // longitude increases along the ray
+    double s_in;
+};
+
+MRTX_HD inline float walk_r2(const Walk& w, float s) { return fmaf(s, fmaf(2.0f, w.od, s), w.oo); }
+
+MRTX_HD inline bool walk_begin(const HeightField& hf, double radius, const Ray64& R, double s_min, int start_level, Walk& w) {
+    const double Rb = radius * (double)hf.dmax;
+    const double disc = R.od * R.od - (R.oo - Rb * Rb);
+    if (!(disc > 0.0)) return false;
+    const double sq = disc * d_rsqrt(disc);
+    const double s_end = -R.od + sq;
+    if (s_end <= s_min) return false;
+    const double s_in = fmax(s_min, -R.od - sq);
+    w.s_in = s_in;
+    w.ox = (float)fma(s_in, R.dx, R.ox); w.oy = (float)fma(s_in, R.dy, R.oy); w.oz = (float)fma(s_in, R.dz, R.oz);
+    w.dx = (float)R.dx; w.dy = (float)R.dy; w.dz = (float)R.dz;
+    w.oo = w.ox * w.ox + w.oy * w.oy + w.oz * w.oz;
+    w.od = w.ox * w.dx + w.oy * w.dy + w.oz * w.dz;
+    w.smax = (float)(s_end - s_in);
+    w.east = w.ox * w.dy - w.oy * w.dx > 0.0f;
+    w.n0 = w.dz * w.oo - w.oz * w.od; w.n1 = w.dz * w.od - w.oz;
+    const int W = hf.W, H = hf.H;
+    const int L = min(max(start_level, 0), hf.top);
+    // first cell from the position just inside (a wrong neighbour is corrected by the on-wall rule)
+    const float t0 = fminf(1e-5f * (float)radius, 0.5f * w.smax);
+    const float x = fmaf(t0, w.dx, w.ox), y = fmaf(t0, w.dy, w.oy), z = fmaf(t0, w.dz, w.oz);
+    const float lon = atan2f(x, -y), lat = atan2f(z, sqrtf(x * x + y * y));
+    const float u = (lon * (0.5f / PI_F) + 0.5f) * (float)W - 0.5f, v = (0.5f - lat * (1.0f / PI_F)) * (float)H - 0.5f;
+    int c0 = (int)floorf(u);
+    c0 = c0 < 0 ? c0 + W : (c0 >= W ? c0 - W : c0);
+    const int r0 = min(max((int)floorf(v), 0), H - 2);
+    w.L = L; w.J = r0 >> L; w.I = c0 >> L;
+    w.s = 0.0f; w.steps = 0;
+    return true;
+}
+
+// smallest crossing of the cone z = k r in (lo, hi], or +inf
+MRTX_HD inline float lat_cross(const Walk& w, float k, float lo, float hi) {
+    const float k2 = k * k;
+    const float A = fmaf(w.dz, w.dz, -k2), B = fmaf(w.oz, w.dz, -k2 * w.od), C = fmaf(w.oz, w.oz, -k2 * w.oo);
+    const float disc = fmaf(B, B, -A * C);
+    float best = INFINITY;
+    if (disc >= 0.0f) {
+        const float q = -(B + copysignf(f_sqrt_fast(disc), B));
+        const float r1 = q * f_rcp_fast(A), r2 = C * f_rcp_fast(q);     // A or q zero: inf / nan, rejected below
+        if (r1 > lo && r1 <= hi && fmaf(r1, w.dz, w.oz) * k >= 0.0f) best = r1;
+        if (r2 > lo && r2 <= hi && r2 < best && fmaf(r2, w.dz, w.oz) * k >= 0.0f) best = r2;
+    }
+    return best;
+}
+
+// faces: 0 longitude wall ahead, 1 north wall, 2 south wall, 4 end of the ray
+MRTX_HD inline bool walk_advance(const HeightField& hf, Walk& w, float sx, int face) {
+    if (face == 4) return false;
+    w.s = sx;
+    int L = w.L, J = w.J, I = w.I;
+    bool up;
+    if (face == 0) {
+        if (w.east) { I += 1; if (I >= hf.nx[L]) I = 0; up = (I & 1) == 0; }
+        else { up = (I & 1) == 0; I -= 1; if (I < 0) I = hf.nx[L] - 1; }
+    } else if (face == 2) { J += 1; up = (J & 1) == 0; }
+    else { up = (J & 1) == 0; J -= 1; }
+    if (J < 0 || J >= hf.ny[L]) return false;                // cannot happen (caps have no wall); be safe
+    if (up && L < hf.top) { L += 1; I >>= 1; J >>= 1; }
+    w.L = L; w.J = J; w.I = I;
+    return true;
+}
+
+template <bool I16>
+MRTX_HD inline int walk_step(const HeightField& hf, float Rf, float inv_rs, Walk& w, RawPatch& P,
+                             float& sx_out, int& face_out, Counters& cnt) {
+    if (++w.steps > MAX_STEPS) { ++cnt.overflow; return TR_END; }
+    const int L = w.L, J = w.J, I = w.I;
+    const int W = hf.W, H = hf.H;
+    const float s = w.s;
+    ++cnt.nodes;
+    float vmax;
+    if (L == 0) {
+        const int c1 = I + 1 == W ? 0 : I + 1;
+        P.r0 = J; P.c0 = I;
+        if (I16) {
+            const int16_t* b = (const int16_t*)hf.base + (size_t)J * W;
+            P.v00 = (float)MRTX_LDG(b + I); P.v01 = (float)MRTX_LDG(b + c1);
+            P.v10 = (float)MRTX_LDG(b + W + I); P.v11 = (float)MRTX_LDG(b + W + c1);
+        } else {
+            const float* b = (const float*)hf.base + (size_t)J * W;
+            P.v00 = MRTX_LDG(b + I); P.v01 = MRTX_LDG(b + c1);
+            P.v10 = MRTX_LDG(b + W + I); P.v11 = MRTX_LDG(b + W + c1);
+        }
+        vmax = fmaxf(fmaxf(P.v00, P.v01), fmaxf(P.v10, P.v11));
+    } else {
+        vmax = I16 ? (float)MRTX_LDG((const int16_t*)hf.level[L] + (size_t)J * hf.nx[L] + I)
+                   : MRTX_LDG((const float*)hf.level[L] + (size_t)J * hf.nx[L] + I);
+    }
+    const float dmax = decode_bound<I16>(hf, vmax, inv_rs);
+    const float marg = 3.0e-6f * Rf;                        // float32 error of a radius near R + the cheap decode
+    const float rc = fmaf(Rf, dmax, marg), rc2 = rc * rc;
+    const float r2s = walk_r2(w, s);
+    float sd = s;
+    if (!(r2s <= rc2 && L > 0)) {       // (inside the cell's shell already: descend where we stand)
+        const float x = fmaf(s, w.dx, w.ox), y = fmaf(s, w.dy, w.oy), z = fmaf(s, w.dz, w.oz);
+        const float rs = f_sqrt_fast(fmaxf(r2s, 1e-30f));
+        const float tol = 2.0e-6f * rs;
+        float sx = w.smax;
+        int face = 4;
+        {   // the longitude wall ahead
+            const int wi = w.east ? min((I + 1) << L, W) : (I << L);
+            const float2 wl = MRTX_LDG(hf.lon32 + wi);
+            const float sg = w.east ? 1.0f : -1.0f;
+            const float g = sg * fmaf(x, wl.x, y * wl.y), dg = sg * fmaf(w.dx, wl.x, w.dy * wl.y);      // outwards positive
+            if (dg > 0.0f) {
+                if (g >= -tol) { sx = s; face = 0; }            // on (or just beyond) it, moving out: leave now
+                else {
+                    const float sc = s - g * f_rcp_fast(dg);
+                    const float px = fmaf(sc, w.dx, w.ox), py = fmaf(sc, w.dy, w.oy);
+                    if (px * wl.y - py * wl.x > 0.0f && sc < sx) { sx = sc; face = 0; }     // not the opposite half-plane
+                }
+            }
+        }
+        if (sx > s) {   // the latitude wall ahead
+            const bool north = fmaf(s, w.n1, w.n0) > 0.0f;
+            float s_turn = INFINITY;                            // where the heading reverses, if that is still ahead
+            if (w.n1 != 0.0f) { const float t = -w.n0 * f_rcp_fast(w.n1); if (t > s) s_turn = t; }
+            const int jn = J << L, js = min((J + 1) << L, H - 1);
+            float sl = INFINITY;
+            int fl = north ? 1 : 2;
+            if (north ? jn > 0 : js < H - 1) {                  // polar caps have no wall
+                const float k = MRTX_LDG(hf.lat32 + (north ? jn : js));
+                const float G = north ? z - k * rs : k * rs - z;        // outwards positive
+                sl = G >= -tol ? s : lat_cross(w, k, s, s_turn);
+            }
+            if (!(sl <= s_turn) && s_turn < sx) {
+                // the ray turns inside this cell: from there on it heads for the other wall
+                sl = INFINITY; fl = north ? 2 : 1;
+                if (north ? js < H - 1 : jn > 0) sl = lat_cross(w, MRTX_LDG(hf.lat32 + (north ? js : jn)), s_turn, INFINITY);
+            }
+            if (sl < sx) { sx = sl; face = fl; }
+        }
+        const float pad = 4.0e-6f * Rf;
+        const float ta = fmaxf(s - pad, 0.0f), tb = fminf(sx + pad, w.smax);
+        const float tm = fminf(fmaxf(-w.od, ta), tb);
+        if (!(walk_r2(w, tm) <= rc2)) return walk_advance(hf, w, sx, face) ? TR_CONTINUE : TR_END;
+        if (L == 0) { sx_out = sx; face_out = face; return TR_CANDIDATE; }
+        if (r2s > rc2) {
+            const float dq = fmaf(w.od, w.od, rc2 - w.oo);
+            if (dq > 0.0f) sd = fminf(fmaxf(-w.od - f_sqrt_fast(dq), s), sx);
+        }
+    }
+    // pick the child at sd
+    const float x = fmaf(sd, w.dx, w.ox), y = fmaf(sd, w.dy, w.oy), z = fmaf(sd, w.dz, w.oz);
+    const int mi = (2 * I + 1) << (L - 1), mj = (2 * J + 1) << (L - 1);
+    int ci = 2 * I, cj = 2 * J;
+    if (mi < min((I + 1) << L, W)) {
+        const float2 wl = MRTX_LDG(hf.lon32 + mi);
+        if (fmaf(x, wl.x, y * wl.y) >= 0.0f) ci += 1;
+    }
+    if (mj < min((J + 1) << L, H - 1)) {
+        const float k = MRTX_LDG(hf.lat32 + mj);
+        if (z - k * f_sqrt_fast(fmaf(x, x, fmaf(y, y, z * z))) < 0.0f) cj += 1;      // south of the mid wall
+    }
+    w.s = sd; w.L = L - 1; w.I = ci; w.J = cj;
+    return TR_CONTINUE;
+}
+
+// Sequential form (host tool): FT_HIT / FT_MISS / FT_DEFER for the whole ray.
+template <bool I16>
+MRTX_HD inline int trace_ray_fast(const HeightField& hf, const FastConsts& K, double radius, const Ray64& R, double s_min,
+                                  int start_level, FastHit& out, Counters& cnt) {
+    Walk w;
+    if (!walk_begin(hf, radius, R, s_min, start_level, w)) return FT_MISS;
+    const float Rf = (float)radius, inv_rs = 1.0f / hf.radius_scale;
+    for (;;) {
+        RawPatch P;
+        float sx;
+        int face;
+        const int r = walk_step<I16>(hf, Rf, inv_rs, w, P, sx, face, cnt);
+        if (r == TR_END) return FT_MISS;
+        if (r == TR_CANDIDATE) {
+            ++cnt.tests;
+            const int t = fast_test<I16>(hf, K, R, w.s_in, s_min, w.s, sx, w.smax, P, out);
+            if (t != FT_MISS) return t;
+            if (!walk_advance(hf, w, sx, face)) return FT_MISS;
+        }
+    }
+}
+
+}  // namespace mrtx_core

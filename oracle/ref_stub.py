@@ -40,7 +40,13 @@ class _Placeholder:
 def _module(name: str, **attrs) -> types.ModuleType:
     m = types.ModuleType(name)
     m.__dict__.update(attrs)
-    m.__getattr__ = lambda attr: _Placeholder  # any other symbol
+
+    def _any(attr):                 # any other symbol; dunders stay absent so `inspect` keeps working
+        if attr.startswith("__") and attr.endswith("__"):
+            raise AttributeError(attr)
+        return _Placeholder
+
+    m.__getattr__ = _any
     sys.modules[name] = m
     return m
 

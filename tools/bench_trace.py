@@ -77,5 +77,25 @@ if __name__ == "__main__":
         rt, info = setup(23040, 11520, 3840, 2160, ds=1)
     print(json.dumps(info))
     spps = [int(v) for v in sys.argv[2].split(',')] if len(sys.argv) > 2 else ((1, 4) if which != "cfg3" else (1, 16))
+    kernels = [int(v) for v in os.environ.get("KERNELS", "2").split(",")]
+    lib, ctx = rt._dev.lib, rt._dev.ctx
+    imgs = {}
     for spp in spps:
-        print(json.dumps(time_frame(rt, spp)))
+        for k in kernels:
+            _lib.check(lib.mrtx_set_uint(ctx, b"kernel", k, 0))
+            r = time_frame(rt, spp)
+            r["kernel"] = k
+            print(json.dumps(r), flush=True)
+            _lib.check(lib.mrtx_resolve(ctx))
+            img = np.empty((rt._height, rt._width, 4), np.uint8)
+            _lib.check(lib.mrtx_read_rgba8(ctx, img.ctypes.data))
+            acc = np.empty((rt._height, rt._width, 4), np.float32)
+            _lib.check(lib.mrtx_read_accum_f32(ctx, acc.ctypes.data))
+            imgs[k] = (img, acc)
+        if len(kernels) > 1:
+            a, b = imgs[kernels[0]], imgs[kernels[1]]
+            d = np.abs(a[0][..., :3].astype(np.int32) - b[0][..., :3].astype(np.int32))
+            da = np.abs(a[1][..., :3] - b[1][..., :3])
+            print(json.dumps({"spp": spp, "compare": kernels[:2], "img_mae": float(d.mean()), "img_max": int(d.max()),
+                              "pixels_differ": int((d.max(axis=2) > 0).sum()), "pixels_differ_gt2": int((d.max(axis=2) > 2).sum()),
+                              "accum_max_abs": float(da.max()), "accum_w_equal": bool(np.array_equal(a[1][..., 3], b[1][..., 3]))}), flush=True)

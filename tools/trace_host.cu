@@ -1,7 +1,7 @@
 // DEVELOPMENT TOOL (not part of the product, never loaded by moonrtx_b200): runs the
 // __host__ __device__ traversal core of csrc/trace_core.cuh on the CPU so that parity
 // problems can be investigated against the oracle without a GPU.
-#include "../moonrtx_b200/csrc/trace_core.cuh"
+#include "../moonrtx_b200/csrc/trace_fast.cuh"
 #include <vector>
 #include <algorithm>
 
@@ -65,6 +65,36 @@ extern "C" int dbg_trace(const void* map, int is_i16, int W, int H, float scale,
         double* o = out + (size_t)i * 8;
         o[0] = t.hit; o[1] = t.hit ? t.s : -1; o[2] = t.hit && !any_hit ? t.info.r : 0; o[3] = t.hit && !any_hit ? t.info.lon : 0;
         o[4] = t.hit && !any_hit ? t.info.lat : 0; o[5] = c.nodes; o[6] = c.tests; o[7] = c.overflow;
+    }
+    return 0;
+}
+
+// fast (filtered float32) path: out[i] = {status (0 miss, 1 hit, 2 defer), s, fc, fr, r0, c0, nodes, tests}
+extern "C" int dbg_trace_fast(const void* map, int is_i16, int W, int H, float scale, float rs, float dmax,
+                              const double* rays, int n, double s_min, double radius, int start_level, double* out) {
+    HeightField hf;
+    memset(&hf, 0, sizeof(hf));
+    hf.base = map; hf.is_i16 = is_i16; hf.W = W; hf.H = H; hf.scale = scale; hf.radius_scale = rs; hf.dmax = dmax;
+    std::vector<std::vector<int16_t>> s16; std::vector<std::vector<float>> s32;
+    if (is_i16) build_host_pyramid<int16_t>(hf, s16); else build_host_pyramid<float>(hf, s32);
+    std::vector<float2> lon32(W + 1); std::vector<double2> lon64(W + 1), lat64(H); std::vector<float> lat32(H);
+    for (int i = 0; i <= W; ++i) { double sn, cs; sincospi((2.0 * i + 1.0) / W - 1.0, &sn, &cs); lon64[i] = make_double2(cs, sn); lon32[i] = make_float2((float)cs, (float)sn); }
+    for (int i = 0; i < H; ++i) { double sn, cs; sincospi((i + 0.5) / H, &sn, &cs); lat64[i] = make_double2(cs, sn); lat32[i] = (float)cs; }
+    hf.lon32 = lon32.data(); hf.lon64 = lon64.data(); hf.lat32 = lat32.data(); hf.lat64 = lat64.data();
+    if (start_level < 0) start_level = hf.top + start_level;
+    const FastConsts K = make_fast_consts(hf, radius);
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int i = 0; i < n; ++i) {
+        const double* q = rays + (size_t)i * 6;
+        Ray64 R;
+        R.ox = q[0]; R.oy = q[1]; R.oz = q[2]; R.dx = q[3]; R.dy = q[4]; R.dz = q[5];
+        R.oo = R.ox * R.ox + R.oy * R.oy + R.oz * R.oz; R.od = R.ox * R.dx + R.oy * R.dy + R.oz * R.dz;
+        FastHit fh; Counters c = {0, 0, 0};
+        memset(&fh, 0, sizeof(fh));
+        int st = is_i16 ? trace_ray_fast<true>(hf, K, radius, R, s_min, start_level, fh, c)
+                        : trace_ray_fast<false>(hf, K, radius, R, s_min, start_level, fh, c);
+        double* o = out + (size_t)i * 8;
+        o[0] = st; o[1] = st == FT_HIT ? fh.s : -1; o[2] = fh.fc; o[3] = fh.fr; o[4] = fh.r0; o[5] = fh.c0; o[6] = c.nodes; o[7] = c.tests;
     }
     return 0;
 }
