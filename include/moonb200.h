@@ -159,6 +159,12 @@ int  mrtx_read_hit_f64(mrtx_ctx* ctx, double* out);
  * [8] float64 test phases executed, [9] lanes in them, [10] traversal steps executed (per warp),
  * [11] lanes in them, [12] ray-start phases, [13] lanes in them, [14] refills, [15] pixels culled */
 int  mrtx_counters(mrtx_ctx* ctx, uint64_t out[16], int reset);
+/* the filtered kernel's deferrals since the last reset: [0] samples handed to the exact kernel;
+ * [r] / [16 + r] primary / shadow rays deferred for reason r: 1 polar-cap row or map too coarse,
+ * 2 ray enters the cell below the surface, 3-4 window start on the surface, 5-6 middle / end of the
+ * window on the surface, 7 grazing double root, 8-9 root search left its bracket, 10 ill-conditioned
+ * root, 11 residual too large, 12-13 root before the cell's longitude / latitude range            */
+int  mrtx_defer_stats(mrtx_ctx* ctx, uint64_t out[32], int reset);
 
 /* ---- multi-GPU (one process per GPU) ----------------------------------------------
  * NCCL is loaded at run time from `libnccl_path` (the torch-bundled libnccl.so.2).     */

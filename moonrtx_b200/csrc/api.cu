@@ -57,6 +57,8 @@ int mrtx_create(int device, mrtx_ctx** out_ctx) {
     MRTX_CUDA(cudaMalloc(&c->d_work, 8 * sizeof(unsigned)));
     MRTX_CUDA(cudaMalloc(&c->d_counters, 16 * sizeof(unsigned long long)));
     MRTX_CUDA(cudaMemset(c->d_counters, 0, 16 * sizeof(unsigned long long)));
+    MRTX_CUDA(cudaMalloc(&c->d_defer_stats, 32 * sizeof(unsigned long long)));
+    MRTX_CUDA(cudaMemset(c->d_defer_stats, 0, 32 * sizeof(unsigned long long)));
     // scene defaults = the reference's (moon_renderer.py:37, 85-101, 597-599, 620-621)
     SceneParams& sp = c->sp;
     sp.radius = 10.0;
@@ -89,6 +91,7 @@ int mrtx_destroy(mrtx_ctx* ctx) {
     cudaFree(ctx->d_max_bits);
     cudaFree(ctx->d_work);
     cudaFree(ctx->d_counters);
+    cudaFree(ctx->d_defer_stats);
     cudaFree(ctx->flush_buf);
     cudaFree(ctx->gather_buf);
     cudaEventDestroy(ctx->ev0);
@@ -531,6 +534,16 @@ int mrtx_counters(mrtx_ctx* ctx, uint64_t out[16], int reset) {
         MRTX_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     if (reset) MRTX_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 128, ctx->stream));
+    return MRTX_OK;
+}
+
+int mrtx_defer_stats(mrtx_ctx* ctx, uint64_t out[32], int reset) {
+    MRTX_CTX(ctx);
+    if (out) {
+        MRTX_CUDA(cudaMemcpyAsync(out, ctx->d_defer_stats, 256, cudaMemcpyDeviceToHost, ctx->stream));
+        MRTX_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    if (reset) MRTX_CUDA(cudaMemsetAsync(ctx->d_defer_stats, 0, 256, ctx->stream));
     return MRTX_OK;
 }
 

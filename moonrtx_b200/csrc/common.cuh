@@ -62,6 +62,7 @@ struct HeightField {
     const double2* lon64;
     const float*   lat32;       // [H]   sin(phi_j), phi_j = (0.5 - (j+0.5)/H) * pi
     const double2* lat64;       // [H]   (sin, cos)(phi_j)
+    const float2*  latsc32;     // [H]   (sin, cos)(phi_j): the directional walk tests polar walls on the cosine
 };
 
 struct Texture8 {
@@ -111,6 +112,7 @@ struct mrtx_ctx {
     int width, height;
     float4* accum; uchar4* rgba8; float4* hit; double4* hit64;
     unsigned long long* d_counters;
+    unsigned long long* d_defer_stats;   // 32 entries
     unsigned* d_work;           // trace work counter + list length
     unsigned* pixel_list;       // width * height entries
     uint2* defer_list;          // width * height entries: samples the filtered kernel hands to the exact one

@@ -62,7 +62,7 @@ __global__ void minmax_kernel(const T* __restrict__ base, size_t n, int* __restr
     if ((threadIdx.x & 31) == 0) { atomicMin(&mm[0], lo); atomicMax(&mm[1], hi); }
 }
 
-__global__ void wall_tables_kernel(float2* lon32, double2* lon64, float* lat32, double2* lat64, int W, int H) {
+__global__ void wall_tables_kernel(float2* lon32, double2* lon64, float* lat32, float2* latsc32, double2* lat64, int W, int H) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i <= W) {
         double sn, cs;
@@ -75,6 +75,7 @@ __global__ void wall_tables_kernel(float2* lon32, double2* lon64, float* lat32, 
         sincospi((i + 0.5) / H, &sn, &cs);
         lat64[i] = make_double2(cs, sn);            // (sin phi, cos phi)
         lat32[i] = (float)cs;
+        latsc32[i] = make_float2((float)cs, (float)sn);
     }
 }
 
@@ -84,14 +85,16 @@ int build_wall_tables(mrtx_ctx* ctx) {
     const size_t n_lon = (size_t)W + 1;
     const size_t off_lon64 = 0, off_lat64 = off_lon64 + n_lon * sizeof(double2);
     const size_t off_lon32 = off_lat64 + (size_t)H * sizeof(double2), off_lat32 = off_lon32 + n_lon * sizeof(float2);
-    const size_t total = off_lat32 + (size_t)H * sizeof(float);
+    const size_t off_latsc32 = (off_lat32 + (size_t)H * sizeof(float) + 15) & ~(size_t)15;
+    const size_t total = off_latsc32 + (size_t)H * sizeof(float2);
     MRTX_CUDA(cudaMalloc(&ctx->hf_tables_owned, total));
     char* p = (char*)ctx->hf_tables_owned;
     hf.lon64 = (const double2*)(p + off_lon64); hf.lat64 = (const double2*)(p + off_lat64);
     hf.lon32 = (const float2*)(p + off_lon32);  hf.lat32 = (const float*)(p + off_lat32);
+    hf.latsc32 = (const float2*)(p + off_latsc32);
     const int n = (W + 1 > H ? W + 1 : H);
     wall_tables_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>((float2*)hf.lon32, (double2*)hf.lon64, (float*)hf.lat32,
-                                                                 (double2*)hf.lat64, W, H);
+                                                                 (float2*)hf.latsc32, (double2*)hf.lat64, W, H);
     MRTX_CUDA(cudaGetLastError());
     return MRTX_OK;
 }

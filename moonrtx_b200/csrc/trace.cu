@@ -65,7 +65,10 @@ struct RenderArgs {
     unsigned long long* counters;
     unsigned* work_counter;          // [0] persistent kernel: next unclaimed entry, [1] pixel list length,
                                      // [2] fast kernel: next unclaimed warp task, [3] deferred list length
-    unsigned* pixel_list;            // pixels whose rays can touch the bounding sphere (x | y << 16)
+    unsigned* pixel_list;            // pixels whose rays can touch the bounding sphere (x | y << 16): [0, work_counter[4])
+                                     // limb pixels, [list_cap - work_counter[1], list_cap) the others, backwards
+    unsigned list_cap;
+    unsigned long long* defer_stats; // [reason + 16 * shadow]: why samples were deferred
     uint2* defer_list;               // (pixel, mask of samples sample0 + bit) the fast kernel could not certify
     FastConsts K;
     float inv_rs;
@@ -75,6 +78,11 @@ struct RenderArgs {
 };
 
 struct RayStats { unsigned primary, inside, hits, shadow, occluded; };
+
+// p-th pixel of the work list (limb pixels first)
+__device__ __forceinline__ unsigned list_pixel(const RenderArgs& A, unsigned p, unsigned n_limb) {
+    return A.pixel_list[p < n_limb ? p : A.list_cap - 1u - (p - n_limb)];
+}
 
 // Primary ray of (pixel x, y; sample sm) in the body frame.
 __device__ __forceinline__ void primary_ray(const RenderArgs& A, int x, int y, uint32_t pixel, unsigned sm, Ray64& R) {
@@ -233,7 +241,7 @@ cull_kernel(const __grid_constant__ RenderArgs A) {
     const unsigned total = tiles_x * tiles_y * 32u;
     const unsigned p = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    bool keep = false;
+    bool keep = false, limb = false;
     unsigned culled = 0;
     int x = 0, y = 0;
     if (p < total) {
@@ -264,14 +272,30 @@ cull_kernel(const __grid_constant__ RenderArgs A) {
                 float4 old = *ap;
                 old.w += (float)A.nsamples;
                 *ap = old;
-            } else keep = true;
+            } else {
+                keep = true;
+                const double core = A.sp.radius * (double)A.hf.dmin - eye_dist * 3.0 * cam.tan_half_fov / A.height;
+                limb = !(core > 0.0 && d2 < core * core && od < 0.0);
+            }
         }
     }
-    const unsigned m = __ballot_sync(0xffffffffu, keep);
-    unsigned base = 0;
-    if (lane == 0 && m) base = atomicAdd(&A.work_counter[1], (unsigned)__popc(m));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (keep) A.pixel_list[base + (unsigned)__popc(m & ((1u << lane) - 1u))] = (unsigned)x | ((unsigned)y << 16);
+    // Rays that can pass through the relief shell without meeting the sphere below it walk hundreds to thousands of
+    // cells (most of all over the poles, where equirectangular cells are slivers): those pixels go to the FRONT of
+    // the list so that their long dependent walks start first and hide behind the bulk of the frame; the rest
+    // is appended from the far end downwards.
+    const unsigned ml = __ballot_sync(0xffffffffu, keep && limb), mi = __ballot_sync(0xffffffffu, keep && !limb);
+    unsigned bl = 0, bi = 0;
+    if (lane == 0) {
+        if (ml) bl = atomicAdd(&A.work_counter[4], (unsigned)__popc(ml));
+        if (mi) bi = atomicAdd(&A.work_counter[1], (unsigned)__popc(mi));
+    }
+    bl = __shfl_sync(0xffffffffu, bl, 0); bi = __shfl_sync(0xffffffffu, bi, 0);
+    const unsigned below = (1u << lane) - 1u;
+    if (keep) {
+        const unsigned packed = (unsigned)x | ((unsigned)y << 16);
+        if (limb) A.pixel_list[bl + (unsigned)__popc(ml & below)] = packed;
+        else A.pixel_list[A.list_cap - 1u - (bi + (unsigned)__popc(mi & below))] = packed;
+    }
     const unsigned nc = __reduce_add_sync(0xffffffffu, culled);
     if (lane == 0 && nc) {
         atomicAdd(&A.counters[0], (unsigned long long)nc * A.nsamples);
@@ -290,14 +314,12 @@ enum { M_IDLE = 0, M_START = 1, M_TRAV = 2, M_CAND = 3, M_BEGIN = 4 };
 constexpr int TRAV_BURST = 16;
 constexpr int CAND_GROUP = 20;     // run the float64 phase once this many lanes wait for it
 
-// DEFER = true: the work list is the fast kernel's deferred list; a lane then owns one (pixel, sample mask)
-// entry, traces exactly the samples in the mask and adds their radiance to what the fast kernel wrote.
-template <bool I16, bool DEFER>
+template <bool I16>
 __global__ void __launch_bounds__(128, 3)
 trace_kernel_persistent(const __grid_constant__ RenderArgs A) {
     const int lane = threadIdx.x & 31;
-    const unsigned total = A.work_counter[DEFER ? 3 : 1]; // list length, written by cull_kernel / trace_kernel_fast
-    unsigned mask = 0;
+    const unsigned n_limb = A.work_counter[4];
+    const unsigned total = n_limb + A.work_counter[1];    // list length, written by cull_kernel
     const float Rf = (float)A.sp.radius;
 
     Counters cnt = {0u, 0u, 0u};
@@ -317,15 +339,11 @@ trace_kernel_persistent(const __grid_constant__ RenderArgs A) {
 
     auto retire_sample = [&]() {
         // next sample of the same pixel, or write the pixel back and free the lane
-        bool more;
-        if (DEFER) { mask &= mask - 1u; more = mask != 0u; if (more) sm = A.sample0 + (unsigned)(__ffs(mask) - 1); }
-        else more = ++sm < A.sample0 + A.nsamples;
-        if (more) mode = M_START;
+        if (++sm < A.sample0 + A.nsamples) mode = M_START;
         else {
             float4* ap = A.accum + (size_t)y * A.width + x;
             float4 old = *ap;
-            old.x += acc.x; old.y += acc.y; old.z += acc.z;
-            if (!DEFER) old.w += (float)A.nsamples;             // the fast kernel has counted its deferred samples
+            old.x += acc.x; old.y += acc.y; old.z += acc.z; old.w += (float)A.nsamples;
             *ap = old;
             mode = M_IDLE;
         }
@@ -351,12 +369,10 @@ trace_kernel_persistent(const __grid_constant__ RenderArgs A) {
             if (mode == M_IDLE) {
                 const unsigned p = base + (unsigned)__popc(idle & ((1u << lane) - 1u));
                 if (p < total) {
-                    unsigned packed;
-                    if (DEFER) { const uint2 e = A.defer_list[p]; packed = e.x; mask = e.y; }
-                    else packed = A.pixel_list[p];
+                    const unsigned packed = list_pixel(A, p, n_limb);
                     x = (int)(packed & 0xffffu); y = (int)(packed >> 16);
                     pixel = (uint32_t)y * (uint32_t)A.width + (uint32_t)x;
-                    sm = DEFER ? A.sample0 + (unsigned)(__ffs(mask) - 1) : A.sample0;
+                    sm = A.sample0;
                     acc = make_float3(0.f, 0.f, 0.f);
                     mode = M_START;
                 }
@@ -468,7 +484,7 @@ trace_kernel_persistent(const __grid_constant__ RenderArgs A) {
 //   * warps claim tasks from a counter, so limb / terminator warps that walk hundreds of cells do not leave
 //     SMs idle at the end of the frame.
 // A sample the filter cannot certify (FT_DEFER) contributes nothing here; its bit is set in the pixel's entry of
-// the deferred list and trace_kernel_persistent<.., true> traces it exactly afterwards.
+// the deferred list and trace_kernel_referee traces it again afterwards.
 __device__ __forceinline__ void primary_ray_fast(const RenderArgs& A, int x, int y, uint32_t pixel, unsigned sm, Ray64& R) {
     const SceneParams& sp = A.sp;
     const Camera& cam = A.cam;
@@ -586,7 +602,8 @@ trace_kernel_fast(const __grid_constant__ RenderArgs A) {
     const int gl = A.g_log2, g = 1 << gl;
     const int sub = lane & (g - 1), pw = lane >> gl;         // lane within the pixel's group, pixel within the warp
     const unsigned ppw = 32u >> gl;
-    const unsigned nkept = A.work_counter[1];
+    const unsigned n_limb = A.work_counter[4];
+    const unsigned nkept = n_limb + A.work_counter[1];
     const unsigned ntasks = (nkept + ppw - 1u) / ppw;
     const float Rf = A.K.R;
     const unsigned rounds = (A.nsamples + (unsigned)g - 1u) >> gl;
@@ -602,7 +619,7 @@ trace_kernel_fast(const __grid_constant__ RenderArgs A) {
         if (task >= ntasks) break;
         const unsigned p = task * ppw + (unsigned)pw;
         const bool valid = p < nkept;
-        const unsigned packed = valid ? A.pixel_list[p] : 0u;
+        const unsigned packed = valid ? list_pixel(A, p, n_limb) : 0u;
         const int x = (int)(packed & 0xffffu), y = (int)(packed >> 16);
         const uint32_t pixel = (uint32_t)y * (uint32_t)A.width + (uint32_t)x;
         float3 acc = make_float3(0.f, 0.f, 0.f);
@@ -643,9 +660,12 @@ trace_kernel_fast(const __grid_constant__ RenderArgs A) {
                     __syncwarp();
                     if (cand) {
                         ++cnt.tests;
-                        const int t = fast_test<I16>(A.hf, A.K, R, st.s_in, 0.0, st.s, sx, st.smax, P, fh);
+                        const int t = fast_test<I16>(A.hf, A.K, R, st.s_in, 0.0, st.s, sx, st.smax, P, pass != 0, fh);
                         if (t == FT_MISS) { if (!walk_advance(A.hf, st, sx, face)) alive = false; }
-                        else { res = t; alive = false; }
+                        else {
+                            res = t & 3; alive = false;
+                            if (res == FT_DEFER) atomicAdd(&A.defer_stats[(t >> 2) + (pass ? 16 : 0)], 1ull);
+                        }
                     }
                 }
                 if (res == FT_DEFER) defer = true;
@@ -696,7 +716,132 @@ trace_kernel_fast(const __grid_constant__ RenderArgs A) {
     }
     flush_counters(A, rs, cnt, lane);
     const unsigned nd = __reduce_add_sync(FULL, n_defer);
-    if (lane == 0 && nd) atomicAdd(&A.counters[13], (unsigned long long)nd);
+    if (lane == 0 && nd) atomicAdd(&A.defer_stats[0], (unsigned long long)nd);
+}
+
+// ---- deferred samples: same walk, float64 referee per undecided patch ---------------------------------
+// One WARP per deferred sample.  The sample is traced again from the start with the float32 walk and the
+// filter; only where the filter says FT_DEFER does the float64 exact test of trace_core.cuh (exact in-cell
+// pieces, walk-back through the neighbours) decide that patch.
+// Deferred rays are the long grazing ones - over a pole a ray crosses tens of thousands of sliver cells, one
+// dependent fetch after the other - and there are only a few of them, so a single lane per ray would leave the
+// whole kernel waiting for the longest walk.  The ray's path through the shell is therefore cut into
+// REFEREE_SEGMENTS pieces that lanes walk independently (32 at a time, nearest first); the first hit is the hit of
+// the nearest piece that has one.  (A piece that starts below the surface reports a hit at its start, which can
+// only lose against the true crossing in an earlier piece.)
+constexpr int REFEREE_SEGMENTS = 128;
+
+template <bool I16>
+__device__ bool trace_referee(const RenderArgs& A, const Ray64& R, double s_lo, double s_hi, int start_level, bool any_hit,
+                              bool& fast, FastHit& fh, TraceOut& h, Counters& cnt) {
+    Walk w;
+    if (!walk_begin(A.hf, A.sp.radius, R, s_lo, start_level, w)) return false;
+    w.smax = fminf(w.smax, (float)(s_hi - w.s_in));
+    if (!(w.smax > 0.0f)) return false;
+    for (;;) {
+        RawPatch P;
+        float sx;
+        int face;
+        const int r = walk_step<I16>(A.hf, A.K.R, A.inv_rs, w, P, sx, face, cnt);
+        if (r == TR_END) return false;
+        if (r == TR_CANDIDATE) {
+            ++cnt.tests;
+            const int t = fast_test<I16>(A.hf, A.K, R, w.s_in, s_lo, w.s, sx, w.smax, P, any_hit, fh) & 3;
+            if (t == FT_HIT) { fast = true; return true; }
+            if (t == FT_DEFER) {
+                TravState st;
+                st.s_in = w.s_in; st.s_min = s_lo; st.s_end = w.s_in + (double)w.smax; st.s = w.s;
+                Patch Pd;
+                load_patch<I16>(A.hf, P.r0, P.c0, Pd);
+                if (exact_test<I16>(A.hf, A.sp.radius, R, st, Pd, sx, h, cnt)) { fast = false; return true; }
+            }
+            if (!walk_advance(A.hf, w, sx, face)) return false;
+        }
+    }
+}
+
+// First hit of R at s >= s_min by the whole warp.  Returns the lane that holds it (fast / fh / h valid there), or -1.
+template <bool I16>
+__device__ int referee_ray(const RenderArgs& A, const Ray64& R, double s_min, int start_level, bool any_hit, bool& fast,
+                           FastHit& fh, TraceOut& h, Counters& cnt, bool& entered) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const double Rb = A.sp.radius * (double)A.hf.dmax;
+    const double disc = R.od * R.od - (R.oo - Rb * Rb);
+    entered = false;
+    if (!(disc > 0.0)) return -1;
+    const double sq = sqrt(disc);
+    const double s1 = -R.od + sq;
+    if (s1 <= s_min) return -1;
+    const double s0 = fmax(s_min, -R.od - sq);
+    entered = true;
+    const double step = (s1 - s0) / REFEREE_SEGMENTS;
+    for (int base = 0; base < REFEREE_SEGMENTS; base += 32) {
+        const int seg = base + lane;
+        // pieces overlap a little: a piece's first cell is found from a float32 position a step inside it
+        const double lap = 3.0e-5 * A.sp.radius;
+        const double a = seg == 0 ? s_min : fmax(s_min, s0 + seg * step - lap), b = seg == REFEREE_SEGMENTS - 1 ? s1 + 1.0 : s0 + (seg + 1) * step;
+        const bool hit = trace_referee<I16>(A, R, a, b, seg == 0 ? start_level : 2, any_hit, fast, fh, h, cnt);
+        __syncwarp();
+        const unsigned m = __ballot_sync(FULL, hit);
+        if (m) return __ffs(m) - 1;
+    }
+    return -1;
+}
+
+__device__ __forceinline__ double shfl_d(double v, int src) {
+    return __hiloint2double(__shfl_sync(0xffffffffu, __double2hiint(v), src), __shfl_sync(0xffffffffu, __double2loint(v), src));
+}
+
+template <bool I16>
+__global__ void __launch_bounds__(64)
+trace_kernel_referee(const __grid_constant__ RenderArgs A) {
+    const unsigned total = A.work_counter[3];
+    const int lane = threadIdx.x & 31;
+    const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    Counters cnt = {0u, 0u, 0u};
+    RayStats rs = {0u, 0u, 0u, 0u, 0u};                    // lane 0 counts rays
+    for (unsigned e = warp; e < total; e += nwarps) {
+        const uint2 ent = A.defer_list[e];
+        const int x = (int)(ent.x & 0xffffu), y = (int)(ent.x >> 16);
+        const uint32_t pixel = (uint32_t)y * (uint32_t)A.width + (uint32_t)x;
+        float3 acc = make_float3(0.f, 0.f, 0.f);            // lane 0 sums the samples in order
+        for (unsigned mask = ent.y; mask; mask &= mask - 1u) {
+            const unsigned sm = A.sample0 + (unsigned)(__ffs(mask) - 1);
+            Ray64 R, S;
+            primary_ray_fast(A, x, y, pixel, sm, R);
+            bool fast = false, entered = false;
+            FastHit fh;
+            TraceOut h;
+            const int who = referee_ray<I16>(A, R, 0.0, A.hf.top - 3, false, fast, fh, h, cnt, entered);
+            if (lane == 0) { ++rs.primary; if (entered) ++rs.inside; }
+            if (who < 0) { if (lane == 0) write_miss(A, x, y, sm == A.sample0); continue; }
+            float3 lit = make_float3(0.f, 0.f, 0.f);
+            bool need_shadow = false;
+            if (lane == who) need_shadow = fast ? shade_fast(A, R, fh, x, y, pixel, sm, lit, S) : shade_hit(A, R, h, x, y, pixel, sm, lit, S);
+            need_shadow = __shfl_sync(0xffffffffu, need_shadow ? 1 : 0, who) != 0;
+            lit.x = __shfl_sync(0xffffffffu, lit.x, who); lit.y = __shfl_sync(0xffffffffu, lit.y, who); lit.z = __shfl_sync(0xffffffffu, lit.z, who);
+            if (lane == 0) ++rs.hits;
+            bool occluded = false;
+            if (need_shadow) {
+                S.ox = shfl_d(S.ox, who); S.oy = shfl_d(S.oy, who); S.oz = shfl_d(S.oz, who);
+                S.dx = shfl_d(S.dx, who); S.dy = shfl_d(S.dy, who); S.dz = shfl_d(S.dz, who);
+                S.oo = S.ox * S.ox + S.oy * S.oy + S.oz * S.oz;
+                S.od = S.ox * S.dx + S.oy * S.dy + S.oz * S.dz;
+                occluded = referee_ray<I16>(A, S, 0.0, 2, true, fast, fh, h, cnt, entered) >= 0;
+                if (lane == 0) { ++rs.shadow; if (occluded) ++rs.occluded; }
+            }
+            if (!occluded) { acc.x += lit.x; acc.y += lit.y; acc.z += lit.z; }
+        }
+        if (lane == 0) {
+            float4* ap = A.accum + (size_t)y * A.width + x;     // the filtered kernel has counted the samples
+            float4 old = *ap;
+            old.x += acc.x; old.y += acc.y; old.z += acc.z;
+            *ap = old;
+        }
+    }
+    __syncwarp();
+    flush_counters(A, rs, cnt, lane);
 }
 
 // K8: Gamma post-process + Overlay alpha blend -> RGBA8
@@ -750,6 +895,7 @@ int launch_trace(mrtx_ctx* ctx, int x0, int y0, int x1, int y1, unsigned s0, uns
     to_body(A.sp, er, A.eye_b);
     to_body(A.sp, lr, A.light_b);
     A.defer_list = ctx->defer_list;
+    A.defer_stats = ctx->d_defer_stats;
     A.K = make_fast_consts(ctx->hf, ctx->sp.radius);
     A.inv_rs = 1.0f / ctx->hf.radius_scale;
     A.g_log2 = 0;
@@ -764,7 +910,8 @@ int launch_trace(mrtx_ctx* ctx, int x0, int y0, int x1, int y1, unsigned s0, uns
         MRTX_CUDA(cudaGetLastError());
         return MRTX_OK;
     }
-    MRTX_CUDA(cudaMemsetAsync(A.work_counter, 0, 4 * sizeof(unsigned), ctx->stream));
+    MRTX_CUDA(cudaMemsetAsync(A.work_counter, 0, 8 * sizeof(unsigned), ctx->stream));
+    A.list_cap = (unsigned)((size_t)ctx->width * ctx->height);
     {
         const unsigned tiles_x = (unsigned)(x1 - x0 + 7) / 8u, tiles_y = (unsigned)(y1 - y0 + 3) / 4u;
         const unsigned total = tiles_x * tiles_y * 32u;
@@ -773,28 +920,22 @@ int launch_trace(mrtx_ctx* ctx, int x0, int y0, int x1, int y1, unsigned s0, uns
     const long long npix = (long long)(x1 - x0) * (y1 - y0);
     if (kernel == 1) {
         int per_sm = 0;
-        if (i16) MRTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel_persistent<true, false>, 128, 0));
-        else     MRTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel_persistent<false, false>, 128, 0));
+        if (i16) MRTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel_persistent<true>, 128, 0));
+        else     MRTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel_persistent<false>, 128, 0));
         if (per_sm < 1) per_sm = 1;
         const long long warps_needed = (npix + 31) / 32;
         long long blocks = (long long)ctx->sm_count * per_sm;
         if (blocks * 4 > warps_needed) blocks = (warps_needed + 3) / 4;     // small rectangles: fewer blocks
         if (blocks < 1) blocks = 1;
-        if (i16) trace_kernel_persistent<true, false><<<(unsigned)blocks, 128, 0, ctx->stream>>>(A);
-        else     trace_kernel_persistent<false, false><<<(unsigned)blocks, 128, 0, ctx->stream>>>(A);
+        if (i16) trace_kernel_persistent<true><<<(unsigned)blocks, 128, 0, ctx->stream>>>(A);
+        else     trace_kernel_persistent<false><<<(unsigned)blocks, 128, 0, ctx->stream>>>(A);
     } else {
         // filtered kernel in chunks of <= 32 samples (one mask bit per sample in the deferred list), each
-        // followed by the exact kernel over whatever it deferred
-        int per_sm = 0, per_sm_x = 0;
-        if (i16) {
-            MRTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel_fast<true>, 128, 0));
-            MRTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_x, trace_kernel_persistent<true, true>, 128, 0));
-        } else {
-            MRTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel_fast<false>, 128, 0));
-            MRTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_x, trace_kernel_persistent<false, true>, 128, 0));
-        }
+        // followed by the referee kernel over whatever it deferred
+        int per_sm = 0;
+        if (i16) MRTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel_fast<true>, 128, 0));
+        else     MRTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel_fast<false>, 128, 0));
         if (per_sm < 1) per_sm = 1;
-        if (per_sm_x < 1) per_sm_x = 1;
         for (unsigned done = 0; done < ns; done += 32u) {
             const unsigned n = ns - done < 32u ? ns - done : 32u;
             A.sample0 = s0 + done; A.nsamples = n;
@@ -808,11 +949,8 @@ int launch_trace(mrtx_ctx* ctx, int x0, int y0, int x1, int y1, unsigned s0, uns
             if (blocks < 1) blocks = 1;
             if (i16) trace_kernel_fast<true><<<(unsigned)blocks, 128, 0, ctx->stream>>>(A);
             else     trace_kernel_fast<false><<<(unsigned)blocks, 128, 0, ctx->stream>>>(A);
-            if (done) MRTX_CUDA(cudaMemsetAsync(A.work_counter, 0, sizeof(unsigned), ctx->stream));
-            long long xblocks = (long long)ctx->sm_count * per_sm_x;
-            if (xblocks * 128 > npix) xblocks = (npix + 127) / 128;
-            if (i16) trace_kernel_persistent<true, true><<<(unsigned)xblocks, 128, 0, ctx->stream>>>(A);
-            else     trace_kernel_persistent<false, true><<<(unsigned)xblocks, 128, 0, ctx->stream>>>(A);
+            if (i16) trace_kernel_referee<true><<<ctx->sm_count * 8, 64, 0, ctx->stream>>>(A);
+            else     trace_kernel_referee<false><<<ctx->sm_count * 8, 64, 0, ctx->stream>>>(A);
         }
     }
     MRTX_CUDA(cudaGetLastError());

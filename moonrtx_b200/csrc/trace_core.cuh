@@ -300,12 +300,16 @@ MRTX_HD float cell_exit32(const HeightField& hf, const Trav& T, int L, int J, in
     face = 4;
     const float x = fmaf(s, T.dx, T.ox), y = fmaf(s, T.dy, T.oy), z = fmaf(s, T.dz, T.oz);
     const float r = sqrtf(fmaxf(ray_r2(T, s), 1e-30f));
-    const float tol = 2.0e-6f * r;
+    // "on the wall" = within the float32 error of the wall function: 2e-7 r from the re-based ray plus the
+    // rounding of the function's two cancelling terms (a uniform 2e-6 r is 3 % of a full-resolution cell and
+    // sends rays that run nearly parallel to a wall into the neighbouring row tens of cells early)
+    const float tol0 = 2.0e-7f * r;
 #pragma unroll
     for (int side = 0; side < 2; ++side) {      // 0 = west wall (index a), 1 = east wall (index b)
         const float2 wl = MRTX_LDG(hf.lon32 + (side ? b : a));
         const float cs = wl.x, sn = wl.y;
         const float sg = side ? 1.0f : -1.0f;                   // outward = +g east, -g west
+        const float tol = fmaf(6.0e-7f, fabsf(x * cs) + fabsf(y * sn), tol0);
         const float q = sg * (x * cs + y * sn), dq = sg * (T.dx * cs + T.dy * sn);
         if (!(dq > 0.0f)) continue;                             // not heading out through this wall
         float sc;
@@ -320,18 +324,32 @@ MRTX_HD float cell_exit32(const HeightField& hf, const Trav& T, int L, int J, in
 #pragma unroll
     for (int side = 0; side < 2; ++side) {      // 0 = north wall (index n), 1 = south wall (index m)
         if (side == 0 ? (n == 0) : (m == H - 1)) continue;      // polar caps have no wall
-        const float k = MRTX_LDG(hf.lat32 + (side == 0 ? n : m));               // sin(lat) of the wall
-        const float sg = side ? -1.0f : 1.0f;                   // outward = +h north, -h south; h = z - k r
-        const float q = sg * (z - k * r), dq = sg * (T.dz * r - k * (T.od + s));  // dq: sign of d(q)/ds (times r > 0)
+        const float2 kk = MRTX_LDG(hf.latsc32 + (side == 0 ? n : m));           // (sin, cos)(lat) of the wall
+        const float k = kk.x;
+        const bool polar = fabsf(k) > 0.70710678f;
+        const float sg = side ? -1.0f : 1.0f;                   // outward = north of the north wall, south of the south wall
+        // Signed distance north of the wall.  z - k r cancels two numbers ~R and shows the distance only as
+        // r cos(lat) d(lat): beyond 45 deg the same cone is tested as rho = kc r (rho = distance from the axis).
+        const float rho = sqrtf(x * x + y * y);
+        const float side_n = !polar ? z - k * r : (k > 0.0f ? (z > 0.0f ? kk.y * r - rho : -r) : (z < 0.0f ? rho - kk.y * r : r));
+        const float tol = fmaf(6.0e-7f * r, fminf(fabsf(k), kk.y), tol0);
+        const float q = sg * side_n, dq = sg * (T.dz * r - k * (T.od + s));  // dq: sign of d(q)/ds (times r > 0)
         if (q >= -tol && dq > 0.0f) {                           // on or beyond the wall, moving outward
             if (s < best) { best = s; face = 2 + side; }
             continue;
         }
-        // outward crossings ahead: roots of F(s) = z^2 - k^2 r^2 = A s^2 + 2 B s + C on the wall's nappe.
+        // outward crossings ahead: roots of F(s) = z^2 - k^2 r^2 = A s^2 + 2 B s + C on the wall's nappe
+        // (polar walls: -F = rho^2 - kc^2 r^2, the same roots from small numbers).
         // On that nappe h = F / (z + k r) and z + k r has the sign of k, so the crossing direction
         // d(h)/ds has the sign of k * F'(s) = k * 2 (A s + B): no square root or division needed.
-        const float k2 = k * k;
-        const float A = T.dz * T.dz - k2, B = T.oz * T.dz - k2 * T.od, Cq = T.oz * T.oz - k2 * T.oo;
+        float A, B, Cq;
+        if (polar) {
+            const float c2 = kk.y * kk.y;
+            A = -(T.dx * T.dx + T.dy * T.dy - c2); B = -(T.ox * T.dx + T.oy * T.dy - c2 * T.od); Cq = -(T.ox * T.ox + T.oy * T.oy - c2 * T.oo);
+        } else {
+            const float k2 = k * k;
+            A = T.dz * T.dz - k2; B = T.oz * T.dz - k2 * T.od; Cq = T.oz * T.oz - k2 * T.oo;
+        }
         float r1 = -1.0f, r2 = -1.0f;
         if (fabsf(A) < 1e-12f) { if (B != 0.0f) r1 = fdiv_fast(-Cq, 2.0f * B); }
         else {
@@ -462,8 +480,11 @@ MRTX_HD inline int trav_step(const HeightField& hf, float Rf, TravState& st, Pat
             if (x * wl.x + y * wl.y >= 0.0f) ci += 1;
         }
         if (mj < min((J + 1) << L, hf.H - 1)) {
-            const float k = MRTX_LDG(hf.lat32 + mj);
-            if (z - k * sqrtf(x * x + y * y + z * z) < 0.0f) cj += 1;     // south of the mid wall
+            const float2 kk = MRTX_LDG(hf.latsc32 + mj);
+            const float rho = sqrtf(x * x + y * y), rr = sqrtf(x * x + y * y + z * z);
+            const float side_n = fabsf(kk.x) <= 0.70710678f ? z - kk.x * rr
+                               : (kk.x > 0.0f ? (z > 0.0f ? kk.y * rr - rho : -rr) : (z < 0.0f ? rho - kk.y * rr : rr));
+            if (side_n < 0.0f) cj += 1;                              // south of the mid wall
         }
         st.s = sd; st.L = L - 1; st.I = ci; st.J = cj;
         return TR_CONTINUE;

@@ -26,6 +26,8 @@
 namespace mrtx_core {
 
 enum { FT_MISS = 0, FT_HIT = 1, FT_DEFER = 2 };
+// fast_test() reports WHY it defers in the bits above the status (statistics only: mrtx_defer_stats)
+#define FT_DEFER_R(reason) (FT_DEFER | ((reason) << 2))
 
 #ifdef __CUDA_ARCH__
 __device__ __forceinline__ float f_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
@@ -58,6 +60,8 @@ struct FastConsts {
     float pad;          // float32 traversal parameter slack
     float epsc;         // a root this far outside the cell (in cells) still belongs to it
     float ds_tol;       // a root must be located to this (ray parameter) or the sample is deferred
+    float sD, cD, tD;   // sin, cos of one cell in longitude (2 pi / W); tan of one cell in latitude (pi / H)
+    float cell;         // size of a cell at the equator, scene units
     int   enabled;      // 0: map too coarse for the small-angle series (W < 360) -> always defer
 };
 
@@ -68,8 +72,10 @@ MRTX_HD inline FastConsts make_fast_consts(const HeightField& hf, double radius)
     K.Kh = (float)(hf.H / PI_D);
     K.mg = (float)(2.0e-9 * radius);
     K.pad = (float)(4.0e-6 * radius);
-    K.epsc = 2.0e-5f;
-    K.ds_tol = (float)(1.0e-4 * 2.0 * PI_D * radius / hf.W);     // 1e-4 texel
+    K.epsc = 2.0e-6f;
+    K.sD = (float)sin(2.0 * PI_D / hf.W); K.cD = (float)cos(2.0 * PI_D / hf.W); K.tD = (float)tan(PI_D / hf.H);
+    K.cell = (float)(2.0 * PI_D * radius / hf.W);
+    K.ds_tol = (float)(5.0e-4 * 2.0 * PI_D * radius / hf.W);     // 5e-4 texel (the parity budget is 1e-3)
     K.enabled = hf.W >= 360 && hf.H >= 180;
     return K;
 }
@@ -121,103 +127,193 @@ MRTX_HD inline float local_f(const LocalRay& Q, const FastConsts& K, float t, fl
 
 // Decide one candidate patch.  [ws, we]: the float32 traversal's window (relative to s_in);
 // s_lo, s_in + smax: the extent of the ray.
+//
+// The traversal's idea of where the ray is inside this cell is only good to its wall tolerance (2e-6 R:
+// 3 % of a cell of the full-resolution map), and its on-wall rule hands a ray to the next cell that early.
+// The test therefore clips the ray to the cell ITSELF, in the local frame where the four walls are (to
+// 1e-6 cell) linear in t, and searches from max(traversal start, true entry) to the TRUE exit: the intervals
+// of consecutive cells tile the ray whatever the float32 walk believed, as next_piece() does for the exact
+// test.
+template <bool I16>
+MRTX_HD inline void load_raw_patch(const HeightField& hf, int r0, int c0, RawPatch& P) {
+    const int W = hf.W, c1 = c0 + 1 == W ? 0 : c0 + 1;
+    P.r0 = r0; P.c0 = c0;
+    if (I16) {
+        const int16_t* b = (const int16_t*)hf.base + (size_t)r0 * W;
+        P.v00 = (float)MRTX_LDG(b + c0); P.v01 = (float)MRTX_LDG(b + c1);
+        P.v10 = (float)MRTX_LDG(b + W + c0); P.v11 = (float)MRTX_LDG(b + W + c1);
+    } else {
+        const float* b = (const float*)hf.base + (size_t)r0 * W;
+        P.v00 = MRTX_LDG(b + c0); P.v01 = MRTX_LDG(b + c1);
+        P.v10 = MRTX_LDG(b + W + c0); P.v11 = MRTX_LDG(b + W + c1);
+    }
+}
+
 template <bool I16>
 MRTX_HD inline int fast_test(const HeightField& hf, const FastConsts& K, const Ray64& R, double s_in, double s_lo,
-                             float ws, float we, float smax, const RawPatch& P, FastHit& out) {
-    if (!K.enabled || P.r0 <= 0 || P.r0 >= hf.H - 2) return FT_DEFER;       // polar caps: rows clamp, no wall
-    const float d00 = decode_exact<I16>(hf, P.v00), d01 = decode_exact<I16>(hf, P.v01);
-    const float d10 = decode_exact<I16>(hf, P.v10), d11 = decode_exact<I16>(hf, P.v11);
-    const double2 w = MRTX_LDG(hf.lon64 + P.c0), n = MRTX_LDG(hf.lat64 + P.r0);   // (cos, sin) lon_w; (sin, cos) lat_n
+                             float ws, float we, float smax, RawPatch P, bool any_hit, FastHit& out) {
+    if (!K.enabled) return FT_DEFER_R(1);
     const double s_c = s_in + (double)ws;
-    LocalRay Q;
-    {
-        const double px = fma(s_c, R.dx, R.ox), py = fma(s_c, R.dy, R.oy), pz = fma(s_c, R.dz, R.oz);
-        const double a0 = px * w.x + py * w.y, m0 = px * w.y - py * w.x;
-        const double da = R.dx * w.x + R.dy * w.y, dm = R.dx * w.y - R.dy * w.x;
-        const double Rc0 = (double)K.R * (double)d00;
-        Q.a0 = (float)a0; Q.da = (float)da;
-        Q.b0 = (float)(n.y * pz - n.x * m0); Q.db = (float)(n.y * R.dz - n.x * dm);
-        Q.c0 = (float)(fma(n.y, m0, n.x * pz) - Rc0); Q.dc = (float)fma(n.y, dm, n.x * R.dz);
-        Q.nk = (float)n.x; Q.nc = (float)n.y; Q.Rc0 = (float)Rc0;
-    }
-    Q.e01 = K.R * (d01 - d00); Q.e10 = K.R * (d10 - d00); Q.exx = K.R * ((d11 - d10) - (d01 - d00));
-
-    float ta = fmaxf(-K.pad, (float)(s_lo - s_c)), tb = fminf((we - ws) + K.pad, smax - ws);
-    if (!(tb > ta)) return FT_MISS;
-    float fc, fr;
-    // start of the window: the ray must be clear of the surface there
-    float fa = local_f(Q, K, ta, fc, fr);
-    if (!(fa > K.mg)) {
-        // inside the cell that is "entered below the surface" (the exact test walks back); in the
-        // slack before the cell the patch is only an extrapolation: retry at the nominal entry
-        const bool inside = fc >= -K.epsc && fc <= 1.0f + K.epsc && fr >= -K.epsc && fr <= 1.0f + K.epsc;
-        if (inside || !(ta + K.pad < tb)) return FT_DEFER;
-        ta += K.pad;
-        fa = local_f(Q, K, ta, fc, fr);
-        if (!(fa > K.mg)) return FT_DEFER;
-    }
-    const float fca = fc, fra = fr;
-    const float fb = local_f(Q, K, tb, fc, fr);
-    const float dfc = fc - fca, dfr = fr - fra;                 // direction of travel through the cell
-    const float tm = 0.5f * (ta + tb), h = 0.5f * (tb - ta);
-    const float fm = local_f(Q, K, tm, fc, fr);
-    // f ~ fm + c1 tau + c2 tau^2 (a bilinear patch along a nearly straight track)
-    const float ih = f_rcp(h);
-    const float c2 = 0.5f * (fa - 2.0f * fm + fb) * ih * ih, c1 = 0.5f * (fb - fa) * ih;
-    float lo, hi;
-    if (fm < -K.mg) { lo = -h; hi = 0.0f; }
-    else if (!(fm > K.mg)) return FT_DEFER;
-    else if (fb < -K.mg) { lo = 0.0f; hi = h; }
-    else if (!(fb > K.mg)) return FT_DEFER;
-    else {
-        // no sign change at the three samples: a grazing double root shows up as a dip
-        if (!(c2 > 0.0f)) return FT_MISS;
-        const float tv = -0.5f * c1 / c2;
-        if (!(tv > -h && tv < h)) return FT_MISS;
-        const float qv = fm - 0.25f * c1 * c1 / c2;
-        if (qv > 0.25f * fminf(fm, fminf(fa, fb))) return FT_MISS;          // dip clear of zero
-        const float fv = local_f(Q, K, tm + tv, fc, fr);
-        if (fv > K.mg + 0.05f * c2 * h * h) return FT_MISS;
-        if (!(fv < -K.mg)) return FT_DEFER;
-        lo = tv > 0.0f ? 0.0f : -h; hi = tv;
-    }
-    // the parabola's root inside the bracket, polished on f itself
-    float tau = 0.5f * (lo + hi);
-    {
-        const float disc = c1 * c1 - 4.0f * c2 * fm;
-        if (disc >= 0.0f) {
-            const float sq = f_sqrt_fast(disc);
-            const float tq = -0.5f * (c1 + (c1 >= 0.0f ? sq : -sq));
-            const float t1 = c2 != 0.0f ? tq / c2 : 2.0f * h, t2 = tq != 0.0f ? fm / tq : 2.0f * h;
-            const bool in1 = t1 > lo && t1 < hi, in2 = t2 > lo && t2 < hi;
-            if (in1) tau = t1;
-            if (in2 && (!in1 || t2 < t1)) tau = t2;
+    const float t_lo = (float)(s_lo - s_c), t_hi = smax - ws;
+    float t_cap = INFINITY;                                     // walk-back: the neighbour is searched up to our entry
+    bool from_entry = false;                                    // search from the cell's own entry, not from where the walk stands
+#pragma unroll 1
+    for (int back = 0; ; ++back) {
+        if (P.r0 <= 0 || P.r0 >= hf.H - 2) return FT_DEFER_R(1);               // polar caps: rows clamp, no wall
+        const float d00 = decode_exact<I16>(hf, P.v00), d01 = decode_exact<I16>(hf, P.v01);
+        const float d10 = decode_exact<I16>(hf, P.v10), d11 = decode_exact<I16>(hf, P.v11);
+        const double2 w = MRTX_LDG(hf.lon64 + P.c0), n = MRTX_LDG(hf.lat64 + P.r0);   // (cos, sin) lon_w; (sin, cos) lat_n
+        LocalRay Q;
+        {
+            const double px = fma(s_c, R.dx, R.ox), py = fma(s_c, R.dy, R.oy), pz = fma(s_c, R.dz, R.oz);
+            const double a0 = px * w.x + py * w.y, m0 = px * w.y - py * w.x;
+            const double da = R.dx * w.x + R.dy * w.y, dm = R.dx * w.y - R.dy * w.x;
+            const double Rc0 = (double)K.R * (double)d00;
+            Q.a0 = (float)a0; Q.da = (float)da;
+            Q.b0 = (float)(n.y * pz - n.x * m0); Q.db = (float)(n.y * R.dz - n.x * dm);
+            Q.c0 = (float)(fma(n.y, m0, n.x * pz) - Rc0); Q.dc = (float)fma(n.y, dm, n.x * R.dz);
+            Q.nk = (float)n.x; Q.nc = (float)n.y; Q.Rc0 = (float)Rc0;
         }
-    }
-    float fx = 0.0f, slope = 0.0f;
+        Q.e01 = K.R * (d01 - d00); Q.e10 = K.R * (d10 - d00); Q.exx = K.R * ((d11 - d10) - (d01 - d00));
+
+        // the ray inside the cell: four walls (west, east, north, south), each g(t) = g0 + t g1 >= 0 inside
+        float t_in = -INFINITY, t_out = INFINITY;
+        int wall_in = -1;
+        {
+            const float Rc = Q.Rc0 + Q.c0;
+            const float hh0 = fmaf(Q.nc, Rc, -Q.nk * Q.b0), dhh = fmaf(Q.nc, Q.dc, -Q.nk * Q.db);
+            const float am = fmaf(0.5f * (we - ws), Q.da, Q.a0);
+            const float u0 = 0.5f * am * am * f_rcp(hh0);       // rho - hh at mid-window (second order in the cell size)
+            const float g0[4] = {Q.a0, fmaf(hh0, K.sD, -Q.a0 * K.cD), fmaf(Q.nk, u0, -Q.b0),
+                                 fmaf(fmaf(Q.nc, u0, Rc), K.tD, fmaf(-Q.nk, u0, Q.b0))};
+            const float g1[4] = {Q.da, fmaf(dhh, K.sD, -Q.da * K.cD), -Q.db, fmaf(Q.dc, K.tD, Q.db)};
 #pragma unroll
-    for (int it = 0; it < 3; ++it) {
-        fx = local_f(Q, K, tm + tau, fc, fr);
-        slope = fmaf(2.0f * c2, tau, c1);
-        if (it == 2) break;
-        if (!(slope < 0.0f)) return FT_DEFER;                   // the first crossing goes downwards
-        tau -= fx / slope;
-        if (!(tau >= lo - K.pad && tau <= hi + K.pad)) return FT_DEFER;
+            for (int i = 0; i < 4; ++i) {
+                const float tc = -g0[i] * f_rcp(g1[i]);
+                if (g1[i] > 0.0f) { if (tc > t_in) { t_in = tc; wall_in = i; } }
+                else if (g1[i] < 0.0f) t_out = fminf(t_out, tc);
+                else if (g0[i] < 0.0f) return back ? FT_DEFER_R(14) : FT_MISS;    // parallel to the wall and outside it
+            }
+        }
+        const float dl = 1.0e-4f * fminf(t_out - t_in, 16.0f * K.cell) + 1.0e-8f * K.R;
+        // first visit: from where the walk stands (it may have entered the cell's shell in mid-cell)
+        const float t_walk = from_entry ? -INFINITY : -K.pad;
+        const float ta = fmaxf(fmaxf(t_walk, t_in - dl), t_lo), tb = fminf(fminf(t_out + dl, t_hi), t_cap);
+        if (!(tb > ta)) return back ? FT_DEFER_R(14) : FT_MISS;  // the ray does not cross this cell (walk tolerance)
+        float fc, fr;
+        // start of the window: the ray must be clear of the surface there
+        const float fa = local_f(Q, K, ta, fc, fr);
+        MRTX_DBG("  fast_test back=%d cell (%d,%d) t_in=%.4e t_out=%.4e ta=%.4e tb=%.4e dl=%.3e wall_in=%d fa=%.4e (fc=%.5f fr=%.5f) from_entry=%d\n",
+                 back, P.r0, P.c0, t_in, t_out, ta, tb, dl, wall_in, fa, fc, fr, (int)from_entry);
+        if (!(fa > K.mg)) {
+            // Below the surface where the ray comes in through a wall: the crossing lies in the cell behind that
+            // wall, which the float32 walk did not propose (the ray clips it within the walk's wall tolerance).
+            if (!(fa < -K.mg) || back >= 4) return FT_DEFER_R(fa < -K.mg ? 2 : 3);
+            if (!(ta == t_in - dl)) {
+                // ... or in this very cell, before the point the walk arrived at: search it from its entry
+                if (from_entry || !(t_in - dl < ta)) return FT_DEFER_R(2);
+                from_entry = true;
+                continue;
+            }
+            from_entry = true;
+            int r0 = P.r0, c0 = P.c0;
+            if (wall_in == 0) c0 = c0 == 0 ? hf.W - 1 : c0 - 1;
+            else if (wall_in == 1) c0 = c0 + 1 == hf.W ? 0 : c0 + 1;
+            else if (wall_in == 2) r0 -= 1;
+            else r0 += 1;
+            load_raw_patch<I16>(hf, r0, c0, P);
+            t_cap = t_in + dl;
+            continue;
+        }
+        const float fca = fc, fra = fr;
+        const float fb = local_f(Q, K, tb, fc, fr);
+        const float dfc = fc - fca, dfr = fr - fra;             // direction of travel through the cell
+        const float tm = 0.5f * (ta + tb), h = 0.5f * (tb - ta);
+        const float fm = local_f(Q, K, tm, fc, fr);
+        if (any_hit && fm < -K.mg) {
+            // a shadow ray only asks whether the surface is crossed: above it at the start, below it in mid-cell
+            out.s = s_c + (double)tm; out.fc = fc; out.fr = fr; out.r0 = P.r0; out.c0 = P.c0;
+            out.d00 = d00; out.d01 = d01; out.d10 = d10; out.d11 = d11;
+            return FT_HIT;
+        }
+        // f ~ fm + c1 tau + c2 tau^2 (a bilinear patch along a nearly straight track)
+        const float ih = f_rcp(h);
+        MRTX_DBG("    fb=%.4e fm=%.4e h=%.4e dfc=%.4f dfr=%.4f\n", fb, fm, h, dfc, dfr);
+        // (curvature below the evaluation noise is no curvature: slivers of cells near the poles are 1e-7 R wide)
+        const float curv = fa - 2.0f * fm + fb;
+        const float c2 = fabsf(curv) > 4.0f * K.mg ? 0.5f * curv * ih * ih : 0.0f, c1 = 0.5f * (fb - fa) * ih;
+        float lo, hi, flo, fhi;
+        // (a sample within the margin of zero is a root there if f goes through it steeply: the conditioning
+        //  check after the polish decides, a tangent ray ends in FT_DEFER)
+        if (!(fm > K.mg)) { lo = -h; hi = 0.0f; flo = fa; fhi = fm; }
+        else if (!(fb > K.mg)) { lo = 0.0f; hi = h; flo = fm; fhi = fb; }
+        else {
+            // no sign change at the three samples: a grazing double root shows up as a dip
+            bool miss = !(c2 > 0.0f);
+            float tv = 0.0f;
+            if (!miss) {
+                tv = -0.5f * c1 / c2;
+                miss = !(tv > -h && tv < h) || fm - 0.25f * c1 * c1 / c2 > 0.25f * fminf(fm, fminf(fa, fb));    // dip clear of zero
+            }
+            float fv = 0.0f;
+            if (!miss) {
+                fv = local_f(Q, K, tm + tv, fc, fr);
+                miss = fv > K.mg + 0.05f * c2 * h * h;
+                if (!miss && !(fv < -K.mg)) return FT_DEFER_R(7);
+            }
+            if (miss) return back ? FT_DEFER_R(14) : FT_MISS;
+            lo = tv > 0.0f ? 0.0f : -h; hi = tv; flo = tv > 0.0f ? fm : fa; fhi = fv;
+        }
+        // the parabola's root inside the bracket, polished on f itself
+        float tau = 0.5f * (lo + hi);
+        if (fabsf(fhi) <= K.mg) tau = hi;                       // the sample at the bracket's end IS the root (to the margin)
+        else {
+            const float disc = c1 * c1 - 4.0f * c2 * fm;
+            if (disc >= 0.0f) {
+                const float sq = f_sqrt_fast(disc);
+                const float tq = -0.5f * (c1 + (c1 >= 0.0f ? sq : -sq));
+                const float t1 = c2 != 0.0f ? tq / c2 : 2.0f * h, t2 = tq != 0.0f ? fm / tq : 2.0f * h;
+                const bool in1 = t1 > lo && t1 < hi, in2 = t2 > lo && t2 < hi;
+                if (in1) tau = t1;
+                if (in2 && (!in1 || t2 < t1)) tau = t2;
+            }
+        }
+        // f(lo) > 0 >= f(hi) brackets the crossing: Newton on the parabola's slope, regula falsi when that leaves the bracket
+        float fx = 0.0f, slope = 0.0f;
+        bool conv = false;
+#pragma unroll 1
+        for (int it = 0; it < 6; ++it) {
+            fx = local_f(Q, K, tm + tau, fc, fr);
+            slope = fmaf(2.0f * c2, tau, c1);
+            if (!(slope < 0.0f)) slope = (fhi - flo) * f_rcp(hi - lo);
+            conv = slope < 0.0f && fabsf(fx) <= -slope * K.ds_tol && fabsf(fx) <= 64.0f * K.mg;
+            MRTX_DBG("    it=%d tau=%.6e fx=%.4e slope=%.4e lo=%.6e hi=%.6e flo=%.3e fhi=%.3e conv=%d need|fx|<=%.3e\n", it, tau, fx, slope, lo, hi, flo, fhi, (int)conv, -slope * K.ds_tol);
+            // stop at 2 % of the tolerance; what only reaches the tolerance itself (grazing roots at the float32
+            // noise floor) is accepted after the last iteration
+            if (conv && it >= 1 && fabsf(fx) <= -slope * (0.02f * K.ds_tol)) break;
+            if (fx > 0.0f) { lo = tau; flo = fx; } else { hi = tau; fhi = fx; }
+            float tn = slope < 0.0f ? tau - fx / slope : INFINITY;
+            if (!(tn >= lo && tn <= hi)) tn = lo - flo * (hi - lo) * f_rcp(fhi - flo);
+            if (!(tn >= lo && tn <= hi)) tn = 0.5f * (lo + hi);
+            tau = tn;
+        }
+        if (!conv) return FT_DEFER_R(slope < 0.0f ? 9 : 8);
+        // whose root is it?  Outside the cell and moving further out: the ray left the cell before it
+        // reached the surface (the next cell decides on its own patch).  Outside and moving in: the root
+        // lies before the entry, where this patch is only an extrapolation -> exact path.
+        const float e = K.epsc;
+        bool outside = false, leaving = false;
+        if (fc < -e) { outside = true; leaving = dfc < 0.0f; }
+        else if (fc > 1.0f + e) { outside = true; leaving = dfc > 0.0f; }
+        else if (fr < -e) { outside = true; leaving = dfr < 0.0f; }
+        else if (fr > 1.0f + e) { outside = true; leaving = dfr > 0.0f; }
+        if (outside) return leaving && !back ? FT_MISS : FT_DEFER_R(12);
+        out.s = s_c + (double)(tm + tau);
+        out.fc = fminf(fmaxf(fc, 0.0f), 1.0f); out.fr = fminf(fmaxf(fr, 0.0f), 1.0f);
+        out.d00 = d00; out.d01 = d01; out.d10 = d10; out.d11 = d11;
+        out.r0 = P.r0; out.c0 = P.c0;
+        return FT_HIT;
     }
-    if (!(slope < 0.0f) || !(fabsf(fx) <= -slope * K.ds_tol) || !(fabsf(fx) <= 64.0f * K.mg)) return FT_DEFER;
-    // whose root is it?  Outside the cell and moving further out: the ray left the cell before it
-    // reached the surface (the next cell decides).  Outside and moving in: the ray was already
-    // below the surface when it entered -> exact path.
-    const float e = K.epsc;
-    if (fc < -e) { if (dfc < 0.0f) return FT_MISS; return FT_DEFER; }
-    if (fc > 1.0f + e) { if (dfc > 0.0f) return FT_MISS; return FT_DEFER; }
-    if (fr < -e) { if (dfr < 0.0f) return FT_MISS; return FT_DEFER; }
-    if (fr > 1.0f + e) { if (dfr > 0.0f) return FT_MISS; return FT_DEFER; }
-    out.s = s_c + (double)(tm + tau);
-    out.fc = fminf(fmaxf(fc, 0.0f), 1.0f); out.fr = fminf(fmaxf(fr, 0.0f), 1.0f);
-    out.d00 = d00; out.d01 = d01; out.d10 = d10; out.d11 = d11;
-    out.r0 = P.r0; out.c0 = P.c0;
-    return FT_HIT;
 }
 
 // ---- directional walk ----------------------------------------------------------------------------
@@ -273,10 +369,32 @@ MRTX_HD inline bool walk_begin(const HeightField& hf, double radius, const Ray64
     return true;
 }
 
-// smallest crossing of the cone z = k r in (lo, hi], or +inf
-MRTX_HD inline float lat_cross(const Walk& w, float k, float lo, float hi) {
-    const float k2 = k * k;
-    const float A = fmaf(w.dz, w.dz, -k2), B = fmaf(w.oz, w.dz, -k2 * w.od), C = fmaf(w.oz, w.oz, -k2 * w.oo);
+// Latitude walls.  A wall is the cone z = k r (k = sin phi).  Towards the poles that form loses the wall in
+// float32: z and k r are both ~R while the distance to the wall only shows as r cos(phi) d(phi) in their
+// difference - at 88.5 deg half a cell of the full-resolution map is 8e-7 R, the rounding error of z.  Walls
+// beyond 45 deg are therefore tested as rho = kc r (kc = cos phi, rho = distance from the polar axis): the
+// same cone, with small numbers where the other form has large ones.
+// lat_side(): signed "northness" of a point relative to the wall, in units in which one radian of latitude is
+// at least 0.7 r (so one tolerance serves both forms).
+MRTX_HD inline float lat_side(float2 kk, float z, float rho, float r) {
+    if (kk.x > 0.70710678f) return z > 0.0f ? kk.y * r - rho : -r;
+    if (kk.x < -0.70710678f) return z < 0.0f ? rho - kk.y * r : r;
+    return z - kk.x * r;
+}
+
+// smallest crossing of the wall in (lo, hi], or +inf
+MRTX_HD inline float lat_cross(const Walk& w, float2 kk, float lo, float hi) {
+    const float k = kk.x;
+    float A, B, C;
+    if (fabsf(k) > 0.70710678f) {
+        const float c2 = kk.y * kk.y;
+        A = fmaf(w.dx, w.dx, fmaf(w.dy, w.dy, -c2));
+        B = fmaf(w.ox, w.dx, fmaf(w.oy, w.dy, -c2 * w.od));
+        C = fmaf(w.ox, w.ox, fmaf(w.oy, w.oy, -c2 * w.oo));
+    } else {
+        const float k2 = k * k;
+        A = fmaf(w.dz, w.dz, -k2); B = fmaf(w.oz, w.dz, -k2 * w.od); C = fmaf(w.oz, w.oz, -k2 * w.oo);
+    }
     const float disc = fmaf(B, B, -A * C);
     float best = INFINITY;
     if (disc >= 0.0f) {
@@ -339,7 +457,11 @@ MRTX_HD inline int walk_step(const HeightField& hf, float Rf, float inv_rs, Walk
     if (!(r2s <= rc2 && L > 0)) {       // (inside the cell's shell already: descend where we stand)
         const float x = fmaf(s, w.dx, w.ox), y = fmaf(s, w.dy, w.oy), z = fmaf(s, w.dz, w.oz);
         const float rs = f_sqrt_fast(fmaxf(r2s, 1e-30f));
-        const float tol = 2.0e-6f * rs;
+        // "On the wall" = within the float32 error of the wall function, which is NOT uniform: the re-based ray
+        // carries 1e-7 r everywhere, the wall functions add the rounding of their two cancelling terms.  A uniform
+        // 2e-6 r (3 % of a full-resolution cell) would hand a ray that runs nearly parallel to a wall to the next
+        // row tens of cells early, and a directional walk never comes back.
+        const float tol0 = 2.0e-7f * rs;
         float sx = w.smax;
         int face = 4;
         {   // the longitude wall ahead
@@ -347,6 +469,7 @@ MRTX_HD inline int walk_step(const HeightField& hf, float Rf, float inv_rs, Walk
             const float2 wl = MRTX_LDG(hf.lon32 + wi);
             const float sg = w.east ? 1.0f : -1.0f;
             const float g = sg * fmaf(x, wl.x, y * wl.y), dg = sg * fmaf(w.dx, wl.x, w.dy * wl.y);      // outwards positive
+            const float tol = fmaf(6.0e-7f, fabsf(x * wl.x) + fabsf(y * wl.y), tol0);
             if (dg > 0.0f) {
                 if (g >= -tol) { sx = s; face = 0; }            // on (or just beyond) it, moving out: leave now
                 else {
@@ -364,20 +487,24 @@ MRTX_HD inline int walk_step(const HeightField& hf, float Rf, float inv_rs, Walk
             float sl = INFINITY;
             int fl = north ? 1 : 2;
             if (north ? jn > 0 : js < H - 1) {                  // polar caps have no wall
-                const float k = MRTX_LDG(hf.lat32 + (north ? jn : js));
-                const float G = north ? z - k * rs : k * rs - z;        // outwards positive
-                sl = G >= -tol ? s : lat_cross(w, k, s, s_turn);
+                const float2 kk = MRTX_LDG(hf.latsc32 + (north ? jn : js));
+                const float side = lat_side(kk, z, f_sqrt_fast(fmaf(x, x, y * y)), rs);
+                const float G = north ? side : -side;                   // outwards positive
+                const float tol = fmaf(6.0e-7f * rs, fminf(fabsf(kk.x), kk.y), tol0);
+                sl = G >= -tol ? s : lat_cross(w, kk, s, s_turn);
             }
             if (!(sl <= s_turn) && s_turn < sx) {
                 // the ray turns inside this cell: from there on it heads for the other wall
                 sl = INFINITY; fl = north ? 2 : 1;
-                if (north ? js < H - 1 : jn > 0) sl = lat_cross(w, MRTX_LDG(hf.lat32 + (north ? js : jn)), s_turn, INFINITY);
+                if (north ? js < H - 1 : jn > 0) sl = lat_cross(w, MRTX_LDG(hf.latsc32 + (north ? js : jn)), s_turn, INFINITY);
             }
             if (sl < sx) { sx = sl; face = fl; }
         }
         const float pad = 4.0e-6f * Rf;
         const float ta = fmaxf(s - pad, 0.0f), tb = fminf(sx + pad, w.smax);
         const float tm = fminf(fmaxf(-w.od, ta), tb);
+        MRTX_DBG("walk %d L%d J%d I%d s=%.7f sx=%.7f face=%d rc=%.7f r(s)=%.7f r(tm)=%.7f east=%d north=%d\n", w.steps, L, J, I, s, sx, face, rc,
+                 sqrtf(r2s), sqrtf(walk_r2(w, tm)), (int)w.east, (int)(fmaf(s, w.n1, w.n0) > 0.0f));
         if (!(walk_r2(w, tm) <= rc2)) return walk_advance(hf, w, sx, face) ? TR_CONTINUE : TR_END;
         if (L == 0) { sx_out = sx; face_out = face; return TR_CANDIDATE; }
         if (r2s > rc2) {
@@ -394,8 +521,8 @@ MRTX_HD inline int walk_step(const HeightField& hf, float Rf, float inv_rs, Walk
         if (fmaf(x, wl.x, y * wl.y) >= 0.0f) ci += 1;
     }
     if (mj < min((J + 1) << L, H - 1)) {
-        const float k = MRTX_LDG(hf.lat32 + mj);
-        if (z - k * f_sqrt_fast(fmaf(x, x, fmaf(y, y, z * z))) < 0.0f) cj += 1;      // south of the mid wall
+        const float rho2 = fmaf(x, x, y * y);
+        if (lat_side(MRTX_LDG(hf.latsc32 + mj), z, f_sqrt_fast(rho2), f_sqrt_fast(fmaf(z, z, rho2))) < 0.0f) cj += 1;   // south of the mid wall
     }
     w.s = sd; w.L = L - 1; w.I = ci; w.J = cj;
     return TR_CONTINUE;
@@ -416,8 +543,8 @@ MRTX_HD inline int trace_ray_fast(const HeightField& hf, const FastConsts& K, do
         if (r == TR_END) return FT_MISS;
         if (r == TR_CANDIDATE) {
             ++cnt.tests;
-            const int t = fast_test<I16>(hf, K, R, w.s_in, s_min, w.s, sx, w.smax, P, out);
-            if (t != FT_MISS) return t;
+            const int t = fast_test<I16>(hf, K, R, w.s_in, s_min, w.s, sx, w.smax, P, false, out);
+            if (t != FT_MISS) return t;                      // FT_DEFER carries its reason in the upper bits
             if (!walk_advance(hf, w, sx, face)) return FT_MISS;
         }
     }

@@ -455,6 +455,13 @@ class B200OptiX:
                  "trav_step_lanes", "start_phases", "start_phase_lanes", "refills", "pixels_culled")
         return {k: int(out[i]) for i, k in enumerate(names)}
 
+    def defer_stats(self, reset: bool = False) -> dict:
+        """Samples the filtered kernel handed to the exact kernel, and why (include/moonb200.h)."""
+        out = (C.c_uint64 * 32)()
+        _lib.check(self._lib.mrtx_defer_stats(self._ctx, out, 1 if reset else 0))
+        return {"deferred_samples": int(out[0]), "primary_reasons": {r: int(out[r]) for r in range(1, 16) if out[r]},
+                "shadow_reasons": {r: int(out[16 + r]) for r in range(1, 16) if out[16 + r]}}
+
     def save_image(self, path: str, bps: str = "Bps8"):
         import cv2
         img = self._img_rgba

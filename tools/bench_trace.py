@@ -55,6 +55,7 @@ def time_frame(rt, spp, reps=3):
     ts = []
     for i in range(reps + 1):
         rt.counters(reset=True)
+        rt.defer_stats(reset=True)
         dev.synchronize()
         dev.timer_start()
         _lib.check(lib.mrtx_render(ctx, 0, 0, rt._width, rt._height, 0, spp, 1))
@@ -64,7 +65,7 @@ def time_frame(rt, spp, reps=3):
     c = rt.counters()
     rays = c["primary_rays"] + c["shadow_rays"]
     ms = float(np.median(ts))
-    return {"spp": spp, "ms": round(ms, 2), "Mrays_s": round(rays / ms / 1e3, 1), **c,
+    return {"spp": spp, "ms": round(ms, 2), "defer": rt.defer_stats(), "Mrays_s": round(rays / ms / 1e3, 1), **c,
             "nodes_per_inray": round(c["node_visits"] / max(1, c["primary_in_sphere"] + c["shadow_rays"]), 1)}
 
 if __name__ == "__main__":

@@ -24,7 +24,9 @@ def run_fast(l, elev, rays, s_min=0.0, scale=0.0, rs=1.0, start_level=-3):
 
 def report(name, W, ex, fa):
     texel = 2 * math.pi * 10 / W
-    st = fa[:, 0].astype(int)
+    raw = fa[:, 0].astype(int)
+    st = raw & 3
+    reasons = np.bincount((raw >> 2)[st == 2], minlength=1)
     hit_e = ex[:, 0] > 0
     n = len(st)
     dec = st != 2
@@ -33,7 +35,7 @@ def report(name, W, ex, fa):
     ds = np.abs(fa[:, 1] - ex[:, 1]) / texel
     print(f"{name}: rays {n}  exact hits {hit_e.sum()}  defer {np.mean(st == 2):.5f}  decided-wrong {wrong.sum()}  "
           f"max ds {ds[both].max() if both.any() else 0:.3g} texel  >1e-3: {(ds[both] > 1e-3).sum()}  "
-          f"nodes/ray {fa[:, 6].mean():.2f} (exact {ex[:, 5].mean():.2f})  tests/ray {fa[:, 7].mean():.2f} (exact {ex[:, 6].mean():.2f})")
+          f"reasons {dict((i, int(c)) for i, c in enumerate(reasons) if c)}  nodes/ray {fa[:, 6].mean():.2f} (exact {ex[:, 5].mean():.2f})  tests/ray {fa[:, 7].mean():.2f} (exact {ex[:, 6].mean():.2f})")
     return wrong, both, ds
 
 

@@ -20,6 +20,7 @@ static void build_host_pyramid(HeightField& hf, std::vector<std::vector<T>>& sto
     for (int k = 1; k <= top; ++k) {
         hf.nx[k] = (W + (1 << k) - 1) >> k; hf.ny[k] = (H - 1 + (1 << k) - 1) >> k;
         store[k].resize((size_t)hf.nx[k] * hf.ny[k]);
+#pragma omp parallel for schedule(static)
         for (int J = 0; J < hf.ny[k]; ++J) for (int I = 0; I < hf.nx[k]; ++I) {
             T m;
             if (k == 1) {
@@ -41,17 +42,36 @@ static void build_host_pyramid(HeightField& hf, std::vector<std::vector<T>>& sto
 
 extern "C" void dbg_set(int v) { mrtx_core::g_debug = v; }
 
+// pyramid + wall tables are cached across calls (keyed on the map pointer): they take minutes at 92160 x 46080
+struct HostScene {
+    const void* key = nullptr; int W = 0, H = 0;
+    HeightField hf;
+    std::vector<std::vector<int16_t>> s16; std::vector<std::vector<float>> s32;
+    std::vector<float2> lon32, latsc32; std::vector<double2> lon64, lat64; std::vector<float> lat32;
+};
+static HostScene g_scene;
+
+static const HeightField& host_scene(const void* map, int is_i16, int W, int H, float scale, float rs, float dmax) {
+    HostScene& S = g_scene;
+    if (S.key != map || S.W != W || S.H != H) {
+        S = HostScene();
+        S.key = map; S.W = W; S.H = H;
+        HeightField& hf = S.hf;
+        memset(&hf, 0, sizeof(hf));
+        hf.base = map; hf.is_i16 = is_i16; hf.W = W; hf.H = H;
+        if (is_i16) build_host_pyramid<int16_t>(hf, S.s16); else build_host_pyramid<float>(hf, S.s32);
+        S.lon32.resize(W + 1); S.lon64.resize(W + 1); S.lat64.resize(H); S.lat32.resize(H); S.latsc32.resize(H);
+        for (int i = 0; i <= W; ++i) { double sn, cs; sincospi((2.0 * i + 1.0) / W - 1.0, &sn, &cs); S.lon64[i] = make_double2(cs, sn); S.lon32[i] = make_float2((float)cs, (float)sn); }
+        for (int i = 0; i < H; ++i) { double sn, cs; sincospi((i + 0.5) / H, &sn, &cs); S.lat64[i] = make_double2(cs, sn); S.lat32[i] = (float)cs; S.latsc32[i] = make_float2((float)cs, (float)sn); }
+        hf.lon32 = S.lon32.data(); hf.lon64 = S.lon64.data(); hf.lat32 = S.lat32.data(); hf.lat64 = S.lat64.data(); hf.latsc32 = S.latsc32.data();
+    }
+    S.hf.scale = scale; S.hf.radius_scale = rs; S.hf.dmax = dmax;
+    return S.hf;
+}
+
 extern "C" int dbg_trace(const void* map, int is_i16, int W, int H, float scale, float rs, float dmax,
                          const double* rays, int n, double s_min, double radius, int any_hit, int start_level, double* out) {
-    HeightField hf;
-    memset(&hf, 0, sizeof(hf));
-    hf.base = map; hf.is_i16 = is_i16; hf.W = W; hf.H = H; hf.scale = scale; hf.radius_scale = rs; hf.dmax = dmax;
-    std::vector<std::vector<int16_t>> s16; std::vector<std::vector<float>> s32;
-    if (is_i16) build_host_pyramid<int16_t>(hf, s16); else build_host_pyramid<float>(hf, s32);
-    std::vector<float2> lon32(W + 1); std::vector<double2> lon64(W + 1), lat64(H); std::vector<float> lat32(H);
-    for (int i = 0; i <= W; ++i) { double sn, cs; sincospi((2.0 * i + 1.0) / W - 1.0, &sn, &cs); lon64[i] = make_double2(cs, sn); lon32[i] = make_float2((float)cs, (float)sn); }
-    for (int i = 0; i < H; ++i) { double sn, cs; sincospi((i + 0.5) / H, &sn, &cs); lat64[i] = make_double2(cs, sn); lat32[i] = (float)cs; }
-    hf.lon32 = lon32.data(); hf.lon64 = lon64.data(); hf.lat32 = lat32.data(); hf.lat64 = lat64.data();
+    const HeightField& hf = host_scene(map, is_i16, W, H, scale, rs, dmax);
     if (start_level < 0) start_level = hf.top + start_level;
 #pragma omp parallel for schedule(dynamic, 16)
     for (int i = 0; i < n; ++i) {
@@ -72,15 +92,7 @@ extern "C" int dbg_trace(const void* map, int is_i16, int W, int H, float scale,
 // fast (filtered float32) path: out[i] = {status (0 miss, 1 hit, 2 defer), s, fc, fr, r0, c0, nodes, tests}
 extern "C" int dbg_trace_fast(const void* map, int is_i16, int W, int H, float scale, float rs, float dmax,
                               const double* rays, int n, double s_min, double radius, int start_level, double* out) {
-    HeightField hf;
-    memset(&hf, 0, sizeof(hf));
-    hf.base = map; hf.is_i16 = is_i16; hf.W = W; hf.H = H; hf.scale = scale; hf.radius_scale = rs; hf.dmax = dmax;
-    std::vector<std::vector<int16_t>> s16; std::vector<std::vector<float>> s32;
-    if (is_i16) build_host_pyramid<int16_t>(hf, s16); else build_host_pyramid<float>(hf, s32);
-    std::vector<float2> lon32(W + 1); std::vector<double2> lon64(W + 1), lat64(H); std::vector<float> lat32(H);
-    for (int i = 0; i <= W; ++i) { double sn, cs; sincospi((2.0 * i + 1.0) / W - 1.0, &sn, &cs); lon64[i] = make_double2(cs, sn); lon32[i] = make_float2((float)cs, (float)sn); }
-    for (int i = 0; i < H; ++i) { double sn, cs; sincospi((i + 0.5) / H, &sn, &cs); lat64[i] = make_double2(cs, sn); lat32[i] = (float)cs; }
-    hf.lon32 = lon32.data(); hf.lon64 = lon64.data(); hf.lat32 = lat32.data(); hf.lat64 = lat64.data();
+    const HeightField& hf = host_scene(map, is_i16, W, H, scale, rs, dmax);
     if (start_level < 0) start_level = hf.top + start_level;
     const FastConsts K = make_fast_consts(hf, radius);
 #pragma omp parallel for schedule(dynamic, 16)
