@@ -247,6 +247,7 @@ def run_ours(args):
     for j in range(args.warmup):
         device_step(states[j])
     rt.counters(reset=True)
+    rt.defer_stats(reset=True)
     barrier()
     clocks = ClockSampler(local)
     clocks.start()
@@ -257,7 +258,9 @@ def run_ours(args):
     barrier()
     clock_info = clocks.stop()
     c = rt.counters()
-    launches = 3 * args.steps          # cull_kernel + trace_kernel_persistent + resolve_kernel per frame
+    # cull_kernel + trace_kernel_fast + trace_kernel_referee + resolve_kernel per frame (<= 32 spp: one sample chunk)
+    launches = (2 + 2 * ((args.spp + 31) // 32)) * args.steps
+    defer = rt.defer_stats()
     ms_total = max_over_ranks(ms_total)
     rays_local = c["primary_rays"] + c["shadow_rays"]
     rays_all = sum_over_ranks(float(rays_local))
@@ -280,7 +283,7 @@ def run_ours(args):
     algo_bytes = b_floor * rays_in
     peak, peak_src = measured_peak()
     achieved = algo_bytes / (k_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "cull_kernel + trace_kernel_persistent<int16> (one mrtx_render)", "achieved": round(achieved, 2), "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "cull_kernel + trace_kernel_fast<int16> + trace_kernel_referee<int16> (one mrtx_render)", "achieved": round(achieved, 2), "peak": peak,
                 "unit": "GB/s", "frac": round(achieved / peak, 5), "traffic": args.traffic,
                 "algorithmic_bytes_per_launch": int(algo_bytes), "bytes_per_ray": b_floor,
                 "rays_in_sphere_per_launch": int(rays_in), "kernel_ms": round(k_ms, 3), "peak_source": peak_src,
@@ -322,7 +325,7 @@ def run_ours(args):
             "metric": "Mrays/s (primary+shadow) @4K", "value": round(value, 2), "unit": "Mrays/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 traversal + f64 root refinement over int16 texels", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f32 (pyramid walk and patch test in a cell-local frame re-based in f64) over int16 texels; f64 referee for undecided samples", "data": "synthetic",
             "config": {"workload": f"{args.img_w}x{args.img_h} frame, {args.map_w}x{args.map_h} int16 synthetic LOLA map + "
                                    f"{args.color_w // COLOR_K}x{args.color_h // COLOR_K} colour texture, {args.spp} spp "
                                    f"(BASELINE config 3; N>1: one frame per rank per step, config 4)",
@@ -333,8 +336,8 @@ def run_ours(args):
                      "primary_in_sphere_per_step": c["primary_in_sphere"] // args.steps,
                      "node_visits_per_step": c["node_visits"] // args.steps, "patch_tests_per_step": c["patch_tests"] // args.steps,
                      "overflow": c["overflow"],
-                     "simd_lanes_per_traversal_step": round(c["trav_step_lanes"] / max(1, c["trav_steps"]), 2),
-                     "simd_lanes_per_float64_test_phase": round(c["test_phase_lanes"] / max(1, c["test_phases"]), 2)},
+                     "samples_deferred_to_f64_referee_per_step": defer["deferred_samples"] // args.steps,
+                     "defer_reasons_primary": defer["primary_reasons"], "defer_reasons_shadow": defer["shadow_reasons"]},
             "frames_per_s": round(world * args.steps / (ms_total * 1e-3), 3),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clock_info,
         }
@@ -423,7 +426,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--spp", type=int, default=16)

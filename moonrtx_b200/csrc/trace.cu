@@ -594,8 +594,11 @@ __device__ __forceinline__ bool shade_fast(const RenderArgs& A, const Ray64& R, 
     return sp.shadows != 0;
 }
 
+#ifndef MRTX_FAST_MINBLOCKS
+#define MRTX_FAST_MINBLOCKS 8
+#endif
 template <bool I16>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, MRTX_FAST_MINBLOCKS)
 trace_kernel_fast(const __grid_constant__ RenderArgs A) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
