@@ -83,6 +83,7 @@ struct SceneParams {
     double scene_epsilon;
     float  exposure, inv_gamma;
     unsigned jitter, shadows, debug_hits;
+    unsigned start_primary, start_shadow;   // filtered kernel: primary rays start at level top - start_primary, shadow rays at start_shadow
     unsigned kernel;                        // 2 = filtered float32 kernel + exact kernel on what it defers (default),
                                             // 1 = exact persistent kernel only, 0 = exact, one thread per pixel
 };

@@ -643,7 +643,7 @@ trace_kernel_fast(const __grid_constant__ RenderArgs A) {
                 bool alive = false;
                 if (want) {
                     if (pass == 0) primary_ray_fast(A, x, y, pixel, sm, R);
-                    alive = walk_begin(A.hf, A.sp.radius, R, 0.0, pass ? 2 : A.hf.top - 3, st);
+                    alive = walk_begin(A.hf, A.sp.radius, R, 0.0, pass ? (int)A.sp.start_shadow : A.hf.top - (int)A.sp.start_primary, st);
                     if (pass == 0) entered = alive;
                 }
                 int res = FT_MISS;

@@ -81,6 +81,9 @@ if __name__ == "__main__":
     kernels = [int(v) for v in os.environ.get("KERNELS", "2").split(",")]
     lib, ctx = rt._dev.lib, rt._dev.ctx
     imgs = {}
+    if os.environ.get("START"):
+        a, b = [int(v) for v in os.environ["START"].split(",")]
+        _lib.check(lib.mrtx_set_uint(ctx, b"start_levels", a, b))
     for spp in spps:
         for k in kernels:
             _lib.check(lib.mrtx_set_uint(ctx, b"kernel", k, 0))

@@ -23,3 +23,20 @@ items.sort(key=lambda t: -t[0])
 print(" share  lanes  stall%  where")
 for wi, ti, sm, f, ln, src in items[:top]:
     print(f"{wi / tot_i:6.3f} {ti / max(wi, 1):6.1f} {sm / max(tot_s, 1):7.3f}  {f}:{ln}  {src}")
+
+# coarse categories (line ranges of trace_fast.cuh / trace.cu at the time of the capture)
+if len(sys.argv) > 3:
+    import re
+    cats = {}
+    for wi, ti, sm, f, ln, src in items:
+        ln = int(ln)
+        if f == "trace_fast.cuh":
+            c = "fast_test/local_f" if ln < 330 else ("walk_begin" if ln < 373 else "walk_step")
+        elif f == "trace.cu":
+            c = "raygen/rng" if ln < 500 else ("shade" if ln < 596 else "kernel loop")
+        else:
+            c = f
+        a = cats.setdefault(c, [0, 0, 0]); a[0] += wi; a[1] += ti; a[2] += sm
+    print("\ncategory            share  lanes  stall%")
+    for c, (wi, ti, sm) in sorted(cats.items(), key=lambda kv: -kv[1][0]):
+        print(f"{c:20s} {wi / tot_i:5.3f} {ti / max(wi, 1):6.1f} {sm / max(tot_s, 1):7.3f}")
