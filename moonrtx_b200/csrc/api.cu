@@ -92,6 +92,7 @@ int mrtx_destroy(mrtx_ctx* ctx) {
     cudaFree(ctx->d_work);
     cudaFree(ctx->d_counters);
     cudaFree(ctx->d_defer_stats);
+    cudaFree(ctx->wave_buf);
     cudaFree(ctx->flush_buf);
     cudaFree(ctx->gather_buf);
     cudaEventDestroy(ctx->ev0);
@@ -449,7 +450,7 @@ int mrtx_set_uint(mrtx_ctx* ctx, const char* name, unsigned a, unsigned b) {
     else if (!strcmp(name, "shadows")) ctx->sp.shadows = a ? 1u : 0u;
     else if (!strcmp(name, "debug_hits")) ctx->sp.debug_hits = a ? 1u : 0u;
     else if (!strcmp(name, "start_levels")) { ctx->sp.start_primary = a; ctx->sp.start_shadow = b; }
-    else if (!strcmp(name, "kernel")) { MRTX_REQUIRE(a <= 2u, "kernel must be 0, 1 or 2"); ctx->sp.kernel = a; }
+    else if (!strcmp(name, "kernel")) { MRTX_REQUIRE(a <= 3u, "kernel must be 0, 1, 2 or 3"); ctx->sp.kernel = a; }
     else { mrtx_set_error("unknown uint parameter '%s'", name); return MRTX_ERR_INVALID; }
     return MRTX_OK;
 }

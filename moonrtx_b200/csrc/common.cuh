@@ -117,6 +117,8 @@ struct mrtx_ctx {
     unsigned* d_work;           // trace work counter + list length
     unsigned* pixel_list;       // width * height entries
     uint2* defer_list;          // width * height entries: samples the filtered kernel hands to the exact one
+    // wavefront pipeline scratch (allocated on first use): ray / hit records, radiance slots, shadow queue, deferred items
+    void* wave_buf; size_t wave_items;
 
     // comm
     void* nccl_lib; void* nccl_comm; int nranks, rank;

@@ -18,6 +18,8 @@
 // Traversal state is float32 re-based at the bounding-sphere entry (H4); every float32
 // decision carries a margin so that it can only add candidate cells, never drop one.
 
+#include <algorithm>
+
 #include "trace_fast.cuh"
 
 namespace {
@@ -70,6 +72,15 @@ struct RenderArgs {
     unsigned list_cap;
     unsigned long long* defer_stats; // [reason + 16 * shadow]: why samples were deferred
     uint2* defer_list;               // (pixel, mask of samples sample0 + bit) the fast kernel could not certify
+    // wavefront pipeline (kernel 3): one wave = list pixels [wave_p0, wave_p0 + wave_np) x nsamples samples
+    unsigned wave_p0, wave_np;
+    float* rad;                      // [item][3] radiance of every sample of the wave, item = (p - wave_p0) * nsamples + k
+    struct RayRec* rays;             // [item] primary ray records
+    struct HitRec* hits;             // [item] what the primary walk decided
+    struct RayRec* srays;            // shadow rays spawned by the shading pass (work_counter[5] of them) ...
+    unsigned* sitem;                 // ... and the item each belongs to
+    uint2* defer_items;              // (list pixel p, sample k) the filter could not certify (work_counter[3] of them)
+    int lvl_primary, lvl_shadow;     // pyramid level the walks start at
     FastConsts K;
     float inv_rs;
     int g_log2;                      // fast kernel: 2^g_log2 lanes share one pixel (one sample each per round)
@@ -722,6 +733,286 @@ trace_kernel_fast(const __grid_constant__ RenderArgs A) {
     if (lane == 0 && nd) atomicAdd(&A.defer_stats[0], (unsigned long long)nd);
 }
 
+// ---- wavefront pipeline (production path, kernel 3) ---------------------------------------------------------------------
+// trace_kernel_fast keeps a sample in one lane from the camera to the light and a warp busy until the LAST of its 32
+// samples is decided: a grazing ray that walks 200 cells keeps 31 finished lanes waiting, and ray generation, patch
+// tests and shading run with whatever lanes happen to need them (measured: 16 of 32 lanes active per instruction on
+// primary rays, 7 on shadow rays).  Here the work of one wave of (pixel, sample) items is cut where its shape changes:
+//   gen_kernel            dense, one item per thread: camera ray, bounding-sphere clip, first cell -> 64-byte ray record
+//   trace_kernel_walk     streaming: each lane owns one ray at a time, walks the pyramid and tests candidate patches;
+//                         a lane whose ray is decided writes a 32-byte hit record and takes the next ray of the queue.
+//                         Nothing but the float32 walk state lives in registers - the float64 ray is read back from
+//                         its record for the ~1.1 patch tests a ray needs.
+//   shade_kernel          dense: normal, albedo, Lambert term -> the item's radiance slot; the shadow ray of a lit hit
+//                         is clipped and appended to the shadow queue as another ray record
+//   trace_kernel_walk     the same streaming kernel over the shadow queue: occluded -> zero the item's slot
+//   trace_kernel_referee  the few samples the filter could not certify, traced again with the float64 referee
+//   reduce_kernel         per pixel: slots summed in sample order, one accumulator update
+// A sample's result does not depend on which lane, warp or launch produced it.
+struct RayRec { double ox, oy, oz, dx, dy, dz, s_in; float smax; unsigned cell; };   // 64 B; smax < 0: nothing to walk
+struct HitRec { double s; float fc, fr; int r0, c0; int status; unsigned pad; };      // 32 B; status -1: missed the bounding sphere
+static_assert(sizeof(RayRec) == 64 && sizeof(HitRec) == 32, "record layout");
+
+__device__ __forceinline__ void store_ray_rec(RayRec* dst, const Ray64& R, const Walk& st, bool alive) {
+    double2* q = (double2*)dst;
+    q[0] = make_double2(R.ox, R.oy); q[1] = make_double2(R.oz, R.dx); q[2] = make_double2(R.dy, R.dz);
+    const float smax = alive ? st.smax : -1.0f;
+    const unsigned cell = alive ? ((unsigned)st.J << 16) | (unsigned)st.I : 0u;
+    q[3] = make_double2(alive ? st.s_in : 0.0, __hiloint2double((int)cell, __float_as_int(smax)));
+}
+__device__ __forceinline__ void load_ray_rec(const RayRec* src, Ray64& R) {
+    const double2* q = (const double2*)src;
+    const double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+    R.ox = a.x; R.oy = a.y; R.oz = b.x; R.dx = b.y; R.dy = c.x; R.dz = c.y;
+}
+
+// item -> pixel and sample of the wave
+struct ItemId { int x, y; uint32_t pixel; unsigned pl, k, sm; };
+__device__ __forceinline__ ItemId item_id(const RenderArgs& A, unsigned it, unsigned n_limb) {
+    ItemId d;
+    d.pl = it / A.nsamples; d.k = it - d.pl * A.nsamples; d.sm = A.sample0 + d.k;
+    const unsigned packed = list_pixel(A, A.wave_p0 + d.pl, n_limb);
+    d.x = (int)(packed & 0xffffu); d.y = (int)(packed >> 16);
+    d.pixel = (uint32_t)d.y * (uint32_t)A.width + (uint32_t)d.x;
+    return d;
+}
+
+__global__ void __launch_bounds__(256)
+gen_kernel(const __grid_constant__ RenderArgs A) {
+    const unsigned n_limb = A.work_counter[4];
+    const unsigned nkept = n_limb + A.work_counter[1];
+    if (A.wave_p0 >= nkept) return;
+    const unsigned n_items = min(A.wave_np, nkept - A.wave_p0) * A.nsamples;
+    for (unsigned it = blockIdx.x * blockDim.x + threadIdx.x; it < n_items; it += gridDim.x * blockDim.x) {
+        const ItemId d = item_id(A, it, n_limb);
+        Ray64 R;
+        Walk st;
+        primary_ray_fast(A, d.x, d.y, d.pixel, d.sm, R);
+        const bool alive = walk_begin(A.hf, A.sp.radius, R, 0.0, A.lvl_primary, st);
+        store_ray_rec(A.rays + it, R, st, alive);
+        if (!alive) A.hits[it].status = -1;
+    }
+}
+
+#ifndef MRTX_WALK_MINBLOCKS
+#define MRTX_WALK_MINBLOCKS 8
+#endif
+#ifndef MRTX_WALK_CAND
+#define MRTX_WALK_CAND 12
+#endif
+#ifndef MRTX_WALK_REFILL
+#define MRTX_WALK_REFILL 4
+#endif
+
+enum { LM_EMPTY = 0, LM_WALK = 1, LM_CAND = 2 };
+
+template <bool I16, bool SHADOW>
+__global__ void __launch_bounds__(128, MRTX_WALK_MINBLOCKS)
+trace_kernel_walk(const __grid_constant__ RenderArgs A) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    unsigned n_items;
+    if (SHADOW) n_items = A.work_counter[5];
+    else {
+        const unsigned nkept = A.work_counter[4] + A.work_counter[1];
+        if (A.wave_p0 >= nkept) return;
+        n_items = min(A.wave_np, nkept - A.wave_p0) * A.nsamples;
+    }
+    const RayRec* const recs = SHADOW ? A.srays : A.rays;
+    unsigned* const queue = A.work_counter + (SHADOW ? 6 : 2);
+    const int L0 = SHADOW ? A.lvl_shadow : A.lvl_primary;
+    const float Rf = A.K.R;
+    Counters cnt = {0u, 0u, 0u};
+    unsigned n_defer = 0, n_occluded = 0;
+
+    int mode = LM_EMPTY, face = 4;
+    unsigned ridx = 0;
+    Walk st;
+    RawPatch P;
+    float sx = 0.f;
+    bool exhausted = false;
+
+    for (;;) {
+        const unsigned m_walk = __ballot_sync(FULL, mode == LM_WALK);
+        const unsigned m_cand = __ballot_sync(FULL, mode == LM_CAND);
+        const unsigned m_empty = ~(m_walk | m_cand);
+        const bool idle = (m_walk | m_cand) == 0u;
+        if (!exhausted && (idle || __popc(m_empty) >= MRTX_WALK_REFILL)) {
+            // ---- refill: the next rays of the queue, one atomic per warp ---------------------------------------
+            const unsigned n = (unsigned)__popc(m_empty);
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(queue, n);
+            base = __shfl_sync(FULL, base, 0);
+            if (base + n >= n_items) exhausted = true;
+            const unsigned idx = base + (unsigned)__popc(m_empty & lt);
+            if (mode == LM_EMPTY && idx < n_items) {
+                const RayRec* rec = recs + idx;
+                const double2 tail = __ldg((const double2*)rec + 3);
+                const float smax = __int_as_float(__double2loint(tail.y));
+                if (smax >= 0.0f) {
+                    const unsigned cell = (unsigned)__double2hiint(tail.y);
+                    Ray64 R;
+                    load_ray_rec(rec, R);
+                    walk_setup(R, tail.x, smax, st);
+                    st.L = L0; st.J = (int)(cell >> 16); st.I = (int)(cell & 0xffffu);
+                    st.s = 0.0f; st.steps = 0;
+                    ridx = idx;
+                    mode = LM_WALK;
+                }
+            }
+            continue;
+        }
+        if (idle) break;
+        bool finished = false;
+        int status = FT_MISS;
+        FastHit fh;
+        if (__popc(m_cand) >= MRTX_WALK_CAND || __popc(m_cand) >= __popc(m_walk)) {
+            // ---- patch test ------------------------------------------------------------------------------------
+            if (mode == LM_CAND) {
+                ++cnt.tests;
+                const RayRec* rec = recs + ridx;
+                Ray64 R;
+                load_ray_rec(rec, R);
+                const double s_in = __ldg(&rec->s_in);
+                status = fast_test<I16>(A.hf, A.K, R, s_in, 0.0, st.s, sx, st.smax, P, SHADOW, fh);
+                if (status == FT_MISS && walk_advance(A.hf, st, sx, face)) mode = LM_WALK;
+                else finished = true;
+            }
+        } else if (mode == LM_WALK) {
+            // ---- walk step -------------------------------------------------------------------------------------
+            const int r = walk_step<I16>(A.hf, Rf, A.inv_rs, st, P, sx, face, cnt);
+            if (r == TR_CANDIDATE) mode = LM_CAND;
+            else if (r == TR_END) finished = true;
+        }
+        if (finished) {
+            mode = LM_EMPTY;
+            if (SHADOW) {
+                if (status != FT_MISS) {
+                    const unsigned item = __ldg(A.sitem + ridx);
+                    float* slot = A.rad + (size_t)item * 3;          // occluded (or undecided: the referee fills it in)
+                    slot[0] = 0.f; slot[1] = 0.f; slot[2] = 0.f;
+                    if ((status & 3) == FT_HIT) ++n_occluded;
+                    else {
+                        atomicAdd(&A.defer_stats[16 + (status >> 2)], 1ull);
+                        const unsigned pl = item / A.nsamples;
+                        A.defer_items[atomicAdd(&A.work_counter[3], 1u)] = make_uint2(A.wave_p0 + pl, item - pl * A.nsamples);
+                        ++n_defer;
+                    }
+                }
+            } else {
+                HitRec* h = A.hits + ridx;
+                if (status == FT_HIT) {
+                    ((double2*)h)[0] = make_double2(fh.s, __hiloint2double(__float_as_int(fh.fr), __float_as_int(fh.fc)));
+                    ((int4*)h)[1] = make_int4(fh.r0, fh.c0, status, 0);
+                } else h->status = status;
+            }
+        }
+    }
+    const RayStats rs = {0u, 0u, 0u, 0u, n_occluded};
+    flush_counters(A, rs, cnt, lane);
+    if (SHADOW) {
+        const unsigned nd = __reduce_add_sync(FULL, n_defer);
+        if (lane == 0 && nd) {
+            // the referee traces these samples from the camera again: take back what the shading pass counted for them
+            const unsigned long long neg = 0ull - (unsigned long long)nd;
+            atomicAdd(&A.defer_stats[0], (unsigned long long)nd);
+            atomicAdd(&A.counters[0], neg); atomicAdd(&A.counters[1], neg); atomicAdd(&A.counters[2], neg); atomicAdd(&A.counters[3], neg);
+        }
+    }
+}
+
+#ifndef MRTX_SHADE_MINBLOCKS
+#define MRTX_SHADE_MINBLOCKS 6
+#endif
+template <bool I16>
+__global__ void __launch_bounds__(128, MRTX_SHADE_MINBLOCKS)
+shade_kernel(const __grid_constant__ RenderArgs A) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned n_limb = A.work_counter[4];
+    const unsigned nkept = n_limb + A.work_counter[1];
+    if (A.wave_p0 >= nkept) return;
+    const unsigned n_items = min(A.wave_np, nkept - A.wave_p0) * A.nsamples;
+    const unsigned n_round = (n_items + 31u) & ~31u;                     // whole warps stay in the loop (ballots)
+    RayStats rs = {0u, 0u, 0u, 0u, 0u};
+    const Counters cnt = {0u, 0u, 0u};
+    unsigned n_defer = 0;
+    for (unsigned it = blockIdx.x * blockDim.x + threadIdx.x; it < n_round; it += gridDim.x * blockDim.x) {
+        float3 lit = make_float3(0.f, 0.f, 0.f);
+        bool spawn = false;
+        Ray64 S;
+        Walk sw;
+        if (it < n_items) {
+            const ItemId d = item_id(A, it, n_limb);
+            const HitRec* h = A.hits + it;
+            const int4 hb = __ldg((const int4*)h + 1);                  // r0, c0, status
+            const int status = hb.z;
+            if (status >= 0 && (status & 3) == FT_DEFER) {
+                atomicAdd(&A.defer_stats[status >> 2], 1ull);
+                A.defer_items[atomicAdd(&A.work_counter[3], 1u)] = make_uint2(A.wave_p0 + d.pl, d.k);
+                ++n_defer;
+            } else {
+                ++rs.primary;
+                if (status >= 0) ++rs.inside;
+                if (status == FT_HIT) {
+                    ++rs.hits;
+                    const double2 ha = __ldg((const double2*)h);
+                    FastHit fh;
+                    fh.s = ha.x; fh.fc = __int_as_float(__double2loint(ha.y)); fh.fr = __int_as_float(__double2hiint(ha.y));
+                    fh.r0 = hb.x; fh.c0 = hb.y;
+                    RawPatch P;
+                    load_raw_patch<I16>(A.hf, fh.r0, fh.c0, P);
+                    fh.d00 = decode_exact<I16>(A.hf, P.v00); fh.d01 = decode_exact<I16>(A.hf, P.v01);
+                    fh.d10 = decode_exact<I16>(A.hf, P.v10); fh.d11 = decode_exact<I16>(A.hf, P.v11);
+                    Ray64 R;
+                    load_ray_rec(A.rays + it, R);
+                    if (shade_fast(A, R, fh, d.x, d.y, d.pixel, d.sm, lit, S)) {
+                        ++rs.shadow;
+                        spawn = walk_begin(A.hf, A.sp.radius, S, 0.0, A.lvl_shadow, sw);
+                    }
+                } else write_miss(A, d.x, d.y, d.sm == A.sample0);
+            }
+            float* slot = A.rad + (size_t)it * 3;
+            slot[0] = lit.x; slot[1] = lit.y; slot[2] = lit.z;
+        }
+        // shadow rays of the warp go to the queue together, in lane order
+        const unsigned m = __ballot_sync(FULL, spawn);
+        if (m) {
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(&A.work_counter[5], (unsigned)__popc(m));
+            base = __shfl_sync(FULL, base, 0);
+            if (spawn) {
+                const unsigned j = base + (unsigned)__popc(m & ((1u << lane) - 1u));
+                store_ray_rec(A.srays + j, S, sw, true);
+                A.sitem[j] = it;
+            }
+        }
+    }
+    flush_counters(A, rs, cnt, lane);
+    const unsigned nd = __reduce_add_sync(FULL, n_defer);
+    if (lane == 0 && nd) atomicAdd(&A.defer_stats[0], (unsigned long long)nd);
+}
+
+// per pixel of the wave: radiance slots summed in sample order -> accumulator
+__global__ void __launch_bounds__(256)
+reduce_kernel(const __grid_constant__ RenderArgs A) {
+    const unsigned n_limb = A.work_counter[4];
+    const unsigned nkept = n_limb + A.work_counter[1];
+    if (A.wave_p0 >= nkept) return;
+    const unsigned npix = min(A.wave_np, nkept - A.wave_p0), ns = A.nsamples;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
+        const float* v = A.rad + (size_t)i * ns * 3;
+        float3 acc = make_float3(0.f, 0.f, 0.f);
+        for (unsigned k = 0; k < ns; ++k) { acc.x += v[3 * k]; acc.y += v[3 * k + 1]; acc.z += v[3 * k + 2]; }
+        const unsigned px = list_pixel(A, A.wave_p0 + i, n_limb);
+        float4* ap = A.accum + (size_t)(px >> 16) * A.width + (px & 0xffffu);
+        float4 old = *ap;
+        old.x += acc.x; old.y += acc.y; old.z += acc.z; old.w += (float)ns;
+        *ap = old;
+    }
+}
+
 // ---- deferred samples: same walk, float64 referee per undecided patch ---------------------------------
 // One WARP per deferred sample.  The sample is traced again from the start with the float32 walk and the
 // filter; only where the filter says FT_DEFER does the float64 exact test of trace_core.cuh (exact in-cell
@@ -796,7 +1087,9 @@ __device__ __forceinline__ double shfl_d(double v, int src) {
     return __hiloint2double(__shfl_sync(0xffffffffu, __double2hiint(v), src), __shfl_sync(0xffffffffu, __double2loint(v), src));
 }
 
-template <bool I16>
+// WAVE: entries are (list pixel, sample) items of the wavefront pipeline and the result goes to the item's
+// radiance slot; otherwise (pixel, sample mask) entries of trace_kernel_fast and the result is added to the accumulator.
+template <bool I16, bool WAVE>
 __global__ void __launch_bounds__(64)
 trace_kernel_referee(const __grid_constant__ RenderArgs A) {
     const unsigned total = A.work_counter[3];
@@ -804,12 +1097,14 @@ trace_kernel_referee(const __grid_constant__ RenderArgs A) {
     const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     Counters cnt = {0u, 0u, 0u};
     RayStats rs = {0u, 0u, 0u, 0u, 0u};                    // lane 0 counts rays
+    const unsigned n_limb = A.work_counter[4];
     for (unsigned e = warp; e < total; e += nwarps) {
-        const uint2 ent = A.defer_list[e];
-        const int x = (int)(ent.x & 0xffffu), y = (int)(ent.x >> 16);
+        const uint2 ent = WAVE ? A.defer_items[e] : A.defer_list[e];
+        const unsigned packed = WAVE ? list_pixel(A, ent.x, n_limb) : ent.x;
+        const int x = (int)(packed & 0xffffu), y = (int)(packed >> 16);
         const uint32_t pixel = (uint32_t)y * (uint32_t)A.width + (uint32_t)x;
         float3 acc = make_float3(0.f, 0.f, 0.f);            // lane 0 sums the samples in order
-        for (unsigned mask = ent.y; mask; mask &= mask - 1u) {
+        for (unsigned mask = WAVE ? 1u << ent.y : ent.y; mask; mask &= mask - 1u) {
             const unsigned sm = A.sample0 + (unsigned)(__ffs(mask) - 1);
             Ray64 R, S;
             primary_ray_fast(A, x, y, pixel, sm, R);
@@ -837,10 +1132,15 @@ trace_kernel_referee(const __grid_constant__ RenderArgs A) {
             if (!occluded) { acc.x += lit.x; acc.y += lit.y; acc.z += lit.z; }
         }
         if (lane == 0) {
-            float4* ap = A.accum + (size_t)y * A.width + x;     // the filtered kernel has counted the samples
-            float4 old = *ap;
-            old.x += acc.x; old.y += acc.y; old.z += acc.z;
-            *ap = old;
+            if (WAVE) {
+                float* slot = A.rad + ((size_t)(ent.x - A.wave_p0) * A.nsamples + ent.y) * 3;
+                slot[0] = acc.x; slot[1] = acc.y; slot[2] = acc.z;
+            } else {
+                float4* ap = A.accum + (size_t)y * A.width + x; // the filtered kernel has counted the samples
+                float4 old = *ap;
+                old.x += acc.x; old.y += acc.y; old.z += acc.z;
+                *ap = old;
+            }
         }
     }
     __syncwarp();
@@ -882,6 +1182,18 @@ static void to_body(const SceneParams& sp, const double* v, double* out) {
     out[2] = sp.ez[0] * v[0] + sp.ez[1] * v[1] + sp.ez[2] * v[2];
 }
 
+// scratch of the wavefront pipeline: one allocation, carved into the per-item arrays
+static int ensure_wave_buffers(mrtx_ctx* ctx, size_t items) {
+    if (ctx->wave_items >= items) return MRTX_OK;
+    MRTX_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->wave_buf);
+    ctx->wave_buf = nullptr; ctx->wave_items = 0;
+    const size_t per_item = 2 * sizeof(RayRec) + sizeof(HitRec) + sizeof(uint2) + 3 * sizeof(float) + sizeof(unsigned);
+    MRTX_CUDA(cudaMalloc(&ctx->wave_buf, items * per_item));
+    ctx->wave_items = items;
+    return MRTX_OK;
+}
+
 int launch_trace(mrtx_ctx* ctx, int x0, int y0, int x1, int y1, unsigned s0, unsigned ns) {
     RenderArgs A;
     A.hf = ctx->hf; A.tex = ctx->tex[0]; A.cam = ctx->cam; A.sp = ctx->sp;
@@ -898,13 +1210,15 @@ int launch_trace(mrtx_ctx* ctx, int x0, int y0, int x1, int y1, unsigned s0, uns
     to_body(A.sp, er, A.eye_b);
     to_body(A.sp, lr, A.light_b);
     A.defer_list = ctx->defer_list;
+    A.rad = nullptr; A.rays = nullptr; A.hits = nullptr; A.srays = nullptr; A.sitem = nullptr; A.defer_items = nullptr;
+    A.wave_p0 = 0; A.wave_np = 0; A.lvl_primary = 0; A.lvl_shadow = 0;
     A.defer_stats = ctx->d_defer_stats;
     A.K = make_fast_consts(ctx->hf, ctx->sp.radius);
     A.inv_rs = 1.0f / ctx->hf.radius_scale;
     A.g_log2 = 0;
     const bool i16 = ctx->hf.is_i16 != 0;
     unsigned kernel = ctx->sp.kernel;
-    if (kernel == 2 && !A.K.enabled) kernel = 1;             // map too coarse for the filter: everything would defer
+    if (kernel >= 2 && !A.K.enabled) kernel = 1;             // map too coarse for the filter: everything would defer
     if (kernel == 0) {
         const dim3 block(8, 16);
         const dim3 grid((x1 - x0 + block.x - 1) / block.x, (y1 - y0 + block.y - 1) / block.y);
@@ -921,7 +1235,63 @@ int launch_trace(mrtx_ctx* ctx, int x0, int y0, int x1, int y1, unsigned s0, uns
         cull_kernel<<<(total + 255u) / 256u, 256, 0, ctx->stream>>>(A);
     }
     const long long npix = (long long)(x1 - x0) * (y1 - y0);
-    if (kernel == 1) {
+    if (kernel == 3) {
+        // wavefront pipeline: sample chunks of <= 32, waves of <= WAVE_ITEMS items (bounded scratch memory)
+        const size_t WAVE_ITEMS = (size_t)1 << 25;
+        int rc = ensure_wave_buffers(ctx, WAVE_ITEMS);
+        if (rc) return rc;
+        {
+            char* q = (char*)ctx->wave_buf;                              // largest alignment first
+            A.rays = (RayRec*)q; q += WAVE_ITEMS * sizeof(RayRec);
+            A.srays = (RayRec*)q; q += WAVE_ITEMS * sizeof(RayRec);
+            A.hits = (HitRec*)q; q += WAVE_ITEMS * sizeof(HitRec);
+            A.defer_items = (uint2*)q; q += WAVE_ITEMS * sizeof(uint2);
+            A.rad = (float*)q; q += WAVE_ITEMS * 3 * sizeof(float);
+            A.sitem = (unsigned*)q;
+        }
+        // the first cell travels in 16 + 16 bits: start no lower than the level whose grid fits
+        int lvl_min = 0;
+        while ((ctx->hf.W >> lvl_min) > 65536 && lvl_min < ctx->hf.top) ++lvl_min;
+        const int top = ctx->hf.top;
+        A.lvl_primary = std::min(std::max(top - (int)A.sp.start_primary, lvl_min), top);
+        A.lvl_shadow = std::min(std::max((int)A.sp.start_shadow, lvl_min), top);
+        void (*k_primary)(const RenderArgs) = i16 ? trace_kernel_walk<true, false> : trace_kernel_walk<false, false>;
+        void (*k_shadow)(const RenderArgs) = i16 ? trace_kernel_walk<true, true> : trace_kernel_walk<false, true>;
+        void (*k_shade)(const RenderArgs) = i16 ? shade_kernel<true> : shade_kernel<false>;
+        void (*k_referee)(const RenderArgs) = i16 ? trace_kernel_referee<true, true> : trace_kernel_referee<false, true>;
+        int per_sm = 0, per_sm_s = 0;
+        MRTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_primary, 128, 0));
+        MRTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_s, k_shadow, 128, 0));
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm_s < 1) per_sm_s = 1;
+        for (unsigned done = 0; done < ns; done += 32u) {
+            const unsigned n = ns - done < 32u ? ns - done : 32u;
+            A.sample0 = s0 + done; A.nsamples = n;
+            const unsigned wave_np = (unsigned)(WAVE_ITEMS / n);
+            for (long long p0 = 0; p0 < npix; p0 += wave_np) {          // waves past the end of the list return at once
+                A.wave_p0 = (unsigned)p0; A.wave_np = wave_np;
+                MRTX_CUDA(cudaMemsetAsync(A.work_counter + 2, 0, 2 * sizeof(unsigned), ctx->stream));
+                MRTX_CUDA(cudaMemsetAsync(A.work_counter + 5, 0, 2 * sizeof(unsigned), ctx->stream));
+                const long long items = (npix - p0 < (long long)wave_np ? npix - p0 : (long long)wave_np) * n;
+                const long long warps_needed = (items + 31) / 32;
+                long long blocks = (long long)ctx->sm_count * per_sm, sblocks = (long long)ctx->sm_count * per_sm_s;
+                if (blocks * 4 > warps_needed) blocks = (warps_needed + 3) / 4;
+                if (sblocks * 4 > warps_needed) sblocks = (warps_needed + 3) / 4;
+                if (blocks < 1) blocks = 1;
+                if (sblocks < 1) sblocks = 1;
+                const long long dense_cap = (long long)ctx->sm_count * 16;
+                long long gblocks = std::min((items + 255) / 256, dense_cap), hblocks = std::min((items + 127) / 128, dense_cap * 2);
+                long long rblocks = std::min((items / n + 255) / 256, dense_cap);
+                gblocks = std::max(gblocks, 1ll); hblocks = std::max(hblocks, 1ll); rblocks = std::max(rblocks, 1ll);
+                gen_kernel<<<(unsigned)gblocks, 256, 0, ctx->stream>>>(A);
+                k_primary<<<(unsigned)blocks, 128, 0, ctx->stream>>>(A);
+                k_shade<<<(unsigned)hblocks, 128, 0, ctx->stream>>>(A);
+                k_shadow<<<(unsigned)sblocks, 128, 0, ctx->stream>>>(A);
+                k_referee<<<ctx->sm_count * 8, 64, 0, ctx->stream>>>(A);
+                reduce_kernel<<<(unsigned)rblocks, 256, 0, ctx->stream>>>(A);
+            }
+        }
+    } else if (kernel == 1) {
         int per_sm = 0;
         if (i16) MRTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel_persistent<true>, 128, 0));
         else     MRTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel_persistent<false>, 128, 0));
@@ -952,8 +1322,8 @@ int launch_trace(mrtx_ctx* ctx, int x0, int y0, int x1, int y1, unsigned s0, uns
             if (blocks < 1) blocks = 1;
             if (i16) trace_kernel_fast<true><<<(unsigned)blocks, 128, 0, ctx->stream>>>(A);
             else     trace_kernel_fast<false><<<(unsigned)blocks, 128, 0, ctx->stream>>>(A);
-            if (i16) trace_kernel_referee<true><<<ctx->sm_count * 8, 64, 0, ctx->stream>>>(A);
-            else     trace_kernel_referee<false><<<ctx->sm_count * 8, 64, 0, ctx->stream>>>(A);
+            if (i16) trace_kernel_referee<true, false><<<ctx->sm_count * 8, 64, 0, ctx->stream>>>(A);
+            else     trace_kernel_referee<false, false><<<ctx->sm_count * 8, 64, 0, ctx->stream>>>(A);
         }
     }
     MRTX_CUDA(cudaGetLastError());

@@ -338,22 +338,35 @@ struct Walk {
 
 MRTX_HD inline float walk_r2(const Walk& w, float s) { return fmaf(s, fmaf(2.0f, w.od, s), w.oo); }
 
-MRTX_HD inline bool walk_begin(const HeightField& hf, double radius, const Ray64& R, double s_min, int start_level, Walk& w) {
-    const double Rb = radius * (double)hf.dmax;
-    const double disc = R.od * R.od - (R.oo - Rb * Rb);
-    if (!(disc > 0.0)) return false;
-    const double sq = disc * d_rsqrt(disc);
-    const double s_end = -R.od + sq;
-    if (s_end <= s_min) return false;
-    const double s_in = fmax(s_min, -R.od - sq);
+// float32 constants of the walk for the ray re-based at s_in (the same arithmetic whoever calls it: a walk that is
+// suspended and resumed from (s_in, s, L, J, I) continues exactly as it would have)
+MRTX_HD inline void walk_setup(const Ray64& R, double s_in, float smax, Walk& w) {
     w.s_in = s_in;
     w.ox = (float)fma(s_in, R.dx, R.ox); w.oy = (float)fma(s_in, R.dy, R.oy); w.oz = (float)fma(s_in, R.dz, R.oz);
     w.dx = (float)R.dx; w.dy = (float)R.dy; w.dz = (float)R.dz;
     w.oo = w.ox * w.ox + w.oy * w.oy + w.oz * w.oz;
     w.od = w.ox * w.dx + w.oy * w.dy + w.oz * w.dz;
-    w.smax = (float)(s_end - s_in);
+    w.smax = smax;
     w.east = w.ox * w.dy - w.oy * w.dx > 0.0f;
     w.n0 = w.dz * w.oo - w.oz * w.od; w.n1 = w.dz * w.od - w.oz;
+}
+
+// where the ray leaves the bounding sphere R * dmax (s_end) - false if it misses it
+MRTX_HD inline bool walk_extent(const HeightField& hf, double radius, const Ray64& R, double& s_first, double& s_end) {
+    const double Rb = radius * (double)hf.dmax;
+    const double disc = R.od * R.od - (R.oo - Rb * Rb);
+    if (!(disc > 0.0)) return false;
+    const double sq = disc * d_rsqrt(disc);
+    s_first = -R.od - sq; s_end = -R.od + sq;
+    return true;
+}
+
+MRTX_HD inline bool walk_begin(const HeightField& hf, double radius, const Ray64& R, double s_min, int start_level, Walk& w) {
+    double s_first, s_end;
+    if (!walk_extent(hf, radius, R, s_first, s_end)) return false;
+    if (s_end <= s_min) return false;
+    const double s_in = fmax(s_min, s_first);
+    walk_setup(R, s_in, (float)(s_end - s_in), w);
     const int W = hf.W, H = hf.H;
     const int L = min(max(start_level, 0), hf.top);
     // first cell from the position just inside (a wrong neighbour is corrected by the on-wall rule)
@@ -431,6 +444,12 @@ MRTX_HD inline int walk_step(const HeightField& hf, float Rf, float inv_rs, Walk
     const int W = hf.W, H = hf.H;
     const float s = w.s;
     ++cnt.nodes;
+    // The walls ahead depend on (L, J, I) and the ray's headings only: their table entries are requested here,
+    // together with the node itself, so that one memory latency covers all three (the loop is latency-bound).
+    const bool north = fmaf(s, w.n1, w.n0) > 0.0f;
+    const int jn = J << L, js = min((J + 1) << L, H - 1);
+    const float2 wl = MRTX_LDG(hf.lon32 + (w.east ? min((I + 1) << L, W) : (I << L)));
+    const float2 kk = MRTX_LDG(hf.latsc32 + (north ? jn : js));
     float vmax;
     if (L == 0) {
         const int c1 = I + 1 == W ? 0 : I + 1;
@@ -465,8 +484,6 @@ MRTX_HD inline int walk_step(const HeightField& hf, float Rf, float inv_rs, Walk
         float sx = w.smax;
         int face = 4;
         {   // the longitude wall ahead
-            const int wi = w.east ? min((I + 1) << L, W) : (I << L);
-            const float2 wl = MRTX_LDG(hf.lon32 + wi);
             const float sg = w.east ? 1.0f : -1.0f;
             const float g = sg * fmaf(x, wl.x, y * wl.y), dg = sg * fmaf(w.dx, wl.x, w.dy * wl.y);      // outwards positive
             const float tol = fmaf(6.0e-7f, fabsf(x * wl.x) + fabsf(y * wl.y), tol0);
@@ -480,14 +497,11 @@ MRTX_HD inline int walk_step(const HeightField& hf, float Rf, float inv_rs, Walk
             }
         }
         if (sx > s) {   // the latitude wall ahead
-            const bool north = fmaf(s, w.n1, w.n0) > 0.0f;
             float s_turn = INFINITY;                            // where the heading reverses, if that is still ahead
             if (w.n1 != 0.0f) { const float t = -w.n0 * f_rcp_fast(w.n1); if (t > s) s_turn = t; }
-            const int jn = J << L, js = min((J + 1) << L, H - 1);
             float sl = INFINITY;
             int fl = north ? 1 : 2;
             if (north ? jn > 0 : js < H - 1) {                  // polar caps have no wall
-                const float2 kk = MRTX_LDG(hf.latsc32 + (north ? jn : js));
                 const float side = lat_side(kk, z, f_sqrt_fast(fmaf(x, x, y * y)), rs);
                 const float G = north ? side : -side;                   // outwards positive
                 const float tol = fmaf(6.0e-7f * rs, fminf(fabsf(kk.x), kk.y), tol0);

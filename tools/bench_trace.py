@@ -3,6 +3,8 @@ import sys, os, json, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from moonrtx_b200 import _lib
+if os.environ.get("MRTX_LIB"):
+    _lib.LIB_PATH = os.environ["MRTX_LIB"]          # tuning variants (tools/build_variant.py)
 from moonrtx_b200.device import Device
 from moonrtx_b200.optix import B200OptiX
 from moonrtx_b200.data_loader import downscale_elevation_dev
