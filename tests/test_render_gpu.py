@@ -303,6 +303,36 @@ def test_filtered_kernel_against_exact_kernel_and_defer_stats():
     assert d.mean() <= 0.01 and int((d.max(axis=2) > 1).sum()) <= 4
 
 
+@pytest.mark.parametrize("spp", [1, 6, 40])
+def test_wavefront_pipeline_equals_filtered_kernel(spp):
+    """Kernel 3 (dense ray generation / streaming walk / dense shading over ray records) traces the same samples with
+    the same arithmetic as kernel 2: same rays, same decisions, same deferrals; the per-pixel sum is taken in sample
+    order instead of lane order, so accumulators agree to float32 rounding."""
+    elev, _ = synth_elevation(2880, 1440, seed=12)
+    kw = dict(light_pos=sun_at_phase(88.0))
+    outs = {}
+    for kernel in (2, 3):
+        rt = make_gpu(elev, 320, 240, debug_hits=(spp == 1), **kw)
+        rt.set_uint("kernel", kernel)
+        if spp > 1:
+            rt.set_param(max_accumulation_frames=spp, min_accumulation_step=spp)
+        rt.counters(reset=True); rt.defer_stats(reset=True)
+        img = rt.render_cycle().copy()
+        outs[kernel] = (img, rt.get_accum_buffer().copy(), rt.counters(), rt.defer_stats(),
+                        rt.get_hit_records_f64().copy() if spp == 1 else None)
+        rt.close()
+    (ia, aa, ca, da, ha), (ib, ab, cb, db, hb) = outs[2], outs[3]
+    for k in ("primary_rays", "primary_in_sphere", "primary_hits", "shadow_rays", "shadow_occluded", "node_visits", "patch_tests"):
+        assert ca[k] == cb[k], (k, ca[k], cb[k])
+    assert da == db
+    assert np.array_equal(aa[..., 3], ab[..., 3]) and np.all(ab[..., 3] == float(spp))
+    assert np.allclose(aa[..., :3], ab[..., :3], rtol=2e-6, atol=1e-6)
+    d = np.abs(ia[..., :3].astype(np.int32) - ib[..., :3].astype(np.int32))
+    assert int(d.max()) <= 1 and int((d.max(axis=2) > 0).sum()) <= 4
+    if spp == 1:
+        assert np.array_equal(ha, hb)
+
+
 def test_more_than_32_samples_are_chunked():
     """The filtered kernel takes <= 32 samples per launch (one mask bit each in the deferred list): 40 spp must
     equal 32 + 8 spp accumulated in two calls, and match the oracle."""
