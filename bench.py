@@ -59,18 +59,22 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.
+
+    nvidia-smi takes a while to come up (seconds on an 8-GPU box) and its start-up stalls CUDA calls of the
+    processes it attaches to, so ONE sampler (rank 0, all visible GPUs) is started before the warm-up steps;
+    only the rows that arrive between begin() and end() are used."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
-
-    def start(self):
+    def __init__(self, enabled=True, gpus=(0,), period_ms=50):
+        self.rows, self.proc, self.t0, self.t1 = [], None, None, None
+        if not enabled:
+            return
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", ",".join(str(g) for g in gpus), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits",
+                                          "-lms", str(period_ms)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -78,11 +82,22 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def wait_ready(self, timeout=20.0):
+        t = time.time()
+        while self.proc and not self.rows and time.time() - t < timeout:
+            time.sleep(0.05)
+
+    def begin(self):
+        self.t0 = time.time()
+
+    def end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return None
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -90,18 +105,19 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for r in self.rows:
-            if len(r) < 6:
+        for ts, r in self.rows:
+            if len(r) < 6 or self.t0 is None or not (self.t0 <= ts <= (self.t1 or ts) + 0.05):
                 continue
             try:
-                sm.append(float(r[0])); mx = float(r[1])
+                sm.append(float(r[0])); mx = max(mx or 0.0, float(r[1]))
             except ValueError:
                 continue
             for n, v in zip(names, r[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no nvidia-smi sample inside the timed region"], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
 def dist_env():
@@ -195,6 +211,7 @@ def overlay_image(h, w, text_seed):
 def run_ours(args):
     rank, world, local = dist_env()
     if world > 1:
+        os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"      # NCCL logs to stdout by default, which carries exactly one JSON line
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)
@@ -244,18 +261,20 @@ def run_ours(args):
         _lib.check(lib.mrtx_resolve(ctx))
 
     # ---- device-resident throughput (value) -------------------------------------------------
+    clocks = ClockSampler(enabled=rank == 0, gpus=range(world))
+    clocks.wait_ready()
     for j in range(args.warmup):
         device_step(states[j])
     rt.counters(reset=True)
     rt.defer_stats(reset=True)
     barrier()
-    clocks = ClockSampler(local)
-    clocks.start()
+    clocks.begin()
     dev.timer_start()
     for j in range(args.warmup, total):
         device_step(states[j])
     ms_total = dev.timer_stop()
     barrier()
+    clocks.end()
     clock_info = clocks.stop()
     c = rt.counters()
     # cull_kernel + trace_kernel_fast + trace_kernel_referee + resolve_kernel per frame (<= 32 spp: one sample chunk)
