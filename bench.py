@@ -40,6 +40,9 @@ COLOR_K = 4
 SEED = 20240314
 FRAME_STEP_MIN = 10.0            # config 4: 10-minute steps through the terminator sweep
 FALLBACK_HBM_GBS = 6650.0        # /opt/skills/guides/B200_PROFILING.md fallback
+# profiles/r03_trace_kernel_fast_raw.csv (ncu --set full, default workload): 5.489 GB read + 5.908 GB written per launch
+# (the writes are register spill slots evicted from L2); only meaningful for the default workload
+NCU_TRAFFIC_BYTES = 5.489479e9 + 5.908359e9
 
 
 def quadtree_depth(W):
@@ -224,7 +227,7 @@ def run_ours(args):
     dev = rt._dev
     lib, ctx = dev.lib, dev.ctx
     total = args.warmup + args.steps
-    states = frame_states(total, rank, world, total)
+    states = frame_states(total, rank * args.frame_stride // max(world, 1) if args.frame_stride else rank, args.frame_stride or world, total)
     t_setup = time.time() - t_setup
 
     def barrier():
@@ -303,7 +306,8 @@ def run_ours(args):
     peak, peak_src = measured_peak()
     achieved = algo_bytes / (k_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "cull_kernel + trace_kernel_fast<int16> + trace_kernel_referee<int16> (one mrtx_render)", "achieved": round(achieved, 2), "peak": peak,
-                "unit": "GB/s", "frac": round(achieved / peak, 5), "traffic": args.traffic,
+                "unit": "GB/s", "frac": round(achieved / peak, 5),
+                "traffic": args.traffic if (args.map_w, args.img_w, args.spp) == (MAP_W, IMG_W, 16) else None,
                 "algorithmic_bytes_per_launch": int(algo_bytes), "bytes_per_ray": b_floor,
                 "rays_in_sphere_per_launch": int(rays_in), "kernel_ms": round(k_ms, 3), "peak_source": peak_src,
                 "kernel_share_of_step": round(k_ms * args.steps / ms_total, 4) if world == 1 else None}
@@ -457,7 +461,9 @@ def main():
     ap.add_argument("--color-h", type=int, default=COLOR_H)
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
-    ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch from the ncu capture (profiles/)")
+    ap.add_argument("--frame-stride", type=int, default=0, help="development: frame index step between steps (default: world size)")
+    ap.add_argument("--traffic", type=float, default=NCU_TRAFFIC_BYTES,
+                    help="dram__bytes_read.sum + dram__bytes_write.sum of trace_kernel_fast per launch, from the ncu capture in profiles/")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -534,7 +534,8 @@ __device__ __forceinline__ bool shade_fast(const RenderArgs& A, const Ray64& R, 
     const float fx = (float)px, fy = (float)py, fz = (float)pz;
     // normal of r(lon, lat) = R * D: n ~ e_r - (r_lon / (r cos lat)) e_lon - (r_lat / r) e_lat
     const float dD_dfc = fmaf(h.fr, (h.d11 - h.d10) - (h.d01 - h.d00), h.d01 - h.d00);
-    const float dD_dfr = fmaf(h.fc, (h.d11 - h.d01) - (h.d10 - h.d00), h.d10 - h.d00);
+    float dD_dfr = fmaf(h.fc, (h.d11 - h.d01) - (h.d10 - h.d00), h.d10 - h.d00);
+    if ((h.r0 == 0 && h.fr <= 0.0f) || (h.r0 == A.hf.H - 2 && h.fr >= 1.0f)) dD_dfr = 0.0f;      // polar cap: the rows clamp
     const float Rf = A.K.R;
     const float r_lon = Rf * dD_dfc * A.K.Kw, r_lat = -Rf * dD_dfr * A.K.Kh;
     const float rho2 = fmaf(fx, fx, fy * fy);
@@ -1040,9 +1041,16 @@ __device__ bool trace_referee(const RenderArgs& A, const Ray64& R, double s_lo, 
         if (r == TR_END) return false;
         if (r == TR_CANDIDATE) {
             ++cnt.tests;
-            const int t = fast_test<I16>(A.hf, A.K, R, w.s_in, s_lo, w.s, sx, w.smax, P, any_hit, fh) & 3;
+            const int tr = fast_test<I16>(A.hf, A.K, R, w.s_in, s_lo, w.s, sx, w.smax, P, any_hit, fh);
+            const int t = tr & 3;
             if (t == FT_HIT) { fast = true; return true; }
             if (t == FT_DEFER) {
+#ifdef MRTX_REFEREE_TIMING
+                {   // development: why the referee runs float64 tests -> counters[8..15] (read as the kernel-1 phase statistics)
+                    const int rr = tr >> 2;
+                    atomicAdd(&A.counters[rr == 1 ? 8 : rr == 2 ? 9 : rr == 3 ? 10 : rr == 7 ? 11 : rr == 8 ? 12 : rr == 9 ? 13 : rr == 12 ? 14 : 15], 1ull);
+                }
+#endif
                 TravState st;
                 st.s_in = w.s_in; st.s_min = s_lo; st.s_end = w.s_in + (double)w.smax; st.s = w.s;
                 Patch Pd;

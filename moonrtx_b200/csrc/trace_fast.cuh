@@ -107,6 +107,8 @@ struct LocalRay {
     float nk, nc;                       // sin, cos of the north row's latitude
     float Rc0;                          // R * D00: radius of the corner sphere
     float e01, e10, exx;                // R * (D01-D00), R * (D10-D00), R * (D11-D10-D01+D00)
+    float fr_lo, fr_hi;                 // polar-cap rows: the rows clamp (renderer_navigation.py:581-587), D does not depend
+                                        // on latitude beyond the last texel centre; elsewhere -inf, +inf
 };
 
 MRTX_HD inline float local_f(const LocalRay& Q, const FastConsts& K, float t, float& fc, float& fr) {
@@ -118,6 +120,7 @@ MRTX_HD inline float local_f(const LocalRay& Q, const FastConsts& K, float t, fl
     const float u = 0.5f * a * q * fmaf(-0.25f, q2, 1.0f);      // rho - hh = a^2 / (rho + hh)
     const float v = fmaf(-Q.nk, u, b) * f_rcp(fmaf(Q.nc, u, Rc)), v2 = v * v;
     fr = -K.Kh * v * fmaf(v2, fmaf(v2, 0.2f, -0.33333334f), 1.0f);          // -atan(v) * H / pi
+    fr = fminf(fmaxf(fr, Q.fr_lo), Q.fr_hi);
     const float rr2 = fmaf(a, a, b * b);
     const float r = f_sqrt_fast(fmaf(Rc, Rc, rr2));
     const float hr = fmaf(rr2, f_rcp(r + Rc), c);               // |p| - R*D00
@@ -159,7 +162,12 @@ MRTX_HD inline int fast_test(const HeightField& hf, const FastConsts& K, const R
     bool from_entry = false;                                    // search from the cell's own entry, not from where the walk stands
 #pragma unroll 1
     for (int back = 0; ; ++back) {
-        if (P.r0 <= 0 || P.r0 >= hf.H - 2) return FT_DEFER_R(1);               // polar caps: rows clamp, no wall
+        // Polar-cap rows (r0 = 0, H - 2): the cell runs on to the pole, with the row coordinate clamped at the last
+        // texel centre and no wall on that side.  Its longitude walls still are planes through the axis and its
+        // latitude offsets still are small angles, so the local frame holds; only next to the axis itself
+        // (a / hh -> 0 / 0) it does not, and that is deferred below.
+        if (P.r0 < 0 || P.r0 > hf.H - 2) return FT_DEFER_R(1);
+        const bool cap_n = P.r0 == 0, cap_s = P.r0 == hf.H - 2;
         const float d00 = decode_exact<I16>(hf, P.v00), d01 = decode_exact<I16>(hf, P.v01);
         const float d10 = decode_exact<I16>(hf, P.v10), d11 = decode_exact<I16>(hf, P.v11);
         const double2 w = MRTX_LDG(hf.lon64 + P.c0), n = MRTX_LDG(hf.lat64 + P.r0);   // (cos, sin) lon_w; (sin, cos) lat_n
@@ -175,6 +183,7 @@ MRTX_HD inline int fast_test(const HeightField& hf, const FastConsts& K, const R
             Q.nk = (float)n.x; Q.nc = (float)n.y; Q.Rc0 = (float)Rc0;
         }
         Q.e01 = K.R * (d01 - d00); Q.e10 = K.R * (d10 - d00); Q.exx = K.R * ((d11 - d10) - (d01 - d00));
+        Q.fr_lo = cap_n ? 0.0f : -INFINITY; Q.fr_hi = cap_s ? 1.0f : INFINITY;
 
         // the ray inside the cell: four walls (west, east, north, south), each g(t) = g0 + t g1 >= 0 inside
         float t_in = -INFINITY, t_out = INFINITY;
@@ -189,6 +198,7 @@ MRTX_HD inline int fast_test(const HeightField& hf, const FastConsts& K, const R
             const float g1[4] = {Q.da, fmaf(dhh, K.sD, -Q.da * K.cD), -Q.db, fmaf(Q.dc, K.tD, Q.db)};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
+                if ((i == 2 && cap_n) || (i == 3 && cap_s)) continue;            // no wall towards the pole
                 const float tc = -g0[i] * f_rcp(g1[i]);
                 if (g1[i] > 0.0f) { if (tc > t_in) { t_in = tc; wall_in = i; } }
                 else if (g1[i] < 0.0f) t_out = fminf(t_out, tc);
@@ -200,6 +210,12 @@ MRTX_HD inline int fast_test(const HeightField& hf, const FastConsts& K, const R
         const float t_walk = from_entry ? -INFINITY : -K.pad;
         const float ta = fmaxf(fmaxf(t_walk, t_in - dl), t_lo), tb = fminf(fminf(t_out + dl, t_hi), t_cap);
         if (!(tb > ta)) return back ? FT_DEFER_R(14) : FT_MISS;  // the ray does not cross this cell (walk tolerance)
+        if (cap_n || cap_s) {
+            // distance from the polar axis is linear in t: its minimum over the interval is at an end
+            const float Rc = Q.Rc0 + Q.c0;
+            const float hh0 = fmaf(Q.nc, Rc, -Q.nk * Q.b0), dhh = fmaf(Q.nc, Q.dc, -Q.nk * Q.db);
+            if (!(fminf(fmaf(ta, dhh, hh0), fmaf(tb, dhh, hh0)) > 1.0e-3f * K.cell)) return FT_DEFER_R(1);
+        }
         float fc, fr;
         // start of the window: the ray must be clear of the surface there
         const float fa = local_f(Q, K, ta, fc, fr);

@@ -144,6 +144,30 @@ def test_polar_view():
     rt.close()
 
 
+@pytest.mark.parametrize("pole", [+1, -1])
+def test_polar_cap_rows_close_up(pole):
+    """Close-up of a pole with the sun on the horizon: most pixels land in the polar-cap rows (the cells that run on
+    to the pole with the row coordinate clamped and no wall on that side) and every shadow ray grazes over them.  The
+    filtered kernel decides those cells itself (they used to be handed to the float64 referee one by one - a ray over
+    the pole crosses thousands of them); the result must match the oracle like anywhere else."""
+    elev, _ = synth_elevation(720, 360, seed=6)
+    z = 12.0 * pole
+    kw = dict(eye=(0.0, 0.0, z), target=(0.0, 0.0, 0.0), up=(0.0, 1.0, 0.0), fov=8.0,
+              light_pos=(21460.0 * math.cos(0.02), 0.0, pole * 21460.0 * math.sin(0.02)))
+    rt = make_gpu(elev, 96, 96, **kw)
+    orc = make_oracle(elev, 96, 96, **kw)
+    rt.defer_stats(reset=True)
+    m = compare(rt, orc, allow_mismatch=3)
+    lat = m["oracle"]["hit64"][..., 3]
+    hit = m["oracle"]["hit64"][..., 0] > 0
+    cap = hit & (np.abs(lat) > math.radians(90.0 - 1.5 * 180.0 / 360))
+    assert int(cap.sum()) > 500, int(cap.sum())                 # the view is inside the cap rows
+    d = rt.defer_stats()
+    assert d["deferred_samples"] <= 0.02 * 96 * 96, d
+    assert rt.counters()["overflow"] == 0
+    rt.close()
+
+
 def test_config2_1080p_ds16_terminator():
     """BASELINE config 2: 1920x1080, 5760x2880 float32 map (a LOLA-shaped synthetic map block-meaned on the
     GPU), sun on the terminator, 1 spp primary + shadow; oracle on every 12th pixel."""

@@ -76,6 +76,11 @@ if __name__ == "__main__":
         rt, info = setup(23040, 11520, 1920, 1080, ds=4)
     elif which == "cfg3":
         rt, info = setup(92160, 46080, 3840, 2160, ds=1)
+    elif which == "cfg5":
+        # BASELINE config 5: 8K narrow-FOV view of the terminator at the disk centre (fov 2.5 deg)
+        rt, info = setup(92160, 46080, 7680, 4320, ds=1)
+        cam = rt.get_camera("cam1")
+        rt.update_camera("cam1", eye=cam["Eye"], target=cam["Target"], up=cam["Up"], fov=2.5)
     elif which == "cfg1k":
         rt, info = setup(23040, 11520, 3840, 2160, ds=1)
     print(json.dumps(info))
