@@ -160,10 +160,12 @@ int  mrtx_read_hit_f64(mrtx_ctx* ctx, double* out);
  * [11] lanes in them, [12] ray-start phases, [13] lanes in them, [14] refills, [15] pixels culled */
 int  mrtx_counters(mrtx_ctx* ctx, uint64_t out[16], int reset);
 /* the filtered kernel's deferrals since the last reset: [0] samples handed to the exact kernel;
- * [r] / [16 + r] primary / shadow rays deferred for reason r: 1 polar-cap row or map too coarse,
- * 2 ray enters the cell below the surface, 3-4 window start on the surface, 5-6 middle / end of the
- * window on the surface, 7 grazing double root, 8-9 root search left its bracket, 10 ill-conditioned
- * root, 11 residual too large, 12-13 root before the cell's longitude / latitude range            */
+ * [r] / [16 + r] primary / shadow rays deferred for reason r: 1 next to the polar axis or map too
+ * coarse, 2 ray enters the cell below the surface, 3-4 window start on the surface, 5-6 middle / end
+ * of the window on the surface, 7 grazing double root, 8-9 root search left its bracket, 10
+ * ill-conditioned root, 11 residual too large, 12-13 root before the cell's longitude / latitude
+ * range, 14 walk-back found no crossing, 15 walk longer than 2048 nodes (the referee's warp walks such
+ * a ray in pieces, side by side)                                                                  */
 int  mrtx_defer_stats(mrtx_ctx* ctx, uint64_t out[32], int reset);
 
 /* ---- multi-GPU (one process per GPU) ----------------------------------------------

@@ -673,6 +673,10 @@ trace_kernel_fast(const __grid_constant__ RenderArgs A) {
                         }
                     }
                     __syncwarp();
+                    if ((alive || cand) && st.steps > LONG_WALK) {
+                        res = FT_DEFER; alive = false; cand = false;
+                        atomicAdd(&A.defer_stats[15 + (pass ? 16 : 0)], 1ull);
+                    }
                     if (cand) {
                         ++cnt.tests;
                         const int t = fast_test<I16>(A.hf, A.K, R, st.s_in, 0.0, st.s, sx, st.smax, P, pass != 0, fh);
@@ -883,8 +887,9 @@ trace_kernel_walk(const __grid_constant__ RenderArgs A) {
         } else if (mode == LM_WALK) {
             // ---- walk step -------------------------------------------------------------------------------------
             const int r = walk_step<I16>(A.hf, Rf, A.inv_rs, st, P, sx, face, cnt);
-            if (r == TR_CANDIDATE) mode = LM_CAND;
-            else if (r == TR_END) finished = true;
+            if (r == TR_END) finished = true;
+            else if (st.steps > LONG_WALK) { finished = true; status = FT_DEFER_R(15); }
+            else if (r == TR_CANDIDATE) mode = LM_CAND;
         }
         if (finished) {
             mode = LM_EMPTY;
@@ -1018,54 +1023,71 @@ reduce_kernel(const __grid_constant__ RenderArgs A) {
 // One WARP per deferred sample.  The sample is traced again from the start with the float32 walk and the
 // filter; only where the filter says FT_DEFER does the float64 exact test of trace_core.cuh (exact in-cell
 // pieces, walk-back through the neighbours) decide that patch.
-// Deferred rays are the long grazing ones - over a pole a ray crosses tens of thousands of sliver cells, one
-// dependent fetch after the other - and there are only a few of them, so a single lane per ray would leave the
-// whole kernel waiting for the longest walk.  The ray's path through the shell is therefore cut into
-// REFEREE_SEGMENTS pieces that lanes walk independently (32 at a time, nearest first); the first hit is the hit of
-// the nearest piece that has one.  (A piece that starts below the surface reports a hit at its start, which can
-// only lose against the true crossing in an earlier piece.)
-constexpr int REFEREE_SEGMENTS = 128;
+// Deferred rays are the long grazing ones and there are only a few thousand of them, so what the launch takes is
+// the longest serial chain in it.  The ray's path through the shell is therefore cut into pieces that lanes walk
+// independently, 32 at a time, nearest first; the first hit is the hit of the nearest piece that has one.  (A piece
+// that starts below the surface reports a hit at its start, which can only lose against the true crossing in an
+// earlier piece.)
+// Equal pieces are not equal work.  A sun ray at the horizon stays within the walk's 5 m margin of level ground for
+// 4 km, and next to a pole those 4 km are tens of thousands of cells 10 cm wide: measured, ONE piece of ONE shadow
+// ray 1.5 km from the south pole held 22 145 nodes and 14 642 patch tests and the launch took 25 ms instead of 2.
+// A lane therefore walks a piece only as far as a budget lets it; what is left of the piece goes back on the warp's
+// stack of intervals and is cut into 32 again.
+constexpr int REFEREE_STACK = 96;           // pending intervals per warp
+#ifndef MRTX_REFEREE_BUDGET
+#define MRTX_REFEREE_BUDGET 1500
+#endif
+constexpr int REFEREE_BUDGET = MRTX_REFEREE_BUDGET;      // nodes + 3 * patch tests a lane spends on one piece
+struct RefIv { double a, b; int depth; int pad; };        // depth > 0: what a lane left of a piece
+enum { RS_CLEAR = 0, RS_HIT = 1, RS_MORE = 2 };
 
+__device__ __forceinline__ double shfl_d(double v, int src) {
+    return __hiloint2double(__shfl_sync(0xffffffffu, __double2hiint(v), src), __shfl_sync(0xffffffffu, __double2loint(v), src));
+}
+
+// One piece: the walk starts at s_lo (a little before the piece, where its first cell can be found safely); cells that
+// end before s_own belong to the piece before and are only walked, not tested.
 template <bool I16>
-__device__ bool trace_referee(const RenderArgs& A, const Ray64& R, double s_lo, double s_hi, int start_level, bool any_hit,
-                              bool& fast, FastHit& fh, TraceOut& h, Counters& cnt) {
+__device__ int trace_referee(const RenderArgs& A, const Ray64& R, double s_lo, double s_own, double s_hi, int start_level, float t0_rel,
+                             bool any_hit, int budget, double& s_stop, bool& fast, FastHit& fh, TraceOut& h, Counters& cnt) {
     Walk w;
-    if (!walk_begin(A.hf, A.sp.radius, R, s_lo, start_level, w)) return false;
+    if (!walk_begin(A.hf, A.sp.radius, R, s_lo, start_level, w, t0_rel)) return RS_CLEAR;
     w.smax = fminf(w.smax, (float)(s_hi - w.s_in));
-    if (!(w.smax > 0.0f)) return false;
+    if (!(w.smax > 0.0f)) return RS_CLEAR;
+    const float own_start = fmaxf((float)(s_own - w.s_in), 0.0f) + 1.0e-6f * A.K.R;
+    const float own_from = own_start - 1.1f * t0_rel * A.K.R;
+    int cost = 0;
     for (;;) {
         RawPatch P;
         float sx;
         int face;
         const int r = walk_step<I16>(A.hf, A.K.R, A.inv_rs, w, P, sx, face, cnt);
-        if (r == TR_END) return false;
+        if (r == TR_END) return RS_CLEAR;
         if (r == TR_CANDIDATE) {
-            ++cnt.tests;
-            const int tr = fast_test<I16>(A.hf, A.K, R, w.s_in, s_lo, w.s, sx, w.smax, P, any_hit, fh);
-            const int t = tr & 3;
-            if (t == FT_HIT) { fast = true; return true; }
-            if (t == FT_DEFER) {
-#ifdef MRTX_REFEREE_TIMING
-                {   // development: why the referee runs float64 tests -> counters[8..15] (read as the kernel-1 phase statistics)
-                    const int rr = tr >> 2;
-                    atomicAdd(&A.counters[rr == 1 ? 8 : rr == 2 ? 9 : rr == 3 ? 10 : rr == 7 ? 11 : rr == 8 ? 12 : rr == 9 ? 13 : rr == 12 ? 14 : 15], 1ull);
+            if (sx > own_from) {
+                cost += 3;
+                ++cnt.tests;
+                const int t = fast_test<I16>(A.hf, A.K, R, w.s_in, s_lo, w.s, sx, w.smax, P, any_hit, fh) & 3;
+                if (t == FT_HIT) { fast = true; return RS_HIT; }
+                if (t == FT_DEFER) {
+                    TravState st;
+                    st.s_in = w.s_in; st.s_min = s_lo; st.s_end = w.s_in + (double)w.smax; st.s = w.s;
+                    Patch Pd;
+                    load_patch<I16>(A.hf, P.r0, P.c0, Pd);
+                    if (exact_test<I16>(A.hf, A.sp.radius, R, st, Pd, sx, h, cnt)) { fast = false; return RS_HIT; }
                 }
-#endif
-                TravState st;
-                st.s_in = w.s_in; st.s_min = s_lo; st.s_end = w.s_in + (double)w.smax; st.s = w.s;
-                Patch Pd;
-                load_patch<I16>(A.hf, P.r0, P.c0, Pd);
-                if (exact_test<I16>(A.hf, A.sp.radius, R, st, Pd, sx, h, cnt)) { fast = false; return true; }
             }
-            if (!walk_advance(A.hf, w, sx, face)) return false;
+            if (!walk_advance(A.hf, w, sx, face)) return RS_CLEAR;
         }
+        // (what is handed back must be strictly shorter than the piece: only positions beyond its own start count)
+        if (w.s > own_start && ++cost > budget) { s_stop = w.s_in + (double)w.s; return RS_MORE; }
     }
 }
 
 // First hit of R at s >= s_min by the whole warp.  Returns the lane that holds it (fast / fh / h valid there), or -1.
 template <bool I16>
-__device__ int referee_ray(const RenderArgs& A, const Ray64& R, double s_min, int start_level, bool any_hit, bool& fast,
-                           FastHit& fh, TraceOut& h, Counters& cnt, bool& entered) {
+__device__ int referee_ray(const RenderArgs& A, RefIv* stack, const Ray64& R, double s_min, int start_level, bool any_hit,
+                           bool& fast, FastHit& fh, TraceOut& h, Counters& cnt, bool& entered) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const double Rb = A.sp.radius * (double)A.hf.dmax;
@@ -1077,22 +1099,63 @@ __device__ int referee_ray(const RenderArgs& A, const Ray64& R, double s_min, in
     if (s1 <= s_min) return -1;
     const double s0 = fmax(s_min, -R.od - sq);
     entered = true;
-    const double step = (s1 - s0) / REFEREE_SEGMENTS;
-    for (int base = 0; base < REFEREE_SEGMENTS; base += 32) {
-        const int seg = base + lane;
-        // pieces overlap a little: a piece's first cell is found from a float32 position a step inside it
-        const double lap = 3.0e-5 * A.sp.radius;
-        const double a = seg == 0 ? s_min : fmax(s_min, s0 + seg * step - lap), b = seg == REFEREE_SEGMENTS - 1 ? s1 + 1.0 : s0 + (seg + 1) * step;
-        const bool hit = trace_referee<I16>(A, R, a, b, seg == 0 ? start_level : 2, any_hit, fast, fh, h, cnt);
+    int top = 4;                                            // the path in four intervals, the nearest on top
+    if (lane < 4) { RefIv& e = stack[3 - lane]; e.a = s0 + lane * 0.25 * (s1 - s0); e.b = lane == 3 ? s1 : s0 + (lane + 1) * 0.25 * (s1 - s0); e.depth = 0; }
+    __syncwarp();
+    int rounds = 0;
+    while (top > 0) {
+        // this round: the n nearest pending intervals, each cut into m pieces; lanes in order of distance
+        // (one interval cut 32 ways at first; once a long chain has been split, its parts run side by side)
+        const int n = any_hit ? min(top, 32) : 1, m = 32 / n;
+        const int q = lane / m, j = lane - q * m;
+        const bool work = q < n;
+        const RefIv iv = stack[top - 1 - (work ? q : 0)];
+        top -= n;
         __syncwarp();
-        const unsigned m = __ballot_sync(FULL, hit);
-        if (m) return __ffs(m) - 1;
+        const double step = (iv.b - iv.a) / (double)m;
+        const double own = iv.a + j * step, end = j == m - 1 ? iv.b : iv.a + (j + 1) * step;
+        const bool first = !(own > s0);
+        // Pieces overlap a little: a piece's first cell is found from a float32 position a step (t0) inside it, so the
+        // walk starts 3 t0 early.  Among polar slivers that lead-in alone is thousands of cells: what comes back from a
+        // lane that ran out of budget is cut with a tenth of it (still 30 times the float32 error of the position).
+        const float t0_rel = iv.depth ? 1.0e-6f : 1.0e-5f;
+        const double lap = 3.0 * (double)t0_rel * A.sp.radius;
+        const double lo = first ? s_min : fmax(s_min, own - lap), hi = end >= s1 ? s1 + 1.0 : end;
+        // (no room to split further, or splitting does not converge: walk it out)
+        const int budget = top + 33 <= REFEREE_STACK && ++rounds < 512 ? REFEREE_BUDGET : 0x7fffffff;
+        double s_stop = end;
+        int st = RS_CLEAR;
+        if (work) st = trace_referee<I16>(A, R, lo, first ? s_min : own, hi, first ? start_level : 2, t0_rel, any_hit, budget, s_stop, fast, fh, h, cnt);
+        __syncwarp();
+        const unsigned m_hit = __ballot_sync(FULL, st == RS_HIT), m_more = __ballot_sync(FULL, st == RS_MORE);
+        const int first_hit = m_hit ? __ffs(m_hit) - 1 : 32;
+        if (any_hit) {
+            if (m_hit) return first_hit;                    // any crossing occludes
+            if (st == RS_MORE) { RefIv& e = stack[top + __popc(m_more & ((1u << lane) - 1u))]; e.a = s_stop; e.b = end; e.depth = iv.depth + 1; }
+            top += __popc(m_more);
+            __syncwarp();
+            continue;
+        }
+        // nearest hit: unfinished pieces in front of the first hit come first, then the piece that hit (traced again)
+        const unsigned before = first_hit < 32 ? m_more & ((1u << first_hit) - 1u) : m_more;
+        if (!before) {
+            if (first_hit < 32) return first_hit;
+            continue;
+        }
+        const int n_hit = first_hit < 32 ? 1 : 0;
+        if (n_hit) {
+            const double ha = shfl_d(own, first_hit), hb = shfl_d(end, first_hit);
+            const int hd = __shfl_sync(FULL, iv.depth, first_hit);
+            if (lane == 0) { stack[top].a = ha; stack[top].b = hb; stack[top].depth = hd; }
+        }
+        if (st == RS_MORE && lane < first_hit) {
+            RefIv& e = stack[top + n_hit + __popc(before & ~((2u << lane) - 1u))];      // the nearest ends up on top
+            e.a = s_stop; e.b = end; e.depth = iv.depth + 1;
+        }
+        top += n_hit + __popc(before);
+        __syncwarp();
     }
     return -1;
-}
-
-__device__ __forceinline__ double shfl_d(double v, int src) {
-    return __hiloint2double(__shfl_sync(0xffffffffu, __double2hiint(v), src), __shfl_sync(0xffffffffu, __double2loint(v), src));
 }
 
 // WAVE: entries are (list pixel, sample) items of the wavefront pipeline and the result goes to the item's
@@ -1100,6 +1163,8 @@ __device__ __forceinline__ double shfl_d(double v, int src) {
 template <bool I16, bool WAVE>
 __global__ void __launch_bounds__(64)
 trace_kernel_referee(const __grid_constant__ RenderArgs A) {
+    __shared__ RefIv stacks[2][REFEREE_STACK];
+    RefIv* const stack = stacks[threadIdx.x >> 5];
     const unsigned total = A.work_counter[3];
     const int lane = threadIdx.x & 31;
     const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -1119,7 +1184,7 @@ trace_kernel_referee(const __grid_constant__ RenderArgs A) {
             bool fast = false, entered = false;
             FastHit fh;
             TraceOut h;
-            const int who = referee_ray<I16>(A, R, 0.0, A.hf.top - 3, false, fast, fh, h, cnt, entered);
+            const int who = referee_ray<I16>(A, stack, R, 0.0, A.hf.top - 3, false, fast, fh, h, cnt, entered);
             if (lane == 0) { ++rs.primary; if (entered) ++rs.inside; }
             if (who < 0) { if (lane == 0) write_miss(A, x, y, sm == A.sample0); continue; }
             float3 lit = make_float3(0.f, 0.f, 0.f);
@@ -1134,7 +1199,7 @@ trace_kernel_referee(const __grid_constant__ RenderArgs A) {
                 S.dx = shfl_d(S.dx, who); S.dy = shfl_d(S.dy, who); S.dz = shfl_d(S.dz, who);
                 S.oo = S.ox * S.ox + S.oy * S.oy + S.oz * S.oz;
                 S.od = S.ox * S.dx + S.oy * S.dy + S.oz * S.dz;
-                occluded = referee_ray<I16>(A, S, 0.0, 2, true, fast, fh, h, cnt, entered) >= 0;
+                occluded = referee_ray<I16>(A, stack, S, 0.0, 2, true, fast, fh, h, cnt, entered) >= 0;
                 if (lane == 0) { ++rs.shadow; if (occluded) ++rs.occluded; }
             }
             if (!occluded) { acc.x += lit.x; acc.y += lit.y; acc.z += lit.z; }

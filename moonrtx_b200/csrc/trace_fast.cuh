@@ -26,6 +26,10 @@
 namespace mrtx_core {
 
 enum { FT_MISS = 0, FT_HIT = 1, FT_DEFER = 2 };
+// A walk this long is a grazing ray among polar slivers (cells centimetres wide): tens of thousands of nodes, one
+// dependent fetch after the other, in ONE lane.  It is handed to the referee (reason 15), whose warp cuts the ray
+// into pieces and walks them side by side.
+constexpr int LONG_WALK = 2048;
 // fast_test() reports WHY it defers in the bits above the status (statistics only: mrtx_defer_stats)
 #define FT_DEFER_R(reason) (FT_DEFER | ((reason) << 2))
 
@@ -377,7 +381,8 @@ MRTX_HD inline bool walk_extent(const HeightField& hf, double radius, const Ray6
     return true;
 }
 
-MRTX_HD inline bool walk_begin(const HeightField& hf, double radius, const Ray64& R, double s_min, int start_level, Walk& w) {
+MRTX_HD inline bool walk_begin(const HeightField& hf, double radius, const Ray64& R, double s_min, int start_level, Walk& w,
+                               float t0_rel = 1e-5f) {
     double s_first, s_end;
     if (!walk_extent(hf, radius, R, s_first, s_end)) return false;
     if (s_end <= s_min) return false;
@@ -386,7 +391,7 @@ MRTX_HD inline bool walk_begin(const HeightField& hf, double radius, const Ray64
     const int W = hf.W, H = hf.H;
     const int L = min(max(start_level, 0), hf.top);
     // first cell from the position just inside (a wrong neighbour is corrected by the on-wall rule)
-    const float t0 = fminf(1e-5f * (float)radius, 0.5f * w.smax);
+    const float t0 = fminf(t0_rel * (float)radius, 0.5f * w.smax);
     const float x = fmaf(t0, w.dx, w.ox), y = fmaf(t0, w.dy, w.oy), z = fmaf(t0, w.dz, w.oz);
     const float lon = atan2f(x, -y), lat = atan2f(z, sqrtf(x * x + y * y));
     const float u = (lon * (0.5f / PI_F) + 0.5f) * (float)W - 0.5f, v = (0.5f - lat * (1.0f / PI_F)) * (float)H - 0.5f;
