@@ -45,6 +45,27 @@ FALLBACK_HBM_GBS = 6650.0        # /opt/skills/guides/B200_PROFILING.md fallback
 NCU_TRAFFIC_BYTES = 5.489479e9 + 5.908359e9
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly one JSON line: libraries that print there (NCCL's version banner does, whatever
+    NCCL_DEBUG_FILE says) are sent to stderr instead; emit() writes to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    data = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def quadtree_depth(W):
     k = 0
     while (W >> (k + 1)) >= 64:
@@ -364,7 +385,7 @@ def run_ours(args):
             "frames_per_s": round(world * args.steps / (ms_total * 1e-3), 3),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clock_info,
         }
-        print(json.dumps(line))
+        emit(line)
     rt.close()
     if world > 1:
         import torch.distributed as dist
@@ -423,7 +444,7 @@ def run_reference(args):
         ldem_host = buf.download((args.map_h, args.map_w), np.int16)
         buf.free(); dev.close()
     except Exception as e:
-        print(json.dumps({"impl": "reference", "unavailable": f"could not generate the synthetic map: {e}"}))
+        emit({"impl": "reference", "unavailable": f"could not generate the synthetic map: {e}"})
         return
     st = scene.frame_state(synth_ephemeris(args.warmup * FRAME_STEP_MIN))
     vals = []
@@ -435,7 +456,7 @@ def run_reference(args):
             vals.append(cpu["value"])
     v = statistics.mean(vals)
     cpu["value"] = round(v, 4)
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "Mrays/s (primary+shadow) @4K", "value": round(v, 4), "unit": "Mrays/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -443,7 +464,7 @@ def run_reference(args):
                                f"{args.spp} spp (BASELINE config 3), bounded sample per step"},
         "cpu_baseline": cpu,
         "e2e": {"value": round(v, 4), "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 def main():
@@ -465,6 +486,7 @@ def main():
     ap.add_argument("--traffic", type=float, default=NCU_TRAFFIC_BYTES,
                     help="dram__bytes_read.sum + dram__bytes_write.sum of trace_kernel_fast per launch, from the ncu capture in profiles/")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
