@@ -222,6 +222,43 @@ def _radius_scale_ds1(dev, ldem, W, H, band=512):
     return best
 
 
+def downscale_line(dev, peak, skip_cpu):
+    """BASELINE config 1 beside the headline: --downscale 4 of a 23040x11520 int16 map, HBM to HBM, L2 flushed between
+    runs, algorithmic bytes 2*W*H + 4*(W/4)*(H/4); the reference's numpy expression (oracle port, pinned
+    bit for bit on data_loader.py:223-242) timed on one host core next to it, and the two results compared."""
+    from moonrtx_b200 import _lib
+    from moonrtx_b200.data_loader import downscale_elevation_dev
+    W, H, ds = 23040, 11520, 4
+    src = dev.alloc(W * H * 2)
+    _lib.check(dev.lib.mrtx_synth_ldem_i16_dev(dev.ctx, src.ptr, W, H, SEED))
+    out = dev.alloc((W // ds) * (H // ds) * 4)
+    for _ in range(3):
+        downscale_elevation_dev(src, W, H, ds, out, want_scale=False)
+    ts = []
+    for _ in range(10):
+        dev.l2_flush(); dev.synchronize()
+        dev.timer_start()
+        _, rs = downscale_elevation_dev(src, W, H, ds, out)
+        ts.append(dev.timer_stop())
+    nbytes = 2 * W * H + 4 * (W // ds) * (H // ds)
+    ms = statistics.median(ts)
+    line = {"workload": f"{W}x{H} int16 -> downscale {ds} (BASELINE config 1), HBM to HBM, L2 flushed between runs",
+            "ms": round(ms, 4), "GBps": round(nbytes / ms / 1e6, 1), "frac_of_hbm_peak": round(nbytes / ms / 1e6 / peak, 4),
+            "algorithmic_bytes": nbytes, "launches": 2}
+    if not skip_cpu:
+        from oracle import downscale_oracle as orc
+        host = src.download((H, W), np.int16)
+        t0 = time.perf_counter()
+        ref, rs_ref = orc.load_elevation(host, ds)
+        dt = time.perf_counter() - t0
+        got = out.download((H // ds, W // ds), np.float32)
+        line["cpu_baseline"] = {"value": round(nbytes / dt / 1e9, 3), "unit": "GB/s", "seconds": round(dt, 2), "cores": 1, "kind": "port",
+                                "sample": "the whole config-1 map, numpy reshape/mean/normalise as data_loader.py:223-242"}
+        line["bit_exact_vs_oracle"] = bool(np.array_equal(got.view(np.uint32), ref.view(np.uint32)) and rs == rs_ref)
+    src.free(); out.free()
+    return line
+
+
 def overlay_image(h, w, text_seed):
     """A frame_overlay like renderer_video.py:106-144 draws (time label box, bottom-left)."""
     buf = np.zeros((h, w, 4), dtype=np.uint8)
@@ -330,6 +367,8 @@ def run_ours(args):
                 "unit": "GB/s", "frac": round(achieved / peak, 5),
                 "traffic": args.traffic if (args.map_w, args.img_w, args.spp) == (MAP_W, IMG_W, 16) else None,
                 "algorithmic_bytes_per_launch": int(algo_bytes), "bytes_per_ray": b_floor,
+                # what the kernel's own counters say it fetched: one 32-byte sector per node visit, two per patch test
+                "counted_bytes_per_ray": round(32.0 * (ck["node_visits"] + 2 * ck["patch_tests"]) / max(1.0, ck["primary_in_sphere"] + ck["shadow_rays"]), 1),
                 "rays_in_sphere_per_launch": int(rays_in), "kernel_ms": round(k_ms, 3), "peak_source": peak_src,
                 "kernel_share_of_step": round(k_ms * args.steps / ms_total, 4) if world == 1 else None}
 
@@ -364,6 +403,9 @@ def run_ours(args):
         cpu = cpu_baseline(args, ldem_host=ldem.download((args.map_h, args.map_w), np.int16),
                            radius_scale=radius_scale, state=states[args.warmup])
 
+    # ---- config 1 beside it (rank 0): the data_loader downscale against the HBM peak -----------------------
+    downscale = downscale_line(dev, peak, args.skip_cpu) if rank == 0 and not args.skip_downscale else None
+
     if rank == 0:
         line = {
             "metric": "Mrays/s (primary+shadow) @4K", "value": round(value, 2), "unit": "Mrays/s",
@@ -384,6 +426,7 @@ def run_ours(args):
                      "defer_reasons_primary": defer["primary_reasons"], "defer_reasons_shadow": defer["shadow_reasons"]},
             "frames_per_s": round(world * args.steps / (ms_total * 1e-3), 3),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clock_info,
+            "downscale": downscale,
         }
         emit(line)
     rt.close()
@@ -482,6 +525,7 @@ def main():
     ap.add_argument("--color-h", type=int, default=COLOR_H)
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-downscale", action="store_true")
     ap.add_argument("--frame-stride", type=int, default=0, help="development: frame index step between steps (default: world size)")
     ap.add_argument("--traffic", type=float, default=NCU_TRAFFIC_BYTES,
                     help="dram__bytes_read.sum + dram__bytes_write.sum of trace_kernel_fast per launch, from the ncu capture in profiles/")
