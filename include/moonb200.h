@@ -126,7 +126,8 @@ int  mrtx_set_light(mrtx_ctx* ctx, const double pos[3], double radius, double ra
  * marching_step_eps are accepted and ignored: intersection here is exact).
  * rt.set_uint: path_seg_range (accepted; direct light only), jitter, shadows.
  * Engine switches (not part of the PlotOptiX surface): debug_hits (float64 hit records for
- * tests), start_levels (a, b: pyramid levels the primary / shadow walks start at), and
+ * tests), start_levels (a, b: pyramid levels the primary / shadow walks start at), long_walk (nodes
+ * after which a walk is handed to the referee, default 2048), referee_budget (default 1500), and
  * kernel = 0 float64 one thread per pixel, 1 float64 persistent warps, 2 (default) filtered
  * float32 kernel + float64 referee, 3 the same arithmetic as a wavefront pipeline of dense
  * generation / streaming walk / dense shading kernels over ray records.   */

@@ -67,7 +67,7 @@ int mrtx_create(int device, mrtx_ctx** out_ctx) {
     sp.light_pos[0] = 21460.0; sp.light_radius = 100.0; sp.light_radiance = 80.0 * 460.5316;
     sp.scene_epsilon = 1.0e-4;
     sp.exposure = 0.9f; sp.inv_gamma = 1.0f / 2.2f;
-    sp.jitter = 0; sp.shadows = 1; sp.debug_hits = 0; sp.kernel = 2; sp.start_primary = 3; sp.start_shadow = 2;
+    sp.jitter = 0; sp.shadows = 1; sp.debug_hits = 0; sp.kernel = 2; sp.start_primary = 3; sp.start_shadow = 2; sp.long_walk = 2048u; sp.referee_budget = 1500u;
     const double eye[3] = {0, -300, 0}, tgt[3] = {0, 0, 0}, up[3] = {0, 0, 1};
     mrtx_set_camera(c, eye, tgt, up, 4.242192793);
     *out_ctx = c;
@@ -450,6 +450,8 @@ int mrtx_set_uint(mrtx_ctx* ctx, const char* name, unsigned a, unsigned b) {
     else if (!strcmp(name, "shadows")) ctx->sp.shadows = a ? 1u : 0u;
     else if (!strcmp(name, "debug_hits")) ctx->sp.debug_hits = a ? 1u : 0u;
     else if (!strcmp(name, "start_levels")) { ctx->sp.start_primary = a; ctx->sp.start_shadow = b; }
+    else if (!strcmp(name, "long_walk")) { MRTX_REQUIRE(a >= 1u, "long_walk must be >= 1"); ctx->sp.long_walk = a; }
+    else if (!strcmp(name, "referee_budget")) { MRTX_REQUIRE(a >= 1u, "referee_budget must be >= 1"); ctx->sp.referee_budget = a; }
     else if (!strcmp(name, "kernel")) { MRTX_REQUIRE(a <= 3u, "kernel must be 0, 1, 2 or 3"); ctx->sp.kernel = a; }
     else { mrtx_set_error("unknown uint parameter '%s'", name); return MRTX_ERR_INVALID; }
     return MRTX_OK;

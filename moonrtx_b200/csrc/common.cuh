@@ -84,6 +84,7 @@ struct SceneParams {
     float  exposure, inv_gamma;
     unsigned jitter, shadows, debug_hits;
     unsigned start_primary, start_shadow;   // filtered kernel: primary rays start at level top - start_primary, shadow rays at start_shadow
+    unsigned long_walk, referee_budget;     // walks longer than long_walk nodes go to the referee; a referee lane spends referee_budget on a piece
     unsigned kernel;                        // 2 = filtered float32 kernel + exact kernel on what it defers (default),
                                             // 1 = exact persistent kernel only, 0 = exact, one thread per pixel
 };

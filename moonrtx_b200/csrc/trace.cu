@@ -673,7 +673,7 @@ trace_kernel_fast(const __grid_constant__ RenderArgs A) {
                         }
                     }
                     __syncwarp();
-                    if ((alive || cand) && st.steps > LONG_WALK) {
+                    if ((alive || cand) && st.steps > (int)A.sp.long_walk) {
                         res = FT_DEFER; alive = false; cand = false;
                         atomicAdd(&A.defer_stats[15 + (pass ? 16 : 0)], 1ull);
                     }
@@ -888,7 +888,7 @@ trace_kernel_walk(const __grid_constant__ RenderArgs A) {
             // ---- walk step -------------------------------------------------------------------------------------
             const int r = walk_step<I16>(A.hf, Rf, A.inv_rs, st, P, sx, face, cnt);
             if (r == TR_END) finished = true;
-            else if (st.steps > LONG_WALK) { finished = true; status = FT_DEFER_R(15); }
+            else if (st.steps > (int)A.sp.long_walk) { finished = true; status = FT_DEFER_R(15); }
             else if (r == TR_CANDIDATE) mode = LM_CAND;
         }
         if (finished) {
@@ -1031,13 +1031,9 @@ reduce_kernel(const __grid_constant__ RenderArgs A) {
 // Equal pieces are not equal work.  A sun ray at the horizon stays within the walk's 5 m margin of level ground for
 // 4 km, and next to a pole those 4 km are tens of thousands of cells 10 cm wide: measured, ONE piece of ONE shadow
 // ray 1.5 km from the south pole held 22 145 nodes and 14 642 patch tests and the launch took 25 ms instead of 2.
-// A lane therefore walks a piece only as far as a budget lets it; what is left of the piece goes back on the warp's
-// stack of intervals and is cut into 32 again.
+// A lane therefore walks a piece only as far as a budget lets it (SceneParams::referee_budget: nodes + 3 * patch
+// tests, default 1500); what is left of the piece goes back on the warp's stack of intervals and is cut again.
 constexpr int REFEREE_STACK = 96;           // pending intervals per warp
-#ifndef MRTX_REFEREE_BUDGET
-#define MRTX_REFEREE_BUDGET 1500
-#endif
-constexpr int REFEREE_BUDGET = MRTX_REFEREE_BUDGET;      // nodes + 3 * patch tests a lane spends on one piece
 struct RefIv { double a, b; int depth; int pad; };        // depth > 0: what a lane left of a piece
 enum { RS_CLEAR = 0, RS_HIT = 1, RS_MORE = 2 };
 
@@ -1122,7 +1118,7 @@ __device__ int referee_ray(const RenderArgs& A, RefIv* stack, const Ray64& R, do
         const double lap = 3.0 * (double)t0_rel * A.sp.radius;
         const double lo = first ? s_min : fmax(s_min, own - lap), hi = end >= s1 ? s1 + 1.0 : end;
         // (no room to split further, or splitting does not converge: walk it out)
-        const int budget = top + 33 <= REFEREE_STACK && ++rounds < 512 ? REFEREE_BUDGET : 0x7fffffff;
+        const int budget = top + 33 <= REFEREE_STACK && ++rounds < 512 ? (int)A.sp.referee_budget : 0x7fffffff;
         double s_stop = end;
         int st = RS_CLEAR;
         if (work) st = trace_referee<I16>(A, R, lo, first ? s_min : own, hi, first ? start_level : 2, t0_rel, any_hit, budget, s_stop, fast, fh, h, cnt);

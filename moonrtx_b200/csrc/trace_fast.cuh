@@ -26,10 +26,9 @@
 namespace mrtx_core {
 
 enum { FT_MISS = 0, FT_HIT = 1, FT_DEFER = 2 };
-// A walk this long is a grazing ray among polar slivers (cells centimetres wide): tens of thousands of nodes, one
-// dependent fetch after the other, in ONE lane.  It is handed to the referee (reason 15), whose warp cuts the ray
-// into pieces and walks them side by side.
-constexpr int LONG_WALK = 2048;
+// A walk longer than SceneParams::long_walk nodes (default 2048) is a grazing ray among polar slivers (cells
+// centimetres wide): tens of thousands of nodes, one dependent fetch after the other, in ONE lane.  It is handed to
+// the referee (reason 15), whose warp cuts the ray into pieces and walks them side by side.
 // fast_test() reports WHY it defers in the bits above the status (statistics only: mrtx_defer_stats)
 #define FT_DEFER_R(reason) (FT_DEFER | ((reason) << 2))
 

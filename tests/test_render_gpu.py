@@ -357,6 +357,41 @@ def test_wavefront_pipeline_equals_filtered_kernel(spp):
         assert np.array_equal(ha, hb)
 
 
+@pytest.mark.parametrize("kernel", [2, 3])
+def test_long_walks_and_budgeted_referee_pieces_change_nothing(kernel):
+    """The referee's machinery for long chains, forced onto ordinary rays: with long_walk = 2 nearly every ray that
+    enters the shell is handed to the referee (reason 15), and with referee_budget = 8 its lanes give up after a few
+    cells, so pieces are re-cut again and again (nearest-hit ordering for primary rays, side-by-side intervals for
+    shadow rays).  Same hits, same image as the default path."""
+    elev, _ = synth_elevation(1440, 720, seed=21)
+    kw = dict(light_pos=sun_at_phase(87.0))
+    outs = []
+    for forced in (False, True):
+        rt = make_gpu(elev, 160, 120, **kw)
+        rt.set_uint("kernel", kernel)
+        if forced:
+            rt.set_uint("long_walk", 2)
+            rt.set_uint("referee_budget", 8)
+        rt.defer_stats(reset=True); rt.counters(reset=True)
+        img = rt.render_cycle().copy()
+        outs.append((img, rt.get_hit_records_f64().copy(), rt.counters(), rt.defer_stats()))
+        rt.close()
+    (ia, ha, ca, da), (ib, hb, cb, db) = outs
+    n15 = db["primary_reasons"].get(15, 0) + db["shadow_reasons"].get(15, 0)
+    assert n15 > 0.5 * ca["primary_in_sphere"], (n15, ca["primary_in_sphere"])
+    hit_a, hit_b = ha[..., 0] > 0, hb[..., 0] > 0
+    assert int((hit_a != hit_b).sum()) <= 2
+    both = hit_a & hit_b
+    texel = 2.0 * math.pi * R / 1440
+    assert int((np.abs(ha[..., 0] - hb[..., 0])[both] / texel > 1e-3).sum()) <= 2
+    for k in ("primary_rays", "primary_in_sphere"):
+        assert ca[k] == cb[k], k
+    for k in ("primary_hits", "shadow_rays", "shadow_occluded"):
+        assert abs(ca[k] - cb[k]) <= 3, (k, ca[k], cb[k])
+    d = np.abs(ia[..., :3].astype(np.int32) - ib[..., :3].astype(np.int32))
+    assert d.mean() <= 0.01 and int((d.max(axis=2) > 1).sum()) <= 4
+
+
 def test_more_than_32_samples_are_chunked():
     """The filtered kernel takes <= 32 samples per launch (one mask bit each in the deferred list): 40 spp must
     equal 32 + 8 spp accumulated in two calls, and match the oracle."""
