@@ -392,6 +392,26 @@ def test_long_walks_and_budgeted_referee_pieces_change_nothing(kernel):
     assert d.mean() <= 0.01 and int((d.max(axis=2) > 1).sum()) <= 4
 
 
+def test_reference_accumulation_parameters_render_one_batched_cycle():
+    """The reference asks for min_accumulation_step=1, max_accumulation_frames=64 (moon_renderer.py:578).  The
+    drop-in renders the cycle's samples together (same samples, keyed on (pixel, index)); the frame is complete
+    when render_cycle returns and the callbacks have fired once."""
+    elev, _ = synth_elevation(720, 360, seed=4)
+    kw = dict(light_pos=sun_at_phase(80.0))
+    fired = []
+    outs = []
+    for step in (1, 24):
+        rt = make_gpu(elev, 64, 48, debug_hits=False, **kw)
+        rt.set_param(min_accumulation_step=step, max_accumulation_frames=24)
+        rt.set_accum_done_cb(lambda r: fired.append(step))
+        rt.render_cycle()
+        outs.append(rt.get_accum_buffer().copy())
+        assert rt.counters()["primary_rays"] == 64 * 48 * 24
+        rt.close()
+    assert fired == [1, 24]
+    assert np.all(outs[0][..., 3] == 24.0) and np.array_equal(outs[0], outs[1])
+
+
 def test_more_than_32_samples_are_chunked():
     """The filtered kernel takes <= 32 samples per launch (one mask bit each in the deferred list): 40 spp must
     equal 32 + 8 spp accumulated in two calls, and match the oracle."""

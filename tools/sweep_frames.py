@@ -8,6 +8,9 @@ from moonrtx_b200.video import apply_frame_state
 rt, info = bt.setup(92160, 46080, 3840, 2160, ds=1)
 lib, ctx = rt._dev.lib, rt._dev.ctx
 _lib.check(lib.mrtx_set_uint(ctx, b"kernel", int(os.environ.get("KERNEL", "2")), 0))
+for name in ("long_walk", "referee_budget"):
+    if os.environ.get(name.upper()):
+        _lib.check(lib.mrtx_set_uint(ctx, name.encode(), int(os.environ[name.upper()]), 0))
 for f in [int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "0,8,24,48,87,160,239").split(",")]:
     apply_frame_state(rt, scene.frame_state(synth_ephemeris(f * 10.0)))
     r = bt.time_frame(rt, 16, reps=2)
