@@ -461,7 +461,7 @@ def cpu_baseline(args, ldem_host, radius_scale, state, budget_s=20.0):
     primary = npx * args.spp
     # shadow rays = samples that hit a sun-facing slope; the oracle reports the cells walked by each
     shadow = int((o["stats"][..., 1] > 0).sum()) * args.spp          # last-sample estimate
-    return {"value": round((primary + shadow) / dt / 1e6, 4), "unit": "Mrays/s", "cores": cores, "kind": "port",
+    return {"value": round((primary + shadow) / dt / 1e6, 4), "unit": "Mrays/s", "cores": cores, "kind": "port", "seconds": round(dt, 3),
             "sample": f"every {stride}th pixel in x and y of the same {args.img_w}x{args.img_h} frame "
                       f"({npx} pixels x {args.spp} spp), {dt:.1f} s, float64 oracle (exhaustive cell walk, no pyramid), "
                       f"OpenMP {cores} threads"}
@@ -490,19 +490,19 @@ def run_reference(args):
         emit({"impl": "reference", "unavailable": f"could not generate the synthetic map: {e}"})
         return
     st = scene.frame_state(synth_ephemeris(args.warmup * FRAME_STEP_MIN))
-    vals = []
+    vals, secs = [], []
     cpu = None
     per_step_budget = max(2.0, min(20.0, 120.0 / (args.steps + args.warmup)))
     for j in range(args.warmup + args.steps):
         cpu = cpu_baseline(args, ldem_host, radius_scale, st, budget_s=per_step_budget)
         if j >= args.warmup:
-            vals.append(cpu["value"])
+            vals.append(cpu["value"]); secs.append(cpu["seconds"])
     v = statistics.mean(vals)
     cpu["value"] = round(v, 4)
     emit({
         "impl": "reference", "metric": "Mrays/s (primary+shadow) @4K", "value": round(v, 4), "unit": "Mrays/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * statistics.mean(secs), 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{args.img_w}x{args.img_h} frame, {args.map_w}x{args.map_h} int16 synthetic LOLA map, "
                                f"{args.spp} spp (BASELINE config 3), bounded sample per step"},
         "cpu_baseline": cpu,
