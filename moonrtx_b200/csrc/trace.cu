@@ -1118,7 +1118,7 @@ __device__ int referee_ray(const RenderArgs& A, RefIv* stack, const Ray64& R, do
         const double lap = 3.0 * (double)t0_rel * A.sp.radius;
         const double lo = first ? s_min : fmax(s_min, own - lap), hi = end >= s1 ? s1 + 1.0 : end;
         // (no room to split further, or splitting does not converge: walk it out)
-        const int budget = top + 33 <= REFEREE_STACK && ++rounds < 512 ? (int)A.sp.referee_budget : 0x7fffffff;
+        const int budget = top + 34 <= REFEREE_STACK && ++rounds < 512 ? (int)A.sp.referee_budget : 0x7fffffff;
         double s_stop = end;
         int st = RS_CLEAR;
         if (work) st = trace_referee<I16>(A, R, lo, first ? s_min : own, hi, first ? start_level : 2, t0_rel, any_hit, budget, s_stop, fast, fh, h, cnt);
@@ -1138,11 +1138,14 @@ __device__ int referee_ray(const RenderArgs& A, RefIv* stack, const Ray64& R, do
             if (first_hit < 32) return first_hit;
             continue;
         }
-        const int n_hit = first_hit < 32 ? 1 : 0;
+        // (under it, what lies beyond that piece in this interval: only looked at should the piece not hit again)
+        const int n_hit = first_hit < 32 ? 2 : 0;
         if (n_hit) {
             const double ha = shfl_d(own, first_hit), hb = shfl_d(end, first_hit);
-            const int hd = __shfl_sync(FULL, iv.depth, first_hit);
-            if (lane == 0) { stack[top].a = ha; stack[top].b = hb; stack[top].depth = hd; }
+            if (lane == 0) {
+                stack[top].a = hb; stack[top].b = iv.b; stack[top].depth = iv.depth;
+                stack[top + 1].a = ha; stack[top + 1].b = hb; stack[top + 1].depth = iv.depth;
+            }
         }
         if (st == RS_MORE && lane < first_hit) {
             RefIv& e = stack[top + n_hit + __popc(before & ~((2u << lane) - 1u))];      // the nearest ends up on top
