@@ -15,8 +15,10 @@ no data-path collective; `value` = rays traced by all ranks / max-over-ranks dev
 
 Metric: Mrays/s (primary + shadow rays actually traced, primary rays that miss the Moon
 included), device-timed with CUDA events on the launching stream; `e2e` = the same through
-the public drop-in API (B200OptiX: overlay texture upload from pinned memory, scene update,
-render_cycle, RGBA8 frame read-back to pinned memory), wall clock around synchronised calls.
+the public drop-in API as the F11 export loop uses it (B200OptiX.submit_frame / wait_frame, two
+frames in flight: overlay copied to pinned memory and uploaded, scene update, accumulation cycle,
+resolve, RGBA8 frame read back to pinned memory - every frame's copies inside the timed region),
+wall clock between barriers; `--e2e-sync` times the one-frame-at-a-time render_cycle instead.
 """
 
 import argparse
@@ -376,26 +378,50 @@ def run_ours(args):
     e2e = None
     if not args.skip_e2e:
         overlays = [overlay_image(args.img_h, args.img_w, 37 * j + rank) for j in range(total)]
-        pinned = rt.pinned_like(overlays[0])
         rt.counters(reset=True)
-        e2e_rays = 0
-        for j in range(total):
-            if j == args.warmup:
-                barrier()
-                rt.counters(reset=True)
-                t0 = time.perf_counter()
-            np.copyto(pinned, overlays[j])                       # the label the host drew for this frame
-            rt.set_texture_2d("frame_overlay", pinned, filter_mode="Nearest", refresh=False)
-            apply_frame_state(rt, states[j])
-            img = rt.render_cycle()                               # renders, resolves, reads the frame back
-            checksum = int(img[::97, ::89, :3].sum())
+        checksum = 0
+        if args.e2e_sync:
+            # one frame at a time: upload, render, resolve, read back, then the next
+            pinned = rt.pinned_like(overlays[0])
+            for j in range(total):
+                if j == args.warmup:
+                    barrier()
+                    rt.counters(reset=True)
+                    t0 = time.perf_counter()
+                np.copyto(pinned, overlays[j])                       # the label the host drew for this frame
+                rt.set_texture_2d("frame_overlay", pinned, filter_mode="Nearest", refresh=False)
+                apply_frame_state(rt, states[j])
+                img = rt.render_cycle()                               # renders, resolves, reads the frame back
+                checksum = int(img[::97, ::89, :3].sum())
+        else:
+            # the F11 export loop as video.render_timelapse(pipelined=True) runs it: frame j + 1 is submitted (overlay
+            # to pinned memory, scene update, queue) before frame j is waited for and consumed; every frame's overlay
+            # goes host -> device and every frame's pixels come device -> host inside the timed region
+            def consume(ticket):
+                img = rt.wait_frame(ticket)
+                return int(img[::97, ::89, :3].sum())
+            pending = None
+            for j in range(total):
+                if j == args.warmup:
+                    if pending is not None:
+                        consume(pending); pending = None         # nothing in flight across the start of the clock
+                    barrier()
+                    rt.counters(reset=True)
+                    t0 = time.perf_counter()
+                apply_frame_state(rt, states[j])
+                ticket = rt.submit_frame(overlays[j])
+                if pending is not None:
+                    checksum = consume(pending)
+                pending = ticket
+            checksum = consume(pending)                               # ... nor across its end
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
         ce = rt.counters()
         e2e_rays = sum_over_ranks(float(ce["primary_rays"] + ce["shadow_rays"]))
         e2e = {"value": round(e2e_rays / dt / 1e6, 2), "unit": "Mrays/s",
                "h2d_bytes_per_step": int(overlays[0].nbytes + 1024), "d2h_bytes_per_step": int(args.img_w * args.img_h * 4),
-               "ms_per_step": round(dt * 1e3 / args.steps, 2), "frame_checksum": checksum}
+               "ms_per_step": round(dt * 1e3 / args.steps, 2), "frame_checksum": checksum,
+               "api": "B200OptiX.render_cycle per frame" if args.e2e_sync else "B200OptiX.submit_frame / wait_frame (two frames in flight)"}
 
     # ---- CPU baseline (rank 0, N = 1 only): the float64 oracle on a bounded sample -----------------
     cpu = None
@@ -525,6 +551,7 @@ def main():
     ap.add_argument("--color-h", type=int, default=COLOR_H)
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--e2e-sync", action="store_true", help="e2e one frame at a time (render_cycle) instead of the pipelined export loop")
     ap.add_argument("--skip-downscale", action="store_true")
     ap.add_argument("--frame-stride", type=int, default=0, help="development: frame index step between steps (default: world size)")
     ap.add_argument("--traffic", type=float, default=NCU_TRAFFIC_BYTES,

@@ -150,6 +150,16 @@ int  mrtx_resolve(mrtx_ctx* ctx);
 int  mrtx_read_rgba8(mrtx_ctx* ctx, uint8_t* out);          /* [H][W][4]                */
 int  mrtx_read_accum_f32(mrtx_ctx* ctx, float* out);        /* [H][W][4] sum r,g,b,count */
 int  mrtx_read_hit_f32(mrtx_ctx* ctx, float* out);          /* [H][W][4] x,y,z,dist      */
+/* Pipelined frames for the F11 export loop (renderer_video.py:276-364: overlay, update_view,
+ * accumulate, grab).  mrtx_frame_submit queues ONE whole frame with the scene as it is now -
+ * overlay upload from pinned memory (or none), nsamples samples of every pixel, resolve, RGBA8
+ * read-back into the caller's pinned buffer - and returns a ticket (0 / 1) without waiting; the
+ * copies run on a second stream against the tracing of the neighbouring frames.  At most two
+ * frames are in flight: a third submit reuses the first one's slot.  mrtx_frame_wait blocks
+ * until that frame's pixels are in the buffer given at submit.                            */
+int  mrtx_frame_submit(mrtx_ctx* ctx, const uint8_t* overlay_rgba_pinned, unsigned nsamples,
+                       uint8_t* out_rgba_pinned, int* ticket);
+int  mrtx_frame_wait(mrtx_ctx* ctx, int ticket);
 /* rt._get_hit_at(x, y) -> (hx, hy, hz, hd), moon_renderer.py:1138; hd <= 0 = miss.     */
 int  mrtx_hit_at(mrtx_ctx* ctx, int x, int y, float out4[4]);
 /* device views of the frame buffers (for collectives and zero-copy consumers)        */

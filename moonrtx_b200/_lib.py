@@ -64,6 +64,8 @@ _SIGNATURES = {
     "mrtx_resize": (C.c_int, [c_ctx, C.c_int, C.c_int]),
     "mrtx_render": (C.c_int, [c_ctx, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_int]),
     "mrtx_resolve": (C.c_int, [c_ctx]),
+    "mrtx_frame_submit": (C.c_int, [c_ctx, C.c_void_p, C.c_uint, C.c_void_p, C.POINTER(C.c_int)]),
+    "mrtx_frame_wait": (C.c_int, [c_ctx, C.c_int]),
     "mrtx_read_rgba8": (C.c_int, [c_ctx, C.c_void_p]),
     "mrtx_read_accum_f32": (C.c_int, [c_ctx, C.c_void_p]),
     "mrtx_read_hit_f32": (C.c_int, [c_ctx, C.c_void_p]),

@@ -80,6 +80,8 @@ static void free_frame(mrtx_ctx* c) {
     c->accum = nullptr; c->rgba8 = nullptr; c->hit = nullptr; c->hit64 = nullptr;
 }
 
+static void pipe_release(mrtx_ctx* ctx);
+
 int mrtx_destroy(mrtx_ctx* ctx) {
     if (!ctx) return MRTX_OK;
     cudaSetDevice(ctx->device);
@@ -87,6 +89,9 @@ int mrtx_destroy(mrtx_ctx* ctx) {
     mrtx_comm_destroy(ctx);
     free_heightfield(ctx);
     for (int s = 0; s < 2; ++s) cudaFree(ctx->tex_owned[s]);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    pipe_release(ctx);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     free_frame(ctx);
     cudaFree(ctx->d_max_bits);
     cudaFree(ctx->d_work);
@@ -473,6 +478,80 @@ int mrtx_resize(mrtx_ctx* ctx, int width, int height) {
     MRTX_CUDA(cudaMemsetAsync(ctx->rgba8, 0, n * sizeof(uchar4), ctx->stream));
     MRTX_CUDA(cudaMemsetAsync(ctx->hit, 0, n * sizeof(float4), ctx->stream));
     ctx->width = width; ctx->height = height;
+    return MRTX_OK;
+}
+
+// ---- pipelined frames ---------------------------------------------------------------------------
+// The synchronous sequence (set overlay texture, render, resolve, read back) leaves the GPU idle while 33 MB go in
+// and 33 MB come out of every 4K frame and while the host gets round to the next one.  mrtx_frame_submit() queues a
+// whole frame - overlay upload, trace, resolve, read-back into the caller's pinned buffer - and returns; the copies
+// run on a second stream against the NEXT / PREVIOUS frame's tracing.  Scene parameters are captured at submit.
+static void pipe_release(mrtx_ctx* ctx) {
+    for (int k = 0; k < 2; ++k) {
+        cudaFree(ctx->pipe_overlay[k]); cudaFree(ctx->pipe_rgba8[k]);
+        ctx->pipe_overlay[k] = nullptr; ctx->pipe_rgba8[k] = nullptr;
+        if (ctx->pipe_ev_upload[k]) { cudaEventDestroy(ctx->pipe_ev_upload[k]); cudaEventDestroy(ctx->pipe_ev_resolve[k]); cudaEventDestroy(ctx->pipe_ev_d2h[k]); }
+        ctx->pipe_ev_upload[k] = ctx->pipe_ev_resolve[k] = ctx->pipe_ev_d2h[k] = nullptr;
+    }
+    ctx->pipe_w = ctx->pipe_h = 0;
+}
+
+static int pipe_ensure(mrtx_ctx* ctx) {
+    if (ctx->pipe_w == ctx->width && ctx->pipe_h == ctx->height && ctx->pipe_rgba8[0]) return MRTX_OK;
+    MRTX_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->copy_stream) MRTX_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+    else MRTX_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    pipe_release(ctx);
+    const size_t bytes = (size_t)ctx->width * ctx->height * sizeof(uchar4);
+    for (int k = 0; k < 2; ++k) {
+        MRTX_CUDA(cudaMalloc(&ctx->pipe_overlay[k], bytes));
+        MRTX_CUDA(cudaMalloc(&ctx->pipe_rgba8[k], bytes));
+        MRTX_CUDA(cudaEventCreateWithFlags(&ctx->pipe_ev_upload[k], cudaEventDisableTiming));
+        MRTX_CUDA(cudaEventCreateWithFlags(&ctx->pipe_ev_resolve[k], cudaEventDisableTiming));
+        MRTX_CUDA(cudaEventCreateWithFlags(&ctx->pipe_ev_d2h[k], cudaEventDisableTiming));
+        // (recorded once so that the first waits on them return at once)
+        MRTX_CUDA(cudaEventRecord(ctx->pipe_ev_resolve[k], ctx->stream));
+        MRTX_CUDA(cudaEventRecord(ctx->pipe_ev_d2h[k], ctx->copy_stream));
+    }
+    ctx->pipe_w = ctx->width; ctx->pipe_h = ctx->height; ctx->pipe_slot = 0;
+    return MRTX_OK;
+}
+
+int mrtx_frame_submit(mrtx_ctx* ctx, const uint8_t* overlay_rgba_pinned, unsigned nsamples, uint8_t* out_rgba_pinned, int* ticket) {
+    MRTX_CTX(ctx);
+    MRTX_REQUIRE(out_rgba_pinned && ticket && nsamples > 0, "null argument / no samples");
+    if (!ctx->accum) { mrtx_set_error("mrtx_resize has not been called"); return MRTX_ERR_STATE; }
+    if (!ctx->hf.base) { mrtx_set_error("no displacement map set"); return MRTX_ERR_STATE; }
+    int rc = pipe_ensure(ctx);
+    if (rc) return rc;
+    const int k = ctx->pipe_slot;
+    ctx->pipe_slot ^= 1;
+    const size_t n = (size_t)ctx->width * ctx->height, bytes = n * sizeof(uchar4);
+    if (overlay_rgba_pinned) {
+        // slot k's overlay was last read by the resolve of the frame two submits ago
+        MRTX_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->pipe_ev_resolve[k], 0));
+        MRTX_CUDA(cudaMemcpyAsync(ctx->pipe_overlay[k], overlay_rgba_pinned, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+        MRTX_CUDA(cudaEventRecord(ctx->pipe_ev_upload[k], ctx->copy_stream));
+    }
+    MRTX_CUDA(cudaMemsetAsync(ctx->accum, 0, n * sizeof(float4), ctx->stream));
+    rc = launch_trace(ctx, 0, 0, ctx->width, ctx->height, 0, nsamples);
+    if (rc) return rc;
+    if (overlay_rgba_pinned) MRTX_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->pipe_ev_upload[k], 0));
+    MRTX_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->pipe_ev_d2h[k], 0));      // slot k's output has left the device
+    rc = launch_resolve_to(ctx, overlay_rgba_pinned ? ctx->pipe_overlay[k] : nullptr, ctx->pipe_rgba8[k]);
+    if (rc) return rc;
+    MRTX_CUDA(cudaEventRecord(ctx->pipe_ev_resolve[k], ctx->stream));
+    MRTX_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->pipe_ev_resolve[k], 0));
+    MRTX_CUDA(cudaMemcpyAsync(out_rgba_pinned, ctx->pipe_rgba8[k], bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    MRTX_CUDA(cudaEventRecord(ctx->pipe_ev_d2h[k], ctx->copy_stream));
+    *ticket = k;
+    return MRTX_OK;
+}
+
+int mrtx_frame_wait(mrtx_ctx* ctx, int ticket) {
+    MRTX_CTX(ctx);
+    MRTX_REQUIRE((ticket == 0 || ticket == 1) && ctx->pipe_ev_d2h[ticket], "no such frame in flight");
+    MRTX_CUDA(cudaEventSynchronize(ctx->pipe_ev_d2h[ticket]));
     return MRTX_OK;
 }
 

@@ -121,6 +121,13 @@ struct mrtx_ctx {
     // wavefront pipeline scratch (allocated on first use): ray / hit records, radiance slots, shadow queue, deferred items
     void* wave_buf; size_t wave_items;
 
+    // pipelined frames (mrtx_frame_submit / mrtx_frame_wait): a copy stream moves frame j's overlay in and frame j-1's
+    // RGBA8 out while the main stream traces; overlay and output are double-buffered, one set of events per slot
+    cudaStream_t copy_stream;
+    uchar4* pipe_overlay[2]; uchar4* pipe_rgba8[2];
+    cudaEvent_t pipe_ev_upload[2], pipe_ev_resolve[2], pipe_ev_d2h[2];
+    int pipe_slot, pipe_w, pipe_h;
+
     // comm
     void* nccl_lib; void* nccl_comm; int nranks, rank;
     void* gather_buf; size_t gather_bytes;
@@ -135,4 +142,5 @@ int launch_synth_color(mrtx_ctx* ctx, uint8_t* out_dev, int W, int H, uint32_t s
 int build_pyramid(mrtx_ctx* ctx);
 int launch_trace(mrtx_ctx* ctx, int x0, int y0, int x1, int y1, unsigned s0, unsigned ns);
 int launch_resolve(mrtx_ctx* ctx);
+int launch_resolve_to(mrtx_ctx* ctx, const uchar4* overlay_dev, uchar4* out_dev);
 void free_heightfield(mrtx_ctx* ctx);

@@ -1403,9 +1403,12 @@ int launch_trace(mrtx_ctx* ctx, int x0, int y0, int x1, int y1, unsigned s0, uns
 }
 
 int launch_resolve(mrtx_ctx* ctx) {
+    return launch_resolve_to(ctx, ctx->tex[1].data, ctx->rgba8);
+}
+
+int launch_resolve_to(mrtx_ctx* ctx, const uchar4* overlay, uchar4* out) {
     const size_t n = (size_t)ctx->width * ctx->height;
-    resolve_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->accum, ctx->tex[1].data, ctx->rgba8, n,
-                                                                ctx->sp.exposure, ctx->sp.inv_gamma);
+    resolve_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->accum, overlay, out, n, ctx->sp.exposure, ctx->sp.inv_gamma);
     MRTX_CUDA(cudaGetLastError());
     return MRTX_OK;
 }

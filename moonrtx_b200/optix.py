@@ -74,6 +74,7 @@ class B200OptiX:
         self._thread = None
         self._encoder = None
         self._frames_rendered = 0
+        self._frames_submitted = 0
         self.deterministic = None      # None: jitter iff max_accumulation_frames > 1
         _lib.check(self._lib.mrtx_resize(self._ctx, self._width, self._height))
         self._push_camera()
@@ -375,6 +376,56 @@ class B200OptiX:
             if self._accum_done_cb is not None:
                 self._accum_done_cb(self)
             return self._img_rgba if read_back else None
+
+    # ---- pipelined frames (time-lapse export) --------------------------------------------------------
+    def submit_frame(self, overlay: Optional[np.ndarray] = None) -> int:
+        """
+        Queue one whole accumulation cycle of the scene as it is now and return at once: overlay upload (an RGBA8
+        [H, W, 4] array, copied to pinned memory here; None = no overlay), tracing, resolve and read-back run on the
+        GPU while the caller prepares the next frame.  At most two frames are in flight.  Returns a ticket for
+        wait_frame().  The F11 loop of renderer_video.py (overlay, update_view, accumulate, grab) maps to
+        submit_frame(i + 1) before wait_frame(i).
+        """
+        with self._padlock:
+            if not hasattr(self, "_pipe_out"):
+                shape = (self._height, self._width, 4)
+                self._pipe_out = [self.pinned_empty(shape, np.uint8) for _ in range(2)]
+                self._pipe_ovl = [self.pinned_empty(shape, np.uint8) for _ in range(2)]
+                self._pipe_next = 0
+            k = self._pipe_next
+            n = max(1, int(self._params["max_accumulation_frames"]))
+            jitter = (n > 1) if self.deterministic is None else (not self.deterministic)
+            _lib.check(self._lib.mrtx_set_uint(self._ctx, b"jitter", 1 if jitter else 0, 0))
+            ov_ptr = None
+            if overlay is not None:
+                if overlay.shape != self._pipe_ovl[k].shape or overlay.dtype != np.uint8:
+                    raise ValueError(f"overlay must be uint8 {self._pipe_ovl[k].shape}")
+                # (the library's slot k was last read two submits ago: wait_frame(k) has been called since, or is now)
+                if self._frames_submitted >= 2:
+                    _lib.check(self._lib.mrtx_frame_wait(self._ctx, k))
+                np.copyto(self._pipe_ovl[k], overlay)
+                ov_ptr = self._pipe_ovl[k].ctypes.data
+            ticket = C.c_int()
+            _lib.check(self._lib.mrtx_frame_submit(self._ctx, ov_ptr, n, self._pipe_out[k].ctypes.data, C.byref(ticket)))
+            assert ticket.value == k
+            self._pipe_next ^= 1
+            self._frames_submitted += 1
+            return k
+
+    def wait_frame(self, ticket: int) -> np.ndarray:
+        """Block until the frame of submit_frame() is in host memory; the returned array (pinned, [H, W, 4] uint8) is
+        reused by the submit after next.  Fires the launch-finished / accumulation-done callbacks like render_cycle."""
+        _lib.check(self._lib.mrtx_frame_wait(self._ctx, int(ticket)))
+        img = self._pipe_out[int(ticket)]
+        with self._padlock:
+            self._frames_rendered += 1
+            if self._encoder is not None:
+                self._encoder.grab(img)
+            if self._on_launch_finished is not None:
+                self._on_launch_finished(self)
+            if self._accum_done_cb is not None:
+                self._accum_done_cb(self)
+        return img
 
     def _run(self):
         while not self._stop.is_set():

@@ -70,13 +70,33 @@ def apply_frame_state(rt, st: FrameState, moon_name: str = "moon", light_name: s
 def render_timelapse(rt, states: Sequence[FrameState], rank: int = 0, world: int = 1,
                      on_frame: Optional[Callable[[int, np.ndarray], None]] = None,
                      overlay_for: Optional[Callable[[int], Optional[np.ndarray]]] = None,
-                     keep: bool = True) -> dict[int, np.ndarray]:
+                     keep: bool = True, pipelined: bool = False) -> dict[int, np.ndarray]:
     """
     Render this rank's share of a time-lapse.  Each frame is one full accumulation cycle
     (rt.set_param(max_accumulation_frames=...) applies), exactly as the reference lets every
     frame converge before the encoder grabs it.  Returns {frame index: RGBA8 image}.
+
+    pipelined=True: frame i + 1 is submitted before frame i is waited for (B200OptiX.submit_frame /
+    wait_frame), so the overlay upload and the frame read-back overlap the tracing; same pixels.
     """
     out: dict[int, np.ndarray] = {}
+    if pipelined:
+        pending = None                                      # (frame index, ticket)
+        def finish(p):
+            img = rt.wait_frame(p[1])
+            if on_frame is not None:
+                on_frame(p[0], img)
+            if keep:
+                out[p[0]] = img.copy()
+        for i in frames_of_rank(len(states), rank, world):
+            apply_frame_state(rt, states[i])
+            ticket = rt.submit_frame(overlay_for(i) if overlay_for is not None else None)
+            if pending is not None:
+                finish(pending)
+            pending = (i, ticket)
+        if pending is not None:
+            finish(pending)
+        return out
     for i in frames_of_rank(len(states), rank, world):
         if overlay_for is not None:
             ov = overlay_for(i)
