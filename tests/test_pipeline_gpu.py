@@ -63,3 +63,52 @@ def test_submit_without_overlay_and_callbacks():
     with pytest.raises(ValueError):
         rt.submit_frame(np.zeros((3, 3, 4), np.uint8))
     rt.close()
+
+
+def test_pipelined_frames_with_a_busy_referee_and_synchronous_calls_in_between():
+    """Frames with a long referee phase (nearly every ray goes through it: long_walk = 2, tiny budgets) queued back to
+    back, with synchronous calls (render_cycle, counters, hit read-back, texture updates) thrown in between."""
+    from moonrtx_b200 import scene
+    from moonrtx_b200.synth import synth_ephemeris, synth_ldem
+    from moonrtx_b200.data_loader import downscale_elevation
+    from moonrtx_b200.video import apply_frame_state
+    elev, _ = downscale_elevation(synth_ldem(1440, 720, seed=11, craters=40), 2)
+    W, H, n = 200, 120, 6
+    states = [scene.frame_state(synth_ephemeris(900.0 * i)) for i in range(n)]
+
+    def new_rt():
+        rt = make_gpu(elev, W, H, debug_hits=False, light_pos=sun_at_phase(90.0))
+        rt.set_param(min_accumulation_step=1, max_accumulation_frames=3)
+        rt.set_uint("long_walk", 2)
+        rt.set_uint("referee_budget", 8)
+        return rt
+
+    rt = new_rt()
+    ref = []
+    for i in range(n):
+        apply_frame_state(rt, states[i])
+        ref.append(rt.render_cycle().copy())
+    rt.close()
+
+    rt = new_rt()
+    got = {}
+    pending = None
+    for i in range(n):
+        apply_frame_state(rt, states[i])
+        t = rt.submit_frame()
+        if pending is not None:
+            got[pending[0]] = rt.wait_frame(pending[1]).copy()
+        pending = (i, t)
+        if i == 2:                                           # synchronous work in the middle of the pipeline
+            got[pending[0]] = rt.wait_frame(pending[1]).copy(); pending = None
+            mid = rt.render_cycle().copy()
+            assert np.array_equal(mid, ref[2])
+            assert rt.counters()["primary_rays"] > 0
+            rt._get_hit_at(W // 2, H // 2)
+            rt.set_texture_2d("moon_color", np.full((8, 16, 4), 200, np.uint8))
+            rt.set_texture_2d("moon_color", np.full((8, 16, 4), 255, np.uint8))
+    got[pending[0]] = rt.wait_frame(pending[1]).copy()
+    rt.close()
+    # (frames 3.. were rendered with the white 8 x 16 albedo texture set in between: same as no texture)
+    for i in range(n):
+        assert np.array_equal(got[i], ref[i]), f"frame {i} differs"
