@@ -292,7 +292,7 @@ MRTX_HD inline float ray_r2(const Trav& T, float s) { return fmaf(s, fmaf(2.0f, 
 // wall).  A point within `tol` of a wall counts as ON it and the direction of travel decides:
 // moving outward -> leave now, moving inward -> stay.  Both cells that share a wall evaluate the
 // same q with opposite sign, so a ray handed across a wall can never be handed straight back.
-MRTX_HD float cell_exit32(const HeightField& hf, const Trav& T, int L, int J, int I, float s, int& face) {
+MRTX_HD inline float cell_exit32(const HeightField& hf, const Trav& T, int L, int J, int I, float s, int& face) {
     const int W = hf.W, H = hf.H;
     const int a = I << L, b = min((I + 1) << L, W);
     const int n = J << L, m = min((J + 1) << L, H - 1);
