@@ -41,6 +41,7 @@ void mrtx_set_error(const char* fmt, ...);
 
 // ---- scene state ------------------------------------------------------------------
 #define MRTX_MAX_LEVELS 20
+#define MRTX_DIL_MIN_LEVEL 2     // lowest level that has a dilated copy (beam pre-pass)
 
 // Height field + max pyramid as the kernels see it.  Level 0 (the 2x2-corner max of
 // every bilinear patch) is never stored: the patch's own four texels give it.
@@ -53,6 +54,7 @@ struct HeightField {
     int   top;                  // highest level used by traversal (0 = plain DDA)
     float scale, radius_scale;  // int16 decode: D = ((c*scale)+1)/radius_scale, each op f32
     const void* level[MRTX_MAX_LEVELS];   // level[k], k = 1..top; same dtype as base
+    const void* dil[MRTX_MAX_LEVELS];     // dil[k], k = MRTX_DIL_MIN_LEVEL..top: level k dilated by one cell (pyramid.cu)
     int   nx[MRTX_MAX_LEVELS], ny[MRTX_MAX_LEVELS];   // cells per level (level 0: W, H-1)
     float dmax, dmin;           // global max / min displacement factor
     // wall tables (one allocation, hf_tables_owned): cell walls are the half-planes of constant
@@ -85,6 +87,9 @@ struct SceneParams {
     unsigned jitter, shadows, debug_hits;
     unsigned start_primary, start_shadow;   // filtered kernel: primary rays start at level top - start_primary, shadow rays at start_shadow
     unsigned long_walk, referee_budget;     // walks longer than long_walk nodes go to the referee; a referee lane spends referee_budget on a piece
+    unsigned shadow_queue;                  // shadow rays through the streaming queue kernel (default) or inside trace_kernel_fast
+    unsigned ceiling;                       // shadow rays: ceiling test from this level upwards (0 = off)
+    unsigned beam, beam_drop;               // beam pre-pass of the filtered kernel (launches of >= 4 samples); samples start beam_drop levels below the beam's
     unsigned kernel;                        // 2 = filtered float32 kernel + exact kernel on what it defers (default),
                                             // 1 = exact persistent kernel only, 0 = exact, one thread per pixel
 };
@@ -118,6 +123,10 @@ struct mrtx_ctx {
     unsigned* d_work;           // trace work counter + list length
     unsigned* pixel_list;       // width * height entries
     uint2* defer_list;          // width * height entries: samples the filtered kernel hands to the exact one
+    unsigned long long* accfix; // 3 * width * height: order-independent radiance sums of a launch (folded into accum at its end)
+    void* sq_buf; size_t sq_cap; // shadow queue (allocated on first use): sq_cap ray records + aux entries
+    double* beam_s;             // width * height entries (by position in the pixel list): where the pixel's samples start ...
+    unsigned char* beam_l;      // ... and the level the beam pre-pass stopped at
     // wavefront pipeline scratch (allocated on first use): ray / hit records, radiance slots, shadow queue, deferred items
     void* wave_buf; size_t wave_items;
 

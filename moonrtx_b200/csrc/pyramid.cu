@@ -42,6 +42,25 @@ __global__ void levelk_kernel(const T* __restrict__ in, int inx, int iny, T* __r
     out[idx] = m;
 }
 
+// dil[k](J, I) = max of level k over the cell and its neighbours (reach cells either side in longitude, wrapping; one
+// row either side, clamped): an upper bound of the surface for every direction within one level-k cell of the cell.
+// The beam pre-pass walks these levels with the CENTRE ray of a pixel (trace_fast.cuh, BeamCtl).
+template <typename T>
+__global__ void dilate_kernel(const T* __restrict__ in, int nx, int ny, int reach, T* __restrict__ out) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)nx * ny) return;
+    const int J = (int)(idx / nx), I = (int)(idx - (long long)J * nx);
+    T m = in[idx];
+    for (int j = max(J - 1, 0); j <= min(J + 1, ny - 1); ++j)
+        for (int d = -reach; d <= reach; ++d) {
+            int i = I + d;
+            i = i < 0 ? i + nx : (i >= nx ? i - nx : i);
+            const T v = in[(size_t)j * nx + i];
+            m = v > m ? v : m;
+        }
+    out[idx] = m;
+}
+
 // global min / max of the base map, as order-preserving ints
 template <typename T> __device__ __forceinline__ int ordered(T v);
 template <> __device__ __forceinline__ int ordered<int16_t>(int16_t v) { return (int)v; }
@@ -112,6 +131,7 @@ int build_levels(mrtx_ctx* ctx) {
         hf.nx[k] = (W + (1 << k) - 1) >> k;
         hf.ny[k] = (H - 1 + (1 << k) - 1) >> k;
         total += (((size_t)hf.nx[k] * hf.ny[k] * sizeof(T)) + 255) & ~(size_t)255;
+        if (k >= MRTX_DIL_MIN_LEVEL) total += (((size_t)hf.nx[k] * hf.ny[k] * sizeof(T)) + 255) & ~(size_t)255;
     }
     cudaStream_t st = ctx->stream;
     if (top > 0) {
@@ -130,6 +150,15 @@ int build_levels(mrtx_ctx* ctx) {
             const long long n = (long long)hf.nx[k] * hf.ny[k];
             levelk_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const T*)hf.level[k - 1], hf.nx[k - 1], hf.ny[k - 1],
                                                                           (T*)hf.level[k], hf.nx[k], hf.ny[k]);
+        }
+        // dilated copies of levels >= MRTX_DIL_MIN_LEVEL (a level whose last column is a partial cell dilates by two)
+        for (int k = 1; k <= top; ++k) hf.dil[k] = nullptr;
+        for (int k = MRTX_DIL_MIN_LEVEL; k <= top; ++k) {
+            hf.dil[k] = p;
+            p += (((size_t)hf.nx[k] * hf.ny[k] * sizeof(T)) + 255) & ~(size_t)255;
+            const long long n = (long long)hf.nx[k] * hf.ny[k];
+            const int reach = ((long long)hf.nx[k] << k) != W ? 2 : 1;
+            dilate_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const T*)hf.level[k], hf.nx[k], hf.ny[k], reach < hf.nx[k] / 2 ? reach : hf.nx[k] / 2, (T*)hf.dil[k]);
         }
         MRTX_CUDA(cudaGetLastError());
     }

@@ -22,31 +22,75 @@
 
 namespace {
 
-// is re-based in float64 per candidate) in one tenth of the instructions, and is laid out for the SIMD
-// width instead of around it:
-//   * a warp owns 32 >> g_log2 neighbouring pixels, 2^g_log2 lanes share one pixel and trace one sample each,
-//     so the lanes of a warp walk the same pyramid nodes (coherent loads, similar trip counts);
-//   * while-while: lanes traverse until each holds a candidate patch (or has left the sphere), then all
-//     candidates are tested at one instruction; primary and shadow rays run through the same loop body;
-//   * per-pixel sums are reduced with shuffles: one accumulator read-modify-write per pixel;
-//   * warps claim tasks from a counter, so limb / terminator warps that walk hundreds of cells do not leave
-//     SMs idle at the end of the frame.
-// A sample the filter cannot certify (FT_DEFER) contributes nothing here; its bit is set in the pixel's entry of
-// the deferred list and trace_kernel_referee traces it again afterwards.
+// ---- beam pre-pass: one thread per listed pixel (trace_fast.cuh, BeamCtl) -------------------------------------------
+// The samples of a pixel are ~15 texels apart at 4K on the full-resolution map: each walks its own cells near the
+// surface, but above it they all cross the same empty coarse cells.  This pass crosses them ONCE per pixel, with the
+// pixel's centre ray against the dilated pyramid, and leaves for every listed pixel the ray parameter before which no
+// sample of it can be below the surface and the level it stopped at; trace_kernel_fast starts the samples there.
+template <bool I16>
+__global__ void __launch_bounds__(256)
+beam_kernel(const __grid_constant__ RenderArgs A) {
+    const unsigned n_limb = A.work_counter[4];
+    const unsigned nkept = n_limb + A.work_counter[1];
+    Counters cnt = {0u, 0u, 0u};
+    for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < nkept; p += gridDim.x * blockDim.x) {
+        const unsigned packed = list_pixel(A, p, n_limb);
+        const int x = (int)(packed & 0xffffu), y = (int)(packed >> 16);
+        Ray64 C;
+        primary_ray_at(A, x, y, 0.5, 0.5, C);
+        // half diagonal of a pixel in the image plane at distance 1 (an upper bound of the angle, the plane's points
+        // being at distance >= 1 from the eye)
+        const double delta = A.cam.tan_half_fov / (double)A.height * 1.4142135623730951;
+        double s_start = 0.0;
+        int level = A.hf.top;
+        const bool alive = beam_walk<I16>(A.hf, A.K, A.sp.radius, C, delta, s_start, level, cnt);
+        A.beam_s[p] = alive ? s_start : 1.0e300;
+        A.beam_l[p] = (unsigned char)level;
+    }
+    const unsigned nodes = __reduce_add_sync(0xffffffffu, cnt.nodes);
+    if ((threadIdx.x & 31) == 0 && nodes) atomicAdd(&A.counters[5], (unsigned long long)nodes);
+}
+
+// ---- production kernels --------------------------------------------------------------------------------------------
+// trace_kernel_fast runs the arithmetic of the filtered float32 path (trace_fast.cuh; every candidate patch is re-based in
+// float64) laid out for the SIMD width:
+//   * a warp owns 32 >> g_log2 neighbouring pixels, 2^g_log2 lanes share one pixel and trace one sample each, so the
+//     lanes of a warp walk the same pyramid nodes (coherent loads, similar trip counts: measured 67 % of the lanes of
+//     a primary walk phase are busy);
+//   * while-while: lanes traverse until each holds a candidate patch (or has left the sphere), then all candidates are
+//     tested at one instruction;
+//   * warps claim tasks from a counter, so limb warps that walk hundreds of cells do not leave SMs idle at the end.
+// Shadow rays are a different population: next to the terminator one lane's sun ray clears the relief after ten nodes
+// and its neighbour's skims it for three hundred.  Traced inside the same warp they kept 28 % of the lanes busy
+// (measured: 60 % of all walk iterations of a frame for 38 % of its nodes).  With QUEUE the kernel therefore stops at
+// the shaded hit: the shadow ray, set up to its first cell, goes to a queue in HBM as a 64-byte record (+ 16 bytes:
+// the radiance it carries if the sun is visible, pixel and sample), and shadow_kernel streams the queue with lane
+// refill - a lane whose ray is decided takes the next record.  Queue order is push order, i.e. the 32 rays of a warp's
+// pixels stay together at first.  The radiance of a visible sample is added to the pixel with 64-bit fixed-point atomics
+// (accfix_add): integer sums do not depend on their order, so the frame stays reproducible bit for bit.
+// A sample the filter cannot certify (FT_DEFER, primary or shadow ray) contributes nothing here; it goes on the
+// deferred list and trace_kernel_referee traces it again from the camera.
+#ifndef MRTX_PHASE_STATS
+#define MRTX_PHASE_STATS 0
+#endif
 #ifndef MRTX_FAST_MINBLOCKS
 #define MRTX_FAST_MINBLOCKS 8
 #endif
-template <bool I16>
+template <bool I16, bool QUEUE>
 __global__ void __launch_bounds__(128, MRTX_FAST_MINBLOCKS)
 trace_kernel_fast(const __grid_constant__ RenderArgs A) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
     const int gl = A.g_log2, g = 1 << gl;
     const int sub = lane & (g - 1), pw = lane >> gl;         // lane within the pixel's group, pixel within the warp
     const unsigned ppw = 32u >> gl;
     const unsigned n_limb = A.work_counter[4];
     const unsigned nkept = n_limb + A.work_counter[1];
-    const unsigned ntasks = (nkept + ppw - 1u) / ppw;
+    // this launch's part of the pixel list (waves bound the shadow queue)
+    const unsigned p_end = min(nkept, A.wave_p0 + A.wave_np);
+    if (A.wave_p0 >= p_end) return;
+    const unsigned ntasks = (p_end - A.wave_p0 + ppw - 1u) / ppw;
     const float Rf = A.K.R;
     const unsigned rounds = (A.nsamples + (unsigned)g - 1u) >> gl;
 
@@ -59,13 +103,20 @@ trace_kernel_fast(const __grid_constant__ RenderArgs A) {
         if (lane == 0) task = atomicAdd(&A.work_counter[2], 1u);
         task = __shfl_sync(FULL, task, 0);
         if (task >= ntasks) break;
-        const unsigned p = task * ppw + (unsigned)pw;
-        const bool valid = p < nkept;
+        const unsigned p = A.wave_p0 + task * ppw + (unsigned)pw;
+        const bool valid = p < p_end;
         const unsigned packed = valid ? list_pixel(A, p, n_limb) : 0u;
         const int x = (int)(packed & 0xffffu), y = (int)(packed >> 16);
         const uint32_t pixel = (uint32_t)y * (uint32_t)A.width + (uint32_t)x;
         float3 acc = make_float3(0.f, 0.f, 0.f);
         unsigned dmask = 0;                                  // group leader: deferred samples of this pixel
+        // where the beam pre-pass lets this pixel's samples start (no pre-pass: at the bounding sphere, level top - start_primary)
+        double s_beam = 0.0;
+        int lvl_primary = A.hf.top - (int)A.sp.start_primary;
+        if (A.beam_s && valid) {
+            s_beam = A.beam_s[p];
+            if (s_beam > 0.0) lvl_primary = max((int)A.beam_l[p] - A.beam_drop, 0);
+        }
 
 #pragma unroll 1
         for (unsigned rd = 0; rd < rounds; ++rd) {
@@ -78,28 +129,57 @@ trace_kernel_fast(const __grid_constant__ RenderArgs A) {
             float3 lit = make_float3(0.f, 0.f, 0.f);
             bool defer = false, want = active, hit = false, entered = false, occluded = false, shadowed = false;
 #pragma unroll 1
-            for (int pass = 0; pass < 2; ++pass) {           // 0: primary ray, 1: shadow ray
+            for (int pass = 0; pass < (QUEUE ? 1 : 2); ++pass) {        // 0: primary ray, 1: shadow ray (in-kernel form)
                 bool alive = false;
                 if (want) {
                     if (pass == 0) primary_ray_fast(A, x, y, pixel, sm, R);
-                    alive = walk_begin(A.hf, A.sp.radius, R, 0.0, pass ? (int)A.sp.start_shadow : A.hf.top - (int)A.sp.start_primary, st);
-                    if (pass == 0) entered = alive;
+                    const int wb = walk_begin2(A.hf, A.sp.radius, R, pass ? 0.0 : s_beam, pass ? (int)A.sp.start_shadow : lvl_primary, st);
+                    alive = wb == 2;
+                    if (pass == 0) entered = wb != 0;
                 }
                 int res = FT_MISS;
+                int ceil_next = pass && A.sp.ceiling ? (int)A.sp.ceiling : 0x7fffffff;
                 while (__any_sync(FULL, alive)) {
                     RawPatch P;
                     float sx = 0.f;
                     int face = 4;
                     bool cand = false;
-                    if (alive) {
-                        for (;;) {
-                            const int r = walk_step<I16>(A.hf, Rf, A.inv_rs, st, P, sx, face, cnt);
-                            if (r == TR_CONTINUE) continue;
-                            if (r == TR_END) alive = false; else cand = true;
-                            break;
+#if MRTX_PHASE_STATS
+                    const int steps0 = alive ? st.steps : 0;
+                    const bool was_alive = alive;
+#endif
+                    // walk phase, in lockstep: one node per lane and iteration, the vote at the loop head brings the warp
+                    // back together after every node (left to itself the compiler lets lanes that took different
+                    // branches of a node run on separately: measured 4 lanes per instruction in walk_step)
+                    while (__any_sync(FULL, alive && !cand)) {
+                        if (alive && !cand) {
+                            bool clear = false;
+                            if (!QUEUE && st.L >= ceil_next) {
+                                ceil_next = st.L + 2;
+                                clear = ceiling_clear<I16>(A.hf, A.K, A.inv_rs, st, A.hf.dmin);
+                            }
+                            if (clear) alive = false;
+                            else {
+                                const int r = walk_step<I16>(A.hf, Rf, A.inv_rs, st, P, sx, face, cnt);
+                                if (r == TR_END) alive = false;
+                                else if (r == TR_CANDIDATE) cand = true;
+                            }
                         }
                     }
-                    __syncwarp();
+#if MRTX_PHASE_STATS
+                    {
+                        const unsigned dn = was_alive ? (unsigned)(st.steps - steps0) : 0u;
+                        const unsigned mx = __reduce_max_sync(FULL, dn), sm_ = __reduce_add_sync(FULL, dn);
+                        const unsigned nt = __popc(__ballot_sync(FULL, cand)), na = __popc(__ballot_sync(FULL, was_alive));
+                        if (lane == 0) {
+                            atomicAdd(&A.counters[pass ? 12 : 10], (unsigned long long)mx);
+                            atomicAdd(&A.counters[pass ? 13 : 11], (unsigned long long)sm_);
+                            if (nt) { atomicAdd(&A.counters[8], 1ull); atomicAdd(&A.counters[9], (unsigned long long)nt); }
+                            atomicAdd(&A.counters[14], (unsigned long long)na);     // lanes alive at the start of walk phases ...
+                            atomicAdd(&A.defer_stats[31], 1ull);                     // ... and the number of walk phases
+                        }
+                    }
+#endif
                     if ((alive || cand) && st.steps > (int)A.sp.long_walk) {
                         res = FT_DEFER; alive = false; cand = false;
                         atomicAdd(&A.defer_stats[15 + (pass ? 16 : 0)], 1ull);
@@ -124,7 +204,23 @@ trace_kernel_fast(const __grid_constant__ RenderArgs A) {
                         shadowed = want;
                         if (want) R = S;
                     }
-                    if (!__any_sync(FULL, want)) break;
+                    if (QUEUE) {
+                        // the shadow ray leaves the kernel here: set up to its first cell, pushed with what it carries
+                        bool push = false;
+                        if (want) push = walk_begin(A.hf, A.sp.radius, R, 0.0, A.sq_level, st);
+                        const unsigned pm = __ballot_sync(FULL, push);
+                        if (pm) {
+                            unsigned base = 0;
+                            if (lane == __ffs(pm) - 1) base = atomicAdd(&A.work_counter[5], (unsigned)__popc(pm));
+                            base = __shfl_sync(FULL, base, __ffs(pm) - 1);
+                            if (push) {
+                                const unsigned j = base + (unsigned)__popc(pm & lt);
+                                store_ray_rec(A.sq_rays + j, R, st, true);
+                                A.sq_aux[j] = make_uint4(__float_as_uint(lit.x), __float_as_uint(lit.y), __float_as_uint(lit.z), pixel | (k << 27));
+                                lit = make_float3(0.f, 0.f, 0.f);            // shadow_kernel adds it if the sun is visible
+                            }
+                        }
+                    } else if (!__any_sync(FULL, want)) break;
                 } else if (want) {
                     occluded = res == FT_HIT;
                 }
@@ -165,6 +261,143 @@ trace_kernel_fast(const __grid_constant__ RenderArgs A) {
     if (lane == 0 && nd) atomicAdd(&A.defer_stats[0], (unsigned long long)nd);
 }
 
+// ---- shadow queue: streaming walk with lane refill -------------------------------------------------------------------
+// Each lane owns one queued shadow ray at a time.  Only the float32 walk state lives in registers; the float64 ray is read
+// back from its record for the patch tests (about one per ten rays).  Walk steps and patch tests alternate warp-wide:
+// a test phase runs once enough lanes hold a candidate, empty lanes are refilled four at a time with one atomic.
+#ifndef MRTX_SQ_MINBLOCKS
+#define MRTX_SQ_MINBLOCKS 8
+#endif
+#ifndef MRTX_SQ_CAND
+#define MRTX_SQ_CAND 12
+#endif
+#ifndef MRTX_SQ_REFILL
+#define MRTX_SQ_REFILL 4
+#endif
+enum { SQ_EMPTY = 0, SQ_WALK = 1, SQ_CAND = 2 };
+
+template <bool I16>
+__global__ void __launch_bounds__(128, MRTX_SQ_MINBLOCKS)
+shadow_kernel(const __grid_constant__ RenderArgs A) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const unsigned n_items = A.work_counter[5];
+    unsigned* const queue = A.work_counter + 6;
+    const float Rf = A.K.R;
+    Counters cnt = {0u, 0u, 0u};
+    unsigned n_defer = 0, n_occluded = 0;
+
+    int mode = SQ_EMPTY, face = 4;
+    int ceil_next = 0x7fffffff;
+    unsigned ridx = 0;
+    Walk st;
+    RawPatch P;
+    float sx = 0.f;
+    bool exhausted = false;
+
+    for (;;) {
+        const unsigned m_walk = __ballot_sync(FULL, mode == SQ_WALK);
+        const unsigned m_cand = __ballot_sync(FULL, mode == SQ_CAND);
+        const unsigned m_empty = ~(m_walk | m_cand);
+        const bool idle = (m_walk | m_cand) == 0u;
+        if (!exhausted && (idle || __popc(m_empty) >= MRTX_SQ_REFILL)) {
+            // ---- refill: the next rays of the queue, one atomic per warp
+            const unsigned n = (unsigned)__popc(m_empty);
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(queue, n);
+            base = __shfl_sync(FULL, base, 0);
+            if (base + n >= n_items) exhausted = true;
+            const unsigned idx = base + (unsigned)__popc(m_empty & lt);
+            if (mode == SQ_EMPTY && idx < n_items) {
+                const RayRec* rec = A.sq_rays + idx;
+                const double2 tail = __ldg((const double2*)rec + 3);
+                const float smax = __int_as_float(__double2loint(tail.y));
+                const unsigned cell = (unsigned)__double2hiint(tail.y);
+                Ray64 R;
+                load_ray_rec(rec, R);
+                walk_setup(R, tail.x, smax, st);
+                st.L = A.sq_level; st.J = (int)(cell >> 16); st.I = (int)(cell & 0xffffu);
+                st.s = 0.0f; st.steps = 0;
+                ridx = idx;
+                mode = SQ_WALK;
+                ceil_next = A.sp.ceiling ? (int)A.sp.ceiling : 0x7fffffff;
+            }
+            continue;
+        }
+        if (idle) break;
+        bool finished = false;
+        int status = FT_MISS;
+        if (__popc(m_cand) >= MRTX_SQ_CAND || __popc(m_cand) >= __popc(m_walk)) {
+            // ---- patch test (any crossing occludes)
+            if (mode == SQ_CAND) {
+                ++cnt.tests;
+                const RayRec* rec = A.sq_rays + ridx;
+                Ray64 R;
+                load_ray_rec(rec, R);
+                FastHit fh;
+                status = fast_test<I16>(A.hf, A.K, R, st.s_in, 0.0, st.s, sx, st.smax, P, true, fh);
+                if (status == FT_MISS && walk_advance(A.hf, st, sx, face)) mode = SQ_WALK;
+                else finished = true;
+            }
+        } else if (mode == SQ_WALK) {
+            // ---- walk step
+            if (st.L >= ceil_next) {
+                ceil_next = st.L + 2;
+                if (ceiling_clear<I16>(A.hf, A.K, A.inv_rs, st, A.hf.dmin)) finished = true;
+            }
+            if (!finished) {
+                const int r = walk_step<I16>(A.hf, Rf, A.inv_rs, st, P, sx, face, cnt);
+                if (r == TR_END) finished = true;
+                else if (st.steps > (int)A.sp.long_walk) { finished = true; status = FT_DEFER_R(15); }
+                else if (r == TR_CANDIDATE) mode = SQ_CAND;
+            }
+        }
+        if (finished) {
+            mode = SQ_EMPTY;
+            const uint4 aux = __ldg(A.sq_aux + ridx);
+            const uint32_t pixel = aux.w & 0x7ffffffu;
+            if (status == FT_MISS) {
+                accfix_add(A.accfix, pixel, make_float3(__uint_as_float(aux.x), __uint_as_float(aux.y), __uint_as_float(aux.z)));
+            } else if ((status & 3) == FT_HIT) ++n_occluded;
+            else {
+                // undecided: the referee traces the whole sample again from the camera
+                atomicAdd(&A.defer_stats[16 + (status >> 2)], 1ull);
+                const unsigned slot = atomicAdd(&A.work_counter[3], 1u);
+                const unsigned px = pixel % (unsigned)A.width, py = pixel / (unsigned)A.width;
+                if (slot < A.list_cap) A.defer_list[slot] = make_uint2(px | (py << 16), 1u << (aux.w >> 27));
+                ++n_defer;
+            }
+        }
+    }
+    const RayStats rs = {0u, 0u, 0u, 0u, n_occluded};
+    flush_counters(A, rs, cnt, lane);
+    const unsigned nd = __reduce_add_sync(FULL, n_defer);
+    if (lane == 0 && nd) {
+        // the referee counts these samples again: take back what trace_kernel_fast counted for them
+        const unsigned long long neg = 0ull - (unsigned long long)nd;
+        atomicAdd(&A.defer_stats[0], (unsigned long long)nd);
+        atomicAdd(&A.counters[0], neg); atomicAdd(&A.counters[1], neg); atomicAdd(&A.counters[2], neg); atomicAdd(&A.counters[3], neg);
+    }
+}
+
+// fixed-point sums of the launch -> float accumulators (and cleared for the next launch)
+__global__ void __launch_bounds__(256)
+fold_kernel(float4* __restrict__ accum, unsigned long long* __restrict__ accfix, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        unsigned long long* a = accfix + i * 3;
+        const unsigned long long r = a[0], g = a[1], b = a[2];
+        if (r | g | b) {
+            float4 v = accum[i];
+            v.x += (float)((double)r * (1.0 / (double)ACCFIX_SCALE));
+            v.y += (float)((double)g * (1.0 / (double)ACCFIX_SCALE));
+            v.z += (float)((double)b * (1.0 / (double)ACCFIX_SCALE));
+            accum[i] = v;
+            a[0] = 0ull; a[1] = 0ull; a[2] = 0ull;
+        }
+    }
+}
+
 // K8: Gamma post-process + Overlay alpha blend -> RGBA8
 __global__ void resolve_kernel(const float4* __restrict__ accum, const uchar4* __restrict__ overlay,
                                uchar4* __restrict__ out, size_t n, float exposure, float inv_gamma) {
@@ -194,40 +427,94 @@ __global__ void resolve_kernel(const float4* __restrict__ accum, const uchar4* _
 
 }  // namespace
 
-int launch_trace(mrtx_ctx* ctx, int x0, int y0, int x1, int y1, unsigned s0, unsigned ns) {
-    unsigned kernel = ctx->sp.kernel;
-    if (kernel >= 2 && !make_fast_consts(ctx->hf, ctx->sp.radius).enabled) kernel = 1;   // map too coarse for the filter: everything would defer
-    if (kernel != 2) return launch_trace_alt(ctx, x0, y0, x1, y1, s0, ns, kernel);
-    RenderArgs A;
-    fill_render_args(ctx, x0, y0, x1, y1, s0, ns, A);
-    const bool i16 = ctx->hf.is_i16 != 0;
+// shadow queue: ray records and their aux entries in one allocation
+static int ensure_shadow_queue(mrtx_ctx* ctx, size_t items) {
+    if (ctx->sq_cap >= items) return MRTX_OK;
+    MRTX_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->sq_buf);
+    ctx->sq_buf = nullptr; ctx->sq_cap = 0;
+    MRTX_CUDA(cudaMalloc(&ctx->sq_buf, items * (sizeof(RayRec) + sizeof(uint4))));
+    ctx->sq_cap = items;
+    return MRTX_OK;
+}
+
+template <bool I16, bool QUEUE>
+static int launch_fast(mrtx_ctx* ctx, RenderArgs& A, long long npix) {
+    int per_sm = 0;
+    MRTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel_fast<I16, QUEUE>, 128, 0));
+    if (per_sm < 1) per_sm = 1;
+    const long long warps_needed = ((npix << A.g_log2) + 31) / 32;
+    long long blocks = (long long)ctx->sm_count * per_sm;
+    if (blocks * 4 > warps_needed) blocks = (warps_needed + 3) / 4;
+    if (blocks < 1) blocks = 1;
+    trace_kernel_fast<I16, QUEUE><<<(unsigned)blocks, 128, 0, ctx->stream>>>(A);
+    return MRTX_OK;
+}
+
+template <bool I16>
+static int launch_trace_t(mrtx_ctx* ctx, RenderArgs& A, unsigned s0, unsigned ns) {
     int rc = launch_cull(ctx, A);
     if (rc) return rc;
-    const long long npix = (long long)(x1 - x0) * (y1 - y0);
-    // filtered kernel in chunks of <= 32 samples (one mask bit per sample in the deferred list), each
-    // followed by the referee kernel over whatever it deferred
-    int per_sm = 0;
-    if (i16) MRTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel_fast<true>, 128, 0));
-    else     MRTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel_fast<false>, 128, 0));
-    if (per_sm < 1) per_sm = 1;
+    const long long npix = (long long)(A.x1 - A.x0) * (A.y1 - A.y0);
+    if (ctx->sp.beam && ctx->sp.jitter && ns >= 4u && ctx->hf.top >= MRTX_DIL_MIN_LEVEL) {
+        A.beam_s = ctx->beam_s; A.beam_l = ctx->beam_l;
+        const unsigned blocks = (unsigned)std::min<long long>((npix + 255) / 256, (long long)ctx->sm_count * 16);
+        beam_kernel<I16><<<blocks, 256, 0, ctx->stream>>>(A);
+    }
+    const bool queue = ctx->sp.shadow_queue != 0 && ctx->sp.shadows != 0;
+    const size_t SQ_MAX = (size_t)1 << 26;                  // 64 Mi queued rays = 5 GiB; larger launches run in waves of pixels
+    int sq_blocks = 0;
+    if (queue) {
+        const size_t chunk = ns < 32u ? ns : 32u;
+        rc = ensure_shadow_queue(ctx, std::min<size_t>((size_t)npix * chunk, SQ_MAX));
+        if (rc) return rc;
+        A.sq_rays = (RayRec*)ctx->sq_buf;
+        A.sq_aux = (uint4*)((char*)ctx->sq_buf + ctx->sq_cap * sizeof(RayRec));
+        A.sq_cap = (unsigned)ctx->sq_cap;
+        // a ray's first cell travels in 16 + 16 bits: start no lower than the level whose grid fits
+        int lvl = (int)ctx->sp.start_shadow;
+        while ((ctx->hf.W >> lvl) > 65536 && lvl < ctx->hf.top) ++lvl;
+        A.sq_level = std::min(lvl, ctx->hf.top);
+        int per_sm = 0;
+        MRTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shadow_kernel<I16>, 128, 0));
+        sq_blocks = ctx->sm_count * (per_sm < 1 ? 1 : per_sm);
+    }
+    // chunks of <= 32 samples (one mask bit per sample in the deferred list); within a chunk, waves of pixels that the
+    // shadow queue can hold; each followed by the referee over whatever was deferred, and the fold of the fixed-point sums
     for (unsigned done = 0; done < ns; done += 32u) {
         const unsigned n = ns - done < 32u ? ns - done : 32u;
         A.sample0 = s0 + done; A.nsamples = n;
         int gl = 0;
         while ((2u << gl) <= n && gl < 5) ++gl;
         A.g_log2 = gl;
-        if (done) MRTX_CUDA(cudaMemsetAsync(A.work_counter + 2, 0, 2 * sizeof(unsigned), ctx->stream));
-        const long long warps_needed = ((npix << gl) + 31) / 32;
-        long long blocks = (long long)ctx->sm_count * per_sm;
-        if (blocks * 4 > warps_needed) blocks = (warps_needed + 3) / 4;
-        if (blocks < 1) blocks = 1;
-        if (i16) trace_kernel_fast<true><<<(unsigned)blocks, 128, 0, ctx->stream>>>(A);
-        else     trace_kernel_fast<false><<<(unsigned)blocks, 128, 0, ctx->stream>>>(A);
-        if (i16) trace_kernel_referee<true, false><<<ctx->sm_count * 8, 64, 0, ctx->stream>>>(A);
-        else     trace_kernel_referee<false, false><<<ctx->sm_count * 8, 64, 0, ctx->stream>>>(A);
+        const long long wave_np = queue ? (long long)(ctx->sq_cap / n) : npix;
+        for (long long p0 = 0; p0 < npix; p0 += wave_np) {              // waves past the end of the list return at once
+            A.wave_p0 = (unsigned)p0; A.wave_np = (unsigned)std::min<long long>(wave_np, npix - p0);
+            if (done || p0) {
+                MRTX_CUDA(cudaMemsetAsync(A.work_counter + 2, 0, 2 * sizeof(unsigned), ctx->stream));
+                MRTX_CUDA(cudaMemsetAsync(A.work_counter + 5, 0, 2 * sizeof(unsigned), ctx->stream));
+            }
+            rc = queue ? launch_fast<I16, true>(ctx, A, A.wave_np) : launch_fast<I16, false>(ctx, A, A.wave_np);
+            if (rc) return rc;
+            if (queue) shadow_kernel<I16><<<sq_blocks, 128, 0, ctx->stream>>>(A);
+            trace_kernel_referee<I16, false><<<ctx->sm_count * 8, 64, 0, ctx->stream>>>(A);
+        }
+    }
+    {
+        const size_t n = (size_t)ctx->width * ctx->height;
+        fold_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->accum, ctx->accfix, n);
     }
     MRTX_CUDA(cudaGetLastError());
     return MRTX_OK;
+}
+
+int launch_trace(mrtx_ctx* ctx, int x0, int y0, int x1, int y1, unsigned s0, unsigned ns) {
+    unsigned kernel = ctx->sp.kernel;
+    if (kernel >= 2 && !make_fast_consts(ctx->hf, ctx->sp.radius).enabled) kernel = 1;   // map too coarse for the filter: everything would defer
+    if (kernel != 2) return launch_trace_alt(ctx, x0, y0, x1, y1, s0, ns, kernel);
+    RenderArgs A;
+    fill_render_args(ctx, x0, y0, x1, y1, s0, ns, A);
+    return ctx->hf.is_i16 ? launch_trace_t<true>(ctx, A, s0, ns) : launch_trace_t<false>(ctx, A, s0, ns);
 }
 
 int launch_resolve(mrtx_ctx* ctx) {

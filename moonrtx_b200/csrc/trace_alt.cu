@@ -235,22 +235,8 @@ trace_kernel_persistent(const __grid_constant__ RenderArgs A) {
 //   trace_kernel_referee  the few samples the filter could not certify, traced again with the float64 referee
 //   reduce_kernel         per pixel: slots summed in sample order, one accumulator update
 // A sample's result does not depend on which lane, warp or launch produced it.
-struct RayRec { double ox, oy, oz, dx, dy, dz, s_in; float smax; unsigned cell; };   // 64 B; smax < 0: nothing to walk
 struct HitRec { double s; float fc, fr; int r0, c0; int status; unsigned pad; };      // 32 B; status -1: missed the bounding sphere
-static_assert(sizeof(RayRec) == 64 && sizeof(HitRec) == 32, "record layout");
-
-__device__ __forceinline__ void store_ray_rec(RayRec* dst, const Ray64& R, const Walk& st, bool alive) {
-    double2* q = (double2*)dst;
-    q[0] = make_double2(R.ox, R.oy); q[1] = make_double2(R.oz, R.dx); q[2] = make_double2(R.dy, R.dz);
-    const float smax = alive ? st.smax : -1.0f;
-    const unsigned cell = alive ? ((unsigned)st.J << 16) | (unsigned)st.I : 0u;
-    q[3] = make_double2(alive ? st.s_in : 0.0, __hiloint2double((int)cell, __float_as_int(smax)));
-}
-__device__ __forceinline__ void load_ray_rec(const RayRec* src, Ray64& R) {
-    const double2* q = (const double2*)src;
-    const double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
-    R.ox = a.x; R.oy = a.y; R.oz = b.x; R.dx = b.y; R.dy = c.x; R.dz = c.y;
-}
+static_assert(sizeof(HitRec) == 32, "record layout");
 
 // item -> pixel and sample of the wave
 struct ItemId { int x, y; uint32_t pixel; unsigned pl, k, sm; };

@@ -69,9 +69,43 @@ struct RenderArgs {
     FastConsts K;
     float inv_rs;
     int g_log2;                      // fast kernel: 2^g_log2 lanes share one pixel (one sample each per round)
+    // shadow queue of the production path: rays pushed by trace_kernel_fast (work_counter[5] of them), their radiance and
+    // (pixel | sample bit << 27), consumed by shadow_kernel (cursor work_counter[6]); accfix: see accfix_add()
+    struct RayRec* sq_rays; uint4* sq_aux; unsigned sq_cap; int sq_level;
+    unsigned long long* accfix;
+    double* beam_s; unsigned char* beam_l;   // beam pre-pass, by position in the pixel list (null: no pre-pass)
+    int beam_drop;
     // eye and light centre in the body frame (host-computed once per launch)
     double eye_b[3], light_b[3];
 };
+
+// ray record of a queue: the float64 ray, where its walk starts and the cell it starts in (J << 16 | I at the queue's start level)
+struct RayRec { double ox, oy, oz, dx, dy, dz, s_in; float smax; unsigned cell; };   // 64 B; smax < 0: nothing to walk
+static_assert(sizeof(RayRec) == 64, "record layout");
+
+__device__ __forceinline__ void store_ray_rec(RayRec* dst, const Ray64& R, const Walk& st, bool alive) {
+    double2* q = (double2*)dst;
+    q[0] = make_double2(R.ox, R.oy); q[1] = make_double2(R.oz, R.dx); q[2] = make_double2(R.dy, R.dz);
+    const float smax = alive ? st.smax : -1.0f;
+    const unsigned cell = alive ? ((unsigned)st.J << 16) | (unsigned)st.I : 0u;
+    q[3] = make_double2(alive ? st.s_in : 0.0, __hiloint2double((int)cell, __float_as_int(smax)));
+}
+__device__ __forceinline__ void load_ray_rec(const RayRec* src, Ray64& R) {
+    const double2* q = (const double2*)src;
+    const double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+    R.ox = a.x; R.oy = a.y; R.oz = b.x; R.dx = b.y; R.dy = c.x; R.dz = c.y;
+}
+
+
+// accumulation that does not depend on the order of its terms: radiance sums in 2^-36 fixed point (64-bit atomics).
+// fold_kernel adds them to the float accumulators at the end of a launch.
+constexpr float ACCFIX_SCALE = 68719476736.0f;      // 2^36
+__device__ __forceinline__ void accfix_add(unsigned long long* accfix, uint32_t pixel, float3 v) {
+    unsigned long long* a = accfix + (size_t)pixel * 3;
+    if (v.x > 0.f) atomicAdd(a + 0, __float2ull_rn(fminf(v.x, 6.0e7f) * ACCFIX_SCALE));
+    if (v.y > 0.f) atomicAdd(a + 1, __float2ull_rn(fminf(v.y, 6.0e7f) * ACCFIX_SCALE));
+    if (v.z > 0.f) atomicAdd(a + 2, __float2ull_rn(fminf(v.z, 6.0e7f) * ACCFIX_SCALE));
+}
 
 struct RayStats { unsigned primary, inside, hits, shadow, occluded; };
 
@@ -257,11 +291,11 @@ cull_kernel(const __grid_constant__ RenderArgs A) {
     }
 }
 
-__device__ __forceinline__ void primary_ray_fast(const RenderArgs& A, int x, int y, uint32_t pixel, unsigned sm, Ray64& R) {
+// ray through the point (x + jx, y + jy) of the frame, in the body frame
+__device__ __forceinline__ void primary_ray_at(const RenderArgs& A, int x, int y, double jx, double jy, Ray64& R) {
     const SceneParams& sp = A.sp;
     const Camera& cam = A.cam;
     const double aspect = (double)A.width / (double)A.height;
-    const double jx = sp.jitter ? rnd(pixel, sm, 0) : 0.5, jy = sp.jitter ? rnd(pixel, sm, 1) : 0.5;
     const double sx = ((x + jx) / A.width * 2.0 - 1.0) * cam.tan_half_fov * aspect;
     const double sy = (1.0 - (y + jy) / A.height * 2.0) * cam.tan_half_fov;
     double d[3];
@@ -276,6 +310,11 @@ __device__ __forceinline__ void primary_ray_fast(const RenderArgs& A, int x, int
     R.dz = sp.ez[0] * d[0] + sp.ez[1] * d[1] + sp.ez[2] * d[2];
     R.oo = R.ox * R.ox + R.oy * R.oy + R.oz * R.oz;
     R.od = R.ox * R.dx + R.oy * R.dy + R.oz * R.dz;
+}
+
+__device__ __forceinline__ void primary_ray_fast(const RenderArgs& A, int x, int y, uint32_t pixel, unsigned sm, Ray64& R) {
+    const bool j = A.sp.jitter != 0;
+    primary_ray_at(A, x, y, j ? rnd(pixel, sm, 0) : 0.5, j ? rnd(pixel, sm, 1) : 0.5, R);
 }
 
 // hit64 debug record (tests): everything from the float64 hit point
@@ -556,10 +595,8 @@ trace_kernel_referee(const __grid_constant__ RenderArgs A) {
                 float* slot = A.rad + ((size_t)(ent.x - A.wave_p0) * A.nsamples + ent.y) * 3;
                 slot[0] = acc.x; slot[1] = acc.y; slot[2] = acc.z;
             } else {
-                float4* ap = A.accum + (size_t)y * A.width + x; // the filtered kernel has counted the samples
-                float4 old = *ap;
-                old.x += acc.x; old.y += acc.y; old.z += acc.z;
-                *ap = old;
+                accfix_add(A.accfix, pixel, acc);               // (the filtered kernel has counted the samples; a pixel may
+                                                                //  have several entries: order-independent sum)
             }
         }
     }
@@ -598,6 +635,8 @@ static void fill_render_args(mrtx_ctx* ctx, int x0, int y0, int x1, int y1, unsi
     A.K = make_fast_consts(ctx->hf, ctx->sp.radius);
     A.inv_rs = 1.0f / ctx->hf.radius_scale;
     A.g_log2 = 0;
+    A.sq_rays = nullptr; A.sq_aux = nullptr; A.sq_cap = 0; A.sq_level = 0; A.accfix = ctx->accfix;
+    A.beam_s = nullptr; A.beam_l = nullptr; A.beam_drop = (int)ctx->sp.beam_drop;
     A.list_cap = (unsigned)((size_t)ctx->width * ctx->height);
 }
 

@@ -355,6 +355,23 @@ struct Walk {
     double s_in;
 };
 
+// ---- beam pre-pass ---------------------------------------------------------------------------------
+// The samples of a pixel leave the same eye within a cone of half-angle Delta (the pixel's half diagonal): at the same
+// ray parameter s a sample ray q lies within rho = s * Delta of the CENTRE ray c, and since q - c is (to second order)
+// perpendicular to the ray, |q(s)| >= |c(s)| - rho * b / |c(s)| with b the centre ray's distance from the Moon's centre.
+// The directions of q(s) and c(s) differ by at most rho / |c(s)|.  So wherever the centre ray, lowered by
+// lift >= rho * b / r, stays above the max of a cell DILATED by that angle (dil[k]: one cell either side, valid as long
+// as the level's cells are wider than the angle in both directions), no sample of the pixel can be below the surface.
+// walk_step<.., BEAM> walks the centre ray through dil[] with that lift and stops at the first cell it cannot clear at the
+// lowest level the dilation still covers; what it returns is a ray parameter before which every sample of the pixel is
+// above the surface - the samples start their own walks there, a few levels from the bottom, instead of at the
+// bounding sphere at level top - 3.
+struct BeamCtl {
+    float lift;         // scene units the centre ray is lowered by
+    float rho_tex;      // angular radius of the beam in texels of the map (with a safety factor)
+    int   lmin;         // lowest level the beam descends to: 2^lmin >= rho_tex
+};
+
 MRTX_HD inline float walk_r2(const Walk& w, float s) { return fmaf(s, fmaf(2.0f, w.od, s), w.oo); }
 
 // float32 constants of the walk for the ray re-based at s_in (the same arithmetic whoever calls it: a walk that is
@@ -371,8 +388,8 @@ MRTX_HD inline void walk_setup(const Ray64& R, double s_in, float smax, Walk& w)
 }
 
 // where the ray leaves the bounding sphere R * dmax (s_end) - false if it misses it
-MRTX_HD inline bool walk_extent(const HeightField& hf, double radius, const Ray64& R, double& s_first, double& s_end) {
-    const double Rb = radius * (double)hf.dmax;
+MRTX_HD inline bool walk_extent(const HeightField& hf, double radius, const Ray64& R, double& s_first, double& s_end, double lift = 0.0) {
+    const double Rb = radius * (double)hf.dmax + lift;
     const double disc = R.od * R.od - (R.oo - Rb * Rb);
     if (!(disc > 0.0)) return false;
     const double sq = disc * d_rsqrt(disc);
@@ -380,11 +397,12 @@ MRTX_HD inline bool walk_extent(const HeightField& hf, double radius, const Ray6
     return true;
 }
 
-MRTX_HD inline bool walk_begin(const HeightField& hf, double radius, const Ray64& R, double s_min, int start_level, Walk& w,
-                               float t0_rel = 1e-5f) {
+// 0: the ray misses the bounding sphere; 1: it enters it, but not beyond s_min; 2: walk set up
+MRTX_HD inline int walk_begin2(const HeightField& hf, double radius, const Ray64& R, double s_min, int start_level, Walk& w,
+                               float t0_rel = 1e-5f, double lift = 0.0) {
     double s_first, s_end;
-    if (!walk_extent(hf, radius, R, s_first, s_end)) return false;
-    if (s_end <= s_min) return false;
+    if (!walk_extent(hf, radius, R, s_first, s_end, lift)) return 0;
+    if (s_end <= s_min) return s_end > 0.0 ? 1 : 0;
     const double s_in = fmax(s_min, s_first);
     walk_setup(R, s_in, (float)(s_end - s_in), w);
     const int W = hf.W, H = hf.H;
@@ -399,7 +417,12 @@ MRTX_HD inline bool walk_begin(const HeightField& hf, double radius, const Ray64
     const int r0 = min(max((int)floorf(v), 0), H - 2);
     w.L = L; w.J = r0 >> L; w.I = c0 >> L;
     w.s = 0.0f; w.steps = 0;
-    return true;
+    return 2;
+}
+
+MRTX_HD inline bool walk_begin(const HeightField& hf, double radius, const Ray64& R, double s_min, int start_level, Walk& w,
+                               float t0_rel = 1e-5f, double lift = 0.0) {
+    return walk_begin2(hf, radius, R, s_min, start_level, w, t0_rel, lift) == 2;
 }
 
 // Latitude walls.  A wall is the cone z = k r (k = sin phi).  Towards the poles that form loses the wall in
@@ -456,9 +479,20 @@ MRTX_HD inline bool walk_advance(const HeightField& hf, Walk& w, float sx, int f
     return true;
 }
 
-template <bool I16>
+// may the beam descend to row J of level L?  Its dilation must still cover rho_tex texels of longitude at the most
+// poleward latitude of the rows J - 1 .. J + 1 (the rows next to a pole never qualify: cos -> 0)
+MRTX_HD inline bool beam_level_ok(const HeightField& hf, int L, int J, float rho_tex) {
+    const int r_n = max((J - 1) << L, 0), r_s = min((J + 2) << L, hf.H - 1);
+    const float cn = MRTX_LDG(hf.latsc32 + r_n).y, cs = MRTX_LDG(hf.latsc32 + r_s).y;
+    return (float)(1 << L) * fminf(cn, cs) >= rho_tex;
+}
+
+// BEAM: the pre-pass form (see BeamCtl): nodes are read from dil[], the shell is raised by bc->lift, and the cell
+// at which the walk stops (TR_CANDIDATE, level >= bc->lmin >= MRTX_DIL_MIN_LEVEL) comes back with sx_out = the parameter at
+// which the lowered ray enters that cell's shell.
+template <bool I16, bool BEAM = false>
 MRTX_HD inline int walk_step(const HeightField& hf, float Rf, float inv_rs, Walk& w, RawPatch& P,
-                             float& sx_out, int& face_out, Counters& cnt) {
+                             float& sx_out, int& face_out, Counters& cnt, const BeamCtl* bc = nullptr) {
     if (++w.steps > MAX_STEPS) { ++cnt.overflow; return TR_END; }
     const int L = w.L, J = w.J, I = w.I;
     const int W = hf.W, H = hf.H;
@@ -471,7 +505,13 @@ MRTX_HD inline int walk_step(const HeightField& hf, float Rf, float inv_rs, Walk
     const float2 wl = MRTX_LDG(hf.lon32 + (w.east ? min((I + 1) << L, W) : (I << L)));
     const float2 kk = MRTX_LDG(hf.latsc32 + (north ? jn : js));
     float vmax;
-    if (L == 0) {
+    if (BEAM) {
+        // a row whose cells are narrower than the beam (towards the poles) cannot bound it: the pre-pass ends here and
+        // the samples walk on from this point on their own
+        if (!beam_level_ok(hf, L, J, bc->rho_tex)) { sx_out = s; return TR_CANDIDATE; }
+        vmax = I16 ? (float)MRTX_LDG((const int16_t*)hf.dil[L] + (size_t)J * hf.nx[L] + I)
+                   : MRTX_LDG((const float*)hf.dil[L] + (size_t)J * hf.nx[L] + I);
+    } else if (L == 0) {
         const int c1 = I + 1 == W ? 0 : I + 1;
         P.r0 = J; P.c0 = I;
         if (I16) {
@@ -489,7 +529,7 @@ MRTX_HD inline int walk_step(const HeightField& hf, float Rf, float inv_rs, Walk
                    : MRTX_LDG((const float*)hf.level[L] + (size_t)J * hf.nx[L] + I);
     }
     const float dmax = decode_bound<I16>(hf, vmax, inv_rs);
-    const float marg = 3.0e-6f * Rf;                        // float32 error of a radius near R + the cheap decode
+    const float marg = 3.0e-6f * Rf + (BEAM ? bc->lift : 0.0f);      // float32 error of a radius near R + the cheap decode
     const float rc = fmaf(Rf, dmax, marg), rc2 = rc * rc;
     const float r2s = walk_r2(w, s);
     float sd = s;
@@ -540,12 +580,13 @@ MRTX_HD inline int walk_step(const HeightField& hf, float Rf, float inv_rs, Walk
         MRTX_DBG("walk %d L%d J%d I%d s=%.7f sx=%.7f face=%d rc=%.7f r(s)=%.7f r(tm)=%.7f east=%d north=%d\n", w.steps, L, J, I, s, sx, face, rc,
                  sqrtf(r2s), sqrtf(walk_r2(w, tm)), (int)w.east, (int)(fmaf(s, w.n1, w.n0) > 0.0f));
         if (!(walk_r2(w, tm) <= rc2)) return walk_advance(hf, w, sx, face) ? TR_CONTINUE : TR_END;
-        if (L == 0) { sx_out = sx; face_out = face; return TR_CANDIDATE; }
+        if (!BEAM && L == 0) { sx_out = sx; face_out = face; return TR_CANDIDATE; }
         if (r2s > rc2) {
             const float dq = fmaf(w.od, w.od, rc2 - w.oo);
             if (dq > 0.0f) sd = fminf(fmaxf(-w.od - f_sqrt_fast(dq), s), sx);
         }
     }
+    if (BEAM && L <= bc->lmin) { sx_out = sd; return TR_CANDIDATE; }
     // pick the child at sd
     const float x = fmaf(sd, w.dx, w.ox), y = fmaf(sd, w.dy, w.oy), z = fmaf(sd, w.dz, w.oz);
     const int mi = (2 * I + 1) << (L - 1), mj = (2 * J + 1) << (L - 1);
@@ -558,21 +599,112 @@ MRTX_HD inline int walk_step(const HeightField& hf, float Rf, float inv_rs, Walk
         const float rho2 = fmaf(x, x, y * y);
         if (lat_side(MRTX_LDG(hf.latsc32 + mj), z, f_sqrt_fast(rho2), f_sqrt_fast(fmaf(z, z, rho2))) < 0.0f) cj += 1;   // south of the mid wall
     }
+    if (BEAM && !beam_level_ok(hf, L - 1, cj, bc->rho_tex)) { sx_out = sd; return TR_CANDIDATE; }
     w.s = sd; w.L = L - 1; w.I = ci; w.J = cj;
     return TR_CONTINUE;
 }
 
-// Sequential form (host tool): FT_HIT / FT_MISS / FT_DEFER for the whole ray.
+// ---- ceiling test (shadow rays) ---------------------------------------------------------------------
+// A ray that is RISING (p . d >= 0: its distance from the centre only grows from here on) and stands at the point
+// p(s) of cell (L, J, I) has nothing left to meet once it is above everything it can still pass over before it leaves
+// the bounding sphere.  dil[K] of the level-K cell that contains p bounds the surface for every direction within one
+// level-K cell of it, and the ray cannot leave that neighbourhood before it has travelled D_K = one cell's width at the
+// neighbourhood's most poleward latitude; by then its radius has grown to r(s + D_K), which is compared with dil[K + 2],
+// and so on up to the top level - a handful of independent loads instead of the ~8 dependent node visits the walk
+// needs to climb from level 3 to the top of the pyramid.  "Clear" is exact (conservative bounds only); "not clear"
+// says nothing, the walk just goes on.
 template <bool I16>
-MRTX_HD inline int trace_ray_fast(const HeightField& hf, const FastConsts& K, double radius, const Ray64& R, double s_min,
-                                  int start_level, FastHit& out, Counters& cnt) {
+MRTX_HD inline bool ceiling_clear(const HeightField& hf, const FastConsts& K, float inv_rs, const Walk& w, float dmin) {
+    const float s = w.s;
+    const float pd = w.od + s;                                  // p(s) . d  (|d| = 1)
+    if (!(pd >= 0.0f)) return false;
+    int L = w.L, J = w.J, I = w.I;
+    if (L < MRTX_DIL_MIN_LEVEL) return false;
+    const float r2 = walk_r2(w, s);
+    const float x = fmaf(s, w.dx, w.ox), y = fmaf(s, w.dy, w.oy);
+    const float cosphi = f_sqrt_fast(fmaf(x, x, y * y)) * f_rsqrt(r2);
+    const float ang_lat = 1.0f / K.Kh, ang_lon = 1.0f / K.Kw;  // one texel of latitude / of longitude at the equator, radians
+    const float Rmin = K.R * dmin;
+    const float Rb = K.R * hf.dmax, Rb2 = Rb * Rb;
+    const float marg = 3.0e-6f * K.R;
+    float t = 0.0f;                                             // the ray has surely travelled this far when stage K is looked at
+    for (;;) {
+        const float rt2 = fmaf(t, fmaf(2.0f, pd, t), r2);       // r^2 after t, a lower bound of r^2 from there on
+        if (rt2 >= Rb2) return true;                            // beyond the bounding sphere
+        const float vmax = I16 ? (float)MRTX_LDG((const int16_t*)hf.dil[L] + (size_t)J * hf.nx[L] + I)
+                               : MRTX_LDG((const float*)hf.dil[L] + (size_t)J * hf.nx[L] + I);
+        const float rc = fmaf(K.R, decode_bound<I16>(hf, vmax, inv_rs), marg);
+        if (!(rt2 > rc * rc)) return false;
+        // distance before which the ray cannot have left the 3 x 3 neighbourhood of its level-L cell
+        const float cells = (float)(1 << L);
+        const float cosmin = cosphi - 2.0f * cells * ang_lat;   // cos is 1-Lipschitz: the neighbourhood's most poleward latitude
+        if (!(cosmin > 0.0f)) return false;
+        const float D = 0.9f * cells * fminf(ang_lat, ang_lon * cosmin) * Rmin;
+        if (L >= hf.top) {
+            // the top level's neighbourhood must see the ray out of the bounding sphere
+            const float re2 = fmaf(D, fmaf(2.0f, pd, D), r2);
+            return re2 >= Rb2;
+        }
+        t = D;
+        const int up = min(2, hf.top - L);
+        L += up; J >>= up; I >>= up;
+    }
+}
+
+// Beam pre-pass of one pixel: centre ray C, angular radius delta (radians) of the pixel.  Returns false if no sample
+// of the pixel can hit at all; else s_start = a parameter before which every sample is above the surface and level =
+// the level the walk stopped at (the samples start a little below it).
+template <bool I16>
+MRTX_HD inline bool beam_walk(const HeightField& hf, const FastConsts& K, double radius, const Ray64& C, double delta,
+                              double& s_start, int& level, Counters& cnt) {
+    const double Rmin = radius * (double)hf.dmin;
+    // rho: the beam's radius at the far end of anything it can meet (its centre ray is nearest to the Moon's centre at
+    // s = -od; nothing it meets lies further than a bounding-sphere radius beyond that)
+    const double Rb = radius * (double)hf.dmax;
+    const double b2 = fmax(C.oo - C.od * C.od, 0.0), b = sqrt(b2);
+    const double rho = (fmax(-C.od, 0.0) + 1.1 * Rb) * delta;
+    if (b - 1.05 * rho > Rb) return false;                      // no ray of the pixel comes within the bounding sphere
+    BeamCtl bc;
+    bc.lift = (float)(1.02 * rho * b / Rmin + rho * rho / Rmin + 1.0e-6 * radius);
+    bc.rho_tex = (float)(1.1 * (rho / Rmin) * (double)K.Kh + 0.25);
+    int lmin = MRTX_DIL_MIN_LEVEL;
+    while ((float)(1 << lmin) < bc.rho_tex && lmin < hf.top) ++lmin;
+    bc.lmin = lmin;
+    s_start = 0.0; level = hf.top;
+    if ((float)(1 << lmin) < bc.rho_tex || (double)bc.lift > 0.01 * radius) return true;     // beam too wide to bound: no information
     Walk w;
-    if (!walk_begin(hf, radius, R, s_min, start_level, w)) return FT_MISS;
+    if (!walk_begin(hf, radius, C, 0.0, hf.top, w, 1e-5f, (double)bc.lift)) return false;
     const float Rf = (float)radius, inv_rs = 1.0f / hf.radius_scale;
     for (;;) {
         RawPatch P;
         float sx;
         int face;
+        const int r = walk_step<I16, true>(hf, Rf, inv_rs, w, P, sx, face, cnt, &bc);
+        if (r == TR_END) return false;
+        if (r == TR_CANDIDATE) {
+            s_start = fmax(w.s_in + (double)sx - 2.0 * (double)K.pad, 0.0);
+            level = w.L;
+            return true;
+        }
+    }
+}
+
+// Sequential form (host tool): FT_HIT / FT_MISS / FT_DEFER for the whole ray.
+template <bool I16>
+MRTX_HD inline int trace_ray_fast(const HeightField& hf, const FastConsts& K, double radius, const Ray64& R, double s_min,
+                                  int start_level, FastHit& out, Counters& cnt, int ceil_level = 0) {
+    Walk w;
+    if (!walk_begin(hf, radius, R, s_min, start_level, w)) return FT_MISS;
+    const float Rf = (float)radius, inv_rs = 1.0f / hf.radius_scale;
+    int ceil_next = ceil_level > 0 ? ceil_level : 0x7fffffff;
+    for (;;) {
+        RawPatch P;
+        float sx;
+        int face;
+        if (w.L >= ceil_next) {
+            ceil_next = w.L + 2;
+            if (ceiling_clear<I16>(hf, K, inv_rs, w, hf.dmin)) return FT_MISS;
+        }
         const int r = walk_step<I16>(hf, Rf, inv_rs, w, P, sx, face, cnt);
         if (r == TR_END) return FT_MISS;
         if (r == TR_CANDIDATE) {

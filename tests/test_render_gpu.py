@@ -338,6 +338,9 @@ def test_wavefront_pipeline_equals_filtered_kernel(spp):
     for kernel in (2, 3):
         rt = make_gpu(elev, 320, 240, debug_hits=(spp == 1), **kw)
         rt.set_uint("kernel", kernel)
+        # kernel 2 in its in-kernel form (shadow rays inside trace_kernel_fast, no ceiling test, no beam pre-pass): the
+        # form whose node counts and float sums kernel 3 reproduces
+        rt.set_uint("shadow_queue", 0); rt.set_uint("ceiling", 0); rt.set_uint("beam", 0)
         if spp > 1:
             rt.set_param(max_accumulation_frames=spp, min_accumulation_step=spp)
         rt.counters(reset=True); rt.defer_stats(reset=True)
@@ -355,6 +358,44 @@ def test_wavefront_pipeline_equals_filtered_kernel(spp):
     assert int(d.max()) <= 1 and int((d.max(axis=2) > 0).sum()) <= 4
     if spp == 1:
         assert np.array_equal(ha, hb)
+
+
+@pytest.mark.parametrize("spp,phase", [(1, 88.0), (16, 90.0), (40, 60.0)])
+def test_shadow_queue_ceiling_and_beam_change_no_decision(spp, phase):
+    """The production form of kernel 2 - shadow rays streamed through the queue kernel with lane refill, the ceiling test
+    that ends rising rays early, the beam pre-pass that starts the samples of a pixel near the surface - against its
+    plain in-kernel form: the same rays with the same hit / miss / occluded decisions; radiance is summed in 2^-36 fixed
+    point instead of float32 lane order."""
+    elev, _ = synth_elevation(2880, 1440, seed=12)
+    kw = dict(light_pos=sun_at_phase(phase))
+    outs = []
+    for sq, ceil, beam in ((0, 0, 0), (1, 2, 1)):
+        rt = make_gpu(elev, 320, 240, debug_hits=(spp == 1), **kw)
+        rt.set_uint("shadow_queue", sq); rt.set_uint("ceiling", ceil); rt.set_uint("beam", beam, 2)
+        if spp > 1:
+            rt.set_param(max_accumulation_frames=spp, min_accumulation_step=spp)
+        rt.counters(reset=True); rt.defer_stats(reset=True)
+        img = rt.render_cycle().copy()
+        outs.append((img, rt.get_accum_buffer().copy(), rt.counters(), rt.defer_stats(),
+                     rt.get_hit_records_f64().copy() if spp == 1 else None))
+        rt.close()
+    (ia, aa, ca, da, ha), (ib, ab, cb, db, hb) = outs
+    for k in ("primary_rays", "primary_in_sphere"):
+        assert ca[k] == cb[k], (k, ca[k], cb[k])
+    # (a sample whose ray starts elsewhere may be deferred where the other form decided it, and the other way round:
+    #  the referee then decides it with the same exact test)
+    for k in ("primary_hits", "shadow_rays", "shadow_occluded"):
+        assert abs(ca[k] - cb[k]) <= 2, (k, ca[k], cb[k])
+    assert cb["node_visits"] < ca["node_visits"]
+    assert np.array_equal(aa[..., 3], ab[..., 3]) and np.all(ab[..., 3] == float(spp))
+    bad = ~np.isclose(aa[..., :3], ab[..., :3], rtol=1e-5, atol=1e-6).all(axis=2)
+    assert int(bad.sum()) <= 2, int(bad.sum())
+    d = np.abs(ia[..., :3].astype(np.int32) - ib[..., :3].astype(np.int32))
+    assert int((d.max(axis=2) > 1).sum()) <= 2
+    if spp == 1:
+        assert int(((ha[..., 0] > 0) != (hb[..., 0] > 0)).sum()) == 0
+        both = ha[..., 0] > 0
+        assert np.abs(ha[..., 0] - hb[..., 0])[both].max() <= 1e-9 * 300.0
 
 
 @pytest.mark.parametrize("kernel", [2, 3])

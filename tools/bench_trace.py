@@ -91,11 +91,23 @@ if __name__ == "__main__":
     if os.environ.get("START"):
         a, b = [int(v) for v in os.environ["START"].split(",")]
         _lib.check(lib.mrtx_set_uint(ctx, b"start_levels", a, b))
+    # VARIANTS="beam=0,0;beam=1,2;start_levels=3,1": engine switches (mrtx_set_uint name=a,b) tried one after the other on kernel 2,
+    # every frame compared with the first variant's
+    variants = [v for v in os.environ.get("VARIANTS", "").split(";") if v]
+    if variants:
+        kernels = list(range(100, 100 + len(variants)))
     for spp in spps:
         for k in kernels:
-            _lib.check(lib.mrtx_set_uint(ctx, b"kernel", k, 0))
+            if k >= 100:
+                _lib.check(lib.mrtx_set_uint(ctx, b"kernel", 2, 0))
+                for item in variants[k - 100].split("+"):
+                    name, val = item.split("=")
+                    a, b = (val.split(",") + ["0"])[:2]
+                    _lib.check(lib.mrtx_set_uint(ctx, name.encode(), int(a), int(b)))
+            else:
+                _lib.check(lib.mrtx_set_uint(ctx, b"kernel", k, 0))
             r = time_frame(rt, spp)
-            r["kernel"] = k
+            r["kernel"] = k if k < 100 else variants[k - 100]
             print(json.dumps(r), flush=True)
             _lib.check(lib.mrtx_resolve(ctx))
             img = np.empty((rt._height, rt._width, 4), np.uint8)
@@ -103,10 +115,10 @@ if __name__ == "__main__":
             acc = np.empty((rt._height, rt._width, 4), np.float32)
             _lib.check(lib.mrtx_read_accum_f32(ctx, acc.ctypes.data))
             imgs[k] = (img, acc)
-        if len(kernels) > 1:
-            a, b = imgs[kernels[0]], imgs[kernels[1]]
+        for other in kernels[1:]:
+            a, b = imgs[kernels[0]], imgs[other]
             d = np.abs(a[0][..., :3].astype(np.int32) - b[0][..., :3].astype(np.int32))
             da = np.abs(a[1][..., :3] - b[1][..., :3])
-            print(json.dumps({"spp": spp, "compare": kernels[:2], "img_mae": float(d.mean()), "img_max": int(d.max()),
+            print(json.dumps({"spp": spp, "compare": [kernels[0], other], "img_mae": float(d.mean()), "img_max": int(d.max()),
                               "pixels_differ": int((d.max(axis=2) > 0).sum()), "pixels_differ_gt2": int((d.max(axis=2) > 2).sum()),
                               "accum_max_abs": float(da.max()), "accum_w_equal": bool(np.array_equal(a[1][..., 3], b[1][..., 3]))}), flush=True)
