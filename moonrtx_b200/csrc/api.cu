@@ -67,7 +67,7 @@ int mrtx_create(int device, mrtx_ctx** out_ctx) {
     sp.light_pos[0] = 21460.0; sp.light_radius = 100.0; sp.light_radiance = 80.0 * 460.5316;
     sp.scene_epsilon = 1.0e-4;
     sp.exposure = 0.9f; sp.inv_gamma = 1.0f / 2.2f;
-    sp.jitter = 0; sp.shadows = 1; sp.debug_hits = 0; sp.kernel = 2; sp.beam = 0; sp.beam_drop = 2; sp.ceiling = 2; sp.shadow_queue = 1; sp.start_primary = 3; sp.start_shadow = 2; sp.long_walk = 2048u; sp.referee_budget = 1500u;
+    sp.jitter = 0; sp.shadows = 1; sp.debug_hits = 0; sp.kernel = 2; sp.beam = 0; sp.beam_drop = 2; sp.ceiling = 2; sp.shadow_queue = 1; sp.start_primary = 3; sp.start_shadow = 2; sp.long_walk = 2048u; sp.referee_budget = 500u;
     const double eye[3] = {0, -300, 0}, tgt[3] = {0, 0, 0}, up[3] = {0, 0, 1};
     mrtx_set_camera(c, eye, tgt, up, 4.242192793);
     *out_ctx = c;
@@ -461,6 +461,7 @@ int mrtx_set_uint(mrtx_ctx* ctx, const char* name, unsigned a, unsigned b) {
     else if (!strcmp(name, "long_walk")) { MRTX_REQUIRE(a >= 1u, "long_walk must be >= 1"); ctx->sp.long_walk = a; }
     else if (!strcmp(name, "referee_budget")) { MRTX_REQUIRE(a >= 1u, "referee_budget must be >= 1"); ctx->sp.referee_budget = a; }
     else if (!strcmp(name, "ceiling")) ctx->sp.ceiling = a;
+    else if (!strcmp(name, "blocks_per_sm")) ctx->sp.blocks_per_sm = a;
     else if (!strcmp(name, "shadow_queue")) ctx->sp.shadow_queue = a ? 1u : 0u;
     else if (!strcmp(name, "beam")) { ctx->sp.beam = a ? 1u : 0u; ctx->sp.beam_drop = b; }
     else if (!strcmp(name, "kernel")) { MRTX_REQUIRE(a <= 3u, "kernel must be 0, 1, 2 or 3"); ctx->sp.kernel = a; }

@@ -55,6 +55,11 @@ struct HeightField {
     float scale, radius_scale;  // int16 decode: D = ((c*scale)+1)/radius_scale, each op f32
     const void* level[MRTX_MAX_LEVELS];   // level[k], k = 1..top; same dtype as base
     const void* dil[MRTX_MAX_LEVELS];     // dil[k], k = MRTX_DIL_MIN_LEVEL..top: level k dilated by one cell (pyramid.cu)
+    // the same levels as element offsets from lvl_base (all levels live in one allocation): off[k] = level k,
+    // off[MRTX_MAX_LEVELS + k] = dil k.  Kernels copy this table to shared memory: a per-lane level index into a
+    // kernel-parameter array costs a dozen instructions per access, into shared memory one.
+    const void* lvl_base;
+    unsigned off[2 * MRTX_MAX_LEVELS];
     int   nx[MRTX_MAX_LEVELS], ny[MRTX_MAX_LEVELS];   // cells per level (level 0: W, H-1)
     float dmax, dmin;           // global max / min displacement factor
     // wall tables (one allocation, hf_tables_owned): cell walls are the half-planes of constant
@@ -87,6 +92,7 @@ struct SceneParams {
     unsigned jitter, shadows, debug_hits;
     unsigned start_primary, start_shadow;   // filtered kernel: primary rays start at level top - start_primary, shadow rays at start_shadow
     unsigned long_walk, referee_budget;     // walks longer than long_walk nodes go to the referee; a referee lane spends referee_budget on a piece
+    unsigned blocks_per_sm;                 // development: cap on resident blocks per SM of the two walk kernels (0 = what fits)
     unsigned shadow_queue;                  // shadow rays through the streaming queue kernel (default) or inside trace_kernel_fast
     unsigned ceiling;                       // shadow rays: ceiling test from this level upwards (0 = off)
     unsigned beam, beam_drop;               // beam pre-pass of the filtered kernel (launches of >= 4 samples); samples start beam_drop levels below the beam's

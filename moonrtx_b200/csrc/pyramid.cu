@@ -141,6 +141,7 @@ int build_levels(mrtx_ctx* ctx) {
             hf.level[k] = p;
             p += (((size_t)hf.nx[k] * hf.ny[k] * sizeof(T)) + 255) & ~(size_t)255;
         }
+        hf.lvl_base = ctx->hf_levels_owned;
         const T* base = (const T*)hf.base;
         {
             const long long n = (long long)hf.nx[1] * hf.ny[1];
@@ -161,6 +162,10 @@ int build_levels(mrtx_ctx* ctx) {
             dilate_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const T*)hf.level[k], hf.nx[k], hf.ny[k], reach < hf.nx[k] / 2 ? reach : hf.nx[k] / 2, (T*)hf.dil[k]);
         }
         MRTX_CUDA(cudaGetLastError());
+        for (int k = 1; k <= top; ++k) {
+            hf.off[k] = (unsigned)(((const char*)hf.level[k] - (const char*)hf.lvl_base) / sizeof(T));
+            hf.off[MRTX_MAX_LEVELS + k] = hf.dil[k] ? (unsigned)(((const char*)hf.dil[k] - (const char*)hf.lvl_base) / sizeof(T)) : 0u;
+        }
     }
     // global range -> bounding sphere (and the "surely inside" sphere)
     int* d_mm = nullptr;

@@ -79,6 +79,9 @@ beam_kernel(const __grid_constant__ RenderArgs A) {
 template <bool I16, bool QUEUE>
 __global__ void __launch_bounds__(128, MRTX_FAST_MINBLOCKS)
 trace_kernel_fast(const __grid_constant__ RenderArgs A) {
+    __shared__ unsigned s_off[2 * MRTX_MAX_LEVELS];          // level offsets (HeightField::off) where a per-lane index is cheap
+    if (threadIdx.x < 2 * MRTX_MAX_LEVELS) s_off[threadIdx.x] = A.hf.off[threadIdx.x];
+    __syncthreads();
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
@@ -156,11 +159,11 @@ trace_kernel_fast(const __grid_constant__ RenderArgs A) {
                             bool clear = false;
                             if (!QUEUE && st.L >= ceil_next) {
                                 ceil_next = st.L + 2;
-                                clear = ceiling_clear<I16>(A.hf, A.K, A.inv_rs, st, A.hf.dmin);
+                                clear = ceiling_clear<I16>(A.hf, A.K, A.inv_rs, st, A.hf.dmin, s_off);
                             }
                             if (clear) alive = false;
                             else {
-                                const int r = walk_step<I16>(A.hf, Rf, A.inv_rs, st, P, sx, face, cnt);
+                                const int r = walk_step<I16>(A.hf, Rf, A.inv_rs, st, P, sx, face, cnt, nullptr, s_off);
                                 if (r == TR_END) alive = false;
                                 else if (r == TR_CANDIDATE) cand = true;
                             }
@@ -269,16 +272,19 @@ trace_kernel_fast(const __grid_constant__ RenderArgs A) {
 #define MRTX_SQ_MINBLOCKS 8
 #endif
 #ifndef MRTX_SQ_CAND
-#define MRTX_SQ_CAND 12
+#define MRTX_SQ_CAND 10
 #endif
 #ifndef MRTX_SQ_REFILL
-#define MRTX_SQ_REFILL 4
+#define MRTX_SQ_REFILL 12
 #endif
 enum { SQ_EMPTY = 0, SQ_WALK = 1, SQ_CAND = 2 };
 
 template <bool I16>
 __global__ void __launch_bounds__(128, MRTX_SQ_MINBLOCKS)
 shadow_kernel(const __grid_constant__ RenderArgs A) {
+    __shared__ unsigned s_off[2 * MRTX_MAX_LEVELS];          // level offsets (HeightField::off) where a per-lane index is cheap
+    if (threadIdx.x < 2 * MRTX_MAX_LEVELS) s_off[threadIdx.x] = A.hf.off[threadIdx.x];
+    __syncthreads();
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
@@ -318,7 +324,7 @@ shadow_kernel(const __grid_constant__ RenderArgs A) {
                 load_ray_rec(rec, R);
                 walk_setup(R, tail.x, smax, st);
                 st.L = A.sq_level; st.J = (int)(cell >> 16); st.I = (int)(cell & 0xffffu);
-                st.s = 0.0f; st.steps = 0;
+                st.s = 0.0f; st.steps = 0; st.vnext = NAN;
                 ridx = idx;
                 mode = SQ_WALK;
                 ceil_next = A.sp.ceiling ? (int)A.sp.ceiling : 0x7fffffff;
@@ -344,10 +350,10 @@ shadow_kernel(const __grid_constant__ RenderArgs A) {
             // ---- walk step
             if (st.L >= ceil_next) {
                 ceil_next = st.L + 2;
-                if (ceiling_clear<I16>(A.hf, A.K, A.inv_rs, st, A.hf.dmin)) finished = true;
+                if (ceiling_clear<I16>(A.hf, A.K, A.inv_rs, st, A.hf.dmin, s_off)) finished = true;
             }
             if (!finished) {
-                const int r = walk_step<I16>(A.hf, Rf, A.inv_rs, st, P, sx, face, cnt);
+                const int r = walk_step<I16>(A.hf, Rf, A.inv_rs, st, P, sx, face, cnt, nullptr, s_off);
                 if (r == TR_END) finished = true;
                 else if (st.steps > (int)A.sp.long_walk) { finished = true; status = FT_DEFER_R(15); }
                 else if (r == TR_CANDIDATE) mode = SQ_CAND;
@@ -443,6 +449,7 @@ static int launch_fast(mrtx_ctx* ctx, RenderArgs& A, long long npix) {
     int per_sm = 0;
     MRTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel_fast<I16, QUEUE>, 128, 0));
     if (per_sm < 1) per_sm = 1;
+    if (ctx->sp.blocks_per_sm && (int)ctx->sp.blocks_per_sm < per_sm) per_sm = (int)ctx->sp.blocks_per_sm;
     const long long warps_needed = ((npix << A.g_log2) + 31) / 32;
     long long blocks = (long long)ctx->sm_count * per_sm;
     if (blocks * 4 > warps_needed) blocks = (warps_needed + 3) / 4;
@@ -477,6 +484,7 @@ static int launch_trace_t(mrtx_ctx* ctx, RenderArgs& A, unsigned s0, unsigned ns
         A.sq_level = std::min(lvl, ctx->hf.top);
         int per_sm = 0;
         MRTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shadow_kernel<I16>, 128, 0));
+        if (ctx->sp.blocks_per_sm && (int)ctx->sp.blocks_per_sm < per_sm) per_sm = (int)ctx->sp.blocks_per_sm;
         sq_blocks = ctx->sm_count * (per_sm < 1 ? 1 : per_sm);
     }
     // chunks of <= 32 samples (one mask bit per sample in the deferred list); within a chunk, waves of pixels that the

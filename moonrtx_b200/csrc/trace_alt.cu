@@ -328,7 +328,7 @@ trace_kernel_walk(const __grid_constant__ RenderArgs A) {
                     load_ray_rec(rec, R);
                     walk_setup(R, tail.x, smax, st);
                     st.L = L0; st.J = (int)(cell >> 16); st.I = (int)(cell & 0xffffu);
-                    st.s = 0.0f; st.steps = 0;
+                    st.s = 0.0f; st.steps = 0; st.vnext = NAN;
                     ridx = idx;
                     mode = LM_WALK;
                 }

@@ -56,6 +56,21 @@ MRTX_HD inline double d_rsqrt(double x) {
     return y;
 }
 
+#ifndef MRTX_PREFETCH
+#define MRTX_PREFETCH 0
+#endif
+// 32-bit read-only load of two neighbouring int16 cells, issued where it stands (volatile: the compiler must not sink it
+// to its use, which would put the latency back on the critical path)
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ unsigned mrtx_ldg_u32(const int16_t* p) {
+    unsigned v;
+    asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+#else
+static inline unsigned mrtx_ldg_u32(const int16_t* p) { unsigned v; memcpy(&v, p, 4); return v; }
+#endif
+
 struct FastConsts {
     float R;            // sphere radius
     float Kw, Kh;       // texels per radian: W / 2 pi, H / pi
@@ -352,6 +367,7 @@ struct Walk {
     int L, J, I;            // current cell
     int steps;
     bool east;              // longitude increases along the ray
+    float vnext;            // the current cell's stored max if the parent's visit has fetched it already (NaN: not known)
     double s_in;
 };
 
@@ -416,7 +432,7 @@ MRTX_HD inline int walk_begin2(const HeightField& hf, double radius, const Ray64
     c0 = c0 < 0 ? c0 + W : (c0 >= W ? c0 - W : c0);
     const int r0 = min(max((int)floorf(v), 0), H - 2);
     w.L = L; w.J = r0 >> L; w.I = c0 >> L;
-    w.s = 0.0f; w.steps = 0;
+    w.s = 0.0f; w.steps = 0; w.vnext = NAN;
     return 2;
 }
 
@@ -462,20 +478,30 @@ MRTX_HD inline float lat_cross(const Walk& w, float2 kk, float lo, float hi) {
     return best;
 }
 
+// cells per level, by arithmetic (= hf.nx[L], hf.ny[L]: indexing those kernel-parameter arrays with a per-lane level was
+// 11 % of the kernel's instructions)
+MRTX_HD inline int lvl_nx(const HeightField& hf, int L) { return (hf.W + (1 << L) - 1) >> L; }
+MRTX_HD inline int lvl_ny(const HeightField& hf, int L) { return (hf.H - 2 + (1 << L)) >> L; }
+
 // faces: 0 longitude wall ahead, 1 north wall, 2 south wall, 4 end of the ray
 MRTX_HD inline bool walk_advance(const HeightField& hf, Walk& w, float sx, int face) {
     if (face == 4) return false;
     w.s = sx;
     int L = w.L, J = w.J, I = w.I;
-    bool up;
-    if (face == 0) {
-        if (w.east) { I += 1; if (I >= hf.nx[L]) I = 0; up = (I & 1) == 0; }
-        else { up = (I & 1) == 0; I -= 1; if (I < 0) I = hf.nx[L] - 1; }
-    } else if (face == 2) { J += 1; up = (J & 1) == 0; }
-    else { up = (J & 1) == 0; J -= 1; }
-    if (J < 0 || J >= hf.ny[L]) return false;                // cannot happen (caps have no wall); be safe
+    // the index that moves, its step, and the boundary it crosses (the higher of the two cells' indices): the walk goes
+    // up a level where that boundary is also a boundary of the level above
+    const bool lon = face == 0;
+    const int step = lon ? (w.east ? 1 : -1) : (face == 2 ? 1 : -1);
+    const int from = lon ? I : J;
+    const int to = from + step;
+    const bool up = ((step > 0 ? to : from) & 1) == 0;
+    if (lon) { const int nx = lvl_nx(hf, L); I = to >= nx ? 0 : (to < 0 ? nx - 1 : to); }
+    else {
+        J = to;
+        if (J < 0 || J >= lvl_ny(hf, L)) return false;       // cannot happen (caps have no wall); be safe
+    }
     if (up && L < hf.top) { L += 1; I >>= 1; J >>= 1; }
-    w.L = L; w.J = J; w.I = I;
+    w.L = L; w.J = J; w.I = I; w.vnext = NAN;
     return true;
 }
 
@@ -492,7 +518,9 @@ MRTX_HD inline bool beam_level_ok(const HeightField& hf, int L, int J, float rho
 // which the lowered ray enters that cell's shell.
 template <bool I16, bool BEAM = false>
 MRTX_HD inline int walk_step(const HeightField& hf, float Rf, float inv_rs, Walk& w, RawPatch& P,
-                             float& sx_out, int& face_out, Counters& cnt, const BeamCtl* bc = nullptr) {
+                             float& sx_out, int& face_out, Counters& cnt, const BeamCtl* bc = nullptr,
+                             const unsigned* loff = nullptr) {
+    if (!loff) loff = hf.off;                                   // (hot kernels pass their shared-memory copy)
     if (++w.steps > MAX_STEPS) { ++cnt.overflow; return TR_END; }
     const int L = w.L, J = w.J, I = w.I;
     const int W = hf.W, H = hf.H;
@@ -504,13 +532,27 @@ MRTX_HD inline int walk_step(const HeightField& hf, float Rf, float inv_rs, Walk
     const int jn = J << L, js = min((J + 1) << L, H - 1);
     const float2 wl = MRTX_LDG(hf.lon32 + (w.east ? min((I + 1) << L, W) : (I << L)));
     const float2 kk = MRTX_LDG(hf.latsc32 + (north ? jn : js));
+    // The four children of this cell are requested NOW, with the cell itself: if the walk descends, the child's max is in
+    // a register when the child is visited and its visit starts without a memory round trip (the kernel is bound by
+    // the latency of the dependent chain node -> decision -> next node, not by bandwidth).
+#if MRTX_PREFETCH
+    unsigned ch0 = 0u, ch1 = 0u;                                // int16 maps: children (2J, 2I..2I+1) and (2J+1, 2I..2I+1), packed
+    const bool pre = !BEAM && I16 && L >= 2;
+    if (pre) {
+        const int cnx = lvl_nx(hf, L - 1), cny = lvl_ny(hf, L - 1);
+        const unsigned e0 = loff[L - 1] + (unsigned)(2 * J) * (unsigned)cnx + (unsigned)(2 * I);
+        const unsigned e1 = 2 * J + 1 < cny ? e0 + (unsigned)cnx : e0;
+        ch0 = mrtx_ldg_u32((const int16_t*)hf.lvl_base + e0);
+        ch1 = mrtx_ldg_u32((const int16_t*)hf.lvl_base + e1);
+    }
+#endif
     float vmax;
     if (BEAM) {
         // a row whose cells are narrower than the beam (towards the poles) cannot bound it: the pre-pass ends here and
         // the samples walk on from this point on their own
         if (!beam_level_ok(hf, L, J, bc->rho_tex)) { sx_out = s; return TR_CANDIDATE; }
-        vmax = I16 ? (float)MRTX_LDG((const int16_t*)hf.dil[L] + (size_t)J * hf.nx[L] + I)
-                   : MRTX_LDG((const float*)hf.dil[L] + (size_t)J * hf.nx[L] + I);
+        const unsigned e = loff[MRTX_MAX_LEVELS + L] + (unsigned)J * (unsigned)lvl_nx(hf, L) + (unsigned)I;
+        vmax = I16 ? (float)MRTX_LDG((const int16_t*)hf.lvl_base + e) : MRTX_LDG((const float*)hf.lvl_base + e);
     } else if (L == 0) {
         const int c1 = I + 1 == W ? 0 : I + 1;
         P.r0 = J; P.c0 = I;
@@ -525,8 +567,11 @@ MRTX_HD inline int walk_step(const HeightField& hf, float Rf, float inv_rs, Walk
         }
         vmax = fmaxf(fmaxf(P.v00, P.v01), fmaxf(P.v10, P.v11));
     } else {
-        vmax = I16 ? (float)MRTX_LDG((const int16_t*)hf.level[L] + (size_t)J * hf.nx[L] + I)
-                   : MRTX_LDG((const float*)hf.level[L] + (size_t)J * hf.nx[L] + I);
+        if (w.vnext == w.vnext) vmax = w.vnext;
+        else {
+            const unsigned e = loff[L] + (unsigned)J * (unsigned)lvl_nx(hf, L) + (unsigned)I;
+            vmax = I16 ? (float)MRTX_LDG((const int16_t*)hf.lvl_base + e) : MRTX_LDG((const float*)hf.lvl_base + e);
+        }
     }
     const float dmax = decode_bound<I16>(hf, vmax, inv_rs);
     const float marg = 3.0e-6f * Rf + (BEAM ? bc->lift : 0.0f);      // float32 error of a radius near R + the cheap decode
@@ -601,6 +646,14 @@ MRTX_HD inline int walk_step(const HeightField& hf, float Rf, float inv_rs, Walk
     }
     if (BEAM && !beam_level_ok(hf, L - 1, cj, bc->rho_tex)) { sx_out = sd; return TR_CANDIDATE; }
     w.s = sd; w.L = L - 1; w.I = ci; w.J = cj;
+#if MRTX_PREFETCH
+    if (pre) {
+        const unsigned pair = (cj & 1) ? ch1 : ch0;
+        w.vnext = (float)(int16_t)((ci & 1) ? pair >> 16 : pair & 0xffffu);
+    } else w.vnext = NAN;
+#else
+    w.vnext = NAN;
+#endif
     return TR_CONTINUE;
 }
 
@@ -614,7 +667,9 @@ MRTX_HD inline int walk_step(const HeightField& hf, float Rf, float inv_rs, Walk
 // needs to climb from level 3 to the top of the pyramid.  "Clear" is exact (conservative bounds only); "not clear"
 // says nothing, the walk just goes on.
 template <bool I16>
-MRTX_HD inline bool ceiling_clear(const HeightField& hf, const FastConsts& K, float inv_rs, const Walk& w, float dmin) {
+MRTX_HD inline bool ceiling_clear(const HeightField& hf, const FastConsts& K, float inv_rs, const Walk& w, float dmin,
+                                  const unsigned* loff = nullptr) {
+    if (!loff) loff = hf.off;
     const float s = w.s;
     const float pd = w.od + s;                                  // p(s) . d  (|d| = 1)
     if (!(pd >= 0.0f)) return false;
@@ -631,8 +686,8 @@ MRTX_HD inline bool ceiling_clear(const HeightField& hf, const FastConsts& K, fl
     for (;;) {
         const float rt2 = fmaf(t, fmaf(2.0f, pd, t), r2);       // r^2 after t, a lower bound of r^2 from there on
         if (rt2 >= Rb2) return true;                            // beyond the bounding sphere
-        const float vmax = I16 ? (float)MRTX_LDG((const int16_t*)hf.dil[L] + (size_t)J * hf.nx[L] + I)
-                               : MRTX_LDG((const float*)hf.dil[L] + (size_t)J * hf.nx[L] + I);
+        const unsigned e = loff[MRTX_MAX_LEVELS + L] + (unsigned)J * (unsigned)lvl_nx(hf, L) + (unsigned)I;
+        const float vmax = I16 ? (float)MRTX_LDG((const int16_t*)hf.lvl_base + e) : MRTX_LDG((const float*)hf.lvl_base + e);
         const float rc = fmaf(K.R, decode_bound<I16>(hf, vmax, inv_rs), marg);
         if (!(rt2 > rc * rc)) return false;
         // distance before which the ray cannot have left the 3 x 3 neighbourhood of its level-L cell

@@ -357,7 +357,10 @@ def test_wavefront_pipeline_equals_filtered_kernel(spp):
     d = np.abs(ia[..., :3].astype(np.int32) - ib[..., :3].astype(np.int32))
     assert int(d.max()) <= 1 and int((d.max(axis=2) > 0).sum()) <= 4
     if spp == 1:
-        assert np.array_equal(ha, hb)
+        # (the two kernels are compiled in different translation units: the same source expression may be contracted
+        #  differently, so records agree to a few ulp rather than bit for bit)
+        assert np.array_equal(ha[..., 0] > 0, hb[..., 0] > 0)
+        assert np.allclose(ha, hb, rtol=1e-12, atol=1e-12)
 
 
 @pytest.mark.parametrize("spp,phase", [(1, 88.0), (16, 90.0), (40, 60.0)])

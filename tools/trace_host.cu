@@ -9,17 +9,26 @@ void mrtx_set_error(const char*, ...) {}
 
 using namespace mrtx_core;
 
+// all levels and their dilated copies in ONE buffer (the walk addresses them as element offsets from hf.lvl_base)
 template <typename T>
-static void build_host_pyramid(HeightField& hf, std::vector<std::vector<T>>& store) {
+static void build_host_pyramid(HeightField& hf, std::vector<T>& all) {
     const int W = hf.W, H = hf.H;
     int top = 0;
     while ((W >> (top + 1)) >= 64 && top + 1 < MRTX_MAX_LEVELS) ++top;
     hf.top = top; hf.nx[0] = W; hf.ny[0] = H - 1;
-    store.resize(top + 1);
-    const T* base = (const T*)hf.base;
+    size_t total = 0;
     for (int k = 1; k <= top; ++k) {
         hf.nx[k] = (W + (1 << k) - 1) >> k; hf.ny[k] = (H - 1 + (1 << k) - 1) >> k;
-        store[k].resize((size_t)hf.nx[k] * hf.ny[k]);
+        hf.off[k] = (unsigned)total; total += (size_t)hf.nx[k] * hf.ny[k];
+        hf.off[MRTX_MAX_LEVELS + k] = 0;
+        if (k >= MRTX_DIL_MIN_LEVEL) { hf.off[MRTX_MAX_LEVELS + k] = (unsigned)total; total += (size_t)hf.nx[k] * hf.ny[k]; }
+    }
+    all.assign(total, T(0));
+    hf.lvl_base = all.data();
+    const T* base = (const T*)hf.base;
+    for (int k = 1; k <= top; ++k) {
+        T* out = all.data() + hf.off[k];
+        hf.level[k] = out;
 #pragma omp parallel for schedule(static)
         for (int J = 0; J < hf.ny[k]; ++J) for (int I = 0; I < hf.nx[k]; ++I) {
             T m;
@@ -30,25 +39,20 @@ static void build_host_pyramid(HeightField& hf, std::vector<std::vector<T>>& sto
             } else {
                 const int inx = hf.nx[k - 1], iny = hf.ny[k - 1];
                 const int r1 = std::min(2 * J + 1, iny - 1), c1 = std::min(2 * I + 1, inx - 1);
-                const T* in = store[k - 1].data();
+                const T* in = (const T*)hf.level[k - 1];
                 m = std::max(std::max(in[(size_t)(2 * J) * inx + 2 * I], in[(size_t)(2 * J) * inx + c1]),
                              std::max(in[(size_t)r1 * inx + 2 * I], in[(size_t)r1 * inx + c1]));
             }
-            store[k][(size_t)J * hf.nx[k] + I] = m;
+            out[(size_t)J * hf.nx[k] + I] = m;
         }
-        hf.level[k] = store[k].data();
     }
-}
-
-template <typename T>
-static void build_host_dil(HeightField& hf, std::vector<std::vector<T>>& store) {
-    store.resize(hf.top + 1);
-    for (int k = MRTX_DIL_MIN_LEVEL; k <= hf.top; ++k) {
+    for (int k = MRTX_DIL_MIN_LEVEL; k <= top; ++k) {
         const int nx = hf.nx[k], ny = hf.ny[k];
-        int reach = ((long long)nx << k) != hf.W ? 2 : 1;
+        int reach = ((long long)nx << k) != W ? 2 : 1;
         if (reach > nx / 2) reach = nx / 2;
-        store[k].resize((size_t)nx * ny);
         const T* in = (const T*)hf.level[k];
+        T* out = all.data() + hf.off[MRTX_MAX_LEVELS + k];
+        hf.dil[k] = out;
 #pragma omp parallel for schedule(static)
         for (int J = 0; J < ny; ++J) for (int I = 0; I < nx; ++I) {
             T m = in[(size_t)J * nx + I];
@@ -56,9 +60,8 @@ static void build_host_dil(HeightField& hf, std::vector<std::vector<T>>& store) 
                 int i = I + d; i = i < 0 ? i + nx : (i >= nx ? i - nx : i);
                 m = std::max(m, in[(size_t)j * nx + i]);
             }
-            store[k][(size_t)J * nx + I] = m;
+            out[(size_t)J * nx + I] = m;
         }
-        hf.dil[k] = store[k].data();
     }
 }
 
@@ -68,8 +71,7 @@ extern "C" void dbg_set(int v) { mrtx_core::g_debug = v; }
 struct HostScene {
     const void* key = nullptr; int W = 0, H = 0;
     HeightField hf;
-    std::vector<std::vector<int16_t>> s16; std::vector<std::vector<float>> s32;
-    std::vector<std::vector<int16_t>> d16; std::vector<std::vector<float>> d32;
+    std::vector<int16_t> s16; std::vector<float> s32;
     std::vector<float2> lon32, latsc32; std::vector<double2> lon64, lat64; std::vector<float> lat32;
 };
 static HostScene g_scene;
@@ -87,7 +89,7 @@ static const HeightField& host_scene(const void* map, int is_i16, int W, int H, 
         for (int i = 0; i <= W; ++i) { double sn, cs; sincospi((2.0 * i + 1.0) / W - 1.0, &sn, &cs); S.lon64[i] = make_double2(cs, sn); S.lon32[i] = make_float2((float)cs, (float)sn); }
         for (int i = 0; i < H; ++i) { double sn, cs; sincospi((i + 0.5) / H, &sn, &cs); S.lat64[i] = make_double2(cs, sn); S.lat32[i] = (float)cs; S.latsc32[i] = make_float2((float)cs, (float)sn); }
         hf.lon32 = S.lon32.data(); hf.lon64 = S.lon64.data(); hf.lat32 = S.lat32.data(); hf.lat64 = S.lat64.data(); hf.latsc32 = S.latsc32.data();
-        if (is_i16) build_host_dil<int16_t>(hf, S.d16); else build_host_dil<float>(hf, S.d32);
+
     }
     S.hf.scale = scale; S.hf.radius_scale = rs; S.hf.dmax = dmax;
     return S.hf;
