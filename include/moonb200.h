@@ -160,6 +160,15 @@ int  mrtx_read_hit_f32(mrtx_ctx* ctx, float* out);          /* [H][W][4] x,y,z,d
 int  mrtx_frame_submit(mrtx_ctx* ctx, const uint8_t* overlay_rgba_pinned, unsigned nsamples,
                        uint8_t* out_rgba_pinned, int* ticket);
 int  mrtx_frame_wait(mrtx_ctx* ctx, int ticket);
+/* Frame-parallel time-lapse across GPUs (renderer_video.py:276-364 feeds ONE encoder, in frame order): a rank that is
+ * not the consumer queues its frame with mrtx_frame_submit_to - as mrtx_frame_submit, but the resolved RGBA8 frame
+ * leaves with ncclSend to rank dst_rank (over NVLink) instead of going to this rank's host memory; mrtx_frame_wait
+ * returns when it has left.  The consumer posts one mrtx_frame_recv per such frame, in the order it wants them: the frame
+ * is received into a device staging buffer and copied on to the caller's pinned buffer; at most two receives are pending,
+ * mrtx_frame_recv_wait blocks until the pixels of that ticket are in host memory.  Needs mrtx_comm_init.           */
+int  mrtx_frame_submit_to(mrtx_ctx* ctx, const uint8_t* overlay_rgba_pinned, unsigned nsamples, int dst_rank, int* ticket);
+int  mrtx_frame_recv(mrtx_ctx* ctx, int src_rank, uint8_t* out_rgba_pinned, int* ticket);
+int  mrtx_frame_recv_wait(mrtx_ctx* ctx, int ticket);
 /* rt._get_hit_at(x, y) -> (hx, hy, hz, hd), moon_renderer.py:1138; hd <= 0 = miss.     */
 int  mrtx_hit_at(mrtx_ctx* ctx, int x, int y, float out4[4]);
 /* device views of the frame buffers (for collectives and zero-copy consumers)        */
@@ -175,6 +184,11 @@ int  mrtx_read_hit_f64(mrtx_ctx* ctx, double* out);
  * [8] float64 test phases executed, [9] lanes in them, [10] traversal steps executed (per warp),
  * [11] lanes in them, [12] ray-start phases, [13] lanes in them, [14] refills, [15] pixels culled */
 int  mrtx_counters(mrtx_ctx* ctx, uint64_t out[16], int reset);
+/* Stopwatch of the trace path (engine switch "profile" = 1): CUDA events at the kernel boundaries of every mrtx_render
+ * since the last reset, summed: out_ms[0] cull_kernel, [1] beam_kernel, [2] trace_kernel_fast, [3] shadow_kernel,
+ * [4] trace_kernel_referee, [5] fold_kernel (first sample chunk / pixel wave of each launch), [6] launches measured.
+ * bench.py reads the dominant kernel's launch duration from it (roofline.achieved).                              */
+int  mrtx_kernel_times(mrtx_ctx* ctx, double out_ms[8], int reset);
 /* the filtered kernel's deferrals since the last reset: [0] samples handed to the exact kernel;
  * [r] / [16 + r] primary / shadow rays deferred for reason r: 1 next to the polar axis or map too
  * coarse, 2 ray enters the cell below the surface, 3-4 window start on the surface, 5-6 middle / end

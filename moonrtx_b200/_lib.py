@@ -66,6 +66,9 @@ _SIGNATURES = {
     "mrtx_resolve": (C.c_int, [c_ctx]),
     "mrtx_frame_submit": (C.c_int, [c_ctx, C.c_void_p, C.c_uint, C.c_void_p, C.POINTER(C.c_int)]),
     "mrtx_frame_wait": (C.c_int, [c_ctx, C.c_int]),
+    "mrtx_frame_submit_to": (C.c_int, [c_ctx, C.c_void_p, C.c_uint, C.c_int, C.POINTER(C.c_int)]),
+    "mrtx_frame_recv": (C.c_int, [c_ctx, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
+    "mrtx_frame_recv_wait": (C.c_int, [c_ctx, C.c_int]),
     "mrtx_read_rgba8": (C.c_int, [c_ctx, C.c_void_p]),
     "mrtx_read_accum_f32": (C.c_int, [c_ctx, C.c_void_p]),
     "mrtx_read_hit_f32": (C.c_int, [c_ctx, C.c_void_p]),
@@ -73,6 +76,7 @@ _SIGNATURES = {
     "mrtx_hit_at": (C.c_int, [c_ctx, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "mrtx_frame_buffers_dev": (C.c_int, [c_ctx, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "mrtx_counters": (C.c_int, [c_ctx, C.POINTER(C.c_uint64), C.c_int]),
+    "mrtx_kernel_times": (C.c_int, [c_ctx, C.POINTER(C.c_double), C.c_int]),
     "mrtx_defer_stats": (C.c_int, [c_ctx, C.POINTER(C.c_uint64), C.c_int]),
     "mrtx_comm_unique_id": (C.c_int, [C.c_char_p, C.c_void_p]),
     "mrtx_comm_init": (C.c_int, [c_ctx, C.c_char_p, C.c_int, C.c_int, C.c_void_p]),

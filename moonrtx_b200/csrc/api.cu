@@ -94,6 +94,8 @@ int mrtx_destroy(mrtx_ctx* ctx) {
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     pipe_release(ctx);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->comm_stream) { cudaStreamSynchronize(ctx->comm_stream); cudaStreamDestroy(ctx->comm_stream); }
+    for (int q = 0; q < 2; ++q) { cudaFree(ctx->recv_buf[q]); if (ctx->recv_ev[q]) cudaEventDestroy(ctx->recv_ev[q]); }
     free_frame(ctx);
     cudaFree(ctx->d_max_bits);
     cudaFree(ctx->d_work);
@@ -101,6 +103,7 @@ int mrtx_destroy(mrtx_ctx* ctx) {
     cudaFree(ctx->d_defer_stats);
     cudaFree(ctx->wave_buf);
     cudaFree(ctx->sq_buf);
+    if (ctx->prof_ev) { for (int i = 0; i < MRTX_PROF_MAX * MRTX_PROF_EVENTS; ++i) cudaEventDestroy(ctx->prof_ev[i]); free(ctx->prof_ev); }
     cudaFree(ctx->flush_buf);
     cudaFree(ctx->gather_buf);
     cudaEventDestroy(ctx->ev0);
@@ -317,6 +320,18 @@ static void cross3(const double* a, const double* b, double* c) {
 
 }  // extern "C"
 
+int prof_mark(mrtx_ctx* ctx, int which) {
+    if (!ctx->prof_on || ctx->prof_n >= MRTX_PROF_MAX) return MRTX_OK;
+    if (!ctx->prof_ev) {
+        ctx->prof_ev = (cudaEvent_t*)calloc((size_t)MRTX_PROF_MAX * MRTX_PROF_EVENTS, sizeof(cudaEvent_t));
+        if (!ctx->prof_ev) { mrtx_set_error("out of host memory"); return MRTX_ERR_INVALID; }
+        for (int i = 0; i < MRTX_PROF_MAX * MRTX_PROF_EVENTS; ++i) MRTX_CUDA(cudaEventCreate(&ctx->prof_ev[i]));
+    }
+    MRTX_CUDA(cudaEventRecord(ctx->prof_ev[(size_t)ctx->prof_n * MRTX_PROF_EVENTS + which], ctx->stream));
+    if (which == MRTX_PROF_EVENTS - 1) ctx->prof_n += 1;
+    return MRTX_OK;
+}
+
 void free_heightfield(mrtx_ctx* ctx) {
     if (ctx->hf_owned_base) cudaFree(ctx->hf_owned_base);
     if (ctx->hf_levels_owned) cudaFree(ctx->hf_levels_owned);
@@ -461,6 +476,7 @@ int mrtx_set_uint(mrtx_ctx* ctx, const char* name, unsigned a, unsigned b) {
     else if (!strcmp(name, "long_walk")) { MRTX_REQUIRE(a >= 1u, "long_walk must be >= 1"); ctx->sp.long_walk = a; }
     else if (!strcmp(name, "referee_budget")) { MRTX_REQUIRE(a >= 1u, "referee_budget must be >= 1"); ctx->sp.referee_budget = a; }
     else if (!strcmp(name, "ceiling")) ctx->sp.ceiling = a;
+    else if (!strcmp(name, "profile")) ctx->prof_on = a ? 1 : 0;
     else if (!strcmp(name, "blocks_per_sm")) ctx->sp.blocks_per_sm = a;
     else if (!strcmp(name, "shadow_queue")) ctx->sp.shadow_queue = a ? 1u : 0u;
     else if (!strcmp(name, "beam")) { ctx->sp.beam = a ? 1u : 0u; ctx->sp.beam_drop = b; }
@@ -469,13 +485,23 @@ int mrtx_set_uint(mrtx_ctx* ctx, const char* name, unsigned a, unsigned b) {
     return MRTX_OK;
 }
 
+static int alloc_frame(mrtx_ctx* ctx, size_t n);
+
 int mrtx_resize(mrtx_ctx* ctx, int width, int height) {
     MRTX_CTX(ctx);
     MRTX_REQUIRE(width > 0 && height > 0 && width <= 65536 && height <= 65536, "bad frame size %d x %d", width, height);
     if (width == ctx->width && height == ctx->height && ctx->accum) return MRTX_OK;
     MRTX_CUDA(cudaStreamSynchronize(ctx->stream));
     free_frame(ctx);
+    ctx->width = ctx->height = 0;                           // until every buffer of the new size exists
     const size_t n = (size_t)width * height;
+    const int rc = alloc_frame(ctx, n);
+    if (rc) { free_frame(ctx); return rc; }
+    ctx->width = width; ctx->height = height;
+    return MRTX_OK;
+}
+
+static int alloc_frame(mrtx_ctx* ctx, size_t n) {
     MRTX_CUDA(cudaMalloc(&ctx->accum, n * sizeof(float4)));
     MRTX_CUDA(cudaMalloc(&ctx->rgba8, n * sizeof(uchar4)));
     MRTX_CUDA(cudaMalloc(&ctx->hit, n * sizeof(float4)));
@@ -488,7 +514,6 @@ int mrtx_resize(mrtx_ctx* ctx, int width, int height) {
     MRTX_CUDA(cudaMemsetAsync(ctx->accum, 0, n * sizeof(float4), ctx->stream));
     MRTX_CUDA(cudaMemsetAsync(ctx->rgba8, 0, n * sizeof(uchar4), ctx->stream));
     MRTX_CUDA(cudaMemsetAsync(ctx->hit, 0, n * sizeof(float4), ctx->stream));
-    ctx->width = width; ctx->height = height;
     return MRTX_OK;
 }
 
@@ -501,8 +526,11 @@ static void pipe_release(mrtx_ctx* ctx) {
     for (int k = 0; k < 2; ++k) {
         cudaFree(ctx->pipe_overlay[k]); cudaFree(ctx->pipe_rgba8[k]);
         ctx->pipe_overlay[k] = nullptr; ctx->pipe_rgba8[k] = nullptr;
-        if (ctx->pipe_ev_upload[k]) { cudaEventDestroy(ctx->pipe_ev_upload[k]); cudaEventDestroy(ctx->pipe_ev_resolve[k]); cudaEventDestroy(ctx->pipe_ev_d2h[k]); }
+        if (ctx->pipe_ev_upload[k]) cudaEventDestroy(ctx->pipe_ev_upload[k]);
+        if (ctx->pipe_ev_resolve[k]) cudaEventDestroy(ctx->pipe_ev_resolve[k]);
+        if (ctx->pipe_ev_d2h[k]) cudaEventDestroy(ctx->pipe_ev_d2h[k]);
         ctx->pipe_ev_upload[k] = ctx->pipe_ev_resolve[k] = ctx->pipe_ev_d2h[k] = nullptr;
+        ctx->pipe_busy[k] = 0;
     }
     ctx->pipe_w = ctx->pipe_h = 0;
 }
@@ -528,15 +556,80 @@ static int pipe_ensure(mrtx_ctx* ctx) {
     return MRTX_OK;
 }
 
+static int frame_submit(mrtx_ctx* ctx, const uint8_t* overlay_rgba_pinned, unsigned nsamples, uint8_t* out_rgba_pinned,
+                        int dst_rank, int* ticket);
+
 int mrtx_frame_submit(mrtx_ctx* ctx, const uint8_t* overlay_rgba_pinned, unsigned nsamples, uint8_t* out_rgba_pinned, int* ticket) {
+    MRTX_REQUIRE(out_rgba_pinned, "null output buffer");
+    return frame_submit(ctx, overlay_rgba_pinned, nsamples, out_rgba_pinned, -1, ticket);
+}
+
+int mrtx_frame_submit_to(mrtx_ctx* ctx, const uint8_t* overlay_rgba_pinned, unsigned nsamples, int dst_rank, int* ticket) {
     MRTX_CTX(ctx);
-    MRTX_REQUIRE(out_rgba_pinned && ticket && nsamples > 0, "null argument / no samples");
+    if (!ctx->nccl_comm) { mrtx_set_error("mrtx_comm_init has not been called"); return MRTX_ERR_STATE; }
+    MRTX_REQUIRE(dst_rank >= 0 && dst_rank < ctx->nranks && dst_rank != ctx->rank, "bad destination rank %d", dst_rank);
+    return frame_submit(ctx, overlay_rgba_pinned, nsamples, nullptr, dst_rank, ticket);
+}
+
+static int comm_stream_ensure(mrtx_ctx* ctx) {
+    if (!ctx->comm_stream) MRTX_CUDA(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+    return MRTX_OK;
+}
+
+int mrtx_frame_recv(mrtx_ctx* ctx, int src_rank, uint8_t* out_rgba_pinned, int* ticket) {
+    MRTX_CTX(ctx);
+    MRTX_REQUIRE(out_rgba_pinned && ticket, "null argument");
+    if (!ctx->nccl_comm) { mrtx_set_error("mrtx_comm_init has not been called"); return MRTX_ERR_STATE; }
+    if (!ctx->accum) { mrtx_set_error("mrtx_resize has not been called"); return MRTX_ERR_STATE; }
+    MRTX_REQUIRE(src_rank >= 0 && src_rank < ctx->nranks && src_rank != ctx->rank, "bad source rank %d", src_rank);
+    int rc = comm_stream_ensure(ctx);
+    if (rc) return rc;
+    const size_t bytes = (size_t)ctx->width * ctx->height * sizeof(uchar4);
+    if (ctx->recv_bytes != bytes) {
+        MRTX_CUDA(cudaStreamSynchronize(ctx->comm_stream));
+        for (int q = 0; q < 2; ++q) {
+            cudaFree(ctx->recv_buf[q]); ctx->recv_buf[q] = nullptr;
+            MRTX_CUDA(cudaMalloc(&ctx->recv_buf[q], bytes));
+            if (!ctx->recv_ev[q]) MRTX_CUDA(cudaEventCreateWithFlags(&ctx->recv_ev[q], cudaEventDisableTiming));
+            ctx->recv_busy[q] = 0;
+        }
+        ctx->recv_bytes = bytes; ctx->recv_slot = 0;
+    }
+    const int q = ctx->recv_slot;
+    if (ctx->recv_busy[q]) {
+        mrtx_set_error("two received frames are pending: mrtx_frame_recv_wait(%d) must be called first", q);
+        return MRTX_ERR_STATE;
+    }
+    rc = comm_recv_bytes(ctx, ctx->recv_buf[q], bytes, src_rank, ctx->comm_stream);
+    if (rc) return rc;
+    MRTX_CUDA(cudaMemcpyAsync(out_rgba_pinned, ctx->recv_buf[q], bytes, cudaMemcpyDeviceToHost, ctx->comm_stream));
+    MRTX_CUDA(cudaEventRecord(ctx->recv_ev[q], ctx->comm_stream));
+    ctx->recv_busy[q] = 1; ctx->recv_slot = q ^ 1;
+    *ticket = q;
+    return MRTX_OK;
+}
+
+int mrtx_frame_recv_wait(mrtx_ctx* ctx, int ticket) {
+    MRTX_CTX(ctx);
+    MRTX_REQUIRE((ticket == 0 || ticket == 1) && ctx->recv_ev[ticket] && ctx->recv_busy[ticket], "no such received frame pending");
+    MRTX_CUDA(cudaEventSynchronize(ctx->recv_ev[ticket]));
+    ctx->recv_busy[ticket] = 0;
+    return MRTX_OK;
+}
+
+static int frame_submit(mrtx_ctx* ctx, const uint8_t* overlay_rgba_pinned, unsigned nsamples, uint8_t* out_rgba_pinned,
+                        int dst_rank, int* ticket) {
+    MRTX_CTX(ctx);
+    MRTX_REQUIRE(ticket && nsamples > 0, "null argument / no samples");
     if (!ctx->accum) { mrtx_set_error("mrtx_resize has not been called"); return MRTX_ERR_STATE; }
     if (!ctx->hf.base) { mrtx_set_error("no displacement map set"); return MRTX_ERR_STATE; }
     int rc = pipe_ensure(ctx);
     if (rc) return rc;
     const int k = ctx->pipe_slot;
-    ctx->pipe_slot ^= 1;
+    if (ctx->pipe_busy[k]) {
+        mrtx_set_error("two frames are in flight: mrtx_frame_wait(%d) must be called before the next submit", k);
+        return MRTX_ERR_STATE;
+    }
     const size_t n = (size_t)ctx->width * ctx->height, bytes = n * sizeof(uchar4);
     if (overlay_rgba_pinned) {
         // slot k's overlay was last read by the resolve of the frame two submits ago
@@ -552,9 +645,21 @@ int mrtx_frame_submit(mrtx_ctx* ctx, const uint8_t* overlay_rgba_pinned, unsigne
     rc = launch_resolve_to(ctx, overlay_rgba_pinned ? ctx->pipe_overlay[k] : nullptr, ctx->pipe_rgba8[k]);
     if (rc) return rc;
     MRTX_CUDA(cudaEventRecord(ctx->pipe_ev_resolve[k], ctx->stream));
-    MRTX_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->pipe_ev_resolve[k], 0));
-    MRTX_CUDA(cudaMemcpyAsync(out_rgba_pinned, ctx->pipe_rgba8[k], bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
-    MRTX_CUDA(cudaEventRecord(ctx->pipe_ev_d2h[k], ctx->copy_stream));
+    if (dst_rank < 0) {
+        MRTX_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->pipe_ev_resolve[k], 0));
+        MRTX_CUDA(cudaMemcpyAsync(out_rgba_pinned, ctx->pipe_rgba8[k], bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        MRTX_CUDA(cudaEventRecord(ctx->pipe_ev_d2h[k], ctx->copy_stream));
+    } else {
+        // the frame leaves over NVLink instead: ncclSend from the slot, which is free again when the send has completed
+        rc = comm_stream_ensure(ctx);
+        if (rc) return rc;
+        MRTX_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->pipe_ev_resolve[k], 0));
+        rc = comm_send_bytes(ctx, ctx->pipe_rgba8[k], bytes, dst_rank, ctx->comm_stream);
+        if (rc) return rc;
+        MRTX_CUDA(cudaEventRecord(ctx->pipe_ev_d2h[k], ctx->comm_stream));
+    }
+    ctx->pipe_busy[k] = 1;
+    ctx->pipe_slot = k ^ 1;                                 // (only a frame that was queued completely takes its slot)
     *ticket = k;
     return MRTX_OK;
 }
@@ -563,6 +668,7 @@ int mrtx_frame_wait(mrtx_ctx* ctx, int ticket) {
     MRTX_CTX(ctx);
     MRTX_REQUIRE((ticket == 0 || ticket == 1) && ctx->pipe_ev_d2h[ticket], "no such frame in flight");
     MRTX_CUDA(cudaEventSynchronize(ctx->pipe_ev_d2h[ticket]));
+    ctx->pipe_busy[ticket] = 0;
     return MRTX_OK;
 }
 
@@ -617,6 +723,27 @@ int mrtx_frame_buffers_dev(mrtx_ctx* ctx, void** accum_dev, void** rgba8_dev, vo
     if (accum_dev) *accum_dev = ctx->accum;
     if (rgba8_dev) *rgba8_dev = ctx->rgba8;
     if (hit_dev) *hit_dev = ctx->hit;
+    return MRTX_OK;
+}
+
+int mrtx_kernel_times(mrtx_ctx* ctx, double out_ms[8], int reset) {
+    MRTX_CTX(ctx);
+    MRTX_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < ctx->prof_n; ++i) {
+        cudaEvent_t* e = ctx->prof_ev + (size_t)i * MRTX_PROF_EVENTS;
+        for (int k = 1; k < MRTX_PROF_EVENTS; ++k) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, e[k - 1], e[k]) == cudaSuccess) ctx->prof_ms[k - 1] += (double)ms;
+        }
+        ctx->prof_launches += 1;
+    }
+    (void)cudaGetLastError();
+    ctx->prof_n = 0;
+    if (out_ms) {
+        for (int k = 0; k < 6; ++k) out_ms[k] = ctx->prof_ms[k];
+        out_ms[6] = (double)ctx->prof_launches; out_ms[7] = 0.0;
+    }
+    if (reset) { for (int k = 0; k < 8; ++k) ctx->prof_ms[k] = 0.0; ctx->prof_launches = 0; }
     return MRTX_OK;
 }
 

@@ -26,6 +26,8 @@ struct NcclApi {
     int (*CommDestroy)(nccl_comm_t);
     int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t);
     int (*AllGather)(const void*, void*, size_t, int, nccl_comm_t, cudaStream_t);
+    int (*Send)(const void*, size_t, int, int, nccl_comm_t, cudaStream_t);
+    int (*Recv)(void*, size_t, int, int, nccl_comm_t, cudaStream_t);
     const char* (*GetErrorString)(int);
 };
 
@@ -46,6 +48,8 @@ int load_nccl(const char* path) {
     SYM(CommDestroy, "ncclCommDestroy")
     SYM(AllReduce, "ncclAllReduce")
     SYM(AllGather, "ncclAllGather")
+    SYM(Send, "ncclSend")
+    SYM(Recv, "ncclRecv")
     SYM(GetErrorString, "ncclGetErrorString")
 #undef SYM
     g_nccl.lib = lib;
@@ -88,6 +92,18 @@ __global__ void unpack_rows_kernel(uchar4* __restrict__ frame, const uchar4* __r
 
 }  // namespace
 
+// point-to-point legs of the frame pipeline (api.cu: mrtx_frame_submit_to / mrtx_frame_recv)
+int comm_send_bytes(mrtx_ctx* ctx, const void* buf_dev, size_t bytes, int peer, cudaStream_t st) {
+    if (!ctx->nccl_comm) { mrtx_set_error("mrtx_comm_init has not been called"); return MRTX_ERR_STATE; }
+    MRTX_NCCL(g_nccl.Send(buf_dev, bytes, NCCL_UINT8, peer, (nccl_comm_t)ctx->nccl_comm, st));
+    return MRTX_OK;
+}
+int comm_recv_bytes(mrtx_ctx* ctx, void* buf_dev, size_t bytes, int peer, cudaStream_t st) {
+    if (!ctx->nccl_comm) { mrtx_set_error("mrtx_comm_init has not been called"); return MRTX_ERR_STATE; }
+    MRTX_NCCL(g_nccl.Recv(buf_dev, bytes, NCCL_UINT8, peer, (nccl_comm_t)ctx->nccl_comm, st));
+    return MRTX_OK;
+}
+
 extern "C" {
 
 int mrtx_comm_unique_id(const char* libnccl_path, uint8_t id128[128]) {
@@ -120,6 +136,7 @@ int mrtx_comm_destroy(mrtx_ctx* ctx) {
     if (!ctx || !ctx->nccl_comm) return MRTX_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm_stream) cudaStreamSynchronize(ctx->comm_stream);
     g_nccl.CommDestroy((nccl_comm_t)ctx->nccl_comm);
     ctx->nccl_comm = nullptr;
     ctx->nranks = 0;

@@ -40,6 +40,8 @@ void mrtx_set_error(const char* fmt, ...);
     } while (0)
 
 // ---- scene state ------------------------------------------------------------------
+#define MRTX_PROF_MAX 256
+#define MRTX_PROF_EVENTS 7       // before cull, after cull, beam, trace_kernel_fast, shadow_kernel, referee, fold
 #define MRTX_MAX_LEVELS 20
 #define MRTX_DIL_MIN_LEVEL 2     // lowest level that has a dilated copy (beam pre-pass)
 
@@ -142,6 +144,17 @@ struct mrtx_ctx {
     uchar4* pipe_overlay[2]; uchar4* pipe_rgba8[2];
     cudaEvent_t pipe_ev_upload[2], pipe_ev_resolve[2], pipe_ev_d2h[2];
     int pipe_slot, pipe_w, pipe_h;
+    int pipe_busy[2];           // slot queued and not yet waited for
+    // frames delivered to another rank (mrtx_frame_submit_to) / received from one (mrtx_frame_recv): NCCL point-to-point
+    // on a third stream; two staging buffers and events on the receiving side
+    cudaStream_t comm_stream;
+    uchar4* recv_buf[2]; cudaEvent_t recv_ev[2]; int recv_slot, recv_busy[2]; size_t recv_bytes;
+
+    // per-kernel stopwatch of the trace path (mrtx_set_uint("profile", 1), mrtx_kernel_times): events at the kernel
+    // boundaries of every mrtx_render, read and summed on request
+    int prof_on, prof_n;
+    cudaEvent_t* prof_ev;       // MRTX_PROF_MAX launches x MRTX_PROF_EVENTS events
+    double prof_ms[8]; unsigned prof_launches;
 
     // comm
     void* nccl_lib; void* nccl_comm; int nranks, rank;
@@ -157,5 +170,8 @@ int launch_synth_color(mrtx_ctx* ctx, uint8_t* out_dev, int W, int H, uint32_t s
 int build_pyramid(mrtx_ctx* ctx);
 int launch_trace(mrtx_ctx* ctx, int x0, int y0, int x1, int y1, unsigned s0, unsigned ns);
 int launch_resolve(mrtx_ctx* ctx);
+int prof_mark(mrtx_ctx* ctx, int which);
+int comm_send_bytes(mrtx_ctx* ctx, const void* buf_dev, size_t bytes, int peer, cudaStream_t st);
+int comm_recv_bytes(mrtx_ctx* ctx, void* buf_dev, size_t bytes, int peer, cudaStream_t st);     // record event `which` of the current launch (no-op unless profiling)
 int launch_resolve_to(mrtx_ctx* ctx, const uchar4* overlay_dev, uchar4* out_dev);
 void free_heightfield(mrtx_ctx* ctx);

@@ -235,7 +235,7 @@ trace_kernel_fast(const __grid_constant__ RenderArgs A) {
                     ++rs.hits;
                     if (shadowed) { ++rs.shadow; if (occluded) ++rs.occluded; }
                     if (!occluded) { acc.x += lit.x; acc.y += lit.y; acc.z += lit.z; }
-                } else write_miss(A, x, y, sm == A.sample0);
+                } else write_miss(A, x, y, sm == A.hit_sample);
             }
             // deferred samples of each pixel -> its leader's mask (bit = sample index in this launch)
             const unsigned dm = __ballot_sync(FULL, defer);
@@ -460,14 +460,17 @@ static int launch_fast(mrtx_ctx* ctx, RenderArgs& A, long long npix) {
 
 template <bool I16>
 static int launch_trace_t(mrtx_ctx* ctx, RenderArgs& A, unsigned s0, unsigned ns) {
+    prof_mark(ctx, 0);
     int rc = launch_cull(ctx, A);
     if (rc) return rc;
+    prof_mark(ctx, 1);
     const long long npix = (long long)(A.x1 - A.x0) * (A.y1 - A.y0);
     if (ctx->sp.beam && ctx->sp.jitter && ns >= 4u && ctx->hf.top >= MRTX_DIL_MIN_LEVEL) {
         A.beam_s = ctx->beam_s; A.beam_l = ctx->beam_l;
         const unsigned blocks = (unsigned)std::min<long long>((npix + 255) / 256, (long long)ctx->sm_count * 16);
         beam_kernel<I16><<<blocks, 256, 0, ctx->stream>>>(A);
     }
+    prof_mark(ctx, 2);
     const bool queue = ctx->sp.shadow_queue != 0 && ctx->sp.shadows != 0;
     const size_t SQ_MAX = (size_t)1 << 26;                  // 64 Mi queued rays = 5 GiB; larger launches run in waves of pixels
     int sq_blocks = 0;
@@ -502,16 +505,21 @@ static int launch_trace_t(mrtx_ctx* ctx, RenderArgs& A, unsigned s0, unsigned ns
                 MRTX_CUDA(cudaMemsetAsync(A.work_counter + 2, 0, 2 * sizeof(unsigned), ctx->stream));
                 MRTX_CUDA(cudaMemsetAsync(A.work_counter + 5, 0, 2 * sizeof(unsigned), ctx->stream));
             }
+            const bool first = !done && !p0;                // (the stopwatch brackets the first chunk and wave of a launch)
             rc = queue ? launch_fast<I16, true>(ctx, A, A.wave_np) : launch_fast<I16, false>(ctx, A, A.wave_np);
             if (rc) return rc;
+            if (first) prof_mark(ctx, 3);
             if (queue) shadow_kernel<I16><<<sq_blocks, 128, 0, ctx->stream>>>(A);
+            if (first) prof_mark(ctx, 4);
             trace_kernel_referee<I16, false><<<ctx->sm_count * 8, 64, 0, ctx->stream>>>(A);
+            if (first) prof_mark(ctx, 5);
         }
     }
     {
         const size_t n = (size_t)ctx->width * ctx->height;
         fold_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->accum, ctx->accfix, n);
     }
+    prof_mark(ctx, 6);
     MRTX_CUDA(cudaGetLastError());
     return MRTX_OK;
 }

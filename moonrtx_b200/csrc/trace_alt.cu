@@ -37,7 +37,7 @@ trace_kernel_simple(const __grid_constant__ RenderArgs A) {
                 }
                 acc.x += lit.x; acc.y += lit.y; acc.z += lit.z;
             } else {
-                write_miss(A, x, y, sm == A.sample0);
+                write_miss(A, x, y, sm == A.hit_sample);
             }
         }
         float4* ap = A.accum + (size_t)y * A.width + x;
@@ -141,7 +141,7 @@ trace_kernel_persistent(const __grid_constant__ RenderArgs A) {
                     if (!shadow) ++rs.inside;
                 } else {
                     if (shadow) { acc.x += lit.x; acc.y += lit.y; acc.z += lit.z; }
-                    else write_miss(A, x, y, sm == A.sample0);
+                    else write_miss(A, x, y, sm == A.hit_sample);
                     retire_sample();
                 }
             }
@@ -180,7 +180,7 @@ trace_kernel_persistent(const __grid_constant__ RenderArgs A) {
                     if (trav_advance(A.hf, st, sx, face)) mode = M_TRAV;
                     else {
                         if (shadow) { acc.x += lit.x; acc.y += lit.y; acc.z += lit.z; }
-                        else write_miss(A, x, y, sm == A.sample0);
+                        else write_miss(A, x, y, sm == A.hit_sample);
                         retire_sample();
                     }
                 }
@@ -196,7 +196,7 @@ trace_kernel_persistent(const __grid_constant__ RenderArgs A) {
                     else if (r == TR_END) {
                         // primary: missed the terrain; shadow: the sun is visible
                         if (shadow) { acc.x += lit.x; acc.y += lit.y; acc.z += lit.z; }
-                        else write_miss(A, x, y, sm == A.sample0);
+                        else write_miss(A, x, y, sm == A.hit_sample);
                         retire_sample();
                     }
                 }
@@ -444,7 +444,7 @@ shade_kernel(const __grid_constant__ RenderArgs A) {
                         ++rs.shadow;
                         spawn = walk_begin(A.hf, A.sp.radius, S, 0.0, A.lvl_shadow, sw);
                     }
-                } else write_miss(A, d.x, d.y, d.sm == A.sample0);
+                } else write_miss(A, d.x, d.y, d.sm == A.hit_sample);
             }
             float* slot = A.rad + (size_t)it * 3;
             slot[0] = lit.x; slot[1] = lit.y; slot[2] = lit.z;

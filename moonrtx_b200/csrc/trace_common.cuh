@@ -48,6 +48,8 @@ struct RenderArgs {
     SceneParams sp;
     int width, height, x0, y0, x1, y1;
     unsigned sample0, nsamples;
+    unsigned hit_sample;             // the sample whose first hit goes to the hit buffer: sample 0 of the cycle, whichever launch,
+                                     // chunk or rank traces it (rt._get_hit_at, moon_renderer.py:1138)
     float4* accum; float4* hit; double4* hit64;
     unsigned long long* counters;
     unsigned* work_counter;          // [0] persistent kernel: next unclaimed entry, [1] pixel list length,
@@ -182,7 +184,7 @@ __device__ __forceinline__ bool shade_hit(const RenderArgs& A, const Ray64& R, c
     const double ln = 1.0 / sqrt(lx * lx + ly * ly + lz * lz);
     lx *= ln; ly *= ln; lz *= ln;
     const double cosl = nx * lx + ny * ly + nz * lz;
-    if (sm == A.sample0 && A.hit) {
+    if (sm == A.hit_sample && A.hit) {
         // scene = pos + R^T p_body
         const float hx = (float)(sp.pos[0] + sp.ex[0] * px + sp.ey[0] * py + sp.ez[0] * pz);
         const float hy = (float)(sp.pos[1] + sp.ex[1] * px + sp.ey[1] * py + sp.ez[1] * pz);
@@ -365,7 +367,7 @@ __device__ __forceinline__ bool shade_fast(const RenderArgs& A, const Ray64& R, 
     const double ln = d_rsqrt(tx * tx + ty * ty + tz * tz);
     const double lx = tx * ln, ly = ty * ln, lz = tz * ln;
     const float cosl = nx * (float)lx + ny * (float)ly + nz * (float)lz;
-    if (sm == A.sample0 && A.hit) {
+    if (sm == A.hit_sample && A.hit) {
         // scene = pos + R^T p_body
         const float hx = (float)(sp.pos[0] + sp.ex[0] * px + sp.ey[0] * py + sp.ez[0] * pz);
         const float hy = (float)(sp.pos[1] + sp.ex[1] * px + sp.ey[1] * py + sp.ez[1] * pz);
@@ -572,7 +574,7 @@ trace_kernel_referee(const __grid_constant__ RenderArgs A) {
             TraceOut h;
             const int who = referee_ray<I16>(A, stack, R, 0.0, A.hf.top - 3, false, fast, fh, h, cnt, entered);
             if (lane == 0) { ++rs.primary; if (entered) ++rs.inside; }
-            if (who < 0) { if (lane == 0) write_miss(A, x, y, sm == A.sample0); continue; }
+            if (who < 0) { if (lane == 0) write_miss(A, x, y, sm == A.hit_sample); continue; }
             float3 lit = make_float3(0.f, 0.f, 0.f);
             bool need_shadow = false;
             if (lane == who) need_shadow = fast ? shade_fast(A, R, fh, x, y, pixel, sm, lit, S) : shade_hit(A, R, h, x, y, pixel, sm, lit, S);
@@ -618,7 +620,7 @@ static void fill_render_args(mrtx_ctx* ctx, int x0, int y0, int x1, int y1, unsi
     A.hf = ctx->hf; A.tex = ctx->tex[0]; A.cam = ctx->cam; A.sp = ctx->sp;
     A.width = ctx->width; A.height = ctx->height;
     A.x0 = x0; A.y0 = y0; A.x1 = x1; A.y1 = y1;
-    A.sample0 = s0; A.nsamples = ns;
+    A.sample0 = s0; A.nsamples = ns; A.hit_sample = 0u;
     A.accum = ctx->accum; A.hit = ctx->hit;
     A.hit64 = ctx->sp.debug_hits ? ctx->hit64 : nullptr;
     A.counters = ctx->d_counters;

@@ -197,6 +197,29 @@ class B200OptiX:
         if refresh:
             self.refresh_scene()
 
+    def set_graph(self, name: str, pos=None, edges=None, r=None, c=None, mat=None, refresh: bool = False, **_):
+        """Grid / label / pin tube geometry (renderer_labels.py:263-305, renderer_pins.py:18-55): recorded, not
+        rendered - the reference's update_overlays() runs unchanged against the drop-in."""
+        self._ignored_geometry[name] = {"geom": "Graph", "pos": pos, "edges": edges, "r": r, "c": c, "mat": mat}
+        if refresh:
+            self.refresh_scene()
+
+    def update_graph(self, name: str, pos=None, edges=None, r=None, c=None, mat=None, refresh: bool = False, **_):
+        if name not in self._ignored_geometry:
+            raise ValueError(f"no geometry named {name}")
+        self._ignored_geometry[name].update({k: w for k, w in (("pos", pos), ("edges", edges), ("r", r), ("c", c), ("mat", mat))
+                                             if w is not None})
+        if refresh:
+            self.refresh_scene()
+
+    def delete_geometry(self, name: str):
+        if name == self._moon_name:
+            raise ValueError("the displaced surface cannot be deleted")
+        self._ignored_geometry.pop(name, None)
+
+    def get_geometry_names(self):
+        return [self._moon_name] + list(k for k in self._ignored_geometry if not k.startswith("material:"))
+
     def update_data(self, name: str, pos=None, r=None, u=None, v=None, c=None, refresh: bool = False, **_):
         if name == self._moon_name:
             with self._padlock:
@@ -378,7 +401,40 @@ class B200OptiX:
             return self._img_rgba if read_back else None
 
     # ---- pipelined frames (time-lapse export) --------------------------------------------------------
-    def submit_frame(self, overlay: Optional[np.ndarray] = None) -> int:
+    def kernel_times(self, reset: bool = False) -> dict:
+        """Per-kernel CUDA-event times of the mrtx_render calls since the last reset (engine switch "profile")."""
+        out = (C.c_double * 8)()
+        with self._padlock:
+            _lib.check(self._lib.mrtx_kernel_times(self._ctx, out, 1 if reset else 0))
+        names = ("cull_kernel", "beam_kernel", "trace_kernel_fast", "shadow_kernel", "trace_kernel_referee", "fold_kernel")
+        d = {k: float(out[i]) for i, k in enumerate(names)}
+        d["launches"] = int(out[6])
+        return d
+
+    def recv_frame(self, src: int) -> int:
+        """Consumer side of a frame-parallel time-lapse: post the receive of the next frame that rank `src` sends with
+        submit_frame(dst=this rank).  Returns a ticket for wait_recv(); at most two receives are pending."""
+        with self._padlock:
+            if not hasattr(self, "_recv_out"):
+                self._recv_out = [self.pinned_empty((self._height, self._width, 4), np.uint8) for _ in range(2)]
+            ticket = C.c_int()
+            # (the library hands out its two staging slots in turn: the pinned buffer of the same index goes with it)
+            k = getattr(self, "_recv_next", 0)
+            _lib.check(self._lib.mrtx_frame_recv(self._ctx, int(src), self._recv_out[k].ctypes.data, C.byref(ticket)))
+            assert ticket.value == k
+            self._recv_next = k ^ 1
+            return k
+
+    def wait_recv(self, ticket: int) -> np.ndarray:
+        """Block until the received frame is in host memory (pinned [H, W, 4] uint8, reused by the receive after next)."""
+        _lib.check(self._lib.mrtx_frame_recv_wait(self._ctx, int(ticket)))
+        img = self._recv_out[int(ticket)]
+        with self._padlock:
+            if self._encoder is not None:
+                self._encoder.grab(img)
+        return img
+
+    def submit_frame(self, overlay: Optional[np.ndarray] = None, dst: Optional[int] = None) -> int:
         """
         Queue one whole accumulation cycle of the scene as it is now and return at once: overlay upload (an RGBA8
         [H, W, 4] array, copied to pinned memory here; None = no overlay), tracing, resolve and read-back run on the
@@ -392,6 +448,7 @@ class B200OptiX:
                 self._pipe_out = [self.pinned_empty(shape, np.uint8) for _ in range(2)]
                 self._pipe_ovl = [self.pinned_empty(shape, np.uint8) for _ in range(2)]
                 self._pipe_next = 0
+                self._pipe_sent = [False, False]
             k = self._pipe_next
             n = max(1, int(self._params["max_accumulation_frames"]))
             jitter = (n > 1) if self.deterministic is None else (not self.deterministic)
@@ -402,11 +459,17 @@ class B200OptiX:
                     raise ValueError(f"overlay must be uint8 {self._pipe_ovl[k].shape}")
                 # (the library's slot k was last read two submits ago: wait_frame(k) has been called since, or is now)
                 if self._frames_submitted >= 2:
-                    _lib.check(self._lib.mrtx_frame_wait(self._ctx, k))
+                    _lib.check(self._lib.mrtx_frame_wait(self._ctx, k))      # (no-op if wait_frame(k) has been called)
                 np.copyto(self._pipe_ovl[k], overlay)
                 ov_ptr = self._pipe_ovl[k].ctypes.data
             ticket = C.c_int()
-            _lib.check(self._lib.mrtx_frame_submit(self._ctx, ov_ptr, n, self._pipe_out[k].ctypes.data, C.byref(ticket)))
+            if dst is None or int(dst) == getattr(self, "_rank", 0):
+                _lib.check(self._lib.mrtx_frame_submit(self._ctx, ov_ptr, n, self._pipe_out[k].ctypes.data, C.byref(ticket)))
+                self._pipe_sent[k] = False
+            else:
+                # the frame goes to rank dst over NVLink (ncclSend) instead of this rank's host memory
+                _lib.check(self._lib.mrtx_frame_submit_to(self._ctx, ov_ptr, n, int(dst), C.byref(ticket)))
+                self._pipe_sent[k] = True
             assert ticket.value == k
             self._pipe_next ^= 1
             self._frames_submitted += 1
@@ -417,6 +480,10 @@ class B200OptiX:
         reused by the submit after next.  Fires the launch-finished / accumulation-done callbacks like render_cycle."""
         _lib.check(self._lib.mrtx_frame_wait(self._ctx, int(ticket)))
         img = self._pipe_out[int(ticket)]
+        if self._pipe_sent[int(ticket)]:
+            with self._padlock:
+                self._frames_rendered += 1
+            return None                                  # the pixels are on their way to the consumer rank
         with self._padlock:
             self._frames_rendered += 1
             if self._encoder is not None:
@@ -434,6 +501,12 @@ class B200OptiX:
             self._dirty.clear()
             try:
                 self.render_cycle()
+            except _lib.MoonB200Error as e:
+                # a CUDA error is sticky: every later cycle would fail the same way, 20 times a second
+                print(f"B200OptiX render thread stopped: {e}")
+                self._render_error = e
+                self._is_started = False
+                return
             except Exception as e:                       # PlotOptiX logs and continues
                 print(f"B200OptiX render thread: {e}")
 

@@ -111,6 +111,59 @@ def render_timelapse(rt, states: Sequence[FrameState], rank: int = 0, world: int
     return out
 
 
+def render_timelapse_delivered(rt, states: Sequence[FrameState], rank: int, world: int, consumer: int = 0,
+                               on_frame: Optional[Callable[[int, np.ndarray], None]] = None,
+                               overlay_for: Optional[Callable[[int], Optional[np.ndarray]]] = None) -> int:
+    """
+    The F11 export across GPUs with ONE consumer (renderer_video.py:276-364 feeds one encoder, in frame order): frame i is
+    rendered by rank i mod world; every rank but the consumer sends its resolved RGBA8 frames to the consumer over
+    NVLink (B200OptiX.submit_frame(dst=consumer): ncclSend from the device, nothing pickled, nothing through the
+    producer's host memory); the consumer renders its own share, posts the receives in frame order and hands every frame
+    to on_frame(i, img) strictly in order.  Two frames are in flight per rank and two receives pending on the consumer,
+    so tracing, NVLink transfers and the consumer's device-to-host copies overlap.  rt.comm_init() must have been called
+    when world > 1.  Returns the number of frames this rank consumed (n on the consumer, 0 elsewhere).
+    """
+    n = len(states)
+    own = frames_of_rank(n, rank, world)
+    ov = (lambda i: overlay_for(i)) if overlay_for is not None else (lambda i: None)
+    if rank != consumer:
+        pending = None
+        for i in own:
+            apply_frame_state(rt, states[i])
+            t = rt.submit_frame(ov(i), dst=consumer)
+            if pending is not None:
+                rt.wait_frame(pending)
+            pending = t
+        if pending is not None:
+            rt.wait_frame(pending)
+        return 0
+    own_q, own_next = [], 0                  # (frame, ticket) submitted and not yet consumed; next index into own
+    remote = [i for i in range(n) if i % world != rank]
+    rem_q, rem_next = [], 0
+    consumed = 0
+    for i in range(n):
+        while own_next < len(own) and len(own_q) < 2:
+            f = own[own_next]
+            apply_frame_state(rt, states[f])
+            own_q.append((f, rt.submit_frame(ov(f))))
+            own_next += 1
+        while rem_next < len(remote) and len(rem_q) < 2:
+            f = remote[rem_next]
+            rem_q.append((f, rt.recv_frame(f % world)))
+            rem_next += 1
+        if i % world == rank:
+            f, t = own_q.pop(0)
+            img = rt.wait_frame(t)
+        else:
+            f, t = rem_q.pop(0)
+            img = rt.wait_recv(t)
+        assert f == i
+        if on_frame is not None:
+            on_frame(i, img)
+        consumed += 1
+    return consumed
+
+
 def merge_in_order(per_rank: Iterable[dict[int, np.ndarray]], n_frames: int) -> list[np.ndarray]:
     """Frames of all ranks back in time order (what feeds the encoder on rank 0)."""
     merged: dict[int, np.ndarray] = {}

@@ -57,6 +57,26 @@ def main():
         solo = render_timelapse(rt, states, 0, 1)
         for i in range(5):
             assert np.array_equal(frames[i], solo[i]), f"time-lapse frame {i}"
+    # the same time-lapse with ordered delivery over NVLink (ncclSend / ncclRecv through the C ABI): rank 0 is handed
+    # every frame, in order, with its overlay burnt in (renderer_video.py:137-144, 276-364)
+    from moonrtx_b200.video import render_timelapse_delivered
+    states = [scene.frame_state(synth_ephemeris(600.0 * i)) for i in range(7)]
+
+    def overlay(i):
+        ov = np.zeros((H, W, 4), np.uint8)
+        ov[4:12, 4:4 + 8 * (i + 1)] = (255, 255, 255, 200)
+        return ov
+    got = []
+    n = render_timelapse_delivered(rt, states, rank, world, consumer=0, on_frame=lambda i, img: got.append((i, img.copy())),
+                                   overlay_for=overlay)
+    if rank == 0:
+        assert n == 7 and [i for i, _ in got] == list(range(7)), "frames must arrive in order"
+        solo = render_timelapse(rt, states, 0, 1, overlay_for=overlay)
+        for i, img in got:
+            assert np.array_equal(img, solo[i]), f"delivered frame {i}"
+            assert img[8, 6, 0] > 150 and (i == 6 or np.array_equal(img[8, 4 + 8 * (i + 1) + 2], solo[i][8, 4 + 8 * (i + 1) + 2]))
+    else:
+        assert n == 0
     rt.close()
     dist.barrier()
     if rank == 0:

@@ -10,11 +10,14 @@ pytestmark = pytest.mark.gpu
 
 def _gpu_count():
     import ctypes as C
-    from moonrtx_b200 import _lib
-    n = C.c_int()
-    if _lib.load().mrtx_device_count(C.byref(n)) != 0:
+    try:
+        from moonrtx_b200 import _lib
+        n = C.c_int()
+        if _lib.load().mrtx_device_count(C.byref(n)) != 0:
+            return 0
+        return n.value
+    except Exception:                       # library not built / no driver: the CPU suite must still collect
         return 0
-    return n.value
 
 
 @pytest.mark.skipif(_gpu_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
