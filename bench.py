@@ -2,26 +2,27 @@
 """
 bench.py - the headline benchmark of BASELINE.json on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
-    python bench.py --impl reference [--gpus N] ...               # CPU arm (oracle port)
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path (mode frames)
+    python bench.py --mode samples|tiles ...                      # the two single-frame sharding modes
+    python bench.py --impl reference [--gpus N] ...               # CPU arm (oracle port, all host threads)
 
-Workload (config 3 of BASELINE.json, `config.workload`): one step = one 3840x2160 frame of
-the default whole-disk camera with the sun on the terminator, rendered from the full-size
-92160x46080 int16 LOLA-shaped synthetic height map (8.5 GB, generated in HBM) and a colour
-texture, 16 spp progressive accumulation (primary ray + sun shadow ray + Lambert shading
-per sample) followed by the Gamma/Overlay resolve.  With N > 1 GPUs every rank renders its
-own frame of the terminator sweep per step (frame-parallel time-lapse, config 4): weak scaling,
-no data-path collective; `value` = rays traced by all ranks / max-over-ranks device time.
+Workload of the default mode (`config.workload`): BASELINE config 3 frames along the config-4 sweep.  One step = 8
+consecutive 3840x2160 frames of the F11 time-lapse (10-minute steps through a terminator sweep, default whole-disk camera),
+each rendered from the full-size 92160x46080 int16 LOLA-shaped synthetic height map (8.5 GB, generated in HBM) and a colour
+texture with 16 spp (primary ray + sun shadow ray + Lambert shading per sample) and resolved (Gamma / Overlay).  Frame f
+is rendered by rank f mod N: the work of a step does not depend on N (strong scaling; --steps 30 is config 4's 240 frames).
 
-Metric: Mrays/s (primary + shadow rays actually traced, primary rays that miss the Moon
-included), device-timed with CUDA events on the launching stream; `e2e` = the same through
-the public drop-in API as the F11 export loop uses it (B200OptiX.submit_frame / wait_frame, two
-frames in flight: overlay copied to pinned memory and uploaded, scene update, accumulation cycle,
-resolve, RGBA8 frame read back to pinned memory - every frame's copies inside the timed region),
-wall clock between barriers; `--e2e-sync` times the one-frame-at-a-time render_cycle instead.
+Metric: Mrays/s = rays that walk the pyramid (primary rays that enter the bounding sphere + shadow rays) per second;
+`value_incl_culled` adds the primary rays of pixels the cull pass rejects with one sphere test (SURVEY.md 8d counts them).
+`value`: frames rendered back to back with everything resident in HBM, CUDA events on the launching stream, max over
+ranks.  `e2e`: the same frames through the public drop-in API as the export loop uses it - every frame's overlay copied
+to pinned memory and uploaded, scene update, accumulation cycle, resolve, and the RGBA8 frame DELIVERED IN FRAME ORDER
+to rank 0's pinned ring (its own frames device -> host, the other ranks' frames ncclSend -> rank 0 -> host) where a
+consumer reads it - wall clock between barriers.
 """
 
 import argparse
+import glob
 import json
 import os
 import statistics
@@ -41,10 +42,9 @@ COLOR_W, COLOR_H = 27360, 13680
 COLOR_K = 4
 SEED = 20240314
 FRAME_STEP_MIN = 10.0            # config 4: 10-minute steps through the terminator sweep
+FRAMES_PER_STEP = 8              # frames of the sweep per step (divisible by every N the driver uses)
 FALLBACK_HBM_GBS = 6650.0        # /opt/skills/guides/B200_PROFILING.md fallback
-# profiles/r03_trace_kernel_fast_raw.csv (ncu --set full, default workload): 5.489 GB read + 5.908 GB written per launch
-# (the writes are register spill slots evicted from L2); only meaningful for the default workload
-NCU_TRAFFIC_BYTES = 5.489479e9 + 5.908359e9
+SCALE_F32 = float(np.float32(0.5 / 1737400.0))
 
 
 _REAL_STDOUT = None
@@ -146,6 +146,7 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -153,11 +154,31 @@ def dist_env():
     return rank, world, local
 
 
-def frame_states(n, rank, world, steps_total):
-    """Frame (step j, rank r) of the terminator sweep: index j*world + r, 10 minutes apart."""
+def sweep_state(frame):
     from moonrtx_b200 import scene
     from moonrtx_b200.synth import synth_ephemeris
-    return [scene.frame_state(synth_ephemeris((j * world + rank) * FRAME_STEP_MIN)) for j in range(steps_total)]
+    return scene.frame_state(synth_ephemeris(frame * FRAME_STEP_MIN))
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of trace_kernel_fast, from the newest
+    profiles/*_raw.csv (`ncu --set full` of this workload; the csv is the raw page of the report)."""
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_raw.csv"))):
+        try:
+            import csv
+            rows = list(csv.reader(open(path)))
+            hdr = rows[0]
+            ik, ir, iw = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+            units = rows[1]
+            mul = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            for r in rows[2:]:
+                if "trace_kernel_fast" in r[ik]:
+                    val = float(r[ir].replace(",", "")) * mul.get(units[ir], 1.0) + float(r[iw].replace(",", "")) * mul.get(units[iw], 1.0)
+                    best = (val, os.path.basename(path))
+        except Exception:
+            continue
+    return best
 
 
 # ------------------------------------------------------------------------------------------------
@@ -203,6 +224,7 @@ def build_scene(args, local_rank):
                     fov=scene.default_fov())
     rt.setup_light("sun", color=scene.light_radiance(80.0), radius=scene.SUN_RADIUS, in_geometry=False)
     rt.add_postproc("Overlay")
+    rt._bench_texture = tex                 # (the oracle of the parity block samples the same albedo texture)
     return rt, ldem, radius_scale
 
 
@@ -224,41 +246,85 @@ def _radius_scale_ds1(dev, ldem, W, H, band=512):
     return best
 
 
-def downscale_line(dev, peak, skip_cpu):
-    """BASELINE config 1 beside the headline: --downscale 4 of a 23040x11520 int16 map, HBM to HBM, L2 flushed between
-    runs, algorithmic bytes 2*W*H + 4*(W/4)*(H/4); the reference's numpy expression (oracle port, pinned
-    bit for bit on data_loader.py:223-242) timed on one host core next to it, and the two results compared."""
+
+def radius_scale_numpy(ldem_host):
+    """data_loader.py:218-220, 232 at downscale 1: max of fl32(fl32(c * scale) + 1) - monotone in c, so from the max count"""
+    m = np.float32(ldem_host.max())
+    return float(np.float32(np.float32(m * np.float32(SCALE_F32)) + np.float32(1)))
+
+
+def downscale_lines(dev, peak, skip_cpu):
+    """BASELINE config 1 beside the headline (data_loader.py:215-242 on the GPU): --downscale 4 of a 23040x11520 int16 map.
+    HBM to HBM (L2 flushed between runs, algorithmic bytes 2*W*H + 4*(W/4)*(H/4)), the same call with HOST
+    buffers (531 MB up through pinned chunks overlapped with the kernel, 66 MB down), the reference's numpy expression
+    (oracle port pinned bit for bit on data_loader.py:223-242) on one host core, and the full-resolution 92160x46080 map at
+    the application's default factors 3 and 4."""
     from moonrtx_b200 import _lib
-    from moonrtx_b200.data_loader import downscale_elevation_dev
+    from moonrtx_b200.data_loader import downscale_elevation, downscale_elevation_dev
+    out_lines = {}
     W, H, ds = 23040, 11520, 4
     src = dev.alloc(W * H * 2)
     _lib.check(dev.lib.mrtx_synth_ldem_i16_dev(dev.ctx, src.ptr, W, H, SEED))
     out = dev.alloc((W // ds) * (H // ds) * 4)
-    for _ in range(3):
-        downscale_elevation_dev(src, W, H, ds, out, want_scale=False)
-    ts = []
-    for _ in range(10):
-        dev.l2_flush(); dev.synchronize()
-        dev.timer_start()
-        _, rs = downscale_elevation_dev(src, W, H, ds, out)
-        ts.append(dev.timer_stop())
+
+    def time_dev(src, W, H, ds, out, reps=10):
+        for _ in range(3):
+            downscale_elevation_dev(src, W, H, ds, out)
+        ts = []
+        for _ in range(reps):
+            dev.l2_flush(); dev.synchronize()
+            dev.timer_start()
+            _, rs = downscale_elevation_dev(src, W, H, ds, out)
+            ts.append(dev.timer_stop())
+        return statistics.median(ts), rs
     nbytes = 2 * W * H + 4 * (W // ds) * (H // ds)
-    ms = statistics.median(ts)
-    line = {"workload": f"{W}x{H} int16 -> downscale {ds} (BASELINE config 1), HBM to HBM, L2 flushed between runs",
+    ms, rs = time_dev(src, W, H, ds, out)
+    line = {"workload": f"{W}x{H} int16 -> downscale {ds} (BASELINE config 1), HBM to HBM, L2 flushed between runs, radius_scale returned to the host",
             "ms": round(ms, 4), "GBps": round(nbytes / ms / 1e6, 1), "frac_of_hbm_peak": round(nbytes / ms / 1e6 / peak, 4),
             "algorithmic_bytes": nbytes, "launches": 2}
+    host = src.download((H, W), np.int16)
+    # the drop-in's own entry point with host buffers (what load_elevation_data calls)
+    downscale_elevation(host, ds)
+    t0 = time.perf_counter()
+    got, rs_host = downscale_elevation(host, ds)
+    dt = time.perf_counter() - t0
+    line["e2e_host_buffers"] = {"ms": round(dt * 1e3, 2), "GBps": round(nbytes / dt / 1e9, 2), "h2d_bytes": int(host.nbytes), "d2h_bytes": int(got.nbytes),
+                                "api": "moonrtx_b200.data_loader.downscale_elevation(ndarray, 4)"}
     if not skip_cpu:
         from oracle import downscale_oracle as orc
-        host = src.download((H, W), np.int16)
         t0 = time.perf_counter()
         ref, rs_ref = orc.load_elevation(host, ds)
-        dt = time.perf_counter() - t0
-        got = out.download((H // ds, W // ds), np.float32)
-        line["cpu_baseline"] = {"value": round(nbytes / dt / 1e9, 3), "unit": "GB/s", "seconds": round(dt, 2), "cores": 1, "kind": "port",
+        dtc = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": round(nbytes / dtc / 1e9, 3), "unit": "GB/s", "seconds": round(dtc, 2), "cores": 1, "kind": "port",
                                 "sample": "the whole config-1 map, numpy reshape/mean/normalise as data_loader.py:223-242"}
-        line["bit_exact_vs_oracle"] = bool(np.array_equal(got.view(np.uint32), ref.view(np.uint32)) and rs == rs_ref)
+        line["bit_exact_vs_oracle"] = bool(np.array_equal(got.view(np.uint32), ref.view(np.uint32)) and rs_host == rs_ref
+                                           and np.array_equal(out.download((H // ds, W // ds), np.float32).view(np.uint32), ref.view(np.uint32)))
     src.free(); out.free()
-    return line
+    out_lines["config1"] = line
+    return out_lines
+
+
+def downscale_fullres(dev, ldem, peak):
+    """the full-resolution map at the application's factors (main.py default 3; 4): output 1.9 / 1.06 GB, larger than L2"""
+    from moonrtx_b200.data_loader import downscale_elevation_dev
+    res = {}
+    W, H = MAP_W, MAP_H
+    for ds in (3, 4):
+        out = dev.alloc((W // ds) * (H // ds) * 4)
+        ts = []
+        for i in range(4):
+            dev.l2_flush(); dev.synchronize()
+            dev.timer_start()
+            downscale_elevation_dev(ldem, W, H, ds, out)
+            t = dev.timer_stop()
+            if i:
+                ts.append(t)
+        out.free()
+        nbytes = 2 * W * H + 4 * (W // ds) * (H // ds)
+        ms = statistics.median(ts)
+        res[f"ds{ds}"] = {"ms": round(ms, 3), "GBps": round(nbytes / ms / 1e6, 1), "frac_of_hbm_peak": round(nbytes / ms / 1e6 / peak, 4),
+                          "algorithmic_bytes": nbytes}
+    return res
 
 
 def overlay_image(h, w, text_seed):
@@ -271,266 +337,451 @@ def overlay_image(h, w, text_seed):
     return buf
 
 
-def run_ours(args):
-    rank, world, local = dist_env()
-    if world > 1:
-        os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"      # NCCL logs to stdout by default, which carries exactly one JSON line
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    from moonrtx_b200 import _lib
-    from moonrtx_b200.video import apply_frame_state
 
+
+class Dist:
+    """torch.distributed plumbing (barriers and scalar reductions only; the data path uses the library's own NCCL calls)"""
+    def __init__(self, rank, world, local):
+        self.rank, self.world = rank, world
+        if world > 1:
+            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"      # NCCL logs to stdout by default, which carries exactly one JSON line
+            import torch
+            import torch.distributed as dist
+            torch.cuda.set_device(local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            self.torch, self.dist = torch, dist
+
+    def barrier(self, dev):
+        dev.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def _red(self, x, op):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    def max(self, x):
+        return self._red(x, self.dist.ReduceOp.MAX if self.world > 1 else None)
+
+    def sum(self, x):
+        return self._red(x, self.dist.ReduceOp.SUM if self.world > 1 else None)
+
+    def comm_init(self, rt):
+        """the library's own communicator (frame delivery, all-reduce, all-gather): unique id from rank 0"""
+        if self.world == 1:
+            return
+        from moonrtx_b200.optix import B200OptiX
+        uid = [B200OptiX.comm_unique_id() if self.rank == 0 else None]
+        self.dist.broadcast_object_list(uid, src=0)
+        rt.comm_init(self.rank, self.world, uid[0])
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def walked(c):
+    return c["primary_in_sphere"] + c["shadow_rays"]
+
+
+def launches_per_frame(args):
+    """kernels of this library per frame: cull, then per sample chunk and pixel wave trace_kernel_fast + shadow_kernel +
+    trace_kernel_referee, fold, resolve"""
+    chunks = (args.spp + 31) // 32
+    per_chunk = min(args.spp, 32)
+    npix = args.img_w * args.img_h
+    cap = min(npix * per_chunk, 1 << 26)
+    waves = -(-npix // (cap // per_chunk))
+    return 1 + 3 * chunks * waves + 1 + 1
+
+
+# ------------------------------------------------------------------------------------------------
+def parity_block(args, rt, ldem_host, radius_scale, frame, budget_s):
+    """Oracle parity on the very frame the bench renders (and the cpu_baseline timing): the float64 oracle on a strided
+    sub-grid of the frame, (a) 1 spp through the pixel centres: hit / miss decisions and hit radius against the GPU's
+    float64 hit records, (b) the full jittered sample set: 8-bit image against the GPU frame.  Tolerances are north_star's."""
+    from oracle.render_oracle import OracleScene
+    from moonrtx_b200 import _lib, scene
+    from moonrtx_b200.video import apply_frame_state
+    st = sweep_state(frame)
+    dev = rt._dev
+    lib, ctx = dev.lib, dev.ctx
+    cores = os.cpu_count() or 1
+    kw = dict(scale=SCALE_F32, radius_scale=radius_scale, img_w=args.img_w, img_h=args.img_h, u=st.u, v=st.v, eye=st.eye,
+              target=st.target, up=st.up, fov=st.fov, light_pos=st.light_pos, light_radius=st.light_radius,
+              light_radiance=scene.light_radiance(80.0), texture=rt._bench_texture)
+    sc1 = OracleScene(ldem_host, jitter=False, **kw)
+    t0 = time.perf_counter()
+    o = sc1.render(stride=96, nsamples=1)
+    t_cal = time.perf_counter() - t0
+    per_px = t_cal / (o["accum"].shape[0] * o["accum"].shape[1]) * (args.spp + 1)
+    want = max(1, int(budget_s / max(per_px, 1e-9)))
+    stride = max(1, int(np.ceil(np.sqrt(args.img_w * args.img_h / want))))
+    # (a) 1 spp, deterministic
+    o1 = sc1.render(stride=stride, nsamples=1)
+    apply_frame_state(rt, st)
+    _lib.check(lib.mrtx_set_uint(ctx, b"debug_hits", 1, 0))
+    _lib.check(lib.mrtx_set_uint(ctx, b"jitter", 0, 0))
+    _lib.check(lib.mrtx_render(ctx, 0, 0, args.img_w, args.img_h, 0, 1, 1))
+    g = rt.get_hit_records_f64()[::stride, ::stride]
+    _lib.check(lib.mrtx_set_uint(ctx, b"debug_hits", 0, 0))
+    oh, gh = o1["hit64"][..., 0] > 0, g[..., 0] > 0
+    both = oh & gh
+    texel = 2.0 * np.pi * scene.MOON_RADIUS / args.map_w
+    dr = np.abs(g[..., 1] - o1["hit64"][..., 1])[both] / texel
+    # (b) the frame as benchmarked
+    scj = OracleScene(ldem_host, jitter=args.spp > 1, **kw)
+    t0 = time.perf_counter()
+    oj = scj.render(stride=stride, nsamples=args.spp)
+    dt = time.perf_counter() - t0
+    _lib.check(lib.mrtx_set_uint(ctx, b"jitter", 1 if args.spp > 1 else 0, 0))
+    _lib.check(lib.mrtx_render(ctx, 0, 0, args.img_w, args.img_h, 0, args.spp, 1))
+    _lib.check(lib.mrtx_resolve(ctx))
+    img = np.empty((args.img_h, args.img_w, 4), np.uint8)
+    _lib.check(lib.mrtx_read_rgba8(ctx, img.ctypes.data))
+    gi = img[::stride, ::stride, :3].astype(np.float64)
+    oi = scj.tonemap(oj["accum"])[..., :3].astype(np.float64)
+    mae = float(np.abs(gi - oi).mean())
+    mse = float(((gi - oi) ** 2).mean())
+    psnr = 99.0 if mse == 0 else float(10.0 * np.log10(255.0 ** 2 / mse))
+    npx = oi.shape[0] * oi.shape[1]
+    parity = {"frame": frame, "sub_grid": f"every {stride}th pixel in x and y ({npx} pixels)",
+              "hit_mask_mismatches": int((oh != gh).sum()), "hits_compared": int(both.sum()),
+              "hit_radius_max_err_texel": float(dr.max()) if dr.size else 0.0, "hit_radius_over_1e-3_texel": int((dr > 1e-3).sum()),
+              "image_mae_8bit": round(mae, 4), "image_psnr_db": round(psnr, 2), "spp": args.spp,
+              "tolerance": "hit radius <= 1e-3 texel, 8-bit MAE <= 1, PSNR >= 40 dB (north_star)"}
+    parity["ok"] = bool(parity["hit_mask_mismatches"] == 0 and parity["hit_radius_over_1e-3_texel"] == 0 and mae <= 1.0 and psnr >= 40.0)
+    inside = int((oj["stats"][..., 0] > 0).sum()) * args.spp
+    shadow = int((oj["stats"][..., 1] > 0).sum()) * args.spp          # last-sample estimate
+    cpu = {"value": round((inside + shadow) / dt / 1e6, 4), "unit": "Mrays/s", "cores": cores, "kind": "port", "seconds": round(dt, 3),
+           "sample": f"every {stride}th pixel in x and y of frame {frame} ({npx} pixels x {args.spp} spp), {dt:.1f} s, float64 oracle "
+                     f"(exhaustive cell walk, no pyramid), OpenMP {cores} threads; rays counted as for `value`"}
+    return parity, cpu
+
+
+def run_frames(args):
+    rank, world, local = dist_env()
+    D = Dist(rank, world, local)
+    from moonrtx_b200 import _lib
+    from moonrtx_b200.video import apply_frame_state, render_timelapse_delivered
+    if FRAMES_PER_STEP % world:
+        raise SystemExit(f"--gpus must divide {FRAMES_PER_STEP}")
     t_setup = time.time()
     rt, ldem, radius_scale = build_scene(args, local)
     dev = rt._dev
     lib, ctx = dev.lib, dev.ctx
-    total = args.warmup + args.steps
-    states = frame_states(total, rank * args.frame_stride // max(world, 1) if args.frame_stride else rank, args.frame_stride or world, total)
+    D.comm_init(rt)
+    n_warm, n_timed = args.warmup * FRAMES_PER_STEP, args.steps * FRAMES_PER_STEP
+    frames = list(range(n_warm + n_timed))
+    mine_warm = [f for f in frames[:n_warm] if f % world == rank]
+    mine = [f for f in frames[n_warm:] if f % world == rank]
+    states = {f: sweep_state(f) for f in frames}
     t_setup = time.time() - t_setup
-
-    def barrier():
-        dev.synchronize()
-        if world > 1:
-            import torch
-            import torch.distributed as dist
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        import torch
-        import torch.distributed as dist
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(x):
-        if world == 1:
-            return x
-        import torch
-        import torch.distributed as dist
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
     _lib.check(lib.mrtx_set_uint(ctx, b"jitter", 1 if args.spp > 1 else 0, 0))
 
-    def device_step(st):
-        apply_frame_state(rt, st)
+    def device_frame(f):
+        apply_frame_state(rt, states[f])
         _lib.check(lib.mrtx_render(ctx, 0, 0, args.img_w, args.img_h, 0, args.spp, 1))
         _lib.check(lib.mrtx_resolve(ctx))
 
-    # ---- device-resident throughput (value) -------------------------------------------------
+    # ---- device-resident throughput (value) + the kernels' own launch durations (roofline) -------------------------
     clocks = ClockSampler(enabled=rank == 0, gpus=range(world))
     clocks.wait_ready()
-    for j in range(args.warmup):
-        device_step(states[j])
-    rt.counters(reset=True)
-    rt.defer_stats(reset=True)
-    barrier()
+    for f in mine_warm:
+        device_frame(f)
+    rt.counters(reset=True); rt.defer_stats(reset=True)
+    _lib.check(lib.mrtx_set_uint(ctx, b"profile", 1, 0))
+    rt.kernel_times(reset=True)
+    D.barrier(dev)
     clocks.begin()
     dev.timer_start()
-    for j in range(args.warmup, total):
-        device_step(states[j])
+    for f in mine:
+        device_frame(f)
     ms_total = dev.timer_stop()
-    barrier()
+    D.barrier(dev)
     clocks.end()
     clock_info = clocks.stop()
+    kt = rt.kernel_times(reset=True)
+    _lib.check(lib.mrtx_set_uint(ctx, b"profile", 0, 0))
     c = rt.counters()
-    # cull_kernel + trace_kernel_fast + trace_kernel_referee + resolve_kernel per frame (<= 32 spp: one sample chunk)
-    launches = (2 + 2 * ((args.spp + 31) // 32)) * args.steps
     defer = rt.defer_stats()
-    ms_total = max_over_ranks(ms_total)
-    rays_local = c["primary_rays"] + c["shadow_rays"]
-    rays_all = sum_over_ranks(float(rays_local))
+    ms_total = D.max(ms_total)
+    rays_all, rays_all_culled = D.sum(float(walked(c))), D.sum(float(c["primary_rays"] + c["shadow_rays"]))
     value = rays_all / (ms_total * 1e-3) / 1e6
 
-    # ---- dominant kernel alone (roofline) -------------------------------------------------------
-    rt.counters(reset=True)
-    kms = []
-    for j in range(args.warmup, total):
-        apply_frame_state(rt, states[j])
-        dev.synchronize()
-        dev.timer_start()
-        _lib.check(lib.mrtx_render(ctx, 0, 0, args.img_w, args.img_h, 0, args.spp, 1))
-        kms.append(dev.timer_stop())
-    ck = rt.counters()
-    k_ms = sum(kms) / len(kms)
     depth = quadtree_depth(args.map_w)
     b_floor = 32 * (depth + 3)
-    rays_in = (ck["primary_in_sphere"] + ck["shadow_rays"]) / args.steps
-    algo_bytes = b_floor * rays_in
     peak, peak_src = measured_peak()
-    achieved = algo_bytes / (k_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "cull_kernel + trace_kernel_fast<int16> + trace_kernel_referee<int16> (one mrtx_render)", "achieved": round(achieved, 2), "peak": peak,
-                "unit": "GB/s", "frac": round(achieved / peak, 5),
-                "traffic": args.traffic if (args.map_w, args.img_w, args.spp) == (MAP_W, IMG_W, 16) else None,
-                "algorithmic_bytes_per_launch": int(algo_bytes), "bytes_per_ray": b_floor,
-                # what the kernel's own counters say it fetched: one 32-byte sector per node visit, two per patch test
-                "counted_bytes_per_ray": round(32.0 * (ck["node_visits"] + 2 * ck["patch_tests"]) / max(1.0, ck["primary_in_sphere"] + ck["shadow_rays"]), 1),
-                "rays_in_sphere_per_launch": int(rays_in), "kernel_ms": round(k_ms, 3), "peak_source": peak_src,
-                "kernel_share_of_step": round(k_ms * args.steps / ms_total, 4) if world == 1 else None}
+    nl = max(1, kt["launches"])
+    fast_ms, shadow_ms, ref_ms = kt["trace_kernel_fast"] / nl, kt["shadow_kernel"] / nl, kt["trace_kernel_referee"] / nl
+    path_ms = sum(kt[k] for k in ("cull_kernel", "beam_kernel", "trace_kernel_fast", "shadow_kernel", "trace_kernel_referee", "fold_kernel")) / nl
+    nf = max(1, len(mine))
+    prim_bytes = b_floor * c["primary_in_sphere"] / nf
+    shad_bytes = b_floor * c["shadow_rays"] / nf
+    traffic = ncu_traffic() if (args.map_w, args.img_w, args.spp) == (MAP_W, IMG_W, 16) else None
 
-    # ---- end to end through the public API (e2e) ----------------------------------------------------
+    def gbs(nbytes, ms):
+        return nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+    roofline = {
+        "bound": "hbm", "kernel": "trace_kernel_fast<int16, queue> (primary ray to the shaded hit; pushes the shadow ray)",
+        "achieved": round(gbs(prim_bytes, fast_ms), 2), "peak": peak, "unit": "GB/s", "frac": round(gbs(prim_bytes, fast_ms) / peak, 5),
+        "traffic": traffic[0] if traffic else None, "traffic_source": traffic[1] if traffic else None,
+        "algorithmic_bytes_per_launch": int(prim_bytes), "bytes_per_ray": b_floor, "rays_per_launch": int(c["primary_in_sphere"] / nf),
+        "kernel_ms": round(fast_ms, 3), "peak_source": peak_src, "launches_timed": kt["launches"],
+        "timing": "CUDA events on the launching stream at the kernel boundaries of every timed frame (mrtx_kernel_times)",
+        "shadow_kernel": {"kernel_ms": round(shadow_ms, 3), "achieved": round(gbs(shad_bytes, shadow_ms), 2), "frac": round(gbs(shad_bytes, shadow_ms) / peak, 5),
+                          "rays_per_launch": int(c["shadow_rays"] / nf), "algorithmic_bytes_per_launch": int(shad_bytes)},
+        "whole_path": {"kernels": "cull + trace_kernel_fast + shadow_kernel + trace_kernel_referee + fold (one mrtx_render)",
+                       "ms": round(path_ms, 3), "referee_ms": round(ref_ms, 3), "achieved": round(gbs(prim_bytes + shad_bytes, path_ms), 2),
+                       "frac": round(gbs(prim_bytes + shad_bytes, path_ms) / peak, 5)},
+        "counted_bytes_per_ray": round(32.0 * (c["node_visits"] + 2 * c["patch_tests"]) / max(1.0, walked(c)), 1),
+        "kernel_share_of_step": round(fast_ms * nf / ms_total, 4) if world == 1 else None,
+    }
+
+    # ---- end to end through the public API (e2e): the export loop with ordered delivery to rank 0 -------------------------
     e2e = None
     if not args.skip_e2e:
-        overlays = [overlay_image(args.img_h, args.img_w, 37 * j + rank) for j in range(total)]
+        ov_cache = {}
+
+        def overlay_for(f):
+            if f not in ov_cache:
+                ov_cache.clear()
+                ov_cache[f] = overlay_image(args.img_h, args.img_w, 37 * f)
+            return ov_cache[f]
+        sums = []
+        warm_states = [states[f] for f in frames[:n_warm]]
+        render_timelapse_delivered(rt, warm_states, rank, world, 0, on_frame=None, overlay_for=overlay_for)
+        D.barrier(dev)
         rt.counters(reset=True)
-        checksum = 0
-        if args.e2e_sync:
-            # one frame at a time: upload, render, resolve, read back, then the next
-            pinned = rt.pinned_like(overlays[0])
-            for j in range(total):
-                if j == args.warmup:
-                    barrier()
-                    rt.counters(reset=True)
-                    t0 = time.perf_counter()
-                np.copyto(pinned, overlays[j])                       # the label the host drew for this frame
-                rt.set_texture_2d("frame_overlay", pinned, filter_mode="Nearest", refresh=False)
-                apply_frame_state(rt, states[j])
-                img = rt.render_cycle()                               # renders, resolves, reads the frame back
-                checksum = int(img[::97, ::89, :3].sum())
-        else:
-            # the F11 export loop as video.render_timelapse(pipelined=True) runs it: frame j + 1 is submitted (overlay
-            # to pinned memory, scene update, queue) before frame j is waited for and consumed; every frame's overlay
-            # goes host -> device and every frame's pixels come device -> host inside the timed region
-            def consume(ticket):
-                img = rt.wait_frame(ticket)
-                return int(img[::97, ::89, :3].sum())
-            pending = None
-            for j in range(total):
-                if j == args.warmup:
-                    if pending is not None:
-                        consume(pending); pending = None         # nothing in flight across the start of the clock
-                    barrier()
-                    rt.counters(reset=True)
-                    t0 = time.perf_counter()
-                apply_frame_state(rt, states[j])
-                ticket = rt.submit_frame(overlays[j])
-                if pending is not None:
-                    checksum = consume(pending)
-                pending = ticket
-            checksum = consume(pending)                               # ... nor across its end
-        barrier()
-        dt = max_over_ranks(time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        timed_states = [states[f] for f in frames[n_warm:]]
+        render_timelapse_delivered(rt, timed_states, rank, world, 0, on_frame=lambda i, img: sums.append(int(img[::97, ::89, :3].sum())),
+                                   overlay_for=lambda i: overlay_for(n_warm + i))
+        D.barrier(dev)
+        dt = D.max(time.perf_counter() - t0)
         ce = rt.counters()
-        e2e_rays = sum_over_ranks(float(ce["primary_rays"] + ce["shadow_rays"]))
+        e2e_rays = D.sum(float(walked(ce)))
+        frame_bytes = args.img_w * args.img_h * 4
         e2e = {"value": round(e2e_rays / dt / 1e6, 2), "unit": "Mrays/s",
-               "h2d_bytes_per_step": int(overlays[0].nbytes + 1024), "d2h_bytes_per_step": int(args.img_w * args.img_h * 4),
-               "ms_per_step": round(dt * 1e3 / args.steps, 2), "frame_checksum": checksum,
-               "api": "B200OptiX.render_cycle per frame" if args.e2e_sync else "B200OptiX.submit_frame / wait_frame (two frames in flight)"}
+               "h2d_bytes_per_step": int(FRAMES_PER_STEP * (frame_bytes + 1024)), "d2h_bytes_per_step": int(FRAMES_PER_STEP * frame_bytes),
+               "nvlink_bytes_per_step": int(FRAMES_PER_STEP * (world - 1) // world * frame_bytes),
+               "ms_per_step": round(dt * 1e3 / args.steps, 2), "frames_per_s": round(n_timed / dt, 3),
+               "frames_delivered_in_order_to_rank0": len(sums) if rank == 0 else None,
+               "frame_checksum": (sum(sums) & 0xffffffff) if rank == 0 else None,
+               "api": "video.render_timelapse_delivered: B200OptiX.submit_frame(dst=0) / recv_frame / wait_frame, two frames in flight per rank"}
 
-    # ---- CPU baseline (rank 0, N = 1 only): the float64 oracle on a bounded sample -----------------
-    cpu = None
+    # ---- oracle parity on the benchmarked frame + CPU baseline (rank 0, N = 1 only) -----------------------------------
+    parity, cpu = None, None
     if rank == 0 and world == 1 and not args.skip_cpu:
-        cpu = cpu_baseline(args, ldem_host=ldem.download((args.map_h, args.map_w), np.int16),
-                           radius_scale=radius_scale, state=states[args.warmup])
+        parity, cpu = parity_block(args, rt, ldem.download((args.map_h, args.map_w), np.int16), radius_scale, n_warm, budget_s=20.0)
 
-    # ---- config 1 beside it (rank 0): the data_loader downscale against the HBM peak -----------------------
-    downscale = downscale_line(dev, peak, args.skip_cpu) if rank == 0 and not args.skip_downscale else None
+    # ---- config 1 beside it (rank 0): the data_loader downscale against the HBM peak -----------------------------------
+    downscale = None
+    if rank == 0 and not args.skip_downscale:
+        downscale = downscale_lines(dev, peak, args.skip_cpu)
+        if (args.map_w, args.map_h) == (MAP_W, MAP_H) and world == 1:
+            downscale["full_resolution_92160x46080"] = downscale_fullres(dev, ldem, peak)
 
     if rank == 0:
         line = {
             "metric": "Mrays/s (primary+shadow) @4K", "value": round(value, 2), "unit": "Mrays/s",
+            "value_incl_culled": round(rays_all_culled / (ms_total * 1e-3) / 1e6, 2),
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32 (pyramid walk and patch test in a cell-local frame re-based in f64) over int16 texels; f64 referee for undecided samples", "data": "synthetic",
-            "config": {"workload": f"{args.img_w}x{args.img_h} frame, {args.map_w}x{args.map_h} int16 synthetic LOLA map + "
-                                   f"{args.color_w // COLOR_K}x{args.color_h // COLOR_K} colour texture, {args.spp} spp "
-                                   f"(BASELINE config 3; N>1: one frame per rank per step, config 4)",
-                       "spp": args.spp, "camera": "default whole-disk, fov 4.2422 deg", "sun": "terminator sweep from phase 90 deg",
-                       "l2_hygiene": "inputs_larger_than_L2 (8.5 GB map + 2.8 GB pyramid)",
-                       "frames_per_step_per_gpu": 1, "setup_s": round(t_setup, 1)},
-            "rays": {"primary_per_step": c["primary_rays"] // args.steps, "shadow_per_step": c["shadow_rays"] // args.steps,
-                     "primary_in_sphere_per_step": c["primary_in_sphere"] // args.steps,
-                     "node_visits_per_step": c["node_visits"] // args.steps, "patch_tests_per_step": c["patch_tests"] // args.steps,
-                     "overflow": c["overflow"],
-                     "samples_deferred_to_f64_referee_per_step": defer["deferred_samples"] // args.steps,
+            "config": {"workload": f"{FRAMES_PER_STEP} frames per step of the F11 terminator sweep (BASELINE config 4; each frame = config 3: "
+                                   f"{args.img_w}x{args.img_h}, {args.map_w}x{args.map_h} int16 synthetic LOLA map + "
+                                   f"{args.color_w // COLOR_K}x{args.color_h // COLOR_K} colour texture, {args.spp} spp); frame f on rank f mod N",
+                       "spp": args.spp, "camera": "default whole-disk, fov 4.2422 deg", "sun": "terminator sweep from phase 90 deg, 10 min per frame",
+                       "frames_per_step": FRAMES_PER_STEP, "frames_timed": n_timed,
+                       "l2_hygiene": "inputs_larger_than_L2 (8.5 GB map + 2.9 GB pyramid)", "setup_s": round(t_setup, 1)},
+            "rays": {"walked_per_frame": int(rays_all / n_timed), "primary_in_sphere_per_frame": int(D.sum(float(c["primary_in_sphere"])) / n_timed) if world == 1 else None,
+                     "primary_incl_culled_per_frame": c["primary_rays"] // nf, "shadow_per_frame": c["shadow_rays"] // nf,
+                     "node_visits_per_frame": c["node_visits"] // nf, "patch_tests_per_frame": c["patch_tests"] // nf, "overflow": c["overflow"],
+                     "samples_deferred_to_f64_referee_per_frame": defer["deferred_samples"] // nf,
                      "defer_reasons_primary": defer["primary_reasons"], "defer_reasons_shadow": defer["shadow_reasons"]},
-            "frames_per_s": round(world * args.steps / (ms_total * 1e-3), 3),
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clock_info,
-            "downscale": downscale,
+            "frames_per_s": round(n_timed / (ms_total * 1e-3), 3), "ms_per_frame_per_gpu": round(ms_total / nf, 3),
+            "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "e2e": e2e,
+            "gpu_launches": launches_per_frame(args) * n_timed, "clocks": clock_info, "downscale": downscale,
         }
         emit(line)
     rt.close()
-    if world > 1:
-        import torch.distributed as dist
-        dist.destroy_process_group()
+    D.close()
+    if parity is not None and not parity["ok"]:
+        sys.stderr.write(f"PARITY OUT OF TOLERANCE: {parity}\n")
+        sys.exit(3)
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_baseline(args, ldem_host, radius_scale, state, budget_s=20.0):
-    """The oracle (oracle/render_oracle.c, float64, OpenMP on every host core) on a strided sub-grid
-    of the same frame; the stride is chosen so the sample costs about `budget_s` seconds."""
-    from oracle.render_oracle import OracleScene
-    from moonrtx_b200 import scene
-    cores = os.cpu_count() or 1
-    sc = OracleScene(ldem_host, scale=float(np.float32(0.5 / 1737400.0)), radius_scale=radius_scale,
-                     img_w=args.img_w, img_h=args.img_h, u=state.u, v=state.v, eye=state.eye, target=state.target,
-                     up=state.up, fov=state.fov, light_pos=state.light_pos, light_radius=state.light_radius,
-                     light_radiance=scene.light_radiance(80.0), jitter=args.spp > 1)
-    # calibrate on a coarse grid, then size the real sample
-    t0 = time.perf_counter()
-    o = sc.render(stride=96, nsamples=1)
-    t_cal = time.perf_counter() - t0
-    n_cal = o["accum"].shape[0] * o["accum"].shape[1]
-    per_px = t_cal / n_cal * args.spp
-    want = max(1, int(budget_s / max(per_px, 1e-9)))
-    stride = max(1, int(np.ceil(np.sqrt(args.img_w * args.img_h / want))))
-    t0 = time.perf_counter()
-    o = sc.render(stride=stride, nsamples=args.spp)
-    dt = time.perf_counter() - t0
-    npx = o["accum"].shape[0] * o["accum"].shape[1]
-    primary = npx * args.spp
-    # shadow rays = samples that hit a sun-facing slope; the oracle reports the cells walked by each
-    shadow = int((o["stats"][..., 1] > 0).sum()) * args.spp          # last-sample estimate
-    return {"value": round((primary + shadow) / dt / 1e6, 4), "unit": "Mrays/s", "cores": cores, "kind": "port", "seconds": round(dt, 3),
-            "sample": f"every {stride}th pixel in x and y of the same {args.img_w}x{args.img_h} frame "
-                      f"({npx} pixels x {args.spp} spp), {dt:.1f} s, float64 oracle (exhaustive cell walk, no pyramid), "
-                      f"OpenMP {cores} threads"}
+def run_single_frame_mode(args):
+    """--mode samples: ONE config-3 frame, its 16 samples split across the ranks, float4 accumulators summed with
+    ncclAllReduce (mrtx_allreduce_accum).  --mode tiles: ONE config-5 frame (7680x4320, fov 2.5 deg, the terminator at
+    the disk centre: grazing incidence everywhere), interleaved 64x64 tiles split across the ranks in one launch, owned
+    tiles tone-mapped into the send buffer and exchanged with ncclAllGather (mrtx_allgather_tiles).  Strong scaling of a
+    single frame; every rank checks its gathered frame against the frame it renders alone."""
+    rank, world, local = dist_env()
+    D = Dist(rank, world, local)
+    from moonrtx_b200 import _lib
+    from moonrtx_b200.video import apply_frame_state
+    tiles = args.mode == "tiles"
+    if tiles:
+        args.img_w, args.img_h = 7680, 4320
+    rt, ldem, radius_scale = build_scene(args, local)
+    dev = rt._dev
+    lib, ctx = dev.lib, dev.ctx
+    D.comm_init(rt)
+    if world == 1:
+        from moonrtx_b200.optix import B200OptiX
+        rt.comm_init(0, 1, B200OptiX.comm_unique_id())
+    st = sweep_state(0)
+    apply_frame_state(rt, st)
+    if tiles:
+        cam = rt.get_camera("cam1")
+        rt.update_camera("cam1", eye=cam["Eye"], target=cam["Target"], up=cam["Up"], fov=2.5)
+    _lib.check(lib.mrtx_set_uint(ctx, b"jitter", 1 if args.spp > 1 else 0, 0))
+    n = args.spp
+    lo, hi = (n * rank) // world, (n * (rank + 1)) // world
+
+    def step(timed=None):
+        if tiles:
+            _lib.check(lib.mrtx_render_tiles(ctx, 64, 0, n, 1))
+        else:
+            _lib.check(lib.mrtx_render(ctx, 0, 0, args.img_w, args.img_h, lo, hi - lo, 1))
+        if timed is not None:
+            dev.synchronize()
+            dev.timer_start()
+        if tiles:
+            _lib.check(lib.mrtx_allgather_tiles(ctx, 64))
+        else:
+            _lib.check(lib.mrtx_allreduce_accum(ctx))
+            _lib.check(lib.mrtx_resolve(ctx))
+        if timed is not None:
+            timed.append(dev.timer_stop())
+
+    # the frame this rank renders alone (outside the timed region): what the sharded frame must reproduce
+    _lib.check(lib.mrtx_render(ctx, 0, 0, args.img_w, args.img_h, 0, n, 1))
+    _lib.check(lib.mrtx_resolve(ctx))
+    solo = np.empty((args.img_h, args.img_w, 4), np.uint8)
+    _lib.check(lib.mrtx_read_rgba8(ctx, solo.ctypes.data))
+    clocks = ClockSampler(enabled=rank == 0, gpus=range(world))
+    clocks.wait_ready()
+    for _ in range(args.warmup):
+        step()
+    rt.counters(reset=True)
+    D.barrier(dev)
+    clocks.begin()
+    dev.timer_start()
+    for _ in range(args.steps):
+        step()
+    ms_total = dev.timer_stop()
+    D.barrier(dev)
+    clocks.end()
+    clock_info = clocks.stop()
+    c = rt.counters()
+    ms_total = D.max(ms_total)
+    rays_all = D.sum(float(walked(c)))
+    coll = []
+    for _ in range(3):
+        step(coll)
+    got = np.empty_like(solo)
+    _lib.check(lib.mrtx_read_rgba8(ctx, got.ctypes.data))
+    diff = np.abs(got[..., :3].astype(np.int32) - solo[..., :3].astype(np.int32))
+    ok = bool(diff.max() <= (0 if tiles else 1))
+    all_ok = D.sum(1.0 if ok else 0.0) == world
+    coll_ms = D.max(statistics.median(coll))
+    if rank == 0:
+        frame_bytes = args.img_w * args.img_h * 4
+        emit({
+            "metric": "Mrays/s (primary+shadow) @8K, one frame screen-tiled" if tiles else "Mrays/s (primary+shadow) @4K, one frame sample-split",
+            "mode": args.mode, "value": round(rays_all / (ms_total * 1e-3) / 1e6, 2), "unit": "Mrays/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32 walk / f64 re-basing over int16 texels", "data": "synthetic",
+            "config": {"workload": (f"BASELINE config 5: {args.img_w}x{args.img_h}, fov 2.5 deg on the terminator at the disk centre, {n} spp, "
+                                    f"interleaved 64x64 tiles over {world} ranks + ncclAllGather of RGBA8 tiles") if tiles else
+                                   (f"BASELINE config 3: {args.img_w}x{args.img_h}, {n} spp split over {world} ranks + ncclAllReduce of the float4 accumulators"),
+                       "map": f"{args.map_w}x{args.map_h} int16 synthetic LOLA map", "spp": n},
+            "collective": {"what": "resolve of owned tiles into the send buffer + ncclAllGather + untile" if tiles else "ncclAllReduce(sum, f32) of the accumulators + resolve",
+                           "ms": round(coll_ms, 3), "bytes": int(frame_bytes if tiles else frame_bytes * 4),
+                           "timing": "CUDA events around the collective step, median of 3, max over ranks"},
+            "matches_single_gpu_frame": all_ok, "max_abs_diff_8bit": int(diff.max()),
+            "frames_per_s": round(args.steps / (ms_total * 1e-3), 3), "clocks": clock_info,
+            "gpu_launches": (launches_per_frame(args) + (1 if tiles else 0)) * args.steps,
+        })
+    rt.close()
+    D.close()
+    if not all_ok:
+        sys.exit(3)
 
 
+# ------------------------------------------------------------------------------------------------
 def run_reference(args):
-    """--impl reference: the CPU arm.  The reference's own engine (PlotOptiX) is a closed binary that
-    cannot be installed offline, so the oracle port is what runs (kind 'port')."""
+    """--impl reference: the CPU arm.  The reference's own engine (PlotOptiX) is a closed binary that cannot be installed
+    offline, so the float64 oracle port is what runs (kind 'port'), on every host thread (torchrun exports
+    OMP_NUM_THREADS=1 to its workers: set back explicitly), on a bounded sub-grid of the same frames.  Its inputs do not come
+    from the code under test except the synthetic map itself: radius_scale is numpy's."""
     rank, world, local = dist_env()
     if rank != 0:
         return
-    from moonrtx_b200.synth import synth_ephemeris
+    cores = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(cores)
     from moonrtx_b200 import scene
-    # the CPU arm needs the same map: generate it on the GPU when there is one, else a host FFT map
-    ldem_host, radius_scale = None, None
     try:
         from moonrtx_b200 import _lib
         from moonrtx_b200.device import Device
         dev = Device(local)
         buf = dev.alloc(args.map_w * args.map_h * 2)
         _lib.check(dev.lib.mrtx_synth_ldem_i16_dev(dev.ctx, buf.ptr, args.map_w, args.map_h, SEED))
-        radius_scale = _radius_scale_ds1(dev, buf, args.map_w, args.map_h)
         ldem_host = buf.download((args.map_h, args.map_w), np.int16)
         buf.free(); dev.close()
     except Exception as e:
         emit({"impl": "reference", "unavailable": f"could not generate the synthetic map: {e}"})
         return
-    st = scene.frame_state(synth_ephemeris(args.warmup * FRAME_STEP_MIN))
-    vals, secs = [], []
-    cpu = None
+    radius_scale = radius_scale_numpy(ldem_host)
+    from oracle.render_oracle import OracleScene, lib as orc_lib
+    try:
+        orc_lib().omp_set_num_threads(cores)             # libgomp, loaded with the oracle
+    except Exception:
+        pass
+    import ctypes as C
+    try:
+        C.CDLL("libgomp.so.1").omp_set_num_threads(cores)
+    except Exception:
+        pass
     per_step_budget = max(2.0, min(20.0, 120.0 / (args.steps + args.warmup)))
+    vals, secs, last = [], [], None
     for j in range(args.warmup + args.steps):
-        cpu = cpu_baseline(args, ldem_host, radius_scale, st, budget_s=per_step_budget)
+        st = sweep_state(j * FRAMES_PER_STEP)
+        sc = OracleScene(ldem_host, scale=SCALE_F32, radius_scale=radius_scale, img_w=args.img_w, img_h=args.img_h, u=st.u, v=st.v,
+                         eye=st.eye, target=st.target, up=st.up, fov=st.fov, light_pos=st.light_pos, light_radius=st.light_radius,
+                         light_radiance=scene.light_radiance(80.0), jitter=args.spp > 1)
+        if last is None:
+            t0 = time.perf_counter()
+            o = sc.render(stride=96, nsamples=1)
+            per_px = (time.perf_counter() - t0) / (o["accum"].shape[0] * o["accum"].shape[1]) * args.spp
+            stride = max(1, int(np.ceil(np.sqrt(args.img_w * args.img_h / max(1, int(per_step_budget / max(per_px, 1e-9)))))))
+        t0 = time.perf_counter()
+        o = sc.render(stride=stride, nsamples=args.spp)
+        dt = time.perf_counter() - t0
+        npx = o["accum"].shape[0] * o["accum"].shape[1]
+        rays = (int((o["stats"][..., 0] > 0).sum()) + int((o["stats"][..., 1] > 0).sum())) * args.spp
+        last = (rays / dt / 1e6, dt, npx)
         if j >= args.warmup:
-            vals.append(cpu["value"]); secs.append(cpu["seconds"])
+            vals.append(last[0]); secs.append(dt)
     v = statistics.mean(vals)
-    cpu["value"] = round(v, 4)
+    cpu = {"value": round(v, 4), "unit": "Mrays/s", "cores": cores, "kind": "port", "omp_threads": cores,
+           "sample": f"every {stride}th pixel in x and y of the first frame of each step ({last[2]} pixels x {args.spp} spp per step), "
+                     f"float64 oracle (exhaustive cell walk, no pyramid), OpenMP {cores} threads; rays counted as for the CUDA arm's `value`"}
     emit({
         "impl": "reference", "metric": "Mrays/s (primary+shadow) @4K", "value": round(v, 4), "unit": "Mrays/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * statistics.mean(secs), 1),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.img_w}x{args.img_h} frame, {args.map_w}x{args.map_h} int16 synthetic LOLA map, "
-                               f"{args.spp} spp (BASELINE config 3), bounded sample per step"},
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{FRAMES_PER_STEP} frames per step of the F11 terminator sweep (BASELINE config 4; each frame = config 3: "
+                               f"{args.img_w}x{args.img_h}, {args.map_w}x{args.map_h} int16 synthetic LOLA map, {args.spp} spp); "
+                               f"bounded sample per step: a sub-grid of the step's first frame"},
         "cpu_baseline": cpu,
         "e2e": {"value": round(v, 4), "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
@@ -539,9 +790,10 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="frames", choices=["frames", "samples", "tiles"])
     ap.add_argument("--spp", type=int, default=16)
     ap.add_argument("--map-w", type=int, default=MAP_W)
     ap.add_argument("--map-h", type=int, default=MAP_H)
@@ -551,17 +803,15 @@ def main():
     ap.add_argument("--color-h", type=int, default=COLOR_H)
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
-    ap.add_argument("--e2e-sync", action="store_true", help="e2e one frame at a time (render_cycle) instead of the pipelined export loop")
     ap.add_argument("--skip-downscale", action="store_true")
-    ap.add_argument("--frame-stride", type=int, default=0, help="development: frame index step between steps (default: world size)")
-    ap.add_argument("--traffic", type=float, default=NCU_TRAFFIC_BYTES,
-                    help="dram__bytes_read.sum + dram__bytes_write.sum of trace_kernel_fast per launch, from the ncu capture in profiles/")
     args = ap.parse_args()
     claim_stdout()
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "frames":
+        run_frames(args)
     else:
-        run_ours(args)
+        run_single_frame_mode(args)
 
 
 if __name__ == "__main__":

@@ -210,6 +210,13 @@ int  mrtx_allreduce_accum(mrtx_ctx* ctx);
  * gather every rank's rows of the resolved RGBA8 frame into every rank's frame.       */
 int  mrtx_allgather_rows(mrtx_ctx* ctx, int tile_rows);
 
+/* screen-tile split, interleaved square tiles (BASELINE config 5): mrtx_render_tiles is mrtx_render over the
+ * whole frame restricted to the tiles t = ty * tiles_x + tx with t mod nranks == rank (ONE launch: the cull pass drops
+ * the other ranks' pixels); mrtx_allgather_tiles tone-maps the owned tiles straight into the send buffer, exchanges them
+ * with one ncclAllGather and writes every rank's frame in frame order.  tile = side in pixels, a power of two.       */
+int  mrtx_render_tiles(mrtx_ctx* ctx, int tile, unsigned sample0, unsigned nsamples, int reset);
+int  mrtx_allgather_tiles(mrtx_ctx* ctx, int tile);
+
 #ifdef __cplusplus
 }
 #endif

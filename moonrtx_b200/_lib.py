@@ -76,6 +76,8 @@ _SIGNATURES = {
     "mrtx_hit_at": (C.c_int, [c_ctx, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "mrtx_frame_buffers_dev": (C.c_int, [c_ctx, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "mrtx_counters": (C.c_int, [c_ctx, C.POINTER(C.c_uint64), C.c_int]),
+    "mrtx_render_tiles": (C.c_int, [c_ctx, C.c_int, C.c_uint, C.c_uint, C.c_int]),
+    "mrtx_allgather_tiles": (C.c_int, [c_ctx, C.c_int]),
     "mrtx_kernel_times": (C.c_int, [c_ctx, C.POINTER(C.c_double), C.c_int]),
     "mrtx_defer_stats": (C.c_int, [c_ctx, C.POINTER(C.c_uint64), C.c_int]),
     "mrtx_comm_unique_id": (C.c_int, [C.c_char_p, C.c_void_p]),

@@ -3,6 +3,8 @@
 
 #include "common.cuh"
 
+#include <thread>
+
 #include <stdarg.h>
 #include <stdlib.h>
 
@@ -105,6 +107,8 @@ int mrtx_destroy(mrtx_ctx* ctx) {
     cudaFree(ctx->sq_buf);
     if (ctx->prof_ev) { for (int i = 0; i < MRTX_PROF_MAX * MRTX_PROF_EVENTS; ++i) cudaEventDestroy(ctx->prof_ev[i]); free(ctx->prof_ev); }
     cudaFree(ctx->flush_buf);
+    if (ctx->h_rs) cudaFreeHost(ctx->h_rs);
+    for (int b = 0; b < 2; ++b) { if (ctx->stage[b]) cudaFreeHost(ctx->stage[b]); if (ctx->stage_ev[b]) cudaEventDestroy(ctx->stage_ev[b]); }
     cudaFree(ctx->gather_buf);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
@@ -214,43 +218,123 @@ static int check_downscale_args(const void* src, int W, int H, int ds, const voi
     return MRTX_OK;
 }
 
+static int ensure_rs_word(mrtx_ctx* ctx) {
+    if (ctx->h_rs) return MRTX_OK;
+    MRTX_CUDA(cudaHostAlloc((void**)&ctx->h_rs, sizeof(float), cudaHostAllocMapped));
+    MRTX_CUDA(cudaHostGetDevicePointer((void**)&ctx->h_rs_dev, ctx->h_rs, 0));
+    return MRTX_OK;
+}
+
 int mrtx_downscale_i16_dev(mrtx_ctx* ctx, const int16_t* src_dev, int W, int H, int ds,
                            float* out_dev, float* radius_scale) {
     MRTX_CTX(ctx);
     int rc = check_downscale_args(src_dev, W, H, ds, out_dev);
     if (rc) return rc;
-    rc = launch_downscale_i16(ctx, src_dev, W, H, ds, out_dev);
+    if (radius_scale) { rc = ensure_rs_word(ctx); if (rc) return rc; }
+    rc = launch_downscale_i16(ctx, src_dev, W, H, ds, out_dev, radius_scale ? ctx->h_rs_dev : nullptr);
     if (rc) return rc;
     if (radius_scale) {
-        MRTX_CUDA(cudaMemcpyAsync(radius_scale, ctx->d_max_bits, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        // the kernel has written the value to mapped host memory: nothing to copy, only to wait for
         MRTX_CUDA(cudaStreamSynchronize(ctx->stream));
+        *radius_scale = *(volatile float*)ctx->h_rs;
     }
     return MRTX_OK;
 }
 
+// memcpy on a few host threads (one thread moves ~10 GB/s, the copy engine five times that)
+static void parallel_memcpy(void* dst, const void* src, size_t bytes) {
+    unsigned nt = std::thread::hardware_concurrency() / 2;
+    nt = nt < 1 ? 1 : (nt > 8 ? 8 : nt);
+    if (bytes < ((size_t)4 << 20) || nt == 1) { memcpy(dst, src, bytes); return; }
+    std::thread th[8];
+    const size_t per = ((bytes / nt) + 4095) & ~(size_t)4095;
+    unsigned used = 0;
+    for (unsigned i = 0; i < nt; ++i) {
+        const size_t off = (size_t)i * per;
+        if (off >= bytes) break;
+        const size_t len = bytes - off < per ? bytes - off : per;
+        th[used++] = std::thread([=] { memcpy((char*)dst + off, (const char*)src + off, len); });
+    }
+    for (unsigned i = 0; i < used; ++i) th[i].join();
+}
+
+static int ensure_staging(mrtx_ctx* ctx, size_t bytes) {
+    if (ctx->stage_bytes >= bytes) return MRTX_OK;
+    MRTX_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int b = 0; b < 2; ++b) {
+        if (ctx->stage[b]) cudaFreeHost(ctx->stage[b]);
+        ctx->stage[b] = nullptr;
+        MRTX_CUDA(cudaHostAlloc(&ctx->stage[b], bytes, cudaHostAllocDefault));
+        if (!ctx->stage_ev[b]) MRTX_CUDA(cudaEventCreateWithFlags(&ctx->stage_ev[b], cudaEventDisableTiming));
+    }
+    ctx->stage_bytes = bytes;
+    return MRTX_OK;
+}
+
+// Host buffers in and out (what load_elevation_data calls, data_loader.py:215-247).  The caller's arrays are pageable:
+// the map goes up in bands through two pinned staging buffers - host threads fill one while the copy engine drains the
+// other and the block-mean kernel reduces the band before - so the call costs about what the slowest of the three
+// (the host-side memcpy) costs; the result comes down the same way.
 int mrtx_downscale_i16(mrtx_ctx* ctx, const int16_t* src, int W, int H, int ds,
                        float* out, float* radius_scale) {
     MRTX_CTX(ctx);
     int rc = check_downscale_args(src, W, H, ds, out);
     if (rc) return rc;
     MRTX_REQUIRE(radius_scale, "null radius_scale");
+    rc = ensure_rs_word(ctx);
+    if (rc) return rc;
+    const int h = H / ds, w = W / ds;
     const size_t in_bytes = (size_t)W * H * sizeof(int16_t);
-    const size_t out_bytes = (size_t)(W / ds) * (H / ds) * sizeof(float);
+    const size_t out_bytes = (size_t)w * h * sizeof(float);
+    // bands of whole output rows, about 32 MB of source each
+    size_t band_out_rows = ((size_t)32 << 20) / ((size_t)W * 2 * ds);
+    if (band_out_rows < 1) band_out_rows = 1;
+    const size_t band_rows = band_out_rows * ds, band_bytes = band_rows * (size_t)W * 2;
+    rc = ensure_staging(ctx, band_bytes);
+    if (rc) return rc;
     int16_t* d_src = nullptr; float* d_out = nullptr;
     MRTX_CUDA(cudaMalloc(&d_src, in_bytes));
     cudaError_t e = cudaMalloc(&d_out, out_bytes);
     if (e != cudaSuccess) { cudaFree(d_src); mrtx_set_error("cudaMalloc: %s", cudaGetErrorString(e)); return MRTX_ERR_CUDA; }
-    rc = MRTX_OK;
-    do {
-        if (cudaMemcpyAsync(d_src, src, in_bytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { rc = MRTX_ERR_CUDA; break; }
-        rc = launch_downscale_i16(ctx, d_src, W, H, ds, d_out);
-        if (rc) break;
-        if (cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) { rc = MRTX_ERR_CUDA; break; }
-        if (cudaMemcpyAsync(radius_scale, ctx->d_max_bits, 4, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) { rc = MRTX_ERR_CUDA; break; }
-        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = MRTX_ERR_CUDA; break; }
-    } while (0);
+    cudaStream_t st = ctx->stream;
+    rc = downscale_begin(ctx);
+    int b = 0;
+    for (size_t r0 = 0; !rc && r0 < (size_t)H; r0 += band_rows, b ^= 1) {
+        const size_t rows = (size_t)H - r0 < band_rows ? (size_t)H - r0 : band_rows;
+        const size_t bytes = rows * (size_t)W * 2;
+        if (cudaEventSynchronize(ctx->stage_ev[b]) != cudaSuccess) { rc = MRTX_ERR_CUDA; break; }     // the copy out of this buffer two bands ago
+        parallel_memcpy(ctx->stage[b], src + r0 * (size_t)W, bytes);
+        if (cudaMemcpyAsync(d_src + r0 * (size_t)W, ctx->stage[b], bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = MRTX_ERR_CUDA; break; }
+        if (cudaEventRecord(ctx->stage_ev[b], st) != cudaSuccess) { rc = MRTX_ERR_CUDA; break; }
+        rc = downscale_band(ctx, d_src + r0 * (size_t)W, W, (int)rows, ds, d_out + (r0 / ds) * (size_t)w);
+    }
+    if (!rc) rc = downscale_finish(ctx, d_out, (size_t)w * h, ctx->h_rs_dev);
+    // the result: device -> pinned staging -> the caller's array, two chunks in flight
+    const size_t chunk = ctx->stage_bytes;
+    size_t done = 0, copied = 0;
+    int q = 0;
+    size_t pend_off[2] = {0, 0}, pend_len[2] = {0, 0};
+    bool pend[2] = {false, false};
+    while (!rc && (done < out_bytes || pend[0] || pend[1])) {
+        if (pend[q]) {
+            if (cudaEventSynchronize(ctx->stage_ev[q]) != cudaSuccess) { rc = MRTX_ERR_CUDA; break; }
+            parallel_memcpy((char*)out + pend_off[q], ctx->stage[q], pend_len[q]);
+            copied += pend_len[q]; pend[q] = false;
+        }
+        if (done < out_bytes) {
+            const size_t len = out_bytes - done < chunk ? out_bytes - done : chunk;
+            if (cudaMemcpyAsync(ctx->stage[q], (const char*)d_out + done, len, cudaMemcpyDeviceToHost, st) != cudaSuccess) { rc = MRTX_ERR_CUDA; break; }
+            if (cudaEventRecord(ctx->stage_ev[q], st) != cudaSuccess) { rc = MRTX_ERR_CUDA; break; }
+            pend_off[q] = done; pend_len[q] = len; pend[q] = true; done += len;
+        }
+        q ^= 1;
+    }
+    if (!rc && cudaStreamSynchronize(st) != cudaSuccess) rc = MRTX_ERR_CUDA;
+    if (!rc) *radius_scale = *(volatile float*)ctx->h_rs;
     if (rc == MRTX_ERR_CUDA) mrtx_set_error("downscale: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaStreamSynchronize(st);
     cudaFree(d_src); cudaFree(d_out);
+    (void)copied;
     return rc;
 }
 
@@ -684,6 +768,18 @@ int mrtx_render(mrtx_ctx* ctx, int x0, int y0, int x1, int y1, unsigned sample0,
     if (ctx->sp.debug_hits && !ctx->hit64) MRTX_CUDA(cudaMalloc(&ctx->hit64, n * sizeof(double4)));
     if (nsamples == 0 || x0 == x1 || y0 == y1) return MRTX_OK;
     return launch_trace(ctx, x0, y0, x1, y1, sample0, nsamples);
+}
+
+int mrtx_render_tiles(mrtx_ctx* ctx, int tile, unsigned sample0, unsigned nsamples, int reset) {
+    MRTX_CTX(ctx);
+    int tl = 0;
+    while ((1 << tl) < tile) ++tl;
+    MRTX_REQUIRE(tile >= 8 && tile <= 1024 && (1 << tl) == tile, "tile side must be a power of two in 8..1024");
+    if (!ctx->nccl_comm || ctx->nranks < 1) { mrtx_set_error("mrtx_comm_init has not been called"); return MRTX_ERR_STATE; }
+    ctx->tile_log2 = tl;
+    const int rc = mrtx_render(ctx, 0, 0, ctx->width, ctx->height, sample0, nsamples, reset);
+    ctx->tile_log2 = 0;
+    return rc;
 }
 
 int mrtx_resolve(mrtx_ctx* ctx) {

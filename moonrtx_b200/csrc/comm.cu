@@ -90,6 +90,57 @@ __global__ void unpack_rows_kernel(uchar4* __restrict__ frame, const uchar4* __r
     }
 }
 
+// Interleaved square tiles (cost is concentrated on the terminator and the limb, so 64 x 64 tiles
+// round-robin, not slabs).  Tile t = ty * tiles_x + tx belongs to rank t mod R and is that rank's slot t / R.
+// resolve_tiles_kernel tone-maps an owned tile straight into its slot of the send buffer (no packing pass);
+// after the all-gather untile_kernel writes every rank's slots back to frame order.
+__global__ void resolve_tiles_kernel(const float4* __restrict__ accum, const uchar4* __restrict__ overlay, uchar4* __restrict__ send,
+                                     int W, int H, int tl, int R, int rank, int slots, float exposure, float inv_gamma) {
+    const int ts = 1 << tl, tiles_x = (W + ts - 1) >> tl, tiles_y = (H + ts - 1) >> tl;
+    const size_t n = (size_t)slots << (2 * tl);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int k = (int)(i >> (2 * tl)), w = (int)(i & ((size_t)(ts * ts) - 1));
+        const int t = k * R + rank;
+        uchar4 px = make_uchar4(0, 0, 0, 0);
+        if (t < tiles_x * tiles_y) {
+            const int x = (t % tiles_x) * ts + (w & (ts - 1)), y = (t / tiles_x) * ts + (w >> tl);
+            if (x < W && y < H) {
+                const size_t j = (size_t)y * W + x;
+                const float4 a = accum[j];
+                const double wgt = a.w > 0.0f ? (double)a.w : 1.0;
+                const double ch[3] = {a.x, a.y, a.z};
+                unsigned c8[3];
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    double c = (double)exposure * ch[q] / wgt;
+                    c = c > 0.0 ? pow(c, (double)inv_gamma) : 0.0;
+                    const double v = floor(c * 255.0 + 0.5);
+                    c8[q] = (unsigned)(v > 255.0 ? 255.0 : v);
+                }
+                if (overlay) {
+                    const uchar4 o = overlay[j];
+                    const unsigned al = o.w, na = 255u - o.w;
+                    c8[0] = (o.x * al + c8[0] * na + 127u) / 255u;
+                    c8[1] = (o.y * al + c8[1] * na + 127u) / 255u;
+                    c8[2] = (o.z * al + c8[2] * na + 127u) / 255u;
+                }
+                px = make_uchar4((unsigned char)c8[0], (unsigned char)c8[1], (unsigned char)c8[2], 255);
+            }
+        }
+        send[i] = px;
+    }
+}
+__global__ void untile_kernel(uchar4* __restrict__ frame, const uchar4* __restrict__ recv, int W, int H, int tl, int R, int slots) {
+    const int ts = 1 << tl, tiles_x = (W + ts - 1) >> tl;
+    const size_t n = (size_t)W * H;
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(j % W), y = (int)(j / W);
+        const int t = (y >> tl) * tiles_x + (x >> tl);
+        const size_t src = (((size_t)(t % R) * slots + (size_t)(t / R)) << (2 * tl)) + (size_t)((y & (ts - 1)) << tl) + (size_t)(x & (ts - 1));
+        frame[j] = recv[src];
+    }
+}
+
 }  // namespace
 
 // point-to-point legs of the frame pipeline (api.cu: mrtx_frame_submit_to / mrtx_frame_recv)
@@ -150,6 +201,39 @@ int mrtx_allreduce_accum(mrtx_ctx* ctx) {
     const size_t count = (size_t)ctx->width * ctx->height * 4;
     MRTX_NCCL(g_nccl.AllReduce(ctx->accum, ctx->accum, count, NCCL_FLOAT32, NCCL_SUM,
                                (nccl_comm_t)ctx->nccl_comm, ctx->stream));
+    return MRTX_OK;
+}
+
+int mrtx_allgather_tiles(mrtx_ctx* ctx, int tile) {
+    MRTX_CTX(ctx);
+    if (!ctx->nccl_comm) { mrtx_set_error("mrtx_comm_init has not been called"); return MRTX_ERR_STATE; }
+    if (!ctx->rgba8) { mrtx_set_error("frame buffer not allocated"); return MRTX_ERR_STATE; }
+    int tl = 0;
+    while ((1 << tl) < tile) ++tl;
+    MRTX_REQUIRE(tile >= 8 && tile <= 1024 && (1 << tl) == tile, "tile side must be a power of two in 8..1024");
+    if (ctx->tex[1].data)
+        MRTX_REQUIRE(ctx->tex[1].W == ctx->width && ctx->tex[1].H == ctx->height, "frame_overlay does not match the frame size");
+    const int W = ctx->width, H = ctx->height, R = ctx->nranks;
+    const int tiles = ((W + tile - 1) >> tl) * ((H + tile - 1) >> tl);
+    const int slots = (tiles + R - 1) / R;
+    const size_t slot_px = (size_t)slots << (2 * tl);               // uchar4 per rank
+    const size_t need = slot_px * (size_t)(R + 1) * sizeof(uchar4);
+    if (!ctx->gather_buf || ctx->gather_bytes < need) {
+        MRTX_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->gather_buf);
+        ctx->gather_buf = nullptr; ctx->gather_bytes = 0;
+        MRTX_CUDA(cudaMalloc(&ctx->gather_buf, need));
+        ctx->gather_bytes = need;
+    }
+    uchar4* send = (uchar4*)ctx->gather_buf;
+    uchar4* recv = send + slot_px;
+    const int blocks = ctx->sm_count * 8;
+    resolve_tiles_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->accum, ctx->tex[1].data, send, W, H, tl, R, ctx->rank, slots,
+                                                         ctx->sp.exposure, ctx->sp.inv_gamma);
+    MRTX_CUDA(cudaGetLastError());
+    MRTX_NCCL(g_nccl.AllGather(send, recv, slot_px * sizeof(uchar4), NCCL_UINT8, (nccl_comm_t)ctx->nccl_comm, ctx->stream));
+    untile_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->rgba8, recv, W, H, tl, R, slots);
+    MRTX_CUDA(cudaGetLastError());
     return MRTX_OK;
 }
 

@@ -112,6 +112,8 @@ struct mrtx_ctx {
     // data_loader scratch
     unsigned* d_max_bits;       // running max of the un-normalised elevation (as uint bits)
     void* flush_buf; size_t flush_bytes;
+    float* h_rs; float* h_rs_dev;   // mapped pinned word the normalise kernel writes radius_scale to
+    void* stage[2]; size_t stage_bytes; cudaEvent_t stage_ev[2];   // pinned staging of host-buffer calls (chunked copies)
 
     // scene
     HeightField hf;
@@ -159,10 +161,14 @@ struct mrtx_ctx {
     // comm
     void* nccl_lib; void* nccl_comm; int nranks, rank;
     void* gather_buf; size_t gather_bytes;
+    int tile_log2;              // > 0 while a tile-sharded launch is being issued (mrtx_render_tiles)
 };
 
 // ---- kernels' host launchers (one per .cu) ---------------------------------------------
-int launch_downscale_i16(mrtx_ctx* ctx, const int16_t* src_dev, int W, int H, int ds, float* out_dev);
+int launch_downscale_i16(mrtx_ctx* ctx, const int16_t* src_dev, int W, int H, int ds, float* out_dev, float* host_rs_dev);
+int downscale_begin(mrtx_ctx* ctx);
+int downscale_band(mrtx_ctx* ctx, const int16_t* src_dev, int W, int Hb, int ds, float* out_dev);
+int downscale_finish(mrtx_ctx* ctx, float* out_dev, size_t n, float* host_rs_dev);
 int launch_color_reduce(mrtx_ctx* ctx, const uint8_t* bgr_dev, int W, int H, int k,
                         const uint8_t* lut_dev, uint8_t* out_dev);
 int launch_synth_ldem(mrtx_ctx* ctx, int16_t* out_dev, int W, int H, uint32_t seed);

@@ -162,8 +162,11 @@ downscale_generic_kernel(const int16_t* __restrict__ src, float* __restrict__ ou
 
 // K2: out /= max.  256-bit vectors for the aligned body, scalars for the tail.
 __global__ void __launch_bounds__(256)
-normalise_kernel(float* __restrict__ out, size_t n, size_t nvec, const unsigned* __restrict__ gmax_bits) {
+normalise_kernel(float* __restrict__ out, size_t n, size_t nvec, const unsigned* __restrict__ gmax_bits,
+                 float* __restrict__ host_rs) {
     const float mx = __uint_as_float(*gmax_bits);
+    // radius_scale goes to the caller through a mapped pinned word: no copy engine round trip behind the kernel
+    if (host_rs && blockIdx.x == 0 && threadIdx.x == 0) { *host_rs = mx; __threadfence_system(); }
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
         float f[8];
@@ -186,13 +189,18 @@ void launch_vec(const int16_t* src, float* out, int W, int h, int w, float scale
 
 }  // namespace
 
-int launch_downscale_i16(mrtx_ctx* ctx, const int16_t* src, int W, int H, int ds, float* out) {
-    const int h = H / ds, w = W / ds;
+// The three steps of a downscale, so that a map arriving from the host band by band can be reduced while it arrives:
+// begin (clear the running max), band (block means of source rows [0, Hb) of `src` -> rows of `out`), finish (/ max).
+int downscale_begin(mrtx_ctx* ctx) {
+    MRTX_CUDA(cudaMemsetAsync(ctx->d_max_bits, 0, sizeof(unsigned), ctx->stream));
+    return MRTX_OK;
+}
+
+int downscale_band(mrtx_ctx* ctx, const int16_t* src, int W, int Hb, int ds, float* out) {
+    const int h = Hb / ds, w = W / ds;
     // data_loader.py:216 - python float scale, applied to a float32 array => fl32(scale)
     const float scale = (float)(0.5 / 1737400.0);
     cudaStream_t st = ctx->stream;
-    MRTX_CUDA(cudaMemsetAsync(ctx->d_max_bits, 0, sizeof(unsigned), st));
-
     int c0 = 0;   // first output column left to the generic kernel
     const bool aligned = (W % 16 == 0) && ((uintptr_t)src % 32 == 0) && ((uintptr_t)out % 32 == 0) && (w % 8 == 0);
     if (aligned) {
@@ -216,13 +224,23 @@ int launch_downscale_i16(mrtx_ctx* ctx, const int16_t* src, int W, int H, int ds
         downscale_generic_kernel<<<blocks, 256, 0, st>>>(src, out, W, h, w, ds, c0, scale, ctx->d_max_bits);
     }
     MRTX_CUDA(cudaGetLastError());
-    const size_t n = (size_t)h * w;
+    return MRTX_OK;
+}
+
+int downscale_finish(mrtx_ctx* ctx, float* out, size_t n, float* host_rs_dev) {
     // 256-bit vectors need a 32-byte aligned destination; otherwise everything is "tail"
     const size_t nvec = ((uintptr_t)out % 32 == 0) ? n / 8 : 0;
     size_t want = ((nvec ? nvec : n) + 255) / 256;
     const size_t cap = (size_t)ctx->sm_count * 16;
     const unsigned blocks = (unsigned)(want < 1 ? 1 : (want > cap ? cap : want));
-    normalise_kernel<<<blocks, 256, 0, st>>>(out, n, nvec, ctx->d_max_bits);
+    normalise_kernel<<<blocks, 256, 0, ctx->stream>>>(out, n, nvec, ctx->d_max_bits, host_rs_dev);
     MRTX_CUDA(cudaGetLastError());
     return MRTX_OK;
+}
+
+int launch_downscale_i16(mrtx_ctx* ctx, const int16_t* src, int W, int H, int ds, float* out, float* host_rs_dev) {
+    int rc = downscale_begin(ctx);
+    if (!rc) rc = downscale_band(ctx, src, W, H, ds, out);
+    if (!rc) rc = downscale_finish(ctx, out, (size_t)(H / ds) * (W / ds), host_rs_dev);
+    return rc;
 }

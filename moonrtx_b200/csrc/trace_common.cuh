@@ -48,6 +48,8 @@ struct RenderArgs {
     SceneParams sp;
     int width, height, x0, y0, x1, y1;
     unsigned sample0, nsamples;
+    int tile_log2, tile_ranks, tile_rank;   // screen-tile sharding (mrtx_render_tiles): this launch renders the pixels of the
+                                     // square tiles (side 2^tile_log2) t with t mod tile_ranks == tile_rank only
     unsigned hit_sample;             // the sample whose first hit goes to the hit buffer: sample 0 of the cycle, whichever launch,
                                      // chunk or rank traces it (rt._get_hit_at, moon_renderer.py:1138)
     float4* accum; float4* hit; double4* hit64;
@@ -238,7 +240,13 @@ cull_kernel(const __grid_constant__ RenderArgs A) {
         const unsigned tile = p >> 5, within = p & 31u;
         x = A.x0 + (int)(tile % tiles_x) * 8 + (int)(within & 7u);
         y = A.y0 + (int)(tile / tiles_x) * 4 + (int)(within >> 3);
-        if (x < A.x1 && y < A.y1) {
+        bool mine = true;
+        if (A.tile_ranks > 1) {
+            const unsigned ttx = ((unsigned)A.width + (1u << A.tile_log2) - 1u) >> A.tile_log2;
+            const unsigned t = ((unsigned)y >> A.tile_log2) * ttx + ((unsigned)x >> A.tile_log2);
+            mine = t % (unsigned)A.tile_ranks == (unsigned)A.tile_rank;
+        }
+        if (x < A.x1 && y < A.y1 && mine) {
             const Camera& cam = A.cam;
             const double Rb = A.sp.radius * (double)A.hf.dmax;
             const double eye_dist = sqrt(A.eye_b[0] * A.eye_b[0] + A.eye_b[1] * A.eye_b[1] + A.eye_b[2] * A.eye_b[2]);
@@ -621,6 +629,7 @@ static void fill_render_args(mrtx_ctx* ctx, int x0, int y0, int x1, int y1, unsi
     A.width = ctx->width; A.height = ctx->height;
     A.x0 = x0; A.y0 = y0; A.x1 = x1; A.y1 = y1;
     A.sample0 = s0; A.nsamples = ns; A.hit_sample = 0u;
+    A.tile_log2 = ctx->tile_log2; A.tile_ranks = ctx->tile_log2 ? ctx->nranks : 1; A.tile_rank = ctx->rank;
     A.accum = ctx->accum; A.hit = ctx->hit;
     A.hit64 = ctx->sp.debug_hits ? ctx->hit64 : nullptr;
     A.counters = ctx->d_counters;

@@ -346,13 +346,15 @@ class B200OptiX:
         self._rank, self._world = int(rank), int(world)
 
     def render_cycle(self, read_back: bool = True, shard: Optional[str] = None,
-                     tile_rows: int = 64) -> Optional[np.ndarray]:
+                     tile_rows: int = 64, tile: int = 64) -> Optional[np.ndarray]:
         """
         One accumulation cycle, synchronously, on the calling thread (padlock held).
 
         shard=None      this GPU renders the whole frame;
         shard="samples" the cycle's samples are split across the communicator's ranks and the float4
                         accumulators are summed with one ncclAllReduce before the resolve;
+        shard="tiles"   interleaved square tiles of side `tile` (a power of two) are split across the ranks in ONE
+                        launch, tone-mapped straight into the send buffer and exchanged with one ncclAllGather;
         shard="rows"    interleaved bands of `tile_rows` rows are split across the ranks and the
                         resolved RGBA8 bands are exchanged with one ncclAllGather.
         """
@@ -374,6 +376,8 @@ class B200OptiX:
                 hi = (n * (self._rank + 1)) // self._world
                 _lib.check(self._lib.mrtx_render(self._ctx, 0, 0, W, H, lo, hi - lo, 1))
                 _lib.check(self._lib.mrtx_allreduce_accum(self._ctx))
+            elif shard == "tiles":
+                _lib.check(self._lib.mrtx_render_tiles(self._ctx, int(tile), 0, n, 1))
             elif shard == "rows":
                 first = True
                 for t in range(self._rank, (H + tile_rows - 1) // tile_rows, self._world):
@@ -384,7 +388,10 @@ class B200OptiX:
                     _lib.check(self._lib.mrtx_render(self._ctx, 0, 0, W, 0, 0, 0, 1))
             else:
                 raise ValueError(f"unknown shard mode {shard}")
-            _lib.check(self._lib.mrtx_resolve(self._ctx))
+            if shard == "tiles":
+                _lib.check(self._lib.mrtx_allgather_tiles(self._ctx, int(tile)))      # resolves the owned tiles itself
+            else:
+                _lib.check(self._lib.mrtx_resolve(self._ctx))
             if shard == "rows":
                 _lib.check(self._lib.mrtx_allgather_rows(self._ctx, int(tile_rows)))
             self._frames_rendered += 1

@@ -38,7 +38,7 @@ def make_gpu(elevation, img_w, img_h, texture=None, scale=None, radius_scale=Non
     rt.update_material("diffuse", {"ColorTextures": ["moon_color"]})
     rt.set_data("moon", geom="ParticleSetTextured", geom_attr="DisplacedSurface",
                 pos=list(p["pos"]), u=list(p["u"]), v=list(p["v"]), r=p["radius"])
-    if elevation.dtype == np.int16:
+    if isinstance(elevation, tuple) or elevation.dtype == np.int16:       # (DeviceBuffer, W, H): the map already in HBM
         rt.set_displacement_i16("moon", elevation, radius_scale=radius_scale, scale=scale)
     else:
         rt.set_displacement("moon", elevation, refresh=False)

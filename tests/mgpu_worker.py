@@ -40,6 +40,10 @@ def main():
     assert np.allclose(acc_s, ref_acc, rtol=1e-5, atol=1e-6), "sample-split accumulators"
     assert np.abs(img_s.astype(int) - ref.astype(int)).max() <= 1, "sample-split image"
 
+    for tile in (16, 64):
+        img_t = rt.render_cycle(shard="tiles", tile=tile).copy()
+        assert np.array_equal(img_t, ref), f"interleaved tile split (tile={tile})"
+
     for tile_rows in (16, 64, 7):
         img_r = rt.render_cycle(shard="rows", tile_rows=tile_rows).copy()
         assert np.array_equal(img_r, ref), f"row-band split (tile_rows={tile_rows})"
