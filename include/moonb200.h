@@ -111,6 +111,18 @@ int  mrtx_set_displacement_i16_dev(mrtx_ctx* ctx, const int16_t* map_dev, int W,
  * moon_renderer.py:614, renderer_video.py:137.  slot 0 = moon_color (bilinear),
  * slot 1 = frame_overlay (nearest, must match the frame size); NULL clears.           */
 int  mrtx_set_texture_rgba8(mrtx_ctx* ctx, int slot, const uint8_t* rgba, int W, int H);
+/* What rays that miss the Moon see.
+ * rt.set_background_mode("TextureEnvironment") + rt.set_background(float32[h][w][3] in [0, 1], gamma=g,
+ * rt_format="UByte4"), moon_renderer.py:602-609: the star map becomes an 8-bit environment texture of linear radiance
+ * v^g (slot 2 of mrtx_set_texture_rgba8 takes such a texture directly), looked up by ray direction - equirectangular,
+ * scene +Z up, -Y at longitude 0, bilinear; NULL = rt.set_background(0), black.
+ * rt.set_data / update_data("sun_disk", pos=, r=, c=), moon_renderer.py:643-650, 855: the visible Sun disk, a flat-shaded
+ * sphere in scene space that primary rays see and shadow rays do not (radius <= 0 removes it).
+ * mrtx_resize_cubic_f32: cv2.resize(INTER_CUBIC) + clip of load_starmap (data_loader.py:412-415), host buffers.      */
+int  mrtx_set_background_f32(mrtx_ctx* ctx, const float* rgb, int W, int H, float gamma);
+int  mrtx_read_background_rgba8(mrtx_ctx* ctx, uint8_t* out, int* W, int* H);
+int  mrtx_set_sun_disk(mrtx_ctx* ctx, const double center[3], double radius, const float color[3]);
+int  mrtx_resize_cubic_f32(mrtx_ctx* ctx, const float* src, int W, int H, int channels, float* dst, int w, int h);
 /* rt.set_data/update_data("moon", pos, u, v, r), moon_renderer.py:620-621, 854:
  * u = scene direction of the body +Z (north pole), v = scene direction of lon 0.      */
 int  mrtx_set_frame(mrtx_ctx* ctx, const double pos[3], const double u[3], const double v[3],

@@ -76,6 +76,10 @@ _SIGNATURES = {
     "mrtx_hit_at": (C.c_int, [c_ctx, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "mrtx_frame_buffers_dev": (C.c_int, [c_ctx, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "mrtx_counters": (C.c_int, [c_ctx, C.POINTER(C.c_uint64), C.c_int]),
+    "mrtx_set_background_f32": (C.c_int, [c_ctx, C.c_void_p, C.c_int, C.c_int, C.c_float]),
+    "mrtx_read_background_rgba8": (C.c_int, [c_ctx, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "mrtx_set_sun_disk": (C.c_int, [c_ctx, C.POINTER(C.c_double), C.c_double, C.POINTER(C.c_float)]),
+    "mrtx_resize_cubic_f32": (C.c_int, [c_ctx, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]),
     "mrtx_render_tiles": (C.c_int, [c_ctx, C.c_int, C.c_uint, C.c_uint, C.c_int]),
     "mrtx_allgather_tiles": (C.c_int, [c_ctx, C.c_int]),
     "mrtx_kernel_times": (C.c_int, [c_ctx, C.POINTER(C.c_double), C.c_int]),

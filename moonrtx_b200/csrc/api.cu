@@ -92,7 +92,7 @@ int mrtx_destroy(mrtx_ctx* ctx) {
     cudaDeviceSynchronize();
     mrtx_comm_destroy(ctx);
     free_heightfield(ctx);
-    for (int s = 0; s < 2; ++s) cudaFree(ctx->tex_owned[s]);
+    for (int s = 0; s < 3; ++s) cudaFree(ctx->tex_owned[s]);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     pipe_release(ctx);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -469,7 +469,7 @@ int mrtx_set_displacement_i16_dev(mrtx_ctx* ctx, const int16_t* map_dev, int W, 
 
 int mrtx_set_texture_rgba8(mrtx_ctx* ctx, int slot, const uint8_t* rgba, int W, int H) {
     MRTX_CTX(ctx);
-    MRTX_REQUIRE(slot == 0 || slot == 1, "texture slot %d (0 = moon_color, 1 = frame_overlay)", slot);
+    MRTX_REQUIRE(slot >= 0 && slot <= 2, "texture slot %d (0 = moon_color, 1 = frame_overlay, 2 = environment)", slot);
     MRTX_CUDA(cudaStreamSynchronize(ctx->stream));
     if (!rgba) {
         cudaFree(ctx->tex_owned[slot]);
@@ -489,6 +489,67 @@ int mrtx_set_texture_rgba8(mrtx_ctx* ctx, int slot, const uint8_t* rgba, int W, 
     ctx->tex[slot].data = (const uchar4*)ctx->tex_owned[slot];
     ctx->tex[slot].W = W; ctx->tex[slot].H = H;
     return MRTX_OK;
+}
+
+int mrtx_set_background_f32(mrtx_ctx* ctx, const float* rgb, int W, int H, float gamma) {
+    MRTX_CTX(ctx);
+    if (!rgb) return mrtx_set_texture_rgba8(ctx, 2, nullptr, 0, 0);
+    MRTX_REQUIRE(W > 1 && H > 1 && gamma > 0.0f, "bad background %d x %d, gamma %g", W, H, (double)gamma);
+    MRTX_CUDA(cudaStreamSynchronize(ctx->stream));
+    const size_t n = (size_t)W * H;
+    float* d_rgb = nullptr;
+    MRTX_CUDA(cudaMalloc(&d_rgb, n * 3 * sizeof(float)));
+    cudaFree(ctx->tex_owned[2]);
+    ctx->tex_owned[2] = nullptr; ctx->tex[2].data = nullptr;
+    cudaError_t e = cudaMalloc(&ctx->tex_owned[2], n * 4);
+    if (e != cudaSuccess) { cudaFree(d_rgb); mrtx_set_error("cudaMalloc: %s", cudaGetErrorString(e)); return MRTX_ERR_CUDA; }
+    int rc = MRTX_OK;
+    if (cudaMemcpyAsync(d_rgb, rgb, n * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) rc = MRTX_ERR_CUDA;
+    if (!rc) rc = launch_background_texture(ctx, d_rgb, W, H, gamma, (uint8_t*)ctx->tex_owned[2]);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = MRTX_ERR_CUDA;
+    cudaFree(d_rgb);
+    if (rc) { mrtx_set_error("background: %s", cudaGetErrorString(cudaGetLastError())); return rc; }
+    ctx->tex[2].data = (const uchar4*)ctx->tex_owned[2];
+    ctx->tex[2].W = W; ctx->tex[2].H = H;
+    return MRTX_OK;
+}
+
+int mrtx_read_background_rgba8(mrtx_ctx* ctx, uint8_t* out, int* W, int* H) {
+    MRTX_CTX(ctx);
+    if (W) *W = ctx->tex[2].W;
+    if (H) *H = ctx->tex[2].H;
+    if (out && ctx->tex[2].data) {
+        MRTX_CUDA(cudaMemcpyAsync(out, ctx->tex[2].data, (size_t)ctx->tex[2].W * ctx->tex[2].H * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        MRTX_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return MRTX_OK;
+}
+
+int mrtx_set_sun_disk(mrtx_ctx* ctx, const double center[3], double radius, const float color[3]) {
+    MRTX_REQUIRE(ctx, "null context");
+    SceneParams& sp = ctx->sp;
+    sp.sun_disk_radius = radius > 0.0 && center && color ? radius : 0.0;
+    if (sp.sun_disk_radius > 0.0)
+        for (int i = 0; i < 3; ++i) { sp.sun_disk_pos[i] = center[i]; sp.sun_disk_color[i] = color[i]; }
+    return MRTX_OK;
+}
+
+int mrtx_resize_cubic_f32(mrtx_ctx* ctx, const float* src, int W, int H, int channels, float* dst, int w, int h) {
+    MRTX_CTX(ctx);
+    MRTX_REQUIRE(src && dst && W > 0 && H > 0 && w > 0 && h > 0 && channels >= 1 && channels <= 4, "bad resize arguments");
+    const size_t nin = (size_t)W * H * channels * sizeof(float), nout = (size_t)w * h * channels * sizeof(float);
+    float* d_in = nullptr; float* d_out = nullptr;
+    MRTX_CUDA(cudaMalloc(&d_in, nin));
+    cudaError_t e = cudaMalloc(&d_out, nout);
+    if (e != cudaSuccess) { cudaFree(d_in); mrtx_set_error("cudaMalloc: %s", cudaGetErrorString(e)); return MRTX_ERR_CUDA; }
+    int rc = MRTX_OK;
+    if (cudaMemcpyAsync(d_in, src, nin, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) rc = MRTX_ERR_CUDA;
+    if (!rc) rc = launch_resize_cubic(ctx, d_in, W, H, channels, d_out, w, h);
+    if (!rc && cudaMemcpyAsync(dst, d_out, nout, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) rc = MRTX_ERR_CUDA;
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = MRTX_ERR_CUDA;
+    cudaFree(d_in); cudaFree(d_out);
+    if (rc == MRTX_ERR_CUDA) mrtx_set_error("resize: %s", cudaGetErrorString(cudaGetLastError()));
+    return rc;
 }
 
 int mrtx_set_frame(mrtx_ctx* ctx, const double pos[3], const double u[3], const double v[3], double radius) {

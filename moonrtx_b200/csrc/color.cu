@@ -53,7 +53,74 @@ color_reduce_kernel(const uint8_t* __restrict__ bgr, int W, int h, int w,
     }
 }
 
+// rt.set_background(star_map, gamma=g, rt_format="UByte4"), moon_renderer.py:606-607: float RGB in [0, 1] -> 8-bit texture
+// of LINEAR radiance v^gamma (the Gamma post-process raises to 1/gamma again, as for the albedo texture), alpha 255.
+__global__ void background_texture_kernel(const float* __restrict__ rgb, size_t n, double gamma, uchar4* __restrict__ out) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        unsigned c[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            double v = (double)rgb[i * 3 + q];
+            v = v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v);
+            c[q] = (unsigned)rint(255.0 * pow(v, gamma));
+        }
+        out[i] = make_uchar4((unsigned char)c[0], (unsigned char)c[1], (unsigned char)c[2], 255);
+    }
+}
+
+// cv2.resize(..., interpolation=cv2.INTER_CUBIC) of a float32 image (load_starmap, data_loader.py:412-414): Keys cubic
+// with A = -0.75, source position (x + 0.5) * W / w - 0.5, taps clamped to the image, horizontal pass then vertical pass
+// in float32 (OpenCV's order; its SIMD paths may contract differently: equal to a few ulp, not bit for bit), clipped
+// to [0, 1] as :415 does.
+__device__ __forceinline__ void cubic_weights(float t, float (&c)[4]) {
+    const float A = -0.75f;
+    c[0] = ((A * (t + 1.0f) - 5.0f * A) * (t + 1.0f) + 8.0f * A) * (t + 1.0f) - 4.0f * A;
+    c[1] = ((A + 2.0f) * t - (A + 3.0f)) * t * t + 1.0f;
+    c[2] = ((A + 2.0f) * (1.0f - t) - (A + 3.0f)) * (1.0f - t) * (1.0f - t) + 1.0f;
+    c[3] = 1.0f - c[0] - c[1] - c[2];
+}
+__global__ void resize_cubic_kernel(const float* __restrict__ src, int W, int H, int C, float* __restrict__ dst, int w, int h) {
+    const size_t n = (size_t)w * h;
+    const double sx = (double)W / w, sy = (double)H / h;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % w), y = (int)(i / w);
+        const float fx = (float)((x + 0.5) * sx - 0.5), fy = (float)((y + 0.5) * sy - 0.5);
+        const int ix = (int)floorf(fx), iy = (int)floorf(fy);
+        float cx[4], cy[4];
+        cubic_weights(fx - (float)ix, cx);
+        cubic_weights(fy - (float)iy, cy);
+        for (int q = 0; q < C; ++q) {
+            float rows[4];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int yy = min(max(iy - 1 + b, 0), H - 1);
+                float acc = 0.0f;
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    const int xx = min(max(ix - 1 + a, 0), W - 1);
+                    acc = __fadd_rn(acc, __fmul_rn(src[((size_t)yy * W + xx) * C + q], cx[a]));
+                }
+                rows[b] = acc;
+            }
+            float v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(rows[0], cy[0]), __fmul_rn(rows[1], cy[1])), __fmul_rn(rows[2], cy[2])), __fmul_rn(rows[3], cy[3]));
+            dst[i * C + q] = fminf(fmaxf(v, 0.0f), 1.0f);
+        }
+    }
+}
+
 }  // namespace
+
+int launch_background_texture(mrtx_ctx* ctx, const float* rgb, int W, int H, float gamma, uint8_t* rgba) {
+    background_texture_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(rgb, (size_t)W * H, (double)gamma, (uchar4*)rgba);
+    MRTX_CUDA(cudaGetLastError());
+    return MRTX_OK;
+}
+
+int launch_resize_cubic(mrtx_ctx* ctx, const float* src, int W, int H, int C, float* dst, int w, int h) {
+    resize_cubic_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(src, W, H, C, dst, w, h);
+    MRTX_CUDA(cudaGetLastError());
+    return MRTX_OK;
+}
 
 int launch_color_reduce(mrtx_ctx* ctx, const uint8_t* bgr, int W, int H, int k,
                         const uint8_t* lut_dev, uint8_t* out) {

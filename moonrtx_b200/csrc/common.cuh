@@ -90,6 +90,8 @@ struct SceneParams {
     double radius;                          // sphere radius (scene units), 10 in MoonRTX
     double light_pos[3], light_radius, light_radiance;
     double scene_epsilon;
+    double sun_disk_pos[3], sun_disk_radius;   // the visible Sun disk (moon_renderer.py:643-650): flat-shaded sphere, scene space; radius <= 0: none
+    float  sun_disk_color[3];
     float  exposure, inv_gamma;
     unsigned jitter, shadows, debug_hits;
     unsigned start_primary, start_shadow;   // filtered kernel: primary rays start at level top - start_primary, shadow rays at start_shadow
@@ -120,8 +122,8 @@ struct mrtx_ctx {
     void* hf_owned_base;        // non-null when the context owns the base map
     void* hf_levels_owned;      // one allocation holding all pyramid levels
     void* hf_tables_owned;      // wall tables
-    Texture8 tex[2];
-    void* tex_owned[2];
+    Texture8 tex[3];            // 0 moon_color, 1 frame_overlay, 2 environment (star map: what rays that miss the Moon see)
+    void* tex_owned[3];
     Camera cam;
     SceneParams sp;
 
@@ -173,6 +175,8 @@ int launch_color_reduce(mrtx_ctx* ctx, const uint8_t* bgr_dev, int W, int H, int
                         const uint8_t* lut_dev, uint8_t* out_dev);
 int launch_synth_ldem(mrtx_ctx* ctx, int16_t* out_dev, int W, int H, uint32_t seed);
 int launch_synth_color(mrtx_ctx* ctx, uint8_t* out_dev, int W, int H, uint32_t seed);
+int launch_background_texture(mrtx_ctx* ctx, const float* rgb_dev, int W, int H, float gamma, uint8_t* rgba_dev);
+int launch_resize_cubic(mrtx_ctx* ctx, const float* src_dev, int W, int H, int C, float* dst_dev, int w, int h);
 int build_pyramid(mrtx_ctx* ctx);
 int launch_trace(mrtx_ctx* ctx, int x0, int y0, int x1, int y1, unsigned s0, unsigned ns);
 int launch_resolve(mrtx_ctx* ctx);

@@ -235,7 +235,10 @@ trace_kernel_fast(const __grid_constant__ RenderArgs A) {
                     ++rs.hits;
                     if (shadowed) { ++rs.shadow; if (occluded) ++rs.occluded; }
                     if (!occluded) { acc.x += lit.x; acc.y += lit.y; acc.z += lit.z; }
-                } else write_miss(A, x, y, sm == A.hit_sample);
+                } else {
+                    write_miss(A, x, y, sm == A.hit_sample);
+                    if (sees_background(A)) { const float3 m = miss_radiance_body(A, R); acc.x += m.x; acc.y += m.y; acc.z += m.z; }
+                }
             }
             // deferred samples of each pixel -> its leader's mask (bit = sample index in this launch)
             const unsigned dm = __ballot_sync(FULL, defer);

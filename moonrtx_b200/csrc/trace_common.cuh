@@ -44,6 +44,7 @@ __device__ float3 sample_albedo(const Texture8& tex, double lon, double lat) {
 struct RenderArgs {
     HeightField hf;
     Texture8 tex;
+    Texture8 env;                    // environment texture (star map) seen by rays that miss the Moon; data null: black
     Camera cam;
     SceneParams sp;
     int width, height, x0, y0, x1, y1;
@@ -226,6 +227,10 @@ __device__ __forceinline__ void flush_counters(const RenderArgs& A, const RaySta
 // keeps screen-space coherence) tests the pixel's centre ray against the bounding sphere grown by 1.5
 // pixels; pixels that cannot hit are finished here, the rest are appended to the work list that the
 // persistent kernel consumes - its lanes then only ever receive pixels with real work.
+__device__ __forceinline__ void primary_ray_fast(const RenderArgs& A, int x, int y, uint32_t pixel, unsigned sm, Ray64& R);
+__device__ __forceinline__ float3 miss_radiance_body(const RenderArgs& A, const Ray64& R);
+__device__ __forceinline__ bool sees_background(const RenderArgs& A);
+
 __global__ void __launch_bounds__(256)
 cull_kernel(const __grid_constant__ RenderArgs A) {
     const int rw = A.x1 - A.x0, rh = A.y1 - A.y0;
@@ -269,6 +274,16 @@ cull_kernel(const __grid_constant__ RenderArgs A) {
                 float4* ap = A.accum + (size_t)y * A.width + x;
                 float4 old = *ap;
                 old.w += (float)A.nsamples;
+                if (sees_background(A)) {
+                    // star map / Sun disk: every sample's own direction, summed in sample order
+                    const uint32_t pixel = (uint32_t)y * (uint32_t)A.width + (uint32_t)x;
+                    for (unsigned k = 0; k < A.nsamples; ++k) {
+                        Ray64 R;
+                        primary_ray_fast(A, x, y, pixel, A.sample0 + k, R);
+                        const float3 m = miss_radiance_body(A, R);
+                        old.x += m.x; old.y += m.y; old.z += m.z;
+                    }
+                }
                 *ap = old;
             } else {
                 keep = true;
@@ -325,6 +340,47 @@ __device__ __forceinline__ void primary_ray_at(const RenderArgs& A, int x, int y
 __device__ __forceinline__ void primary_ray_fast(const RenderArgs& A, int x, int y, uint32_t pixel, unsigned sm, Ray64& R) {
     const bool j = A.sp.jitter != 0;
     primary_ray_at(A, x, y, j ? rnd(pixel, sm, 0) : 0.5, j ? rnd(pixel, sm, 1) : 0.5, R);
+}
+
+// ---- rays that miss the Moon --------------------------------------------------------------------
+// The visible Sun disk (a flat-shaded sphere: its colour, no lighting, never an occluder - moon_renderer.py:133-139,
+// 643-650) and the star map (environment texture of linear radiance, equirectangular: scene +Z up, -Y at longitude 0,
+// bilinear, columns wrap, rows clamp).  d = unit direction from the eye, scene space.
+__device__ __forceinline__ bool sees_background(const RenderArgs& A) { return A.env.data != nullptr || A.sp.sun_disk_radius > 0.0; }
+
+__device__ float3 miss_radiance(const RenderArgs& A, double dx, double dy, double dz) {
+    const SceneParams& sp = A.sp;
+    if (sp.sun_disk_radius > 0.0) {
+        const double ox = A.cam.eye[0] - sp.sun_disk_pos[0], oy = A.cam.eye[1] - sp.sun_disk_pos[1], oz = A.cam.eye[2] - sp.sun_disk_pos[2];
+        const double b = ox * dx + oy * dy + oz * dz, c = ox * ox + oy * oy + oz * oz - sp.sun_disk_radius * sp.sun_disk_radius;
+        const double disc = b * b - c;
+        if (disc > 0.0 && -b + sqrt(disc) > 0.0) return make_float3(sp.sun_disk_color[0], sp.sun_disk_color[1], sp.sun_disk_color[2]);
+    }
+    if (!A.env.data) return make_float3(0.f, 0.f, 0.f);
+    const int w = A.env.W, h = A.env.H;
+    const double lon = atan2(dx, -dy), lat = asin(fmin(fmax(dz, -1.0), 1.0));
+    const double u = (lon * (0.5 / PI_D) + 0.5) * w - 0.5, v = (0.5 - lat * (1.0 / PI_D)) * h - 0.5;
+    const double fu = floor(u);
+    int c0 = (int)fu;
+    const float fc = (float)(u - fu);
+    c0 = c0 < 0 ? c0 + w : (c0 >= w ? c0 - w : c0);
+    const int c1 = c0 + 1 == w ? 0 : c0 + 1;
+    const int r0 = min(max((int)floor(v), 0), h - 2);
+    const float fr = fminf(fmaxf((float)(v - (double)r0), 0.0f), 1.0f);
+    const uchar4 a = __ldg(A.env.data + (size_t)r0 * w + c0), b = __ldg(A.env.data + (size_t)r0 * w + c1);
+    const uchar4 c = __ldg(A.env.data + (size_t)(r0 + 1) * w + c0), e = __ldg(A.env.data + (size_t)(r0 + 1) * w + c1);
+    const float s = 1.0f / 255.0f;
+    return make_float3(((a.x * (1.0f - fc) + b.x * fc) * (1.0f - fr) + (c.x * (1.0f - fc) + e.x * fc) * fr) * s,
+                       ((a.y * (1.0f - fc) + b.y * fc) * (1.0f - fr) + (c.y * (1.0f - fc) + e.y * fc) * fr) * s,
+                       ((a.z * (1.0f - fc) + b.z * fc) * (1.0f - fr) + (c.z * (1.0f - fc) + e.z * fc) * fr) * s);
+}
+
+// the same for a body-frame ray direction (scene = R^T body)
+__device__ __forceinline__ float3 miss_radiance_body(const RenderArgs& A, const Ray64& R) {
+    const SceneParams& sp = A.sp;
+    return miss_radiance(A, sp.ex[0] * R.dx + sp.ey[0] * R.dy + sp.ez[0] * R.dz,
+                            sp.ex[1] * R.dx + sp.ey[1] * R.dy + sp.ez[1] * R.dz,
+                            sp.ex[2] * R.dx + sp.ey[2] * R.dy + sp.ez[2] * R.dz);
 }
 
 // hit64 debug record (tests): everything from the float64 hit point
@@ -582,7 +638,13 @@ trace_kernel_referee(const __grid_constant__ RenderArgs A) {
             TraceOut h;
             const int who = referee_ray<I16>(A, stack, R, 0.0, A.hf.top - 3, false, fast, fh, h, cnt, entered);
             if (lane == 0) { ++rs.primary; if (entered) ++rs.inside; }
-            if (who < 0) { if (lane == 0) write_miss(A, x, y, sm == A.hit_sample); continue; }
+            if (who < 0) {
+                if (lane == 0) {
+                    write_miss(A, x, y, sm == A.hit_sample);
+                    if (sees_background(A)) { const float3 m = miss_radiance_body(A, R); acc.x += m.x; acc.y += m.y; acc.z += m.z; }
+                }
+                continue;
+            }
             float3 lit = make_float3(0.f, 0.f, 0.f);
             bool need_shadow = false;
             if (lane == who) need_shadow = fast ? shade_fast(A, R, fh, x, y, pixel, sm, lit, S) : shade_hit(A, R, h, x, y, pixel, sm, lit, S);
@@ -625,7 +687,7 @@ static void to_body(const SceneParams& sp, const double* v, double* out) {
 
 // launch arguments common to every kernel of the path
 static void fill_render_args(mrtx_ctx* ctx, int x0, int y0, int x1, int y1, unsigned s0, unsigned ns, RenderArgs& A) {
-    A.hf = ctx->hf; A.tex = ctx->tex[0]; A.cam = ctx->cam; A.sp = ctx->sp;
+    A.hf = ctx->hf; A.tex = ctx->tex[0]; A.env = ctx->tex[2]; A.cam = ctx->cam; A.sp = ctx->sp;
     A.width = ctx->width; A.height = ctx->height;
     A.x0 = x0; A.y0 = y0; A.x1 = x1; A.y1 = y1;
     A.sample0 = s0; A.nsamples = ns; A.hit_sample = 0u;

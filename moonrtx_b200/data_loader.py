@@ -106,6 +106,21 @@ def _color_reduce_lut(src: np.ndarray, lut: np.ndarray, k: int, dev: Device) -> 
     return out
 
 
+def resize_cubic(img: np.ndarray, width: int, height: int, device: Optional[Device] = None) -> np.ndarray:
+    """cv2.resize(img, (width, height), interpolation=cv2.INTER_CUBIC) of a float32 (H, W, C) image followed by the clip
+    to [0, 1] - the two lines of load_starmap that touch every pixel (data_loader.py:412-415) - on the device."""
+    src = np.ascontiguousarray(img, dtype=np.float32)
+    if src.ndim == 2:
+        src = src[..., None]
+    if src.ndim != 3 or not (1 <= src.shape[2] <= 4):
+        raise ValueError("image must be (H, W) or (H, W, C <= 4) float32")
+    dev = device or get_device()
+    out = np.empty((int(height), int(width), src.shape[2]), dtype=np.float32)
+    _lib.check(dev.lib.mrtx_resize_cubic_f32(dev.ctx, src.ctypes.data, src.shape[1], src.shape[0], src.shape[2],
+                                             out.ctypes.data, int(width), int(height)))
+    return out
+
+
 # --------------------------------------------------------------------------------------
 # file level (same behaviour as the reference functions)
 # --------------------------------------------------------------------------------------
@@ -220,3 +235,36 @@ def load_color_data(filepath: str, gamma: float = 2.2, downscale: int = 1) -> np
         ident = _color_reduce_lut(np.ascontiguousarray(src), np.arange(256, dtype=np.uint8), downscale, get_device())
         _cache_save(base, np.ascontiguousarray(ident[..., 2::-1]), fingerprint)
     return color_texture(src, gamma, downscale)
+
+
+def load_starmap(filepath: str, target_width: int) -> Optional[np.ndarray]:
+    """
+    data_loader.py:371-425: the star map for the background, float32 RGB (h, w, 3) in [0, 1], at most `target_width` wide;
+    None if the file is missing or unreadable.  Same cache files (`<file>.w<width>.npy` + sidecar); the bicubic resize
+    of the 16k source runs on the device.
+    """
+    if not os.path.isfile(filepath):
+        print(f"Star map not found: {filepath}")
+        return None
+    print(f"Loading star map from {filepath}...")
+    cache_base = f"{filepath}.w{target_width}"
+    fingerprint = _fingerprint(filepath, target_width=target_width)
+    star_map, _ = _cache_load(cache_base, fingerprint)
+    if star_map is not None:
+        print(f"  Loaded from cache: {cache_base}.npy, dimensions {star_map.shape}")
+        return star_map
+    import cv2
+    star_src = cv2.imread(filepath)
+    if star_src is None:
+        print(f"Failed to read star map: {filepath}")
+        return None
+    star_src = star_src[..., ::-1].astype(np.float32)
+    star_src *= 1 / 255
+    if target_width < star_src.shape[1]:
+        target_height = int(star_src.shape[0] * target_width / star_src.shape[1])
+        star_map = resize_cubic(star_src, target_width, target_height)
+    else:
+        star_map = star_src
+    print(f"  Dimensions: {star_map.shape}")
+    _cache_save(cache_base, star_map, fingerprint)
+    return star_map

@@ -165,10 +165,59 @@ class B200OptiX:
             self.refresh_scene()
 
     def set_background_mode(self, mode, refresh: bool = False):
-        self._background_mode = mode       # star background: SURVEY.md §8f N1 (next)
+        """moon_renderer.py:605: "TextureEnvironment" = the background texture is looked up by ray direction."""
+        self._background_mode = mode
+        if refresh:
+            self.refresh_scene()
 
-    def set_background(self, bg, gamma=None, rt_format=None, refresh: bool = False, **_):
-        self._background = None            # rendered black; see set_background_mode
+    def set_background(self, bg, gamma: float = 1.0, rt_format=None, refresh: bool = False, **_):
+        """
+        moon_renderer.py:606-609.  A float32 (h, w, 3) array in [0, 1] (the star map of load_starmap) becomes the
+        environment texture rays that miss the Moon see: 8-bit linear radiance v^gamma, as PlotOptiX's "UByte4"
+        format with `gamma` stores it; a scalar / colour 0 = black.  A uint8 (h, w, 4) array is taken as the finished
+        texture.  Its orientation (scene +Z up, -Y at longitude 0) is this engine's choice: PlotOptiX's own
+        TextureEnvironment mapping is closed.
+        """
+        a = np.asarray(bg)
+        with self._padlock:
+            if a.ndim == 3 and a.shape[2] == 3 and a.dtype != np.uint8:
+                a = np.ascontiguousarray(a, dtype=np.float32)
+                _lib.check(self._lib.mrtx_set_background_f32(self._ctx, a.ctypes.data, a.shape[1], a.shape[0], float(gamma)))
+                self._background = (a.shape[1], a.shape[0])
+            elif a.ndim == 3 and a.shape[2] == 4 and a.dtype == np.uint8:
+                a = np.ascontiguousarray(a)
+                _lib.check(self._lib.mrtx_set_texture_rgba8(self._ctx, 2, a.ctypes.data, a.shape[1], a.shape[0]))
+                self._background = (a.shape[1], a.shape[0])
+            elif a.size <= 4 and not np.any(a):
+                _lib.check(self._lib.mrtx_set_texture_rgba8(self._ctx, 2, None, 0, 0))
+                self._background = None
+            else:
+                raise ValueError("background must be a float (h, w, 3) image, a uint8 (h, w, 4) texture or 0")
+        if refresh:
+            self.refresh_scene()
+
+    def get_background_texture(self) -> Optional[np.ndarray]:
+        """the environment texture as the device holds it (uint8 RGBA, linear radiance); None = black"""
+        w, h = C.c_int(), C.c_int()
+        with self._padlock:
+            _lib.check(self._lib.mrtx_read_background_rgba8(self._ctx, None, C.byref(w), C.byref(h)))
+            if w.value == 0:
+                return None
+            out = np.empty((h.value, w.value, 4), np.uint8)
+            _lib.check(self._lib.mrtx_read_background_rgba8(self._ctx, out.ctypes.data, C.byref(w), C.byref(h)))
+        return out
+
+    def _push_sun_disk(self):
+        g = self._ignored_geometry.get(self._sun_disk_name) if getattr(self, "_sun_disk_name", None) else None
+        if g is None or g.get("pos") is None or g.get("r") is None:
+            _lib.check(self._lib.mrtx_set_sun_disk(self._ctx, None, 0.0, None))
+            return
+        pos = np.asarray(g["pos"], dtype=np.float64).reshape(-1)[:3]
+        r = float(np.asarray(g["r"], dtype=np.float64).reshape(-1)[0])
+        c = g.get("c")
+        col = np.asarray(1.0 if c is None else c, dtype=np.float32).reshape(-1)
+        col = np.full(3, col[0], np.float32) if col.size == 1 else col[:3].astype(np.float32)
+        _lib.check(self._lib.mrtx_set_sun_disk(self._ctx, (C.c_double * 3)(*pos), r, (C.c_float * 3)(*col)))
 
     def update_material(self, name, data, refresh: bool = False):
         self._material = (name, dict(data))
@@ -192,8 +241,13 @@ class B200OptiX:
                     self._moon["r"] = float(np.asarray(r, dtype=np.float64).reshape(-1)[0])
                 self._push_frame()
         else:
-            # sun disk / overlay geometry: not on the hot path
+            # a single flat-shaded particle is the visible Sun disk (moon_renderer.py:643-650): rendered on rays that
+            # miss the Moon; other overlay geometry is recorded only
             self._ignored_geometry[name] = {"geom": geom, "pos": pos, "r": r, "c": c, "mat": mat}
+            if geom == "ParticleSet" and mat == "flat" and pos is not None and np.asarray(pos).size == 3:
+                with self._padlock:
+                    self._sun_disk_name = name
+                    self._push_sun_disk()
         if refresh:
             self.refresh_scene()
 
@@ -216,6 +270,10 @@ class B200OptiX:
         if name == self._moon_name:
             raise ValueError("the displaced surface cannot be deleted")
         self._ignored_geometry.pop(name, None)
+        if name == getattr(self, "_sun_disk_name", None):
+            with self._padlock:
+                self._sun_disk_name = None
+                self._push_sun_disk()
 
     def get_geometry_names(self):
         return [self._moon_name] + list(k for k in self._ignored_geometry if not k.startswith("material:"))
@@ -234,6 +292,9 @@ class B200OptiX:
                 self._push_frame()
         elif name in self._ignored_geometry:
             self._ignored_geometry[name].update({k: w for k, w in (("pos", pos), ("r", r), ("c", c)) if w is not None})
+            if name == getattr(self, "_sun_disk_name", None):
+                with self._padlock:
+                    self._push_sun_disk()
         else:
             raise ValueError(f"no geometry named {name}")
         if refresh:

@@ -58,6 +58,12 @@ typedef struct {
     const uint8_t* tex;
     int tex_w, tex_h;
     float exposure, inv_gamma;
+    /* what a ray that misses the Moon sees (moon_renderer.py:602-609, 643-650): the visible Sun disk, a flat-shaded
+     * sphere in scene space (radius <= 0: none), else the star map, an equirectangular RGBA8 environment texture of
+     * linear radiance (null: black) */
+    double sun_disk_pos[3], sun_disk_radius, sun_disk_color[3];
+    const uint8_t* env;
+    int env_w, env_h;
 } orc_scene;
 
 /* ------------------------------------------------------------------------------ */
@@ -371,6 +377,41 @@ static void sample_albedo(const orc_scene* S, double lon, double lat, double* rg
     }
 }
 
+/* Radiance along a scene-space ray (origin o, unit direction d) that does not meet the Moon.
+ * Sun disk: nearest intersection with the sphere (flat material: its colour, no lighting, moon_renderer.py:133-139).
+ * Environment: direction -> (lon, lat) with the scene's +Z up and -Y at longitude 0 (the convention the reference uses
+ * for the Moon itself, renderer_navigation.py:47-53; PlotOptiX's own TextureEnvironment mapping is closed - inferred),
+ * u = (lon / 2 pi + 0.5) w - 0.5, v = (0.5 - lat / pi) h - 0.5, bilinear, columns wrap, rows clamp. */
+static void miss_radiance(const orc_scene* S, const double* o, const double* d, double* rgb) {
+    rgb[0] = rgb[1] = rgb[2] = 0.0;
+    if (S->sun_disk_radius > 0.0) {
+        const double oc[3] = {o[0] - S->sun_disk_pos[0], o[1] - S->sun_disk_pos[1], o[2] - S->sun_disk_pos[2]};
+        const double b = dot3(oc, d), c = dot3(oc, oc) - S->sun_disk_radius * S->sun_disk_radius;
+        const double disc = b * b - c;
+        if (disc > 0.0 && -b + sqrt(disc) > 0.0) { for (int q = 0; q < 3; ++q) rgb[q] = S->sun_disk_color[q]; return; }
+    }
+    if (!S->env) return;
+    const double lon = atan2(d[0], -d[1]), lat = asin(d[2] > 1.0 ? 1.0 : (d[2] < -1.0 ? -1.0 : d[2]));
+    const int w = S->env_w, h = S->env_h;
+    const double u = (lon / (2.0 * PI) + 0.5) * w - 0.5, v = (0.5 - lat / PI) * h - 0.5;
+    const double fu = floor(u);
+    int c0 = (int)fu;
+    const double fc = u - fu;
+    c0 = ((c0 % w) + w) % w;
+    const int c1 = (c0 + 1) % w;
+    int r0 = (int)floor(v);
+    if (r0 < 0) r0 = 0;
+    if (r0 > h - 2) r0 = h - 2;
+    double fr = v - r0;
+    if (fr < 0.0) fr = 0.0;
+    if (fr > 1.0) fr = 1.0;
+    for (int q = 0; q < 3; ++q) {
+        const double a = S->env[((size_t)r0 * w + c0) * 4 + q], b = S->env[((size_t)r0 * w + c1) * 4 + q];
+        const double c = S->env[((size_t)(r0 + 1) * w + c0) * 4 + q], e = S->env[((size_t)(r0 + 1) * w + c1) * 4 + q];
+        rgb[q] = ((a * (1.0 - fc) + b * fc) * (1.0 - fr) + (c * (1.0 - fc) + e * fc) * fr) / 255.0;
+    }
+}
+
 /*
  * Render samples sample0 .. sample0+nsamples-1 of the pixels (x0 + i*stride, y0 + j*stride)
  * inside [x0,x1) x [y0,y1).  Outputs are compact arrays over that sub-grid, row-major:
@@ -440,6 +481,8 @@ long orc_render(const orc_scene* S, int x0, int y0, int x1, int y1, int stride,
                         const double E = S->light_radiance * (S->light_radius / dist) * (S->light_radius / dist) * cosl * vis;
                         for (int q = 0; q < 3; ++q) rgb[q] = alb[q] * E;
                     }
+                } else {
+                    miss_radiance(S, S->eye, dir, rgb);
                 }
                 acc[0] += rgb[0]; acc[1] += rgb[1]; acc[2] += rgb[2]; acc[3] += 1.0;
                 if (hit64) {

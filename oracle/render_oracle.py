@@ -36,6 +36,8 @@ class _Scene(C.Structure):
         ("jitter", C.c_int), ("shadows", C.c_int),
         ("tex", C.c_void_p), ("tex_w", C.c_int), ("tex_h", C.c_int),
         ("exposure", C.c_float), ("inv_gamma", C.c_float),
+        ("sun_disk_pos", _D3), ("sun_disk_radius", C.c_double), ("sun_disk_color", _D3),
+        ("env", C.c_void_p), ("env_w", C.c_int), ("env_h", C.c_int),
     ]
 
 
@@ -86,7 +88,7 @@ class OracleScene:
                  eye=(0, -300, 0), target=(0, 0, 0), up=(0, 0, 1), fov=4.242192793,
                  light_pos=(21460.0, 0.0, 0.0), light_radius=100.0, light_radiance=80.0 * (2146.0 / 100.0) ** 2,
                  scene_epsilon=1.0e-4, jitter=False, shadows=True, texture=None,
-                 exposure=0.9, gamma=2.2):
+                 exposure=0.9, gamma=2.2, background=None, sun_disk=None):
         self.s = _Scene()
         s = self.s
         self.elevation = np.ascontiguousarray(elevation)
@@ -128,6 +130,20 @@ class OracleScene:
             s.tex = self.texture.ctypes.data
             s.tex_h, s.tex_w = self.texture.shape[:2]
         s.exposure, s.inv_gamma = float(exposure), float(1.0 / gamma)
+        # what rays that miss the Moon see: background = RGBA8 environment texture of linear radiance (the star map as
+        # moonrtx_b200.data_loader.background_texture prepares it), sun_disk = (centre, radius, colour)
+        self.background = None
+        if background is not None:
+            self.background = np.ascontiguousarray(background, dtype=np.uint8)
+            s.env = self.background.ctypes.data
+            s.env_h, s.env_w = self.background.shape[:2]
+        s.sun_disk_radius = 0.0
+        if sun_disk is not None:
+            c, r, col = sun_disk
+            s.sun_disk_pos = _D3(*[float(x) for x in c])
+            s.sun_disk_radius = float(r)
+            col = np.broadcast_to(np.asarray(col, dtype=np.float64).reshape(-1), (3,)) if np.size(col) in (1, 3) else np.asarray(col, dtype=np.float64)[:3]
+            s.sun_disk_color = _D3(*[float(x) for x in col])
 
     def render(self, x0=0, y0=0, x1=None, y1=None, stride=1, sample0=0, nsamples=1):
         s = self.s

@@ -162,3 +162,27 @@ def test_file_level_functions_and_cache_format(dl, tmp_path):
     cached = np.load(pc + ".ds4.npy")
     assert np.array_equal(cached, orc.color_reduce(col, 4))  # the reference caches reduced BGR
     assert np.array_equal(dl.load_color_data(pc, 1.0, 4), orc.load_color(col, 1.0, 4))
+
+
+def test_starmap_bicubic_resize_matches_opencv(tmp_path):
+    """load_starmap (data_loader.py:371-425): BGR -> RGB / 255, cv2.resize(INTER_CUBIC) to the target width, clip - the
+    resize on the device against OpenCV's own on the same image; and the file-level function with its cache."""
+    import cv2
+    from moonrtx_b200.data_loader import load_starmap, resize_cubic
+    rng = np.random.default_rng(3)
+    src = rng.uniform(0, 1, (257, 512, 3)).astype(np.float32)
+    src[rng.integers(0, 257, 300), rng.integers(0, 512, 300)] = 1.0
+    for (w, h) in ((128, 64), (200, 100), (511, 256), (37, 19)):
+        want = np.clip(cv2.resize(src, (w, h), interpolation=cv2.INTER_CUBIC), 0, 1)
+        got = resize_cubic(src, w, h)
+        assert got.shape == want.shape and float(np.abs(got - want).max()) <= 2e-6, float(np.abs(got - want).max())
+    img8 = (rng.uniform(0, 1, (128, 256, 3)) ** 6 * 255).astype(np.uint8)
+    path = str(tmp_path / "stars.tif")
+    cv2.imwrite(path, img8)
+    got = load_starmap(path, 96)
+    ref = cv2.imread(path)[..., ::-1].astype(np.float32) * (1 / 255)
+    want = np.clip(cv2.resize(ref, (96, 48), interpolation=cv2.INTER_CUBIC), 0, 1)
+    assert got.dtype == np.float32 and got.shape == (48, 96, 3) and float(np.abs(got - want).max()) <= 2e-6
+    again = load_starmap(path, 96)                       # served from <file>.w96.npy
+    assert np.array_equal(again, got)
+    assert load_starmap(str(tmp_path / "missing.tif"), 96) is None

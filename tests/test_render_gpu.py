@@ -499,3 +499,51 @@ def test_fine_cells_polar_and_limb_rays_match_oracle():
     assert rt.counters()["overflow"] == 0
     print({k: v for k, v in m.items() if k not in ("img", "oracle")}, d)
     rt.close()
+
+
+def test_star_map_background_and_sun_disk_on_miss_rays():
+    """what the 64 % of a whole-disk frame that misses the Moon shows.  The reference's own calls
+    (moon_renderer.py:602-609, 643-650, 855): set_background_mode("TextureEnvironment"), set_background(star map,
+    gamma, "UByte4"), a flat-shaded "sun_disk" particle placed by update_data.  The oracle reads the same 8-bit environment
+    texture and the same sphere: every pixel of the frame is compared, at 1 spp and with jittered samples."""
+    elev, _ = synth_elevation(720, 360, seed=6)
+    rng = np.random.default_rng(5)
+    stars = np.zeros((180, 360, 3), np.float32)
+    stars += rng.uniform(0.0, 0.04, stars.shape).astype(np.float32)
+    ys, xs = rng.integers(0, 180, 400), rng.integers(0, 360, 400)
+    stars[ys, xs] = rng.uniform(0.3, 1.0, (400, 3)).astype(np.float32)
+    # the Sun disk a little off the limb, as calculate_sun_disk places it near new moon (moon_renderer.py:775-777)
+    disk_pos, disk_r = [14.0 * 3100 / 300, -300.0 + 3100.0, 6.0 * 3100 / 300], 3100 * math.tan(math.radians(0.45))
+    kw = dict(light_pos=sun_at_phase(120.0))
+    for spp in (1, 8):
+        rt = make_gpu(elev, 192, 128, debug_hits=False, **kw)
+        rt.set_background_mode("TextureEnvironment")
+        rt.set_background(stars, gamma=2.2, rt_format="UByte4")
+        rt.setup_material("flat", {"dummy": 1})
+        rt.set_data("sun_disk", geom="ParticleSet", mat="flat", pos=[[0.0, 3100.0, 0.0]], r=0.01, c=2.0)
+        rt.update_data("sun_disk", pos=[disk_pos], r=disk_r)
+        if spp > 1:
+            rt.set_param(max_accumulation_frames=spp, min_accumulation_step=spp)
+        img = rt.render_cycle().copy()
+        env = rt.get_background_texture()
+        # the texture itself: round(255 v^gamma), data as PlotOptiX's UByte4 + gamma stores it
+        want = np.rint(255.0 * np.clip(stars.astype(np.float64), 0, 1) ** 2.2).astype(np.uint8)
+        assert env.shape == (180, 360, 4) and np.array_equal(env[..., :3], want) and np.all(env[..., 3] == 255)
+        orc = make_oracle(elev, 192, 128, jitter=spp > 1, background=env, sun_disk=(disk_pos, disk_r, 2.0), **kw)
+        o = orc.render(nsamples=spp)
+        ref = orc.tonemap(o["accum"])
+        miss = o["hit64"][..., 0] <= 0
+        assert miss.mean() > 0.5
+        d = np.abs(img[..., :3].astype(np.int32) - ref[..., :3].astype(np.int32))
+        assert int(d[miss].max()) <= 1, int(d[miss].max())                  # background pixels: the same lookup
+        mae, psnr = image_metrics(img, ref)
+        assert mae <= 1.0 and psnr >= 40.0, (mae, psnr)
+        # the disk is there (pure white where the flat colour 2.0 saturates) and stars are visible
+        assert int((img[..., :3].min(axis=2) == 255).sum()) > 30
+        assert int((img[miss][:, :3].max(axis=1) > 60).sum()) > 20
+        # removing both gives the black background back
+        rt.set_background(0)
+        rt.delete_geometry("sun_disk")
+        img0 = rt.render_cycle()
+        assert int(img0[miss][:, :3].max()) == 0
+        rt.close()
