@@ -121,5 +121,5 @@ def test_config5_8k_eyepiece_on_the_terminator(full_map):
     grazing sun incidence in every pixel."""
     kw = frame_kw(0)
     kw["fov"] = 2.5
-    m = check_frame(full_map, 7680, 4320, 120, kw, min_hits=2000)
+    m = check_frame(full_map, 7680, 4320, 80, kw, min_hits=3000)
     print("config 5", m)
