@@ -157,3 +157,71 @@ def test_reference_video_overlay_calls_bind_to_the_dropin():
     for name in ("_padlock", "_width", "_height", "_is_started", "_optix"):
         assert name in B200OptiX.__init__.__code__.co_names or hasattr(B200OptiX, name) or name in inspect.getsource(B200OptiX), name
     assert len(calls) == 13
+
+
+def test_unmodified_reference_export_callback_call_order(tmp_path):
+    """renderer_video.py:148-320 run UNMODIFIED against the recording proxy: per exported frame the reference draws the
+    next frame's overlay, then update_view moves the scene and refreshes - the order tests/test_video_export_gpu.py
+    restates on the GPU box (where the reference tree does not exist).  Also drives update_overlays with the grid and a pin
+    enabled (renderer_labels.py, renderer_pins.py): set_graph / update_graph / delete_geometry must exist on the drop-in."""
+    from datetime import datetime, timedelta
+    mr = ref_stub.import_reference("moon_renderer")
+    calls = []
+    mr.TkOptiX = make_proxy_class(calls)
+    r = bare_renderer(mr, tmp_path)
+    r._init_video_export()
+    r.init_renderer()
+    from moonrtx_b200.synth import synth_ephemeris
+    mr.astro.calculate_moon_ephemeris = lambda dt, parallactic: synth_ephemeris(600.0)
+    r.parallactic_mode = False
+    r.dt_local = datetime(2026, 1, 1)
+    r.in_observer_clock = lambda d: d
+    r.shifted_time = lambda minutes: r.dt_local + timedelta(minutes=minutes)
+    r.update_overlays = lambda: None
+    r.sync_datetime_dialog = lambda: None
+    r._auto_advance_var = None
+    r._preview_restore_id = None
+    r._preview_active = False
+    posted = []
+    r.rt._root = type("Root", (), {"after": lambda self, ms, fn, *a: posted.append((fn, a)), "after_cancel": lambda self, i: None})()
+    r.rt.encoder_is_open = lambda: True                 # (a started encoder is always open, renderer_video.py:246-252)
+    progress = []
+    err = r.start_video_export(str(tmp_path / "x.mp4"), 3, 10, 25, 16.0, lambda f, n, dt: progress.append(f), lambda e: progress.append(("done", e)))
+    assert err is None
+    names = [c[0] for c in calls]
+    for must in ("encoder_create", "encoder_start", "set_accum_done_cb", "set_texture_2d", "add_postproc", "refresh_scene"):
+        assert must in names, must
+    cb = next(c for c in calls if c[0] == "set_accum_done_cb")[1][0]
+    for frame in (1, 2):
+        n0 = len(calls)
+        cb(r.rt)                                        # what the render thread does after each accumulation cycle
+        seq = [c[0] for c in calls[n0:]]
+        i_ov, i_data, i_ref = seq.index("set_texture_2d"), seq.index("update_data"), seq.index("refresh_scene")
+        assert i_ov < i_data < i_ref, seq                # overlay of the NEXT frame first, then update_view, then the refresh
+        ov = calls[n0 + i_ov]
+        assert ov[1][0] == "frame_overlay" and ov[2] == {"filter_mode": "Nearest", "refresh": False}
+    n0 = len(calls)
+    cb(r.rt)                                            # third frame: the export ends
+    assert ("set_accum_done_cb", (None,), {}) in calls[n0:]
+
+    # grid + pins through the unmodified overlay code: the geometry calls exist and bind
+    for name in ("set_graph", "update_graph", "delete_geometry"):
+        from moonrtx_b200.optix import B200OptiX
+        assert callable(getattr(B200OptiX, name, None)), name
+    # the UNMODIFIED grid / pin code of the reference (renderer_labels.py:263-305, 513-527; renderer_pins.py:18-69, 149-163)
+    # and the real update_overlays (moon_renderer.py:781-789) with both visible
+    del r.update_overlays
+    r.view_orientation = r.initial_view_orientation = getattr(mr, "VIEW_ORIENTATION_NSWE", "NSWE")
+    r.moon_grid, r.moon_grid_visible = None, False
+    r.standard_labels_visible = r.spot_labels_visible = False
+    r.pins, r.pins_visible = {}, True
+    n0 = len(calls)
+    r.setup_moon_grid()
+    r.create_pin(3, 10.0, 20.0)
+    r.update_overlays()
+    r.remove_pin(3)
+    geo = [c for c in calls[n0:] if c[0] in ("set_graph", "update_graph", "delete_geometry")]
+    kinds = [c[0] for c in geo]
+    assert kinds.count("set_graph") == 3 and "update_graph" in kinds and kinds[-1] == "delete_geometry", kinds
+    grid = next(c for c in geo if c[0] == "set_graph")
+    assert set(grid[2]) >= {"pos", "edges", "r", "c", "mat"}
