@@ -393,7 +393,10 @@ __device__ __noinline__ void write_hit64(const RenderArgs& A, const Ray64& R, co
 
 // Lambert term, albedo and shadow ray of a primary hit; float32 except where positions near R are
 // added or subtracted.  Same model as shade_hit().
-__device__ __forceinline__ bool shade_fast(const RenderArgs& A, const Ray64& R, const FastHit& h, int x, int y,
+#ifndef MRTX_SHADE_ATTR
+#define MRTX_SHADE_ATTR __forceinline__
+#endif
+__device__ MRTX_SHADE_ATTR bool shade_fast(const RenderArgs& A, const Ray64& R, const FastHit& h, int x, int y,
                                            uint32_t pixel, unsigned sm, float3& lit, Ray64& S) {
     const SceneParams& sp = A.sp;
     const double px = fma(h.s, R.dx, R.ox), py = fma(h.s, R.dy, R.oy), pz = fma(h.s, R.dz, R.oz);

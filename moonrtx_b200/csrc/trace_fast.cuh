@@ -170,8 +170,11 @@ MRTX_HD inline void load_raw_patch(const HeightField& hf, int r0, int c0, RawPat
     }
 }
 
+#ifndef MRTX_TEST_ATTR
+#define MRTX_TEST_ATTR inline
+#endif
 template <bool I16>
-MRTX_HD inline int fast_test(const HeightField& hf, const FastConsts& K, const Ray64& R, double s_in, double s_lo,
+MRTX_HD MRTX_TEST_ATTR int fast_test(const HeightField& hf, const FastConsts& K, const Ray64& R, double s_in, double s_lo,
                              float ws, float we, float smax, RawPatch P, bool any_hit, FastHit& out) {
     if (!K.enabled) return FT_DEFER_R(1);
     const double s_c = s_in + (double)ws;
