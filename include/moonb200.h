@@ -198,7 +198,8 @@ int  mrtx_read_hit_f64(mrtx_ctx* ctx, double* out);
 int  mrtx_counters(mrtx_ctx* ctx, uint64_t out[16], int reset);
 /* Stopwatch of the trace path (engine switch "profile" = 1): CUDA events at the kernel boundaries of every mrtx_render
  * since the last reset, summed: out_ms[0] cull_kernel, [1] beam_kernel, [2] trace_kernel_fast, [3] shadow_kernel,
- * [4] trace_kernel_referee, [5] fold_kernel (first sample chunk / pixel wave of each launch), [6] launches measured.
+ * [4] trace_kernel_referee, [5] fold_kernel (first sample chunk / pixel wave of each launch), [6] launches measured,
+ * [7] shade_kernel.
  * bench.py reads the dominant kernel's launch duration from it (roofline.achieved).                              */
 int  mrtx_kernel_times(mrtx_ctx* ctx, double out_ms[8], int reset);
 /* the filtered kernel's deferrals since the last reset: [0] samples handed to the exact kernel;

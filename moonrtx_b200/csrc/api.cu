@@ -69,7 +69,7 @@ int mrtx_create(int device, mrtx_ctx** out_ctx) {
     sp.light_pos[0] = 21460.0; sp.light_radius = 100.0; sp.light_radiance = 80.0 * 460.5316;
     sp.scene_epsilon = 1.0e-4;
     sp.exposure = 0.9f; sp.inv_gamma = 1.0f / 2.2f;
-    sp.jitter = 0; sp.shadows = 1; sp.debug_hits = 0; sp.kernel = 2; sp.beam = 0; sp.beam_drop = 2; sp.ceiling = 0; sp.shadow_queue = 1; sp.start_primary = 3; sp.start_shadow = 2; sp.long_walk = 2048u; sp.referee_budget = 500u;
+    sp.jitter = 0; sp.shadows = 1; sp.debug_hits = 0; sp.kernel = 2; sp.beam = 0; sp.beam_drop = 2; sp.ceiling = 0; sp.shadow_queue = 2; sp.start_primary = 3; sp.start_shadow = 2; sp.long_walk = 2048u; sp.referee_budget = 500u;
     const double eye[3] = {0, -300, 0}, tgt[3] = {0, 0, 0}, up[3] = {0, 0, 1};
     mrtx_set_camera(c, eye, tgt, up, 4.242192793);
     *out_ctx = c;
@@ -104,7 +104,7 @@ int mrtx_destroy(mrtx_ctx* ctx) {
     cudaFree(ctx->d_counters);
     cudaFree(ctx->d_defer_stats);
     cudaFree(ctx->wave_buf);
-    cudaFree(ctx->sq_buf);
+    cudaFree(ctx->sq_buf); cudaFree(ctx->hq_buf);
     if (ctx->prof_ev) { for (int i = 0; i < MRTX_PROF_MAX * MRTX_PROF_EVENTS; ++i) cudaEventDestroy(ctx->prof_ev[i]); free(ctx->prof_ev); }
     cudaFree(ctx->flush_buf);
     if (ctx->h_rs) cudaFreeHost(ctx->h_rs);
@@ -623,7 +623,7 @@ int mrtx_set_uint(mrtx_ctx* ctx, const char* name, unsigned a, unsigned b) {
     else if (!strcmp(name, "ceiling")) ctx->sp.ceiling = a;
     else if (!strcmp(name, "profile")) ctx->prof_on = a ? 1 : 0;
     else if (!strcmp(name, "blocks_per_sm")) ctx->sp.blocks_per_sm = a;
-    else if (!strcmp(name, "shadow_queue")) ctx->sp.shadow_queue = a ? 1u : 0u;
+    else if (!strcmp(name, "shadow_queue")) ctx->sp.shadow_queue = a > 2u ? 2u : a;
     else if (!strcmp(name, "beam")) { ctx->sp.beam = a ? 1u : 0u; ctx->sp.beam_drop = b; }
     else if (!strcmp(name, "kernel")) { MRTX_REQUIRE(a <= 3u, "kernel must be 0, 1, 2 or 3"); ctx->sp.kernel = a; }
     else { mrtx_set_error("unknown uint parameter '%s'", name); return MRTX_ERR_INVALID; }
@@ -897,8 +897,10 @@ int mrtx_kernel_times(mrtx_ctx* ctx, double out_ms[8], int reset) {
     (void)cudaGetLastError();
     ctx->prof_n = 0;
     if (out_ms) {
-        for (int k = 0; k < 6; ++k) out_ms[k] = ctx->prof_ms[k];
-        out_ms[6] = (double)ctx->prof_launches; out_ms[7] = 0.0;
+        // intervals: 0 cull, 1 beam, 2 trace_kernel_fast, 3 shade_kernel, 4 shadow_kernel, 5 referee, 6 fold
+        out_ms[0] = ctx->prof_ms[0]; out_ms[1] = ctx->prof_ms[1]; out_ms[2] = ctx->prof_ms[2];
+        out_ms[3] = ctx->prof_ms[4]; out_ms[4] = ctx->prof_ms[5]; out_ms[5] = ctx->prof_ms[6];
+        out_ms[6] = (double)ctx->prof_launches; out_ms[7] = ctx->prof_ms[3];
     }
     if (reset) { for (int k = 0; k < 8; ++k) ctx->prof_ms[k] = 0.0; ctx->prof_launches = 0; }
     return MRTX_OK;

@@ -41,7 +41,7 @@ void mrtx_set_error(const char* fmt, ...);
 
 // ---- scene state ------------------------------------------------------------------
 #define MRTX_PROF_MAX 256
-#define MRTX_PROF_EVENTS 7       // before cull, after cull, beam, trace_kernel_fast, shadow_kernel, referee, fold
+#define MRTX_PROF_EVENTS 8       // before cull, after cull, beam, trace_kernel_fast, shade_kernel, shadow_kernel, referee, fold
 #define MRTX_MAX_LEVELS 20
 #define MRTX_DIL_MIN_LEVEL 2     // lowest level that has a dilated copy (beam pre-pass)
 
@@ -97,7 +97,8 @@ struct SceneParams {
     unsigned start_primary, start_shadow;   // filtered kernel: primary rays start at level top - start_primary, shadow rays at start_shadow
     unsigned long_walk, referee_budget;     // walks longer than long_walk nodes go to the referee; a referee lane spends referee_budget on a piece
     unsigned blocks_per_sm;                 // development: cap on resident blocks per SM of the two walk kernels (0 = what fits)
-    unsigned shadow_queue;                  // shadow rays through the streaming queue kernel (default) or inside trace_kernel_fast
+    unsigned shadow_queue;                  // 2 (default): primary hits -> hit queue -> shade_kernel -> shadow queue -> shadow_kernel;
+                                            // 1: shading inside trace_kernel_fast, shadow rays through the queue; 0: everything inside trace_kernel_fast
     unsigned ceiling;                       // shadow rays: ceiling test from this level upwards (0 = off)
     unsigned beam, beam_drop;               // beam pre-pass of the filtered kernel (launches of >= 4 samples); samples start beam_drop levels below the beam's
     unsigned kernel;                        // 2 = filtered float32 kernel + exact kernel on what it defers (default),
@@ -136,7 +137,8 @@ struct mrtx_ctx {
     unsigned* pixel_list;       // width * height entries
     uint2* defer_list;          // width * height entries: samples the filtered kernel hands to the exact one
     unsigned long long* accfix; // 3 * width * height: order-independent radiance sums of a launch (folded into accum at its end)
-    void* sq_buf; size_t sq_cap; // shadow queue (allocated on first use): sq_cap ray records + aux entries
+    void* sq_buf; size_t sq_cap; // shadow queue (allocated on first use): sq_cap ray records + aux entries ...
+    void* hq_buf; size_t hq_cap; // ... and the hit queue in front of it: hq_cap slots
     double* beam_s;             // width * height entries (by position in the pixel list): where the pixel's samples start ...
     unsigned char* beam_l;      // ... and the level the beam pre-pass stopped at
     // wavefront pipeline scratch (allocated on first use): ray / hit records, radiance slots, shadow queue, deferred items

@@ -76,9 +76,15 @@ beam_kernel(const __grid_constant__ RenderArgs A) {
 #ifndef MRTX_FAST_MINBLOCKS
 #define MRTX_FAST_MINBLOCKS 8
 #endif
-template <bool I16, bool QUEUE>
+// MODE (SceneParams::shadow_queue): 0 both rays and the shading in this kernel; 1 shading here, shadow ray -> shadow queue;
+// 2 (production) the kernel ends at the primary hit, which goes to the hit queue: shade_kernel (dense, one thread per hit)
+// shades it and pushes the shadow ray.  Cutting there takes the shading, the second first-cell lookup and the record
+// store out of this kernel's 70 KB of code and out of its register budget (measured at config 3: 19.0 -> 14.0 ms for
+// this kernel, + shade_kernel).
+template <bool I16, int MODE>
 __global__ void __launch_bounds__(128, MRTX_FAST_MINBLOCKS)
 trace_kernel_fast(const __grid_constant__ RenderArgs A) {
+    constexpr bool QUEUE = MODE == 1;
     __shared__ unsigned s_off[2 * MRTX_MAX_LEVELS];          // level offsets (HeightField::off) where a per-lane index is cheap
     if (threadIdx.x < 2 * MRTX_MAX_LEVELS) s_off[threadIdx.x] = A.hf.off[threadIdx.x];
     __syncthreads();
@@ -132,13 +138,33 @@ trace_kernel_fast(const __grid_constant__ RenderArgs A) {
             float3 lit = make_float3(0.f, 0.f, 0.f);
             bool defer = false, want = active, hit = false, entered = false, occluded = false, shadowed = false;
 #pragma unroll 1
-            for (int pass = 0; pass < (QUEUE ? 1 : 2); ++pass) {        // 0: primary ray, 1: shadow ray (in-kernel form)
+            for (int pass = 0; pass < (MODE == 2 ? 1 : 2); ++pass) {    // 0: primary ray, 1: shadow ray
                 bool alive = false;
                 if (want) {
                     if (pass == 0) primary_ray_fast(A, x, y, pixel, sm, R);
-                    const int wb = walk_begin2(A.hf, A.sp.radius, R, pass ? 0.0 : s_beam, pass ? (int)A.sp.start_shadow : lvl_primary, st);
+                    // (ONE call site for both rays: the first-cell lookup is 4 KB of code, and this kernel's instruction
+                    //  footprint is what stalls it - profiles/r06: "no instruction" is its largest stall reason)
+                    const int wb = walk_begin2(A.hf, A.sp.radius, R, pass ? 0.0 : s_beam,
+                                               pass ? (QUEUE ? A.sq_level : (int)A.sp.start_shadow) : lvl_primary, st);
                     alive = wb == 2;
                     if (pass == 0) entered = wb != 0;
+                }
+                if (QUEUE && pass == 1) {
+                    // the shadow ray leaves the kernel here: set up to its first cell, pushed with what it carries
+                    const bool push = alive;
+                    const unsigned pm = __ballot_sync(FULL, push);
+                    if (pm) {
+                        unsigned base = 0;
+                        if (lane == __ffs(pm) - 1) base = atomicAdd(&A.work_counter[5], (unsigned)__popc(pm));
+                        base = __shfl_sync(FULL, base, __ffs(pm) - 1);
+                        if (push) {
+                            const unsigned j = base + (unsigned)__popc(pm & lt);
+                            store_ray_rec(A.sq_rays + j, R, st, true);
+                            A.sq_aux[j] = make_uint4(__float_as_uint(lit.x), __float_as_uint(lit.y), __float_as_uint(lit.z), pixel | (k << 27));
+                            lit = make_float3(0.f, 0.f, 0.f);        // shadow_kernel adds it if the sun is visible
+                        }
+                    }
+                    break;
                 }
                 int res = FT_MISS;
                 int ceil_next = pass && A.sp.ceiling ? (int)A.sp.ceiling : 0x7fffffff;
@@ -201,29 +227,33 @@ trace_kernel_fast(const __grid_constant__ RenderArgs A) {
                 if (pass == 0) {
                     hit = res == FT_HIT;
                     want = false;
+                    if (MODE == 2) {
+                        // the hit leaves the kernel here.  A warp always takes 32 slots (lanes without a hit mark theirs empty),
+                        // so that shade_kernel's warps see the hits of one warp's pixels together and push their shadow rays
+                        // together: shadow_kernel's lanes are refilled from neighbouring queue entries, and rays of the same
+                        // pixels walk the same nodes (measured: hits packed densely cost shadow_kernel 1 ms in 12)
+                        const unsigned hm = __ballot_sync(FULL, hit);
+                        if (hm) {
+                            unsigned base = 0;
+                            if (lane == 0) base = atomicAdd(&A.work_counter[7], 32u);
+                            base = __shfl_sync(FULL, base, 0);
+                            uint4* q = (uint4*)(A.hq + base + (unsigned)lane);
+                            // (streaming stores: the queue is read once, much later, and must not push the pyramid out of L2)
+                            __stcs(q + 1, make_uint4((unsigned)fh.r0, (unsigned)fh.c0, hit ? pixel | (k << 27) : 0xffffffffu, 0u));
+                            if (hit) {
+                                __stcs(q, make_uint4((unsigned)__double2loint(fh.s), (unsigned)__double2hiint(fh.s), __float_as_uint(fh.fc), __float_as_uint(fh.fr)));
+                                __stcs(q + 2, make_uint4(__float_as_uint(fh.d00), __float_as_uint(fh.d01), __float_as_uint(fh.d10), __float_as_uint(fh.d11)));
+                            }
+                        }
+                        break;
+                    }
                     if (hit) {
                         Ray64 S;
                         want = shade_fast(A, R, fh, x, y, pixel, sm, lit, S);
                         shadowed = want;
                         if (want) R = S;
                     }
-                    if (QUEUE) {
-                        // the shadow ray leaves the kernel here: set up to its first cell, pushed with what it carries
-                        bool push = false;
-                        if (want) push = walk_begin(A.hf, A.sp.radius, R, 0.0, A.sq_level, st);
-                        const unsigned pm = __ballot_sync(FULL, push);
-                        if (pm) {
-                            unsigned base = 0;
-                            if (lane == __ffs(pm) - 1) base = atomicAdd(&A.work_counter[5], (unsigned)__popc(pm));
-                            base = __shfl_sync(FULL, base, __ffs(pm) - 1);
-                            if (push) {
-                                const unsigned j = base + (unsigned)__popc(pm & lt);
-                                store_ray_rec(A.sq_rays + j, R, st, true);
-                                A.sq_aux[j] = make_uint4(__float_as_uint(lit.x), __float_as_uint(lit.y), __float_as_uint(lit.z), pixel | (k << 27));
-                                lit = make_float3(0.f, 0.f, 0.f);            // shadow_kernel adds it if the sun is visible
-                            }
-                        }
-                    } else if (!__any_sync(FULL, want)) break;
+                    if (!__any_sync(FULL, want)) break;
                 } else if (want) {
                     occluded = res == FT_HIT;
                 }
@@ -265,6 +295,64 @@ trace_kernel_fast(const __grid_constant__ RenderArgs A) {
     flush_counters(A, rs, cnt, lane);
     const unsigned nd = __reduce_add_sync(FULL, n_defer);
     if (lane == 0 && nd) atomicAdd(&A.defer_stats[0], (unsigned long long)nd);
+}
+
+// ---- shade_kernel: one thread per queued primary hit ----------------------------------------------------------------------
+// Dense and coherent (hits of a warp's pixels are neighbours in the queue): the primary ray evaluated again from (pixel,
+// sample), normal, albedo, Lambert term, light sample; the shadow ray set up to its first cell and appended to the shadow
+// queue with the radiance it carries.  A lit sample that needs no shadow ray (shadows off, or a ray that starts outside the
+// bounding sphere) is added to the pixel here.
+template <bool I16>
+__global__ void __launch_bounds__(256)
+shade_kernel(const __grid_constant__ RenderArgs A) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const unsigned n_hits = A.work_counter[7];                          // slots (32 per warp that had a hit), some empty
+    const unsigned n_round = n_hits;
+    RayStats rs = {0u, 0u, 0u, 0u, 0u};
+    const Counters cnt = {0u, 0u, 0u};
+    for (unsigned it = blockIdx.x * blockDim.x + threadIdx.x; it < n_round; it += gridDim.x * blockDim.x) {
+        float3 lit = make_float3(0.f, 0.f, 0.f);
+        bool push = false;
+        Ray64 S;
+        Walk sw;
+        uint32_t pixel = 0;
+        unsigned k = 0;
+        if (it < n_hits) {
+            const uint4* q = (const uint4*)(A.hq + it);
+            const uint4 b = __ldcs(q + 1);
+            if (b.z != 0xffffffffu) {
+            const uint4 a = __ldcs(q), c = __ldcs(q + 2);
+            FastHit fh;
+            fh.s = __hiloint2double((int)a.y, (int)a.x); fh.fc = __uint_as_float(a.z); fh.fr = __uint_as_float(a.w);
+            fh.r0 = (int)b.x; fh.c0 = (int)b.y;
+            fh.d00 = __uint_as_float(c.x); fh.d01 = __uint_as_float(c.y); fh.d10 = __uint_as_float(c.z); fh.d11 = __uint_as_float(c.w);
+            pixel = b.z & 0x7ffffffu; k = b.z >> 27;
+            const int x = (int)(pixel % (unsigned)A.width), y = (int)(pixel / (unsigned)A.width);
+            const unsigned sm = A.sample0 + k;
+            Ray64 R;
+            primary_ray_fast(A, x, y, pixel, sm, R);
+            if (shade_fast(A, R, fh, x, y, pixel, sm, lit, S)) {
+                ++rs.shadow;
+                push = walk_begin(A.hf, A.sp.radius, S, 0.0, A.sq_level, sw);
+            }
+            }
+        }
+        const unsigned pm = __ballot_sync(FULL, push);
+        if (pm) {
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(&A.work_counter[5], (unsigned)__popc(pm));
+            base = __shfl_sync(FULL, base, 0);
+            if (push) {
+                const unsigned j = base + (unsigned)__popc(pm & lt);
+                store_ray_rec(A.sq_rays + j, S, sw, true);
+                A.sq_aux[j] = make_uint4(__float_as_uint(lit.x), __float_as_uint(lit.y), __float_as_uint(lit.z), pixel | (k << 27));
+            }
+        }
+        if (!push) accfix_add(A.accfix, pixel, lit);                     // (adds nothing where lit is zero)
+    }
+    flush_counters(A, rs, cnt, lane);
 }
 
 // ---- shadow queue: streaming walk with lane refill -------------------------------------------------------------------
@@ -437,27 +525,37 @@ __global__ void resolve_kernel(const float4* __restrict__ accum, const uchar4* _
 }  // namespace
 
 // shadow queue: ray records and their aux entries in one allocation
-static int ensure_shadow_queue(mrtx_ctx* ctx, size_t items) {
-    if (ctx->sq_cap >= items) return MRTX_OK;
-    MRTX_CUDA(cudaStreamSynchronize(ctx->stream));
-    cudaFree(ctx->sq_buf);
-    ctx->sq_buf = nullptr; ctx->sq_cap = 0;
-    MRTX_CUDA(cudaMalloc(&ctx->sq_buf, items * (sizeof(RayRec) + sizeof(uint4))));
-    ctx->sq_cap = items;
+// hit queue: a warp takes 32 slots per round of 2^g samples, so a sample count that is no power of two leaves part of the
+// last round's slots empty
+static int ensure_queues(mrtx_ctx* ctx, size_t items, size_t hit_slots) {
+    if (ctx->sq_cap < items) {
+        MRTX_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->sq_buf);
+        ctx->sq_buf = nullptr; ctx->sq_cap = 0;
+        MRTX_CUDA(cudaMalloc(&ctx->sq_buf, items * (sizeof(RayRec) + sizeof(uint4))));
+        ctx->sq_cap = items;
+    }
+    if (ctx->hq_cap < hit_slots) {
+        MRTX_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->hq_buf);
+        ctx->hq_buf = nullptr; ctx->hq_cap = 0;
+        MRTX_CUDA(cudaMalloc(&ctx->hq_buf, hit_slots * sizeof(HitQRec)));
+        ctx->hq_cap = hit_slots;
+    }
     return MRTX_OK;
 }
 
-template <bool I16, bool QUEUE>
+template <bool I16, int MODE>
 static int launch_fast(mrtx_ctx* ctx, RenderArgs& A, long long npix) {
     int per_sm = 0;
-    MRTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel_fast<I16, QUEUE>, 128, 0));
+    MRTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel_fast<I16, MODE>, 128, 0));
     if (per_sm < 1) per_sm = 1;
     if (ctx->sp.blocks_per_sm && (int)ctx->sp.blocks_per_sm < per_sm) per_sm = (int)ctx->sp.blocks_per_sm;
     const long long warps_needed = ((npix << A.g_log2) + 31) / 32;
     long long blocks = (long long)ctx->sm_count * per_sm;
     if (blocks * 4 > warps_needed) blocks = (warps_needed + 3) / 4;
     if (blocks < 1) blocks = 1;
-    trace_kernel_fast<I16, QUEUE><<<(unsigned)blocks, 128, 0, ctx->stream>>>(A);
+    trace_kernel_fast<I16, MODE><<<(unsigned)blocks, 128, 0, ctx->stream>>>(A);
     return MRTX_OK;
 }
 
@@ -479,10 +577,13 @@ static int launch_trace_t(mrtx_ctx* ctx, RenderArgs& A, unsigned s0, unsigned ns
     int sq_blocks = 0;
     if (queue) {
         const size_t chunk = ns < 32u ? ns : 32u;
-        rc = ensure_shadow_queue(ctx, std::min<size_t>((size_t)npix * chunk, SQ_MAX));
+        const size_t items = std::min<size_t>((size_t)npix * chunk, SQ_MAX);
+        const bool pow2 = (chunk & (chunk - 1)) == 0 && (ns <= 32u || ns % 32u == 0);
+        rc = ensure_queues(ctx, items, ctx->sp.shadow_queue >= 2u ? items * (pow2 ? 1 : 2) + 2048 : 0);
         if (rc) return rc;
         A.sq_rays = (RayRec*)ctx->sq_buf;
         A.sq_aux = (uint4*)((char*)ctx->sq_buf + ctx->sq_cap * sizeof(RayRec));
+        A.hq = (HitQRec*)ctx->hq_buf;
         A.sq_cap = (unsigned)ctx->sq_cap;
         // a ray's first cell travels in 16 + 16 bits: start no lower than the level whose grid fits
         int lvl = (int)ctx->sp.start_shadow;
@@ -506,23 +607,31 @@ static int launch_trace_t(mrtx_ctx* ctx, RenderArgs& A, unsigned s0, unsigned ns
             A.wave_p0 = (unsigned)p0; A.wave_np = (unsigned)std::min<long long>(wave_np, npix - p0);
             if (done || p0) {
                 MRTX_CUDA(cudaMemsetAsync(A.work_counter + 2, 0, 2 * sizeof(unsigned), ctx->stream));
-                MRTX_CUDA(cudaMemsetAsync(A.work_counter + 5, 0, 2 * sizeof(unsigned), ctx->stream));
+                MRTX_CUDA(cudaMemsetAsync(A.work_counter + 5, 0, 3 * sizeof(unsigned), ctx->stream));
             }
             const bool first = !done && !p0;                // (the stopwatch brackets the first chunk and wave of a launch)
-            rc = queue ? launch_fast<I16, true>(ctx, A, A.wave_np) : launch_fast<I16, false>(ctx, A, A.wave_np);
+            const bool hitq = queue && ctx->sp.shadow_queue >= 2u;
+            rc = hitq ? launch_fast<I16, 2>(ctx, A, A.wave_np) : queue ? launch_fast<I16, 1>(ctx, A, A.wave_np) : launch_fast<I16, 0>(ctx, A, A.wave_np);
             if (rc) return rc;
             if (first) prof_mark(ctx, 3);
-            if (queue) shadow_kernel<I16><<<sq_blocks, 128, 0, ctx->stream>>>(A);
+            if (hitq) shade_kernel<I16><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(A);
             if (first) prof_mark(ctx, 4);
-            trace_kernel_referee<I16, false><<<ctx->sm_count * 8, 64, 0, ctx->stream>>>(A);
+            if (queue) shadow_kernel<I16><<<sq_blocks, 128, 0, ctx->stream>>>(A);
+#ifdef MRTX_DIAG_SHADOW_TWICE
+            if (first) prof_mark(ctx, 4);
+            MRTX_CUDA(cudaMemsetAsync(A.work_counter + 6, 0, sizeof(unsigned), ctx->stream));
+            if (queue) shadow_kernel<I16><<<sq_blocks, 128, 0, ctx->stream>>>(A);
+#endif
             if (first) prof_mark(ctx, 5);
+            trace_kernel_referee<I16, false><<<ctx->sm_count * 8, 64, 0, ctx->stream>>>(A);
+            if (first) prof_mark(ctx, 6);
         }
     }
     {
         const size_t n = (size_t)ctx->width * ctx->height;
         fold_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->accum, ctx->accfix, n);
     }
-    prof_mark(ctx, 6);
+    prof_mark(ctx, 7);
     MRTX_CUDA(cudaGetLastError());
     return MRTX_OK;
 }

@@ -77,6 +77,8 @@ struct RenderArgs {
     // shadow queue of the production path: rays pushed by trace_kernel_fast (work_counter[5] of them), their radiance and
     // (pixel | sample bit << 27), consumed by shadow_kernel (cursor work_counter[6]); accfix: see accfix_add()
     struct RayRec* sq_rays; uint4* sq_aux; unsigned sq_cap; int sq_level;
+    // hit queue (shadow_queue = 2): primary hits pushed by trace_kernel_fast (work_counter[7] of them), shaded by shade_kernel
+    struct HitQRec* hq;
     unsigned long long* accfix;
     double* beam_s; unsigned char* beam_l;   // beam pre-pass, by position in the pixel list (null: no pre-pass)
     int beam_drop;
@@ -95,6 +97,11 @@ __device__ __forceinline__ void store_ray_rec(RayRec* dst, const Ray64& R, const
     const unsigned cell = alive ? ((unsigned)st.J << 16) | (unsigned)st.I : 0u;
     q[3] = make_double2(alive ? st.s_in : 0.0, __hiloint2double((int)cell, __float_as_int(smax)));
 }
+// record of the hit queue: what fast_test() found (FastHit) + pixel | sample bit << 27.  The primary ray itself is not
+// stored: it is a function of (pixel, sample) alone and shade_kernel evaluates it again, bit for bit.
+struct HitQRec { double s; float fc, fr; int r0, c0; unsigned pix_k, pad; float d00, d01, d10, d11; };   // 48 B
+static_assert(sizeof(HitQRec) == 48, "record layout");
+
 __device__ __forceinline__ void load_ray_rec(const RayRec* src, Ray64& R) {
     const double2* q = (const double2*)src;
     const double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
@@ -348,7 +355,10 @@ __device__ __forceinline__ void primary_ray_fast(const RenderArgs& A, int x, int
 // bilinear, columns wrap, rows clamp).  d = unit direction from the eye, scene space.
 __device__ __forceinline__ bool sees_background(const RenderArgs& A) { return A.env.data != nullptr || A.sp.sun_disk_radius > 0.0; }
 
-__device__ float3 miss_radiance(const RenderArgs& A, double dx, double dy, double dz) {
+#ifndef MRTX_MISS_ATTR
+#define MRTX_MISS_ATTR __noinline__     // rare in the walk kernels (rays that graze past the limb), 6 KB of code when inlined
+#endif
+__device__ MRTX_MISS_ATTR float3 miss_radiance(const RenderArgs& A, double dx, double dy, double dz) {
     const SceneParams& sp = A.sp;
     if (sp.sun_disk_radius > 0.0) {
         const double ox = A.cam.eye[0] - sp.sun_disk_pos[0], oy = A.cam.eye[1] - sp.sun_disk_pos[1], oz = A.cam.eye[2] - sp.sun_disk_pos[2];

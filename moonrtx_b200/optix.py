@@ -476,6 +476,7 @@ class B200OptiX:
             _lib.check(self._lib.mrtx_kernel_times(self._ctx, out, 1 if reset else 0))
         names = ("cull_kernel", "beam_kernel", "trace_kernel_fast", "shadow_kernel", "trace_kernel_referee", "fold_kernel")
         d = {k: float(out[i]) for i, k in enumerate(names)}
+        d["shade_kernel"] = float(out[7])
         d["launches"] = int(out[6])
         return d
 

@@ -363,6 +363,41 @@ def test_wavefront_pipeline_equals_filtered_kernel(spp):
         assert np.allclose(ha, hb, rtol=1e-12, atol=1e-12)
 
 
+@pytest.mark.parametrize("spp,phase,shadows", [(1, 88.0, 1), (16, 90.0, 1), (24, 75.0, 1), (40, 60.0, 1), (6, 90.0, 0)])
+def test_hit_queue_and_shade_kernel_equal_in_kernel_shading(spp, phase, shadows):
+    """The production cut of kernel 2 (shadow_queue = 2: trace_kernel_fast stops at the primary hit, which goes through the
+    hit queue to shade_kernel; that pushes the shadow ray) against shading inside trace_kernel_fast (shadow_queue = 1): the
+    same rays, the same records, sums in fixed point either way - the frames are equal bit for bit.  Sample counts that
+    are no power of two leave empty slots in the hit queue (24 = 16 + 8 lanes of a second round; 40 = 32 + 8)."""
+    elev, _ = synth_elevation(2880, 1440, seed=12)
+    outs = []
+    for sq in (1, 2):
+        rt = make_gpu(elev, 320, 240, debug_hits=(spp == 1), light_pos=sun_at_phase(phase))
+        rt.set_uint("shadow_queue", sq); rt.set_uint("shadows", shadows)
+        if spp > 1:
+            rt.set_param(max_accumulation_frames=spp, min_accumulation_step=spp)
+        rt.counters(reset=True); rt.defer_stats(reset=True)
+        img = rt.render_cycle().copy()
+        outs.append((img, rt.get_accum_buffer().copy(), rt.counters(), rt.defer_stats(), rt.get_hit_buffer().copy(),
+                     rt.get_hit_records_f64().copy() if spp == 1 else None))
+        rt.close()
+    (ia, aa, ca, da, hia, ha), (ib, ab, cb, db, hib, hb) = outs
+    assert ca == cb, (ca, cb)
+    assert da == db
+    assert ca["primary_hits"] > 10000 and (ca["shadow_rays"] > 5000 or not shadows)
+    if shadows:
+        assert np.array_equal(aa, ab)
+    else:
+        # (no shadow ray: shade_kernel adds the radiance in fixed point, the in-kernel form in float32 lane order)
+        assert np.array_equal(aa[..., 3], ab[..., 3])
+        assert np.allclose(aa[..., :3], ab[..., :3], rtol=1e-5, atol=1e-6)
+    assert np.array_equal(hia, hib)
+    d = np.abs(ia[..., :3].astype(np.int32) - ib[..., :3].astype(np.int32))
+    assert int(d.max()) <= (0 if shadows else 1)
+    if spp == 1:
+        assert np.array_equal(ha, hb)
+
+
 @pytest.mark.parametrize("spp,phase", [(1, 88.0), (16, 90.0), (40, 60.0)])
 def test_shadow_queue_ceiling_and_beam_change_no_decision(spp, phase):
     """The production form of kernel 2 - shadow rays streamed through the queue kernel with lane refill, the ceiling test

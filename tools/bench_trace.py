@@ -55,7 +55,9 @@ def time_frame(rt, spp, reps=3):
     lib, ctx = dev.lib, dev.ctx
     _lib.check(lib.mrtx_set_uint(ctx, b"jitter", 1 if spp > 1 else 0, 0))
     ts = []
+    _lib.check(lib.mrtx_set_uint(ctx, b"profile", 1, 0))
     for i in range(reps + 1):
+        rt.kernel_times(reset=True)
         rt.counters(reset=True)
         rt.defer_stats(reset=True)
         dev.synchronize()
@@ -65,9 +67,12 @@ def time_frame(rt, spp, reps=3):
         if i:
             ts.append(ms)
     c = rt.counters()
+    kt = rt.kernel_times()
+    _lib.check(lib.mrtx_set_uint(ctx, b"profile", 0, 0))
     rays = c["primary_rays"] + c["shadow_rays"]
     ms = float(np.median(ts))
-    return {"spp": spp, "ms": round(ms, 2), "defer": rt.defer_stats(), "Mrays_s": round(rays / ms / 1e3, 1), **c,
+    n = max(1, kt.pop("launches"))
+    return {"spp": spp, "ms": round(ms, 2), "kernel_ms": {k.replace("_kernel", "").replace("trace_", ""): round(v / n, 2) for k, v in kt.items()}, "defer": rt.defer_stats(), "Mrays_s": round(rays / ms / 1e3, 1), **c,
             "nodes_per_inray": round(c["node_visits"] / max(1, c["primary_in_sphere"] + c["shadow_rays"]), 1)}
 
 if __name__ == "__main__":

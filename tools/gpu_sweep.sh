@@ -23,5 +23,5 @@ for f in sorted(glob.glob(f"gpurun_out/{sys.argv[1]}_*.log")):
             continue
         d = json.loads(line)
         if "compare" in d: print("   cmp", d["compare"], "max", d["img_max"], "px", d["pixels_differ"], "gt2", d["pixels_differ_gt2"], "accmax", round(d["accum_max_abs"], 4), d["accum_w_equal"])
-        elif "ms" in d: print(f'{str(d["kernel"]):34s} ms {d["ms"]:7.2f}  nodes/ray {d["nodes_per_inray"]:5.1f}  tests {d.get("patch_tests")}  defer {d["defer"]["deferred_samples"]}  hits {d["primary_hits"]} occl {d["shadow_occluded"]}')
+        elif "ms" in d: print(f'{str(d["kernel"]):34s} ms {d["ms"]:7.2f}  nodes/ray {d["nodes_per_inray"]:5.1f}  tests {d.get("patch_tests")}  defer {d["defer"]["deferred_samples"]}  {d.get("kernel_ms")}  hits {d["primary_hits"]} occl {d["shadow_occluded"]}')
 PY
