@@ -379,6 +379,14 @@ class Dist:
         self.dist.broadcast_object_list(uid, src=0)
         rt.comm_init(self.rank, self.world, uid[0])
 
+    def p2p_connect(self, rt):
+        """frame delivery through peer memory (copy engines over NVLink): every rank's mailbox handle to every rank"""
+        if self.world == 1:
+            return
+        handles = [None] * self.world
+        self.dist.all_gather_object(handles, rt.p2p_open(self.rank, self.world))
+        rt.p2p_connect(handles)
+
     def close(self):
         if self.world > 1:
             self.dist.destroy_process_group()
@@ -475,6 +483,8 @@ def run_frames(args):
     dev = rt._dev
     lib, ctx = dev.lib, dev.ctx
     D.comm_init(rt)
+    if args.delivery == "p2p":
+        D.p2p_connect(rt)
     n_warm, n_timed = args.warmup * FRAMES_PER_STEP, args.steps * FRAMES_PER_STEP
     frames = list(range(n_warm + n_timed))
     mine_warm = [f for f in frames[:n_warm] if f % world == rank]
@@ -572,6 +582,8 @@ def run_frames(args):
                "ms_per_step": round(dt * 1e3 / args.steps, 2), "frames_per_s": round(n_timed / dt, 3),
                "frames_delivered_in_order_to_rank0": len(sums) if rank == 0 else None,
                "frame_checksum": (sum(sums) & 0xffffffff) if rank == 0 else None,
+               "delivery": None if world == 1 else ("peer-memory mailboxes: copy-engine copies over NVLink + stream memory operations (mrtx_p2p_*)"
+                                                    if args.delivery == "p2p" else "ncclSend / ncclRecv"),
                "api": "video.render_timelapse_delivered: B200OptiX.submit_frame(dst=0) / recv_frame / wait_frame, two frames in flight per rank"}
 
     # ---- oracle parity on the benchmarked frame + CPU baseline (rank 0, N = 1 only) -----------------------------------
@@ -801,6 +813,8 @@ def main():
     ap.add_argument("--img-h", type=int, default=IMG_H)
     ap.add_argument("--color-w", type=int, default=COLOR_W)
     ap.add_argument("--color-h", type=int, default=COLOR_H)
+    ap.add_argument("--delivery", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1, frames mode: frames reach rank 0 through peer-memory mailboxes (copy engines) or ncclSend / ncclRecv")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-downscale", action="store_true")

@@ -181,6 +181,17 @@ int  mrtx_frame_wait(mrtx_ctx* ctx, int ticket);
 int  mrtx_frame_submit_to(mrtx_ctx* ctx, const uint8_t* overlay_rgba_pinned, unsigned nsamples, int dst_rank, int* ticket);
 int  mrtx_frame_recv(mrtx_ctx* ctx, int src_rank, uint8_t* out_rgba_pinned, int* ticket);
 int  mrtx_frame_recv_wait(mrtx_ctx* ctx, int ticket);
+/* The same delivery through peer memory instead of NCCL kernels.  The trace kernels are persistent and own every
+ * register of every SM, so an ncclSend / ncclRecv kernel only ever starts at one of their boundaries - on BOTH GPUs at
+ * once; at 8 GPUs the consumer cannot take 7 frames per frame time that way.  mrtx_p2p_open allocates this rank's
+ * mailbox in its HBM (two frame slots of slot_bytes and two sequence words per sending rank) and returns its CUDA IPC
+ * handle as 64 opaque bytes; the host exchanges the handles of all ranks (as it does the NCCL unique id) and gives the
+ * nranks x 64 bytes, in rank order, to mrtx_p2p_connect.  From then on mrtx_frame_submit_to copies the frame into the
+ * consumer's slot with the copy engine (NVLink), followed by the 4-byte sequence number; mrtx_frame_recv makes the
+ * consumer's stream wait for that word (stream memory operation), copy the slot to the pinned buffer and hand the slot
+ * back.  No SM takes part.  Same tickets, same ordering rules as above.  Works with or without mrtx_comm_init.       */
+int  mrtx_p2p_open(mrtx_ctx* ctx, int nranks, int rank, size_t slot_bytes, uint8_t handle_out[64]);
+int  mrtx_p2p_connect(mrtx_ctx* ctx, const uint8_t* handles);
 /* rt._get_hit_at(x, y) -> (hx, hy, hz, hd), moon_renderer.py:1138; hd <= 0 = miss.     */
 int  mrtx_hit_at(mrtx_ctx* ctx, int x, int y, float out4[4]);
 /* device views of the frame buffers (for collectives and zero-copy consumers)        */

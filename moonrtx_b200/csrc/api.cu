@@ -97,6 +97,7 @@ int mrtx_destroy(mrtx_ctx* ctx) {
     pipe_release(ctx);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->comm_stream) { cudaStreamSynchronize(ctx->comm_stream); cudaStreamDestroy(ctx->comm_stream); }
+    p2p_release(ctx);
     for (int q = 0; q < 2; ++q) { cudaFree(ctx->recv_buf[q]); if (ctx->recv_ev[q]) cudaEventDestroy(ctx->recv_ev[q]); }
     free_frame(ctx);
     cudaFree(ctx->d_max_bits);
@@ -711,7 +712,7 @@ int mrtx_frame_submit(mrtx_ctx* ctx, const uint8_t* overlay_rgba_pinned, unsigne
 
 int mrtx_frame_submit_to(mrtx_ctx* ctx, const uint8_t* overlay_rgba_pinned, unsigned nsamples, int dst_rank, int* ticket) {
     MRTX_CTX(ctx);
-    if (!ctx->nccl_comm) { mrtx_set_error("mrtx_comm_init has not been called"); return MRTX_ERR_STATE; }
+    if (!ctx->nccl_comm && !ctx->p2p_on) { mrtx_set_error("neither mrtx_comm_init nor mrtx_p2p_connect has been called"); return MRTX_ERR_STATE; }
     MRTX_REQUIRE(dst_rank >= 0 && dst_rank < ctx->nranks && dst_rank != ctx->rank, "bad destination rank %d", dst_rank);
     return frame_submit(ctx, overlay_rgba_pinned, nsamples, nullptr, dst_rank, ticket);
 }
@@ -724,18 +725,19 @@ static int comm_stream_ensure(mrtx_ctx* ctx) {
 int mrtx_frame_recv(mrtx_ctx* ctx, int src_rank, uint8_t* out_rgba_pinned, int* ticket) {
     MRTX_CTX(ctx);
     MRTX_REQUIRE(out_rgba_pinned && ticket, "null argument");
-    if (!ctx->nccl_comm) { mrtx_set_error("mrtx_comm_init has not been called"); return MRTX_ERR_STATE; }
+    if (!ctx->nccl_comm && !ctx->p2p_on) { mrtx_set_error("neither mrtx_comm_init nor mrtx_p2p_connect has been called"); return MRTX_ERR_STATE; }
     if (!ctx->accum) { mrtx_set_error("mrtx_resize has not been called"); return MRTX_ERR_STATE; }
     MRTX_REQUIRE(src_rank >= 0 && src_rank < ctx->nranks && src_rank != ctx->rank, "bad source rank %d", src_rank);
     int rc = comm_stream_ensure(ctx);
     if (rc) return rc;
     const size_t bytes = (size_t)ctx->width * ctx->height * sizeof(uchar4);
-    if (ctx->recv_bytes != bytes) {
+    for (int q = 0; q < 2; ++q)
+        if (!ctx->recv_ev[q]) MRTX_CUDA(cudaEventCreateWithFlags(&ctx->recv_ev[q], cudaEventDisableTiming));
+    if (!ctx->p2p_on && ctx->recv_bytes != bytes) {
         MRTX_CUDA(cudaStreamSynchronize(ctx->comm_stream));
         for (int q = 0; q < 2; ++q) {
             cudaFree(ctx->recv_buf[q]); ctx->recv_buf[q] = nullptr;
             MRTX_CUDA(cudaMalloc(&ctx->recv_buf[q], bytes));
-            if (!ctx->recv_ev[q]) MRTX_CUDA(cudaEventCreateWithFlags(&ctx->recv_ev[q], cudaEventDisableTiming));
             ctx->recv_busy[q] = 0;
         }
         ctx->recv_bytes = bytes; ctx->recv_slot = 0;
@@ -745,9 +747,15 @@ int mrtx_frame_recv(mrtx_ctx* ctx, int src_rank, uint8_t* out_rgba_pinned, int* 
         mrtx_set_error("two received frames are pending: mrtx_frame_recv_wait(%d) must be called first", q);
         return MRTX_ERR_STATE;
     }
-    rc = comm_recv_bytes(ctx, ctx->recv_buf[q], bytes, src_rank, ctx->comm_stream);
-    if (rc) return rc;
-    MRTX_CUDA(cudaMemcpyAsync(out_rgba_pinned, ctx->recv_buf[q], bytes, cudaMemcpyDeviceToHost, ctx->comm_stream));
+    if (ctx->p2p_on) {
+        // the sender's copy engine has put (or will put) the frame into this rank's mailbox: no staging copy, no kernel
+        rc = p2p_recv_frame(ctx, out_rgba_pinned, bytes, src_rank, ctx->comm_stream);
+        if (rc) return rc;
+    } else {
+        rc = comm_recv_bytes(ctx, ctx->recv_buf[q], bytes, src_rank, ctx->comm_stream);
+        if (rc) return rc;
+        MRTX_CUDA(cudaMemcpyAsync(out_rgba_pinned, ctx->recv_buf[q], bytes, cudaMemcpyDeviceToHost, ctx->comm_stream));
+    }
     MRTX_CUDA(cudaEventRecord(ctx->recv_ev[q], ctx->comm_stream));
     ctx->recv_busy[q] = 1; ctx->recv_slot = q ^ 1;
     *ticket = q;
@@ -799,7 +807,8 @@ static int frame_submit(mrtx_ctx* ctx, const uint8_t* overlay_rgba_pinned, unsig
         rc = comm_stream_ensure(ctx);
         if (rc) return rc;
         MRTX_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->pipe_ev_resolve[k], 0));
-        rc = comm_send_bytes(ctx, ctx->pipe_rgba8[k], bytes, dst_rank, ctx->comm_stream);
+        rc = ctx->p2p_on ? p2p_send_frame(ctx, ctx->pipe_rgba8[k], bytes, dst_rank, ctx->comm_stream)
+                         : comm_send_bytes(ctx, ctx->pipe_rgba8[k], bytes, dst_rank, ctx->comm_stream);
         if (rc) return rc;
         MRTX_CUDA(cudaEventRecord(ctx->pipe_ev_d2h[k], ctx->comm_stream));
     }

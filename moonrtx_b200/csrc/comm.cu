@@ -267,3 +267,119 @@ int mrtx_allgather_rows(mrtx_ctx* ctx, int tile_rows) {
 }
 
 }  // extern "C"
+
+
+// ---- frame delivery through peer memory (mailboxes) -----------------------------------------------------------------------
+// See mrtx_ctx::p2p_box.  Layout of a mailbox: u32 ready[MAX_RANKS][2] at 0, u32 free[MAX_RANKS][2] at 1024, frame slots
+// [src][2] from 4096.  ready[s][q] = k: rank s has written its (2 k - 2 + q)-th frame for this rank into slot [s][q];
+// free[d][q] = k (in the SENDER's mailbox): rank d has copied the k-th frame it received through its slot [me][q] out.
+namespace {
+
+constexpr size_t P2P_READY_OFF = 0, P2P_FREE_OFF = 1024, P2P_SLOTS_OFF = 4096;
+constexpr unsigned P2P_SEQ_N = 1u << 16;                    // frames per (sender, slot): 131 072 frames per pair of ranks
+typedef int (*wait_value32_fn)(cudaStream_t, unsigned long long, unsigned, unsigned);
+
+inline unsigned* box_word(void* box, size_t off, int r, int q) { return (unsigned*)((char*)box + off) + 2 * r + q; }
+inline char* box_slot(void* box, size_t stride, int src, int q) { return (char*)box + P2P_SLOTS_OFF + (size_t)(2 * src + q) * stride; }
+
+int p2p_wait(mrtx_ctx* ctx, cudaStream_t st, unsigned* word, unsigned value) {
+    const int rc = ((wait_value32_fn)ctx->p2p_wait_fn)(st, (unsigned long long)(uintptr_t)word, value, ctx->p2p_wait_flags);
+    if (rc != 0) { mrtx_set_error("cuStreamWaitValue32 failed (CUresult %d)", rc); return MRTX_ERR_CUDA; }
+    return MRTX_OK;
+}
+
+}  // namespace
+
+void p2p_release(mrtx_ctx* ctx) {
+    for (int r = 0; r < MRTX_P2P_MAX_RANKS; ++r) {
+        if (ctx->p2p_peer[r] && r != ctx->rank) cudaIpcCloseMemHandle(ctx->p2p_peer[r]);
+        ctx->p2p_peer[r] = nullptr;
+    }
+    cudaFree(ctx->p2p_box); cudaFree(ctx->p2p_seq);
+    ctx->p2p_box = nullptr; ctx->p2p_seq = nullptr; ctx->p2p_on = 0;
+}
+
+int mrtx_p2p_open(mrtx_ctx* ctx, int nranks, int rank, size_t slot_bytes, uint8_t handle_out[64]) {
+    MRTX_CTX(ctx);
+    MRTX_REQUIRE(handle_out && slot_bytes > 0, "null argument");
+    MRTX_REQUIRE(nranks >= 1 && nranks <= MRTX_P2P_MAX_RANKS && rank >= 0 && rank < nranks, "bad rank %d of %d", rank, nranks);
+    if (ctx->nccl_comm) MRTX_REQUIRE(nranks == ctx->nranks && rank == ctx->rank, "rank %d of %d differs from the communicator's %d of %d", rank, nranks, ctx->rank, ctx->nranks);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle crosses the ABI as 64 opaque bytes");
+    MRTX_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->comm_stream) MRTX_CUDA(cudaStreamSynchronize(ctx->comm_stream));
+    p2p_release(ctx);
+    // the stream wait on a memory word: a driver entry point, reached through the runtime (no link against libcuda)
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    MRTX_CUDA(cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &qr));
+    if (!fn || qr != cudaDriverEntryPointSuccess) { mrtx_set_error("cuStreamWaitValue32 is not available in this driver"); return MRTX_ERR_CUDA; }
+    ctx->p2p_wait_fn = fn;
+    int dev = 0, can_flush = 0;
+    MRTX_CUDA(cudaGetDevice(&dev));
+    (void)cudaDeviceGetAttribute(&can_flush, cudaDevAttrCanFlushRemoteWrites, dev);
+    (void)cudaGetLastError();
+    ctx->p2p_wait_flags = 0x0u /* GEQ */ | (can_flush ? (1u << 30) /* FLUSH */ : 0u);
+    ctx->p2p_stride = (slot_bytes + 255) & ~(size_t)255;
+    ctx->p2p_slot_bytes = slot_bytes;
+    const size_t total = P2P_SLOTS_OFF + (size_t)2 * nranks * ctx->p2p_stride;
+    MRTX_CUDA(cudaMalloc(&ctx->p2p_box, total));
+    MRTX_CUDA(cudaMemset(ctx->p2p_box, 0, P2P_SLOTS_OFF));
+    MRTX_CUDA(cudaMalloc(&ctx->p2p_seq, P2P_SEQ_N * sizeof(unsigned)));
+    {
+        unsigned* h = (unsigned*)malloc(P2P_SEQ_N * sizeof(unsigned));
+        if (!h) { mrtx_set_error("out of host memory"); return MRTX_ERR_INVALID; }
+        for (unsigned i = 0; i < P2P_SEQ_N; ++i) h[i] = i;
+        const cudaError_t e = cudaMemcpy(ctx->p2p_seq, h, P2P_SEQ_N * sizeof(unsigned), cudaMemcpyHostToDevice);
+        free(h);
+        MRTX_CUDA(e);
+    }
+    cudaIpcMemHandle_t h;
+    MRTX_CUDA(cudaIpcGetMemHandle(&h, ctx->p2p_box));
+    memcpy(handle_out, &h, 64);
+    ctx->nranks = nranks; ctx->rank = rank;
+    for (int r = 0; r < MRTX_P2P_MAX_RANKS; ++r) { ctx->p2p_sent[r] = 0; ctx->p2p_rcvd[r] = 0; }
+    return MRTX_OK;
+}
+
+int mrtx_p2p_connect(mrtx_ctx* ctx, const uint8_t* handles) {
+    MRTX_CTX(ctx);
+    MRTX_REQUIRE(handles, "null argument");
+    if (!ctx->p2p_box) { mrtx_set_error("mrtx_p2p_open has not been called"); return MRTX_ERR_STATE; }
+    for (int r = 0; r < ctx->nranks; ++r) {
+        if (r == ctx->rank) { ctx->p2p_peer[r] = ctx->p2p_box; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)64 * r, 64);
+        MRTX_CUDA(cudaIpcOpenMemHandle(&ctx->p2p_peer[r], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    ctx->p2p_on = 1;
+    return MRTX_OK;
+}
+
+// queue on `st`: wait until the consumer has emptied the slot, copy the frame into it, publish its sequence number
+int p2p_send_frame(mrtx_ctx* ctx, const void* frame_dev, size_t bytes, int dst, cudaStream_t st) {
+    MRTX_REQUIRE(ctx->p2p_on && bytes <= ctx->p2p_slot_bytes, "frame of %zu bytes does not fit the %zu-byte mailbox slots", bytes, ctx->p2p_slot_bytes);
+    const unsigned j = ctx->p2p_sent[dst], seq = j / 2 + 1;
+    const int q = (int)(j & 1u);
+    MRTX_REQUIRE(seq < P2P_SEQ_N, "sequence numbers exhausted");
+    int rc = MRTX_OK;
+    if (seq > 1 && (rc = p2p_wait(ctx, st, box_word(ctx->p2p_box, P2P_FREE_OFF, dst, q), seq - 1))) return rc;
+    void* peer = ctx->p2p_peer[dst];
+    MRTX_CUDA(cudaMemcpyAsync(box_slot(peer, ctx->p2p_stride, ctx->rank, q), frame_dev, bytes, cudaMemcpyDeviceToDevice, st));
+    MRTX_CUDA(cudaMemcpyAsync(box_word(peer, P2P_READY_OFF, ctx->rank, q), ctx->p2p_seq + seq, sizeof(unsigned), cudaMemcpyDeviceToDevice, st));
+    ctx->p2p_sent[dst] = j + 1;
+    return MRTX_OK;
+}
+
+// queue on `st`: wait for the sender's sequence number, copy the slot to pinned host memory, hand the slot back
+int p2p_recv_frame(mrtx_ctx* ctx, void* out_pinned, size_t bytes, int src, cudaStream_t st) {
+    MRTX_REQUIRE(ctx->p2p_on && bytes <= ctx->p2p_slot_bytes, "frame of %zu bytes does not fit the %zu-byte mailbox slots", bytes, ctx->p2p_slot_bytes);
+    const unsigned j = ctx->p2p_rcvd[src], seq = j / 2 + 1;
+    const int q = (int)(j & 1u);
+    MRTX_REQUIRE(seq < P2P_SEQ_N, "sequence numbers exhausted");
+    const int rc = p2p_wait(ctx, st, box_word(ctx->p2p_box, P2P_READY_OFF, src, q), seq);
+    if (rc) return rc;
+    MRTX_CUDA(cudaMemcpyAsync(out_pinned, box_slot(ctx->p2p_box, ctx->p2p_stride, src, q), bytes, cudaMemcpyDeviceToHost, st));
+    MRTX_CUDA(cudaMemcpyAsync(box_word(ctx->p2p_peer[src], P2P_FREE_OFF, ctx->rank, q), ctx->p2p_seq + seq, sizeof(unsigned), cudaMemcpyDeviceToDevice, st));
+    ctx->p2p_rcvd[src] = j + 1;
+    return MRTX_OK;
+}

@@ -41,6 +41,7 @@ void mrtx_set_error(const char* fmt, ...);
 
 // ---- scene state ------------------------------------------------------------------
 #define MRTX_PROF_MAX 256
+#define MRTX_P2P_MAX_RANKS 64
 #define MRTX_PROF_EVENTS 8       // before cull, after cull, beam, trace_kernel_fast, shade_kernel, shadow_kernel, referee, fold
 #define MRTX_MAX_LEVELS 20
 #define MRTX_DIL_MIN_LEVEL 2     // lowest level that has a dilated copy (beam pre-pass)
@@ -156,6 +157,19 @@ struct mrtx_ctx {
     cudaStream_t comm_stream;
     uchar4* recv_buf[2]; cudaEvent_t recv_ev[2]; int recv_slot, recv_busy[2]; size_t recv_bytes;
 
+    // the same delivery through peer memory (mrtx_p2p_open / mrtx_p2p_connect): every rank owns a MAILBOX in its HBM -
+    // per sending rank two frame slots and two sequence words - which its peers map with CUDA IPC.  A frame crosses NVLink
+    // as a copy-engine copy into the consumer's slot followed by a 4-byte copy of the sequence number; the consumer's
+    // stream waits for that word (stream memory operation, no kernel) and copies the slot to pinned host memory, then
+    // hands the slot back by writing the sender's "free" word.  No SM is involved on either side: the trace kernels are
+    // persistent and own every register of every SM, so an NCCL send / recv kernel only ever starts at their boundaries.
+    void* p2p_box; size_t p2p_slot_bytes, p2p_stride; int p2p_on;
+    void* p2p_peer[MRTX_P2P_MAX_RANKS];
+    unsigned* p2p_seq;          // p2p_seq[i] = i: source of the 4-byte sequence copies
+    unsigned p2p_sent[MRTX_P2P_MAX_RANKS], p2p_rcvd[MRTX_P2P_MAX_RANKS];
+    void* p2p_wait_fn;          // cuStreamWaitValue32 (driver entry point), p2p_wait_flags: GEQ (| FLUSH where supported)
+    unsigned p2p_wait_flags;
+
     // per-kernel stopwatch of the trace path (mrtx_set_uint("profile", 1), mrtx_kernel_times): events at the kernel
     // boundaries of every mrtx_render, read and summed on request
     int prof_on, prof_n;
@@ -184,6 +198,9 @@ int launch_trace(mrtx_ctx* ctx, int x0, int y0, int x1, int y1, unsigned s0, uns
 int launch_resolve(mrtx_ctx* ctx);
 int prof_mark(mrtx_ctx* ctx, int which);
 int comm_send_bytes(mrtx_ctx* ctx, const void* buf_dev, size_t bytes, int peer, cudaStream_t st);
+int p2p_send_frame(mrtx_ctx* ctx, const void* frame_dev, size_t bytes, int dst, cudaStream_t st);    // mailbox transport (comm.cu)
+int p2p_recv_frame(mrtx_ctx* ctx, void* out_pinned, size_t bytes, int src, cudaStream_t st);
+void p2p_release(mrtx_ctx* ctx);
 int comm_recv_bytes(mrtx_ctx* ctx, void* buf_dev, size_t bytes, int peer, cudaStream_t st);     // record event `which` of the current launch (no-op unless profiling)
 int launch_resolve_to(mrtx_ctx* ctx, const uchar4* overlay_dev, uchar4* out_dev);
 void free_heightfield(mrtx_ctx* ctx);

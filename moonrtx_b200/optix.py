@@ -18,7 +18,7 @@ Headless users can skip the thread and call `render_cycle()` synchronously.
 
 import ctypes as C
 import threading
-from typing import Callable, Optional
+from typing import Callable, Optional, Sequence
 
 import numpy as np
 
@@ -405,6 +405,25 @@ class B200OptiX:
         with self._padlock:
             _lib.check(self._lib.mrtx_comm_init(self._ctx, _lib.nccl_library_path().encode(), int(world), int(rank), buf))
         self._rank, self._world = int(rank), int(world)
+
+    def p2p_open(self, rank: int, world: int) -> bytes:
+        """Peer-memory frame delivery (mrtx_p2p_open): allocate this rank's mailbox for frames of the current size and
+        return its CUDA IPC handle (64 bytes) for the host to exchange between the ranks."""
+        buf = (C.c_uint8 * 64)()
+        with self._padlock:
+            _lib.check(self._lib.mrtx_p2p_open(self._ctx, int(world), int(rank), self._width * self._height * 4, buf))
+        self._rank, self._world = int(rank), int(world)
+        return bytes(buf)
+
+    def p2p_connect(self, handles: Sequence[bytes]) -> None:
+        """Map every rank's mailbox (handles in rank order, as returned by p2p_open on each): from now on
+        submit_frame(dst=...) / recv_frame move frames with the copy engines over NVLink, no kernel on either side."""
+        blob = b"".join(handles)
+        if len(blob) != 64 * len(handles):
+            raise ValueError("every handle is 64 bytes")
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        with self._padlock:
+            _lib.check(self._lib.mrtx_p2p_connect(self._ctx, buf))
 
     def render_cycle(self, read_back: bool = True, shard: Optional[str] = None,
                      tile_rows: int = 64, tile: int = 64) -> Optional[np.ndarray]:

@@ -70,17 +70,25 @@ def main():
         ov = np.zeros((H, W, 4), np.uint8)
         ov[4:12, 4:4 + 8 * (i + 1)] = (255, 255, 255, 200)
         return ov
-    got = []
-    n = render_timelapse_delivered(rt, states, rank, world, consumer=0, on_frame=lambda i, img: got.append((i, img.copy())),
-                                   overlay_for=overlay)
-    if rank == 0:
-        assert n == 7 and [i for i, _ in got] == list(range(7)), "frames must arrive in order"
-        solo = render_timelapse(rt, states, 0, 1, overlay_for=overlay)
-        for i, img in got:
-            assert np.array_equal(img, solo[i]), f"delivered frame {i}"
-            assert img[8, 6, 0] > 150 and (i == 6 or np.array_equal(img[8, 4 + 8 * (i + 1) + 2], solo[i][8, 4 + 8 * (i + 1) + 2]))
-    else:
-        assert n == 0
+    solo = render_timelapse(rt, states, 0, 1, overlay_for=overlay) if rank == 0 else None
+    for transport in ("nccl", "p2p"):
+        if transport == "p2p":
+            # peer-memory mailboxes (CUDA IPC + copy engines + stream memory operations): no kernel on either side
+            handles = [None] * world
+            dist.all_gather_object(handles, rt.p2p_open(rank, world))
+            rt.p2p_connect(handles)
+        for rep in range(2):                      # (twice: slots and sequence numbers carry on from one export to the next)
+            got = []
+            n = render_timelapse_delivered(rt, states, rank, world, consumer=0, on_frame=lambda i, img: got.append((i, img.copy())),
+                                           overlay_for=overlay)
+            if rank == 0:
+                assert n == 7 and [i for i, _ in got] == list(range(7)), f"{transport}: frames must arrive in order"
+                for i, img in got:
+                    assert np.array_equal(img, solo[i]), f"{transport}: delivered frame {i}"
+                    assert img[8, 6, 0] > 150 and (i == 6 or np.array_equal(img[8, 4 + 8 * (i + 1) + 2], solo[i][8, 4 + 8 * (i + 1) + 2]))
+            else:
+                assert n == 0
+            dist.barrier()
     rt.close()
     dist.barrier()
     if rank == 0:
