@@ -111,6 +111,13 @@ int  mrtx_set_displacement_i16_dev(mrtx_ctx* ctx, const int16_t* map_dev, int W,
  * moon_renderer.py:614, renderer_video.py:137.  slot 0 = moon_color (bilinear),
  * slot 1 = frame_overlay (nearest, must match the frame size); NULL clears.           */
 int  mrtx_set_texture_rgba8(mrtx_ctx* ctx, int slot, const uint8_t* rgba, int W, int H);
+/* rt.set_graph / update_graph / delete_geometry (renderer_labels.py:263-305, 324-325, renderer_pins.py:18-55, 131): the
+ * overlay tubes of the grid, its number labels, the feature labels and the pins.  ALL visible segments of all graphs in one
+ * list, scene space: n x 12 floats = (ax, ay, az, r, bx, by, bz, 0, red, green, blue, 0).  A segment is a capsule of radius
+ * r; it is flat-shaded (the colour is the radiance of a camera sample that meets it before the surface), it casts no shadow
+ * and receives none (the reference's material lets shadow rays through, renderer_labels.py:133-139).  n = 0 removes them.
+ * The list is binned to 32 x 32-pixel screen tiles for the camera of every launch.                                        */
+int  mrtx_set_tubes(mrtx_ctx* ctx, const float* segments, int n);
 /* What rays that miss the Moon see.
  * rt.set_background_mode("TextureEnvironment") + rt.set_background(float32[h][w][3] in [0, 1], gamma=g,
  * rt_format="UByte4"), moon_renderer.py:602-609: the star map becomes an 8-bit environment texture of linear radiance

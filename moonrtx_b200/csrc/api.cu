@@ -106,6 +106,7 @@ int mrtx_destroy(mrtx_ctx* ctx) {
     cudaFree(ctx->d_defer_stats);
     cudaFree(ctx->wave_buf);
     cudaFree(ctx->sq_buf); cudaFree(ctx->hq_buf);
+    cudaFree(ctx->tube_seg); cudaFree(ctx->tube_tiles);
     if (ctx->prof_ev) { for (int i = 0; i < MRTX_PROF_MAX * MRTX_PROF_EVENTS; ++i) cudaEventDestroy(ctx->prof_ev[i]); free(ctx->prof_ev); }
     cudaFree(ctx->flush_buf);
     if (ctx->h_rs) cudaFreeHost(ctx->h_rs);
@@ -523,6 +524,22 @@ int mrtx_read_background_rgba8(mrtx_ctx* ctx, uint8_t* out, int* W, int* H) {
         MRTX_CUDA(cudaMemcpyAsync(out, ctx->tex[2].data, (size_t)ctx->tex[2].W * ctx->tex[2].H * 4, cudaMemcpyDeviceToHost, ctx->stream));
         MRTX_CUDA(cudaStreamSynchronize(ctx->stream));
     }
+    return MRTX_OK;
+}
+
+int mrtx_set_tubes(mrtx_ctx* ctx, const float* segments, int n) {
+    MRTX_CTX(ctx);
+    MRTX_REQUIRE(n >= 0 && (n == 0 || segments), "bad segment list");
+    MRTX_CUDA(cudaStreamSynchronize(ctx->stream));             // (a frame in flight may still read the old list)
+    if (ctx->copy_stream) MRTX_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+    if ((unsigned)n > ctx->tube_cap) {
+        cudaFree(ctx->tube_seg); ctx->tube_seg = nullptr; ctx->tube_cap = 0; ctx->n_tubes = 0;
+        const unsigned cap = (unsigned)n + (unsigned)n / 2u + 64u;
+        MRTX_CUDA(cudaMalloc(&ctx->tube_seg, (size_t)cap * 3 * sizeof(float4)));
+        ctx->tube_cap = cap;
+    }
+    if (n) MRTX_CUDA(cudaMemcpy(ctx->tube_seg, segments, (size_t)n * 3 * sizeof(float4), cudaMemcpyHostToDevice));
+    ctx->n_tubes = (unsigned)n;
     return MRTX_OK;
 }
 

@@ -42,6 +42,8 @@ void mrtx_set_error(const char* fmt, ...);
 // ---- scene state ------------------------------------------------------------------
 #define MRTX_PROF_MAX 256
 #define MRTX_P2P_MAX_RANKS 64
+#define MRTX_TUBE_TILE_LOG2 5    // screen tiles of the overlay-tube bins: 32 x 32 pixels ...
+#define MRTX_TUBE_TILE_CAP 62     // ... listing up to this many segments each (more: every segment is tested)
 #define MRTX_PROF_EVENTS 8       // before cull, after cull, beam, trace_kernel_fast, shade_kernel, shadow_kernel, referee, fold
 #define MRTX_MAX_LEVELS 20
 #define MRTX_DIL_MIN_LEVEL 2     // lowest level that has a dilated copy (beam pre-pass)
@@ -144,6 +146,13 @@ struct mrtx_ctx {
     unsigned char* beam_l;      // ... and the level the beam pre-pass stopped at
     // wavefront pipeline scratch (allocated on first use): ray / hit records, radiance slots, shadow queue, deferred items
     void* wave_buf; size_t wave_items;
+
+    // overlay tubes (grid lines, labels, pins: rt.set_graph, renderer_labels.py:263-305, renderer_pins.py:18-55): capsule
+    // segments in scene space, flat-shaded, never occluders of the sun.  tube_seg: 3 float4 per segment (a.xyz, r; b.xyz, -;
+    // colour.rgb, -); tube_tiles: per 32 x 32-pixel screen tile a count and up to MRTX_TUBE_TILE_CAP segment indices,
+    // rebuilt for the camera of every launch (tube_bin_kernel)
+    float4* tube_seg; unsigned n_tubes, tube_cap;
+    unsigned* tube_tiles; int tube_tx, tube_ty;
 
     // pipelined frames (mrtx_frame_submit / mrtx_frame_wait): a copy stream moves frame j's overlay in and frame j-1's
     // RGBA8 out while the main stream traces; overlay and output are double-buffered, one set of events per slot

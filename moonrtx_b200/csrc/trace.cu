@@ -249,7 +249,8 @@ trace_kernel_fast(const __grid_constant__ RenderArgs A) {
                     }
                     if (hit) {
                         Ray64 S;
-                        want = shade_fast(A, R, fh, x, y, pixel, sm, lit, S);
+                        if (tube_tile_count(A, x, y) && tube_nearest(A, x, y, pixel, sm, fh.s, lit)) want = false;   // an overlay tube in front
+                        else want = shade_fast(A, R, fh, x, y, pixel, sm, lit, S);
                         shadowed = want;
                         if (want) R = S;
                     }
@@ -266,8 +267,12 @@ trace_kernel_fast(const __grid_constant__ RenderArgs A) {
                     if (shadowed) { ++rs.shadow; if (occluded) ++rs.occluded; }
                     if (!occluded) { acc.x += lit.x; acc.y += lit.y; acc.z += lit.z; }
                 } else {
-                    write_miss(A, x, y, sm == A.hit_sample);
-                    if (sees_background(A)) { const float3 m = miss_radiance_body(A, R); acc.x += m.x; acc.y += m.y; acc.z += m.z; }
+                    float3 tc;
+                    if (tube_tile_count(A, x, y) && tube_nearest(A, x, y, pixel, sm, 1.0e300, tc)) { acc.x += tc.x; acc.y += tc.y; acc.z += tc.z; }
+                    else {
+                        write_miss(A, x, y, sm == A.hit_sample);
+                        if (sees_background(A)) { const float3 m = miss_radiance_body(A, R); acc.x += m.x; acc.y += m.y; acc.z += m.z; }
+                    }
                 }
             }
             // deferred samples of each pixel -> its leader's mask (bit = sample index in this launch)
@@ -333,7 +338,9 @@ shade_kernel(const __grid_constant__ RenderArgs A) {
             const unsigned sm = A.sample0 + k;
             Ray64 R;
             primary_ray_fast(A, x, y, pixel, sm, R);
-            if (shade_fast(A, R, fh, x, y, pixel, sm, lit, S)) {
+            if (tube_tile_count(A, x, y) && tube_nearest(A, x, y, pixel, sm, fh.s, lit)) {
+                // an overlay tube in front of the surface: its flat colour is the sample (added below)
+            } else if (shade_fast(A, R, fh, x, y, pixel, sm, lit, S)) {
                 ++rs.shadow;
                 push = walk_begin(A.hf, A.sp.radius, S, 0.0, A.sq_level, sw);
             }
@@ -562,6 +569,20 @@ static int launch_fast(mrtx_ctx* ctx, RenderArgs& A, long long npix) {
 template <bool I16>
 static int launch_trace_t(mrtx_ctx* ctx, RenderArgs& A, unsigned s0, unsigned ns) {
     prof_mark(ctx, 0);
+    if (ctx->n_tubes) {
+        const int tx = (ctx->width + (1 << MRTX_TUBE_TILE_LOG2) - 1) >> MRTX_TUBE_TILE_LOG2, ty = (ctx->height + (1 << MRTX_TUBE_TILE_LOG2) - 1) >> MRTX_TUBE_TILE_LOG2;
+        if (tx != ctx->tube_tx || ty != ctx->tube_ty || !ctx->tube_tiles) {
+            MRTX_CUDA(cudaStreamSynchronize(ctx->stream));
+            cudaFree(ctx->tube_tiles); ctx->tube_tiles = nullptr;
+            MRTX_CUDA(cudaMalloc(&ctx->tube_tiles, (size_t)tx * ty * (MRTX_TUBE_TILE_CAP + 2) * sizeof(unsigned)));
+            ctx->tube_tx = tx; ctx->tube_ty = ty;
+            A.tube_tiles = ctx->tube_tiles; A.tube_tx = tx;
+        }
+        const size_t words = (size_t)ctx->tube_tx * ctx->tube_ty * (MRTX_TUBE_TILE_CAP + 2);
+        MRTX_CUDA(cudaMemsetAsync(ctx->tube_tiles, 0, words * sizeof(unsigned), ctx->stream));
+        tube_bin_kernel<<<(ctx->n_tubes + 127) / 128, 128, 0, ctx->stream>>>(ctx->tube_seg, ctx->n_tubes, ctx->tube_tiles, ctx->tube_tx, ctx->tube_ty,
+                                                                          ctx->cam, ctx->width, ctx->height);
+    }
     int rc = launch_cull(ctx, A);
     if (rc) return rc;
     prof_mark(ctx, 1);
@@ -572,7 +593,8 @@ static int launch_trace_t(mrtx_ctx* ctx, RenderArgs& A, unsigned s0, unsigned ns
         beam_kernel<I16><<<blocks, 256, 0, ctx->stream>>>(A);
     }
     prof_mark(ctx, 2);
-    const bool queue = ctx->sp.shadow_queue != 0 && ctx->sp.shadows != 0;
+    // (the hit-queue form also serves a scene without shadow rays: shade_kernel then adds the radiance itself)
+    const bool queue = ctx->sp.shadow_queue >= 2u || (ctx->sp.shadow_queue != 0 && ctx->sp.shadows != 0);
     const size_t SQ_MAX = (size_t)1 << 26;                  // 64 Mi queued rays = 5 GiB; larger launches run in waves of pixels
     int sq_blocks = 0;
     if (queue) {

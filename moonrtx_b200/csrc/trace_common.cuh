@@ -77,6 +77,8 @@ struct RenderArgs {
     // shadow queue of the production path: rays pushed by trace_kernel_fast (work_counter[5] of them), their radiance and
     // (pixel | sample bit << 27), consumed by shadow_kernel (cursor work_counter[6]); accfix: see accfix_add()
     struct RayRec* sq_rays; uint4* sq_aux; unsigned sq_cap; int sq_level;
+    // overlay tubes (mrtx_set_tubes): segments, per-tile lists (see mrtx_ctx::tube_tiles); n_tubes = 0: none
+    const float4* tubes; unsigned n_tubes; const unsigned* tube_tiles; int tube_tx;
     // hit queue (shadow_queue = 2): primary hits pushed by trace_kernel_fast (work_counter[7] of them), shaded by shade_kernel
     struct HitQRec* hq;
     unsigned long long* accfix;
@@ -220,6 +222,120 @@ __device__ __forceinline__ void write_miss(const RenderArgs& A, int x, int y, bo
     if (A.hit64) A.hit64[(size_t)y * A.width + x] = make_double4(-1.0, 0.0, 0.0, 0.0);
 }
 
+// ---- overlay tubes ----------------------------------------------------------------------------------
+// Grid lines, labels and pins are graphs of thin tubes floating 0.5 % above the sphere (moon_grid.py:188, 273), drawn with a
+// flat material that shadow rays pass through (renderer_labels.py:133-139): a camera sample that meets a tube before the
+// terrain takes the tube's colour as its radiance, nothing else changes.  A segment is a capsule (two end points, one
+// radius); the nearest one along the sample's ray is found among the segments binned to the pixel's screen tile.
+__device__ __forceinline__ unsigned tube_tile_count(const RenderArgs& A, int x, int y) {
+    if (!A.n_tubes) return 0u;
+    return __ldg(A.tube_tiles + (size_t)((y >> MRTX_TUBE_TILE_LOG2) * A.tube_tx + (x >> MRTX_TUBE_TILE_LOG2)) * (MRTX_TUBE_TILE_CAP + 2));
+}
+
+// first intersection of the ray o + t d (|d| = 1) with the capsule (a, b, r), or a negative number
+__device__ __forceinline__ double capsule_hit(const double o[3], const double d[3], const float4 sa, const float4 sb) {
+    const double ax = sa.x, ay = sa.y, az = sa.z, r = sa.w;
+    const double bax = (double)sb.x - ax, bay = (double)sb.y - ay, baz = (double)sb.z - az;
+    const double oax = o[0] - ax, oay = o[1] - ay, oaz = o[2] - az;
+    const double baba = bax * bax + bay * bay + baz * baz, bard = bax * d[0] + bay * d[1] + baz * d[2];
+    const double baoa = bax * oax + bay * oay + baz * oaz, rdoa = d[0] * oax + d[1] * oay + d[2] * oaz;
+    const double oaoa = oax * oax + oay * oay + oaz * oaz;
+    const double qa = baba - bard * bard, qb = baba * rdoa - baoa * bard, qc = baba * oaoa - baoa * baoa - r * r * baba;
+    double best = -1.0;
+    if (qa > 1.0e-12 * baba) {
+        const double h = qb * qb - qa * qc;
+        if (h >= 0.0) {
+            const double t = (-qb - sqrt(h)) / qa;
+            const double yy = baoa + t * bard;
+            if (yy > 0.0 && yy < baba) return t;            // the cylinder between the caps (entry point: nearest of all)
+        }
+    }
+    // the spheres at the two ends
+    {
+        const double B = rdoa, Cc = oaoa - r * r, h = B * B - Cc;
+        if (h > 0.0) best = -B - sqrt(h);
+    }
+    {
+        const double obx = oax - bax, oby = oay - bay, obz = oaz - baz;
+        const double B = d[0] * obx + d[1] * oby + d[2] * obz, Cc = obx * obx + oby * oby + obz * obz - r * r, h = B * B - Cc;
+        if (h > 0.0) { const double t = -B - sqrt(h); if (t > 0.0 && (best <= 0.0 || t < best)) best = t; }
+    }
+    return best;
+}
+
+// nearest tube along the primary ray of (x, y; sample sm) before s_max; writes the hit buffer like a surface hit would
+__device__ __noinline__ bool tube_nearest(const RenderArgs& A, int x, int y, uint32_t pixel, unsigned sm, double s_max, float3& col) {
+    const unsigned* L = A.tube_tiles + (size_t)((y >> MRTX_TUBE_TILE_LOG2) * A.tube_tx + (x >> MRTX_TUBE_TILE_LOG2)) * (MRTX_TUBE_TILE_CAP + 2);
+    const unsigned cnt = __ldg(L);
+    if (!cnt) return false;
+    const Camera& cam = A.cam;
+    const bool j = A.sp.jitter != 0;
+    const double jx = j ? rnd(pixel, sm, 0) : 0.5, jy = j ? rnd(pixel, sm, 1) : 0.5;
+    const double aspect = (double)A.width / (double)A.height;
+    const double sx = ((x + jx) / A.width * 2.0 - 1.0) * cam.tan_half_fov * aspect;
+    const double sy = (1.0 - (y + jy) / A.height * 2.0) * cam.tan_half_fov;
+    double d[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) d[a] = cam.w[a] + sx * cam.right[a] + sy * cam.up[a];
+    const double dn = 1.0 / sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) d[a] *= dn;
+    const bool all = cnt > MRTX_TUBE_TILE_CAP;                 // list overflowed: every segment is a candidate
+    const unsigned n = all ? A.n_tubes : cnt;
+    double best = s_max;
+    int which = -1;
+    for (unsigned i = 0; i < n; ++i) {
+        const unsigned k = all ? i : __ldg(L + 1 + i);
+        const float4 sa = __ldg(A.tubes + 3 * (size_t)k), sb = __ldg(A.tubes + 3 * (size_t)k + 1);
+        const double t = capsule_hit(cam.eye, d, sa, sb);
+        if (t > 0.0 && t < best) { best = t; which = (int)k; }
+    }
+    if (which < 0) return false;
+    const float4 c = __ldg(A.tubes + 3 * (size_t)which + 2);
+    col = make_float3(c.x, c.y, c.z);
+    if (sm == A.hit_sample && A.hit)
+        A.hit[(size_t)y * A.width + x] = make_float4((float)(cam.eye[0] + best * d[0]), (float)(cam.eye[1] + best * d[1]),
+                                                     (float)(cam.eye[2] + best * d[2]), (float)best);
+    if (A.hit64) A.hit64[(size_t)y * A.width + x] = make_double4(-2.0, 0.0, 0.0, best);      // s = -2: a tube, at distance w
+    return true;
+}
+
+// bins the segments to the screen tiles their projection (grown by the tube radius and a pixel of jitter) touches
+__global__ void __launch_bounds__(128)
+tube_bin_kernel(const float4* __restrict__ tubes, unsigned n, unsigned* __restrict__ tiles, int tx, int ty, Camera cam, int width, int height) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 sa = tubes[3 * (size_t)i], sb = tubes[3 * (size_t)i + 1];
+    const double aspect = (double)width / (double)height;
+    double lo_x = 1e30, hi_x = -1e30, lo_y = 1e30, hi_y = -1e30;
+    bool everywhere = false;
+    const float4 ends[2] = {sa, sb};
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const double vx = (double)ends[e].x - cam.eye[0], vy = (double)ends[e].y - cam.eye[1], vz = (double)ends[e].z - cam.eye[2];
+        const double z = vx * cam.w[0] + vy * cam.w[1] + vz * cam.w[2];
+        if (!(z > 4.0 * (double)sa.w + 1e-6)) { everywhere = true; continue; }       // at or behind the eye
+        const double px = ((vx * cam.right[0] + vy * cam.right[1] + vz * cam.right[2]) / z / (cam.tan_half_fov * aspect) + 1.0) * 0.5 * width;
+        const double py = (1.0 - (vx * cam.up[0] + vy * cam.up[1] + vz * cam.up[2]) / z / cam.tan_half_fov) * 0.5 * height;
+        // radius on the screen (x 3: off-axis stretch of the perspective projection, 1 / cos of up to 64 deg at the corners of a
+        // 90-degree view, and some)
+        const double pr = 3.0 * (double)sa.w / z / cam.tan_half_fov * 0.5 * height + 2.0;
+        lo_x = fmin(lo_x, px - pr); hi_x = fmax(hi_x, px + pr); lo_y = fmin(lo_y, py - pr); hi_y = fmax(hi_y, py + pr);
+    }
+    int t0x = 0, t1x = tx - 1, t0y = 0, t1y = ty - 1;
+    if (!everywhere) {
+        if (hi_x < 0.0 || hi_y < 0.0 || lo_x >= (double)width || lo_y >= (double)height) return;
+        t0x = max((int)floor(lo_x) >> MRTX_TUBE_TILE_LOG2, 0); t1x = min((int)floor(hi_x) >> MRTX_TUBE_TILE_LOG2, tx - 1);
+        t0y = max((int)floor(lo_y) >> MRTX_TUBE_TILE_LOG2, 0); t1y = min((int)floor(hi_y) >> MRTX_TUBE_TILE_LOG2, ty - 1);
+    }
+    for (int y = t0y; y <= t1y; ++y)
+        for (int x = t0x; x <= t1x; ++x) {
+            unsigned* L = tiles + (size_t)(y * tx + x) * (MRTX_TUBE_TILE_CAP + 2);
+            const unsigned k = atomicAdd(L, 1u);
+            if (k < MRTX_TUBE_TILE_CAP) L[1 + k] = i;
+        }
+}
+
 __device__ __forceinline__ void flush_counters(const RenderArgs& A, const RayStats& rs, const Counters& cnt, int lane) {
     const unsigned vals[8] = {rs.primary, rs.inside, rs.hits, rs.shadow, rs.occluded, cnt.nodes, cnt.tests, cnt.overflow};
 #pragma unroll
@@ -275,7 +391,7 @@ cull_kernel(const __grid_constant__ RenderArgs A) {
             const double bz = (A.sp.ez[0] * d[0] + A.sp.ez[1] * d[1] + A.sp.ez[2] * d[2]) * dn;
             const double od = A.eye_b[0] * bx + A.eye_b[1] * by + A.eye_b[2] * bz;
             const double d2 = eye_dist * eye_dist - od * od;
-            if (eye_dist > cull_r && (d2 > cull_r * cull_r || od > 0.0)) {
+            if (eye_dist > cull_r && (d2 > cull_r * cull_r || od > 0.0) && !tube_tile_count(A, x, y)) {
                 culled = 1;                                     // every sample of this pixel misses
                 write_miss(A, x, y, true);
                 float4* ap = A.accum + (size_t)y * A.width + x;
@@ -653,14 +769,22 @@ trace_kernel_referee(const __grid_constant__ RenderArgs A) {
             if (lane == 0) { ++rs.primary; if (entered) ++rs.inside; }
             if (who < 0) {
                 if (lane == 0) {
-                    write_miss(A, x, y, sm == A.hit_sample);
-                    if (sees_background(A)) { const float3 m = miss_radiance_body(A, R); acc.x += m.x; acc.y += m.y; acc.z += m.z; }
+                    float3 tc;
+                    if (tube_tile_count(A, x, y) && tube_nearest(A, x, y, pixel, sm, 1.0e300, tc)) { acc.x += tc.x; acc.y += tc.y; acc.z += tc.z; }
+                    else {
+                        write_miss(A, x, y, sm == A.hit_sample);
+                        if (sees_background(A)) { const float3 m = miss_radiance_body(A, R); acc.x += m.x; acc.y += m.y; acc.z += m.z; }
+                    }
                 }
                 continue;
             }
             float3 lit = make_float3(0.f, 0.f, 0.f);
             bool need_shadow = false;
-            if (lane == who) need_shadow = fast ? shade_fast(A, R, fh, x, y, pixel, sm, lit, S) : shade_hit(A, R, h, x, y, pixel, sm, lit, S);
+            if (lane == who) {
+                // (a tube in front of the hit: its flat colour is the sample)
+                if (tube_tile_count(A, x, y) && tube_nearest(A, x, y, pixel, sm, fast ? fh.s : h.s, lit)) need_shadow = false;
+                else need_shadow = fast ? shade_fast(A, R, fh, x, y, pixel, sm, lit, S) : shade_hit(A, R, h, x, y, pixel, sm, lit, S);
+            }
             need_shadow = __shfl_sync(0xffffffffu, need_shadow ? 1 : 0, who) != 0;
             lit.x = __shfl_sync(0xffffffffu, lit.x, who); lit.y = __shfl_sync(0xffffffffu, lit.y, who); lit.z = __shfl_sync(0xffffffffu, lit.z, who);
             if (lane == 0) ++rs.hits;
@@ -709,6 +833,7 @@ static void fill_render_args(mrtx_ctx* ctx, int x0, int y0, int x1, int y1, unsi
     A.hit64 = ctx->sp.debug_hits ? ctx->hit64 : nullptr;
     A.counters = ctx->d_counters;
     A.work_counter = ctx->d_work;
+    A.tubes = ctx->tube_seg; A.n_tubes = ctx->n_tubes; A.tube_tiles = ctx->tube_tiles; A.tube_tx = ctx->tube_tx;
     A.pixel_list = ctx->pixel_list;
     const double er[3] = {A.cam.eye[0] - A.sp.pos[0], A.cam.eye[1] - A.sp.pos[1], A.cam.eye[2] - A.sp.pos[2]};
     const double lr[3] = {A.sp.light_pos[0] - A.sp.pos[0], A.sp.light_pos[1] - A.sp.pos[1], A.sp.light_pos[2] - A.sp.pos[2]};

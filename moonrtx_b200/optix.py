@@ -4,8 +4,10 @@ path calls (`self.rt` in moonrtx/moon_renderer.py:571-650, 852-871, renderer_vid
 renderer_navigation.py) - same method names, argument meaning and threading contract
 (SURVEY.md §8b).  The scene it accepts is the one MoonRTX builds: one textured, displaced
 sphere ("moon"), one spherical light ("sun"), one pinhole camera, Gamma and Overlay
-post-processing.  Geometry the hot path does not need (sun disk, grid/label tubes, star
-background) is accepted and ignored so that the reference's call sequence runs unchanged.
+post-processing; beside them what the reference draws around the Moon: the star-map background and the
+visible Sun disk on rays that miss it (set_background, set_data("sun_disk")) and the tube graphs of the
+selenographic grid, the labels and the pins (set_graph / update_graph / delete_geometry), flat-shaded and
+shadowless as the reference's materials make them.
 
 Rendering runs on the B200 through libmoonb200.so; there is no CPU fallback.
 
@@ -37,6 +39,41 @@ class _OptixShim:
 
     def set_camera_fov(self, fov: float) -> None:
         self._rt.update_camera(fov=fov)
+
+
+def tube_segments(geometry: dict) -> np.ndarray:
+    """every visible segment of every graph: float32 (n, 12) = a.xyz, r, b.xyz, 0, colour.rgb, 0 (mrtx_set_tubes)"""
+    parts = []
+    for g in geometry.values():
+        if g.get("geom") != "Graph" or g.get("pos") is None or g.get("edges") is None:
+            continue
+        pos = np.asarray(g["pos"], dtype=np.float64).reshape(-1, 3)
+        edges = np.asarray(g["edges"], dtype=np.int64).reshape(-1, 2)
+        if len(pos) == 0 or len(edges) == 0:
+            continue
+        r = np.asarray(0.05 if g.get("r") is None else g["r"], dtype=np.float64).reshape(-1)
+        r = np.full(len(pos), r[0]) if r.size == 1 else r
+        if r.size != len(pos):
+            raise ValueError("graph radii: one value or one per vertex")
+        c = np.asarray(0.94 if g.get("c") is None else g["c"], dtype=np.float64)
+        if c.size == 1:
+            col = np.full((len(pos), 3), float(c.reshape(-1)[0]))
+        elif c.size == 3:
+            col = np.broadcast_to(c.reshape(1, 3), (len(pos), 3))
+        else:
+            col = c.reshape(-1, 3)
+        # (a segment between vertices of different radii is drawn with the smaller one: the reference only ever
+        #  gives a whole label one radius, or 0 to hide it - renderer_labels.py:128-130)
+        rs = np.minimum(r[edges[:, 0]], r[edges[:, 1]])
+        keep = rs > 0.0
+        if not keep.any():
+            continue
+        seg = np.zeros((int(keep.sum()), 12), np.float32)
+        seg[:, 0:3] = pos[edges[keep, 0]]; seg[:, 3] = rs[keep]
+        seg[:, 4:7] = pos[edges[keep, 1]]
+        seg[:, 8:11] = col[edges[keep, 0]]
+        parts.append(seg)
+    return np.concatenate(parts, axis=0) if parts else np.zeros((0, 12), np.float32)
 
 
 class B200OptiX:
@@ -252,24 +289,40 @@ class B200OptiX:
             self.refresh_scene()
 
     def set_graph(self, name: str, pos=None, edges=None, r=None, c=None, mat=None, refresh: bool = False, **_):
-        """Grid / label / pin tube geometry (renderer_labels.py:263-305, renderer_pins.py:18-55): recorded, not
-        rendered - the reference's update_overlays() runs unchanged against the drop-in."""
-        self._ignored_geometry[name] = {"geom": "Graph", "pos": pos, "edges": edges, "r": r, "c": c, "mat": mat}
+        """Grid / label / pin tube geometry (renderer_labels.py:263-305, renderer_pins.py:18-55): a graph of thin tubes,
+        vertices `pos` (n, 3) in scene space joined by `edges` (m, 2), radius `r` (one number or one per vertex; 0 hides),
+        colour `c`.  Rendered flat-shaded in front of the surface, casting no shadow."""
+        with self._padlock:
+            self._ignored_geometry[name] = {"geom": "Graph", "pos": pos, "edges": edges, "r": r, "c": c, "mat": mat}
+            self._push_tubes()
         if refresh:
             self.refresh_scene()
 
     def update_graph(self, name: str, pos=None, edges=None, r=None, c=None, mat=None, refresh: bool = False, **_):
         if name not in self._ignored_geometry:
             raise ValueError(f"no geometry named {name}")
-        self._ignored_geometry[name].update({k: w for k, w in (("pos", pos), ("edges", edges), ("r", r), ("c", c), ("mat", mat))
-                                             if w is not None})
+        with self._padlock:
+            self._ignored_geometry[name].update({k: w for k, w in (("pos", pos), ("edges", edges), ("r", r), ("c", c), ("mat", mat))
+                                                 if w is not None})
+            if self._ignored_geometry[name].get("geom") == "Graph":
+                self._push_tubes()
         if refresh:
             self.refresh_scene()
+
+    def _tube_segments(self) -> np.ndarray:
+        return tube_segments(self._ignored_geometry)
+
+    def _push_tubes(self):
+        seg = np.ascontiguousarray(self._tube_segments())
+        _lib.check(self._lib.mrtx_set_tubes(self._ctx, seg.ctypes.data if len(seg) else None, len(seg)))
 
     def delete_geometry(self, name: str):
         if name == self._moon_name:
             raise ValueError("the displaced surface cannot be deleted")
-        self._ignored_geometry.pop(name, None)
+        g = self._ignored_geometry.pop(name, None)
+        if g is not None and g.get("geom") == "Graph":
+            with self._padlock:
+                self._push_tubes()
         if name == getattr(self, "_sun_disk_name", None):
             with self._padlock:
                 self._sun_disk_name = None

@@ -64,6 +64,11 @@ typedef struct {
     double sun_disk_pos[3], sun_disk_radius, sun_disk_color[3];
     const uint8_t* env;
     int env_w, env_h;
+    /* overlay tubes (rt.set_graph: grid lines, labels, pins - renderer_labels.py:263-305, renderer_pins.py:18-55): n_tubes
+     * capsules, 12 floats each = (a.xyz, r, b.xyz, -, colour.rgb, -), scene space.  Flat-shaded (the colour is the radiance
+     * of a camera sample that meets the tube before the surface), never an occluder of the sun (renderer_labels.py:133-139) */
+    const float* tubes;
+    int n_tubes;
 } orc_scene;
 
 /* ------------------------------------------------------------------------------ */
@@ -412,6 +417,43 @@ static void miss_radiance(const orc_scene* S, const double* o, const double* d, 
     }
 }
 
+/* first intersection of the ray o + t d (|d| = 1) with the capsule (a, b, r): negative = none.  Brute force over all tubes. */
+static double capsule_hit(const double* o, const double* d, const float* seg) {
+    const double a[3] = {seg[0], seg[1], seg[2]}, r = seg[3];
+    const double ba[3] = {seg[4] - a[0], seg[5] - a[1], seg[6] - a[2]}, oa[3] = {o[0] - a[0], o[1] - a[1], o[2] - a[2]};
+    const double baba = dot3(ba, ba), bard = dot3(ba, d), baoa = dot3(ba, oa), rdoa = dot3(d, oa), oaoa = dot3(oa, oa);
+    const double qa = baba - bard * bard, qb = baba * rdoa - baoa * bard, qc = baba * oaoa - baoa * baoa - r * r * baba;
+    double best = -1.0;
+    if (qa > 1.0e-12 * baba) {
+        const double h = qb * qb - qa * qc;
+        if (h >= 0.0) {
+            const double t = (-qb - sqrt(h)) / qa, y = baoa + t * bard;
+            if (y > 0.0 && y < baba) return t;
+        }
+    }
+    {
+        const double h = rdoa * rdoa - (oaoa - r * r);
+        if (h > 0.0) best = -rdoa - sqrt(h);
+    }
+    {
+        const double ob[3] = {oa[0] - ba[0], oa[1] - ba[1], oa[2] - ba[2]};
+        const double B = dot3(d, ob), h = B * B - (dot3(ob, ob) - r * r);
+        if (h > 0.0) { const double t = -B - sqrt(h); if (t > 0.0 && (best <= 0.0 || t < best)) best = t; }
+    }
+    return best;
+}
+
+static int nearest_tube(const orc_scene* S, const double* o, const double* d, double s_max, double* s_hit) {
+    int which = -1;
+    double best = s_max;
+    for (int i = 0; i < S->n_tubes; ++i) {
+        const double t = capsule_hit(o, d, S->tubes + (size_t)i * 12);
+        if (t > 0.0 && t < best) { best = t; which = i; }
+    }
+    *s_hit = best;
+    return which;
+}
+
 /*
  * Render samples sample0 .. sample0+nsamples-1 of the pixels (x0 + i*stride, y0 + j*stride)
  * inside [x0,x1) x [y0,y1).  Outputs are compact arrays over that sub-grid, row-major:
@@ -449,7 +491,11 @@ long orc_render(const orc_scene* S, int x0, int y0, int x1, int y1, int stride,
                 trace(S, ob, db, 0.0, &h);
                 long shadow_cells = 0;
                 double rgb[3] = {0, 0, 0};
-                if (h.hit) {
+                double s_tube = 0.0;
+                const int tube = S->n_tubes ? nearest_tube(S, S->eye, dir, h.hit ? h.s : 1.0e300, &s_tube) : -1;
+                if (tube >= 0) {
+                    for (int q = 0; q < 3; ++q) rgb[q] = S->tubes[(size_t)tube * 12 + 8 + q];
+                } else if (h.hit) {
                     double tp[3] = {Lb[0] - h.p[0], Lb[1] - h.p[1], Lb[2] - h.p[2]};
                     const double dist = sqrt(dot3(tp, tp));
                     double lc[3] = {tp[0] / dist, tp[1] / dist, tp[2] / dist};
@@ -488,14 +534,16 @@ long orc_render(const orc_scene* S, int x0, int y0, int x1, int y1, int stride,
                 if (hit64) {
                     hit64[k * 4 + 0] = h.hit ? h.s : -1.0; hit64[k * 4 + 1] = h.hit ? h.r : 0.0;
                     hit64[k * 4 + 2] = h.hit ? h.lon : 0.0; hit64[k * 4 + 3] = h.hit ? h.lat : 0.0;
+                    if (tube >= 0) { hit64[k * 4 + 0] = -2.0; hit64[k * 4 + 1] = 0.0; hit64[k * 4 + 2] = 0.0; hit64[k * 4 + 3] = s_tube; }
                 }
                 if (hit32 && sm == sample0) {
                     for (int q = 0; q < 3; ++q) {
                         /* scene = pos + R^T p_body */
-                        const double sc = h.hit ? S->pos[q] + S->ex[q] * h.p[0] + S->ey[q] * h.p[1] + S->ez[q] * h.p[2] : 0.0;
+                        double sc = h.hit ? S->pos[q] + S->ex[q] * h.p[0] + S->ey[q] * h.p[1] + S->ez[q] * h.p[2] : 0.0;
+                        if (tube >= 0) sc = S->eye[q] + s_tube * dir[q];
                         hit32[k * 4 + q] = (float)sc;
                     }
-                    hit32[k * 4 + 3] = h.hit ? (float)h.s : 0.0f;
+                    hit32[k * 4 + 3] = tube >= 0 ? (float)s_tube : (h.hit ? (float)h.s : 0.0f);
                 }
                 if (stats) { stats[k * 2] = h.cells; stats[k * 2 + 1] = shadow_cells; }
             }

@@ -38,6 +38,7 @@ class _Scene(C.Structure):
         ("exposure", C.c_float), ("inv_gamma", C.c_float),
         ("sun_disk_pos", _D3), ("sun_disk_radius", C.c_double), ("sun_disk_color", _D3),
         ("env", C.c_void_p), ("env_w", C.c_int), ("env_h", C.c_int),
+        ("tubes", C.c_void_p), ("n_tubes", C.c_int),
     ]
 
 
@@ -88,7 +89,7 @@ class OracleScene:
                  eye=(0, -300, 0), target=(0, 0, 0), up=(0, 0, 1), fov=4.242192793,
                  light_pos=(21460.0, 0.0, 0.0), light_radius=100.0, light_radiance=80.0 * (2146.0 / 100.0) ** 2,
                  scene_epsilon=1.0e-4, jitter=False, shadows=True, texture=None,
-                 exposure=0.9, gamma=2.2, background=None, sun_disk=None):
+                 exposure=0.9, gamma=2.2, background=None, sun_disk=None, tubes=None):
         self.s = _Scene()
         s = self.s
         self.elevation = np.ascontiguousarray(elevation)
@@ -144,6 +145,13 @@ class OracleScene:
             s.sun_disk_radius = float(r)
             col = np.broadcast_to(np.asarray(col, dtype=np.float64).reshape(-1), (3,)) if np.size(col) in (1, 3) else np.asarray(col, dtype=np.float64)[:3]
             s.sun_disk_color = _D3(*[float(x) for x in col])
+        self.set_tubes(tubes)
+
+    def set_tubes(self, tubes):
+        """overlay tubes: float32 (n, 12) = a.xyz, r, b.xyz, -, colour.rgb, - in scene space (B200OptiX._tube_segments())"""
+        self.tubes = None if tubes is None or len(tubes) == 0 else np.ascontiguousarray(tubes, dtype=np.float32).reshape(-1, 12)
+        self.s.tubes = None if self.tubes is None else self.tubes.ctypes.data
+        self.s.n_tubes = 0 if self.tubes is None else len(self.tubes)
 
     def render(self, x0=0, y0=0, x1=None, y1=None, stride=1, sample0=0, nsamples=1):
         s = self.s

@@ -395,7 +395,8 @@ def test_hit_queue_and_shade_kernel_equal_in_kernel_shading(spp, phase, shadows)
     d = np.abs(ia[..., :3].astype(np.int32) - ib[..., :3].astype(np.int32))
     assert int(d.max()) <= (0 if shadows else 1)
     if spp == 1:
-        assert np.array_equal(ha, hb)
+        # (written by different kernels: the same source expression may be contracted differently)
+        assert np.array_equal(ha[..., 0] > 0, hb[..., 0] > 0) and np.allclose(ha, hb, rtol=1e-12, atol=1e-12)
 
 
 @pytest.mark.parametrize("spp,phase", [(1, 88.0), (16, 90.0), (40, 60.0)])
