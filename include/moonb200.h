@@ -78,6 +78,16 @@ int  mrtx_l2_flush(mrtx_ctx* ctx);   /* overwrite a scratch buffer larger than L
  * Bit-exact against the reference for every ds >= 1.                                 */
 int  mrtx_downscale_i16(mrtx_ctx* ctx, const int16_t* src, int W, int H, int ds,
                         float* out, float* radius_scale);
+/* The same straight from the LDEM file (replaces plotoptix.utils.read_image, data_loader.py:206, for the file the
+ * reference ships: an uncompressed little-endian single-channel 16-bit strip TIFF, classic or BigTIFF).  mrtx_tiff_info
+ * parses the directory on the host (no device work): size, bits per sample, and whether the strips can be streamed as they
+ * lie.  mrtx_downscale_tiff_i16 then reads them with pread() into the pinned staging buffers of the banded upload - no
+ * decoded copy of the 8.5 GB map in host memory - and, if npy_cache_path is given, writes the result into that file in
+ * numpy's .npy format while it comes down from the device (the downscale cache, data_loader.py:88-95); on any error no
+ * cache file is left behind.  Not streamable (compressed, tiled, big-endian ...): MRTX_ERR_INVALID, decode on the host.  */
+int  mrtx_tiff_info(const char* path, int* W, int* H, int* bits_per_sample, int* streamable);
+int  mrtx_downscale_tiff_i16(mrtx_ctx* ctx, const char* path, int ds, float* out, float* radius_scale,
+                             const char* npy_cache_path);
 int  mrtx_downscale_i16_dev(mrtx_ctx* ctx, const int16_t* src_dev, int W, int H, int ds,
                             float* out_dev, float* radius_scale /* host, may be NULL */);
 

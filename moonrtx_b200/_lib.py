@@ -69,6 +69,8 @@ _SIGNATURES = {
     "mrtx_frame_submit_to": (C.c_int, [c_ctx, C.c_void_p, C.c_uint, C.c_int, C.POINTER(C.c_int)]),
     "mrtx_frame_recv": (C.c_int, [c_ctx, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
     "mrtx_frame_recv_wait": (C.c_int, [c_ctx, C.c_int]),
+    "mrtx_tiff_info": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "mrtx_downscale_tiff_i16": (C.c_int, [c_ctx, C.c_char_p, C.c_int, C.c_void_p, C.POINTER(C.c_float), C.c_char_p]),
     "mrtx_set_tubes": (C.c_int, [c_ctx, C.c_void_p, C.c_int]),
     "mrtx_p2p_open": (C.c_int, [c_ctx, C.c_int, C.c_int, C.c_size_t, C.POINTER(C.c_uint8)]),
     "mrtx_p2p_connect": (C.c_int, [c_ctx, C.POINTER(C.c_uint8)]),

@@ -4,6 +4,12 @@
 #include "common.cuh"
 
 #include <thread>
+#include <atomic>
+#include <vector>
+#include <algorithm>
+#include <fcntl.h>
+#include <unistd.h>
+#include <sys/types.h>
 
 #include <stdarg.h>
 #include <stdlib.h>
@@ -277,13 +283,12 @@ static int ensure_staging(mrtx_ctx* ctx, size_t bytes) {
 // the map goes up in bands through two pinned staging buffers - host threads fill one while the copy engine drains the
 // other and the block-mean kernel reduces the band before - so the call costs about what the slowest of the three
 // (the host-side memcpy) costs; the result comes down the same way.
-int mrtx_downscale_i16(mrtx_ctx* ctx, const int16_t* src, int W, int H, int ds,
-                       float* out, float* radius_scale) {
-    MRTX_CTX(ctx);
-    int rc = check_downscale_args(src, W, H, ds, out);
-    if (rc) return rc;
-    MRTX_REQUIRE(radius_scale, "null radius_scale");
-    rc = ensure_rs_word(ctx);
+// `fill(dst, first_row, rows)` puts source rows into a pinned staging buffer (from the caller's array, or straight from the
+// strips of a TIFF file); `npy`, if given, receives the result as it comes down (the downscale cache, data_loader.py:88-95).
+extern "C++" {
+template <typename Fill>
+static int downscale_stream(mrtx_ctx* ctx, int W, int H, int ds, float* out, float* radius_scale, Fill fill, FILE* npy) {
+    int rc = ensure_rs_word(ctx);
     if (rc) return rc;
     const int h = H / ds, w = W / ds;
     const size_t in_bytes = (size_t)W * H * sizeof(int16_t);
@@ -305,13 +310,14 @@ int mrtx_downscale_i16(mrtx_ctx* ctx, const int16_t* src, int W, int H, int ds,
         const size_t rows = (size_t)H - r0 < band_rows ? (size_t)H - r0 : band_rows;
         const size_t bytes = rows * (size_t)W * 2;
         if (cudaEventSynchronize(ctx->stage_ev[b]) != cudaSuccess) { rc = MRTX_ERR_CUDA; break; }     // the copy out of this buffer two bands ago
-        parallel_memcpy(ctx->stage[b], src + r0 * (size_t)W, bytes);
+        rc = fill(ctx->stage[b], r0, rows);
+        if (rc) break;
         if (cudaMemcpyAsync(d_src + r0 * (size_t)W, ctx->stage[b], bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = MRTX_ERR_CUDA; break; }
         if (cudaEventRecord(ctx->stage_ev[b], st) != cudaSuccess) { rc = MRTX_ERR_CUDA; break; }
         rc = downscale_band(ctx, d_src + r0 * (size_t)W, W, (int)rows, ds, d_out + (r0 / ds) * (size_t)w);
     }
     if (!rc) rc = downscale_finish(ctx, d_out, (size_t)w * h, ctx->h_rs_dev);
-    // the result: device -> pinned staging -> the caller's array, two chunks in flight
+    // the result: device -> pinned staging -> the caller's array (and the cache file), two chunks in flight
     const size_t chunk = ctx->stage_bytes;
     size_t done = 0, copied = 0;
     int q = 0;
@@ -321,6 +327,7 @@ int mrtx_downscale_i16(mrtx_ctx* ctx, const int16_t* src, int W, int H, int ds,
         if (pend[q]) {
             if (cudaEventSynchronize(ctx->stage_ev[q]) != cudaSuccess) { rc = MRTX_ERR_CUDA; break; }
             parallel_memcpy((char*)out + pend_off[q], ctx->stage[q], pend_len[q]);
+            if (npy && fwrite(ctx->stage[q], 1, pend_len[q], npy) != pend_len[q]) { mrtx_set_error("cache file: short write"); rc = MRTX_ERR_INVALID; break; }
             copied += pend_len[q]; pend[q] = false;
         }
         if (done < out_bytes) {
@@ -337,6 +344,189 @@ int mrtx_downscale_i16(mrtx_ctx* ctx, const int16_t* src, int W, int H, int ds,
     cudaStreamSynchronize(st);
     cudaFree(d_src); cudaFree(d_out);
     (void)copied;
+    return rc;
+}
+}  // extern "C++"
+
+int mrtx_downscale_i16(mrtx_ctx* ctx, const int16_t* src, int W, int H, int ds,
+                       float* out, float* radius_scale) {
+    MRTX_CTX(ctx);
+    int rc = check_downscale_args(src, W, H, ds, out);
+    if (rc) return rc;
+    MRTX_REQUIRE(radius_scale, "null radius_scale");
+    return downscale_stream(ctx, W, H, ds, out, radius_scale, [=](void* dst, size_t r0, size_t rows) {
+        parallel_memcpy(dst, src + r0 * (size_t)W, rows * (size_t)W * 2);
+        return (int)MRTX_OK;
+    }, nullptr);
+}
+
+// ---- the LDEM file itself -------------------------------------------------------------------------
+// plotoptix.utils.read_image (data_loader.py:206) decodes the whole 8.5 GB TIFF into a host array before the first
+// element is reduced.  The LOLA LDEM is an uncompressed single-channel 16-bit strip TIFF (BigTIFF at 128 px/deg): its
+// strips ARE the row-major array, so they are read with pread() straight into the pinned staging buffers of the banded
+// upload above - no decoded copy, no second pass over host memory.
+struct TiffInfo { int W, H, bits, samples, compression, little, tiled, format; unsigned long long rows_per_strip; std::vector<unsigned long long> off, cnt; };
+
+static unsigned long long tiff_get(const unsigned char* p, int bytes, bool le) {
+    unsigned long long v = 0;
+    for (int i = 0; i < bytes; ++i) v |= (unsigned long long)p[le ? i : bytes - 1 - i] << (8 * i);
+    return v;
+}
+
+static int tiff_parse(const char* path, TiffInfo& T) {
+    FILE* f = fopen(path, "rb");
+    if (!f) { mrtx_set_error("cannot open %s", path); return MRTX_ERR_INVALID; }
+    unsigned char hd[16];
+    int rc = MRTX_ERR_INVALID;
+    T = TiffInfo();
+    T.samples = 1; T.compression = 1; T.format = 1; T.rows_per_strip = ~0ull;
+    do {
+        if (fread(hd, 1, 16, f) != 16) { mrtx_set_error("%s: not a TIFF file", path); break; }
+        const bool le = hd[0] == 'I' && hd[1] == 'I';
+        if (!le && !(hd[0] == 'M' && hd[1] == 'M')) { mrtx_set_error("%s: not a TIFF file", path); break; }
+        T.little = le;
+        const unsigned magic = (unsigned)tiff_get(hd + 2, 2, le);
+        const bool big = magic == 43;
+        if (magic != 42 && !big) { mrtx_set_error("%s: not a TIFF file", path); break; }
+        const unsigned long long ifd = big ? tiff_get(hd + 8, 8, le) : tiff_get(hd + 4, 4, le);
+        if (fseeko(f, (off_t)ifd, SEEK_SET)) { mrtx_set_error("%s: bad directory offset", path); break; }
+        unsigned char nb[8];
+        if (fread(nb, 1, big ? 8 : 2, f) != (size_t)(big ? 8 : 2)) { mrtx_set_error("%s: truncated", path); break; }
+        const unsigned long long n = tiff_get(nb, big ? 8 : 2, le);
+        const int esz = big ? 20 : 12;
+        if (n > 4096) { mrtx_set_error("%s: implausible directory", path); break; }
+        std::vector<unsigned char> dir((size_t)n * esz);
+        if (fread(dir.data(), 1, dir.size(), f) != dir.size()) { mrtx_set_error("%s: truncated", path); break; }
+        static const int tsz[] = {0, 1, 1, 2, 4, 8, 1, 1, 2, 4, 8, 4, 8, 4, 0, 0, 8, 8, 8};
+        bool bad = false;
+        auto values = [&](const unsigned char* e, std::vector<unsigned long long>& out) {
+            const unsigned type = (unsigned)tiff_get(e + 2, 2, le);
+            const unsigned long long count = big ? tiff_get(e + 4, 8, le) : tiff_get(e + 4, 4, le);
+            const int sz = type < 19 ? tsz[type] : 0;
+            if (!sz || count > ((unsigned long long)1 << 28)) { bad = true; return; }
+            const unsigned char* vp = e + (big ? 12 : 8);
+            const size_t inline_bytes = big ? 8 : 4;
+            std::vector<unsigned char> buf;
+            if (count * sz > inline_bytes) {
+                const unsigned long long at = big ? tiff_get(vp, 8, le) : tiff_get(vp, 4, le);
+                buf.resize((size_t)count * sz);
+                if (fseeko(f, (off_t)at, SEEK_SET) || fread(buf.data(), 1, buf.size(), f) != buf.size()) { bad = true; return; }
+                vp = buf.data();
+            }
+            out.resize((size_t)count);
+            for (size_t i = 0; i < (size_t)count; ++i) out[i] = tiff_get(vp + i * sz, sz, le);
+        };
+        for (unsigned long long k = 0; k < n && !bad; ++k) {
+            const unsigned char* e = dir.data() + (size_t)k * esz;
+            const unsigned tag = (unsigned)tiff_get(e, 2, le);
+            std::vector<unsigned long long> v;
+            switch (tag) {
+                case 256: values(e, v); if (!v.empty()) T.W = (int)v[0]; break;
+                case 257: values(e, v); if (!v.empty()) T.H = (int)v[0]; break;
+                case 258: values(e, v); if (!v.empty()) T.bits = (int)v[0]; break;
+                case 259: values(e, v); if (!v.empty()) T.compression = (int)v[0]; break;
+                case 277: values(e, v); if (!v.empty()) T.samples = (int)v[0]; break;
+                case 278: values(e, v); if (!v.empty()) T.rows_per_strip = v[0]; break;
+                case 339: values(e, v); if (!v.empty()) T.format = (int)v[0]; break;
+                case 273: values(e, T.off); break;
+                case 279: values(e, T.cnt); break;
+                case 322: case 324: T.tiled = 1; break;
+                default: break;
+            }
+        }
+        if (bad || T.W <= 0 || T.H <= 0) { mrtx_set_error("%s: unreadable TIFF directory", path); break; }
+        rc = MRTX_OK;
+    } while (0);
+    fclose(f);
+    return rc;
+}
+
+// can the strips be streamed as they lie?  (else the caller decodes the file on the host, as the reference does)
+static bool tiff_streamable(const TiffInfo& T) {
+    if (T.tiled || T.compression != 1 || T.samples != 1 || T.bits != 16 || !T.little || T.off.empty() || T.off.size() != T.cnt.size()) return false;
+    const unsigned long long rps = T.rows_per_strip > (unsigned long long)T.H ? (unsigned long long)T.H : T.rows_per_strip;
+    if (!rps || T.off.size() != ((unsigned long long)T.H + rps - 1) / rps) return false;
+    for (size_t i = 0; i < T.off.size(); ++i) {
+        const unsigned long long rows = i + 1 < T.off.size() ? rps : (unsigned long long)T.H - rps * i;
+        if (T.cnt[i] != rows * (unsigned long long)T.W * 2) return false;
+    }
+    return true;
+}
+
+int mrtx_tiff_info(const char* path, int* W, int* H, int* bits_per_sample, int* streamable) {
+    MRTX_REQUIRE(path && W && H && bits_per_sample && streamable, "null argument");
+    TiffInfo T;
+    const int rc = tiff_parse(path, T);
+    if (rc) return rc;
+    *W = T.W; *H = T.H; *bits_per_sample = T.bits; *streamable = tiff_streamable(T) ? 1 : 0;
+    return MRTX_OK;
+}
+
+int mrtx_downscale_tiff_i16(mrtx_ctx* ctx, const char* path, int ds, float* out, float* radius_scale, const char* npy_cache_path) {
+    MRTX_CTX(ctx);
+    MRTX_REQUIRE(path && out && radius_scale, "null argument");
+    TiffInfo T;
+    int rc = tiff_parse(path, T);
+    if (rc) return rc;
+    if (!tiff_streamable(T)) { mrtx_set_error("%s: not an uncompressed little-endian 16-bit single-channel strip TIFF", path); return MRTX_ERR_INVALID; }
+    rc = check_downscale_args(path, T.W, T.H, ds, out);
+    if (rc) return rc;
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) { mrtx_set_error("cannot open %s", path); return MRTX_ERR_INVALID; }
+    FILE* npy = nullptr;
+    if (npy_cache_path) {
+        npy = fopen(npy_cache_path, "wb");
+        if (!npy) { close(fd); mrtx_set_error("cannot write %s", npy_cache_path); return MRTX_ERR_INVALID; }
+        // numpy format 1.0: magic, version, little-endian u16 header length, dict padded with spaces to a multiple of 64, '\n'
+        char dict[160];
+        int n = snprintf(dict, sizeof dict, "{'descr': '<f4', 'fortran_order': False, 'shape': (%d, %d), }", T.H / ds, T.W / ds);
+        const int total = ((10 + n + 1 + 63) / 64) * 64;
+        const int hlen = total - 10;
+        unsigned char pre[10] = {0x93, 'N', 'U', 'M', 'P', 'Y', 1, 0, (unsigned char)(hlen & 255), (unsigned char)(hlen >> 8)};
+        fwrite(pre, 1, 10, npy);
+        fwrite(dict, 1, (size_t)n, npy);
+        for (int i = n; i < hlen - 1; ++i) fputc(' ', npy);
+        fputc('\n', npy);
+    }
+    const unsigned long long rps = T.rows_per_strip > (unsigned long long)T.H ? (unsigned long long)T.H : T.rows_per_strip;
+    const size_t row_bytes = (size_t)T.W * 2;
+    rc = downscale_stream(ctx, T.W, T.H, ds, out, radius_scale, [&](void* dst, size_t r0, size_t rows) {
+        // rows [r0, r0 + rows) lie in strips r0 / rps ...: one pread per strip piece, in parallel for large bands
+        struct Piece { off_t at; size_t len, dst; };
+        std::vector<Piece> pieces;
+        for (size_t r = r0; r < r0 + rows;) {
+            const size_t sidx = r / rps, in_strip = r - sidx * rps;
+            const size_t take = std::min<size_t>(rps - in_strip, r0 + rows - r);
+            pieces.push_back({(off_t)(T.off[sidx] + in_strip * row_bytes), take * row_bytes, (r - r0) * row_bytes});
+            r += take;
+        }
+        std::atomic<int> failed{0};
+        auto run = [&](size_t a, size_t b) {
+            for (size_t i = a; i < b; ++i) {
+                size_t got = 0;
+                while (got < pieces[i].len) {
+                    const ssize_t k = pread(fd, (char*)dst + pieces[i].dst + got, pieces[i].len - got, pieces[i].at + (off_t)got);
+                    if (k <= 0) { failed = 1; return; }
+                    got += (size_t)k;
+                }
+            }
+        };
+        unsigned nt = std::thread::hardware_concurrency() / 2;
+        nt = nt < 1 ? 1 : (nt > 8 ? 8 : nt);
+        if (pieces.size() < 2 * nt) run(0, pieces.size());
+        else {
+            std::thread th[8];
+            const size_t per = (pieces.size() + nt - 1) / nt;
+            unsigned used = 0;
+            for (unsigned i = 0; i < nt && (size_t)i * per < pieces.size(); ++i)
+                th[used++] = std::thread(run, (size_t)i * per, std::min(pieces.size(), (size_t)(i + 1) * per));
+            for (unsigned i = 0; i < used; ++i) th[i].join();
+        }
+        if (failed) { mrtx_set_error("%s: read error", path); return (int)MRTX_ERR_INVALID; }
+        return (int)MRTX_OK;
+    }, npy);
+    close(fd);
+    if (npy) { if (fclose(npy) != 0 && !rc) { mrtx_set_error("cache file: write error"); rc = MRTX_ERR_INVALID; } if (rc) remove(npy_cache_path); }
     return rc;
 }
 

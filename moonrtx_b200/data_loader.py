@@ -184,6 +184,35 @@ def read_image(filepath: str) -> Optional[np.ndarray]:
         return cv2.imread(filepath, cv2.IMREAD_UNCHANGED)
 
 
+def tiff_info(filepath: str) -> Optional[dict]:
+    """Size of a TIFF and whether its strips can be streamed to the device as they lie (mrtx_tiff_info: an uncompressed
+    little-endian single-channel 16-bit strip TIFF, classic or BigTIFF - the LDEM as NASA ships it).  Host work only."""
+    w, h, bits, ok = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    if _lib.load().mrtx_tiff_info(os.fsencode(filepath), C.byref(w), C.byref(h), C.byref(bits), C.byref(ok)) != 0:
+        return None
+    return {"width": w.value, "height": h.value, "bits": bits.value, "streamable": bool(ok.value)}
+
+
+def downscale_elevation_file(filepath: str, downscale: int, cache_npy: Optional[str] = None,
+                             device: Optional[Device] = None) -> tuple[np.ndarray, float]:
+    """
+    read_image + block mean + normalise of load_elevation_data (data_loader.py:206-242) in one pass over the FILE: the
+    strips of the TIFF go through pinned staging buffers straight to the device (no decoded copy of the 8.5 GB map in
+    host memory) and the result is written to `cache_npy` in .npy format while it comes down.  ValueError if the file is
+    not laid out for that (tiff_info()["streamable"]).
+    """
+    info = tiff_info(filepath)
+    if info is None or not info["streamable"]:
+        raise ValueError(f"{filepath}: not an uncompressed 16-bit strip TIFF")
+    ds = int(downscale)
+    dev = device or get_device()
+    out = np.empty((info["height"] // ds, info["width"] // ds), dtype=np.float32)
+    rs = C.c_float()
+    _lib.check(dev.lib.mrtx_downscale_tiff_i16(dev.ctx, os.fsencode(filepath), ds, out.ctypes.data, C.byref(rs),
+                                               os.fsencode(cache_npy) if cache_npy else None))
+    return out, float(rs.value)
+
+
 def load_elevation_data(filepath: str, downscale: int) -> tuple[np.ndarray, float]:
     print(f"Loading elevation data from {filepath}...")
     base = f"{filepath}.ds{downscale}"
@@ -197,6 +226,27 @@ def load_elevation_data(filepath: str, downscale: int) -> tuple[np.ndarray, floa
     if not os.path.isfile(filepath):
         raise FileNotFoundError(
             f"Elevation file not found: {filepath}, and no cache of it downscaled by {downscale} beside it.")
+    info = tiff_info(filepath)
+    if info is not None and info["streamable"] and info["height"] % downscale == 0 and info["width"] % downscale == 0:
+        # the file's strips are the array: streamed to the device, the cache written as the result comes down
+        print(f"  Original dimensions: {(info['height'], info['width'])}")
+        try:
+            elevation, radius_scale = downscale_elevation_file(filepath, downscale, base + ".npy" if fingerprint is not None else None)
+        except _lib.MoonB200Error as e:
+            if fingerprint is None or "cache" not in str(e) and "write" not in str(e):
+                raise
+            print(f"Warning: could not write cache {base}.npy: {e}")        # a broken cache may only cost time
+            elevation, radius_scale = downscale_elevation_file(filepath, downscale, None)
+            fingerprint = None
+        print(f"  Downscaled dimensions: {elevation.shape}")
+        if fingerprint is not None:
+            try:
+                with open(base + ".json", "w", encoding="utf-8") as f:
+                    json.dump({**fingerprint, "radius_scale": radius_scale}, f)
+                print(f"  Cached to {base}.npy for faster next start")
+            except Exception as e:
+                print(f"Warning: could not write cache {base}.npy: {e}")
+        return elevation, radius_scale
     src = read_image(filepath)
     if src is None:
         raise ValueError(f"Failed to read elevation file: {filepath}")
