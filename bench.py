@@ -206,7 +206,9 @@ def build_scene(args, local_rank):
     bgr.free(); tex_dev.free()
 
     rt.set_param(min_accumulation_step=args.spp, max_accumulation_frames=args.spp)
-    rt.set_uint("path_seg_range", 2, 4)
+    # direct light: camera segment + light segment, the north_star path.  The reference's own setting
+    # (2, 4) adds two diffuse interreflection bounces; the line's "interreflection" block times that
+    rt.set_uint("path_seg_range", 2, 2)
     rt.set_float("scene_epsilon", scene.SCENE_EPSILON)
     rt.set_float("marching_step", scene.MARCHING_STEP)
     rt.set_float("marching_step_eps", scene.MARCHING_STEP_EPS)
@@ -397,14 +399,14 @@ def walked(c):
 
 
 def launches_per_frame(args):
-    """kernels of this library per frame: cull, then per sample chunk and pixel wave trace_kernel_fast + shadow_kernel +
-    trace_kernel_referee, fold, resolve"""
+    """kernels of this library per frame: cull, then per sample chunk and pixel wave trace_kernel_fast + shade_kernel +
+    shadow_kernel + trace_kernel_referee, fold, resolve"""
     chunks = (args.spp + 31) // 32
     per_chunk = min(args.spp, 32)
     npix = args.img_w * args.img_h
     cap = min(npix * per_chunk, 1 << 26)
     waves = -(-npix // (cap // per_chunk))
-    return 1 + 3 * chunks * waves + 1 + 1
+    return 1 + 4 * chunks * waves + 1 + 1
 
 
 # ------------------------------------------------------------------------------------------------
@@ -528,7 +530,8 @@ def run_frames(args):
     peak, peak_src = measured_peak()
     nl = max(1, kt["launches"])
     fast_ms, shadow_ms, ref_ms = kt["trace_kernel_fast"] / nl, kt["shadow_kernel"] / nl, kt["trace_kernel_referee"] / nl
-    path_ms = sum(kt[k] for k in ("cull_kernel", "beam_kernel", "trace_kernel_fast", "shadow_kernel", "trace_kernel_referee", "fold_kernel")) / nl
+    shade_ms = kt["shade_kernel"] / nl
+    path_ms = sum(kt[k] for k in ("cull_kernel", "beam_kernel", "trace_kernel_fast", "shade_kernel", "shadow_kernel", "trace_kernel_referee", "fold_kernel")) / nl
     nf = max(1, len(mine))
     prim_bytes = b_floor * c["primary_in_sphere"] / nf
     shad_bytes = b_floor * c["shadow_rays"] / nf
@@ -537,7 +540,7 @@ def run_frames(args):
     def gbs(nbytes, ms):
         return nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
     roofline = {
-        "bound": "hbm", "kernel": "trace_kernel_fast<int16, queue> (primary ray to the shaded hit; pushes the shadow ray)",
+        "bound": "hbm", "kernel": "trace_kernel_fast<int16, hit queue> (primary ray to its first hit, which goes to the hit queue)",
         "achieved": round(gbs(prim_bytes, fast_ms), 2), "peak": peak, "unit": "GB/s", "frac": round(gbs(prim_bytes, fast_ms) / peak, 5),
         "traffic": traffic[0] if traffic else None, "traffic_source": traffic[1] if traffic else None,
         "algorithmic_bytes_per_launch": int(prim_bytes), "bytes_per_ray": b_floor, "rays_per_launch": int(c["primary_in_sphere"] / nf),
@@ -545,8 +548,8 @@ def run_frames(args):
         "timing": "CUDA events on the launching stream at the kernel boundaries of every timed frame (mrtx_kernel_times)",
         "shadow_kernel": {"kernel_ms": round(shadow_ms, 3), "achieved": round(gbs(shad_bytes, shadow_ms), 2), "frac": round(gbs(shad_bytes, shadow_ms) / peak, 5),
                           "rays_per_launch": int(c["shadow_rays"] / nf), "algorithmic_bytes_per_launch": int(shad_bytes)},
-        "whole_path": {"kernels": "cull + trace_kernel_fast + shadow_kernel + trace_kernel_referee + fold (one mrtx_render)",
-                       "ms": round(path_ms, 3), "referee_ms": round(ref_ms, 3), "achieved": round(gbs(prim_bytes + shad_bytes, path_ms), 2),
+        "whole_path": {"kernels": "cull + trace_kernel_fast + shade_kernel + shadow_kernel + trace_kernel_referee + fold (one mrtx_render)",
+                       "ms": round(path_ms, 3), "referee_ms": round(ref_ms, 3), "shade_ms": round(shade_ms, 3), "achieved": round(gbs(prim_bytes + shad_bytes, path_ms), 2),
                        "frac": round(gbs(prim_bytes + shad_bytes, path_ms) / peak, 5)},
         "counted_bytes_per_ray": round(32.0 * (c["node_visits"] + 2 * c["patch_tests"]) / max(1.0, walked(c)), 1),
         "kernel_share_of_step": round(fast_ms * nf / ms_total, 4) if world == 1 else None,
@@ -586,6 +589,24 @@ def run_frames(args):
                                                     if args.delivery == "p2p" else "ncclSend / ncclRecv"),
                "api": "video.render_timelapse_delivered: B200OptiX.submit_frame(dst=0) / recv_frame / wait_frame, two frames in flight per rank"}
 
+    # ---- the reference's own path_seg_range (2, 4): two interreflection bounces, device-resident, N = 1 -----------------
+    bounce = None
+    if rank == 0 and world == 1 and not args.skip_e2e:
+        rt.set_uint("path_seg_range", 2, 4)
+        device_frame(frames[n_warm])
+        rt.counters(reset=True)
+        dev.synchronize()
+        dev.timer_start()
+        for f in frames[n_warm:n_warm + 2]:
+            device_frame(f)
+        bms = dev.timer_stop() / 2
+        cb = rt.counters()
+        bounce = {"path_seg_range": [2, 4], "ms_per_frame": round(bms, 3),
+                  "rays_walked_per_frame": int(walked(cb) // 2), "node_visits_per_frame": int(cb["node_visits"] // 2),
+                  "note": "camera ray + 2 diffuse bounces, direct light with a shadow ray at each of the 3 hits (SURVEY.md 8f N2); "
+                          "bounce rays are not in the ray counters, their node visits are"}
+        rt.set_uint("path_seg_range", 2, 2)
+
     # ---- oracle parity on the benchmarked frame + CPU baseline (rank 0, N = 1 only) -----------------------------------
     parity, cpu = None, None
     if rank == 0 and world == 1 and not args.skip_cpu:
@@ -609,6 +630,7 @@ def run_frames(args):
                                    f"{args.img_w}x{args.img_h}, {args.map_w}x{args.map_h} int16 synthetic LOLA map + "
                                    f"{args.color_w // COLOR_K}x{args.color_h // COLOR_K} colour texture, {args.spp} spp); frame f on rank f mod N",
                        "spp": args.spp, "camera": "default whole-disk, fov 4.2422 deg", "sun": "terminator sweep from phase 90 deg, 10 min per frame",
+                       "light": "direct (path_seg_range 2, 2: camera ray + sun shadow ray, the north_star path)",
                        "frames_per_step": FRAMES_PER_STEP, "frames_timed": n_timed,
                        "l2_hygiene": "inputs_larger_than_L2 (8.5 GB map + 2.9 GB pyramid)", "setup_s": round(t_setup, 1)},
             "rays": {"walked_per_frame": int(rays_all / n_timed), "primary_in_sphere_per_frame": int(D.sum(float(c["primary_in_sphere"])) / n_timed) if world == 1 else None,
@@ -617,7 +639,7 @@ def run_frames(args):
                      "samples_deferred_to_f64_referee_per_frame": defer["deferred_samples"] // nf,
                      "defer_reasons_primary": defer["primary_reasons"], "defer_reasons_shadow": defer["shadow_reasons"]},
             "frames_per_s": round(n_timed / (ms_total * 1e-3), 3), "ms_per_frame_per_gpu": round(ms_total / nf, 3),
-            "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "e2e": e2e,
+            "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "e2e": e2e, "interreflection": bounce,
             "gpu_launches": launches_per_frame(args) * n_timed, "clocks": clock_info, "downscale": downscale,
         }
         emit(line)

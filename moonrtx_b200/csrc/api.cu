@@ -62,7 +62,7 @@ int mrtx_create(int device, mrtx_ctx** out_ctx) {
     MRTX_CUDA(cudaEventCreate(&c->ev0));
     MRTX_CUDA(cudaEventCreate(&c->ev1));
     MRTX_CUDA(cudaMalloc(&c->d_max_bits, sizeof(unsigned)));
-    MRTX_CUDA(cudaMalloc(&c->d_work, 8 * sizeof(unsigned)));
+    MRTX_CUDA(cudaMalloc(&c->d_work, 16 * sizeof(unsigned)));
     MRTX_CUDA(cudaMalloc(&c->d_counters, 16 * sizeof(unsigned long long)));
     MRTX_CUDA(cudaMemset(c->d_counters, 0, 16 * sizeof(unsigned long long)));
     MRTX_CUDA(cudaMalloc(&c->d_defer_stats, 32 * sizeof(unsigned long long)));
@@ -111,7 +111,7 @@ int mrtx_destroy(mrtx_ctx* ctx) {
     cudaFree(ctx->d_counters);
     cudaFree(ctx->d_defer_stats);
     cudaFree(ctx->wave_buf);
-    cudaFree(ctx->sq_buf); cudaFree(ctx->hq_buf);
+    cudaFree(ctx->sq_buf); cudaFree(ctx->hq_buf); cudaFree(ctx->bq_buf[0]); cudaFree(ctx->bq_buf[1]);
     cudaFree(ctx->tube_seg); cudaFree(ctx->tube_tiles);
     if (ctx->prof_ev) { for (int i = 0; i < MRTX_PROF_MAX * MRTX_PROF_EVENTS; ++i) cudaEventDestroy(ctx->prof_ev[i]); free(ctx->prof_ev); }
     cudaFree(ctx->flush_buf);
@@ -821,7 +821,11 @@ int mrtx_set_float(mrtx_ctx* ctx, const char* name, double value) {
 
 int mrtx_set_uint(mrtx_ctx* ctx, const char* name, unsigned a, unsigned b) {
     MRTX_REQUIRE(ctx && name, "null argument");
-    if (!strcmp(name, "path_seg_range")) { /* direct light only: camera segment + light segment */ }
+    if (!strcmp(name, "path_seg_range")) {
+        // (min, max) ray segments of a path, moon_renderer.py:583: the camera ray and the light ray are two; every segment
+        // beyond is one diffuse interreflection bounce (traced to the maximum, no Russian roulette)
+        ctx->sp.n_bounce = b > 2u ? (b - 2u > 4u ? 4u : b - 2u) : 0u;
+    }
     else if (!strcmp(name, "jitter")) ctx->sp.jitter = a ? 1u : 0u;
     else if (!strcmp(name, "shadows")) ctx->sp.shadows = a ? 1u : 0u;
     else if (!strcmp(name, "debug_hits")) ctx->sp.debug_hits = a ? 1u : 0u;

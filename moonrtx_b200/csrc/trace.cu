@@ -302,26 +302,32 @@ trace_kernel_fast(const __grid_constant__ RenderArgs A) {
     if (lane == 0 && nd) atomicAdd(&A.defer_stats[0], (unsigned long long)nd);
 }
 
-// ---- shade_kernel: one thread per queued primary hit ----------------------------------------------------------------------
+// ---- shade_kernel: one thread per queued hit ---------------------------------------------------------------------------------
 // Dense and coherent (hits of a warp's pixels are neighbours in the queue): the primary ray evaluated again from (pixel,
 // sample), normal, albedo, Lambert term, light sample; the shadow ray set up to its first cell and appended to the shadow
 // queue with the radiance it carries.  A lit sample that needs no shadow ray (shadows off, or a ray that starts outside the
 // bounding sphere) is added to the pixel here.
-template <bool I16>
-__global__ void __launch_bounds__(256)
+// Interreflection (path_seg_range, moon_renderer.py:583).  BOUNCE = false: hits of camera rays.  With
+// A.n_bounce > 0 every hit also continues the path: a cosine-distributed direction about its normal (so the Lambert term
+// and the density cancel and the path's throughput is just multiplied by the albedo), pushed to the bounce queue; bounce_kernel
+// traces that queue to its first hits, which come back here with BOUNCE = true: ray and throughput are read from the bounce
+// ray's queue entry, the direct light at the new hit is weighted with the throughput and goes through the same shadow queue.
+template <bool I16, bool BOUNCE>
+__global__ void __launch_bounds__(256, 2)
 shade_kernel(const __grid_constant__ RenderArgs A) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     const unsigned n_hits = A.work_counter[7];                          // slots (32 per warp that had a hit), some empty
-    const unsigned n_round = n_hits;
+    const unsigned n_round = (n_hits + 31u) & ~31u;                     // whole warps stay in the loop (ballots)
+    const bool spawn = A.depth < A.n_bounce;
     RayStats rs = {0u, 0u, 0u, 0u, 0u};
     const Counters cnt = {0u, 0u, 0u};
     for (unsigned it = blockIdx.x * blockDim.x + threadIdx.x; it < n_round; it += gridDim.x * blockDim.x) {
-        float3 lit = make_float3(0.f, 0.f, 0.f);
-        bool push = false;
-        Ray64 S;
-        Walk sw;
+        float3 lit = make_float3(0.f, 0.f, 0.f), thr = make_float3(1.f, 1.f, 1.f);
+        bool push = false, bpush = false;
+        Ray64 S, B;
+        Walk sw, bw;
         uint32_t pixel = 0;
         unsigned k = 0;
         if (it < n_hits) {
@@ -337,12 +343,46 @@ shade_kernel(const __grid_constant__ RenderArgs A) {
             const int x = (int)(pixel % (unsigned)A.width), y = (int)(pixel / (unsigned)A.width);
             const unsigned sm = A.sample0 + k;
             Ray64 R;
-            primary_ray_fast(A, x, y, pixel, sm, R);
-            if (tube_tile_count(A, x, y) && tube_nearest(A, x, y, pixel, sm, fh.s, lit)) {
+            if (BOUNCE) {
+                load_ray_rec(A.bq_in_rays + b.w, R);
+                R.oo = R.ox * R.ox + R.oy * R.oy + R.oz * R.oz; R.od = R.ox * R.dx + R.oy * R.dy + R.oz * R.dz;
+                const uint4 ax = __ldg(A.bq_in_aux + b.w);
+                thr = make_float3(__uint_as_float(ax.x), __uint_as_float(ax.y), __uint_as_float(ax.z));
+            } else primary_ray_fast(A, x, y, pixel, sm, R);
+            ShadeAux aux;
+            if (!BOUNCE && tube_tile_count(A, x, y) && tube_nearest(A, x, y, pixel, sm, fh.s, lit)) {
                 // an overlay tube in front of the surface: its flat colour is the sample (added below)
-            } else if (shade_fast(A, R, fh, x, y, pixel, sm, lit, S)) {
-                ++rs.shadow;
-                push = walk_begin(A.hf, A.sp.radius, S, 0.0, A.sq_level, sw);
+            } else {
+                const unsigned dim0 = 2u + 4u * (unsigned)A.depth;
+                if (shade_fast(A, R, fh, x, y, pixel, sm, lit, S, dim0, !BOUNCE, spawn ? &aux : nullptr)) {
+                    ++rs.shadow;
+                    push = walk_begin(A.hf, A.sp.radius, S, 0.0, A.sq_level, sw);
+                }
+                lit.x *= thr.x; lit.y *= thr.y; lit.z *= thr.z;
+                if (spawn) {
+                    thr.x *= aux.alb.x; thr.y *= aux.alb.y; thr.z *= aux.alb.z;
+                    if (fmaxf(thr.x, fmaxf(thr.y, thr.z)) > 0.0f) {
+                        // cosine-distributed direction about the normal (branchless ONB, Duff et al. 2017)
+                        const float u1 = (float)rnd(pixel, sm, dim0 + 2u), u2 = (float)rnd(pixel, sm, dim0 + 3u);
+                        const float rr = sqrtf(u1), cz = sqrtf(fmaxf(1.0f - u1, 0.0f));
+                        float st, ct;
+                        sincospif(2.0f * u2, &st, &ct);
+                        const float nx = aux.nx, ny = aux.ny, nz = aux.nz;
+                        const float sg = nz >= 0.0f ? 1.0f : -1.0f, aa = -1.0f / (sg + nz), bb = nx * ny * aa;
+                        const float b1x = 1.0f + sg * nx * nx * aa, b1y = sg * bb, b1z = -sg * nx;
+                        const float b2x = bb, b2y = sg + ny * ny * aa, b2z = -ny;
+                        const float lx = rr * ct, ly = rr * st;
+                        double dx = (double)(lx * b1x + ly * b2x + cz * nx), dy = (double)(lx * b1y + ly * b2y + cz * ny), dz = (double)(lx * b1z + ly * b2z + cz * nz);
+                        const double dn = d_rsqrt(dx * dx + dy * dy + dz * dz);
+                        dx *= dn; dy *= dn; dz *= dn;
+                        const double eps = A.sp.scene_epsilon;
+                        B.ox = fma(eps, (double)nx, aux.px); B.oy = fma(eps, (double)ny, aux.py); B.oz = fma(eps, (double)nz, aux.pz);
+                        B.dx = dx; B.dy = dy; B.dz = dz;
+                        B.oo = B.ox * B.ox + B.oy * B.oy + B.oz * B.oz;
+                        B.od = B.ox * B.dx + B.oy * B.dy + B.oz * B.dz;
+                        bpush = walk_begin(A.hf, A.sp.radius, B, 0.0, A.sq_level, bw);
+                    }
+                }
             }
             }
         }
@@ -358,8 +398,27 @@ shade_kernel(const __grid_constant__ RenderArgs A) {
             }
         }
         if (!push) accfix_add(A.accfix, pixel, lit);                     // (adds nothing where lit is zero)
+        if (spawn) {
+            const unsigned bm = __ballot_sync(FULL, bpush);
+            if (bm) {
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(&A.work_counter[10], (unsigned)__popc(bm));
+                base = __shfl_sync(FULL, base, 0);
+                if (bpush) {
+                    const unsigned j = base + (unsigned)__popc(bm & lt);
+                    store_ray_rec(A.bq_out_rays + j, B, bw, true);
+                    A.bq_out_aux[j] = make_uint4(__float_as_uint(thr.x), __float_as_uint(thr.y), __float_as_uint(thr.z), pixel | (k << 27));
+                }
+            }
+        }
     }
     flush_counters(A, rs, cnt, lane);
+}
+
+// the bounce rays just written become the next stage's input: counters [8] <- [10], [9] = [10] = 0; hit and shadow queue emptied
+__global__ void queue_flip_kernel(unsigned* wc) {
+    wc[8] = wc[10]; wc[9] = 0u; wc[10] = 0u;
+    wc[5] = 0u; wc[6] = 0u; wc[7] = 0u;
 }
 
 // ---- shadow queue: streaming walk with lane refill -------------------------------------------------------------------
@@ -377,7 +436,11 @@ shade_kernel(const __grid_constant__ RenderArgs A) {
 #endif
 enum { SQ_EMPTY = 0, SQ_WALK = 1, SQ_CAND = 2 };
 
-template <bool I16>
+// CLOSEST (bounce_kernel): the same streaming walk over the bounce queue, but the ray's FIRST crossing is
+// wanted (cells are walked front to back, so that is the first patch that reports one): it goes to the hit queue with the
+// index of its ray.  A bounce ray the filter cannot certify is dropped (counted in defer_stats[30]): the float64 referee
+// re-traces camera samples, and a 2e-5 share of a path's second-order light is far below one 8-bit step.
+template <bool I16, bool CLOSEST>
 __global__ void __launch_bounds__(128, MRTX_SQ_MINBLOCKS)
 shadow_kernel(const __grid_constant__ RenderArgs A) {
     __shared__ unsigned s_off[2 * MRTX_MAX_LEVELS];          // level offsets (HeightField::off) where a per-lane index is cheap
@@ -386,11 +449,14 @@ shadow_kernel(const __grid_constant__ RenderArgs A) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
-    const unsigned n_items = A.work_counter[5];
-    unsigned* const queue = A.work_counter + 6;
+    const unsigned n_items = A.work_counter[CLOSEST ? 8 : 5];
+    unsigned* const queue = A.work_counter + (CLOSEST ? 9 : 6);
+    const RayRec* const q_rays = CLOSEST ? A.bq_in_rays : A.sq_rays;
+    const uint4* const q_aux = CLOSEST ? A.bq_in_aux : A.sq_aux;
     const float Rf = A.K.R;
     Counters cnt = {0u, 0u, 0u};
     unsigned n_defer = 0, n_occluded = 0;
+    FastHit fh;
 
     int mode = SQ_EMPTY, face = 4;
     int ceil_next = 0x7fffffff;
@@ -414,7 +480,7 @@ shadow_kernel(const __grid_constant__ RenderArgs A) {
             if (base + n >= n_items) exhausted = true;
             const unsigned idx = base + (unsigned)__popc(m_empty & lt);
             if (mode == SQ_EMPTY && idx < n_items) {
-                const RayRec* rec = A.sq_rays + idx;
+                const RayRec* rec = q_rays + idx;
                 const double2 tail = __ldg((const double2*)rec + 3);
                 const float smax = __int_as_float(__double2loint(tail.y));
                 const unsigned cell = (unsigned)__double2hiint(tail.y);
@@ -436,11 +502,10 @@ shadow_kernel(const __grid_constant__ RenderArgs A) {
             // ---- patch test (any crossing occludes)
             if (mode == SQ_CAND) {
                 ++cnt.tests;
-                const RayRec* rec = A.sq_rays + ridx;
+                const RayRec* rec = q_rays + ridx;
                 Ray64 R;
                 load_ray_rec(rec, R);
-                FastHit fh;
-                status = fast_test<I16>(A.hf, A.K, R, st.s_in, 0.0, st.s, sx, st.smax, P, true, fh);
+                status = fast_test<I16>(A.hf, A.K, R, st.s_in, 0.0, st.s, sx, st.smax, P, !CLOSEST, fh);
                 if (status == FT_MISS && walk_advance(A.hf, st, sx, face)) mode = SQ_WALK;
                 else finished = true;
             }
@@ -457,9 +522,29 @@ shadow_kernel(const __grid_constant__ RenderArgs A) {
                 else if (r == TR_CANDIDATE) mode = SQ_CAND;
             }
         }
-        if (finished) {
+        if (CLOSEST) {
+            // first hits of bounce rays -> hit queue (one reservation per warp and step)
+            const bool hitp = finished && (status & 3) == FT_HIT;
+            const unsigned hm = __ballot_sync(FULL, hitp);
+            if (hm) {
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(&A.work_counter[7], (unsigned)__popc(hm));
+                base = __shfl_sync(FULL, base, 0);
+                if (hitp) {
+                    const uint4 aux = __ldg(q_aux + ridx);
+                    uint4* q = (uint4*)(A.hq + base + (unsigned)__popc(hm & lt));
+                    __stcs(q, make_uint4((unsigned)__double2loint(fh.s), (unsigned)__double2hiint(fh.s), __float_as_uint(fh.fc), __float_as_uint(fh.fr)));
+                    __stcs(q + 1, make_uint4((unsigned)fh.r0, (unsigned)fh.c0, aux.w, ridx));
+                    __stcs(q + 2, make_uint4(__float_as_uint(fh.d00), __float_as_uint(fh.d01), __float_as_uint(fh.d10), __float_as_uint(fh.d11)));
+                }
+            }
+            if (finished) {
+                mode = SQ_EMPTY;
+                if ((status & 3) == FT_DEFER) { atomicAdd(&A.defer_stats[30], 1ull); }
+            }
+        } else if (finished) {
             mode = SQ_EMPTY;
-            const uint4 aux = __ldg(A.sq_aux + ridx);
+            const uint4 aux = __ldg(q_aux + ridx);
             const uint32_t pixel = aux.w & 0x7ffffffu;
             if (status == FT_MISS) {
                 accfix_add(A.accfix, pixel, make_float3(__uint_as_float(aux.x), __uint_as_float(aux.y), __uint_as_float(aux.z)));
@@ -534,7 +619,14 @@ __global__ void resolve_kernel(const float4* __restrict__ accum, const uchar4* _
 // shadow queue: ray records and their aux entries in one allocation
 // hit queue: a warp takes 32 slots per round of 2^g samples, so a sample count that is no power of two leaves part of the
 // last round's slots empty
-static int ensure_queues(mrtx_ctx* ctx, size_t items, size_t hit_slots) {
+static int ensure_queues(mrtx_ctx* ctx, size_t items, size_t hit_slots, bool bounces) {
+    if (bounces && ctx->bq_cap < items) {
+        MRTX_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (int q = 0; q < 2; ++q) { cudaFree(ctx->bq_buf[q]); ctx->bq_buf[q] = nullptr; }
+        ctx->bq_cap = 0;
+        for (int q = 0; q < 2; ++q) MRTX_CUDA(cudaMalloc(&ctx->bq_buf[q], items * (sizeof(RayRec) + sizeof(uint4))));
+        ctx->bq_cap = items;
+    }
     if (ctx->sq_cap < items) {
         MRTX_CUDA(cudaStreamSynchronize(ctx->stream));
         cudaFree(ctx->sq_buf);
@@ -596,12 +688,14 @@ static int launch_trace_t(mrtx_ctx* ctx, RenderArgs& A, unsigned s0, unsigned ns
     // (the hit-queue form also serves a scene without shadow rays: shade_kernel then adds the radiance itself)
     const bool queue = ctx->sp.shadow_queue >= 2u || (ctx->sp.shadow_queue != 0 && ctx->sp.shadows != 0);
     const size_t SQ_MAX = (size_t)1 << 26;                  // 64 Mi queued rays = 5 GiB; larger launches run in waves of pixels
-    int sq_blocks = 0;
+    int sq_blocks = 0, n_bounce = 0;
+    A.depth = 0; A.n_bounce = 0;
     if (queue) {
         const size_t chunk = ns < 32u ? ns : 32u;
         const size_t items = std::min<size_t>((size_t)npix * chunk, SQ_MAX);
         const bool pow2 = (chunk & (chunk - 1)) == 0 && (ns <= 32u || ns % 32u == 0);
-        rc = ensure_queues(ctx, items, ctx->sp.shadow_queue >= 2u ? items * (pow2 ? 1 : 2) + 2048 : 0);
+        n_bounce = ctx->sp.shadow_queue >= 2u ? (int)ctx->sp.n_bounce : 0;       // (interreflection runs through the queues)
+        rc = ensure_queues(ctx, items, ctx->sp.shadow_queue >= 2u ? items * (pow2 ? 1 : 2) + 2048 : 0, n_bounce > 0);
         if (rc) return rc;
         A.sq_rays = (RayRec*)ctx->sq_buf;
         A.sq_aux = (uint4*)((char*)ctx->sq_buf + ctx->sq_cap * sizeof(RayRec));
@@ -612,7 +706,7 @@ static int launch_trace_t(mrtx_ctx* ctx, RenderArgs& A, unsigned s0, unsigned ns
         while ((ctx->hf.W >> lvl) > 65536 && lvl < ctx->hf.top) ++lvl;
         A.sq_level = std::min(lvl, ctx->hf.top);
         int per_sm = 0;
-        MRTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shadow_kernel<I16>, 128, 0));
+        MRTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shadow_kernel<I16, false>, 128, 0));
         if (ctx->sp.blocks_per_sm && (int)ctx->sp.blocks_per_sm < per_sm) per_sm = (int)ctx->sp.blocks_per_sm;
         sq_blocks = ctx->sm_count * (per_sm < 1 ? 1 : per_sm);
     }
@@ -636,14 +730,27 @@ static int launch_trace_t(mrtx_ctx* ctx, RenderArgs& A, unsigned s0, unsigned ns
             rc = hitq ? launch_fast<I16, 2>(ctx, A, A.wave_np) : queue ? launch_fast<I16, 1>(ctx, A, A.wave_np) : launch_fast<I16, 0>(ctx, A, A.wave_np);
             if (rc) return rc;
             if (first) prof_mark(ctx, 3);
-            if (hitq) shade_kernel<I16><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(A);
+            A.depth = 0; A.n_bounce = n_bounce;
+            if (n_bounce) {
+                A.bq_out_rays = (RayRec*)ctx->bq_buf[0]; A.bq_out_aux = (uint4*)((char*)ctx->bq_buf[0] + ctx->bq_cap * sizeof(RayRec));
+                MRTX_CUDA(cudaMemsetAsync(A.work_counter + 8, 0, 3 * sizeof(unsigned), ctx->stream));
+            }
+            if (hitq) shade_kernel<I16, false><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(A);
             if (first) prof_mark(ctx, 4);
-            if (queue) shadow_kernel<I16><<<sq_blocks, 128, 0, ctx->stream>>>(A);
-#ifdef MRTX_DIAG_SHADOW_TWICE
-            if (first) prof_mark(ctx, 4);
-            MRTX_CUDA(cudaMemsetAsync(A.work_counter + 6, 0, sizeof(unsigned), ctx->stream));
-            if (queue) shadow_kernel<I16><<<sq_blocks, 128, 0, ctx->stream>>>(A);
-#endif
+            if (queue) shadow_kernel<I16, false><<<sq_blocks, 128, 0, ctx->stream>>>(A);
+            // interreflection: bounce rays -> first hits -> shading (direct light weighted with the path's throughput, next
+            // bounce) -> shadow rays, once per bounce; the two bounce queues swap roles
+            for (int d = 1; d <= n_bounce; ++d) {
+                queue_flip_kernel<<<1, 1, 0, ctx->stream>>>(A.work_counter);
+                A.depth = d;
+                void* in = ctx->bq_buf[(d - 1) & 1]; void* out = ctx->bq_buf[d & 1];
+                A.bq_in_rays = (RayRec*)in; A.bq_in_aux = (uint4*)((char*)in + ctx->bq_cap * sizeof(RayRec));
+                A.bq_out_rays = (RayRec*)out; A.bq_out_aux = (uint4*)((char*)out + ctx->bq_cap * sizeof(RayRec));
+                shadow_kernel<I16, true><<<sq_blocks, 128, 0, ctx->stream>>>(A);         // bounce_kernel: first hits -> hit queue
+                shade_kernel<I16, true><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(A);
+                shadow_kernel<I16, false><<<sq_blocks, 128, 0, ctx->stream>>>(A);
+            }
+            A.depth = 0;
             if (first) prof_mark(ctx, 5);
             trace_kernel_referee<I16, false><<<ctx->sm_count * 8, 64, 0, ctx->stream>>>(A);
             if (first) prof_mark(ctx, 6);

@@ -79,6 +79,11 @@ struct RenderArgs {
     struct RayRec* sq_rays; uint4* sq_aux; unsigned sq_cap; int sq_level;
     // overlay tubes (mrtx_set_tubes): segments, per-tile lists (see mrtx_ctx::tube_tiles); n_tubes = 0: none
     const float4* tubes; unsigned n_tubes; const unsigned* tube_tiles; int tube_tx;
+    // interreflection (path_seg_range): bounce rays in two queues of the shadow queue's layout - bq_in is
+    // traced to its first hit by bounce_kernel (work_counter[8] rays, cursor [9]), bq_out is filled by shade_kernel
+    // ([10] rays); their aux entries carry the path's throughput.  depth: 0 = camera hits, d = hits of the d-th bounce
+    struct RayRec* bq_in_rays; uint4* bq_in_aux; struct RayRec* bq_out_rays; uint4* bq_out_aux;
+    int depth, n_bounce;
     // hit queue (shadow_queue = 2): primary hits pushed by trace_kernel_fast (work_counter[7] of them), shaded by shade_kernel
     struct HitQRec* hq;
     unsigned long long* accfix;
@@ -101,7 +106,7 @@ __device__ __forceinline__ void store_ray_rec(RayRec* dst, const Ray64& R, const
 }
 // record of the hit queue: what fast_test() found (FastHit) + pixel | sample bit << 27.  The primary ray itself is not
 // stored: it is a function of (pixel, sample) alone and shade_kernel evaluates it again, bit for bit.
-struct HitQRec { double s; float fc, fr; int r0, c0; unsigned pix_k, pad; float d00, d01, d10, d11; };   // 48 B
+struct HitQRec { double s; float fc, fr; int r0, c0; unsigned pix_k, ridx; float d00, d01, d10, d11; };   // 48 B; ridx: the bounce ray's queue entry
 static_assert(sizeof(HitQRec) == 48, "record layout");
 
 __device__ __forceinline__ void load_ray_rec(const RayRec* src, Ray64& R) {
@@ -522,8 +527,14 @@ __device__ __noinline__ void write_hit64(const RenderArgs& A, const Ray64& R, co
 #ifndef MRTX_SHADE_ATTR
 #define MRTX_SHADE_ATTR __forceinline__
 #endif
+// what the interreflection pass needs of a shaded hit: where it is, its normal and its albedo
+struct ShadeAux { double px, py, pz; float nx, ny, nz; float3 alb; };
+
+// dim0: first random dimension of the light sample (2 at the camera hit, 2 + 4 d at the d-th bounce); primary: the hit
+// of a camera ray (the only one that goes to the hit buffer)
 __device__ MRTX_SHADE_ATTR bool shade_fast(const RenderArgs& A, const Ray64& R, const FastHit& h, int x, int y,
-                                           uint32_t pixel, unsigned sm, float3& lit, Ray64& S) {
+                                           uint32_t pixel, unsigned sm, float3& lit, Ray64& S,
+                                           unsigned dim0 = 2u, bool primary = true, ShadeAux* aux = nullptr) {
     const SceneParams& sp = A.sp;
     const double px = fma(h.s, R.dx, R.ox), py = fma(h.s, R.dy, R.oy), pz = fma(h.s, R.dz, R.oz);
     const float fx = (float)px, fy = (float)py, fz = (float)pz;
@@ -552,24 +563,25 @@ __device__ MRTX_SHADE_ATTR bool shade_fast(const RenderArgs& A, const Ray64& R, 
         const float sg = cz >= 0.0f ? 1.0f : -1.0f, a = -1.0f / (sg + cz), b = cx * cy * a;
         const float b1x = 1.0f + sg * cx * cx * a, b1y = sg * b, b1z = -sg * cx;
         const float b2x = b, b2y = sg + cy * cy * a, b2z = -cy;
-        const float rr = (float)sp.light_radius * sqrtf((float)rnd(pixel, sm, 2));
+        const float rr = (float)sp.light_radius * sqrtf((float)rnd(pixel, sm, dim0));
         float st, ct;
-        sincospif(2.0f * (float)rnd(pixel, sm, 3), &st, &ct);
+        sincospif(2.0f * (float)rnd(pixel, sm, dim0 + 1u), &st, &ct);
         tx += (double)(rr * (ct * b1x + st * b2x)); ty += (double)(rr * (ct * b1y + st * b2y)); tz += (double)(rr * (ct * b1z + st * b2z));
     }
     const double ln = d_rsqrt(tx * tx + ty * ty + tz * tz);
     const double lx = tx * ln, ly = ty * ln, lz = tz * ln;
     const float cosl = nx * (float)lx + ny * (float)ly + nz * (float)lz;
-    if (sm == A.hit_sample && A.hit) {
+    if (primary && sm == A.hit_sample && A.hit) {
         // scene = pos + R^T p_body
         const float hx = (float)(sp.pos[0] + sp.ex[0] * px + sp.ey[0] * py + sp.ez[0] * pz);
         const float hy = (float)(sp.pos[1] + sp.ex[1] * px + sp.ey[1] * py + sp.ez[1] * pz);
         const float hz = (float)(sp.pos[2] + sp.ex[2] * px + sp.ey[2] * py + sp.ez[2] * pz);
         A.hit[(size_t)y * A.width + x] = make_float4(hx, hy, hz, (float)h.s);
     }
-    if (A.hit64) write_hit64(A, R, h, x, y);
+    if (primary && A.hit64) write_hit64(A, R, h, x, y);
     lit = make_float3(0.f, 0.f, 0.f);
-    if (!(cosl > 0.0f)) return false;
+    if (aux) { aux->px = px; aux->py = py; aux->pz = pz; aux->nx = nx; aux->ny = ny; aux->nz = nz; aux->alb = make_float3(0.f, 0.f, 0.f); }
+    if (!(cosl > 0.0f) && !aux) return false;
     float3 alb = make_float3(1.0f, 1.0f, 1.0f);
     if (A.tex.data) {
         const int w = A.tex.W, hgt = A.tex.H;
@@ -590,6 +602,8 @@ __device__ MRTX_SHADE_ATTR bool shade_fast(const RenderArgs& A, const Ray64& R, 
                           (ta.y * w00 + tb.y * w01 + tc.y * w10 + td.y * w11) * sc,
                           (ta.z * w00 + tb.z * w01 + tc.z * w10 + td.z * w11) * sc);
     }
+    if (aux) aux->alb = alb;
+    if (!(cosl > 0.0f)) return false;
     const float q = (float)(sp.light_radius * idist);
     const float E = (float)sp.light_radiance * q * q * cosl;
     lit = make_float3(alb.x * E, alb.y * E, alb.z * E);
@@ -852,7 +866,7 @@ static void fill_render_args(mrtx_ctx* ctx, int x0, int y0, int x1, int y1, unsi
 }
 
 static int launch_cull(mrtx_ctx* ctx, const RenderArgs& A) {
-    MRTX_CUDA(cudaMemsetAsync(A.work_counter, 0, 8 * sizeof(unsigned), ctx->stream));
+    MRTX_CUDA(cudaMemsetAsync(A.work_counter, 0, 16 * sizeof(unsigned), ctx->stream));
     const unsigned tiles_x = (unsigned)(A.x1 - A.x0 + 7) / 8u, tiles_y = (unsigned)(A.y1 - A.y0 + 3) / 4u;
     const unsigned total = tiles_x * tiles_y * 32u;
     cull_kernel<<<(total + 255u) / 256u, 256, 0, ctx->stream>>>(A);

@@ -69,6 +69,9 @@ typedef struct {
      * of a camera sample that meets the tube before the surface), never an occluder of the sun (renderer_labels.py:133-139) */
     const float* tubes;
     int n_tubes;
+    /* diffuse interreflection bounces after the camera hit (rt.set_uint("path_seg_range", 2, 4), moon_renderer.py:583:
+     * max segments - 2; 0 = direct light only) */
+    int n_bounce;
 } orc_scene;
 
 /* ------------------------------------------------------------------------------ */
@@ -417,6 +420,40 @@ static void miss_radiance(const orc_scene* S, const double* o, const double* d, 
     }
 }
 
+/* direct light of the sun at a hit (Lambert, one sample of the sun's disk, one shadow ray): rgb = albedo * E * visibility */
+static void direct_light(const orc_scene* S, const orc_hit* h, const double* Lb, uint32_t pixel, unsigned sm, unsigned dim0,
+                         double* rgb, double* alb, long* shadow_cells) {
+    rgb[0] = rgb[1] = rgb[2] = 0.0;
+    sample_albedo(S, h->lon, h->lat, alb);
+    double tp[3] = {Lb[0] - h->p[0], Lb[1] - h->p[1], Lb[2] - h->p[2]};
+    const double dist = sqrt(dot3(tp, tp));
+    double lc[3] = {tp[0] / dist, tp[1] / dist, tp[2] / dist};
+    double target[3] = {Lb[0], Lb[1], Lb[2]};
+    if (S->jitter && S->light_radius > 0.0) {
+        /* uniform point on the disk facing the hit (branchless ONB, Duff et al. 2017) */
+        const double sg = lc[2] >= 0.0 ? 1.0 : -1.0, a = -1.0 / (sg + lc[2]), bq = lc[0] * lc[1] * a;
+        const double b1[3] = {1.0 + sg * lc[0] * lc[0] * a, sg * bq, -sg * lc[0]};
+        const double b2[3] = {bq, sg + lc[1] * lc[1] * a, -lc[1]};
+        const double rr = S->light_radius * sqrt(rnd(pixel, sm, dim0)), th = 2.0 * PI * rnd(pixel, sm, dim0 + 1u);
+        for (int q = 0; q < 3; ++q) target[q] += rr * (cos(th) * b1[q] + sin(th) * b2[q]);
+    }
+    double l[3] = {target[0] - h->p[0], target[1] - h->p[1], target[2] - h->p[2]};
+    const double ln = sqrt(dot3(l, l));
+    for (int q = 0; q < 3; ++q) l[q] /= ln;
+    const double cosl = dot3(h->n, l);
+    if (!(cosl > 0.0)) return;
+    double vis = 1.0;
+    if (S->shadows) {
+        double so[3] = {h->p[0] + S->scene_epsilon * h->n[0], h->p[1] + S->scene_epsilon * h->n[1], h->p[2] + S->scene_epsilon * h->n[2]};
+        orc_hit sh;
+        trace(S, so, l, 0.0, &sh);
+        *shadow_cells = sh.cells;
+        if (sh.hit) vis = 0.0;
+    }
+    const double E = S->light_radiance * (S->light_radius / dist) * (S->light_radius / dist) * cosl * vis;
+    for (int q = 0; q < 3; ++q) rgb[q] = alb[q] * E;
+}
+
 /* first intersection of the ray o + t d (|d| = 1) with the capsule (a, b, r): negative = none.  Brute force over all tubes. */
 static double capsule_hit(const double* o, const double* d, const float* seg) {
     const double a[3] = {seg[0], seg[1], seg[2]}, r = seg[3];
@@ -496,36 +533,33 @@ long orc_render(const orc_scene* S, int x0, int y0, int x1, int y1, int stride,
                 if (tube >= 0) {
                     for (int q = 0; q < 3; ++q) rgb[q] = S->tubes[(size_t)tube * 12 + 8 + q];
                 } else if (h.hit) {
-                    double tp[3] = {Lb[0] - h.p[0], Lb[1] - h.p[1], Lb[2] - h.p[2]};
-                    const double dist = sqrt(dot3(tp, tp));
-                    double lc[3] = {tp[0] / dist, tp[1] / dist, tp[2] / dist};
-                    double target[3] = {Lb[0], Lb[1], Lb[2]};
-                    if (S->jitter && S->light_radius > 0.0) {
-                        /* uniform point on the disk facing the hit (branchless ONB, Duff et al. 2017) */
-                        const double sg = lc[2] >= 0.0 ? 1.0 : -1.0, a = -1.0 / (sg + lc[2]), bq = lc[0] * lc[1] * a;
-                        const double b1[3] = {1.0 + sg * lc[0] * lc[0] * a, sg * bq, -sg * lc[0]};
-                        const double b2[3] = {bq, sg + lc[1] * lc[1] * a, -lc[1]};
-                        const double rr = S->light_radius * sqrt(rnd(pixel, sm, 2)), th = 2.0 * PI * rnd(pixel, sm, 3);
-                        for (int q = 0; q < 3; ++q) target[q] += rr * (cos(th) * b1[q] + sin(th) * b2[q]);
-                    }
-                    double l[3] = {target[0] - h.p[0], target[1] - h.p[1], target[2] - h.p[2]};
-                    const double ln = sqrt(dot3(l, l));
-                    for (int q = 0; q < 3; ++q) l[q] /= ln;
-                    const double cosl = dot3(h.n, l);
-                    if (cosl > 0.0) {
-                        double vis = 1.0;
-                        if (S->shadows) {
-                            double so[3] = {h.p[0] + S->scene_epsilon * h.n[0], h.p[1] + S->scene_epsilon * h.n[1],
-                                            h.p[2] + S->scene_epsilon * h.n[2]};
-                            orc_hit sh;
-                            trace(S, so, l, 0.0, &sh);
-                            shadow_cells = sh.cells;
-                            if (sh.hit) vis = 0.0;
-                        }
-                        double alb[3];
-                        sample_albedo(S, h.lon, h.lat, alb);
-                        const double E = S->light_radiance * (S->light_radius / dist) * (S->light_radius / dist) * cosl * vis;
-                        for (int q = 0; q < 3; ++q) rgb[q] = alb[q] * E;
+                    /* the path: direct light at every hit, weighted with the product of the albedos before it; the next
+                     * hit lies in a cosine-distributed direction about the normal (density and Lambert term cancel) */
+                    double thr[3] = {1.0, 1.0, 1.0};
+                    orc_hit cur = h;
+                    for (int depth = 0; ; ++depth) {
+                        double direct[3], alb[3];
+                        long sc = 0;
+                        direct_light(S, &cur, Lb, pixel, sm, 2u + 4u * (unsigned)depth, direct, alb, &sc);
+                        if (depth == 0) shadow_cells = sc;
+                        for (int q = 0; q < 3; ++q) rgb[q] += thr[q] * direct[q];
+                        if (depth >= S->n_bounce) break;
+                        for (int q = 0; q < 3; ++q) thr[q] *= alb[q];
+                        if (!(thr[0] > 0.0 || thr[1] > 0.0 || thr[2] > 0.0)) break;
+                        const double u1 = rnd(pixel, sm, 4u + 4u * (unsigned)depth), u2 = rnd(pixel, sm, 5u + 4u * (unsigned)depth);
+                        const double rr = sqrt(u1), cz = sqrt(1.0 - u1 > 0.0 ? 1.0 - u1 : 0.0), th = 2.0 * PI * u2;
+                        const double* n = cur.n;
+                        const double sg = n[2] >= 0.0 ? 1.0 : -1.0, a = -1.0 / (sg + n[2]), bq = n[0] * n[1] * a;
+                        const double b1[3] = {1.0 + sg * n[0] * n[0] * a, sg * bq, -sg * n[0]};
+                        const double b2[3] = {bq, sg + n[1] * n[1] * a, -n[1]};
+                        double bd[3], bo[3];
+                        for (int q = 0; q < 3; ++q) bd[q] = rr * cos(th) * b1[q] + rr * sin(th) * b2[q] + cz * n[q];
+                        const double bn = sqrt(dot3(bd, bd));
+                        for (int q = 0; q < 3; ++q) { bd[q] /= bn; bo[q] = cur.p[q] + S->scene_epsilon * n[q]; }
+                        orc_hit nx;
+                        trace(S, bo, bd, 0.0, &nx);
+                        if (!nx.hit) break;
+                        cur = nx;
                     }
                 } else {
                     miss_radiance(S, S->eye, dir, rgb);

@@ -39,6 +39,7 @@ class _Scene(C.Structure):
         ("sun_disk_pos", _D3), ("sun_disk_radius", C.c_double), ("sun_disk_color", _D3),
         ("env", C.c_void_p), ("env_w", C.c_int), ("env_h", C.c_int),
         ("tubes", C.c_void_p), ("n_tubes", C.c_int),
+        ("n_bounce", C.c_int),
     ]
 
 
@@ -89,7 +90,7 @@ class OracleScene:
                  eye=(0, -300, 0), target=(0, 0, 0), up=(0, 0, 1), fov=4.242192793,
                  light_pos=(21460.0, 0.0, 0.0), light_radius=100.0, light_radiance=80.0 * (2146.0 / 100.0) ** 2,
                  scene_epsilon=1.0e-4, jitter=False, shadows=True, texture=None,
-                 exposure=0.9, gamma=2.2, background=None, sun_disk=None, tubes=None):
+                 exposure=0.9, gamma=2.2, background=None, sun_disk=None, tubes=None, path_seg_range=(2, 2)):
         self.s = _Scene()
         s = self.s
         self.elevation = np.ascontiguousarray(elevation)
@@ -146,6 +147,8 @@ class OracleScene:
             col = np.broadcast_to(np.asarray(col, dtype=np.float64).reshape(-1), (3,)) if np.size(col) in (1, 3) else np.asarray(col, dtype=np.float64)[:3]
             s.sun_disk_color = _D3(*[float(x) for x in col])
         self.set_tubes(tubes)
+        # rt.set_uint("path_seg_range", min, max): camera ray + light ray are two segments, every one beyond is a bounce
+        s.n_bounce = max(0, min(int(path_seg_range[1]) - 2, 4))
 
     def set_tubes(self, tubes):
         """overlay tubes: float32 (n, 12) = a.xyz, r, b.xyz, -, colour.rgb, - in scene space (B200OptiX._tube_segments())"""

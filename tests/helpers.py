@@ -8,6 +8,9 @@ DEFAULTS = dict(
     eye=(0.0, -300.0, 0.0), target=(0.0, 0.0, 0.0), up=(0.0, 0.0, 1.0), fov=4.242192793,
     light_pos=(21460.0, 0.0, 0.0), light_radius=100.0, light_radiance=80.0 * (2146.0 / 100.0) ** 2,
     scene_epsilon=1.0e-4, shadows=True, exposure=0.9, gamma=2.2,
+    # direct light (camera segment + light segment): the north_star path.  The reference asks for (2, 4) - two diffuse
+    # interreflection bounces (moon_renderer.py:583) - which tests/test_bounce_gpu.py covers
+    path_seg_range=(2, 2),
 )
 
 
@@ -24,7 +27,7 @@ def make_gpu(elevation, img_w, img_h, texture=None, scale=None, radius_scale=Non
     p = {**DEFAULTS, **kw}
     rt = B200OptiX(width=img_w, height=img_h)
     rt.set_param(min_accumulation_step=1, max_accumulation_frames=1)
-    rt.set_uint("path_seg_range", 2, 4)
+    rt.set_uint("path_seg_range", *p["path_seg_range"])
     rt.set_float("scene_epsilon", p["scene_epsilon"])
     rt.set_float("marching_step", 5.0e-3)
     rt.set_float("marching_step_eps", 3.0e-4)
