@@ -41,6 +41,9 @@ void mrtx_set_error(const char* fmt, ...);
 
 // ---- scene state ------------------------------------------------------------------
 #define MRTX_PROF_MAX 256
+#ifndef MRTX_TILED
+#define MRTX_TILED 0            // development switch: pyramid levels also in 8 x 8-cell tiles, walked by the filtered kernels (measured: no gain)
+#endif
 #define MRTX_P2P_MAX_RANKS 64
 #define MRTX_TUBE_TILE_LOG2 5    // screen tiles of the overlay-tube bins: 32 x 32 pixels ...
 #define MRTX_TUBE_TILE_CAP 62     // ... listing up to this many segments each (more: every segment is tested)
@@ -64,7 +67,7 @@ struct HeightField {
     // off[MRTX_MAX_LEVELS + k] = dil k.  Kernels copy this table to shared memory: a per-lane level index into a
     // kernel-parameter array costs a dozen instructions per access, into shared memory one.
     const void* lvl_base;
-    unsigned off[2 * MRTX_MAX_LEVELS];
+    unsigned off[3 * MRTX_MAX_LEVELS];      // [2 * MRTX_MAX_LEVELS + k]: level k again in 8 x 8-cell tiles (one 128-byte line each, int16)
     int   nx[MRTX_MAX_LEVELS], ny[MRTX_MAX_LEVELS];   // cells per level (level 0: W, H-1)
     float dmax, dmin;           // global max / min displacement factor
     // wall tables (one allocation, hf_tables_owned): cell walls are the half-planes of constant

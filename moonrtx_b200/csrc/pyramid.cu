@@ -118,6 +118,17 @@ int build_wall_tables(mrtx_ctx* ctx) {
     return MRTX_OK;
 }
 
+// level (row-major) -> 8 x 8-cell tiles, tile after tile in row-major order, cells past the level's edge repeated from it
+template <typename T>
+__global__ void tile_kernel(const T* __restrict__ src, int nx, int ny, int tx, long long n, T* __restrict__ dst) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long tile = i >> 6;
+    const int within = (int)(i & 63);
+    const int J = (int)(tile / tx) * 8 + (within >> 3), I = (int)(tile % tx) * 8 + (within & 7);
+    dst[i] = src[(size_t)min(J, ny - 1) * nx + min(I, nx - 1)];
+}
+
 template <typename T>
 int build_levels(mrtx_ctx* ctx) {
     HeightField& hf = ctx->hf;
@@ -132,6 +143,9 @@ int build_levels(mrtx_ctx* ctx) {
         hf.ny[k] = (H - 1 + (1 << k) - 1) >> k;
         total += (((size_t)hf.nx[k] * hf.ny[k] * sizeof(T)) + 255) & ~(size_t)255;
         if (k >= MRTX_DIL_MIN_LEVEL) total += (((size_t)hf.nx[k] * hf.ny[k] * sizeof(T)) + 255) & ~(size_t)255;
+#if MRTX_TILED
+        total += (size_t)((hf.nx[k] + 7) >> 3) * ((hf.ny[k] + 7) >> 3) * 64 * sizeof(T);        // the tiled copy (a multiple of 128 bytes)
+#endif
     }
     cudaStream_t st = ctx->stream;
     if (top > 0) {
@@ -161,6 +175,18 @@ int build_levels(mrtx_ctx* ctx) {
             const int reach = ((long long)hf.nx[k] << k) != W ? 2 : 1;
             dilate_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const T*)hf.level[k], hf.nx[k], hf.ny[k], reach < hf.nx[k] / 2 ? reach : hf.nx[k] / 2, (T*)hf.dil[k]);
         }
+#if MRTX_TILED
+        // the levels again in 8 x 8-cell tiles for the filtered walk: a ray moves through a level in both directions and
+        // descends to the four children of a cell - in rows, every step in latitude and every second child is another
+        // cache line; in tiles, seven of eight steps and all four children stay in the line
+        for (int k = 1; k <= top; ++k) {
+            const int tx = (hf.nx[k] + 7) >> 3, ty = (hf.ny[k] + 7) >> 3;
+            hf.off[2 * MRTX_MAX_LEVELS + k] = (unsigned)((p - (const char*)hf.lvl_base) / sizeof(T));
+            const long long n = (long long)tx * ty * 64;
+            tile_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const T*)hf.level[k], hf.nx[k], hf.ny[k], tx, n, (T*)p);
+            p += (size_t)n * sizeof(T);
+        }
+#endif
         MRTX_CUDA(cudaGetLastError());
         for (int k = 1; k <= top; ++k) {
             hf.off[k] = (unsigned)(((const char*)hf.level[k] - (const char*)hf.lvl_base) / sizeof(T));

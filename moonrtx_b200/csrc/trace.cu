@@ -85,8 +85,8 @@ template <bool I16, int MODE>
 __global__ void __launch_bounds__(128, MRTX_FAST_MINBLOCKS)
 trace_kernel_fast(const __grid_constant__ RenderArgs A) {
     constexpr bool QUEUE = MODE == 1;
-    __shared__ unsigned s_off[2 * MRTX_MAX_LEVELS];          // level offsets (HeightField::off) where a per-lane index is cheap
-    if (threadIdx.x < 2 * MRTX_MAX_LEVELS) s_off[threadIdx.x] = A.hf.off[threadIdx.x];
+    __shared__ unsigned s_off[3 * MRTX_MAX_LEVELS];          // level offsets (HeightField::off) where a per-lane index is cheap
+    if (threadIdx.x < 3 * MRTX_MAX_LEVELS) s_off[threadIdx.x] = A.hf.off[threadIdx.x];
     __syncthreads();
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -312,7 +312,7 @@ trace_kernel_fast(const __grid_constant__ RenderArgs A) {
 // and the density cancel and the path's throughput is just multiplied by the albedo), pushed to the bounce queue; bounce_kernel
 // traces that queue to its first hits, which come back here with BOUNCE = true: ray and throughput are read from the bounce
 // ray's queue entry, the direct light at the new hit is weighted with the throughput and goes through the same shadow queue.
-template <bool I16, bool BOUNCE>
+template <bool I16, bool BOUNCE, bool SPAWN>
 __global__ void __launch_bounds__(256, 2)
 shade_kernel(const __grid_constant__ RenderArgs A) {
     const unsigned FULL = 0xffffffffu;
@@ -320,7 +320,7 @@ shade_kernel(const __grid_constant__ RenderArgs A) {
     const unsigned lt = (1u << lane) - 1u;
     const unsigned n_hits = A.work_counter[7];                          // slots (32 per warp that had a hit), some empty
     const unsigned n_round = (n_hits + 31u) & ~31u;                     // whole warps stay in the loop (ballots)
-    const bool spawn = A.depth < A.n_bounce;
+    constexpr bool spawn = SPAWN;                                        // (this stage's hits continue their paths)
     RayStats rs = {0u, 0u, 0u, 0u, 0u};
     const Counters cnt = {0u, 0u, 0u};
     for (unsigned it = blockIdx.x * blockDim.x + threadIdx.x; it < n_round; it += gridDim.x * blockDim.x) {
@@ -443,8 +443,8 @@ enum { SQ_EMPTY = 0, SQ_WALK = 1, SQ_CAND = 2 };
 template <bool I16, bool CLOSEST>
 __global__ void __launch_bounds__(128, MRTX_SQ_MINBLOCKS)
 shadow_kernel(const __grid_constant__ RenderArgs A) {
-    __shared__ unsigned s_off[2 * MRTX_MAX_LEVELS];          // level offsets (HeightField::off) where a per-lane index is cheap
-    if (threadIdx.x < 2 * MRTX_MAX_LEVELS) s_off[threadIdx.x] = A.hf.off[threadIdx.x];
+    __shared__ unsigned s_off[3 * MRTX_MAX_LEVELS];          // level offsets (HeightField::off) where a per-lane index is cheap
+    if (threadIdx.x < 3 * MRTX_MAX_LEVELS) s_off[threadIdx.x] = A.hf.off[threadIdx.x];
     __syncthreads();
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -735,7 +735,10 @@ static int launch_trace_t(mrtx_ctx* ctx, RenderArgs& A, unsigned s0, unsigned ns
                 A.bq_out_rays = (RayRec*)ctx->bq_buf[0]; A.bq_out_aux = (uint4*)((char*)ctx->bq_buf[0] + ctx->bq_cap * sizeof(RayRec));
                 MRTX_CUDA(cudaMemsetAsync(A.work_counter + 8, 0, 3 * sizeof(unsigned), ctx->stream));
             }
-            if (hitq) shade_kernel<I16, false><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(A);
+            if (hitq) {
+                if (n_bounce) shade_kernel<I16, false, true><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(A);
+                else shade_kernel<I16, false, false><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(A);
+            }
             if (first) prof_mark(ctx, 4);
             if (queue) shadow_kernel<I16, false><<<sq_blocks, 128, 0, ctx->stream>>>(A);
             // interreflection: bounce rays -> first hits -> shading (direct light weighted with the path's throughput, next
@@ -747,7 +750,8 @@ static int launch_trace_t(mrtx_ctx* ctx, RenderArgs& A, unsigned s0, unsigned ns
                 A.bq_in_rays = (RayRec*)in; A.bq_in_aux = (uint4*)((char*)in + ctx->bq_cap * sizeof(RayRec));
                 A.bq_out_rays = (RayRec*)out; A.bq_out_aux = (uint4*)((char*)out + ctx->bq_cap * sizeof(RayRec));
                 shadow_kernel<I16, true><<<sq_blocks, 128, 0, ctx->stream>>>(A);         // bounce_kernel: first hits -> hit queue
-                shade_kernel<I16, true><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(A);
+                if (d < n_bounce) shade_kernel<I16, true, true><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(A);
+                else shade_kernel<I16, true, false><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(A);
                 shadow_kernel<I16, false><<<sq_blocks, 128, 0, ctx->stream>>>(A);
             }
             A.depth = 0;
