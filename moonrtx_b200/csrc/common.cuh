@@ -146,7 +146,6 @@ struct mrtx_ctx {
     unsigned long long* accfix; // 3 * width * height: order-independent radiance sums of a launch (folded into accum at its end)
     void* sq_buf; size_t sq_cap; // shadow queue (allocated on first use): sq_cap ray records + aux entries ...
     void* hq_buf; size_t hq_cap; // ... and the hit queue in front of it: hq_cap slots
-    void* pool_buf; size_t pool_bytes;   // trace_kernel_pool's straggler pools
     void* bq_buf[2]; size_t bq_cap;  // bounce-ray queues (interreflection; allocated when path_seg_range asks for bounces)
     double* beam_s;             // width * height entries (by position in the pixel list): where the pixel's samples start ...
     unsigned char* beam_l;      // ... and the level the beam pre-pass stopped at

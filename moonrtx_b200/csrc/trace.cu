@@ -302,164 +302,6 @@ trace_kernel_fast(const __grid_constant__ RenderArgs A) {
     if (lane == 0 && nd) atomicAdd(&A.defer_stats[0], (unsigned long long)nd);
 }
 
-// ---- trace_kernel_stream: the hit-queue form with in-place lane refill -------------------------------------------------------
-// In trace_kernel_fast a warp stays with its 32 rays until the last of them is decided.  Measured at config 3 (phase
-// counters): 2.36 walk phases and 2.35 patch-test phases per warp task - the first with ~31 lanes, the others with 5.5: the
-// few rays whose first candidate patch was a miss (grazing rays, 11 M of 47.5 M) hold the warp for 26 % of its walk
-// iterations and 57 % of its test phases.  Here a warp owns a contiguous run of the pixel list (MRTX_STREAM_CHUNK tasks at a
-// time) and walks through its rays in order, pixel by pixel, sample by sample: every iteration is one walk phase and one test
-// phase; a lane whose ray is decided takes the next ray of the run, a lane whose ray goes on keeps it.  Stragglers ride
-// along with the fresh rays of the neighbouring pixels, and the hits of one iteration - neighbours on the screen - go to the
-// hit queue together.
-#ifndef MRTX_STREAM_CHUNK
-#define MRTX_STREAM_CHUNK 8u
-#endif
-
-template <bool I16>
-__global__ void __launch_bounds__(128, MRTX_FAST_MINBLOCKS)
-trace_kernel_stream(const __grid_constant__ RenderArgs A) {
-    __shared__ unsigned s_off[3 * MRTX_MAX_LEVELS];
-    if (threadIdx.x < 3 * MRTX_MAX_LEVELS) s_off[threadIdx.x] = A.hf.off[threadIdx.x];
-    __syncthreads();
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const unsigned lt = (1u << lane) - 1u;
-    const unsigned n_limb = A.work_counter[4];
-    const unsigned nkept = n_limb + A.work_counter[1];
-    const unsigned p_end = min(nkept, A.wave_p0 + A.wave_np);
-    if (A.wave_p0 >= p_end) return;
-    const unsigned ppw = 32u >> A.g_log2;                    // pixels per task (the unit work_counter[2] counts)
-    const unsigned ntasks = (p_end - A.wave_p0 + ppw - 1u) / ppw;
-    const float Rf = A.K.R;
-    const unsigned ns = A.nsamples;
-    unsigned run_p = 0, run_n = 0, nxt = 0;                  // the warp's run: pixels [run_p, run_p + run_n), next ray of it
-    bool exhausted = false;
-
-    Counters cnt = {0u, 0u, 0u};
-    RayStats rs = {0u, 0u, 0u, 0u, 0u};
-    unsigned n_defer = 0;
-    Ray64 R;
-    Walk st;
-    uint32_t pixel = 0;
-    unsigned k = 0;
-    bool alive = false;
-
-    for (;;) {
-        // ---- free lanes take the next rays of the run
-        bool have = alive, entered = alive;
-        unsigned m_free = __ballot_sync(FULL, !alive);
-        if (m_free && nxt >= run_n * ns && !exhausted) {
-            unsigned task = 0;
-            if (lane == 0) task = atomicAdd(&A.work_counter[2], MRTX_STREAM_CHUNK);
-            task = __shfl_sync(FULL, task, 0);
-            if (task >= ntasks) exhausted = true;
-            else {
-                run_p = A.wave_p0 + task * ppw;
-                run_n = min(MRTX_STREAM_CHUNK * ppw, p_end - run_p);
-                nxt = 0;
-            }
-        }
-        if (m_free && nxt < run_n * ns) {
-            const unsigned j = nxt + (unsigned)__popc(m_free & lt);
-            if (!alive && j < run_n * ns) {
-                const unsigned p = run_p + j / ns;
-                k = j - (j / ns) * ns;
-                const unsigned packed = list_pixel(A, p, n_limb);
-                const int x = (int)(packed & 0xffffu), y = (int)(packed >> 16);
-                pixel = (uint32_t)y * (uint32_t)A.width + (uint32_t)x;
-                if (k == 0u) A.accum[pixel].w += (float)ns;                  // one lane per pixel and launch
-                double s_beam = 0.0;
-                int lvl_primary = A.hf.top - (int)A.sp.start_primary;
-                if (A.beam_s) {
-                    s_beam = A.beam_s[p];
-                    if (s_beam > 0.0) lvl_primary = max((int)A.beam_l[p] - A.beam_drop, 0);
-                }
-                primary_ray_fast(A, x, y, pixel, A.sample0 + k, R);
-                const int wb = walk_begin2(A.hf, A.sp.radius, R, s_beam, lvl_primary, st);
-                alive = wb == 2;
-                entered = wb != 0;
-                have = true;
-            }
-            nxt = min(nxt + (unsigned)__popc(m_free), run_n * ns);
-        }
-        if (!__any_sync(FULL, have)) break;                  // nothing in flight, nothing left to claim
-        const unsigned sm = A.sample0 + k;
-
-        // ---- one walk phase (in lockstep), one test phase
-        RawPatch P;
-        FastHit fh;
-        float sx = 0.f;
-        int face = 4, res = FT_MISS;
-        bool cand = false;
-        while (__any_sync(FULL, alive && !cand)) {
-            if (alive && !cand) {
-                const int r = walk_step<I16>(A.hf, Rf, A.inv_rs, st, P, sx, face, cnt, nullptr, s_off);
-                if (r == TR_END) alive = false;
-                else if (r == TR_CANDIDATE) cand = true;
-            }
-        }
-        if ((alive || cand) && st.steps > (int)A.sp.long_walk) {
-            res = FT_DEFER; alive = false; cand = false;
-            atomicAdd(&A.defer_stats[15], 1ull);
-        }
-        if (cand) {
-            ++cnt.tests;
-            const int t = fast_test<I16>(A.hf, A.K, R, st.s_in, 0.0, st.s, sx, st.smax, P, false, fh);
-            if (t == FT_MISS) { if (!walk_advance(A.hf, st, sx, face)) alive = false; }
-            else {
-                res = t & 3; alive = false;
-                if (res == FT_DEFER) atomicAdd(&A.defer_stats[t >> 2], 1ull);
-            }
-        }
-
-        // ---- decided rays: the hit goes to the hit queue, a miss sees what lies behind the Moon, a deferral goes to the referee
-        const bool done = have && !alive;
-        bool hit = done && res == FT_HIT;
-        const unsigned hm = __ballot_sync(FULL, hit);
-        if (hm) {
-            // (32 slots per iteration, lanes without a hit mark theirs empty: see trace_kernel_fast)
-            unsigned base = 0;
-            if (lane == 0) base = atomicAdd(&A.work_counter[7], 32u);
-            base = __shfl_sync(FULL, base, 0);
-            if (base + 32u > A.hq_cap) {
-                // the queue is full (a frame of nothing but stragglers): these samples are traced again by the referee
-                if (hit) { hit = false; res = FT_DEFER; }
-            } else {
-            uint4* q = (uint4*)(A.hq + base + (unsigned)lane);
-            __stcs(q + 1, make_uint4((unsigned)fh.r0, (unsigned)fh.c0, hit ? pixel | (k << 27) : 0xffffffffu, 0u));
-            if (hit) {
-                __stcs(q, make_uint4((unsigned)__double2loint(fh.s), (unsigned)__double2hiint(fh.s), __float_as_uint(fh.fc), __float_as_uint(fh.fr)));
-                __stcs(q + 2, make_uint4(__float_as_uint(fh.d00), __float_as_uint(fh.d01), __float_as_uint(fh.d10), __float_as_uint(fh.d11)));
-            }
-            }
-        }
-        if (done) {
-            if (res == FT_DEFER) {
-                const unsigned slot = atomicAdd(&A.work_counter[3], 1u);
-                const unsigned px = pixel % (unsigned)A.width, py = pixel / (unsigned)A.width;
-                if (slot < A.list_cap) A.defer_list[slot] = make_uint2(px | (py << 16), 1u << k);
-                ++n_defer;
-            } else {
-                ++rs.primary;
-                if (entered) ++rs.inside;
-                if (hit) ++rs.hits;
-                else {
-                    const int x = (int)(pixel % (unsigned)A.width), y = (int)(pixel / (unsigned)A.width);
-                    float3 tc;
-                    if (tube_tile_count(A, x, y) && tube_nearest(A, x, y, pixel, sm, 1.0e300, tc)) accfix_add(A.accfix, pixel, tc);
-                    else {
-                        write_miss(A, x, y, sm == A.hit_sample);
-                        if (sees_background(A)) accfix_add(A.accfix, pixel, miss_radiance_body(A, R));
-                    }
-                }
-            }
-        }
-    }
-    flush_counters(A, rs, cnt, lane);
-    const unsigned nd = __reduce_add_sync(FULL, n_defer);
-    if (lane == 0 && nd) atomicAdd(&A.defer_stats[0], (unsigned long long)nd);
-}
-
 // ---- shade_kernel: one thread per queued hit ---------------------------------------------------------------------------------
 // Dense and coherent (hits of a warp's pixels are neighbours in the queue): the primary ray evaluated again from (pixel,
 // sample), normal, albedo, Lambert term, light sample; the shadow ray set up to its first cell and appended to the shadow
@@ -854,8 +696,7 @@ static int launch_trace_t(mrtx_ctx* ctx, RenderArgs& A, unsigned s0, unsigned ns
         const size_t items = std::min<size_t>((size_t)npix * chunk, SQ_MAX);
         const bool pow2 = (chunk & (chunk - 1)) == 0 && (ns <= 32u || ns % 32u == 0);
         n_bounce = ctx->sp.shadow_queue >= 2u ? (int)ctx->sp.n_bounce : 0;       // (interreflection runs through the queues)
-        // (hit slots: 32 per warp iteration with a hit; the streaming form has more, emptier iterations)
-        rc = ensure_queues(ctx, items, ctx->sp.shadow_queue >= 2u ? items * ((pow2 ? 1 : 2) + (ctx->sp.shadow_queue >= 3u ? 1 : 0)) + 2048 : 0, n_bounce > 0);
+        rc = ensure_queues(ctx, items, ctx->sp.shadow_queue >= 2u ? items * (pow2 ? 1 : 2) + 2048 : 0, n_bounce > 0);
         if (rc) return rc;
         A.sq_rays = (RayRec*)ctx->sq_buf;
         A.sq_aux = (uint4*)((char*)ctx->sq_buf + ctx->sq_cap * sizeof(RayRec));
@@ -888,18 +729,6 @@ static int launch_trace_t(mrtx_ctx* ctx, RenderArgs& A, unsigned s0, unsigned ns
             }
             const bool first = !done && !p0;                // (the stopwatch brackets the first chunk and wave of a launch)
             const bool hitq = queue && ctx->sp.shadow_queue >= 2u;
-            if (hitq && ctx->sp.shadow_queue >= 3u) {
-                // the streaming form
-                int per_sm = 0;
-                MRTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel_stream<I16>, 128, 0));
-                if (per_sm < 1) per_sm = 1;
-                if (ctx->sp.blocks_per_sm && (int)ctx->sp.blocks_per_sm < per_sm) per_sm = (int)ctx->sp.blocks_per_sm;
-                long long blocks = (long long)ctx->sm_count * per_sm;
-                const long long warps_needed = (((long long)A.wave_np << A.g_log2) + 31) / 32 / MRTX_STREAM_CHUNK + 1;
-                if (blocks * 4 > warps_needed) blocks = (warps_needed + 3) / 4;
-                if (blocks < 1) blocks = 1;
-                trace_kernel_stream<I16><<<(unsigned)blocks, 128, 0, ctx->stream>>>(A);
-            } else
             rc = hitq ? launch_fast<I16, 2>(ctx, A, A.wave_np) : queue ? launch_fast<I16, 1>(ctx, A, A.wave_np) : launch_fast<I16, 0>(ctx, A, A.wave_np);
             if (rc) return rc;
             if (first) prof_mark(ctx, 3);

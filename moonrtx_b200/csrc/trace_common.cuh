@@ -84,7 +84,6 @@ struct RenderArgs {
     // ([10] rays); their aux entries carry the path's throughput.  depth: 0 = camera hits, d = hits of the d-th bounce
     struct RayRec* bq_in_rays; uint4* bq_in_aux; struct RayRec* bq_out_rays; uint4* bq_out_aux;
     int depth, n_bounce;
-    void* pool;                      // trace_kernel_pool: POOL_CAP parked rays per warp
     // hit queue (shadow_queue = 2): primary hits pushed by trace_kernel_fast (work_counter[7] of them), shaded by shade_kernel
     struct HitQRec* hq; unsigned hq_cap;
     unsigned long long* accfix;
