@@ -63,6 +63,7 @@ int mrtx_create(int device, mrtx_ctx** out_ctx) {
     MRTX_CUDA(cudaEventCreate(&c->ev1));
     MRTX_CUDA(cudaMalloc(&c->d_max_bits, sizeof(unsigned)));
     MRTX_CUDA(cudaMalloc(&c->d_work, 16 * sizeof(unsigned)));
+    MRTX_CUDA(cudaMalloc(&c->hard_buf, 256 * 2560));            // HARD_MAX_RAYS x sizeof(HardRay) (checked in trace.cu)
     MRTX_CUDA(cudaMalloc(&c->d_counters, 16 * sizeof(unsigned long long)));
     MRTX_CUDA(cudaMemset(c->d_counters, 0, 16 * sizeof(unsigned long long)));
     MRTX_CUDA(cudaMalloc(&c->d_defer_stats, 32 * sizeof(unsigned long long)));
@@ -75,7 +76,7 @@ int mrtx_create(int device, mrtx_ctx** out_ctx) {
     sp.light_pos[0] = 21460.0; sp.light_radius = 100.0; sp.light_radiance = 80.0 * 460.5316;
     sp.scene_epsilon = 1.0e-4;
     sp.exposure = 0.9f; sp.inv_gamma = 1.0f / 2.2f;
-    sp.jitter = 0; sp.shadows = 1; sp.debug_hits = 0; sp.kernel = 2; sp.beam = 0; sp.beam_drop = 2; sp.ceiling = 0; sp.shadow_queue = 2; sp.start_primary = 3; sp.start_shadow = 2; sp.long_walk = 2048u; sp.referee_budget = 500u;
+    sp.jitter = 0; sp.shadows = 1; sp.debug_hits = 0; sp.kernel = 2; sp.beam = 0; sp.beam_drop = 2; sp.ceiling = 0; sp.shadow_queue = 2; sp.start_primary = 3; sp.start_shadow = 2; sp.long_walk = 2048u; sp.referee_budget = 500u; sp.hard_rays = 1u;
     const double eye[3] = {0, -300, 0}, tgt[3] = {0, 0, 0}, up[3] = {0, 0, 1};
     mrtx_set_camera(c, eye, tgt, up, 4.242192793);
     *out_ctx = c;
@@ -107,7 +108,7 @@ int mrtx_destroy(mrtx_ctx* ctx) {
     for (int q = 0; q < 2; ++q) { cudaFree(ctx->recv_buf[q]); if (ctx->recv_ev[q]) cudaEventDestroy(ctx->recv_ev[q]); }
     free_frame(ctx);
     cudaFree(ctx->d_max_bits);
-    cudaFree(ctx->d_work);
+    cudaFree(ctx->d_work); cudaFree(ctx->hard_buf);
     cudaFree(ctx->d_counters);
     cudaFree(ctx->d_defer_stats);
     cudaFree(ctx->wave_buf);
@@ -831,6 +832,7 @@ int mrtx_set_uint(mrtx_ctx* ctx, const char* name, unsigned a, unsigned b) {
     else if (!strcmp(name, "debug_hits")) ctx->sp.debug_hits = a ? 1u : 0u;
     else if (!strcmp(name, "start_levels")) { ctx->sp.start_primary = a; ctx->sp.start_shadow = b; }
     else if (!strcmp(name, "long_walk")) { MRTX_REQUIRE(a >= 1u, "long_walk must be >= 1"); ctx->sp.long_walk = a; }
+    else if (!strcmp(name, "hard_rays")) ctx->sp.hard_rays = a ? 1u : 0u;
     else if (!strcmp(name, "referee_budget")) { MRTX_REQUIRE(a >= 1u, "referee_budget must be >= 1"); ctx->sp.referee_budget = a; }
     else if (!strcmp(name, "ceiling")) ctx->sp.ceiling = a;
     else if (!strcmp(name, "profile")) ctx->prof_on = a ? 1 : 0;

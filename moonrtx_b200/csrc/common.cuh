@@ -103,6 +103,7 @@ struct SceneParams {
     unsigned start_primary, start_shadow;   // filtered kernel: primary rays start at level top - start_primary, shadow rays at start_shadow
     unsigned long_walk, referee_budget;     // walks longer than long_walk nodes go to the referee; a referee lane spends referee_budget on a piece
     unsigned blocks_per_sm;                 // development: cap on resident blocks per SM of the two walk kernels (0 = what fits)
+    unsigned hard_rays;                     // shadow rays too long for one referee warp are finished by the whole grid (default on)
     unsigned n_bounce;                      // diffuse interreflection bounces after the camera hit (path_seg_range max - 2; 0 = direct light)
     unsigned shadow_queue;                  // 2 (default): primary hits -> hit queue -> shade_kernel -> shadow queue -> shadow_kernel;
                                             // 1: shading inside trace_kernel_fast, shadow rays through the queue; 0: everything inside trace_kernel_fast
@@ -146,6 +147,7 @@ struct mrtx_ctx {
     unsigned long long* accfix; // 3 * width * height: order-independent radiance sums of a launch (folded into accum at its end)
     void* sq_buf; size_t sq_cap; // shadow queue (allocated on first use): sq_cap ray records + aux entries ...
     void* hq_buf; size_t hq_cap; // ... and the hit queue in front of it: hq_cap slots
+    void* hard_buf;                  // shadow rays trace_kernel_referee hands to referee_hard_kernel (allocated with the context)
     void* bq_buf[2]; size_t bq_cap;  // bounce-ray queues (interreflection; allocated when path_seg_range asks for bounces)
     double* beam_s;             // width * height entries (by position in the pixel list): where the pixel's samples start ...
     unsigned char* beam_l;      // ... and the level the beam pre-pass stopped at

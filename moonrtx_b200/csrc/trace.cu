@@ -22,6 +22,11 @@
 
 namespace {
 
+#ifndef MRTX_HARD_BLOCKS
+#define MRTX_HARD_BLOCKS 1024
+#endif
+static_assert(sizeof(HardRay) * HARD_MAX_RAYS <= 256 * 2560, "hard_buf is allocated in api.cu");
+
 // ---- beam pre-pass: one thread per listed pixel (trace_fast.cuh, BeamCtl) -------------------------------------------
 // The samples of a pixel are ~15 texels apart at 4K on the full-resolution map: each walks its own cells near the
 // surface, but above it they all cross the same empty coarse cells.  This pass crosses them ONCE per pixel, with the
@@ -725,7 +730,7 @@ static int launch_trace_t(mrtx_ctx* ctx, RenderArgs& A, unsigned s0, unsigned ns
             if (done || p0) {
                 MRTX_CUDA(cudaMemsetAsync(A.work_counter + 2, 0, 2 * sizeof(unsigned), ctx->stream));
                 MRTX_CUDA(cudaMemsetAsync(A.work_counter + 5, 0, 3 * sizeof(unsigned), ctx->stream));
-                MRTX_CUDA(cudaMemsetAsync(A.work_counter + 11, 0, sizeof(unsigned), ctx->stream));
+                MRTX_CUDA(cudaMemsetAsync(A.work_counter + 11, 0, 2 * sizeof(unsigned), ctx->stream));
             }
             const bool first = !done && !p0;                // (the stopwatch brackets the first chunk and wave of a launch)
             const bool hitq = queue && ctx->sp.shadow_queue >= 2u;
@@ -759,6 +764,11 @@ static int launch_trace_t(mrtx_ctx* ctx, RenderArgs& A, unsigned s0, unsigned ns
             A.depth = 0;
             if (first) prof_mark(ctx, 5);
             trace_kernel_referee<I16, false><<<ctx->sm_count * 8, 64, 0, ctx->stream>>>(A);
+            if (A.hard) {
+                // shadow rays too long for one warp (polar slivers): every one walked by 16 384 threads, a few at a time
+                referee_hard_kernel<I16><<<dim3(MRTX_HARD_BLOCKS, 8), 64, 0, ctx->stream>>>(A);
+                referee_hard_finish_kernel<<<1, 64, 0, ctx->stream>>>(A);
+            }
             if (first) prof_mark(ctx, 6);
         }
     }

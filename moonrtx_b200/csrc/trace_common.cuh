@@ -84,6 +84,7 @@ struct RenderArgs {
     // ([10] rays); their aux entries carry the path's throughput.  depth: 0 = camera hits, d = hits of the d-th bounce
     struct RayRec* bq_in_rays; uint4* bq_in_aux; struct RayRec* bq_out_rays; uint4* bq_out_aux;
     int depth, n_bounce;
+    struct HardRay* hard;            // shadow rays handed from trace_kernel_referee to referee_hard_kernel (work_counter[12] of them)
     // hit queue (shadow_queue = 2): primary hits pushed by trace_kernel_fast (work_counter[7] of them), shaded by shade_kernel
     struct HitQRec* hq; unsigned hq_cap;
     unsigned long long* accfix;
@@ -678,8 +679,11 @@ __device__ int trace_referee(const RenderArgs& A, const Ray64& R, double s_lo, d
 
 // First hit of R at s >= s_min by the whole warp.  Returns the lane that holds it (fast / fh / h valid there), or -1.
 template <bool I16>
+// max_rounds (any-hit rays only): after that many rounds with intervals still pending the warp gives up and returns -2 with
+// the pending intervals in stack[0 .. n_left): the caller hands them to referee_hard_kernel.
 __device__ int referee_ray(const RenderArgs& A, RefIv* stack, const Ray64& R, double s_min, int start_level, bool any_hit,
-                           bool& fast, FastHit& fh, TraceOut& h, Counters& cnt, bool& entered) {
+                           bool& fast, FastHit& fh, TraceOut& h, Counters& cnt, bool& entered, int max_rounds = 0x7fffffff,
+                           int* n_left = nullptr) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const double Rb = A.sp.radius * (double)A.hf.dmax;
@@ -696,6 +700,7 @@ __device__ int referee_ray(const RenderArgs& A, RefIv* stack, const Ray64& R, do
     __syncwarp();
     int rounds = 0;
     while (top > 0) {
+        if (any_hit && rounds >= max_rounds) { if (n_left) *n_left = top; return -2; }
         // this round: the n nearest pending intervals, each cut into m pieces; lanes in order of distance
         // (one interval cut 32 ways at first; once a long chain has been split, its parts run side by side)
         const int n = any_hit ? min(top, 32) : 1, m = 32 / n;
@@ -753,6 +758,24 @@ __device__ int referee_ray(const RenderArgs& A, RefIv* stack, const Ray64& R, do
     return -1;
 }
 
+// ---- second tier: shadow rays whose chain one warp cannot finish in time -------------------------------------------------------
+// Measured on the terminator sweep (config 4, frames 24..62): ONE sun ray that skims the ground 1.5 km from the south pole
+// crosses tens of thousands of cells 10 cm wide and holds one warp of trace_kernel_referee for up to 19 ms while 2 367 others
+// have long finished (frame 56: 50 ms instead of 31).  A warp that has spent MRTX_HARD_ROUNDS rounds on a shadow ray now
+// publishes the ray, what it would add to the pixel and the intervals still pending; referee_hard_kernel then walks each
+// such ray with the whole grid - thousands of short pieces, each decided by the same float32 filter + float64 exact test.
+// Any crossing occludes, so the pieces need no order.
+#ifndef MRTX_HARD_ROUNDS
+#define MRTX_HARD_ROUNDS 1
+#endif
+constexpr int HARD_MAX_RAYS = 256;
+struct HardRay {
+    double ox, oy, oz, dx, dy, dz;
+    float lit[3]; uint32_t pixel;
+    int n_iv, occluded, pad0, pad1;
+    RefIv iv[REFEREE_STACK];
+};
+
 // WAVE: entries are (list pixel, sample) items of the wavefront pipeline and the result goes to the item's
 // radiance slot; otherwise (pixel, sample mask) entries of trace_kernel_fast and the result is added to the accumulator.
 template <bool I16, bool WAVE>
@@ -779,7 +802,13 @@ trace_kernel_referee(const __grid_constant__ RenderArgs A) {
             bool fast = false, entered = false;
             FastHit fh;
             TraceOut h;
+#ifdef MRTX_REFEREE_TIMING
+            const long long tt0 = clock64();
+#endif
             const int who = referee_ray<I16>(A, stack, R, 0.0, A.hf.top - 3, false, fast, fh, h, cnt, entered);
+#ifdef MRTX_REFEREE_TIMING
+            if (lane == 0) atomicMax(&A.defer_stats[26], (unsigned long long)(clock64() - tt0));
+#endif
             if (lane == 0) { ++rs.primary; if (entered) ++rs.inside; }
             if (who < 0) {
                 if (lane == 0) {
@@ -808,7 +837,37 @@ trace_kernel_referee(const __grid_constant__ RenderArgs A) {
                 S.dx = shfl_d(S.dx, who); S.dy = shfl_d(S.dy, who); S.dz = shfl_d(S.dz, who);
                 S.oo = S.ox * S.ox + S.oy * S.oy + S.oz * S.oz;
                 S.od = S.ox * S.dx + S.oy * S.dy + S.oz * S.dz;
-                occluded = referee_ray<I16>(A, stack, S, 0.0, 2, true, fast, fh, h, cnt, entered) >= 0;
+                int n_left = 0;
+#ifdef MRTX_REFEREE_TIMING
+                const long long tt1 = clock64();
+#endif
+                const int sr = referee_ray<I16>(A, stack, S, 0.0, 2, true, fast, fh, h, cnt, entered,
+                                                !WAVE && A.hard ? MRTX_HARD_ROUNDS : 0x7fffffff, &n_left);
+#ifdef MRTX_REFEREE_TIMING
+                if (lane == 0) atomicMax(&A.defer_stats[27], (unsigned long long)(clock64() - tt1));
+#endif
+                occluded = sr >= 0;
+                if (sr == -2) {
+                    // too long a chain for one warp: the grid finishes it (referee_hard_kernel adds lit if the sun is visible)
+                    unsigned slot = 0;
+                    if (lane == 0) slot = atomicAdd(&A.work_counter[12], 1u);
+                    slot = __shfl_sync(0xffffffffu, slot, 0);
+                    if (slot < (unsigned)HARD_MAX_RAYS) {
+                        HardRay* hr = A.hard + slot;
+                        if (lane == 0) {
+                            hr->ox = S.ox; hr->oy = S.oy; hr->oz = S.oz; hr->dx = S.dx; hr->dy = S.dy; hr->dz = S.dz;
+                            hr->lit[0] = lit.x; hr->lit[1] = lit.y; hr->lit[2] = lit.z; hr->pixel = pixel;
+                            hr->n_iv = n_left; hr->occluded = 0;
+                        }
+                        for (int i = lane; i < n_left; i += 32) hr->iv[i] = stack[i];
+                        __syncwarp();
+                        occluded = true;                    // (nothing is added here)
+                        if (lane == 0) ++rs.shadow;
+                        continue;
+                    }
+                    // (list full: finish it here after all)
+                    occluded = referee_ray<I16>(A, stack, S, 0.0, 2, true, fast, fh, h, cnt, entered) >= 0;
+                }
                 if (lane == 0) { ++rs.shadow; if (occluded) ++rs.occluded; }
             }
             if (!occluded) { acc.x += lit.x; acc.y += lit.y; acc.z += lit.z; }
@@ -825,6 +884,55 @@ trace_kernel_referee(const __grid_constant__ RenderArgs A) {
     }
     __syncwarp();
     flush_counters(A, rs, cnt, lane);
+}
+
+// One thread per piece: the pending intervals of hard ray blockIdx.y, each cut into gridDim.x * blockDim.x / n_iv pieces.
+template <bool I16>
+__global__ void __launch_bounds__(64)
+referee_hard_kernel(const __grid_constant__ RenderArgs A) {
+    const unsigned n_hard = min(A.work_counter[12], (unsigned)HARD_MAX_RAYS);
+    Counters cnt = {0u, 0u, 0u};
+    for (unsigned hi = blockIdx.y; hi < n_hard; hi += gridDim.y) {
+        HardRay* hr = A.hard + hi;
+        const int n_iv = hr->n_iv;
+        if (n_iv <= 0) continue;
+        const unsigned P = gridDim.x * blockDim.x, t = blockIdx.x * blockDim.x + threadIdx.x;
+        const unsigned m = max(P / (unsigned)n_iv, 1u);                   // pieces per interval
+        const unsigned i = t / m, j = t - i * m;
+        if (i >= (unsigned)n_iv) continue;
+        if (*(volatile int*)&hr->occluded) continue;
+        Ray64 S;
+        S.ox = hr->ox; S.oy = hr->oy; S.oz = hr->oz; S.dx = hr->dx; S.dy = hr->dy; S.dz = hr->dz;
+        S.oo = S.ox * S.ox + S.oy * S.oy + S.oz * S.oz; S.od = S.ox * S.dx + S.oy * S.dy + S.oz * S.dz;
+        const RefIv iv = hr->iv[i];
+        const double step = (iv.b - iv.a) / (double)m;
+        const double own = iv.a + j * step, end = j == m - 1 ? iv.b : iv.a + (j + 1) * step;
+        // (pieces start a little early, as in referee_ray: the first cell is found from a float32 position inside the piece)
+        const float t0_rel = 1.0e-6f;
+        const double lap = 3.0 * (double)t0_rel * A.sp.radius;
+        const double lo = fmax(0.0, own - lap);
+        double s_stop = end;
+        bool fast = false;
+        FastHit fh;
+        TraceOut h;
+        const int st = trace_referee<I16>(A, S, lo, own, end, 2, t0_rel, true, 0x7fffffff, s_stop, fast, fh, h, cnt);
+        if (st == RS_HIT) atomicExch(&hr->occluded, 1);
+    }
+    const Counters& c = cnt;
+    const RayStats rs = {0u, 0u, 0u, 0u, 0u};
+    flush_counters(A, rs, c, threadIdx.x & 31);
+}
+
+// what the hard rays add to their pixels, once all their pieces are decided
+__global__ void referee_hard_finish_kernel(const __grid_constant__ RenderArgs A) {
+    const unsigned n_hard = min(A.work_counter[12], (unsigned)HARD_MAX_RAYS);
+    unsigned occluded = 0;
+    for (unsigned hi = threadIdx.x; hi < n_hard; hi += blockDim.x) {
+        const HardRay* hr = A.hard + hi;
+        if (hr->occluded) ++occluded;
+        else accfix_add(A.accfix, hr->pixel, make_float3(hr->lit[0], hr->lit[1], hr->lit[2]));
+    }
+    if (occluded) atomicAdd(&A.counters[4], (unsigned long long)occluded);
 }
 
 }  // namespace
@@ -847,6 +955,7 @@ static void fill_render_args(mrtx_ctx* ctx, int x0, int y0, int x1, int y1, unsi
     A.hit64 = ctx->sp.debug_hits ? ctx->hit64 : nullptr;
     A.counters = ctx->d_counters;
     A.work_counter = ctx->d_work;
+    A.hard = ctx->sp.hard_rays ? (HardRay*)ctx->hard_buf : nullptr;
     A.tubes = ctx->tube_seg; A.n_tubes = ctx->n_tubes; A.tube_tiles = ctx->tube_tiles; A.tube_tx = ctx->tube_tx;
     A.pixel_list = ctx->pixel_list;
     const double er[3] = {A.cam.eye[0] - A.sp.pos[0], A.cam.eye[1] - A.sp.pos[1], A.cam.eye[2] - A.sp.pos[2]};

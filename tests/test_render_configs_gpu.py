@@ -116,6 +116,26 @@ def test_config4_sweep_frames(full_map, frame):
     print("config 4 frame", frame, m)
 
 
+def test_hard_shadow_rays_finished_by_the_grid_change_nothing(full_map):
+    """Frame 56 of the sweep holds the sun ray that skims the ground next to the south pole (tens of thousands of cells
+    10 cm wide): trace_kernel_referee hands it to referee_hard_kernel.  Same decisions, same frame, bit for bit."""
+    src, counts, rs = full_map
+    kw = frame_kw(56)
+    outs = []
+    for hard in (0, 1):
+        rt = make_gpu((src, MAP_W, MAP_H), 3840, 2160, scale=SCALE, radius_scale=rs, debug_hits=False, **kw)
+        rt.set_uint("hard_rays", hard)
+        rt.set_param(max_accumulation_frames=16, min_accumulation_step=16)
+        rt.counters(reset=True)
+        rt.render_cycle(read_back=False)
+        outs.append((rt.get_accum_buffer().copy(), rt.counters()))
+        rt.close()
+    (a0, c0), (a1, c1) = outs
+    assert np.array_equal(a0, a1)
+    for k in ("primary_rays", "primary_hits", "shadow_rays", "shadow_occluded"):
+        assert c0[k] == c1[k], (k, c0[k], c1[k])
+
+
 def test_config5_8k_eyepiece_on_the_terminator(full_map):
     """BASELINE config 5: 7680x4320, fov 2.5 deg (renderer_fov.py:47-55, 98-101), looking at the terminator at latitude 0:
     grazing sun incidence in every pixel."""

@@ -14,5 +14,5 @@ for name in ("long_walk", "referee_budget"):
 for f in [int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "0,8,24,48,87,160,239").split(",")]:
     apply_frame_state(rt, scene.frame_state(synth_ephemeris(f * 10.0)))
     r = bt.time_frame(rt, 16, reps=2)
-    print(json.dumps({"frame": f, "ms": r["ms"], "nodes": r["node_visits"], "tests": r["patch_tests"], "shadow": r["shadow_rays"], "occluded": r["shadow_occluded"],
+    print(json.dumps({"frame": f, "ms": r["ms"], "kernel_ms": r["kernel_ms"], "defer_shadow": r["defer"]["shadow_reasons"], "nodes": r["node_visits"], "tests": r["patch_tests"], "shadow": r["shadow_rays"], "occluded": r["shadow_occluded"],
                       "in_sphere": r["primary_in_sphere"], "deferred": r["defer"]["deferred_samples"], "nodes_per_inray": r["nodes_per_inray"]}), flush=True)
