@@ -8,6 +8,7 @@ grazing case: the oracle's own surface function along that ray dips below zero b
 ray touches: which side of a tangent root a sample falls on is decided by the last bits of either implementation).
 """
 import math
+import os
 
 import numpy as np
 import pytest
@@ -114,6 +115,24 @@ def test_config4_sweep_frames(full_map, frame):
     longest chains of the sweep (the referee and the poles)."""
     m = check_frame(full_map, 3840, 2160, 60, frame_kw(frame), min_hits=600)
     print("config 4 frame", frame, m)
+
+
+def test_kernel_counters_agree_with_the_measured_bytes_per_ray(full_map):
+    """the bytes the kernels count per ray (32 B per node visit, 64 B per patch test) must agree with the
+    oracle-side figure frozen in tests/golden/bray.json / BASELINE.md within 2x, so that roofline bytes cannot be inflated."""
+    import json
+    bray = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bray.json")))["config3"]
+    src, counts, rs = full_map
+    rt = make_gpu((src, MAP_W, MAP_H), 3840, 2160, scale=SCALE, radius_scale=rs, debug_hits=False, **frame_kw(0))
+    rt.set_param(max_accumulation_frames=16, min_accumulation_step=16)
+    rt.counters(reset=True)
+    rt.render_cycle(read_back=False)
+    c = rt.counters()
+    rt.close()
+    rays = c["primary_in_sphere"] + c["shadow_rays"]
+    counted = 32.0 * (c["node_visits"] + 2 * c["patch_tests"]) / rays
+    assert 0.5 * bray["B_ray"] <= counted <= 2.0 * bray["B_ray"], (counted, bray["B_ray"])
+    assert 416 * 0.9 <= bray["B_ray"] <= 416 * 1.2                    # ... and that figure sits at the closed-form floor
 
 
 def test_hard_shadow_rays_finished_by_the_grid_change_nothing(full_map):
