@@ -273,18 +273,29 @@ def load_color_data(filepath: str, gamma: float = 2.2, downscale: int = 1) -> np
         raise FileNotFoundError(
             f"Color file not found: {filepath}, and no cache of it downscaled by {downscale} beside it.")
     import cv2
-    src = cv2.imread(filepath, cv2.IMREAD_COLOR)        # full decode; the reduce runs on the GPU
-    if src is None:
-        raise ValueError(f"Failed to read color file: {filepath}")
-    if downscale not in COLOR_DOWNSCALE_FACTORS:
-        downscale = 1                                   # data_loader.py:331 falls back to IMREAD_COLOR
-    print(f"  Dimensions: {src.shape}")
-    if fingerprint is not None and downscale > 1:
-        # the cache holds the reduced BGR image (gamma is applied after reading it,
-        # data_loader.py:303-306): one extra pass with the identity table produces it
-        ident = _color_reduce_lut(np.ascontiguousarray(src), np.arange(256, dtype=np.uint8), downscale, get_device())
-        _cache_save(base, np.ascontiguousarray(ident[..., 2::-1]), fingerprint)
-    return color_texture(src, gamma, downscale)
+    k = downscale if downscale in COLOR_DOWNSCALE_FACTORS else 1        # data_loader.py:331 falls back to IMREAD_COLOR
+    reduced = None
+    if k > 1 and filepath.lower().endswith((".tif", ".tiff")):
+        # a TIFF is decoded in full by OpenCV and reduced afterwards (central 2x2 of every k x k block):
+        # that reduce runs on the GPU, once, to BGR - the image the reference caches
+        src = cv2.imread(filepath, cv2.IMREAD_COLOR)
+        if src is None:
+            raise ValueError(f"Failed to read color file: {filepath}")
+        if src.shape[0] % k == 0 and src.shape[1] % k == 0:
+            ident = _color_reduce_lut(np.ascontiguousarray(src), np.arange(256, dtype=np.uint8), k, get_device())
+            reduced = np.ascontiguousarray(ident[..., 2::-1])
+        del src
+    if reduced is None:
+        # other formats are reduced inside their codecs (JPEG by DCT scaling), and sizes the factor does not divide are
+        # resampled with other weights: the reference's own call, on the host, keeps those bit-exact too
+        flag = {2: cv2.IMREAD_REDUCED_COLOR_2, 4: cv2.IMREAD_REDUCED_COLOR_4, 8: cv2.IMREAD_REDUCED_COLOR_8}.get(downscale, cv2.IMREAD_COLOR)
+        reduced = cv2.imread(filepath, flag)
+        if reduced is None:
+            raise ValueError(f"Failed to read color file: {filepath}")
+    print(f"  Dimensions: {reduced.shape}" + (f" (decoded at 1/{downscale})" if downscale > 1 else ""))
+    if fingerprint is not None:
+        _cache_save(base, reduced, fingerprint)         # (also for a factor OpenCV has no flag for: the full image, as the reference does)
+    return color_texture(reduced, gamma, 1)
 
 
 def load_starmap(filepath: str, target_width: int) -> Optional[np.ndarray]:

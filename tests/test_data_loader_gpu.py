@@ -235,3 +235,27 @@ def test_streamed_tiff_rejects_what_it_cannot_stream(dl, tmp_path):
     with pytest.raises(Exception):
         dl.downscale_elevation_file(raw, 5)                  # 96 is not divisible by 5: numpy's reshape ValueError
     assert not os.path.exists(raw + ".ds5.npy")
+
+
+def test_color_files_the_gpu_reduce_does_not_cover_still_match_opencv(dl, tmp_path):
+    """load_color_data (data_loader.py:290-343) for inputs outside the GPU reduce: a size the factor does not divide, a JPEG
+    (reduced inside the codec) and a factor OpenCV has no flag for - each must give what the reference's own call gives
+    (cv2.imread with the same flag, then _moon_texture), and cache the same BGR image."""
+    import cv2
+    rng = np.random.default_rng(11)
+    col = rng.integers(0, 256, size=(70, 130, 3), dtype=np.int32).astype(np.uint8)
+    odd = str(tmp_path / "odd.tif")
+    cv2.imwrite(odd, col)
+    want = cv2.imread(odd, cv2.IMREAD_REDUCED_COLOR_4)
+    assert np.array_equal(dl.load_color_data(odd, 2.2, 4), orc.load_color(want, 2.2, 1))
+    assert np.array_equal(np.load(odd + ".ds4.npy"), want)
+    smooth = cv2.GaussianBlur(rng.integers(0, 256, size=(64, 128, 3), dtype=np.int32).astype(np.uint8), (0, 0), 3)
+    jpg = str(tmp_path / "c.jpg")
+    cv2.imwrite(jpg, smooth)
+    want = cv2.imread(jpg, cv2.IMREAD_REDUCED_COLOR_2)
+    assert np.array_equal(dl.load_color_data(jpg, 2.2, 2), orc.load_color(want, 2.2, 1))
+    tif = str(tmp_path / "c.tif")
+    cv2.imwrite(tif, col[:64, :128])
+    full = cv2.imread(tif, cv2.IMREAD_COLOR)
+    assert np.array_equal(dl.load_color_data(tif, 2.2, 3), orc.load_color(full, 2.2, 1))          # no flag for 3: full size ...
+    assert np.array_equal(np.load(tif + ".ds3.npy"), full)                                       # ... cached all the same
