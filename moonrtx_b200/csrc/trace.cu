@@ -434,6 +434,9 @@ __global__ void queue_flip_kernel(unsigned* wc) {
 #ifndef MRTX_SQ_MINBLOCKS
 #define MRTX_SQ_MINBLOCKS 8
 #endif
+#ifndef MRTX_SQ_ASCEND
+#define MRTX_SQ_ASCEND false
+#endif
 #ifndef MRTX_SQ_CAND
 #define MRTX_SQ_CAND 10
 #endif
@@ -522,7 +525,7 @@ shadow_kernel(const __grid_constant__ RenderArgs A) {
                 if (ceiling_clear<I16>(A.hf, A.K, A.inv_rs, st, A.hf.dmin, s_off)) finished = true;
             }
             if (!finished) {
-                const int r = walk_step<I16>(A.hf, Rf, A.inv_rs, st, P, sx, face, cnt, nullptr, s_off);
+                const int r = walk_step<I16, false, MRTX_SQ_ASCEND>(A.hf, Rf, A.inv_rs, st, P, sx, face, cnt, nullptr, s_off);
                 if (r == TR_END) finished = true;
                 else if (st.steps > (int)A.sp.long_walk) { finished = true; status = FT_DEFER_R(15); }
                 else if (r == TR_CANDIDATE) mode = SQ_CAND;
