@@ -382,12 +382,35 @@ class Dist:
         rt.comm_init(self.rank, self.world, uid[0])
 
     def p2p_connect(self, rt):
-        """frame delivery through peer memory (copy engines over NVLink): every rank's mailbox handle to every rank"""
+        """frame delivery through peer memory (copy engines over NVLink): every rank's mailbox handle to every rank.
+        Returns False - on every rank - if CUDA IPC is not available to any of them (delivery then uses NCCL)."""
         if self.world == 1:
-            return
+            return True
+        handle, ok = None, 1.0
+        try:
+            handle = rt.p2p_open(self.rank, self.world)
+        except Exception as e:
+            sys.stderr.write(f"rank {self.rank}: peer-memory mailbox not available ({e})\n")
+            ok = 0.0
         handles = [None] * self.world
-        self.dist.all_gather_object(handles, rt.p2p_open(self.rank, self.world))
-        rt.p2p_connect(handles)
+        self.dist.all_gather_object(handles, handle)
+        if ok and all(h is not None for h in handles):
+            try:
+                rt.p2p_connect(handles)
+            except Exception as e:
+                sys.stderr.write(f"rank {self.rank}: cannot map the peers' mailboxes ({e})\n")
+                ok = 0.0
+        else:
+            ok = 0.0
+        t = self.torch.tensor([ok], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        if float(t.item()) < 1.0:
+            try:
+                rt.p2p_close()
+            except Exception:
+                pass
+            return False
+        return True
 
     def close(self):
         if self.world > 1:
@@ -400,13 +423,13 @@ def walked(c):
 
 def launches_per_frame(args):
     """kernels of this library per frame: cull, then per sample chunk and pixel wave trace_kernel_fast + shade_kernel +
-    shadow_kernel + trace_kernel_referee, fold, resolve"""
+    shadow_kernel + trace_kernel_referee + referee_hard_kernel + its finish kernel, fold, resolve"""
     chunks = (args.spp + 31) // 32
     per_chunk = min(args.spp, 32)
     npix = args.img_w * args.img_h
     cap = min(npix * per_chunk, 1 << 26)
     waves = -(-npix // (cap // per_chunk))
-    return 1 + 4 * chunks * waves + 1 + 1
+    return 1 + 6 * chunks * waves + 1 + 1
 
 
 # ------------------------------------------------------------------------------------------------
@@ -485,8 +508,8 @@ def run_frames(args):
     dev = rt._dev
     lib, ctx = dev.lib, dev.ctx
     D.comm_init(rt)
-    if args.delivery == "p2p":
-        D.p2p_connect(rt)
+    if args.delivery == "p2p" and not D.p2p_connect(rt):
+        args.delivery = "nccl"
     n_warm, n_timed = args.warmup * FRAMES_PER_STEP, args.steps * FRAMES_PER_STEP
     frames = list(range(n_warm + n_timed))
     mine_warm = [f for f in frames[:n_warm] if f % world == rank]

@@ -209,6 +209,9 @@ int  mrtx_frame_recv_wait(mrtx_ctx* ctx, int ticket);
  * back.  No SM takes part.  Same tickets, same ordering rules as above.  Works with or without mrtx_comm_init.       */
 int  mrtx_p2p_open(mrtx_ctx* ctx, int nranks, int rank, size_t slot_bytes, uint8_t handle_out[64]);
 int  mrtx_p2p_connect(mrtx_ctx* ctx, const uint8_t* handles);
+/* unmaps the peers' mailboxes and frees this rank's: frame delivery goes back to NCCL point-to-point (every rank must do the
+ * same, with no frame in flight)                                                                                          */
+int  mrtx_p2p_close(mrtx_ctx* ctx);
 /* rt._get_hit_at(x, y) -> (hx, hy, hz, hd), moon_renderer.py:1138; hd <= 0 = miss.     */
 int  mrtx_hit_at(mrtx_ctx* ctx, int x, int y, float out4[4]);
 /* device views of the frame buffers (for collectives and zero-copy consumers)        */

@@ -74,6 +74,7 @@ _SIGNATURES = {
     "mrtx_set_tubes": (C.c_int, [c_ctx, C.c_void_p, C.c_int]),
     "mrtx_p2p_open": (C.c_int, [c_ctx, C.c_int, C.c_int, C.c_size_t, C.POINTER(C.c_uint8)]),
     "mrtx_p2p_connect": (C.c_int, [c_ctx, C.POINTER(C.c_uint8)]),
+    "mrtx_p2p_close": (C.c_int, [c_ctx]),
     "mrtx_read_rgba8": (C.c_int, [c_ctx, C.c_void_p]),
     "mrtx_read_accum_f32": (C.c_int, [c_ctx, C.c_void_p]),
     "mrtx_read_hit_f32": (C.c_int, [c_ctx, C.c_void_p]),

@@ -355,6 +355,14 @@ int mrtx_p2p_connect(mrtx_ctx* ctx, const uint8_t* handles) {
     return MRTX_OK;
 }
 
+int mrtx_p2p_close(mrtx_ctx* ctx) {
+    MRTX_CTX(ctx);
+    MRTX_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->comm_stream) MRTX_CUDA(cudaStreamSynchronize(ctx->comm_stream));
+    p2p_release(ctx);
+    return MRTX_OK;
+}
+
 // queue on `st`: wait until the consumer has emptied the slot, copy the frame into it, publish its sequence number
 int p2p_send_frame(mrtx_ctx* ctx, const void* frame_dev, size_t bytes, int dst, cudaStream_t st) {
     MRTX_REQUIRE(ctx->p2p_on && bytes <= ctx->p2p_slot_bytes, "frame of %zu bytes does not fit the %zu-byte mailbox slots", bytes, ctx->p2p_slot_bytes);

@@ -478,6 +478,11 @@ class B200OptiX:
         with self._padlock:
             _lib.check(self._lib.mrtx_p2p_connect(self._ctx, buf))
 
+    def p2p_close(self) -> None:
+        """Give the mailboxes up (all ranks, no frame in flight): delivery goes back to ncclSend / ncclRecv."""
+        with self._padlock:
+            _lib.check(self._lib.mrtx_p2p_close(self._ctx))
+
     def render_cycle(self, read_back: bool = True, shard: Optional[str] = None,
                      tile_rows: int = 64, tile: int = 64) -> Optional[np.ndarray]:
         """
