@@ -78,6 +78,9 @@ beam_kernel(const __grid_constant__ RenderArgs A) {
 #ifndef MRTX_PHASE_STATS
 #define MRTX_PHASE_STATS 0
 #endif
+#ifndef MRTX_DEFER_PER_SAMPLE
+#define MRTX_DEFER_PER_SAMPLE 0      // (one list entry per deferred sample instead of per pixel: measured, no difference)
+#endif
 #ifndef MRTX_FAST_MINBLOCKS
 #define MRTX_FAST_MINBLOCKS 8
 #endif
@@ -280,13 +283,22 @@ trace_kernel_fast(const __grid_constant__ RenderArgs A) {
                     }
                 }
             }
-            // deferred samples of each pixel -> its leader's mask (bit = sample index in this launch)
+            // a deferred sample -> its own entry of the deferred list (pixel, bit = sample index in this launch): the referee
+            // gives every entry a warp, and the samples of a limb pixel - where several defer at once - are each a long chain
+#if MRTX_DEFER_PER_SAMPLE
+            if (defer) {
+                const unsigned slot = atomicAdd(&A.work_counter[3], 1u);
+                if (slot < A.list_cap) A.defer_list[slot] = make_uint2(packed, 1u << k);
+                ++n_defer;
+            }
+#else
             const unsigned dm = __ballot_sync(FULL, defer);
             if (dm) {
                 const unsigned gm = g == 32 ? dm : (dm >> (pw << gl)) & ((1u << g) - 1u);
                 dmask |= gm << (rd << gl);
                 if (defer) ++n_defer;
             }
+#endif
         }
         // per-pixel sum over the group's lanes, one read-modify-write per pixel
         for (int o = g >> 1; o > 0; o >>= 1) {
@@ -317,8 +329,11 @@ trace_kernel_fast(const __grid_constant__ RenderArgs A) {
 // and the density cancel and the path's throughput is just multiplied by the albedo), pushed to the bounce queue; bounce_kernel
 // traces that queue to its first hits, which come back here with BOUNCE = true: ray and throughput are read from the bounce
 // ray's queue entry, the direct light at the new hit is weighted with the throughput and goes through the same shadow queue.
+#ifndef MRTX_SHADE_MINBLOCKS
+#define MRTX_SHADE_MINBLOCKS 2
+#endif
 template <bool I16, bool BOUNCE, bool SPAWN>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, MRTX_SHADE_MINBLOCKS)
 shade_kernel(const __grid_constant__ RenderArgs A) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
