@@ -26,6 +26,9 @@
 namespace mrtx_core {
 
 enum { FT_MISS = 0, FT_HIT = 1, FT_DEFER = 2 };
+#if defined(MRTX_LEVEL_HIST) && !defined(__CUDA_ARCH__)
+extern unsigned long long g_level_hist[32];
+#endif
 // A walk longer than SceneParams::long_walk nodes (default 2048) is a grazing ray among polar slivers (cells
 // centimetres wide): tens of thousands of nodes, one dependent fetch after the other, in ONE lane.  It is handed to
 // the referee (reason 15), whose warp cuts the ray into pieces and walks them side by side.
@@ -538,6 +541,9 @@ MRTX_HD inline int walk_step(const HeightField& hf, float Rf, float inv_rs, Walk
     const int W = hf.W, H = hf.H;
     const float s = w.s;
     ++cnt.nodes;
+#if defined(MRTX_LEVEL_HIST) && !defined(__CUDA_ARCH__)
+    __atomic_fetch_add(&g_level_hist[L], 1ull, __ATOMIC_RELAXED);      // host tool: node visits by level (tools/trace_host.cu)
+#endif
     // The walls ahead depend on (L, J, I) and the ray's headings only: their table entries are requested here,
     // together with the node itself, so that one memory latency covers all three (the loop is latency-bound).
     const bool north = fmaf(s, w.n1, w.n0) > 0.0f;

@@ -1,13 +1,20 @@
 // DEVELOPMENT TOOL (not part of the product, never loaded by moonrtx_b200): runs the
 // __host__ __device__ traversal core of csrc/trace_core.cuh on the CPU so that parity
 // problems can be investigated against the oracle without a GPU.
+#define MRTX_LEVEL_HIST 1
 #include "../moonrtx_b200/csrc/trace_fast.cuh"
 #include <vector>
 #include <algorithm>
 
 void mrtx_set_error(const char*, ...) {}
 
+namespace mrtx_core { unsigned long long g_level_hist[32]; }
 using namespace mrtx_core;
+
+// node visits of the filtered walk by pyramid level since the last reset (walk_step, MRTX_LEVEL_HIST)
+extern "C" void dbg_level_hist(unsigned long long* out32, int reset) {
+    for (int i = 0; i < 32; ++i) { out32[i] = g_level_hist[i]; if (reset) g_level_hist[i] = 0; }
+}
 
 // all levels and their dilated copies in ONE buffer (the walk addresses them as element offsets from hf.lvl_base)
 template <typename T>
