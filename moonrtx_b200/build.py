@@ -58,7 +58,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if failed:
         raise RuntimeError("libmoonb200 build failed")
     if force or procs or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-ldl", "-Xcompiler", "-fPIC"]
+        cmd = [nvcc, "-shared", "-Wno-deprecated-gpu-targets", "-o", LIB] + objs + ["-ldl", "-Xcompiler", "-fPIC"]
         subprocess.run(cmd, check=True)
     return LIB
 
