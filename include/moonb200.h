@@ -126,7 +126,7 @@ int  mrtx_set_texture_rgba8(mrtx_ctx* ctx, int slot, const uint8_t* rgba, int W,
  * list, scene space: n x 12 floats = (ax, ay, az, r, bx, by, bz, 0, red, green, blue, 0).  A segment is a capsule of radius
  * r; it is flat-shaded (the colour is the radiance of a camera sample that meets it before the surface), it casts no shadow
  * and receives none (the reference's material lets shadow rays through, renderer_labels.py:133-139).  n = 0 removes them.
- * The list is binned to 32 x 32-pixel screen tiles for the camera of every launch.                                        */
+ * The list is binned to 16 x 16-pixel screen tiles for the camera of every launch.                                        */
 int  mrtx_set_tubes(mrtx_ctx* ctx, const float* segments, int n);
 /* What rays that miss the Moon see.
  * rt.set_background_mode("TextureEnvironment") + rt.set_background(float32[h][w][3] in [0, 1], gamma=g,

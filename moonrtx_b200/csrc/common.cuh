@@ -45,7 +45,7 @@ void mrtx_set_error(const char* fmt, ...);
 #define MRTX_TILED 0            // development switch: pyramid levels also in 8 x 8-cell tiles, walked by the filtered kernels (measured: no gain)
 #endif
 #define MRTX_P2P_MAX_RANKS 64
-#define MRTX_TUBE_TILE_LOG2 5    // screen tiles of the overlay-tube bins: 32 x 32 pixels ...
+#define MRTX_TUBE_TILE_LOG2 4    // screen tiles of the overlay-tube bins: 16 x 16 pixels ...
 #define MRTX_TUBE_TILE_CAP 62     // ... listing up to this many segments each (more: every segment is tested)
 #define MRTX_PROF_EVENTS 8       // before cull, after cull, beam, trace_kernel_fast, shade_kernel, shadow_kernel, referee, fold
 #define MRTX_MAX_LEVELS 20
@@ -156,7 +156,7 @@ struct mrtx_ctx {
 
     // overlay tubes (grid lines, labels, pins: rt.set_graph, renderer_labels.py:263-305, renderer_pins.py:18-55): capsule
     // segments in scene space, flat-shaded, never occluders of the sun.  tube_seg: 3 float4 per segment (a.xyz, r; b.xyz, -;
-    // colour.rgb, -); tube_tiles: per 32 x 32-pixel screen tile a count and up to MRTX_TUBE_TILE_CAP segment indices,
+    // colour.rgb, -); tube_tiles: per 16 x 16-pixel screen tile a count and up to MRTX_TUBE_TILE_CAP segment indices,
     // rebuilt for the camera of every launch (tube_bin_kernel)
     float4* tube_seg; unsigned n_tubes, tube_cap;
     unsigned* tube_tiles; int tube_tx, tube_ty;

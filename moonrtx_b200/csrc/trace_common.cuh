@@ -290,9 +290,21 @@ __device__ __noinline__ bool tube_nearest(const RenderArgs& A, int x, int y, uin
     const unsigned n = all ? A.n_tubes : cnt;
     double best = s_max;
     int which = -1;
+    const float dfx = (float)d[0], dfy = (float)d[1], dfz = (float)d[2];
+    const float efx = (float)cam.eye[0], efy = (float)cam.eye[1], efz = (float)cam.eye[2];
     for (unsigned i = 0; i < n; ++i) {
         const unsigned k = all ? i : __ldg(L + 1 + i);
         const float4 sa = __ldg(A.tubes + 3 * (size_t)k), sb = __ldg(A.tubes + 3 * (size_t)k + 1);
+        {
+            // float32 filter: a ray further from the capsule's AXIS LINE than its radius (+ 1e-3: thirty times what float32
+            // loses on coordinates of this size) cannot meet it; the float64 test below is for the few that come close
+            const float ux = sb.x - sa.x, uy = sb.y - sa.y, uz = sb.z - sa.z;
+            const float nx = dfy * uz - dfz * uy, ny = dfz * ux - dfx * uz, nz = dfx * uy - dfy * ux;
+            const float nn = nx * nx + ny * ny + nz * nz;
+            const float wx = sa.x - efx, wy = sa.y - efy, wz = sa.z - efz;
+            const float wn = wx * nx + wy * ny + wz * nz, lim = sa.w + 1.0e-3f;
+            if (nn > 1.0e-12f * (ux * ux + uy * uy + uz * uz) && wn * wn > lim * lim * nn) continue;
+        }
         const double t = capsule_hit(cam.eye, d, sa, sb);
         if (t > 0.0 && t < best) { best = t; which = (int)k; }
     }
