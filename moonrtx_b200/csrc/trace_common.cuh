@@ -502,15 +502,18 @@ __device__ MRTX_MISS_ATTR float3 miss_radiance(const RenderArgs& A, double dx, d
     }
     if (!A.env.data) return make_float3(0.f, 0.f, 0.f);
     const int w = A.env.W, h = A.env.H;
-    const double lon = atan2(dx, -dy), lat = asin(fmin(fmax(dz, -1.0), 1.0));
-    const double u = (lon * (0.5 / PI_D) + 0.5) * w - 0.5, v = (0.5 - lat * (1.0 / PI_D)) * h - 0.5;
-    const double fu = floor(u);
+    // (float32 angles: 1e-7 rad is 3e-4 texel of a 16k star map - the lookup runs for every sample of every pixel beside the
+    //  Moon, 85 M times per 4K frame)
+    const float fx = (float)dx, fy = (float)dy, fz = (float)dz;
+    const float lon = atan2f(fx, -fy), lat = atan2f(fz, sqrtf(fx * fx + fy * fy));
+    const float u = (lon * (0.5f / PI_F) + 0.5f) * (float)w - 0.5f, v = (0.5f - lat * (1.0f / PI_F)) * (float)h - 0.5f;
+    const float fu = floorf(u);
     int c0 = (int)fu;
-    const float fc = (float)(u - fu);
+    const float fc = u - fu;
     c0 = c0 < 0 ? c0 + w : (c0 >= w ? c0 - w : c0);
     const int c1 = c0 + 1 == w ? 0 : c0 + 1;
-    const int r0 = min(max((int)floor(v), 0), h - 2);
-    const float fr = fminf(fmaxf((float)(v - (double)r0), 0.0f), 1.0f);
+    const int r0 = min(max((int)floorf(v), 0), h - 2);
+    const float fr = fminf(fmaxf(v - (float)r0, 0.0f), 1.0f);
     const uchar4 a = __ldg(A.env.data + (size_t)r0 * w + c0), b = __ldg(A.env.data + (size_t)r0 * w + c1);
     const uchar4 c = __ldg(A.env.data + (size_t)(r0 + 1) * w + c0), e = __ldg(A.env.data + (size_t)(r0 + 1) * w + c1);
     const float s = 1.0f / 255.0f;
