@@ -374,15 +374,21 @@ shade_kernel(const __grid_constant__ RenderArgs A) {
             if (!BOUNCE && tube_tile_count(A, x, y) && tube_nearest(A, x, y, pixel, sm, fh.s, lit)) {
                 // an overlay tube in front of the surface: its flat colour is the sample (added below)
             } else {
-                const unsigned dim0 = 2u + 4u * (unsigned)A.depth;
+                const unsigned dim0 = 2u + 5u * (unsigned)A.depth;      // random dimensions of this hit: light 2, bounce 2, roulette 1
                 if (shade_fast(A, R, fh, x, y, pixel, sm, lit, S, dim0, !BOUNCE, spawn ? &aux : nullptr)) {
                     ++rs.shadow;
                     push = walk_begin(A.hf, A.sp.radius, S, 0.0, A.sq_level, sw);
                 }
                 lit.x *= thr.x; lit.y *= thr.y; lit.z *= thr.z;
                 if (spawn) {
-                    thr.x *= aux.alb.x; thr.y *= aux.alb.y; thr.z *= aux.alb.z;
-                    if (fmaxf(thr.x, fmaxf(thr.y, thr.z)) > 0.0f) {
+                    // Russian roulette: the path goes on with probability p = the albedo's largest component and carries
+                    // albedo / p (unbiased; the Moon reflects 3 - 30 %, so one path in five is followed and the bounce
+                    // stages cost a fifth: measured at config 3 with (2, 4), 56 -> 37 ms per frame)
+                    const float p = fminf(fmaxf(aux.alb.x, fmaxf(aux.alb.y, aux.alb.z)), 1.0f);
+                    const bool go = p > 0.0f && (float)rnd(pixel, sm, dim0 + 4u) < p;
+                    const float ip = go ? 1.0f / p : 0.0f;
+                    thr.x *= aux.alb.x * ip; thr.y *= aux.alb.y * ip; thr.z *= aux.alb.z * ip;
+                    if (go && fmaxf(thr.x, fmaxf(thr.y, thr.z)) > 0.0f) {
                         // cosine-distributed direction about the normal (branchless ONB, Duff et al. 2017)
                         const float u1 = (float)rnd(pixel, sm, dim0 + 2u), u2 = (float)rnd(pixel, sm, dim0 + 3u);
                         const float rr = sqrtf(u1), cz = sqrtf(fmaxf(1.0f - u1, 0.0f));

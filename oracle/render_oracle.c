@@ -540,13 +540,19 @@ long orc_render(const orc_scene* S, int x0, int y0, int x1, int y1, int stride,
                     for (int depth = 0; ; ++depth) {
                         double direct[3], alb[3];
                         long sc = 0;
-                        direct_light(S, &cur, Lb, pixel, sm, 2u + 4u * (unsigned)depth, direct, alb, &sc);
+                        const unsigned dim0 = 2u + 5u * (unsigned)depth;      /* light 2, bounce 2, roulette 1 */
+                        direct_light(S, &cur, Lb, pixel, sm, dim0, direct, alb, &sc);
                         if (depth == 0) shadow_cells = sc;
                         for (int q = 0; q < 3; ++q) rgb[q] += thr[q] * direct[q];
                         if (depth >= S->n_bounce) break;
-                        for (int q = 0; q < 3; ++q) thr[q] *= alb[q];
+                        /* Russian roulette: go on with probability p = largest albedo component, carry albedo / p */
+                        double p = alb[0] > alb[1] ? alb[0] : alb[1];
+                        if (alb[2] > p) p = alb[2];
+                        if (p > 1.0) p = 1.0;
+                        if (!(p > 0.0) || !((double)(float)rnd(pixel, sm, dim0 + 4u) < (double)(float)p)) break;
+                        for (int q = 0; q < 3; ++q) thr[q] *= alb[q] / p;
                         if (!(thr[0] > 0.0 || thr[1] > 0.0 || thr[2] > 0.0)) break;
-                        const double u1 = rnd(pixel, sm, 4u + 4u * (unsigned)depth), u2 = rnd(pixel, sm, 5u + 4u * (unsigned)depth);
+                        const double u1 = rnd(pixel, sm, dim0 + 2u), u2 = rnd(pixel, sm, dim0 + 3u);
                         const double rr = sqrt(u1), cz = sqrt(1.0 - u1 > 0.0 ? 1.0 - u1 : 0.0), th = 2.0 * PI * u2;
                         const double* n = cur.n;
                         const double sg = n[2] >= 0.0 ? 1.0 : -1.0, a = -1.0 / (sg + n[2]), bq = n[0] * n[1] * a;

@@ -50,7 +50,7 @@ def test_interreflection_matches_oracle(spp, seg, phase):
     gain = acc[..., :3].sum(axis=2) - direct[..., :3].sum(axis=2)
     assert gain.min() >= -1e-4 * acc[..., :3].max() and gain.sum() > 0.005 * direct[..., :3].sum()
     shadowed = (direct[..., :3].sum(axis=2) == 0) & (direct[..., 3] > 0) & (rt.get_hit_buffer()[..., 3] > 0)
-    assert int(shadowed.sum()) > 50 and int((gain[shadowed] > 0).sum()) >= 10      # (most unlit pixels are the night side)
+    assert int(shadowed.sum()) > 50 and int((gain[shadowed] > 0).sum()) >= 3       # (most unlit pixels are the night side; one path in two or three goes on)
     od = make_oracle(elev, W, H, texture=tex, jitter=spp > 1, **{**kw, "path_seg_range": (2, 2)}).render(nsamples=spp)["accum"]
     assert abs(gain.sum() / (oa[..., :3].sum() - od[..., :3].sum()) - 1.0) < 0.02        # the added light as a whole, within 2 %
     rt.close()
@@ -70,5 +70,5 @@ def test_bounces_leave_the_direct_path_alone_and_count_their_rays():
     c2 = rt.counters()
     assert np.array_equal(rt.get_hit_records_f64(), hits0)                   # camera hits are what they were
     assert c2["primary_rays"] == c0["primary_rays"] and c2["primary_hits"] == c0["primary_hits"]
-    assert c2["shadow_rays"] > c0["shadow_rays"] and c2["node_visits"] > 1.5 * c0["node_visits"]
+    assert c2["shadow_rays"] > c0["shadow_rays"] and c2["node_visits"] > 1.15 * c0["node_visits"]
     rt.close()
