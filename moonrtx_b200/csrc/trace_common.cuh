@@ -817,13 +817,7 @@ trace_kernel_referee(const __grid_constant__ RenderArgs A) {
             bool fast = false, entered = false;
             FastHit fh;
             TraceOut h;
-#ifdef MRTX_REFEREE_TIMING
-            const long long tt0 = clock64();
-#endif
             const int who = referee_ray<I16>(A, stack, R, 0.0, A.hf.top - 3, false, fast, fh, h, cnt, entered);
-#ifdef MRTX_REFEREE_TIMING
-            if (lane == 0) atomicMax(&A.defer_stats[26], (unsigned long long)(clock64() - tt0));
-#endif
             if (lane == 0) { ++rs.primary; if (entered) ++rs.inside; }
             if (who < 0) {
                 if (lane == 0) {
@@ -853,14 +847,8 @@ trace_kernel_referee(const __grid_constant__ RenderArgs A) {
                 S.oo = S.ox * S.ox + S.oy * S.oy + S.oz * S.oz;
                 S.od = S.ox * S.dx + S.oy * S.dy + S.oz * S.dz;
                 int n_left = 0;
-#ifdef MRTX_REFEREE_TIMING
-                const long long tt1 = clock64();
-#endif
                 const int sr = referee_ray<I16>(A, stack, S, 0.0, 2, true, fast, fh, h, cnt, entered,
                                                 !WAVE && A.hard ? MRTX_HARD_ROUNDS : 0x7fffffff, &n_left);
-#ifdef MRTX_REFEREE_TIMING
-                if (lane == 0) atomicMax(&A.defer_stats[27], (unsigned long long)(clock64() - tt1));
-#endif
                 occluded = sr >= 0;
                 if (sr == -2) {
                     // too long a chain for one warp: the grid finishes it (referee_hard_kernel adds lit if the sun is visible)
