@@ -29,6 +29,10 @@
  * crossings, and inside a cell the first root of f(s) = |p(s)| - R*bilinear(u(s), v(s))
  * is bracketed on a fine subdivision (with a local-minimum probe for grazing double
  * roots) and polished by bisection-safeguarded secant steps, all in float64.
+ * Around the Moon: rays that miss it see the Sun disk / the star map (N1); overlay tubes are capsules tested
+ * one by one against every camera sample (N4); with n_bounce > 0 a path continues from every hit in a cosine-distributed
+ * direction, by Russian roulette on the albedo, and collects the direct light of the hits it finds (N2) - the same random
+ * dimensions as the product, so that paths can be compared sample for sample.
  */
 
 #include <math.h>
