@@ -382,8 +382,8 @@ shade_kernel(const __grid_constant__ RenderArgs A) {
                 lit.x *= thr.x; lit.y *= thr.y; lit.z *= thr.z;
                 if (spawn) {
                     // Russian roulette: the path goes on with probability p = the albedo's largest component and carries
-                    // albedo / p (unbiased; the Moon reflects 3 - 30 %, so one path in five is followed and the bounce
-                    // stages cost a fifth: measured at config 3 with (2, 4), 56 -> 37 ms per frame)
+                    // albedo / p (unbiased; the Moon reflects 3 - 30 %, so one path in three to five is followed: measured at
+                    // config 3 with (2, 4), 56 -> 44 ms per frame)
                     const float p = fminf(fmaxf(aux.alb.x, fmaxf(aux.alb.y, aux.alb.z)), 1.0f);
                     const bool go = p > 0.0f && (float)rnd(pixel, sm, dim0 + 4u) < p;
                     const float ip = go ? 1.0f / p : 0.0f;
