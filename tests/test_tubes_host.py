@@ -100,3 +100,24 @@ def test_reference_grid_flattens_to_the_segment_list():
     assert np.allclose(seg[:len(edges), 0:3], pos[edges[:, 0]], atol=1e-6) and np.allclose(seg[:len(edges), 4:7], pos[edges[:, 1]], atol=1e-6)
     assert np.all(seg[:len(edges), 3] == np.float32(0.006)) and np.all(seg[len(edges):, 3] == np.float32(0.012))
     assert np.allclose(seg[len(edges):, 8:11], (1, 0, 0))
+
+
+def test_tube_segments_flattening_rules():
+    """rt.set_graph arguments -> the segment list: one radius or one per vertex (0 hides, the smaller end wins), one colour, a
+    grey level or one colour per vertex; geometry that is no graph, or has no edges, contributes nothing."""
+    from moonrtx_b200.optix import tube_segments
+    pos = np.array([[0, 0, 10.0], [1, 0, 10.0], [2, 0, 10.0], [3, 0, 10.0]])
+    edges = np.array([[0, 1], [1, 2], [2, 3]])
+    seg = tube_segments({"a": {"geom": "Graph", "pos": pos, "edges": edges, "r": 0.02, "c": 0.5}})
+    assert seg.shape == (3, 12) and np.all(seg[:, 3] == np.float32(0.02)) and np.allclose(seg[:, 8:11], 0.5)
+    assert np.allclose(seg[1, 0:3], pos[1]) and np.allclose(seg[1, 4:7], pos[2]) and np.all(seg[:, [7, 11]] == 0)
+    seg = tube_segments({"a": {"geom": "Graph", "pos": pos, "edges": edges, "r": [0.02, 0.02, 0.0, 0.01],
+                               "c": [[1, 0, 0], [0, 1, 0], [0, 0, 1], [1, 1, 1]]}})
+    assert seg.shape == (1, 12) and np.allclose(seg[0, 8:11], (1, 0, 0))                 # edges touching the hidden vertex are gone
+    assert len(tube_segments({"m": {"geom": "ParticleSetTextured"}, "e": {"geom": "Graph", "pos": pos, "edges": np.zeros((0, 2), int)},
+                              "n": {"geom": "Graph", "pos": None, "edges": None}})) == 0
+    with pytest.raises(ValueError):
+        tube_segments({"a": {"geom": "Graph", "pos": pos, "edges": edges, "r": [0.1, 0.2]}})
+    two = tube_segments({"a": {"geom": "Graph", "pos": pos, "edges": edges[:1], "r": 0.01, "c": [1, 0, 0]},
+                         "b": {"geom": "Graph", "pos": pos, "edges": edges[1:], "r": 0.03, "c": [0, 0, 1]}})
+    assert two.shape == (3, 12) and sorted(np.unique(two[:, 3]).tolist()) == [np.float32(0.01), np.float32(0.03)]
