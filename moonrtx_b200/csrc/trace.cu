@@ -380,7 +380,16 @@ shade_kernel(const __grid_constant__ RenderArgs A) {
                     push = walk_begin(A.hf, A.sp.radius, S, 0.0, A.sq_level, sw);
                 }
                 lit.x *= thr.x; lit.y *= thr.y; lit.z *= thr.z;
+                // A path that leaves a point deep in the night finds nothing lit (night_sin2(), host side): every further hit
+                // of it would have zero direct light.  Exact, not a cut-off: such paths end here.
+                bool night = false;
                 if (spawn) {
+                    const double rp2 = aux.px * aux.px + aux.py * aux.py + aux.pz * aux.pz;
+                    const double lx = A.light_b[0] - aux.px, ly = A.light_b[1] - aux.py, lz = A.light_b[2] - aux.pz;
+                    const double pl = aux.px * lx + aux.py * ly + aux.pz * lz;
+                    night = pl < 0.0 && pl * pl > (double)A.night_sin2 * rp2 * (lx * lx + ly * ly + lz * lz);
+                }
+                if (spawn && !night) {
                     // Russian roulette: the path goes on with probability p = the albedo's largest component and carries
                     // albedo / p (unbiased; the Moon reflects 3 - 30 %, so one path in three to five is followed: measured at
                     // config 3 with (2, 4), 56 -> 44 ms per frame)
@@ -674,6 +683,16 @@ static int ensure_queues(mrtx_ctx* ctx, size_t items, size_t hit_slots, bool bou
     return MRTX_OK;
 }
 
+// sin^2 of the Sun's depression below the horizon of the SPHERE beyond which a path with `left` more bounces cannot reach lit
+// terrain: alpha = acos(Rmin / Rmax) is how far beyond the terminator terrain still sees the Sun and half of how far apart two
+// surface points can see each other, so lit terrain lies within (1 + 2 left) alpha of the path's present hit (+ 1 degree for
+// the Sun's disk and its finite distance)
+static float night_sin2(const mrtx_ctx* ctx, int left) {
+    const double alpha = acos(std::min(1.0, (double)ctx->hf.dmin / (double)ctx->hf.dmax));
+    const double sn = sin(std::min((1.0 + 2.0 * left) * alpha + 0.0175, 1.5707));
+    return (float)(sn * sn);
+}
+
 template <bool I16, int MODE>
 static int launch_fast(mrtx_ctx* ctx, RenderArgs& A, long long npix) {
     int per_sm = 0;
@@ -763,6 +782,7 @@ static int launch_trace_t(mrtx_ctx* ctx, RenderArgs& A, unsigned s0, unsigned ns
             if (first) prof_mark(ctx, 3);
             A.depth = 0; A.n_bounce = n_bounce;
             if (n_bounce) {
+                A.night_sin2 = night_sin2(ctx, n_bounce);
                 A.bq_out_rays = (RayRec*)ctx->bq_buf[0]; A.bq_out_aux = (uint4*)((char*)ctx->bq_buf[0] + ctx->bq_cap * sizeof(RayRec));
                 MRTX_CUDA(cudaMemsetAsync(A.work_counter + 8, 0, 3 * sizeof(unsigned), ctx->stream));
             }
@@ -777,6 +797,7 @@ static int launch_trace_t(mrtx_ctx* ctx, RenderArgs& A, unsigned s0, unsigned ns
             for (int d = 1; d <= n_bounce; ++d) {
                 queue_flip_kernel<<<1, 1, 0, ctx->stream>>>(A.work_counter);
                 A.depth = d;
+                A.night_sin2 = night_sin2(ctx, n_bounce - d);
                 void* in = ctx->bq_buf[(d - 1) & 1]; void* out = ctx->bq_buf[d & 1];
                 A.bq_in_rays = (RayRec*)in; A.bq_in_aux = (uint4*)((char*)in + ctx->bq_cap * sizeof(RayRec));
                 A.bq_out_rays = (RayRec*)out; A.bq_out_aux = (uint4*)((char*)out + ctx->bq_cap * sizeof(RayRec));

@@ -84,6 +84,7 @@ struct RenderArgs {
     // ([10] rays); their aux entries carry the path's throughput.  depth: 0 = camera hits, d = hits of the d-th bounce
     struct RayRec* bq_in_rays; uint4* bq_in_aux; struct RayRec* bq_out_rays; uint4* bq_out_aux;
     int depth, n_bounce;
+    float night_sin2;                // sin^2 of the Sun's depression beyond which a path cannot reach lit terrain (shade_kernel)
     struct HardRay* hard;            // shadow rays handed from trace_kernel_referee to referee_hard_kernel (work_counter[12] of them)
     // hit queue (shadow_queue = 2): primary hits pushed by trace_kernel_fast (work_counter[7] of them), shaded by shade_kernel
     struct HitQRec* hq; unsigned hq_cap;
