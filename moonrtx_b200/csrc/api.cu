@@ -76,7 +76,7 @@ int mrtx_create(int device, mrtx_ctx** out_ctx) {
     sp.light_pos[0] = 21460.0; sp.light_radius = 100.0; sp.light_radiance = 80.0 * 460.5316;
     sp.scene_epsilon = 1.0e-4;
     sp.exposure = 0.9f; sp.inv_gamma = 1.0f / 2.2f;
-    sp.jitter = 0; sp.shadows = 1; sp.debug_hits = 0; sp.kernel = 2; sp.beam = 0; sp.beam_drop = 2; sp.ceiling = 0; sp.shadow_queue = 2; sp.start_primary = 3; sp.start_shadow = 2; sp.long_walk = 2048u; sp.referee_budget = 500u; sp.hard_rays = 1u;
+    sp.jitter = 0; sp.shadows = 1; sp.debug_hits = 0; sp.kernel = 2; sp.beam = 0; sp.beam_drop = 2; sp.ceiling = 0; sp.shadow_queue = 3; sp.start_primary = 3; sp.start_shadow = 2; sp.long_walk = 2048u; sp.referee_budget = 500u; sp.hard_rays = 1u;
     const double eye[3] = {0, -300, 0}, tgt[3] = {0, 0, 0}, up[3] = {0, 0, 1};
     mrtx_set_camera(c, eye, tgt, up, 4.242192793);
     *out_ctx = c;
@@ -84,10 +84,10 @@ int mrtx_create(int device, mrtx_ctx** out_ctx) {
 }
 
 static void free_frame(mrtx_ctx* c) {
-    cudaFree(c->accum); cudaFree(c->rgba8); cudaFree(c->hit); cudaFree(c->hit64); cudaFree(c->pixel_list); cudaFree(c->defer_list);
+    cudaFree(c->accum); cudaFree(c->rgba8); cudaFree(c->hit); cudaFree(c->hit64); cudaFree(c->pixel_list); cudaFree(c->defer_list); cudaFree(c->defer_mask);
     cudaFree(c->beam_s); cudaFree(c->beam_l); cudaFree(c->accfix);
     c->accfix = nullptr;
-    c->pixel_list = nullptr; c->defer_list = nullptr; c->beam_s = nullptr; c->beam_l = nullptr;
+    c->pixel_list = nullptr; c->defer_list = nullptr; c->defer_mask = nullptr; c->beam_s = nullptr; c->beam_l = nullptr;
     c->accum = nullptr; c->rgba8 = nullptr; c->hit = nullptr; c->hit64 = nullptr;
 }
 
@@ -112,7 +112,7 @@ int mrtx_destroy(mrtx_ctx* ctx) {
     cudaFree(ctx->d_counters);
     cudaFree(ctx->d_defer_stats);
     cudaFree(ctx->wave_buf);
-    cudaFree(ctx->sq_buf); cudaFree(ctx->hq_buf); cudaFree(ctx->bq_buf[0]); cudaFree(ctx->bq_buf[1]);
+    cudaFree(ctx->sq_buf); cudaFree(ctx->hq_buf); cudaFree(ctx->bq_buf[0]); cudaFree(ctx->bq_buf[1]); cudaFree(ctx->pool_buf);
     cudaFree(ctx->tube_seg); cudaFree(ctx->tube_tiles);
     if (ctx->prof_ev) { for (int i = 0; i < MRTX_PROF_MAX * MRTX_PROF_EVENTS; ++i) cudaEventDestroy(ctx->prof_ev[i]); free(ctx->prof_ev); }
     cudaFree(ctx->flush_buf);
@@ -837,7 +837,7 @@ int mrtx_set_uint(mrtx_ctx* ctx, const char* name, unsigned a, unsigned b) {
     else if (!strcmp(name, "ceiling")) ctx->sp.ceiling = a;
     else if (!strcmp(name, "profile")) ctx->prof_on = a ? 1 : 0;
     else if (!strcmp(name, "blocks_per_sm")) ctx->sp.blocks_per_sm = a;
-    else if (!strcmp(name, "shadow_queue")) ctx->sp.shadow_queue = a > 2u ? 2u : a;
+    else if (!strcmp(name, "shadow_queue")) ctx->sp.shadow_queue = a > 3u ? 3u : a;
     else if (!strcmp(name, "beam")) { ctx->sp.beam = a ? 1u : 0u; ctx->sp.beam_drop = b; }
     else if (!strcmp(name, "kernel")) { MRTX_REQUIRE(a <= 3u, "kernel must be 0, 1, 2 or 3"); ctx->sp.kernel = a; }
     else { mrtx_set_error("unknown uint parameter '%s'", name); return MRTX_ERR_INVALID; }
@@ -866,6 +866,8 @@ static int alloc_frame(mrtx_ctx* ctx, size_t n) {
     MRTX_CUDA(cudaMalloc(&ctx->hit, n * sizeof(float4)));
     MRTX_CUDA(cudaMalloc(&ctx->pixel_list, n * sizeof(unsigned)));
     MRTX_CUDA(cudaMalloc(&ctx->defer_list, n * sizeof(uint2)));
+    MRTX_CUDA(cudaMalloc(&ctx->defer_mask, n * sizeof(unsigned)));
+    MRTX_CUDA(cudaMemsetAsync(ctx->defer_mask, 0, n * sizeof(unsigned), ctx->stream));
     MRTX_CUDA(cudaMalloc(&ctx->accfix, n * 3 * sizeof(unsigned long long)));
     MRTX_CUDA(cudaMemsetAsync(ctx->accfix, 0, n * 3 * sizeof(unsigned long long), ctx->stream));
     MRTX_CUDA(cudaMalloc(&ctx->beam_s, n * sizeof(double)));

@@ -105,7 +105,8 @@ struct SceneParams {
     unsigned blocks_per_sm;                 // development: cap on resident blocks per SM of the two walk kernels (0 = what fits)
     unsigned hard_rays;                     // shadow rays too long for one referee warp are finished by the whole grid (default on)
     unsigned n_bounce;                      // diffuse interreflection bounces after the camera hit (path_seg_range max - 2; 0 = direct light)
-    unsigned shadow_queue;                  // 2 (default): primary hits -> hit queue -> shade_kernel -> shadow queue -> shadow_kernel;
+    unsigned shadow_queue;                  // 3 (default): as 2, primary rays by trace_kernel_pool (undecided rays parked in a per-warp pool);
+                                            // 2: primary hits -> hit queue -> shade_kernel -> shadow queue -> shadow_kernel;
                                             // 1: shading inside trace_kernel_fast, shadow rays through the queue; 0: everything inside trace_kernel_fast
     unsigned ceiling;                       // shadow rays: ceiling test from this level upwards (0 = off)
     unsigned beam, beam_drop;               // beam pre-pass of the filtered kernel (launches of >= 4 samples); samples start beam_drop levels below the beam's
@@ -144,10 +145,12 @@ struct mrtx_ctx {
     unsigned* d_work;           // trace work counter + list length
     unsigned* pixel_list;       // width * height entries
     uint2* defer_list;          // width * height entries: samples the filtered kernel hands to the exact one
+    unsigned* defer_mask;       // width * height words: the samples of a pixel that found that list full
     unsigned long long* accfix; // 3 * width * height: order-independent radiance sums of a launch (folded into accum at its end)
     void* sq_buf; size_t sq_cap; // shadow queue (allocated on first use): sq_cap ray records + aux entries ...
     void* hq_buf; size_t hq_cap; // ... and the hit queue in front of it: hq_cap slots
     void* hard_buf;                  // shadow rays trace_kernel_referee hands to referee_hard_kernel (allocated with the context)
+    void* pool_buf; size_t pool_bytes;   // trace_kernel_pool's straggler pools
     void* bq_buf[2]; size_t bq_cap;  // bounce-ray queues (interreflection; allocated when path_seg_range asks for bounces)
     double* beam_s;             // width * height entries (by position in the pixel list): where the pixel's samples start ...
     unsigned char* beam_l;      // ... and the level the beam pre-pass stopped at

@@ -287,8 +287,7 @@ trace_kernel_fast(const __grid_constant__ RenderArgs A) {
             // gives every entry a warp, and the samples of a limb pixel - where several defer at once - are each a long chain
 #if MRTX_DEFER_PER_SAMPLE
             if (defer) {
-                const unsigned slot = atomicAdd(&A.work_counter[3], 1u);
-                if (slot < A.list_cap) A.defer_list[slot] = make_uint2(packed, 1u << k);
+                defer_push(A, pixel, k);
                 ++n_defer;
             }
 #else
@@ -313,6 +312,202 @@ trace_kernel_fast(const __grid_constant__ RenderArgs A) {
             *ap = old;
             if (dmask) A.defer_list[atomicAdd(&A.work_counter[3], 1u)] = make_uint2(packed, dmask);
         }
+    }
+    flush_counters(A, rs, cnt, lane);
+    const unsigned nd = __reduce_add_sync(FULL, n_defer);
+    if (lane == 0 && nd) atomicAdd(&A.defer_stats[0], (unsigned long long)nd);
+}
+
+// ---- trace_kernel_pool: the hit-queue form with a straggler pool ------------------------------------------------------------
+// In trace_kernel_fast a warp stays with its 32 rays until the last of them is decided.  Measured at config 3 (phase
+// counters): 2.36 walk phases and 2.35 patch-test phases per warp task - the first with ~31 lanes, the others with 5.5: the
+// few rays whose first candidate patch was a miss (grazing rays, 11 M of 47.5 M) hold the warp for 26 % of its walk
+// iterations and 57 % of its test phases.  Here a warp gives every batch of rays ONE walk phase and ONE test phase; rays
+// that are still undecided after it are parked in the warp's own pool (96-byte records in global memory: ray, walk position -
+// walk_setup() rebuilds the rest exactly) and the warp goes on to its next task.  Whenever 32 rays are parked they form the
+// next batch, with all lanes busy.  A batch of fresh rays reserves its 32 hit-queue slots as trace_kernel_fast does; a parked
+// ray remembers its slot and fills it whenever it is decided, so shade_kernel and shadow_kernel see the queue they would
+// have seen.  Everything else a finished ray causes leaves through atomics (fixed-point sums, deferred list).
+struct PoolRec { double ox, oy, oz, dx, dy, dz, s_in; float smax, s; int L, J, I, steps; unsigned pix_k, slot, pad1, pad2; };
+static_assert(sizeof(PoolRec) == 96, "record layout");
+constexpr unsigned POOL_CAP = 64;                           // per warp: at most 31 parked + 32 parked again by a pool batch
+#ifndef MRTX_POOL_CHECK
+#define MRTX_POOL_CHECK 0
+#endif
+#if MRTX_POOL_CHECK
+#define POOL_ASSERT(c, ...) do { if (!(c)) { printf("POOL_ASSERT line %d: ", __LINE__); printf(__VA_ARGS__); printf("\n"); } } while (0)
+#else
+#define POOL_ASSERT(c, ...) do { } while (0)
+#endif
+
+template <bool I16>
+__global__ void __launch_bounds__(128, MRTX_FAST_MINBLOCKS)
+trace_kernel_pool(const __grid_constant__ RenderArgs A) {
+    __shared__ unsigned s_off[3 * MRTX_MAX_LEVELS];
+    if (threadIdx.x < 3 * MRTX_MAX_LEVELS) s_off[threadIdx.x] = A.hf.off[threadIdx.x];
+    __syncthreads();
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const int gl = A.g_log2, g = 1 << gl;
+    const int sub = lane & (g - 1), pw = lane >> gl;
+    const unsigned ppw = 32u >> gl;
+    const unsigned n_limb = A.work_counter[4];
+    const unsigned nkept = n_limb + A.work_counter[1];
+    const unsigned p_end = min(nkept, A.wave_p0 + A.wave_np);
+    if (A.wave_p0 >= p_end) return;
+    const unsigned ntasks = (p_end - A.wave_p0 + ppw - 1u) / ppw;
+    const float Rf = A.K.R;
+    const unsigned rounds = (A.nsamples + (unsigned)g - 1u) >> gl;
+    PoolRec* const pool = (PoolRec*)A.pool + (size_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * POOL_CAP;
+    unsigned npool = 0;                                      // warp-uniform
+    unsigned task = 0, rd = rounds;                          // fresh batches: (task, round); rd == rounds: claim the next task
+    bool exhausted = false;
+
+    Counters cnt = {0u, 0u, 0u};
+    RayStats rs = {0u, 0u, 0u, 0u, 0u};
+    unsigned n_defer = 0;
+
+    for (;;) {
+        // ---- the next batch: 32 parked rays if there are that many, else a fresh round of a task, else what is parked
+        bool from_pool = npool >= 32u;
+        if (!from_pool && !exhausted && rd >= rounds) {
+            if (lane == 0) task = atomicAdd(&A.work_counter[2], 1u);
+            task = __shfl_sync(FULL, task, 0);
+            if (task >= ntasks) exhausted = true; else rd = 0;
+        }
+        if (!from_pool && exhausted) {
+            if (!npool) break;
+            from_pool = true;
+        }
+        Ray64 R;
+        Walk st;
+        FastHit fh;
+        uint32_t pixel = 0;
+        unsigned k = 0, slot = 0xffffffffu;
+        bool have = false, alive = false, entered = false;
+        if (from_pool) {
+            const unsigned take = npool < 32u ? npool : 32u;
+            npool -= take;
+            if ((unsigned)lane < take) {
+                const double2* q = (const double2*)(pool + npool + lane);
+                const double2 a = q[0], b = q[1], c = q[2], d = q[3];
+                const uint4 e = *((const uint4*)q + 4), f = *((const uint4*)q + 5);
+                R.ox = a.x; R.oy = a.y; R.oz = b.x; R.dx = b.y; R.dy = c.x; R.dz = c.y;
+                R.oo = R.ox * R.ox + R.oy * R.oy + R.oz * R.oz; R.od = R.ox * R.dx + R.oy * R.dy + R.oz * R.dz;
+                walk_setup(R, d.x, __int_as_float(__double2loint(d.y)), st);
+                st.s = __int_as_float(__double2hiint(d.y));
+                st.L = (int)e.x; st.J = (int)e.y; st.I = (int)e.z; st.steps = (int)e.w; st.vnext = NAN;
+                pixel = f.x & 0x7ffffffu; k = f.x >> 27; slot = f.y;
+                have = true; alive = true; entered = true;
+                POOL_ASSERT(slot < A.hq_cap && pixel < (unsigned)(A.width * A.height) && st.L >= 0 && st.L <= A.hf.top && st.J >= 0 && st.I >= 0,
+                            "restored slot %u cap %u pixel %u L %d J %d I %d npool %u lane %d", slot, A.hq_cap, pixel, st.L, st.J, st.I, npool, lane);
+            }
+            __syncwarp();
+        } else {
+            const unsigned p = A.wave_p0 + task * ppw + (unsigned)pw;
+            const bool valid = p < p_end;
+            const unsigned packed = valid ? list_pixel(A, p, n_limb) : 0u;
+            const int x = (int)(packed & 0xffffu), y = (int)(packed >> 16);
+            pixel = (uint32_t)y * (uint32_t)A.width + (uint32_t)x;
+            k = rd * (unsigned)g + (unsigned)sub;
+            have = valid && k < A.nsamples;
+            if (valid && sub == 0 && rd == 0) A.accum[pixel].w += (float)A.nsamples;       // one lane per pixel and launch
+            if (have) {
+                double s_beam = 0.0;
+                int lvl_primary = A.hf.top - (int)A.sp.start_primary;
+                if (A.beam_s) {
+                    s_beam = A.beam_s[p];
+                    if (s_beam > 0.0) lvl_primary = max((int)A.beam_l[p] - A.beam_drop, 0);
+                }
+                primary_ray_fast(A, x, y, pixel, A.sample0 + k, R);
+                const int wb = walk_begin2(A.hf, A.sp.radius, R, s_beam, lvl_primary, st);
+                alive = wb == 2;
+                entered = wb != 0;
+            }
+            ++rd;
+        }
+        const unsigned sm = A.sample0 + k;
+
+        // ---- one walk phase (in lockstep), one test phase
+        RawPatch P;
+        float sx = 0.f;
+        int face = 4, res = FT_MISS;
+        bool cand = false;
+        while (__any_sync(FULL, alive && !cand)) {
+            if (alive && !cand) {
+                const int r = walk_step<I16>(A.hf, Rf, A.inv_rs, st, P, sx, face, cnt, nullptr, s_off);
+                if (r == TR_END) alive = false;
+                else if (r == TR_CANDIDATE) cand = true;
+            }
+        }
+        if ((alive || cand) && st.steps > (int)A.sp.long_walk) {
+            res = FT_DEFER; alive = false; cand = false;
+            atomicAdd(&A.defer_stats[15], 1ull);
+        }
+        if (cand) {
+            ++cnt.tests;
+            const int t = fast_test<I16>(A.hf, A.K, R, st.s_in, 0.0, st.s, sx, st.smax, P, false, fh);
+            if (t == FT_MISS) { if (!walk_advance(A.hf, st, sx, face)) alive = false; }
+            else {
+                res = t & 3; alive = false;
+                if (res == FT_DEFER) atomicAdd(&A.defer_stats[t >> 2], 1ull);
+            }
+        }
+
+        const bool done = have && !alive;
+        const bool hit = done && res == FT_HIT;
+        // ---- a fresh batch reserves its 32 slots if any of its rays has, or may still get, a hit; lanes mark theirs empty
+        if (!from_pool) {
+            const unsigned need = __ballot_sync(FULL, hit || alive);
+            if (need) {
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(&A.work_counter[7], 32u);
+                base = __shfl_sync(FULL, base, 0);
+                slot = base + (unsigned)lane;
+                POOL_ASSERT(slot < A.hq_cap, "fresh slot %u cap %u", slot, A.hq_cap);
+                if (!hit) __stcs((uint4*)(A.hq + slot) + 1, make_uint4(0u, 0u, 0xffffffffu, 0u));
+            }
+        }
+        if (hit) {
+            POOL_ASSERT(slot < A.hq_cap, "hit slot %u cap %u from_pool %d", slot, A.hq_cap, (int)from_pool);
+            uint4* q = (uint4*)(A.hq + slot);
+            __stcs(q, make_uint4((unsigned)__double2loint(fh.s), (unsigned)__double2hiint(fh.s), __float_as_uint(fh.fc), __float_as_uint(fh.fr)));
+            __stcs(q + 1, make_uint4((unsigned)fh.r0, (unsigned)fh.c0, pixel | (k << 27), 0u));
+            __stcs(q + 2, make_uint4(__float_as_uint(fh.d00), __float_as_uint(fh.d01), __float_as_uint(fh.d10), __float_as_uint(fh.d11)));
+        }
+        __syncwarp();
+
+        // ---- undecided rays wait in the pool
+        const unsigned pm = __ballot_sync(FULL, alive);
+        if (alive) {
+            POOL_ASSERT(npool + (unsigned)__popc(pm & lt) < POOL_CAP && slot != 0xffffffffu, "park at %u slot %u", npool + (unsigned)__popc(pm & lt), slot);
+            double2* q = (double2*)(pool + npool + (unsigned)__popc(pm & lt));
+            q[0] = make_double2(R.ox, R.oy); q[1] = make_double2(R.oz, R.dx); q[2] = make_double2(R.dy, R.dz);
+            q[3] = make_double2(st.s_in, __hiloint2double(__float_as_int(st.s), __float_as_int(st.smax)));
+            *((uint4*)q + 4) = make_uint4((unsigned)st.L, (unsigned)st.J, (unsigned)st.I, (unsigned)st.steps);
+            *((uint4*)q + 5) = make_uint4(pixel | (k << 27), slot, 0u, 0u);
+        }
+        npool += (unsigned)__popc(pm);
+        __syncwarp();
+
+        // ---- decided rays without a hit: a miss sees what lies behind the Moon, a deferral goes to the referee
+        if (done && !hit) {
+            if (res == FT_DEFER) {
+                defer_push(A, pixel, k);
+                ++n_defer;
+            } else {
+                ++rs.primary;
+                if (entered) ++rs.inside;
+                const int x = (int)(pixel % (unsigned)A.width), y = (int)(pixel / (unsigned)A.width);
+                float3 tc;
+                if (tube_tile_count(A, x, y) && tube_nearest(A, x, y, pixel, sm, 1.0e300, tc)) accfix_add(A.accfix, pixel, tc);
+                else {
+                    write_miss(A, x, y, sm == A.hit_sample);
+                    if (sees_background(A)) accfix_add(A.accfix, pixel, miss_radiance_body(A, R));
+                }
+            }
+        } else if (hit) { ++rs.primary; ++rs.inside; ++rs.hits; }
     }
     flush_counters(A, rs, cnt, lane);
     const unsigned nd = __reduce_add_sync(FULL, n_defer);
@@ -591,9 +786,7 @@ shadow_kernel(const __grid_constant__ RenderArgs A) {
             else {
                 // undecided: the referee traces the whole sample again from the camera
                 atomicAdd(&A.defer_stats[16 + (status >> 2)], 1ull);
-                const unsigned slot = atomicAdd(&A.work_counter[3], 1u);
-                const unsigned px = pixel % (unsigned)A.width, py = pixel / (unsigned)A.width;
-                if (slot < A.list_cap) A.defer_list[slot] = make_uint2(px | (py << 16), 1u << (aux.w >> 27));
+                defer_push(A, pixel, aux.w >> 27);
                 ++n_defer;
             }
         }
@@ -777,6 +970,26 @@ static int launch_trace_t(mrtx_ctx* ctx, RenderArgs& A, unsigned s0, unsigned ns
             }
             const bool first = !done && !p0;                // (the stopwatch brackets the first chunk and wave of a launch)
             const bool hitq = queue && ctx->sp.shadow_queue >= 2u;
+            if (hitq && ctx->sp.shadow_queue >= 3u) {
+                // the pooled form: one block per resident slot, each warp with its own pool
+                int per_sm = 0;
+                MRTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel_pool<I16>, 128, 0));
+                if (per_sm < 1) per_sm = 1;
+                if (ctx->sp.blocks_per_sm && (int)ctx->sp.blocks_per_sm < per_sm) per_sm = (int)ctx->sp.blocks_per_sm;
+                long long blocks = (long long)ctx->sm_count * per_sm;
+                const long long warps_needed = (((long long)A.wave_np << A.g_log2) + 31) / 32;
+                if (blocks * 4 > warps_needed) blocks = (warps_needed + 3) / 4;
+                if (blocks < 1) blocks = 1;
+                const size_t need = (size_t)ctx->sm_count * 16 * 4 * POOL_CAP * sizeof(PoolRec);
+                if (ctx->pool_bytes < need) {
+                    MRTX_CUDA(cudaStreamSynchronize(ctx->stream));
+                    cudaFree(ctx->pool_buf); ctx->pool_buf = nullptr; ctx->pool_bytes = 0;
+                    MRTX_CUDA(cudaMalloc(&ctx->pool_buf, need));
+                    ctx->pool_bytes = need;
+                }
+                A.pool = ctx->pool_buf;
+                trace_kernel_pool<I16><<<(unsigned)blocks, 128, 0, ctx->stream>>>(A);
+            } else
             rc = hitq ? launch_fast<I16, 2>(ctx, A, A.wave_np) : queue ? launch_fast<I16, 1>(ctx, A, A.wave_np) : launch_fast<I16, 0>(ctx, A, A.wave_np);
             if (rc) return rc;
             if (first) prof_mark(ctx, 3);

@@ -62,6 +62,7 @@ struct RenderArgs {
     unsigned list_cap;
     unsigned long long* defer_stats; // [reason + 16 * shadow]: why samples were deferred
     uint2* defer_list;               // (pixel, mask of samples sample0 + bit) the fast kernel could not certify
+    unsigned* defer_mask;            // per pixel: samples that found the list full (defer_push); all zero between launches
     // wavefront pipeline (kernel 3): one wave = list pixels [wave_p0, wave_p0 + wave_np) x nsamples samples
     unsigned wave_p0, wave_np;
     float* rad;                      // [item][3] radiance of every sample of the wave, item = (p - wave_p0) * nsamples + k
@@ -86,6 +87,7 @@ struct RenderArgs {
     int depth, n_bounce;
     float night_sin2;                // sin^2 of the Sun's depression beyond which a path cannot reach lit terrain (shade_kernel)
     struct HardRay* hard;            // shadow rays handed from trace_kernel_referee to referee_hard_kernel (work_counter[12] of them)
+    void* pool;                      // trace_kernel_pool: POOL_CAP parked rays per warp
     // hit queue (shadow_queue = 2): primary hits pushed by trace_kernel_fast (work_counter[7] of them), shaded by shade_kernel
     struct HitQRec* hq; unsigned hq_cap;
     unsigned long long* accfix;
@@ -129,6 +131,18 @@ __device__ __forceinline__ void accfix_add(unsigned long long* accfix, uint32_t 
 }
 
 struct RayStats { unsigned primary, inside, hits, shadow, occluded; };
+
+// One sample for the referee: an entry of the deferred list (list_cap = one per pixel of the frame).  Writers that make an
+// entry per SAMPLE (shadow_kernel, trace_kernel_pool) can fill the list when nearly every ray defers (long_walk of a few
+// steps); what does not fit is kept as a bit of the pixel's word in defer_mask, which the referee scans if - and only if -
+// work_counter[3] has passed list_cap.  No sample is ever dropped.
+__device__ __forceinline__ void defer_push(const RenderArgs& A, uint32_t pixel, unsigned k) {
+    const unsigned slot = atomicAdd(&A.work_counter[3], 1u);
+    if (slot < A.list_cap) {
+        const unsigned px = pixel % (unsigned)A.width, py = pixel / (unsigned)A.width;
+        A.defer_list[slot] = make_uint2(px | (py << 16), 1u << k);
+    } else atomicOr(&A.defer_mask[pixel], 1u << k);
+}
 
 // p-th pixel of the work list (limb pixels first)
 __device__ __forceinline__ unsigned list_pixel(const RenderArgs& A, unsigned p, unsigned n_limb) {
@@ -799,14 +813,27 @@ __global__ void __launch_bounds__(64)
 trace_kernel_referee(const __grid_constant__ RenderArgs A) {
     __shared__ RefIv stacks[2][REFEREE_STACK];
     RefIv* const stack = stacks[threadIdx.x >> 5];
-    const unsigned total = A.work_counter[3];
+    // entries [0, n_list) come from the list; if it overflowed, entries n_list + p are the pixels of the frame with the
+    // samples defer_push() parked in their mask words (cleared here for the next launch)
+    const unsigned n_pushed = A.work_counter[3];
+    const unsigned n_list = WAVE ? n_pushed : min(n_pushed, A.list_cap);
+    const unsigned total = !WAVE && n_pushed > A.list_cap ? n_list + (unsigned)(A.width * A.height) : n_list;
     const int lane = threadIdx.x & 31;
     const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     Counters cnt = {0u, 0u, 0u};
     RayStats rs = {0u, 0u, 0u, 0u, 0u};                    // lane 0 counts rays
     const unsigned n_limb = A.work_counter[4];
     for (unsigned e = warp; e < total; e += nwarps) {
-        const uint2 ent = WAVE ? A.defer_items[e] : A.defer_list[e];
+        uint2 ent;
+        if (WAVE) ent = A.defer_items[e];
+        else if (e < n_list) ent = A.defer_list[e];
+        else {
+            const unsigned p = e - n_list, m = A.defer_mask[p];
+            if (!m) continue;
+            __syncwarp();
+            if (lane == 0) A.defer_mask[p] = 0u;
+            ent = make_uint2((p % (unsigned)A.width) | ((p / (unsigned)A.width) << 16), m);
+        }
         const unsigned packed = WAVE ? list_pixel(A, ent.x, n_limb) : ent.x;
         const int x = (int)(packed & 0xffffu), y = (int)(packed >> 16);
         const uint32_t pixel = (uint32_t)y * (uint32_t)A.width + (uint32_t)x;
@@ -967,6 +994,7 @@ static void fill_render_args(mrtx_ctx* ctx, int x0, int y0, int x1, int y1, unsi
     to_body(A.sp, er, A.eye_b);
     to_body(A.sp, lr, A.light_b);
     A.defer_list = ctx->defer_list;
+    A.defer_mask = ctx->defer_mask;
     A.rad = nullptr; A.rays = nullptr; A.hits = nullptr; A.srays = nullptr; A.sitem = nullptr; A.defer_items = nullptr;
     A.wave_p0 = 0; A.wave_np = 0; A.lvl_primary = 0; A.lvl_shadow = 0;
     A.defer_stats = ctx->d_defer_stats;

@@ -363,15 +363,17 @@ def test_wavefront_pipeline_equals_filtered_kernel(spp):
         assert np.allclose(ha, hb, rtol=1e-12, atol=1e-12)
 
 
+@pytest.mark.parametrize("sq_mode", [2, 3])
 @pytest.mark.parametrize("spp,phase,shadows", [(1, 88.0, 1), (16, 90.0, 1), (24, 75.0, 1), (40, 60.0, 1), (6, 90.0, 0)])
-def test_hit_queue_and_shade_kernel_equal_in_kernel_shading(spp, phase, shadows):
+def test_hit_queue_and_shade_kernel_equal_in_kernel_shading(spp, phase, shadows, sq_mode):
     """The production cut of kernel 2 (shadow_queue = 2: trace_kernel_fast stops at the primary hit, which goes through the
-    hit queue to shade_kernel; that pushes the shadow ray) against shading inside trace_kernel_fast (shadow_queue = 1): the
-    same rays, the same records, sums in fixed point either way - the frames are equal bit for bit.  Sample counts that
-    are no power of two leave empty slots in the hit queue (24 = 16 + 8 lanes of a second round; 40 = 32 + 8)."""
+    hit queue to shade_kernel; that pushes the shadow ray; shadow_queue = 3, the default: the same with trace_kernel_pool,
+    whose warps park undecided rays in a pool and fill their hit-queue slots later) against shading inside trace_kernel_fast
+    (shadow_queue = 1): the same rays, the same records, sums in fixed point either way - the frames are equal bit for bit.
+    Sample counts that are no power of two leave empty slots in the hit queue (24 = 16 + 8 lanes of a second round; 40 = 32 + 8)."""
     elev, _ = synth_elevation(2880, 1440, seed=12)
     outs = []
-    for sq in (1, 2):
+    for sq in (1, sq_mode):
         rt = make_gpu(elev, 320, 240, debug_hits=(spp == 1), light_pos=sun_at_phase(phase))
         rt.set_uint("shadow_queue", sq); rt.set_uint("shadows", shadows)
         if spp > 1:
@@ -397,6 +399,35 @@ def test_hit_queue_and_shade_kernel_equal_in_kernel_shading(spp, phase, shadows)
     if spp == 1:
         # (written by different kernels: the same source expression may be contracted differently)
         assert np.array_equal(ha[..., 0] > 0, hb[..., 0] > 0) and np.allclose(ha, hb, rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("sq_mode", [2, 3])
+def test_deferred_list_overflow_keeps_every_sample(sq_mode):
+    """With long_walk of two steps nearly every ray goes to the referee; 8 samples per pixel in ONE launch make more
+    per-sample entries than the deferred list holds (one per pixel of the frame).  What does not fit waits in the pixel's
+    mask word and the referee scans those: the frame equals the one made by 8 launches of one sample each, where the list
+    cannot fill up (the fixed-point sums are folded into the float accumulators once per launch, so the two agree to
+    float32 rounding; one lost sample of 8 would show as 12 % of a pixel)."""
+    from moonrtx_b200 import _lib
+    elev, _ = synth_elevation(1440, 720, seed=11)
+    W, H, spp = 200, 120, 8
+    outs = []
+    for split in (False, True):
+        rt = make_gpu(elev, W, H, debug_hits=False, light_pos=sun_at_phase(90.0))
+        rt.set_uint("shadow_queue", sq_mode); rt.set_uint("long_walk", 2)
+        rt._lib.mrtx_set_uint(rt._ctx, b"jitter", 1, 0)
+        rt.defer_stats(reset=True)
+        if split:
+            for k in range(spp):
+                _lib.check(rt._lib.mrtx_render(rt._ctx, 0, 0, W, H, k, 1, 1 if k == 0 else 0))
+        else:
+            _lib.check(rt._lib.mrtx_render(rt._ctx, 0, 0, W, H, 0, spp, 1))
+        outs.append((rt.get_accum_buffer().copy(), rt.defer_stats()["deferred_samples"]))
+        rt.close()
+    (a, na), (b, nb) = outs
+    assert na == nb and na > W * H, (na, nb, W * H)
+    assert np.array_equal(a[..., 3], b[..., 3]) and float(a[..., :3].max()) > 0.1
+    assert np.allclose(a, b, rtol=1e-5, atol=1e-6), float(np.abs(a - b).max())
 
 
 @pytest.mark.parametrize("spp,phase", [(1, 88.0), (16, 90.0), (40, 60.0)])
