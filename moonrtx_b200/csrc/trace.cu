@@ -331,6 +331,9 @@ trace_kernel_fast(const __grid_constant__ RenderArgs A) {
 struct PoolRec { double ox, oy, oz, dx, dy, dz, s_in; float smax, s; int L, J, I, steps; unsigned pix_k, slot, pad1, pad2; };
 static_assert(sizeof(PoolRec) == 96, "record layout");
 constexpr unsigned POOL_CAP = 64;                           // per warp: at most 31 parked + 32 parked again by a pool batch
+#ifndef MRTX_POOL_T
+#define MRTX_POOL_T 8
+#endif
 #ifndef MRTX_POOL_CHECK
 #define MRTX_POOL_CHECK 0
 #endif
@@ -434,13 +437,16 @@ trace_kernel_pool(const __grid_constant__ RenderArgs A) {
         float sx = 0.f;
         int face = 4, res = FT_MISS;
         bool cand = false;
-        while (__any_sync(FULL, alive && !cand)) {
+        // (the walk phase ends when fewer than MRTX_POOL_T lanes are still walking: those rays are parked as they are and
+        //  continue in a later batch with full lanes; while the pools are being emptied every ray walks to its end)
+        const unsigned walk_min = exhausted ? 1u : (unsigned)MRTX_POOL_T;
+        do {
             if (alive && !cand) {
                 const int r = walk_step<I16>(A.hf, Rf, A.inv_rs, st, P, sx, face, cnt, nullptr, s_off);
                 if (r == TR_END) alive = false;
                 else if (r == TR_CANDIDATE) cand = true;
             }
-        }
+        } while ((unsigned)__popc(__ballot_sync(FULL, alive && !cand)) >= walk_min);
         if ((alive || cand) && st.steps > (int)A.sp.long_walk) {
             res = FT_DEFER; alive = false; cand = false;
             atomicAdd(&A.defer_stats[15], 1ull);
