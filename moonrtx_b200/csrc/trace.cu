@@ -188,8 +188,10 @@ trace_kernel_fast(const __grid_constant__ RenderArgs A) {
                     // walk phase, in lockstep: one node per lane and iteration, the vote at the loop head brings the warp
                     // back together after every node (left to itself the compiler lets lanes that took different
                     // branches of a node run on separately: measured 4 lanes per instruction in walk_step)
-                    while (__any_sync(FULL, alive && !cand)) {
-                        if (alive && !cand) {
+                    // (a ray that is still walking after long_walk nodes stops here and is deferred below: decided per ray,
+                    //  whatever the other lanes do - trace_kernel_pool and shadow_kernel apply the same rule)
+                    while (__any_sync(FULL, alive && !cand && st.steps <= (int)A.sp.long_walk)) {
+                        if (alive && !cand && st.steps <= (int)A.sp.long_walk) {
                             bool clear = false;
                             if (!QUEUE && st.L >= ceil_next) {
                                 ceil_next = st.L + 2;
@@ -440,13 +442,14 @@ trace_kernel_pool(const __grid_constant__ RenderArgs A) {
         // (the walk phase ends when fewer than MRTX_POOL_T lanes are still walking: those rays are parked as they are and
         //  continue in a later batch with full lanes; while the pools are being emptied every ray walks to its end)
         const unsigned walk_min = exhausted ? 1u : (unsigned)MRTX_POOL_T;
+        const int long_walk = (int)A.sp.long_walk;          // (a ray still walking after that many nodes goes to the referee)
         do {
-            if (alive && !cand) {
+            if (alive && !cand && st.steps <= long_walk) {
                 const int r = walk_step<I16>(A.hf, Rf, A.inv_rs, st, P, sx, face, cnt, nullptr, s_off);
                 if (r == TR_END) alive = false;
                 else if (r == TR_CANDIDATE) cand = true;
             }
-        } while ((unsigned)__popc(__ballot_sync(FULL, alive && !cand)) >= walk_min);
+        } while ((unsigned)__popc(__ballot_sync(FULL, alive && !cand && st.steps <= long_walk)) >= walk_min);
         if ((alive || cand) && st.steps > (int)A.sp.long_walk) {
             res = FT_DEFER; alive = false; cand = false;
             atomicAdd(&A.defer_stats[15], 1ull);
@@ -484,19 +487,6 @@ trace_kernel_pool(const __grid_constant__ RenderArgs A) {
         }
         __syncwarp();
 
-        // ---- undecided rays wait in the pool
-        const unsigned pm = __ballot_sync(FULL, alive);
-        if (alive) {
-            POOL_ASSERT(npool + (unsigned)__popc(pm & lt) < POOL_CAP && slot != 0xffffffffu, "park at %u slot %u", npool + (unsigned)__popc(pm & lt), slot);
-            double2* q = (double2*)(pool + npool + (unsigned)__popc(pm & lt));
-            q[0] = make_double2(R.ox, R.oy); q[1] = make_double2(R.oz, R.dx); q[2] = make_double2(R.dy, R.dz);
-            q[3] = make_double2(st.s_in, __hiloint2double(__float_as_int(st.s), __float_as_int(st.smax)));
-            *((uint4*)q + 4) = make_uint4((unsigned)st.L, (unsigned)st.J, (unsigned)st.I, (unsigned)st.steps);
-            *((uint4*)q + 5) = make_uint4(pixel | (k << 27), slot, 0u, 0u);
-        }
-        npool += (unsigned)__popc(pm);
-        __syncwarp();
-
         // ---- decided rays without a hit: a miss sees what lies behind the Moon, a deferral goes to the referee
         if (done && !hit) {
             if (res == FT_DEFER) {
@@ -514,6 +504,20 @@ trace_kernel_pool(const __grid_constant__ RenderArgs A) {
                 }
             }
         } else if (hit) { ++rs.primary; ++rs.inside; ++rs.hits; }
+        __syncwarp();
+
+        // ---- undecided rays wait in the pool
+        const unsigned pm = __ballot_sync(FULL, alive);
+        if (alive) {
+            POOL_ASSERT(npool + (unsigned)__popc(pm & lt) < POOL_CAP && slot != 0xffffffffu, "park at %u slot %u", npool + (unsigned)__popc(pm & lt), slot);
+            double2* q = (double2*)(pool + npool + (unsigned)__popc(pm & lt));
+            q[0] = make_double2(R.ox, R.oy); q[1] = make_double2(R.oz, R.dx); q[2] = make_double2(R.dy, R.dz);
+            q[3] = make_double2(st.s_in, __hiloint2double(__float_as_int(st.s), __float_as_int(st.smax)));
+            *((uint4*)q + 4) = make_uint4((unsigned)st.L, (unsigned)st.J, (unsigned)st.I, (unsigned)st.steps);
+            *((uint4*)q + 5) = make_uint4(pixel | (k << 27), slot, 0u, 0u);
+        }
+        npool += (unsigned)__popc(pm);
+        __syncwarp();
     }
     flush_counters(A, rs, cnt, lane);
     const unsigned nd = __reduce_add_sync(FULL, n_defer);
