@@ -333,6 +333,9 @@ trace_kernel_fast(const __grid_constant__ RenderArgs A) {
 struct PoolRec { double ox, oy, oz, dx, dy, dz, s_in; float smax, s; int L, J, I, steps; unsigned pix_k, slot, pad1, pad2; };
 static_assert(sizeof(PoolRec) == 96, "record layout");
 constexpr unsigned POOL_CAP = 64;                           // per warp: at most 31 parked + 32 parked again by a pool batch
+#ifndef MRTX_POOL_MINBLOCKS
+#define MRTX_POOL_MINBLOCKS MRTX_FAST_MINBLOCKS
+#endif
 #ifndef MRTX_POOL_T
 #define MRTX_POOL_T 8
 #endif
@@ -346,7 +349,7 @@ constexpr unsigned POOL_CAP = 64;                           // per warp: at most
 #endif
 
 template <bool I16>
-__global__ void __launch_bounds__(128, MRTX_FAST_MINBLOCKS)
+__global__ void __launch_bounds__(128, MRTX_POOL_MINBLOCKS)
 trace_kernel_pool(const __grid_constant__ RenderArgs A) {
     __shared__ unsigned s_off[3 * MRTX_MAX_LEVELS];
     if (threadIdx.x < 3 * MRTX_MAX_LEVELS) s_off[threadIdx.x] = A.hf.off[threadIdx.x];
