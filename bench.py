@@ -161,8 +161,8 @@ def sweep_state(frame):
 
 
 def ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of trace_kernel_fast, from the newest
-    profiles/*_raw.csv (`ncu --set full` of this workload; the csv is the raw page of the report)."""
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the primary-ray kernel (trace_kernel_pool; captures older
+    than it hold trace_kernel_fast), from the newest profiles/*_raw.csv (`ncu --set full` of this workload; the csv is the raw page of the report)."""
     best = None
     for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_raw.csv"))):
         try:
@@ -173,7 +173,7 @@ def ncu_traffic():
             units = rows[1]
             mul = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
             for r in rows[2:]:
-                if "trace_kernel_fast" in r[ik]:
+                if "trace_kernel_pool" in r[ik] or "trace_kernel_fast" in r[ik]:
                     val = float(r[ir].replace(",", "")) * mul.get(units[ir], 1.0) + float(r[iw].replace(",", "")) * mul.get(units[iw], 1.0)
                     best = (val, os.path.basename(path))
         except Exception:
@@ -422,7 +422,7 @@ def walked(c):
 
 
 def launches_per_frame(args):
-    """kernels of this library per frame: cull, then per sample chunk and pixel wave trace_kernel_fast + shade_kernel +
+    """kernels of this library per frame: cull, then per sample chunk and pixel wave trace_kernel_pool + shade_kernel +
     shadow_kernel + trace_kernel_referee + referee_hard_kernel + its finish kernel, fold, resolve"""
     chunks = (args.spp + 31) // 32
     per_chunk = min(args.spp, 32)
@@ -563,7 +563,7 @@ def run_frames(args):
     def gbs(nbytes, ms):
         return nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
     roofline = {
-        "bound": "hbm", "kernel": "trace_kernel_fast<int16, hit queue> (primary ray to its first hit, which goes to the hit queue)",
+        "bound": "hbm", "kernel": "trace_kernel_pool<int16> (primary ray to its first hit, which goes to the hit queue; undecided rays parked in per-warp pools)",
         "achieved": round(gbs(prim_bytes, fast_ms), 2), "peak": peak, "unit": "GB/s", "frac": round(gbs(prim_bytes, fast_ms) / peak, 5),
         "traffic": traffic[0] if traffic else None, "traffic_source": traffic[1] if traffic else None,
         "algorithmic_bytes_per_launch": int(prim_bytes), "bytes_per_ray": b_floor, "rays_per_launch": int(c["primary_in_sphere"] / nf),
@@ -571,7 +571,7 @@ def run_frames(args):
         "timing": "CUDA events on the launching stream at the kernel boundaries of every timed frame (mrtx_kernel_times)",
         "shadow_kernel": {"kernel_ms": round(shadow_ms, 3), "achieved": round(gbs(shad_bytes, shadow_ms), 2), "frac": round(gbs(shad_bytes, shadow_ms) / peak, 5),
                           "rays_per_launch": int(c["shadow_rays"] / nf), "algorithmic_bytes_per_launch": int(shad_bytes)},
-        "whole_path": {"kernels": "cull + trace_kernel_fast + shade_kernel + shadow_kernel + trace_kernel_referee + fold (one mrtx_render)",
+        "whole_path": {"kernels": "cull + trace_kernel_pool + shade_kernel + shadow_kernel + trace_kernel_referee + fold (one mrtx_render)",
                        "ms": round(path_ms, 3), "referee_ms": round(ref_ms, 3), "shade_ms": round(shade_ms, 3), "achieved": round(gbs(prim_bytes + shad_bytes, path_ms), 2),
                        "frac": round(gbs(prim_bytes + shad_bytes, path_ms) / peak, 5)},
         "counted_bytes_per_ray": round(32.0 * (c["node_visits"] + 2 * c["patch_tests"]) / max(1.0, walked(c)), 1),

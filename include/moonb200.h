@@ -228,7 +228,7 @@ int  mrtx_read_hit_f64(mrtx_ctx* ctx, double* out);
  * [11] lanes in them, [12] ray-start phases, [13] lanes in them, [14] refills, [15] pixels culled */
 int  mrtx_counters(mrtx_ctx* ctx, uint64_t out[16], int reset);
 /* Stopwatch of the trace path (engine switch "profile" = 1): CUDA events at the kernel boundaries of every mrtx_render
- * since the last reset, summed: out_ms[0] cull_kernel, [1] beam_kernel, [2] trace_kernel_fast, [3] shadow_kernel,
+ * since the last reset, summed: out_ms[0] cull_kernel, [1] beam_kernel, [2] the primary-ray kernel (trace_kernel_pool; trace_kernel_fast with shadow_queue <= 2), [3] shadow_kernel,
  * [4] trace_kernel_referee, [5] fold_kernel (first sample chunk / pixel wave of each launch), [6] launches measured,
  * [7] shade_kernel.
  * bench.py reads the dominant kernel's launch duration from it (roofline.achieved).                              */

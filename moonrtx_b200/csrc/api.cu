@@ -837,7 +837,7 @@ int mrtx_set_uint(mrtx_ctx* ctx, const char* name, unsigned a, unsigned b) {
     else if (!strcmp(name, "ceiling")) ctx->sp.ceiling = a;
     else if (!strcmp(name, "profile")) ctx->prof_on = a ? 1 : 0;
     else if (!strcmp(name, "blocks_per_sm")) ctx->sp.blocks_per_sm = a;
-    else if (!strcmp(name, "shadow_queue")) ctx->sp.shadow_queue = a > 3u ? 3u : a;
+    else if (!strcmp(name, "shadow_queue")) ctx->sp.shadow_queue = a > 4u ? 4u : a;
     else if (!strcmp(name, "beam")) { ctx->sp.beam = a ? 1u : 0u; ctx->sp.beam_drop = b; }
     else if (!strcmp(name, "kernel")) { MRTX_REQUIRE(a <= 3u, "kernel must be 0, 1, 2 or 3"); ctx->sp.kernel = a; }
     else { mrtx_set_error("unknown uint parameter '%s'", name); return MRTX_ERR_INVALID; }

@@ -815,6 +815,141 @@ shadow_kernel(const __grid_constant__ RenderArgs A) {
     }
 }
 
+// ---- shadow_kernel_pool: the shadow queue in batches, with a straggler pool ----------------------------------------------------
+// The streaming kernel above keeps every lane busy by refilling it, which mixes rays at different stages of their walks in
+// one warp: walk_step runs at 14.6 of 32 lanes there (ncu, profiles/r08), against 22.9 in trace_kernel_pool, whose batches
+// start together.  Queue entries are coherent as they lie - 32 consecutive entries are the shadow rays of one shade warp:
+// neighbouring hits, the same Sun.  Here a warp takes 32 consecutive entries, gives them one walk phase in lockstep (ending
+// when fewer than MRTX_SPOOL_T lanes still walk) and one patch test, and parks what is still undecided (32-byte records: queue
+// index + walk position; walk_setup() rebuilds the rest from the queue entry exactly); 32 parked rays form a batch of their own.
+// Any crossing occludes; decisions and sums are the streaming kernel's (same per-ray arithmetic, fixed-point sums).
+struct SPoolRec { unsigned ridx; float s; int L, J, I, steps; unsigned pad0, pad1; };
+static_assert(sizeof(SPoolRec) == 32, "record layout");
+#ifndef MRTX_SPOOL_T
+#define MRTX_SPOOL_T 8
+#endif
+template <bool I16>
+__global__ void __launch_bounds__(128, MRTX_SQ_MINBLOCKS)
+shadow_kernel_pool(const __grid_constant__ RenderArgs A) {
+    __shared__ unsigned s_off[3 * MRTX_MAX_LEVELS];
+    if (threadIdx.x < 3 * MRTX_MAX_LEVELS) s_off[threadIdx.x] = A.hf.off[threadIdx.x];
+    __syncthreads();
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const unsigned n_items = A.work_counter[5];
+    unsigned* const queue = A.work_counter + 6;
+    const float Rf = A.K.R;
+    const int long_walk = (int)A.sp.long_walk;
+    SPoolRec* const pool = (SPoolRec*)A.pool + (size_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * POOL_CAP;
+    unsigned npool = 0;                                      // warp-uniform
+    bool exhausted = false;
+    Counters cnt = {0u, 0u, 0u};
+    unsigned n_defer = 0, n_occluded = 0;
+    FastHit fh;
+
+    for (;;) {
+        bool from_pool = npool >= 32u;
+        unsigned base = 0;
+        if (!from_pool && !exhausted) {
+            if (lane == 0) base = atomicAdd(queue, 32u);
+            base = __shfl_sync(FULL, base, 0);
+            if (base >= n_items) exhausted = true;
+        }
+        if (!from_pool && exhausted) {
+            if (!npool) break;
+            from_pool = true;
+        }
+        Walk st;
+        unsigned ridx = 0;
+        bool alive = false;
+        if (from_pool) {
+            const unsigned take = npool < 32u ? npool : 32u;
+            npool -= take;
+            if ((unsigned)lane < take) {
+                const uint4* q = (const uint4*)(pool + npool + lane);
+                const uint4 a = q[0], b = q[1];
+                ridx = a.x;
+                const RayRec* rec = A.sq_rays + ridx;
+                const double2 tail = __ldg((const double2*)rec + 3);
+                Ray64 R;
+                load_ray_rec(rec, R);
+                walk_setup(R, tail.x, __int_as_float(__double2loint(tail.y)), st);
+                st.s = __uint_as_float(a.y); st.L = (int)a.z; st.J = (int)a.w; st.I = (int)b.x; st.steps = (int)b.y; st.vnext = NAN;
+                alive = true;
+            }
+            __syncwarp();
+        } else {
+            const unsigned idx = base + (unsigned)lane;
+            if (idx < n_items) {
+                const RayRec* rec = A.sq_rays + idx;
+                const double2 tail = __ldg((const double2*)rec + 3);
+                const unsigned cell = (unsigned)__double2hiint(tail.y);
+                Ray64 R;
+                load_ray_rec(rec, R);
+                walk_setup(R, tail.x, __int_as_float(__double2loint(tail.y)), st);
+                st.L = A.sq_level; st.J = (int)(cell >> 16); st.I = (int)(cell & 0xffffu);
+                st.s = 0.0f; st.steps = 0; st.vnext = NAN;
+                ridx = idx;
+                alive = true;
+            }
+        }
+        const bool have = alive;
+
+        RawPatch P;
+        float sx = 0.f;
+        int face = 4, status = FT_MISS;
+        bool cand = false;
+        const unsigned walk_min = exhausted ? 1u : (unsigned)MRTX_SPOOL_T;
+        do {
+            if (alive && !cand && st.steps <= long_walk) {
+                const int r = walk_step<I16>(A.hf, Rf, A.inv_rs, st, P, sx, face, cnt, nullptr, s_off);
+                if (r == TR_END) alive = false;
+                else if (r == TR_CANDIDATE) cand = true;
+            }
+        } while ((unsigned)__popc(__ballot_sync(FULL, alive && !cand && st.steps <= long_walk)) >= walk_min);
+        if ((alive || cand) && st.steps > long_walk) { status = FT_DEFER_R(15); alive = false; cand = false; }
+        if (cand) {
+            ++cnt.tests;
+            Ray64 R;
+            load_ray_rec(A.sq_rays + ridx, R);
+            status = fast_test<I16>(A.hf, A.K, R, st.s_in, 0.0, st.s, sx, st.smax, P, true, fh);
+            if (!(status == FT_MISS && walk_advance(A.hf, st, sx, face))) alive = false;
+        }
+        if (have && !alive) {
+            const uint4 aux = __ldg(A.sq_aux + ridx);
+            const uint32_t pixel = aux.w & 0x7ffffffu;
+            if (status == FT_MISS) {
+                accfix_add(A.accfix, pixel, make_float3(__uint_as_float(aux.x), __uint_as_float(aux.y), __uint_as_float(aux.z)));
+            } else if ((status & 3) == FT_HIT) ++n_occluded;
+            else {
+                // undecided: the referee traces the whole sample again from the camera
+                atomicAdd(&A.defer_stats[16 + (status >> 2)], 1ull);
+                defer_push(A, pixel, aux.w >> 27);
+                ++n_defer;
+            }
+        }
+        __syncwarp();
+        const unsigned pm = __ballot_sync(FULL, alive);
+        if (alive) {
+            uint4* q = (uint4*)(pool + npool + (unsigned)__popc(pm & lt));
+            q[0] = make_uint4(ridx, __float_as_uint(st.s), (unsigned)st.L, (unsigned)st.J);
+            q[1] = make_uint4((unsigned)st.I, (unsigned)st.steps, 0u, 0u);
+        }
+        npool += (unsigned)__popc(pm);
+        __syncwarp();
+    }
+    const RayStats rs = {0u, 0u, 0u, 0u, n_occluded};
+    flush_counters(A, rs, cnt, lane);
+    const unsigned nd = __reduce_add_sync(FULL, n_defer);
+    if (lane == 0 && nd) {
+        // the referee counts these samples again: take back what the primary-ray kernel counted for them
+        const unsigned long long neg = 0ull - (unsigned long long)nd;
+        atomicAdd(&A.defer_stats[0], (unsigned long long)nd);
+        atomicAdd(&A.counters[0], neg); atomicAdd(&A.counters[1], neg); atomicAdd(&A.counters[2], neg); atomicAdd(&A.counters[3], neg);
+    }
+}
+
 // fixed-point sums of the launch -> float accumulators (and cleared for the next launch)
 __global__ void __launch_bounds__(256)
 fold_kernel(float4* __restrict__ accum, unsigned long long* __restrict__ accfix, size_t n) {
@@ -943,7 +1078,7 @@ static int launch_trace_t(mrtx_ctx* ctx, RenderArgs& A, unsigned s0, unsigned ns
     // (the hit-queue form also serves a scene without shadow rays: shade_kernel then adds the radiance itself)
     const bool queue = ctx->sp.shadow_queue >= 2u || (ctx->sp.shadow_queue != 0 && ctx->sp.shadows != 0);
     const size_t SQ_MAX = (size_t)1 << 26;                  // 64 Mi queued rays = 5 GiB; larger launches run in waves of pixels
-    int sq_blocks = 0, n_bounce = 0;
+    int sq_blocks = 0, sq_pool_blocks = 0, n_bounce = 0;
     A.depth = 0; A.n_bounce = 0;
     if (queue) {
         const size_t chunk = ns < 32u ? ns : 32u;
@@ -964,7 +1099,17 @@ static int launch_trace_t(mrtx_ctx* ctx, RenderArgs& A, unsigned s0, unsigned ns
         MRTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shadow_kernel<I16, false>, 128, 0));
         if (ctx->sp.blocks_per_sm && (int)ctx->sp.blocks_per_sm < per_sm) per_sm = (int)ctx->sp.blocks_per_sm;
         sq_blocks = ctx->sm_count * (per_sm < 1 ? 1 : per_sm);
+        if (ctx->sp.shadow_queue >= 4u && !ctx->sp.ceiling) {
+            MRTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shadow_kernel_pool<I16>, 128, 0));
+            if (ctx->sp.blocks_per_sm && (int)ctx->sp.blocks_per_sm < per_sm) per_sm = (int)ctx->sp.blocks_per_sm;
+            sq_pool_blocks = ctx->sm_count * (per_sm < 1 ? 1 : per_sm);
+        }
     }
+    // (shadow rays: the batched kernel with its straggler pool unless an engine switch asks for the streaming one)
+    auto launch_shadow = [&]() {
+        if (sq_pool_blocks) shadow_kernel_pool<I16><<<sq_pool_blocks, 128, 0, ctx->stream>>>(A);
+        else shadow_kernel<I16, false><<<sq_blocks, 128, 0, ctx->stream>>>(A);
+    };
     // chunks of <= 32 samples (one mask bit per sample in the deferred list); within a chunk, waves of pixels that the
     // shadow queue can hold; each followed by the referee over whatever was deferred, and the fold of the fixed-point sums
     for (unsigned done = 0; done < ns; done += 32u) {
@@ -1017,7 +1162,7 @@ static int launch_trace_t(mrtx_ctx* ctx, RenderArgs& A, unsigned s0, unsigned ns
                 else shade_kernel<I16, false, false><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(A);
             }
             if (first) prof_mark(ctx, 4);
-            if (queue) shadow_kernel<I16, false><<<sq_blocks, 128, 0, ctx->stream>>>(A);
+            if (queue) launch_shadow();
             // interreflection: bounce rays -> first hits -> shading (direct light weighted with the path's throughput, next
             // bounce) -> shadow rays, once per bounce; the two bounce queues swap roles
             for (int d = 1; d <= n_bounce; ++d) {
@@ -1030,7 +1175,7 @@ static int launch_trace_t(mrtx_ctx* ctx, RenderArgs& A, unsigned s0, unsigned ns
                 shadow_kernel<I16, true><<<sq_blocks, 128, 0, ctx->stream>>>(A);         // bounce_kernel: first hits -> hit queue
                 if (d < n_bounce) shade_kernel<I16, true, true><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(A);
                 else shade_kernel<I16, true, false><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(A);
-                shadow_kernel<I16, false><<<sq_blocks, 128, 0, ctx->stream>>>(A);
+                launch_shadow();
             }
             A.depth = 0;
             if (first) prof_mark(ctx, 5);

@@ -551,6 +551,7 @@ class B200OptiX:
         out = (C.c_double * 8)()
         with self._padlock:
             _lib.check(self._lib.mrtx_kernel_times(self._ctx, out, 1 if reset else 0))
+        # ("trace_kernel_fast" is the primary-ray kernel of the launch: trace_kernel_pool unless shadow_queue <= 2)
         names = ("cull_kernel", "beam_kernel", "trace_kernel_fast", "shadow_kernel", "trace_kernel_referee", "fold_kernel")
         d = {k: float(out[i]) for i, k in enumerate(names)}
         d["shade_kernel"] = float(out[7])

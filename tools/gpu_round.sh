@@ -8,7 +8,7 @@ python -c 'import __graft_entry__ as g; g.smoke()' 2>&1 | tail -1 | tee $out/${t
 timeout 1500 python bench.py > $out/${tag}_bench_n1.json 2> $out/${tag}_bench_n1.err; echo "bench rc=$?"; tail -2 $out/${tag}_bench_n1.err
 timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > $out/${tag}_reference_n1.json 2> $out/${tag}_reference_n1.err; echo "ref rc=$?"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $out/${tag}_launches.csv python bench.py --steps 2 --warmup 1 --skip-cpu --skip-e2e --skip-downscale > $out/${tag}_launches.log 2>&1
-timeout 1300 ncu --set full --import-source on --clock-control none -k regex:'trace_kernel_fast|shade_kernel|shadow_kernel' -s 6 -c 3 -o $out/${tag}_walk -f python tools/bench_trace.py cfg3 16 > $out/${tag}_ncu.log 2>&1
+timeout 1300 ncu --set full --import-source on --clock-control none -k regex:'trace_kernel_pool|shade_kernel|shadow_kernel' -s 6 -c 3 -o $out/${tag}_walk -f python tools/bench_trace.py cfg3 16 > $out/${tag}_ncu.log 2>&1
 timeout 600 ncu --set full --clock-control none -k regex:'downscale_vec_kernel|normalise_kernel' -s 6 -c 2 -o $out/${tag}_downscale -f python tools/bench_downscale.py > $out/${tag}_ncu_ds.log 2>&1
 python - "$tag" <<'PY'
 import json, sys
