@@ -76,7 +76,7 @@ int mrtx_create(int device, mrtx_ctx** out_ctx) {
     sp.light_pos[0] = 21460.0; sp.light_radius = 100.0; sp.light_radiance = 80.0 * 460.5316;
     sp.scene_epsilon = 1.0e-4;
     sp.exposure = 0.9f; sp.inv_gamma = 1.0f / 2.2f;
-    sp.jitter = 0; sp.shadows = 1; sp.debug_hits = 0; sp.kernel = 2; sp.beam = 0; sp.beam_drop = 2; sp.ceiling = 0; sp.shadow_queue = 3; sp.start_primary = 3; sp.start_shadow = 2; sp.long_walk = 2048u; sp.referee_budget = 500u; sp.hard_rays = 1u;
+    sp.jitter = 0; sp.shadows = 1; sp.debug_hits = 0; sp.kernel = 2; sp.beam = 0; sp.beam_drop = 2; sp.ceiling = 0; sp.shadow_queue = 4; sp.start_primary = 3; sp.start_shadow = 2; sp.long_walk = 2048u; sp.referee_budget = 500u; sp.hard_rays = 1u;
     const double eye[3] = {0, -300, 0}, tgt[3] = {0, 0, 0}, up[3] = {0, 0, 1};
     mrtx_set_camera(c, eye, tgt, up, 4.242192793);
     *out_ctx = c;

@@ -105,7 +105,8 @@ struct SceneParams {
     unsigned blocks_per_sm;                 // development: cap on resident blocks per SM of the two walk kernels (0 = what fits)
     unsigned hard_rays;                     // shadow rays too long for one referee warp are finished by the whole grid (default on)
     unsigned n_bounce;                      // diffuse interreflection bounces after the camera hit (path_seg_range max - 2; 0 = direct light)
-    unsigned shadow_queue;                  // 3 (default): as 2, primary rays by trace_kernel_pool (undecided rays parked in a per-warp pool);
+    unsigned shadow_queue;                  // 4 (default): as 3, shadow rays by shadow_kernel_pool (batches of 32 queue entries + straggler pool);
+                                            // 3: as 2, primary rays by trace_kernel_pool (undecided rays parked in a per-warp pool);
                                             // 2: primary hits -> hit queue -> shade_kernel -> shadow queue -> shadow_kernel;
                                             // 1: shading inside trace_kernel_fast, shadow rays through the queue; 0: everything inside trace_kernel_fast
     unsigned ceiling;                       // shadow rays: ceiling test from this level upwards (0 = off)

@@ -336,6 +336,9 @@ constexpr unsigned POOL_CAP = 64;                           // per warp: at most
 #ifndef MRTX_POOL_MINBLOCKS
 #define MRTX_POOL_MINBLOCKS MRTX_FAST_MINBLOCKS
 #endif
+#ifndef MRTX_POOL_CH
+#define MRTX_POOL_CH 1
+#endif
 #ifndef MRTX_POOL_T
 #define MRTX_POOL_T 8
 #endif
@@ -369,7 +372,7 @@ trace_kernel_pool(const __grid_constant__ RenderArgs A) {
     const unsigned rounds = (A.nsamples + (unsigned)g - 1u) >> gl;
     PoolRec* const pool = (PoolRec*)A.pool + (size_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * POOL_CAP;
     unsigned npool = 0;                                      // warp-uniform
-    unsigned task = 0, rd = rounds;                          // fresh batches: (task, round); rd == rounds: claim the next task
+    unsigned task = 0, rd = rounds, claimed = 0;             // fresh batches: (task, round); rd == rounds: claim the next task
     bool exhausted = false;
 
     Counters cnt = {0u, 0u, 0u};
@@ -380,8 +383,13 @@ trace_kernel_pool(const __grid_constant__ RenderArgs A) {
         // ---- the next batch: 32 parked rays if there are that many, else a fresh round of a task, else what is parked
         bool from_pool = npool >= 32u;
         if (!from_pool && !exhausted && rd >= rounds) {
-            if (lane == 0) task = atomicAdd(&A.work_counter[2], 1u);
-            task = __shfl_sync(FULL, task, 0);
+            // (tasks are claimed MRTX_POOL_CH at a time: a warp's pool then holds rays of neighbouring pixels)
+            if (!claimed) {
+                if (lane == 0) task = atomicAdd(&A.work_counter[2], (unsigned)MRTX_POOL_CH);
+                task = __shfl_sync(FULL, task, 0);
+                claimed = (unsigned)MRTX_POOL_CH;
+            } else ++task;
+            --claimed;
             if (task >= ntasks) exhausted = true; else rd = 0;
         }
         if (!from_pool && exhausted) {
@@ -826,9 +834,12 @@ shadow_kernel(const __grid_constant__ RenderArgs A) {
 struct SPoolRec { unsigned ridx; float s; int L, J, I, steps; unsigned pad0, pad1; };
 static_assert(sizeof(SPoolRec) == 32, "record layout");
 #ifndef MRTX_SPOOL_T
-#define MRTX_SPOOL_T 8
+#define MRTX_SPOOL_T 14
 #endif
-template <bool I16>
+#ifndef MRTX_SPOOL_CH
+#define MRTX_SPOOL_CH 1
+#endif
+template <bool I16, bool CLOSEST>
 __global__ void __launch_bounds__(128, MRTX_SQ_MINBLOCKS)
 shadow_kernel_pool(const __grid_constant__ RenderArgs A) {
     __shared__ unsigned s_off[3 * MRTX_MAX_LEVELS];
@@ -837,12 +848,14 @@ shadow_kernel_pool(const __grid_constant__ RenderArgs A) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
-    const unsigned n_items = A.work_counter[5];
-    unsigned* const queue = A.work_counter + 6;
+    const unsigned n_items = A.work_counter[CLOSEST ? 8 : 5];
+    unsigned* const queue = A.work_counter + (CLOSEST ? 9 : 6);
+    const RayRec* const q_rays = CLOSEST ? A.bq_in_rays : A.sq_rays;
+    const uint4* const q_aux = CLOSEST ? A.bq_in_aux : A.sq_aux;
     const float Rf = A.K.R;
     const int long_walk = (int)A.sp.long_walk;
     SPoolRec* const pool = (SPoolRec*)A.pool + (size_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * POOL_CAP;
-    unsigned npool = 0;                                      // warp-uniform
+    unsigned npool = 0, next = 0, claimed = 0;               // warp-uniform
     bool exhausted = false;
     Counters cnt = {0u, 0u, 0u};
     unsigned n_defer = 0, n_occluded = 0;
@@ -852,8 +865,13 @@ shadow_kernel_pool(const __grid_constant__ RenderArgs A) {
         bool from_pool = npool >= 32u;
         unsigned base = 0;
         if (!from_pool && !exhausted) {
-            if (lane == 0) base = atomicAdd(queue, 32u);
-            base = __shfl_sync(FULL, base, 0);
+            // (MRTX_SPOOL_CH batches are claimed at a time: a warp's pool then holds rays of neighbouring hits)
+            if (!claimed) {
+                if (lane == 0) next = atomicAdd(queue, 32u * (unsigned)MRTX_SPOOL_CH);
+                next = __shfl_sync(FULL, next, 0);
+                claimed = (unsigned)MRTX_SPOOL_CH;
+            }
+            base = next; next += 32u; --claimed;
             if (base >= n_items) exhausted = true;
         }
         if (!from_pool && exhausted) {
@@ -870,7 +888,7 @@ shadow_kernel_pool(const __grid_constant__ RenderArgs A) {
                 const uint4* q = (const uint4*)(pool + npool + lane);
                 const uint4 a = q[0], b = q[1];
                 ridx = a.x;
-                const RayRec* rec = A.sq_rays + ridx;
+                const RayRec* rec = q_rays + ridx;
                 const double2 tail = __ldg((const double2*)rec + 3);
                 Ray64 R;
                 load_ray_rec(rec, R);
@@ -882,7 +900,7 @@ shadow_kernel_pool(const __grid_constant__ RenderArgs A) {
         } else {
             const unsigned idx = base + (unsigned)lane;
             if (idx < n_items) {
-                const RayRec* rec = A.sq_rays + idx;
+                const RayRec* rec = q_rays + idx;
                 const double2 tail = __ldg((const double2*)rec + 3);
                 const unsigned cell = (unsigned)__double2hiint(tail.y);
                 Ray64 R;
@@ -912,12 +930,29 @@ shadow_kernel_pool(const __grid_constant__ RenderArgs A) {
         if (cand) {
             ++cnt.tests;
             Ray64 R;
-            load_ray_rec(A.sq_rays + ridx, R);
-            status = fast_test<I16>(A.hf, A.K, R, st.s_in, 0.0, st.s, sx, st.smax, P, true, fh);
+            load_ray_rec(q_rays + ridx, R);
+            status = fast_test<I16>(A.hf, A.K, R, st.s_in, 0.0, st.s, sx, st.smax, P, !CLOSEST, fh);
             if (!(status == FT_MISS && walk_advance(A.hf, st, sx, face))) alive = false;
         }
-        if (have && !alive) {
-            const uint4 aux = __ldg(A.sq_aux + ridx);
+        if (CLOSEST) {
+            // first hits of bounce rays -> hit queue (one reservation per warp and batch); an undecided bounce ray is dropped
+            const bool hitp = have && !alive && (status & 3) == FT_HIT;
+            const unsigned hm = __ballot_sync(FULL, hitp);
+            if (hm) {
+                unsigned hbase = 0;
+                if (lane == 0) hbase = atomicAdd(&A.work_counter[7], (unsigned)__popc(hm));
+                hbase = __shfl_sync(FULL, hbase, 0);
+                if (hitp) {
+                    const uint4 aux = __ldg(q_aux + ridx);
+                    uint4* q = (uint4*)(A.hq + hbase + (unsigned)__popc(hm & lt));
+                    __stcs(q, make_uint4((unsigned)__double2loint(fh.s), (unsigned)__double2hiint(fh.s), __float_as_uint(fh.fc), __float_as_uint(fh.fr)));
+                    __stcs(q + 1, make_uint4((unsigned)fh.r0, (unsigned)fh.c0, aux.w, ridx));
+                    __stcs(q + 2, make_uint4(__float_as_uint(fh.d00), __float_as_uint(fh.d01), __float_as_uint(fh.d10), __float_as_uint(fh.d11)));
+                }
+            }
+            if (have && !alive && (status & 3) == FT_DEFER) atomicAdd(&A.defer_stats[30], 1ull);
+        } else if (have && !alive) {
+            const uint4 aux = __ldg(q_aux + ridx);
             const uint32_t pixel = aux.w & 0x7ffffffu;
             if (status == FT_MISS) {
                 accfix_add(A.accfix, pixel, make_float3(__uint_as_float(aux.x), __uint_as_float(aux.y), __uint_as_float(aux.z)));
@@ -1100,14 +1135,14 @@ static int launch_trace_t(mrtx_ctx* ctx, RenderArgs& A, unsigned s0, unsigned ns
         if (ctx->sp.blocks_per_sm && (int)ctx->sp.blocks_per_sm < per_sm) per_sm = (int)ctx->sp.blocks_per_sm;
         sq_blocks = ctx->sm_count * (per_sm < 1 ? 1 : per_sm);
         if (ctx->sp.shadow_queue >= 4u && !ctx->sp.ceiling) {
-            MRTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shadow_kernel_pool<I16>, 128, 0));
+            MRTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shadow_kernel_pool<I16, false>, 128, 0));
             if (ctx->sp.blocks_per_sm && (int)ctx->sp.blocks_per_sm < per_sm) per_sm = (int)ctx->sp.blocks_per_sm;
             sq_pool_blocks = ctx->sm_count * (per_sm < 1 ? 1 : per_sm);
         }
     }
     // (shadow rays: the batched kernel with its straggler pool unless an engine switch asks for the streaming one)
     auto launch_shadow = [&]() {
-        if (sq_pool_blocks) shadow_kernel_pool<I16><<<sq_pool_blocks, 128, 0, ctx->stream>>>(A);
+        if (sq_pool_blocks) shadow_kernel_pool<I16, false><<<sq_pool_blocks, 128, 0, ctx->stream>>>(A);
         else shadow_kernel<I16, false><<<sq_blocks, 128, 0, ctx->stream>>>(A);
     };
     // chunks of <= 32 samples (one mask bit per sample in the deferred list); within a chunk, waves of pixels that the
@@ -1172,7 +1207,9 @@ static int launch_trace_t(mrtx_ctx* ctx, RenderArgs& A, unsigned s0, unsigned ns
                 void* in = ctx->bq_buf[(d - 1) & 1]; void* out = ctx->bq_buf[d & 1];
                 A.bq_in_rays = (RayRec*)in; A.bq_in_aux = (uint4*)((char*)in + ctx->bq_cap * sizeof(RayRec));
                 A.bq_out_rays = (RayRec*)out; A.bq_out_aux = (uint4*)((char*)out + ctx->bq_cap * sizeof(RayRec));
-                shadow_kernel<I16, true><<<sq_blocks, 128, 0, ctx->stream>>>(A);         // bounce_kernel: first hits -> hit queue
+                // bounce_kernel: first hits -> hit queue
+                if (sq_pool_blocks) shadow_kernel_pool<I16, true><<<sq_pool_blocks, 128, 0, ctx->stream>>>(A);
+                else shadow_kernel<I16, true><<<sq_blocks, 128, 0, ctx->stream>>>(A);
                 if (d < n_bounce) shade_kernel<I16, true, true><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(A);
                 else shade_kernel<I16, true, false><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(A);
                 launch_shadow();

@@ -363,12 +363,13 @@ def test_wavefront_pipeline_equals_filtered_kernel(spp):
         assert np.allclose(ha, hb, rtol=1e-12, atol=1e-12)
 
 
-@pytest.mark.parametrize("sq_mode", [2, 3])
+@pytest.mark.parametrize("sq_mode", [2, 3, 4])
 @pytest.mark.parametrize("spp,phase,shadows", [(1, 88.0, 1), (16, 90.0, 1), (24, 75.0, 1), (40, 60.0, 1), (6, 90.0, 0)])
 def test_hit_queue_and_shade_kernel_equal_in_kernel_shading(spp, phase, shadows, sq_mode):
     """The production cut of kernel 2 (shadow_queue = 2: trace_kernel_fast stops at the primary hit, which goes through the
-    hit queue to shade_kernel; that pushes the shadow ray; shadow_queue = 3, the default: the same with trace_kernel_pool,
-    whose warps park undecided rays in a pool and fill their hit-queue slots later) against shading inside trace_kernel_fast
+    hit queue to shade_kernel; that pushes the shadow ray; shadow_queue = 3: the same with trace_kernel_pool, whose warps
+    park undecided rays in a pool and fill their hit-queue slots later; shadow_queue = 4, the default: shadow rays too go
+    through a batched kernel with a straggler pool, shadow_kernel_pool) against shading inside trace_kernel_fast
     (shadow_queue = 1): the same rays, the same records, sums in fixed point either way - the frames are equal bit for bit.
     Sample counts that are no power of two leave empty slots in the hit queue (24 = 16 + 8 lanes of a second round; 40 = 32 + 8)."""
     elev, _ = synth_elevation(2880, 1440, seed=12)
@@ -401,7 +402,7 @@ def test_hit_queue_and_shade_kernel_equal_in_kernel_shading(spp, phase, shadows,
         assert np.array_equal(ha[..., 0] > 0, hb[..., 0] > 0) and np.allclose(ha, hb, rtol=1e-12, atol=1e-12)
 
 
-@pytest.mark.parametrize("sq_mode", [2, 3])
+@pytest.mark.parametrize("sq_mode", [2, 3, 4])
 def test_deferred_list_overflow_keeps_every_sample(sq_mode):
     """With long_walk of two steps nearly every ray goes to the referee; 8 samples per pixel in ONE launch make more
     per-sample entries than the deferred list holds (one per pixel of the frame).  What does not fit waits in the pixel's
