@@ -836,11 +836,14 @@ static_assert(sizeof(SPoolRec) == 32, "record layout");
 #ifndef MRTX_SPOOL_T
 #define MRTX_SPOOL_T 14
 #endif
+#ifndef MRTX_SPOOL_MINBLOCKS
+#define MRTX_SPOOL_MINBLOCKS MRTX_SQ_MINBLOCKS
+#endif
 #ifndef MRTX_SPOOL_CH
 #define MRTX_SPOOL_CH 1
 #endif
 template <bool I16, bool CLOSEST>
-__global__ void __launch_bounds__(128, MRTX_SQ_MINBLOCKS)
+__global__ void __launch_bounds__(128, MRTX_SPOOL_MINBLOCKS)
 shadow_kernel_pool(const __grid_constant__ RenderArgs A) {
     __shared__ unsigned s_off[3 * MRTX_MAX_LEVELS];
     if (threadIdx.x < 3 * MRTX_MAX_LEVELS) s_off[threadIdx.x] = A.hf.off[threadIdx.x];
