@@ -795,6 +795,9 @@ __device__ int referee_ray(const RenderArgs& A, RefIv* stack, const Ray64& R, do
 // publishes the ray, what it would add to the pixel and the intervals still pending; referee_hard_kernel then walks each
 // such ray with the whole grid - thousands of short pieces, each decided by the same float32 filter + float64 exact test.
 // Any crossing occludes, so the pieces need no order.
+#ifndef MRTX_REFEREE_CLOCK
+#define MRTX_REFEREE_CLOCK 0
+#endif
 #ifndef MRTX_HARD_ROUNDS
 #define MRTX_HARD_ROUNDS 1
 #endif
@@ -837,6 +840,10 @@ trace_kernel_referee(const __grid_constant__ RenderArgs A) {
         const unsigned packed = WAVE ? list_pixel(A, ent.x, n_limb) : ent.x;
         const int x = (int)(packed & 0xffffu), y = (int)(packed >> 16);
         const uint32_t pixel = (uint32_t)y * (uint32_t)A.width + (uint32_t)x;
+#if MRTX_REFEREE_CLOCK
+        const long long t_entry = clock64();
+        long long t_primary = 0;
+#endif
         float3 acc = make_float3(0.f, 0.f, 0.f);            // lane 0 sums the samples in order
         for (unsigned mask = WAVE ? 1u << ent.y : ent.y; mask; mask &= mask - 1u) {
             const unsigned sm = A.sample0 + (unsigned)(__ffs(mask) - 1);
@@ -847,6 +854,9 @@ trace_kernel_referee(const __grid_constant__ RenderArgs A) {
             TraceOut h;
             const int who = referee_ray<I16>(A, stack, R, 0.0, A.hf.top - 3, false, fast, fh, h, cnt, entered);
             if (lane == 0) { ++rs.primary; if (entered) ++rs.inside; }
+#if MRTX_REFEREE_CLOCK
+            t_primary = clock64() - t_entry;
+#endif
             if (who < 0) {
                 if (lane == 0) {
                     float3 tc;
@@ -903,6 +913,9 @@ trace_kernel_referee(const __grid_constant__ RenderArgs A) {
             }
             if (!occluded) { acc.x += lit.x; acc.y += lit.y; acc.z += lit.z; }
         }
+#if MRTX_REFEREE_CLOCK
+        if (lane == 0) printf("REF %u %u %lld %lld %lld\n", e, blockIdx.x, t_entry, t_primary, clock64() - t_entry);
+#endif
         if (lane == 0) {
             if (WAVE) {
                 float* slot = A.rad + ((size_t)(ent.x - A.wave_p0) * A.nsamples + ent.y) * 3;
