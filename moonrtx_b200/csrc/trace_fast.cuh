@@ -500,21 +500,21 @@ MRTX_HD inline int lvl_ny(const HeightField& hf, int L) { return (hf.H - 2 + (1 
 MRTX_HD inline bool walk_advance(const HeightField& hf, Walk& w, float sx, int face) {
     if (face == 4) return false;
     w.s = sx;
-    int L = w.L, J = w.J, I = w.I;
     // the index that moves, its step, and the boundary it crosses (the higher of the two cells' indices): the walk goes
-    // up a level where that boundary is also a boundary of the level above
+    // up a level where that boundary is also a boundary of the level above.  Written without branches: the lanes that leave
+    // through a longitude wall and those that leave through a latitude wall run these lines together (profiles/r08: the
+    // branched form ran at 3.8 - 9.8 of 32 lanes and was 13 % of shadow_kernel_pool's instructions).
+    const int L = w.L;
     const bool lon = face == 0;
     const int step = lon ? (w.east ? 1 : -1) : (face == 2 ? 1 : -1);
-    const int from = lon ? I : J;
-    const int to = from + step;
-    const bool up = ((step > 0 ? to : from) & 1) == 0;
-    if (lon) { const int nx = lvl_nx(hf, L); I = to >= nx ? 0 : (to < 0 ? nx - 1 : to); }
-    else {
-        J = to;
-        if (J < 0 || J >= lvl_ny(hf, L)) return false;       // cannot happen (caps have no wall); be safe
-    }
-    if (up && L < hf.top) { L += 1; I >>= 1; J >>= 1; }
-    w.L = L; w.J = J; w.I = I; w.vnext = NAN;
+    const int from = lon ? w.I : w.J, to = from + step;
+    const int nx = lvl_nx(hf, L);
+    int I = lon ? to : w.I;
+    const int J = lon ? w.J : to;
+    I = I >= nx ? 0 : (I < 0 ? nx - 1 : I);
+    if (J < 0 || J >= lvl_ny(hf, L)) return false;           // cannot happen (caps have no wall); be safe
+    const int sh = (max(from, to) & 1) == 0 && L < hf.top ? 1 : 0;
+    w.L = L + sh; w.J = J >> sh; w.I = I >> sh; w.vnext = NAN;
     return true;
 }
 
