@@ -545,11 +545,14 @@ trace_kernel_pool(const __grid_constant__ RenderArgs A) {
 // and the density cancel and the path's throughput is just multiplied by the albedo), pushed to the bounce queue; bounce_kernel
 // traces that queue to its first hits, which come back here with BOUNCE = true: ray and throughput are read from the bounce
 // ray's queue entry, the direct light at the new hit is weighted with the throughput and goes through the same shadow queue.
+#ifndef MRTX_SHADE_THREADS
+#define MRTX_SHADE_THREADS 256
+#endif
 #ifndef MRTX_SHADE_MINBLOCKS
 #define MRTX_SHADE_MINBLOCKS 2
 #endif
 template <bool I16, bool BOUNCE, bool SPAWN>
-__global__ void __launch_bounds__(256, MRTX_SHADE_MINBLOCKS)
+__global__ void __launch_bounds__(MRTX_SHADE_THREADS, MRTX_SHADE_MINBLOCKS)
 shade_kernel(const __grid_constant__ RenderArgs A) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -1196,8 +1199,8 @@ static int launch_trace_t(mrtx_ctx* ctx, RenderArgs& A, unsigned s0, unsigned ns
                 MRTX_CUDA(cudaMemsetAsync(A.work_counter + 8, 0, 3 * sizeof(unsigned), ctx->stream));
             }
             if (hitq) {
-                if (n_bounce) shade_kernel<I16, false, true><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(A);
-                else shade_kernel<I16, false, false><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(A);
+                if (n_bounce) shade_kernel<I16, false, true><<<ctx->sm_count * 8 * (256 / MRTX_SHADE_THREADS), MRTX_SHADE_THREADS, 0, ctx->stream>>>(A);
+                else shade_kernel<I16, false, false><<<ctx->sm_count * 8 * (256 / MRTX_SHADE_THREADS), MRTX_SHADE_THREADS, 0, ctx->stream>>>(A);
             }
             if (first) prof_mark(ctx, 4);
             if (queue) launch_shadow();
@@ -1213,8 +1216,8 @@ static int launch_trace_t(mrtx_ctx* ctx, RenderArgs& A, unsigned s0, unsigned ns
                 // bounce_kernel: first hits -> hit queue
                 if (sq_pool_blocks) shadow_kernel_pool<I16, true><<<sq_pool_blocks, 128, 0, ctx->stream>>>(A);
                 else shadow_kernel<I16, true><<<sq_blocks, 128, 0, ctx->stream>>>(A);
-                if (d < n_bounce) shade_kernel<I16, true, true><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(A);
-                else shade_kernel<I16, true, false><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(A);
+                if (d < n_bounce) shade_kernel<I16, true, true><<<ctx->sm_count * 8 * (256 / MRTX_SHADE_THREADS), MRTX_SHADE_THREADS, 0, ctx->stream>>>(A);
+                else shade_kernel<I16, true, false><<<ctx->sm_count * 8 * (256 / MRTX_SHADE_THREADS), MRTX_SHADE_THREADS, 0, ctx->stream>>>(A);
                 launch_shadow();
             }
             A.depth = 0;
