@@ -927,7 +927,7 @@ shadow_kernel_pool(const __grid_constant__ RenderArgs A) {
         const unsigned walk_min = exhausted ? 1u : (unsigned)MRTX_SPOOL_T;
         do {
             if (alive && !cand && st.steps <= long_walk) {
-                const int r = walk_step<I16>(A.hf, Rf, A.inv_rs, st, P, sx, face, cnt, nullptr, s_off);
+                const int r = walk_step<I16, false, MRTX_SQ_ASCEND>(A.hf, Rf, A.inv_rs, st, P, sx, face, cnt, nullptr, s_off);
                 if (r == TR_END) alive = false;
                 else if (r == TR_CANDIDATE) cand = true;
             }
