@@ -153,13 +153,17 @@ int  mrtx_set_camera(mrtx_ctx* ctx, const double eye[3], const double target[3],
 int  mrtx_set_light(mrtx_ctx* ctx, const double pos[3], double radius, double radiance);
 /* rt.set_float: scene_epsilon, tonemap_exposure, tonemap_gamma (marching_step,
  * marching_step_eps are accepted and ignored: intersection here is exact).
- * rt.set_uint: path_seg_range (accepted; direct light only), jitter, shadows.
+ * rt.set_uint: path_seg_range (2, 2 + n: n diffuse interreflection bounces after the camera hit), jitter, shadows.
  * Engine switches (not part of the PlotOptiX surface): debug_hits (float64 hit records for
  * tests), start_levels (a, b: pyramid levels the primary / shadow walks start at), long_walk (nodes
  * after which a walk is handed to the referee, default 2048), referee_budget (default 1500), and
  * kernel = 0 float64 one thread per pixel, 1 float64 persistent warps, 2 (default) filtered
  * float32 kernel + float64 referee, 3 the same arithmetic as a wavefront pipeline of dense
- * generation / streaming walk / dense shading kernels over ray records.   */
+ * generation / streaming walk / dense shading kernels over ray records;
+ * shadow_queue = 4 (default) kernel 2 as hit queue -> shade_kernel -> shadow queue with the batched
+ * pool kernels for primary and shadow rays, 3 / 2 / 1 / 0 its earlier forms (streaming shadow kernel;
+ * warp-bound primary kernel; shading in-kernel; everything in one kernel), kept for A/B tests: the
+ * same rays and decisions, frames equal bit for bit.                                     */
 int  mrtx_set_float(mrtx_ctx* ctx, const char* name, double value);
 int  mrtx_set_uint(mrtx_ctx* ctx, const char* name, unsigned a, unsigned b);
 /* frame size (TkOptiX(width=, height=)); reallocates accumulation / hit / output.     */
