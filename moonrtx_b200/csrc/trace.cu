@@ -333,6 +333,9 @@ trace_kernel_fast(const __grid_constant__ RenderArgs A) {
 struct PoolRec { double ox, oy, oz, dx, dy, dz, s_in; float smax, s; int L, J, I, steps; unsigned pix_k, slot, pad1, pad2; };
 static_assert(sizeof(PoolRec) == 96, "record layout");
 constexpr unsigned POOL_CAP = 64;                           // per warp: at most 31 parked + 32 parked again by a pool batch
+#ifndef MRTX_POOL_T2
+#define MRTX_POOL_T2 MRTX_POOL_T
+#endif
 #ifndef MRTX_POOL_MINBLOCKS
 #define MRTX_POOL_MINBLOCKS MRTX_FAST_MINBLOCKS
 #endif
@@ -452,7 +455,7 @@ trace_kernel_pool(const __grid_constant__ RenderArgs A) {
         bool cand = false;
         // (the walk phase ends when fewer than MRTX_POOL_T lanes are still walking: those rays are parked as they are and
         //  continue in a later batch with full lanes; while the pools are being emptied every ray walks to its end)
-        const unsigned walk_min = exhausted ? 1u : (unsigned)MRTX_POOL_T;
+        const unsigned walk_min = exhausted ? 1u : (unsigned)(from_pool ? MRTX_POOL_T2 : MRTX_POOL_T);
         const int long_walk = (int)A.sp.long_walk;          // (a ray still walking after that many nodes goes to the referee)
         do {
             if (alive && !cand && st.steps <= long_walk) {
@@ -839,6 +842,9 @@ static_assert(sizeof(SPoolRec) == 32, "record layout");
 #ifndef MRTX_SPOOL_T
 #define MRTX_SPOOL_T 14
 #endif
+#ifndef MRTX_SPOOL_T2
+#define MRTX_SPOOL_T2 MRTX_SPOOL_T                          // ... of a batch of parked rays
+#endif
 #ifndef MRTX_SPOOL_MINBLOCKS
 #define MRTX_SPOOL_MINBLOCKS MRTX_SQ_MINBLOCKS
 #endif
@@ -924,7 +930,7 @@ shadow_kernel_pool(const __grid_constant__ RenderArgs A) {
         float sx = 0.f;
         int face = 4, status = FT_MISS;
         bool cand = false;
-        const unsigned walk_min = exhausted ? 1u : (unsigned)MRTX_SPOOL_T;
+        const unsigned walk_min = exhausted ? 1u : (unsigned)(from_pool ? MRTX_SPOOL_T2 : MRTX_SPOOL_T);
         do {
             if (alive && !cand && st.steps <= long_walk) {
                 const int r = walk_step<I16, false, MRTX_SQ_ASCEND>(A.hf, Rf, A.inv_rs, st, P, sx, face, cnt, nullptr, s_off);
