@@ -7,8 +7,9 @@ from oracle import downscale_oracle as dorc
 from moonrtx_b200.synth import synth_ldem
 from helpers import make_oracle, sun_at_phase, DEFAULTS
 
-SO = "/tmp/libtrace_host.so"
+SO = os.path.join(ROOT, "tools", "_build", "libtrace_host.so")      # (git-ignored)
 def build():
+    os.makedirs(os.path.dirname(SO), exist_ok=True)
     subprocess.run(["nvcc", "-O2", "-Xcompiler", "-fPIC,-fopenmp,-ffp-contract=off", "-shared", "-o", SO,
                     os.path.join(ROOT, "tools", "trace_host.cu")], check=True, stderr=subprocess.PIPE)
     l = C.CDLL(SO)
