@@ -68,3 +68,24 @@ def sun_at_phase(phase_deg, bright_limb_deg=-90.0, dist=21460.0):
     """moon_renderer.py:723-725"""
     b, p = math.radians(bright_limb_deg), math.radians(phase_deg)
     return (-math.sin(b) * math.sin(p) * dist, -math.cos(p) * dist, math.cos(b) * math.sin(p) * dist)
+
+
+def penetration_texels(orc, x, y, s_root, texel, half_window_texels=2.0, n=81):
+    """How far below the oracle's surface the pixel-centre ray of (x, y) gets around parameter s_root, in texels.  A pixel on
+    which the GPU and the oracle disagree is a grazing case - a crest the ray touches: which side of a tangent root a ray
+    falls on is decided by the last bits of either implementation - only if this is below the tolerance."""
+    import math
+    s = orc.s
+    sx = ((x + 0.5) / s.img_w * 2.0 - 1.0) * s.tan_half_fov * s.img_w / s.img_h
+    sy = (1.0 - (y + 0.5) / s.img_h * 2.0) * s.tan_half_fov
+    d = np.array(s.w) + sx * np.array(s.right) + sy * np.array(s.up)
+    d /= np.linalg.norm(d)
+    Rm = np.array([list(s.ex), list(s.ey), list(s.ez)])
+    o_b, d_b = Rm @ (np.array(s.eye) - np.array(s.pos)), Rm @ d
+    worst = 0.0
+    for t in np.linspace(s_root - half_window_texels * texel, s_root + half_window_texels * texel, n):
+        p = o_b + t * d_b
+        r = np.linalg.norm(p)
+        lat, lon = math.degrees(math.asin(p[2] / r)), math.degrees(math.atan2(p[0], -p[1]))
+        worst = min(worst, r - s.radius * orc.displacement(lat, lon))
+    return -worst / texel

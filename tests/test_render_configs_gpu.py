@@ -13,7 +13,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import image_metrics, make_gpu, make_oracle
+from helpers import image_metrics, make_gpu, make_oracle, penetration_texels
 
 pytestmark = pytest.mark.gpu
 
@@ -45,24 +45,6 @@ def frame_kw(frame):
                 light_radius=st.light_radius, light_radiance=scene.light_radiance(80.0))
 
 
-def penetration_texels(orc, x, y, s_root, half_window_texels=2.0, n=81):
-    """How far below the oracle's surface the pixel-centre ray of (x, y) gets around parameter s_root, in texels."""
-    s = orc.s
-    sx = ((x + 0.5) / s.img_w * 2.0 - 1.0) * s.tan_half_fov * s.img_w / s.img_h
-    sy = (1.0 - (y + 0.5) / s.img_h * 2.0) * s.tan_half_fov
-    d = np.array(s.w) + sx * np.array(s.right) + sy * np.array(s.up)
-    d /= np.linalg.norm(d)
-    Rm = np.array([list(s.ex), list(s.ey), list(s.ez)])
-    o_b, d_b = Rm @ (np.array(s.eye) - np.array(s.pos)), Rm @ d
-    worst = 0.0
-    for t in np.linspace(s_root - half_window_texels * TEXEL, s_root + half_window_texels * TEXEL, n):
-        p = o_b + t * d_b
-        r = np.linalg.norm(p)
-        lat, lon = math.degrees(math.asin(p[2] / r)), math.degrees(math.atan2(p[0], -p[1]))
-        worst = min(worst, r - s.radius * orc.displacement(lat, lon))
-    return -worst / TEXEL
-
-
 def check_frame(full_map, img_w, img_h, stride, kw, spp=16, min_hits=500):
     src, counts, rs = full_map
     rt = make_gpu((src, MAP_W, MAP_H), img_w, img_h, scale=SCALE, radius_scale=rs, **kw)
@@ -78,7 +60,7 @@ def check_frame(full_map, img_w, img_h, stride, kw, spp=16, min_hits=500):
     suspects = np.argwhere((gh != oh) | (both & (dr > 1e-3)))
     for (j, i) in suspects:
         s_root = g[j, i, 0] if gh[j, i] else o[j, i, 0]
-        depth = penetration_texels(orc, int(i) * stride, int(j) * stride, float(s_root))
+        depth = penetration_texels(orc, int(i) * stride, int(j) * stride, float(s_root), TEXEL)
         assert depth < 1e-3, (f"pixel ({i * stride}, {j * stride}): gpu hit {bool(gh[j, i])} s={g[j, i, 0]:.9f}, oracle hit {bool(oh[j, i])} "
                               f"s={o[j, i, 0]:.9f}, the ray goes {depth:.3g} texel below the surface: not a grazing case")
     clean = both.copy()

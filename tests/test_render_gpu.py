@@ -8,7 +8,7 @@ import math
 import numpy as np
 import pytest
 
-from helpers import image_metrics, make_gpu, make_oracle, sun_at_phase
+from helpers import image_metrics, make_gpu, make_oracle, penetration_texels, sun_at_phase
 
 pytestmark = pytest.mark.gpu
 
@@ -22,28 +22,34 @@ def synth_elevation(W, H, seed=3, ds=1):
 
 
 def compare(rt, orc, stride=1, texel_tol=1e-3, allow_mismatch=0):
-    """Render both; returns metrics after asserting the hit-radius and image tolerances."""
+    """Render both; returns metrics after asserting the hit-radius and image tolerances.  There is no outlier allowance: a
+    pixel on which the two disagree (hit / miss, or hit radius beyond the tolerance) must be shown to be a grazing case -
+    the oracle's own surface function along that ray dips below zero by less than the tolerance (a crest the ray touches) -
+    and allow_mismatch only bounds how many such silhouette pixels a scene may have."""
     img = rt.render_cycle().copy()
     g = rt.get_hit_records_f64()[::stride, ::stride]
     o = orc.render(stride=stride)
     oh = o["hit64"]
     assert g.shape == oh.shape
     ghit, ohit = g[..., 0] > 0, oh[..., 0] > 0
-    mismatch = int((ghit != ohit).sum())
-    assert mismatch <= allow_mismatch, f"{mismatch} pixels disagree on hit/miss"
     both = ghit & ohit
     texel = 2.0 * math.pi * R / orc.s.W                       # scene units per texel at the equator
-    dr = np.abs(g[..., 1] - oh[..., 1])[both] / texel
+    dr = np.abs(g[..., 1] - oh[..., 1]) / texel
     ds_ = np.abs(g[..., 0] - oh[..., 0])[both] / texel
-    # silhouette pixels can legitimately land on a different ridge when the ray grazes a crest;
-    # they must be very few, everything else must be within tolerance
-    bad = int((dr > texel_tol).sum())
-    assert bad <= allow_mismatch, f"{bad} of {both.sum()} hits differ by more than {texel_tol} texel (max {dr.max():.3g})"
+    suspects = np.argwhere((ghit != ohit) | (both & (dr > texel_tol)))
+    assert len(suspects) <= allow_mismatch, f"{len(suspects)} pixels disagree on hit / miss or hit radius"
+    clean = both.copy()
+    for (j, i) in suspects:
+        s_root = g[j, i, 0] if ghit[j, i] else oh[j, i, 0]
+        depth = penetration_texels(orc, int(i) * stride, int(j) * stride, float(s_root), texel)
+        assert depth < texel_tol, (f"pixel ({i * stride}, {j * stride}): gpu hit {bool(ghit[j, i])} s={g[j, i, 0]:.9f}, oracle hit "
+                                   f"{bool(ohit[j, i])} s={oh[j, i, 0]:.9f}, the ray goes {depth:.3g} texel below the surface: not a grazing case")
+        clean[j, i] = False
     ref_img = orc.tonemap(o["accum"])
     mae, psnr = image_metrics(img[::stride, ::stride], ref_img)
     assert mae <= 1.0 and psnr >= 40.0, (mae, psnr)
-    return {"max_dr_texel": float(np.sort(dr)[-1 - bad] if len(dr) > bad else 0.0), "max_ds_texel": float(ds_.max()),
-            "mae": mae, "psnr": psnr, "hits": int(both.sum()), "img": img, "oracle": o}
+    return {"max_dr_texel": float(dr[clean].max()) if clean.any() else 0.0, "max_ds_texel": float(ds_.max()) if len(ds_) else 0.0,
+            "mae": mae, "psnr": psnr, "hits": int(both.sum()), "grazing_outliers": len(suspects), "img": img, "oracle": o}
 
 
 def test_flat_sphere_is_analytic():
