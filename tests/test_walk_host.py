@@ -113,3 +113,20 @@ def test_host_build_of_the_float64_walk_matches_the_oracle(host):
     texel = 2 * math.pi * R / 720
     ds = np.abs(ex[hit_e, 1] - orc[hit_o, 1]) / texel
     assert float(ds.max()) <= 1.0e-6
+
+
+def test_host_build_of_the_float32_walk_on_int16_texels_matches_the_oracle(host):
+    """The production form of the map: int16 LOLA counts decoded in the walk (height = 1 + count * SCALE, radius_scale as
+    data_loader.py:232-242 computes it at downscale 1), against the oracle reading the same counts."""
+    l, dp, df = host
+    W, H = 1440, 720
+    scale = float(np.float32(0.5 / 1737400.0))
+    d = relief(W, H, 9).astype(np.float64)
+    counts = np.round((d - 1.0) * 0.12 / scale).astype(np.int16)            # up to ~8 km of relief: inside the int16 range
+    counts -= counts.min() // 2                                              # heights on both sides of the datum
+    rs = float(np.float32(np.float32(np.float32(counts.max()) * np.float32(scale)) + np.float32(1)))
+    sc = OracleScene(counts, scale=scale, radius_scale=rs)
+    rays, _ = dp.camera_rays(128, 96, (0, -300, 0), (0, 0, 0), (0, 0, 1), 4.242192793)
+    fast = df.run_fast(l, counts, rays, scale=scale, rs=rs, start_level=-3)
+    orc = oracle_trace(sc, rays)
+    check("camera rays, int16 map", W, fast, orc, 0.02)
